@@ -1,0 +1,198 @@
+/*
+ * libjtdsp -- B200-native (sm_100a CUDA) replacement for the DSP that jivetalking
+ * delegates to embedded FFmpeg filter graphs.  C ABI: plain pointers and sizes only.
+ *
+ * The boundary is the reference's seam S4:
+ *     setupFilterGraph(decCtx, filterSpec)          internal/processor/frame_processor.go:164-216
+ *     runFilterGraph(ctx, reader, src, sink, cfg)   internal/processor/frame_processor.go:64-159
+ *     per-frame metadata dictionary                 internal/processor/analyser_metrics.go:432-483
+ *     loudnorm stats_file JSON                      internal/processor/normalise.go:64-75,143-165
+ * exposed as a whole-buffer batch call instead of 4096-sample frame pumping.
+ *
+ * Conventions (mirroring third_party/ffmpeg-statigo/functions.gen.go:5246-5257 WrapErr):
+ *   - every entry point returns 0 on success, a negative JT_ERR_* otherwise; a failing
+ *     call fails as a whole (never partial output);
+ *   - the caller owns every buffer; the library keeps no pointer past the call;
+ *   - a jt_ctx is single-threaded (one CUDA stream); distinct contexts may be used
+ *     concurrently from distinct threads (one per worker, cf. CloneForWorker,
+ *     internal/processor/filters.go:368-373);
+ *   - there is no CPU fallback: without a CUDA device jt_create fails with JT_ERR_CUDA.
+ */
+#ifndef JTDSP_H
+#define JTDSP_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JT_OK                 0
+#define JT_ERR_INVALID_ARG   (-1)
+#define JT_ERR_CUDA          (-2)
+#define JT_ERR_NOMEM         (-3)
+#define JT_ERR_SPEC          (-4)   /* filter spec string could not be parsed           */
+#define JT_ERR_UNSUPPORTED   (-5)   /* valid FFmpeg, but outside the hot path built here */
+#define JT_ERR_CANCELLED     (-6)   /* jt_cancel() seen (ctx.Err(), frame_processor.go:116) */
+#define JT_ERR_BUFFER        (-7)   /* caller buffer too small                           */
+
+/* AVSampleFormat values (third_party/ffmpeg-statigo/include/libavutil/samplefmt.h) */
+#define JT_FMT_S16 1
+#define JT_FMT_S32 2
+#define JT_FMT_FLT 3
+#define JT_FMT_DBL 4
+
+typedef struct jt_ctx jt_ctx;
+
+int         jt_version(void);
+int         jt_create(int device, jt_ctx **out);
+void        jt_destroy(jt_ctx *ctx);
+const char *jt_strerror(int code);
+const char *jt_last_error(const jt_ctx *ctx);      /* detail of the last failure on this ctx */
+void        jt_cancel(jt_ctx *ctx);                 /* async-signal-safe flag, polled between launches */
+
+/* ---- the a3 wire (analyser_metrics.go:432-483) as doubles, NaN = key absent ---------- */
+enum {  /* lavfi.astats.1.<key>, order of analyser_metrics.go:448-469 */
+    JT_AS_Dynamic_range = 0, JT_AS_RMS_level, JT_AS_Peak_level, JT_AS_RMS_trough, JT_AS_RMS_peak,
+    JT_AS_DC_offset, JT_AS_Flat_factor, JT_AS_Crest_factor, JT_AS_Zero_crossings_rate,
+    JT_AS_Zero_crossings, JT_AS_Max_difference, JT_AS_Min_difference, JT_AS_Mean_difference,
+    JT_AS_RMS_difference, JT_AS_Entropy, JT_AS_Min_level, JT_AS_Max_level, JT_AS_Noise_floor,
+    JT_AS_Noise_floor_count, JT_AS_Bit_depth, JT_AS_Number_of_samples,
+    JT_AS_COUNT
+};
+enum {  /* lavfi.aspectralstats.1.<key>, order of analyser_metrics.go:433-445 */
+    JT_SP_mean = 0, JT_SP_variance, JT_SP_centroid, JT_SP_spread, JT_SP_skewness, JT_SP_kurtosis,
+    JT_SP_entropy, JT_SP_flatness, JT_SP_crest, JT_SP_flux, JT_SP_slope, JT_SP_decrease, JT_SP_rolloff,
+    JT_SP_COUNT
+};
+
+/* One record per frame the reference would pull from the buffersink.  Values are what
+ * strconv.ParseFloat would read back from the metadata strings, i.e. already rounded the
+ * way FFmpeg prints them ("%.3f" for lavfi.r128.*, "%f" for astats, "%g" for
+ * aspectralstats).  astats values are cumulative (reset=0): the reference keeps only the
+ * latest (analyser_metrics.go:485-487), so they are materialised on the LAST record only. */
+typedef struct jt_frame_meta {
+    int64_t first_sample;          /* index of the frame's first sample on the sink link */
+    int32_t nb_samples;
+    int32_t reserved;
+    double  r128_M, r128_S, r128_I, r128_LRA, r128_LRA_low, r128_LRA_high;
+    double  r128_true_peak, r128_sample_peak;     /* linear, max over channels            */
+    double  astats[JT_AS_COUNT];                   /* lavfi.astats.1.*                      */
+    double  astats_overall_RMS_level, astats_overall_Peak_level;  /* lavfi.astats.Overall.* */
+    double  spectral[JT_SP_COUNT];                 /* lavfi.aspectralstats.1.*              */
+} jt_frame_meta;
+
+/* loudnorm print_format=json fields (LoudnormStats, normalise.go:64-75) as numbers;
+ * jt_loudnorm_stats_json() renders the exact text FFmpeg writes to stats_file. */
+typedef struct jt_loudnorm_stats {
+    double input_i, input_tp, input_lra, input_thresh;
+    double output_i, output_tp, output_lra, output_thresh;
+    double target_offset;
+    int32_t normalization_type;    /* 0 = "linear", 1 = "dynamic" */
+    int32_t valid;                 /* 0 when the spec held no loudnorm filter */
+} jt_loudnorm_stats;
+int jt_loudnorm_stats_json(const jt_loudnorm_stats *st, char *buf, size_t cap);
+
+/* ---- S4: run one filter graph over one whole (decoded) stream --------------------------
+ * filter_spec : the exact string the reference builds (BuildFilterSpec filters.go:968-989,
+ *               measureWithLoudnorm normalise.go:257-264, buildLoudnormFilterSpec
+ *               normalise.go:1231-1334, analyser_bands.go:33, analyser_output.go:18).
+ * pcm_in      : interleaved samples, n_frames * channels, sample_fmt = JT_FMT_*.
+ * frame_size  : decoder frame size to emulate for metadata cadence (4096 for WAV/FLAC,
+ *               processor.go:272-275); <= 0 selects 4096.
+ * pcm_out     : receives the sink stream (may be NULL with cap 0 for measure-only graphs);
+ *               *out_fmt / *out_rate describe it.
+ * meta        : receives up to meta_cap sink-frame records; *n_meta = records the graph
+ *               produced (call fails with JT_ERR_BUFFER if meta != NULL and cap is short).
+ * ln_stats    : loudnorm JSON fields when the spec contains loudnorm, else valid = 0.
+ * The *_dev variant takes DEVICE pointers for pcm_in / pcm_out (already resident in HBM).
+ */
+int jt_run_graph(jt_ctx *ctx, const char *filter_spec,
+                 const void *pcm_in, int64_t n_frames, int sample_rate, int channels, int sample_fmt,
+                 int frame_size,
+                 void *pcm_out, int64_t pcm_out_cap_frames, int64_t *n_out, int *out_rate, int *out_fmt,
+                 jt_frame_meta *meta, int64_t meta_cap, int64_t *n_meta,
+                 jt_loudnorm_stats *ln_stats);
+int jt_run_graph_dev(jt_ctx *ctx, const char *filter_spec,
+                 const void *d_pcm_in, int64_t n_frames, int sample_rate, int channels, int sample_fmt,
+                 int frame_size,
+                 void *d_pcm_out, int64_t pcm_out_cap_frames, int64_t *n_out, int *out_rate, int *out_fmt,
+                 jt_frame_meta *meta, int64_t meta_cap, int64_t *n_meta,
+                 jt_loudnorm_stats *ln_stats);
+/* upper bound on sink frames / records for sizing caller buffers */
+int64_t jt_graph_max_out_frames(const char *filter_spec, int64_t n_frames, int sample_rate);
+int64_t jt_graph_max_meta(const char *filter_spec, int64_t n_frames, int sample_rate, int frame_size);
+
+/* ---- accumulated Pass-1 result (metadataAccumulators + []IntervalSample,
+ *      analyser_metrics.go:17-32,488-621; collectAnalysisFrames analyser.go:538-650) ----- */
+typedef struct jt_interval {
+    double timestamp_s;
+    double rms_level, peak_level;                 /* dBFS from raw input frames (a2)       */
+    double spectral[JT_SP_COUNT];
+    int32_t spectral_found, frame_count;
+    double momentary_lufs, short_term_lufs, true_peak, sample_peak;   /* dB */
+} jt_interval;
+
+typedef struct jt_measurements {
+    double input_i, input_tp, input_sp, input_lra, last_m, last_s;    /* LUFS / dB */
+    double astats[JT_AS_COUNT];
+    double spectral_mean[JT_SP_COUNT];            /* mean over sink frames with keys found */
+    int64_t spectral_frames, sink_frames;
+    double duration_s;
+} jt_measurements;
+
+/* Pass 1 (collectAnalysisFrames): spec = Pass1FilterOrder (filters.go:42-45). */
+int jt_analyse(jt_ctx *ctx, const void *pcm_in, int64_t n_frames, int sample_rate, int channels,
+               int sample_fmt, int frame_size,
+               jt_measurements *out, jt_interval *intervals, int64_t interval_cap, int64_t *n_intervals);
+
+/* 17-band region RMS (measureSpeechBandRMS analyser_bands.go:33-104): n_bands (lo,hi) pairs
+ * over region [start_s, start_s+duration_s); rms_db[i] = lavfi.astats.Overall.RMS_level,
+ * found[i] = 0 when the reference would have seen no metadata. */
+int jt_band_rms(jt_ctx *ctx, const void *pcm_in, int64_t n_frames, int sample_rate, int channels,
+                int sample_fmt, double start_s, double duration_s,
+                const double *lo_hz, const double *hi_hz, int n_bands, double *rms_db, int32_t *found);
+
+/* Output of the full four-pass chain (ProcessAudio processor.go:78-216). */
+typedef struct jt_process_result {
+    jt_measurements input;            /* Pass 1                                            */
+    jt_measurements filtered;         /* Pass 2 output analysis                            */
+    jt_measurements final;            /* Pass 4 output analysis                            */
+    jt_loudnorm_stats pass3, pass4;   /* loudnorm JSON of Pass 3 and Pass 4                */
+    double limiter_ceiling_db, limiter_pregain_db, gain_db, effective_target_i;
+    int32_t limiter_needed, limiter_clamped, linear_possible, reserved;
+    int64_t n_out;                    /* s16 mono 44.1 kHz samples written                 */
+} jt_process_result;
+
+/* pass2_spec: Pass-2 spec string from the reference's AdaptConfig+BuildFilterSpec
+ * (adaptive.go:13-40); NULL selects DefaultFilterConfig()'s spec (filters.go:353-355).
+ * pcm_out: int16 mono 44.1 kHz, 4096-sample frames (processor.go:379-384). */
+int jt_process_audio(jt_ctx *ctx, const void *pcm_in, int64_t n_frames, int sample_rate, int channels,
+                     int sample_fmt, const char *pass2_spec,
+                     int16_t *pcm_out, int64_t pcm_out_cap, jt_process_result *res);
+int jt_process_audio_dev(jt_ctx *ctx, const void *d_pcm_in, int64_t n_frames, int sample_rate, int channels,
+                     int sample_fmt, const char *pass2_spec,
+                     int16_t *d_pcm_out, int64_t pcm_out_cap, jt_process_result *res);
+
+/* Host-side planners of Pass 3/4 (a9: normalise.go:373-392,407-425,539-561,583-585,611-632,
+ * 1198-1203) and the spec builders, exported so callers and tests see the same strings. */
+int jt_build_pass3_spec(double output_i, double output_tp, double target_i, double target_tp, double target_lra,
+                        char *buf, size_t cap, jt_process_result *plan_out);
+int jt_build_pass4_spec(const jt_process_result *plan, const jt_loudnorm_stats *pass3,
+                        double target_i, double target_tp, double target_lra, int source_rate,
+                        char *buf, size_t cap, double *effective_target_i, double *offset_db);
+int jt_default_pass2_spec(char *buf, size_t cap);
+int jt_pass1_spec(char *buf, size_t cap);
+
+/* kernel launches since jt_create / since the last reset (bench.py's gpu_launches) */
+int64_t jt_launch_count(const jt_ctx *ctx);
+void    jt_reset_launch_count(jt_ctx *ctx);
+/* device time (ms) of the dominant kernel group accumulated by CUDA events when
+ * jt_enable_kernel_timing(ctx, 1) is set; name of slot i or NULL past the end */
+void        jt_enable_kernel_timing(jt_ctx *ctx, int on);
+const char *jt_kernel_timing(const jt_ctx *ctx, int slot, double *ms, int64_t *launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

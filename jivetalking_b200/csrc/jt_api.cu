@@ -1,0 +1,513 @@
+// extern "C" entry points (include/jtdsp.h) + the host-side accumulation the reference does
+// in Go around its frame pump (collectAnalysisFrames analyser.go:538-650,
+// extractFrameMetadata / extractOutputFrameMetadata analyser_metrics.go:784-924,
+// ApplyNormalisation normalise.go:722-905) restated in C++ above the kernels.
+#include "jt_graph.h"
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <climits>
+
+// ---------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------
+extern "C" int jt_version(void) { return 100; }
+
+extern "C" const char *jt_strerror(int code)
+{
+    switch (code) {
+    case JT_OK: return "success";
+    case JT_ERR_INVALID_ARG: return "invalid argument";
+    case JT_ERR_CUDA: return "CUDA error (no usable sm_100a device, or a kernel failed)";
+    case JT_ERR_NOMEM: return "out of device memory";
+    case JT_ERR_SPEC: return "filter spec could not be parsed";
+    case JT_ERR_UNSUPPORTED: return "filter or option outside the implemented hot path";
+    case JT_ERR_CANCELLED: return "cancelled";
+    case JT_ERR_BUFFER: return "caller buffer too small";
+    }
+    return "unknown error";
+}
+
+extern "C" int jt_create(int device, jt_ctx **out)
+{
+    if (!out) return JT_ERR_INVALID_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return JT_ERR_CUDA;     // no CPU fallback
+    if (device < 0 || device >= ndev) return JT_ERR_INVALID_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return JT_ERR_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return JT_ERR_CUDA;
+    if (prop.major < 10) return JT_ERR_CUDA;                                           // built for sm_100a only
+    jt_ctx *c = new jt_ctx();
+    c->device = device; c->num_sms = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return JT_ERR_CUDA; }
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    *out = c;
+    return JT_OK;
+}
+
+extern "C" void jt_destroy(jt_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    jt_release_all(c);
+    jt_flush_timing(c);
+    if (c->pin_in) cudaFreeHost(c->pin_in);
+    if (c->pin_out) cudaFreeHost(c->pin_out);
+    if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+    delete c;
+}
+
+extern "C" const char *jt_last_error(const jt_ctx *c) { return c ? c->last_error.c_str() : ""; }
+extern "C" void jt_cancel(jt_ctx *c) { if (c) c->cancel.store(1); }
+extern "C" int64_t jt_launch_count(const jt_ctx *c) { return c ? c->launches : 0; }
+extern "C" void jt_reset_launch_count(jt_ctx *c) { if (c) { c->launches = 0; jt_flush_timing(c); for (auto &s : c->slots) { s.ms = 0; s.launches = 0; } } }
+extern "C" void jt_enable_kernel_timing(jt_ctx *c, int on) { if (c) c->timing = on != 0; }
+extern "C" const char *jt_kernel_timing(const jt_ctx *cc, int slot, double *ms, int64_t *launches)
+{
+    jt_ctx *c = const_cast<jt_ctx *>(cc);
+    if (!c) return nullptr;
+    jt_flush_timing(c);
+    if (slot < 0 || slot >= (int)c->slots.size()) return nullptr;
+    if (ms) *ms = c->slots[slot].ms;
+    if (launches) *launches = c->slots[slot].launches;
+    return c->slots[slot].name.c_str();
+}
+
+// run `body`, translate exceptions into codes, always release per-call device memory
+template <class F> static int guarded(jt_ctx *c, F body)
+{
+    if (!c) return JT_ERR_INVALID_ARG;
+    int rc = JT_OK;
+    c->cancel.store(0);
+    cudaSetDevice(c->device);
+    try { body(); }
+    catch (const JtError &e) { rc = e.code; c->last_error = e.msg; }
+    catch (const std::bad_alloc &) { rc = JT_ERR_NOMEM; c->last_error = "host allocation failed"; }
+    jt_release_all(c);
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (rc == JT_OK && e != cudaSuccess) { rc = JT_ERR_CUDA; c->last_error = cudaGetErrorString(e); }
+    cudaError_t e2 = cudaGetLastError();
+    if (rc == JT_OK && e2 != cudaSuccess) { rc = JT_ERR_CUDA; c->last_error = cudaGetErrorString(e2); }
+    return rc;
+}
+
+static void *pinned(jt_ctx *c, void **slot, size_t *cap, size_t bytes)
+{
+    if (*cap < bytes) {
+        if (*slot) cudaFreeHost(*slot);
+        *slot = nullptr; *cap = 0;
+        if (cudaHostAlloc(slot, bytes, cudaHostAllocDefault) != cudaSuccess) JT_THROW(JT_ERR_NOMEM, "cudaHostAlloc(%zu)", bytes);
+        *cap = bytes;
+    }
+    return *slot;
+}
+
+// host -> device upload of the caller's PCM.  Pageable caller memory is staged through a
+// ctx-owned pinned buffer in chunks so the copy engine runs at full PCIe rate.
+static void *upload(jt_ctx *c, const void *h, size_t bytes)
+{
+    void *d = jt_dalloc_bytes(c, bytes);
+    if (!bytes) return d;
+    cudaPointerAttributes at;
+    bool is_pinned = cudaPointerGetAttributes(&at, h) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (is_pinned) { JT_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, c->stream)); return d; }
+    const size_t chunk = 32u << 20;
+    char *stage = (char *)pinned(c, &c->pin_in, &c->pin_in_bytes, 2 * chunk);
+    cudaEvent_t ev[2]; cudaEventCreate(&ev[0]); cudaEventCreate(&ev[1]);
+    size_t off = 0; int k = 0;
+    while (off < bytes) {
+        const size_t m = std::min(chunk, bytes - off);
+        cudaEventSynchronize(ev[k]);
+        memcpy(stage + k * chunk, (const char *)h + off, m);
+        cudaMemcpyAsync((char *)d + off, stage + k * chunk, m, cudaMemcpyHostToDevice, c->stream);
+        cudaEventRecord(ev[k], c->stream);
+        off += m; k ^= 1;
+    }
+    cudaEventSynchronize(ev[0]); cudaEventSynchronize(ev[1]);
+    cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]);
+    JT_CUDA(cudaGetLastError());
+    return d;
+}
+
+static void download(jt_ctx *c, void *h, const void *d, size_t bytes)
+{
+    if (!bytes) return;
+    JT_CUDA(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, c->stream));
+    JT_CUDA(cudaStreamSynchronize(c->stream));
+}
+
+extern "C" int jt_loudnorm_stats_json(const jt_loudnorm_stats *s, char *buf, size_t cap)
+{
+    if (!s || !buf) return JT_ERR_INVALID_ARG;
+    int n = snprintf(buf, cap,
+        "\n{\n\t\"input_i\" : \"%.2f\",\n\t\"input_tp\" : \"%.2f\",\n\t\"input_lra\" : \"%.2f\",\n\t\"input_thresh\" : \"%.2f\",\n"
+        "\t\"output_i\" : \"%.2f\",\n\t\"output_tp\" : \"%+.2f\",\n\t\"output_lra\" : \"%.2f\",\n\t\"output_thresh\" : \"%.2f\",\n"
+        "\t\"normalization_type\" : \"%s\",\n\t\"target_offset\" : \"%.2f\"\n}\n",
+        s->input_i, s->input_tp, s->input_lra, s->input_thresh, s->output_i, s->output_tp, s->output_lra, s->output_thresh,
+        s->normalization_type == 0 ? "linear" : "dynamic", s->target_offset);
+    return (n < 0 || (size_t)n >= cap) ? JT_ERR_BUFFER : JT_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// S4
+// ---------------------------------------------------------------------------------------
+static int run_graph_common(jt_ctx *c, const char *spec, const void *pcm_in, bool in_on_device, int64_t n_frames, int rate,
+                            int channels, int fmt, int frame_size, void *pcm_out, bool out_on_device, int64_t cap,
+                            int64_t *n_out, int *out_rate, int *out_fmt, jt_frame_meta *meta, int64_t meta_cap,
+                            int64_t *n_meta, jt_loudnorm_stats *ln)
+{
+    return guarded(c, [&]() {
+        if (!spec || (!pcm_in && n_frames > 0)) JT_THROW(JT_ERR_INVALID_ARG, "null spec or input");
+        if (fmt != JT_FMT_S16 && fmt != JT_FMT_FLT && fmt != JT_FMT_DBL) JT_THROW(JT_ERR_UNSUPPORTED, "input sample format %d", fmt);
+        const size_t in_bytes = (size_t)n_frames * channels * jt_fmt_bytes(fmt);
+        const void *d_in = in_on_device ? pcm_in : upload(c, pcm_in, in_bytes);
+        GraphResult g;
+        jt_graph_run(c, spec, d_in, n_frames, rate, channels, fmt, frame_size, pcm_out != nullptr, meta != nullptr || n_meta != nullptr, g);
+        if (n_out) *n_out = g.out.n;
+        if (out_rate) *out_rate = g.out.rate;
+        if (out_fmt) *out_fmt = g.out.fmt;
+        if (pcm_out) {
+            if (g.out.n > cap) JT_THROW(JT_ERR_BUFFER, "pcm_out holds %lld frames, graph produced %lld", (long long)cap, (long long)g.out.n);
+            const size_t ob = (size_t)g.out.n * jt_fmt_bytes(g.out.fmt);
+            if (out_on_device) { if (ob) JT_CUDA(cudaMemcpyAsync(pcm_out, g.out.d, ob, cudaMemcpyDeviceToDevice, c->stream)); }
+            else download(c, pcm_out, g.out.d, ob);
+        }
+        if (n_meta) *n_meta = (int64_t)g.meta.size();
+        if (meta) {
+            if ((int64_t)g.meta.size() > meta_cap) JT_THROW(JT_ERR_BUFFER, "meta holds %lld records, graph produced %zu", (long long)meta_cap, g.meta.size());
+            if (!g.meta.empty()) memcpy(meta, g.meta.data(), g.meta.size() * sizeof(jt_frame_meta));
+        }
+        if (ln) *ln = g.ln;
+    });
+}
+
+extern "C" int jt_run_graph(jt_ctx *c, const char *spec, const void *pcm_in, int64_t n_frames, int rate, int channels, int fmt,
+                            int frame_size, void *pcm_out, int64_t cap, int64_t *n_out, int *out_rate, int *out_fmt,
+                            jt_frame_meta *meta, int64_t meta_cap, int64_t *n_meta, jt_loudnorm_stats *ln)
+{
+    return run_graph_common(c, spec, pcm_in, false, n_frames, rate, channels, fmt, frame_size, pcm_out, false, cap, n_out, out_rate, out_fmt, meta, meta_cap, n_meta, ln);
+}
+extern "C" int jt_run_graph_dev(jt_ctx *c, const char *spec, const void *d_in, int64_t n_frames, int rate, int channels, int fmt,
+                            int frame_size, void *d_out, int64_t cap, int64_t *n_out, int *out_rate, int *out_fmt,
+                            jt_frame_meta *meta, int64_t meta_cap, int64_t *n_meta, jt_loudnorm_stats *ln)
+{
+    return run_graph_common(c, spec, d_in, true, n_frames, rate, channels, fmt, frame_size, d_out, true, cap, n_out, out_rate, out_fmt, meta, meta_cap, n_meta, ln);
+}
+
+static int spec_out_rate(const char *spec, int rate)
+{
+    try {
+        for (const FilterNode &f : jt_parse_spec(spec ? spec : "")) {
+            if (f.name == "aformat") rate = (int)f.num("sample_rates", "r", rate);
+            else if (f.name == "aresample") { if (const std::string *p = f.get("")) rate = atoi(p->c_str()); }
+        }
+    } catch (const JtError &) {}
+    return rate;
+}
+extern "C" int64_t jt_graph_max_out_frames(const char *spec, int64_t n_frames, int rate)
+{
+    const int orate = spec_out_rate(spec, rate);
+    return (int64_t)((double)n_frames * orate / rate) + 2 * 4096 + 1024;
+}
+extern "C" int64_t jt_graph_max_meta(const char *spec, int64_t n_frames, int rate, int frame_size)
+{
+    (void)spec;
+    if (frame_size <= 0) frame_size = 4096;
+    const int64_t by_tick = n_frames / std::max(rate / 10, 1) + 4;
+    const int64_t by_frame = n_frames / std::min(frame_size, 512) + 4;     // finest framing any filter of the path emits (afftdn rate/80, anlmdn 2K+1)
+    return std::max(by_tick, by_frame);
+}
+
+// ---------------------------------------------------------------------------------------
+// measurement accumulation (latest-wins / averages), shared by Pass 1, 2 and 4
+// ---------------------------------------------------------------------------------------
+static double ratio_db(double r) { return r <= 0 ? -120.0 : 20 * log10(r); }
+
+struct MeasAcc {
+    jt_measurements m; double spec_sum[JT_SP_COUNT];
+    MeasAcc() { memset(&m, 0, sizeof(m)); for (double &s : spec_sum) s = 0; for (double &a : m.astats) a = NAN; }
+    void add(const jt_frame_meta &f) {
+        bool sf = false;
+        for (int k = 0; k < JT_SP_COUNT; k++) if (!std::isnan(f.spectral[k])) sf = true;
+        if (sf) { for (int k = 0; k < JT_SP_COUNT; k++) spec_sum[k] += std::isnan(f.spectral[k]) ? 0 : f.spectral[k]; m.spectral_frames++; }
+        for (int k = 0; k < JT_AS_COUNT; k++) if (!std::isnan(f.astats[k])) m.astats[k] = f.astats[k];
+        if (!std::isnan(f.r128_I)) m.input_i = f.r128_I;
+        if (!std::isnan(f.r128_M)) m.last_m = f.r128_M;
+        if (!std::isnan(f.r128_S)) m.last_s = f.r128_S;
+        if (!std::isnan(f.r128_true_peak)) m.input_tp = ratio_db(f.r128_true_peak);
+        if (!std::isnan(f.r128_sample_peak)) m.input_sp = ratio_db(f.r128_sample_peak);
+        if (!std::isnan(f.r128_LRA)) m.input_lra = f.r128_LRA;
+        m.sink_frames++;
+    }
+    void finish(double duration_s) {
+        for (int k = 0; k < JT_SP_COUNT; k++) m.spectral_mean[k] = m.spectral_frames ? spec_sum[k] / m.spectral_frames : 0.0;
+        m.duration_s = duration_s;
+    }
+};
+
+static const char *PASS1_SPEC =
+    "aformat=channel_layouts=mono,astats=metadata=1:measure_perchannel=all,"
+    "aspectralstats=win_size=2048:win_func=hann:measure=all,"
+    "ebur128=metadata=1:peak=sample+true:dualmono=true:target=-16";
+static const char *PASS2_DEFAULT_SPEC =
+    "aformat=channel_layouts=mono,"
+    "highpass=f=80:poles=2:width_type=q:width=0.707:normalize=1:a=tdii,"
+    "lowpass=f=20500:poles=2:width_type=q:width=0.707:normalize=1:a=tdii,"
+    "anlmdn=s=0.00001:p=0.0060:r=0.0020:m=3,afftdn=nr=12:nt=w:tn=1,"
+    "agate=threshold=0.010000:ratio=2.0:attack=5.00:release=200:range=0.1995:knee=3.0:detection=rms:makeup=1.0,"
+    "acompressor=threshold=0.125893:ratio=3.0:attack=10:release=200:makeup=1.00:knee=4.0:detection=rms:mix=1.00,"
+    "astats=metadata=1:measure_perchannel=all,aspectralstats=win_size=2048:win_func=hann:measure=all,"
+    "ebur128=metadata=1:peak=sample+true:dualmono=true:target=-16,"
+    "aformat=sample_rates=44100:channel_layouts=mono:sample_fmts=s16,asetnsamples=n=4096";
+
+static int copy_str(const char *s, char *buf, size_t cap)
+{
+    if (!buf || strlen(s) + 1 > cap) return JT_ERR_BUFFER;
+    strcpy(buf, s); return JT_OK;
+}
+extern "C" int jt_pass1_spec(char *buf, size_t cap) { return copy_str(PASS1_SPEC, buf, cap); }
+extern "C" int jt_default_pass2_spec(char *buf, size_t cap) { return copy_str(PASS2_DEFAULT_SPEC, buf, cap); }
+
+// ---------------------------------------------------------------------------------------
+// Pass 1 with the interval accumulation of collectAnalysisFrames (analyser.go:571-638)
+// ---------------------------------------------------------------------------------------
+static void analyse_device(jt_ctx *c, const void *d_in, int64_t n_frames, int rate, int channels, int fmt, int F,
+                           jt_measurements *out, jt_interval *iv, int64_t iv_cap, int64_t *n_iv)
+{
+    if (F <= 0) F = 4096;
+    const int64_t nsrc = (n_frames + F - 1) / F;
+    double *d_ss = jt_dalloc<double>(c, nsrc), *d_pk = jt_dalloc<double>(c, nsrc);
+    jt_raw_frame_stats(c, d_in, n_frames, channels, fmt, F, d_ss, d_pk, nsrc);
+    std::vector<double> ss(nsrc), pk(nsrc);
+    GraphResult g;
+    jt_graph_run(c, PASS1_SPEC, d_in, n_frames, rate, channels, fmt, F, false, true, g);
+    if (nsrc) {
+        JT_CUDA(cudaMemcpyAsync(ss.data(), d_ss, sizeof(double) * nsrc, cudaMemcpyDeviceToHost, c->stream));
+        JT_CUDA(cudaMemcpyAsync(pk.data(), d_pk, sizeof(double) * nsrc, cudaMemcpyDeviceToHost, c->stream));
+        JT_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    MeasAcc acc;
+    struct IvAcc { int frameCount = 0; double rawSS = 0; int64_t rawN = 0; double rawPeak = 0; double spec[JT_SP_COUNT] = {0}; bool specFound = false;
+                   double mSum = 0, sSum = 0, tpMax = 0, spMax = 0; } ia;
+    auto reset = [&]() { ia = IvAcc(); ia.tpMax = -120.0; ia.spMax = -120.0; };
+    int64_t n_int = 0;
+    auto finalize = [&](int64_t start_ns) {
+        if (iv && n_int >= iv_cap) JT_THROW(JT_ERR_BUFFER, "interval buffer holds %lld records", (long long)iv_cap);
+        jt_interval r; memset(&r, 0, sizeof(r));
+        r.timestamp_s = start_ns * 1e-9;
+        r.peak_level = ia.rawPeak > 0 ? 20.0 * log10(ia.rawPeak) : -120.0;
+        r.true_peak = ia.tpMax; r.sample_peak = ia.spMax;
+        if (ia.rawN > 0) { double rms = sqrt(ia.rawSS / (double)ia.rawN); r.rms_level = rms < 0.00001 ? -120.0 : 20.0 * log10(rms); }
+        else r.rms_level = -120.0;
+        r.frame_count = ia.frameCount;
+        if (ia.frameCount > 0) {
+            const double n = ia.frameCount;
+            for (int k = 0; k < JT_SP_COUNT; k++) r.spectral[k] = ia.spec[k] / n;
+            r.spectral_found = ia.specFound;
+            r.momentary_lufs = ia.mSum / n; r.short_term_lufs = ia.sSum / n;
+        }
+        if (iv) iv[n_int] = r;
+        n_int++;
+    };
+    auto add_sink = [&](const jt_frame_meta &f) {
+        acc.add(f);
+        const double tp = std::isnan(f.r128_true_peak) ? 0.0 : ratio_db(f.r128_true_peak);
+        const double sp = std::isnan(f.r128_sample_peak) ? 0.0 : ratio_db(f.r128_sample_peak);
+        if (ia.frameCount == 0 || tp > ia.tpMax) ia.tpMax = tp;
+        if (ia.frameCount == 0 || sp > ia.spMax) ia.spMax = sp;
+        for (int k = 0; k < JT_SP_COUNT; k++) if (!std::isnan(f.spectral[k])) { ia.spec[k] += f.spectral[k]; ia.specFound = true; }
+        ia.mSum += std::isnan(f.r128_M) ? 0.0 : f.r128_M;
+        ia.sSum += std::isnan(f.r128_S) ? 0.0 : f.r128_S;
+        ia.frameCount++;
+    };
+    const int64_t hop_ns = 250000000;
+    int64_t start_ns = 0, pushed = 0; size_t sink = 0;
+    for (int64_t f = 0; f < nsrc; f++) {
+        const int64_t t_ns = (int64_t)((double)pushed / (double)rate * 1e9);
+        const int64_t nb = std::min<int64_t>(F, n_frames - pushed);
+        pushed += nb;
+        ia.rawSS += ss[f]; ia.rawN += nb * channels; if (pk[f] > ia.rawPeak) ia.rawPeak = pk[f];
+        if (t_ns - start_ns >= hop_ns) { finalize(start_ns); start_ns = t_ns; reset(); }
+        while (sink < g.meta.size() && g.meta_ready[sink] <= pushed) add_sink(g.meta[sink++]);
+    }
+    while (sink < g.meta.size()) add_sink(g.meta[sink++]);       // EOF flush
+    if (ia.rawN > 0) finalize(start_ns);
+    acc.finish((double)n_frames / rate);
+    if (out) *out = acc.m;
+    if (n_iv) *n_iv = n_int;
+}
+
+extern "C" int jt_analyse(jt_ctx *c, const void *pcm_in, int64_t n_frames, int rate, int channels, int fmt, int frame_size,
+                          jt_measurements *out, jt_interval *iv, int64_t iv_cap, int64_t *n_iv)
+{
+    return guarded(c, [&]() {
+        if (!pcm_in && n_frames > 0) JT_THROW(JT_ERR_INVALID_ARG, "null input");
+        if (fmt != JT_FMT_S16 && fmt != JT_FMT_FLT && fmt != JT_FMT_DBL) JT_THROW(JT_ERR_UNSUPPORTED, "input sample format %d", fmt);
+        const void *d_in = upload(c, pcm_in, (size_t)n_frames * channels * jt_fmt_bytes(fmt));
+        analyse_device(c, d_in, n_frames, rate, channels, fmt, frame_size, out, iv, iv_cap, n_iv);
+    });
+}
+
+// ---------------------------------------------------------------------------------------
+// K20: band RMS batch (measureSpeechBandRMS, analyser_bands.go:33-104)
+// ---------------------------------------------------------------------------------------
+extern "C" int jt_band_rms(jt_ctx *c, const void *pcm_in, int64_t n_frames, int rate, int channels, int fmt,
+                           double start_s, double duration_s, const double *lo, const double *hi, int n_bands,
+                           double *rms_db, int32_t *found)
+{
+    return guarded(c, [&]() {
+        if (!pcm_in || !lo || !hi || !rms_db || n_bands <= 0) JT_THROW(JT_ERR_INVALID_ARG, "null argument");
+        if (start_s < 0) JT_THROW(JT_ERR_INVALID_ARG, "invalid region: negative start time");
+        if (duration_s <= 0) JT_THROW(JT_ERR_INVALID_ARG, "invalid region: non-positive duration");
+        const void *d_in = upload(c, pcm_in, (size_t)n_frames * channels * jt_fmt_bytes(fmt));
+        Sig mono = jt_downmix(c, d_in, n_frames, channels, fmt, rate);
+        const int64_t st_us = llround(start_s * 1e6), du_us = llround(duration_s * 1e6);
+        const int64_t s0 = (st_us * rate + 500000) / 1000000, len = (du_us * rate + 500000) / 1000000;
+        Sig reg = jt_slice(mono, s0, len);
+        std::vector<int32_t> fnd(n_bands, 0);
+        jt_band_rms_batch(c, reg, lo, hi, n_bands, rms_db, fnd.data());
+        if (found) memcpy(found, fnd.data(), sizeof(int32_t) * n_bands);
+    });
+}
+
+// ---------------------------------------------------------------------------------------
+// a9 planners (normalise.go:373-392, 407-425, 539-561, 583-585, 611-632, 1198-1203)
+// ---------------------------------------------------------------------------------------
+static const double kMinLimiterCeilingDB = -24.0, kBrickwallHeadroomDB = 0.9, kCushionDB = 0.2, kLinearSafety = 0.1;
+static const double kTPMax = 0.0, kTPMin = -9.0;
+static double db_to_lin(double db) { return pow(10, db / 20.0); }
+
+static std::string pre_limiter_prefix(double preGain, double ceiling, bool needed)
+{
+    if (!needed) return "";
+    char b[256]; std::string s;
+    if (preGain > 0) { snprintf(b, sizeof(b), "volume=%.1fdB,", preGain); s += b; }
+    snprintf(b, sizeof(b), "alimiter=limit=%.6f:attack=5:release=100:level_in=1:level_out=1:level=0:latency=1:asc=1:asc_level=0.8", db_to_lin(ceiling));
+    return s + b;
+}
+
+extern "C" int jt_build_pass3_spec(double outI, double outTP, double tI, double tTP, double tLRA, char *buf, size_t cap, jt_process_result *plan)
+{
+    if (!buf) return JT_ERR_INVALID_ARG;
+    // calculateLimiterCeiling
+    const double gainRequired = tI - outI, projectedTP = outTP + gainRequired;
+    double ceiling = 0; bool needed = false, clamped = false;
+    if (projectedTP > tTP) { ceiling = tTP - gainRequired; needed = true; if (ceiling < kMinLimiterCeilingDB) { ceiling = kMinLimiterCeilingDB; clamped = true; } }
+    // calculatePreGain
+    double preGain = 0, reCeil = 0;
+    { const double ideal = tTP - gainRequired;
+      if (ideal < kMinLimiterCeilingDB) { preGain = kMinLimiterCeilingDB - ideal; const double postI = outI + preGain; reCeil = tTP - (tI - postI); } }
+    if (clamped) ceiling = reCeil;
+    std::string prefix = pre_limiter_prefix(preGain, ceiling, needed);
+    char ln[256];
+    snprintf(ln, sizeof(ln), "loudnorm=I=%.1f:TP=%.1f:LRA=%.1f:dual_mono=true:print_format=json", tI, tTP, tLRA);
+    std::string spec = prefix.empty() ? std::string(ln) : prefix + "," + ln;
+    if (plan) {
+        plan->limiter_ceiling_db = ceiling; plan->limiter_pregain_db = preGain; plan->gain_db = gainRequired;
+        plan->limiter_needed = needed; plan->limiter_clamped = clamped;
+    }
+    return copy_str(spec.c_str(), buf, cap);
+}
+
+extern "C" int jt_build_pass4_spec(const jt_process_result *plan, const jt_loudnorm_stats *p3, double tI, double tTP, double tLRA,
+                                   int source_rate, char *buf, size_t cap, double *eff_out, double *off_out)
+{
+    if (!plan || !p3 || !buf) return JT_ERR_INVALID_ARG;
+    // the Go side parses the JSON strings, i.e. sees "%.2f"-rounded values (normalise.go:321-343)
+    const double mI = jt_wire("%.2f", p3->input_i), mTP = jt_wire("%.2f", p3->input_tp);
+    const double mLRA = jt_wire("%.2f", p3->input_lra), mTh = jt_wire("%.2f", p3->input_thresh);
+    const double internalTP = mTP + (tI - mI) + kLinearSafety + kCushionDB;             // loudnormInternalTargetTP
+    const double maxLinear = internalTP - mTP + mI - kLinearSafety;                      // calculateLinearModeTarget
+    double eff = tI; if (!(tI <= maxLinear)) eff = maxLinear;
+    const double offset = eff - mI;
+    const double emittedTP = std::max(kTPMin, std::min(internalTP, kTPMax));             // loudnormTPTargets
+    const double brickwall = tTP - kBrickwallHeadroomDB;
+    std::string spec = pre_limiter_prefix(plan->limiter_pregain_db, plan->limiter_ceiling_db, plan->limiter_needed != 0);
+    if (!spec.empty()) spec += ",";
+    char b[1024];
+    snprintf(b, sizeof(b), "loudnorm=I=%.2f:TP=%.2f:LRA=%.1f:measured_I=%.2f:measured_TP=%.2f:measured_LRA=%.2f:measured_thresh=%.2f:offset=%.2f:dual_mono=true:linear=true:print_format=json",
+             eff, emittedTP, tLRA, mI, mTP, mLRA, mTh, offset);
+    spec += b;
+    if (source_rate > 0) { snprintf(b, sizeof(b), ",aresample=%d", source_rate); spec += b; }
+    spec += ",adeclick=t=1.7:w=55:o=50:m=s";
+    snprintf(b, sizeof(b), ",alimiter=limit=%.6f:attack=1:release=50:level_in=1:level_out=1:level=0:latency=1:asc=1:asc_level=0.8", db_to_lin(brickwall));
+    spec += b;
+    spec += ",astats=metadata=1:measure_perchannel=all,aspectralstats=win_size=2048:win_func=hann:measure=all,"
+            "ebur128=metadata=1:peak=sample+true:dualmono=true,"
+            "aformat=sample_rates=44100:channel_layouts=mono:sample_fmts=s16,asetnsamples=n=4096";
+    if (eff_out) *eff_out = eff;
+    if (off_out) *off_out = offset;
+    return copy_str(spec.c_str(), buf, cap);
+}
+
+// ---------------------------------------------------------------------------------------
+// the four-pass chain (ProcessAudio, processor.go:78-216)
+// ---------------------------------------------------------------------------------------
+static void process_device(jt_ctx *c, const void *d_in, int64_t n_frames, int rate, int channels, int fmt, const char *pass2_spec,
+                           int16_t *pcm_out, bool out_on_device, int64_t cap, jt_process_result *res)
+{
+    jt_process_result R; memset(&R, 0, sizeof(R));
+    const double tI = -16.0, tTP = -1.0, tLRA = 20.0;          // defaultLoudnormConfig, filters.go:523-532
+    // Pass 1
+    analyse_device(c, d_in, n_frames, rate, channels, fmt, 4096, &R.input, nullptr, 0, nullptr);
+    jt_check_cancel(c);
+    // Pass 2
+    GraphResult g2;
+    jt_graph_run(c, pass2_spec ? pass2_spec : PASS2_DEFAULT_SPEC, d_in, n_frames, rate, channels, fmt, 4096, true, true, g2);
+    { MeasAcc a; for (auto &m : g2.meta) a.add(m); a.finish((double)g2.out.n / g2.out.rate); R.filtered = a.m; }
+    if (g2.out.fmt != JT_FMT_S16 || g2.out.rate != 44100) JT_THROW(JT_ERR_SPEC, "Pass-2 spec must end in the s16/44.1 kHz output stage (processor.go:379-384)");
+    jt_check_cancel(c);
+    // Pass 3: the Pass-2 output is re-read as the s16 FLAC the reference wrote (processor.go:126-146)
+    char spec3[1024], spec4[4096];
+    int rc = jt_build_pass3_spec(R.filtered.input_i, R.filtered.input_tp, tI, tTP, tLRA, spec3, sizeof(spec3), &R);
+    if (rc) JT_THROW(rc, "pass-3 spec");
+    GraphResult g3;
+    jt_graph_run(c, spec3, g2.out.d, g2.out.n, 44100, 1, JT_FMT_S16, 4096, false, false, g3);
+    R.pass3 = g3.ln;
+    const double mI = jt_wire("%.2f", R.pass3.input_i);
+    if (std::isinf(mI) || std::isnan(mI) || mI < -70.0) JT_THROW(JT_ERR_INVALID_ARG, "cannot normalise silent audio (measured %.1f LUFS)", mI);
+    jt_check_cancel(c);
+    // Pass 4
+    double eff = 0, off = 0;
+    rc = jt_build_pass4_spec(&R, &R.pass3, tI, tTP, tLRA, 44100, spec4, sizeof(spec4), &eff, &off);
+    if (rc) JT_THROW(rc, "pass-4 spec");
+    R.effective_target_i = eff; R.linear_possible = eff == tI;
+    GraphResult g4;
+    jt_graph_run(c, spec4, g2.out.d, g2.out.n, 44100, 1, JT_FMT_S16, 4096, true, true, g4);
+    { MeasAcc a; for (auto &m : g4.meta) a.add(m); a.finish((double)g4.out.n / g4.out.rate); R.final = a.m; }
+    R.pass4 = g4.ln;
+    R.n_out = g4.out.n;
+    if (pcm_out) {
+        if (g4.out.n > cap) JT_THROW(JT_ERR_BUFFER, "pcm_out holds %lld samples, chain produced %lld", (long long)cap, (long long)g4.out.n);
+        const size_t ob = (size_t)g4.out.n * sizeof(int16_t);
+        if (out_on_device) { if (ob) JT_CUDA(cudaMemcpyAsync(pcm_out, g4.out.d, ob, cudaMemcpyDeviceToDevice, c->stream)); }
+        else download(c, pcm_out, g4.out.d, ob);
+    }
+    if (res) *res = R;
+}
+
+extern "C" int jt_process_audio(jt_ctx *c, const void *pcm_in, int64_t n_frames, int rate, int channels, int fmt,
+                                const char *pass2_spec, int16_t *pcm_out, int64_t cap, jt_process_result *res)
+{
+    return guarded(c, [&]() {
+        if (!pcm_in && n_frames > 0) JT_THROW(JT_ERR_INVALID_ARG, "null input");
+        if (fmt != JT_FMT_S16 && fmt != JT_FMT_FLT && fmt != JT_FMT_DBL) JT_THROW(JT_ERR_UNSUPPORTED, "input sample format %d", fmt);
+        const void *d_in = upload(c, pcm_in, (size_t)n_frames * channels * jt_fmt_bytes(fmt));
+        process_device(c, d_in, n_frames, rate, channels, fmt, pass2_spec, pcm_out, false, cap, res);
+    });
+}
+extern "C" int jt_process_audio_dev(jt_ctx *c, const void *d_in, int64_t n_frames, int rate, int channels, int fmt,
+                                const char *pass2_spec, int16_t *d_out, int64_t cap, jt_process_result *res)
+{
+    return guarded(c, [&]() {
+        if (!d_in && n_frames > 0) JT_THROW(JT_ERR_INVALID_ARG, "null input");
+        process_device(c, d_in, n_frames, rate, channels, fmt, pass2_spec, d_out, true, cap, res);
+    });
+}

@@ -1,0 +1,448 @@
+// Filter-spec parser + whole-stream graph executor + sink-frame metadata assembly.
+// Replaces setupFilterGraph / runFilterGraph (internal/processor/frame_processor.go:64-216):
+// the spec strings are the reference's own (filters.go:968-989, normalise.go:257-264,
+// 1231-1334, analyser_bands.go:33, analyser_output.go:18); instead of pumping 4096-sample
+// frames through libavfilter, each filter runs as whole-stream kernels, and the frame /
+// metadata cadence libavfilter would have produced is reconstructed with integer arithmetic
+// (which sink frame inherits which astats / aspectralstats / ebur128 stamp, and after which
+// pushed input frame it becomes pullable).
+#include "jt_graph.h"
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <climits>
+
+// ---------------------------------------------------------------------------------------
+// parsing
+// ---------------------------------------------------------------------------------------
+const std::string *FilterNode::get(const char *k1, const char *k2) const
+{
+    for (auto &kv : opts) if (kv.first == k1 || (k2 && kv.first == k2)) return &kv.second;
+    return nullptr;
+}
+double FilterNode::num(const char *k1, const char *k2, double dflt) const
+{
+    const std::string *s = get(k1, k2);
+    if (!s) return dflt;
+    char *end = nullptr;
+    double v = strtod(s->c_str(), &end);
+    if (end == s->c_str()) JT_THROW(JT_ERR_SPEC, "filter %s: option %s=%s is not a number", name.c_str(), k1, s->c_str());
+    return v;
+}
+std::string FilterNode::str(const char *k1, const char *k2, const char *dflt) const
+{
+    const std::string *s = get(k1, k2);
+    return s ? *s : std::string(dflt);
+}
+bool FilterNode::flag(const char *k1, const char *k2, bool dflt) const
+{
+    const std::string *s = get(k1, k2);
+    if (!s) return dflt;
+    if (*s == "1" || *s == "true" || *s == "yes" || *s == "on") return true;
+    if (*s == "0" || *s == "false" || *s == "no" || *s == "off") return false;
+    JT_THROW(JT_ERR_SPEC, "filter %s: option %s=%s is not a boolean", name.c_str(), k1, s->c_str());
+}
+
+// split on `sep` at top level, honouring backslash escapes and single quotes
+static std::vector<std::string> split_escaped(const std::string &s, char sep, bool unescape)
+{
+    std::vector<std::string> out; std::string cur; bool quote = false;
+    for (size_t i = 0; i < s.size(); i++) {
+        char ch = s[i];
+        if (ch == '\\' && i + 1 < s.size()) { if (!unescape) cur += ch; cur += s[++i]; continue; }
+        if (ch == '\'') { quote = !quote; if (!unescape) cur += ch; continue; }
+        if (ch == sep && !quote) { out.push_back(cur); cur.clear(); continue; }
+        cur += ch;
+    }
+    out.push_back(cur);
+    return out;
+}
+
+std::vector<FilterNode> jt_parse_spec(const std::string &spec)
+{
+    std::vector<FilterNode> nodes;
+    if (spec.empty()) return nodes;
+    if (spec.find(';') != std::string::npos || spec.find('[') != std::string::npos)
+        JT_THROW(JT_ERR_SPEC, "only linear filter chains are supported");
+    for (const std::string &f : split_escaped(spec, ',', false)) {
+        if (f.empty()) JT_THROW(JT_ERR_SPEC, "empty filter in spec");
+        FilterNode n;
+        size_t eq = f.find('=');
+        n.name = f.substr(0, eq);
+        for (char ch : n.name) if (!(isalnum((unsigned char)ch) || ch == '_')) JT_THROW(JT_ERR_SPEC, "bad filter name '%s'", n.name.c_str());
+        if (eq != std::string::npos) {
+            for (const std::string &o : split_escaped(f.substr(eq + 1), ':', true)) {
+                size_t e2 = o.find('=');
+                if (e2 == std::string::npos) n.opts.push_back({"", o});
+                else n.opts.push_back({o.substr(0, e2), o.substr(e2 + 1)});
+            }
+        }
+        nodes.push_back(n);
+    }
+    return nodes;
+}
+
+double jt_wire(const char *fmt, double v)
+{
+    char b[128];
+    snprintf(b, sizeof(b), fmt, v);
+    return strtod(b, nullptr);
+}
+
+// ---------------------------------------------------------------------------------------
+// frame bookkeeping
+// ---------------------------------------------------------------------------------------
+static std::vector<FrameRef> source_frames(int64_t n, int F)
+{
+    std::vector<FrameRef> v;
+    for (int64_t s = 0; s < n; s += F) {
+        FrameRef f; f.start = s; f.nb = (int32_t)std::min<int64_t>(F, n - s); f.ready = s + f.nb;
+        v.push_back(f);
+    }
+    return v;
+}
+
+// libavfilter's ff_inlink_consume_samples(min=max=F): new frames of F samples (last partial);
+// properties come from the queued frame holding the first sample (take_samples:
+// av_frame_copy_props(buf, frame0)); a frame can be built once its last sample has arrived.
+static std::vector<FrameRef> reframe(const std::vector<FrameRef> &old, int64_t n, int F)
+{
+    std::vector<FrameRef> v;
+    size_t a = 0, b = 0;
+    for (int64_t s = 0; s < n; s += F) {
+        FrameRef f; f.start = s; f.nb = (int32_t)std::min<int64_t>(F, n - s);
+        while (a + 1 < old.size() && old[a + 1].start <= s) a++;
+        const int64_t last = s + f.nb - 1;
+        if (b < a) b = a;
+        while (b + 1 < old.size() && old[b + 1].start <= last) b++;
+        if (!old.empty()) {
+            f.astats_pos = old[a].astats_pos; f.hop = old[a].hop; f.tick = old[a].tick;
+            f.ready = old[b].ready;
+        }
+        v.push_back(f);
+    }
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------
+// executor
+// ---------------------------------------------------------------------------------------
+namespace {
+struct Exec {
+    jt_ctx *c; Sig cur; int link_fmt; std::vector<FrameRef> frames;
+    // analysis products
+    bool has_astats = false, has_spec = false, has_r128 = false, astats_overall_only = false;
+    Sig astats_sig; R128Result r128; std::vector<float> spec_rows; int64_t spec_hops = 0;
+    void storage(int fmt) { cur = jt_convert(c, cur, fmt); link_fmt = fmt; }
+    void materialise() { if (cur.fmt != link_fmt) cur = jt_convert(c, cur, link_fmt); }
+};
+}
+
+static int swr_internal_fmt(int in_fmt, int out_fmt)
+{   // libswresample/swresample.c swr_init(): int_sample_fmt when a rate conversion is involved
+    const size_t bi = jt_fmt_bytes(in_fmt), bo = jt_fmt_bytes(out_fmt);
+    if (bi <= 2 && bo <= 2) return JT_FMT_S16;
+    if (bi <= 4) return JT_FMT_FLT;
+    return JT_FMT_DBL;
+}
+
+static void do_resample(Exec &E, int out_rate, int out_fmt /* 0 = keep link format */)
+{
+    jt_ctx *c = E.c;
+    const int in_link = E.link_fmt;
+    if (!out_fmt) out_fmt = in_link;
+    if (out_rate == E.cur.rate) {          // format conversion only
+        if (out_fmt != in_link) { E.materialise(); E.storage(out_fmt); }
+        return;
+    }
+    const int work = swr_internal_fmt(in_link, out_fmt);
+    if (work == JT_FMT_S16) JT_THROW(JT_ERR_UNSUPPORTED, "s16-internal resampling (s16 -> s16 rate change)");
+    SwrPlan p = jt_swr_plan(E.cur.rate, out_rate);
+    const int64_t n_in = E.cur.n;
+    // swr converts to its internal format first, then resamples
+    Sig src = E.cur;
+    if (work == JT_FMT_FLT && src.fmt == JT_FMT_DBL) src = jt_convert(c, src, JT_FMT_FLT);
+    Sig r = jt_swr_resample(c, src, p, work, true);
+    // frames: one output frame per input frame (aresample filter_frame), then the EOF flush frame
+    std::vector<FrameRef> nf; int64_t done = 0;
+    for (const FrameRef &f : E.frames) {
+        const int64_t cnt = std::min<int64_t>(p.out_count(f.start + f.nb), r.n);
+        if (cnt > done) { FrameRef o = f; o.start = done; o.nb = (int32_t)(cnt - done); nf.push_back(o); done = cnt; }
+    }
+    if (r.n > done) { FrameRef o; o.start = done; o.nb = (int32_t)(r.n - done); o.ready = INT64_MAX; nf.push_back(o); }
+    (void)n_in;
+    E.frames.swap(nf);
+    E.cur = r; E.link_fmt = work;
+    if (out_fmt != work) E.storage(out_fmt);
+}
+
+static std::vector<double> parse_bn(const std::string &s)
+{
+    std::vector<double> v;
+    for (const std::string &t : split_escaped(s, '|', true)) {
+        if (t.empty()) continue;
+        size_t p = 0; std::string u = t;
+        while ((p = u.find(' ')) != std::string::npos) u.erase(p, 1);
+        v.push_back(strtod(u.c_str(), nullptr));
+    }
+    return v;
+}
+
+void jt_graph_run(jt_ctx *c, const std::string &spec, const void *d_in, int64_t n_frames, int rate, int channels,
+                  int fmt, int frame_size, bool want_pcm, bool want_meta, GraphResult &res)
+{
+    if (n_frames < 0 || rate <= 0 || channels <= 0) JT_THROW(JT_ERR_INVALID_ARG, "bad stream description");
+    if (frame_size <= 0) frame_size = 4096;
+    std::vector<FilterNode> nodes = jt_parse_spec(spec);
+    res = GraphResult();
+    memset(&res.ln, 0, sizeof(res.ln));
+
+    Exec E; E.c = c;
+    bool have_mono = false;
+    const void *raw = d_in;
+    if (channels == 1) { E.cur = jt_downmix(c, raw, n_frames, 1, fmt, rate); have_mono = true; }
+    E.link_fmt = fmt;
+    E.frames = source_frames(n_frames, frame_size);
+
+    for (size_t ni = 0; ni < nodes.size(); ni++) {
+        const FilterNode &f = nodes[ni];
+        const bool last = ni + 1 == nodes.size();
+        jt_check_cancel(c);
+        if (!have_mono) {
+            // the only multi-channel-aware filter of the path is the leading downmix
+            if (f.name == "aformat" && f.str("channel_layouts", "cl", "") == "mono") {
+                E.cur = jt_downmix(c, raw, n_frames, channels, fmt, rate);
+                have_mono = true;
+            } else JT_THROW(JT_ERR_UNSUPPORTED, "filter %s on %d-channel audio (specs of this path start with aformat=channel_layouts=mono)", f.name.c_str(), channels);
+        }
+        if (f.name == "aformat") {
+            const std::string cl = f.str("channel_layouts", "cl", "mono");
+            if (cl != "mono") JT_THROW(JT_ERR_UNSUPPORTED, "aformat channel_layouts=%s", cl.c_str());
+            int out_rate = (int)f.num("sample_rates", "r", E.cur.rate);
+            std::string sf = f.str("sample_fmts", "f", "");
+            int out_fmt = 0;
+            if (sf == "s16") out_fmt = JT_FMT_S16; else if (sf == "flt" || sf == "fltp") out_fmt = JT_FMT_FLT;
+            else if (sf == "dbl" || sf == "dblp") out_fmt = JT_FMT_DBL; else if (!sf.empty()) JT_THROW(JT_ERR_UNSUPPORTED, "aformat sample_fmts=%s", sf.c_str());
+            if (last && !want_pcm && out_rate != E.cur.rate) {
+                // measure-only call: the resampled audio would be discarded, keep the frame cadence only
+                SwrPlan p = jt_swr_plan(E.cur.rate, out_rate);
+                std::vector<FrameRef> nf; int64_t done = 0; const int64_t tot = p.out_count_flush(E.cur.n);
+                for (const FrameRef &fr : E.frames) { int64_t cnt = std::min(p.out_count(fr.start + fr.nb), tot); if (cnt > done) { FrameRef o = fr; o.start = done; o.nb = (int32_t)(cnt - done); nf.push_back(o); done = cnt; } }
+                if (tot > done) { FrameRef o; o.start = done; o.nb = (int32_t)(tot - done); o.ready = INT64_MAX; nf.push_back(o); }
+                E.frames.swap(nf); E.cur.n = tot; E.cur.rate = out_rate; E.cur.d = nullptr;
+            } else do_resample(E, out_rate, out_fmt);
+        } else if (f.name == "aresample") {
+            int out_rate = (int)f.num("sample_rate", "", E.cur.rate);
+            if (const std::string *p = f.get("")) out_rate = atoi(p->c_str());
+            do_resample(E, out_rate, 0);
+        } else if (f.name == "asetnsamples") {
+            const int n = (int)f.num("n", "nb_out_samples", 1024);
+            const bool pad = f.flag("p", "pad", true);
+            E.frames = reframe(E.frames, E.cur.n, n);
+            if (pad && !E.frames.empty() && E.frames.back().nb < n) {
+                const int64_t tot = E.frames.back().start + n;
+                E.frames.back().nb = n;
+                if (E.cur.d) { E.materialise(); E.cur = jt_pad_zero(c, E.cur, tot); } else E.cur.n = tot;
+            }
+        } else if (f.name == "atrim") {
+            // libavfilter/trim.c: start_pts / duration_tb = av_rescale_q(usec, AV_TIME_BASE_Q, 1/rate), nearest
+            const double st = f.num("start", "starti", 0.0), du = f.num("duration", "durationi", 0.0);
+            const int64_t st_us = llround(st * 1e6), du_us = llround(du * 1e6);
+            const int64_t s0 = (st_us * E.cur.rate + 500000) / 1000000;
+            const int64_t len = du_us > 0 ? (du_us * E.cur.rate + 500000) / 1000000 : INT64_MAX / 4;
+            const int64_t a = std::min(std::max<int64_t>(s0, 0), E.cur.n), b = std::min(E.cur.n, s0 + len);
+            std::vector<FrameRef> nf;
+            for (const FrameRef &fr : E.frames) {
+                const int64_t lo = std::max(fr.start, a), hi = std::min(fr.start + fr.nb, b);
+                if (hi > lo) { FrameRef o = fr; o.start = lo - a; o.nb = (int32_t)(hi - lo); nf.push_back(o); }
+            }
+            E.frames.swap(nf);
+            E.materialise();
+            E.cur = jt_slice(E.cur, a, std::max<int64_t>(b - a, 0));
+        } else if (f.name == "asetpts") {
+            // timestamps only
+        } else if (f.name == "highpass" || f.name == "lowpass") {
+            E.materialise();
+            if (E.link_fmt != JT_FMT_S16 && E.link_fmt != JT_FMT_FLT && E.link_fmt != JT_FMT_DBL) JT_THROW(JT_ERR_UNSUPPORTED, "biquad format");
+            const double freq = f.num("f", "frequency", 3000);
+            const int poles = (int)f.num("p", "poles", 2);
+            const std::string wt = f.str("t", "width_type", "q");
+            const double width = f.num("w", "width", 0.707);
+            const bool norm = f.flag("n", "normalize", false);
+            const std::string tr = f.str("a", "transform", "di");
+            const double mix = f.num("m", "mix", 1.0);
+            if (poles != 2 || wt != "q") JT_THROW(JT_ERR_UNSUPPORTED, "%s poles=%d width_type=%s", f.name.c_str(), poles, wt.c_str());
+            if (tr != "di" && tr != "tdii") JT_THROW(JT_ERR_UNSUPPORTED, "biquad transform %s", tr.c_str());
+            BiquadCoef k = jt_biquad_design(f.name == "highpass", freq, width, E.cur.rate, norm);
+            E.cur = jt_biquad(c, E.cur, k, tr == "tdii", mix);
+        } else if (f.name == "anlmdn") {
+            E.materialise(); E.storage(JT_FMT_FLT);
+            const std::string om = f.str("o", "output", "o");
+            if (om != "o") JT_THROW(JT_ERR_UNSUPPORTED, "anlmdn output mode %s", om.c_str());
+            const double s = f.num("s", "strength", 0.00001), p = f.num("p", "patch", 0.002), r = f.num("r", "research", 0.006), m = f.num("m", "smooth", 11.0);
+            Sig o = jt_anlmdn(c, E.cur, s, p, r, m);
+            const int K = (int)llround(p * E.cur.rate);      // frames of H = 2K+1 samples
+            E.cur = o; E.frames = reframe(E.frames, E.cur.n, 2 * K + 1);
+        } else if (f.name == "afftdn") {
+            E.materialise(); E.storage(JT_FMT_FLT);
+            AfftdnParams p;
+            p.nr = f.num("nr", "noise_reduction", 12); p.nf = f.num("nf", "noise_floor", -50); p.rf = f.num("rf", "residual_floor", -38);
+            p.ad = f.num("ad", "adaptivity", 0.5); p.fo = f.num("fo", "floor_offset", 1.0); p.bm = f.num("bm", "band_multiplier", 1.25);
+            p.gs = (int)f.num("gs", "gain_smooth", 0);
+            p.tn = f.flag("tn", "track_noise", false);
+            if (f.flag("tr", "track_residual", false)) JT_THROW(JT_ERR_UNSUPPORTED, "afftdn track_residual");
+            const std::string nt = f.str("nt", "noise_type", "w");
+            if (nt == "w" || nt == "white") p.nt = 0; else if (nt == "v" || nt == "vinyl") p.nt = 1; else if (nt == "s" || nt == "shellac") p.nt = 2;
+            else if (nt == "c" || nt == "custom") p.nt = 3; else JT_THROW(JT_ERR_SPEC, "afftdn nt=%s", nt.c_str());
+            if (const std::string *bn = f.get("bn", "band_noise")) {
+                std::vector<double> v = parse_bn(*bn); p.has_bn = true;
+                for (size_t i = 0; i < 15 && i < v.size(); i++) p.bn[i] = v[i];
+            }
+            const std::string om = f.str("om", "output_mode", "o");
+            if (om != "o" && om != "output") JT_THROW(JT_ERR_UNSUPPORTED, "afftdn output mode %s", om.c_str());
+            E.cur = jt_afftdn(c, E.cur, p);
+            E.frames = reframe(E.frames, E.cur.n, E.cur.rate / 80);
+        } else if (f.name == "agate") {
+            E.materialise(); E.storage(JT_FMT_DBL);
+            GateParams p;
+            p.threshold = f.num("threshold", "", 0.125); p.ratio = f.num("ratio", "", 2); p.attack = f.num("attack", "", 20);
+            p.release = f.num("release", "", 250); p.range = f.num("range", "", 0.06125); p.knee = f.num("knee", "", 2.828427125);
+            p.makeup = f.num("makeup", "", 1); p.detection_rms = f.str("detection", "", "rms") == "rms";
+            if (f.num("level_in", "", 1) != 1 || f.str("mode", "", "downward") != "downward") JT_THROW(JT_ERR_UNSUPPORTED, "agate level_in/mode");
+            E.cur = jt_agate(c, E.cur, p);
+        } else if (f.name == "acompressor") {
+            E.materialise(); E.storage(JT_FMT_DBL);
+            CompParams p;
+            p.threshold = f.num("threshold", "", 0.125); p.ratio = f.num("ratio", "", 2); p.attack = f.num("attack", "", 20);
+            p.release = f.num("release", "", 250); p.makeup = f.num("makeup", "", 1); p.knee = f.num("knee", "", 2.82843);
+            p.mix = f.num("mix", "", 1); p.detection_rms = f.str("detection", "", "rms") == "rms";
+            if (f.num("level_in", "", 1) != 1 || f.str("mode", "", "downward") != "downward" || f.str("link", "", "average") != "average")
+                JT_THROW(JT_ERR_UNSUPPORTED, "acompressor level_in/mode/link");
+            E.cur = jt_acompressor(c, E.cur, p);
+        } else if (f.name == "deesser") {
+            E.materialise(); E.storage(JT_FMT_DBL);
+            if (f.str("s", "", "o") != "o") JT_THROW(JT_ERR_UNSUPPORTED, "deesser mode");
+            E.cur = jt_deesser(c, E.cur, f.num("i", "", 0.0), f.num("m", "", 0.5), f.num("f", "", 0.5));
+        } else if (f.name == "volume") {
+            std::string v = f.str("volume", "", "1.0");
+            if (const std::string *p = f.get("")) v = *p;
+            char *end = nullptr; double g = strtod(v.c_str(), &end);
+            if (end && !strcmp(end, "dB")) g = pow(10.0, g / 20.0); else if (end && *end) JT_THROW(JT_ERR_UNSUPPORTED, "volume expression '%s'", v.c_str());
+            E.materialise();
+            E.cur = jt_volume(c, E.cur, g); E.link_fmt = JT_FMT_FLT;
+        } else if (f.name == "alimiter") {
+            E.materialise(); E.storage(JT_FMT_DBL);
+            LimiterParams p;
+            p.limit = f.num("limit", "", 1); p.attack_ms = f.num("attack", "", 5); p.release_ms = f.num("release", "", 50);
+            p.level_in = f.num("level_in", "", 1); p.level_out = f.num("level_out", "", 1); p.auto_level = f.flag("level", "", true);
+            p.asc = f.flag("asc", "", false); p.asc_level = f.num("asc_level", "", 0.5); p.latency = f.flag("latency", "", false);
+            if (!p.latency) JT_THROW(JT_ERR_UNSUPPORTED, "alimiter latency=0");
+            E.cur = jt_alimiter(c, E.cur, p);
+        } else if (f.name == "adeclick") {
+            E.materialise(); E.storage(JT_FMT_DBL);
+            const std::string m = f.str("m", "method", "a");
+            const int save = (m == "s" || m == "save") ? 1 : 0;
+            const double w = f.num("w", "window", 55), o = f.num("o", "overlap", 75);
+            E.cur = jt_adeclick(c, E.cur, w, o, f.num("a", "arorder", 2), f.num("t", "threshold", 2), f.num("b", "burst", 2), save);
+            const int ws = (int)(E.cur.rate * w / 1000.), hop = (int)(ws * (1. - o / 100.));
+            E.frames = reframe(E.frames, E.cur.n, std::max(hop, 1));
+        } else if (f.name == "loudnorm") {
+            const double I = f.num("I", "i", -24), TP = f.num("TP", "tp", -2), LRA = f.num("LRA", "lra", 7);
+            const double mI = f.num("measured_I", "measured_i", 0), mTP = f.num("measured_TP", "measured_tp", 99);
+            const double mLRA = f.num("measured_LRA", "measured_lra", 0), mTh = f.num("measured_thresh", "", -70);
+            double offset = f.num("offset", "", 0);
+            const bool linear = f.flag("linear", "", true), dual = f.flag("dual_mono", "", false);
+            bool lin_mode = false;
+            if (linear) {     // af_loudnorm.c init()
+                const double off = I - mI, off_tp = mTP + off;
+                if (mTP != 99 && mTh != -70 && mLRA != 0 && mI != 0 && off_tp <= TP && mLRA <= LRA) { lin_mode = true; offset = off; }
+            }
+            res.ln.valid = 1;
+            LoudnormMeter mi, mo;
+            if (lin_mode) {
+                E.materialise(); E.storage(JT_FMT_DBL);
+                jt_loudnorm_meter(c, E.cur, dual, mi);
+                E.cur = jt_gain_f64(c, E.cur, pow(10., offset / 20.));
+                jt_loudnorm_meter(c, E.cur, dual, mo);
+                res.ln.normalization_type = 0;
+                res.ln.output_i = mo.I; res.ln.output_tp = 20. * log10(mo.sample_peak); res.ln.output_lra = mo.LRA; res.ln.output_thresh = mo.thresh;
+                res.ln.target_offset = I - mo.I;
+            } else {
+                // dynamic mode: af_loudnorm.c query_formats forces the input link to 192 kHz / dbl
+                if (want_pcm || !last) JT_THROW(JT_ERR_UNSUPPORTED, "loudnorm dynamic mode with audio output (linear-mode preconditions not met: measured_I=%g measured_TP=%g measured_LRA=%g measured_thresh=%g)", mI, mTP, mLRA, mTh);
+                do_resample(E, 192000, JT_FMT_DBL);
+                jt_loudnorm_meter(c, E.cur, dual, mi);
+                res.ln.normalization_type = 1;
+                res.ln.output_i = res.ln.output_tp = res.ln.output_lra = res.ln.output_thresh = res.ln.target_offset = NAN;
+            }
+            res.ln.input_i = mi.I; res.ln.input_tp = 20. * log10(mi.sample_peak); res.ln.input_lra = mi.LRA; res.ln.input_thresh = mi.thresh;
+        } else if (f.name == "astats") {
+            E.materialise();
+            E.has_astats = true; E.astats_sig = E.cur;
+            { const std::string mp = f.str("measure_perchannel", "", "all"); E.astats_overall_only = (mp == "0" || mp == "none"); }
+            for (FrameRef &fr : E.frames) fr.astats_pos = fr.start + fr.nb;
+        } else if (f.name == "aspectralstats") {
+            E.materialise(); E.storage(JT_FMT_FLT);
+            const int win = (int)f.num("win_size", "", 2048);
+            if (f.str("win_func", "", "hann") != "hann" && f.str("win_func", "", "hann") != "hanning") JT_THROW(JT_ERR_UNSUPPORTED, "aspectralstats win_func");
+            if (f.num("overlap", "", 0.5) != 0.5) JT_THROW(JT_ERR_UNSUPPORTED, "aspectralstats overlap");
+            if (want_meta) jt_aspectralstats(c, E.cur, win, E.spec_rows, E.spec_hops);
+            E.has_spec = true;
+            E.frames = reframe(E.frames, E.cur.n, win / 2);
+            for (size_t j = 0; j < E.frames.size(); j++) E.frames[j].hop = (int32_t)j;
+        } else if (f.name == "ebur128") {
+            const std::string peak = f.str("peak", "", "none");
+            const bool tp = peak.find("true") != std::string::npos;
+            const bool dual = f.flag("dualmono", "", false);
+            // input link is dbl; s16/flt storage widens exactly on load
+            if (want_meta) jt_ebur128(c, E.cur, dual, tp, E.r128);
+            E.has_r128 = true; E.link_fmt = JT_FMT_DBL;
+            const int tick = E.cur.rate / 10;
+            E.frames = reframe(E.frames, E.cur.n, tick);
+            for (size_t k = 0; k < E.frames.size(); k++) if (E.frames[k].nb == tick) E.frames[k].tick = (int32_t)k;
+        } else {
+            JT_THROW(JT_ERR_UNSUPPORTED, "filter '%s' is not part of the jivetalking hot path", f.name.c_str());
+        }
+    }
+    if (!have_mono) JT_THROW(JT_ERR_UNSUPPORTED, "%d-channel graph without a mono downmix", channels);
+    if (E.cur.d && want_pcm) E.materialise();
+    res.out = E.cur; if (E.cur.d) res.out.fmt = E.cur.fmt; else res.out.fmt = E.link_fmt;
+
+    // ---- sink-frame metadata ------------------------------------------------------------
+    if (!want_meta) return;
+    const size_t nf = E.frames.size();
+    res.meta.resize(nf); res.meta_ready.resize(nf);
+    int64_t last_tick = -1; long last_astats_frame = -1;
+    for (size_t i = 0; i < nf; i++) {
+        if (E.frames[i].tick >= 0) last_tick = std::max<int64_t>(last_tick, E.frames[i].tick);
+        if (E.frames[i].astats_pos >= 0) last_astats_frame = (long)i;
+    }
+    for (size_t i = 0; i < nf; i++) {
+        const FrameRef &fr = E.frames[i];
+        jt_frame_meta &m = res.meta[i];
+        double *dp = &m.r128_M;
+        const size_t ndbl = (sizeof(jt_frame_meta) - offsetof(jt_frame_meta, r128_M)) / sizeof(double);
+        for (size_t k = 0; k < ndbl; k++) dp[k] = NAN;
+        m.first_sample = fr.start; m.nb_samples = fr.nb; m.reserved = 0;
+        res.meta_ready[i] = fr.ready;
+        if (E.has_r128 && fr.tick >= 0 && fr.tick < E.r128.n_ticks) {
+            const int64_t k = fr.tick;
+            m.r128_M = jt_wire("%.3f", E.r128.M[k]); m.r128_S = jt_wire("%.3f", E.r128.S[k]);
+            m.r128_sample_peak = jt_wire("%.3f", E.r128.sp_cum[k]);
+            m.r128_true_peak = jt_wire("%.3f", E.r128.tp_cum[k]);
+            if (k == last_tick) {
+                m.r128_I = jt_wire("%.3f", E.r128.I); m.r128_LRA = jt_wire("%.3f", E.r128.LRA);
+                m.r128_LRA_low = jt_wire("%.3f", E.r128.LRA_low); m.r128_LRA_high = jt_wire("%.3f", E.r128.LRA_high);
+            }
+        }
+        if (E.has_spec && fr.hop >= 0 && fr.hop < E.spec_hops)
+            for (int k = 0; k < JT_SP_COUNT; k++) m.spectral[k] = jt_wire("%g", (double)E.spec_rows[(size_t)fr.hop * JT_SP_COUNT + k]);
+        if (E.has_astats && (long)i == last_astats_frame) {
+            AstatsResult a; jt_astats(c, E.astats_sig, fr.astats_pos, a);
+            if (!E.astats_overall_only) for (int k = 0; k < JT_AS_COUNT; k++) m.astats[k] = std::isnan(a.v[k]) ? NAN : jt_wire("%f", a.v[k]);
+            m.astats_overall_RMS_level = jt_wire("%f", a.overall_rms);
+            m.astats_overall_Peak_level = jt_wire("%f", a.overall_peak);
+        }
+    }
+}

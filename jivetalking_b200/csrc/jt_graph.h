@@ -1,0 +1,41 @@
+// Filter-spec parser and whole-stream graph executor (the S4 seam:
+// setupFilterGraph/runFilterGraph, internal/processor/frame_processor.go:64-216).
+#pragma once
+#include "jt_internal.h"
+#include <string>
+#include <vector>
+#include <map>
+
+struct FilterNode {
+    std::string name;
+    std::vector<std::pair<std::string, std::string>> opts;   // in order; positional args have empty key
+    const std::string *get(const char *k1, const char *k2 = nullptr) const;
+    double num(const char *k1, const char *k2, double dflt) const;
+    std::string str(const char *k1, const char *k2, const char *dflt) const;
+    bool flag(const char *k1, const char *k2, bool dflt) const;
+};
+std::vector<FilterNode> jt_parse_spec(const std::string &spec);
+
+// One frame on a link, with the metadata it inherited (indices into the producers' outputs).
+struct FrameRef {
+    int64_t start = 0;       // first sample on this link
+    int32_t nb = 0;
+    int64_t ready = 0;       // source samples that must have been pushed before this frame can be pulled
+    int64_t astats_pos = -1; // astats cumulative over [0, astats_pos) of the astats input signal
+    int32_t hop = -1;        // aspectralstats hop index
+    int32_t tick = -1;       // ebur128 100 ms tick index
+};
+
+struct GraphResult {
+    Sig out;                                  // sink signal (device)
+    std::vector<jt_frame_meta> meta;          // one per sink frame
+    std::vector<int64_t> meta_ready;          // FrameRef::ready per sink frame (INT64_MAX = only at flush)
+    jt_loudnorm_stats ln;
+};
+
+// d_in: device pointer to interleaved input.  want_pcm=false lets measure-only graphs skip
+// work whose only product is discarded audio (loudnorm dynamic mode in Pass 3).
+void jt_graph_run(jt_ctx *c, const std::string &spec, const void *d_in, int64_t n_frames, int rate, int channels,
+                  int fmt, int frame_size, bool want_pcm, bool want_meta, GraphResult &res);
+
+double jt_wire(const char *fmt, double v);    // value as the Go side parses it back from FFmpeg's printf

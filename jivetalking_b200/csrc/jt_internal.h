@@ -1,0 +1,142 @@
+// libjtdsp internals: context, device-signal descriptor, kernel launcher prototypes.
+// Product code: nothing here may reference oracle/.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <atomic>
+#include <string>
+#include <vector>
+#include <map>
+#include <cmath>
+#include "../../include/jtdsp.h"
+
+#define JT_NSM_DEFAULT 148
+
+struct JtTimingSlot { std::string name; double ms = 0; int64_t launches = 0; };
+
+struct jt_ctx {
+    int device = 0;
+    int num_sms = JT_NSM_DEFAULT;
+    cudaStream_t stream = nullptr;
+    std::string last_error;
+    std::atomic<int> cancel{0};
+    int64_t launches = 0;
+    bool timing = false;
+    std::vector<JtTimingSlot> slots;
+    struct Pending { cudaEvent_t a, b; int slot; };
+    std::vector<Pending> pending;
+    std::vector<void *> allocs;        // freed by jt_release_all at the end of each API call
+    std::vector<void *> host_allocs;   // pinned staging
+    void *pin_in = nullptr; size_t pin_in_bytes = 0;
+    void *pin_out = nullptr; size_t pin_out_bytes = 0;
+};
+
+struct JtError { int code; std::string msg; };
+
+#define JT_THROW(code, ...) do { char _b[512]; snprintf(_b, sizeof(_b), __VA_ARGS__); throw JtError{code, _b}; } while (0)
+#define JT_CUDA(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) \
+    JT_THROW(JT_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #x, cudaGetErrorString(_e)); } while (0)
+
+void *jt_dalloc_bytes(jt_ctx *c, size_t bytes);
+template <class T> static inline T *jt_dalloc(jt_ctx *c, size_t n) { return (T *)jt_dalloc_bytes(c, (n ? n : 1) * sizeof(T)); }
+void jt_release_all(jt_ctx *c);
+void jt_check_cancel(jt_ctx *c);
+void jt_flush_timing(jt_ctx *c);
+
+// RAII launch bookkeeping: counts one launch of `name`, optionally brackets it with events.
+struct JtLaunch {
+    jt_ctx *c; int slot = -1; cudaEvent_t a = nullptr, b = nullptr;
+    JtLaunch(jt_ctx *ctx, const char *name, int n_launches = 1);
+    ~JtLaunch();
+};
+
+// ---- device-resident mono signal --------------------------------------------------------
+struct Sig {
+    int fmt = 0;        // JT_FMT_S16 / FLT / DBL
+    int rate = 0;
+    int64_t n = 0;      // samples (mono)
+    void *d = nullptr;  // device pointer
+};
+static inline size_t jt_fmt_bytes(int fmt) { return fmt == JT_FMT_S16 ? 2 : fmt == JT_FMT_DBL ? 8 : 4; }
+
+// ---- jt_util.cu ---------------------------------------------------------------------------
+Sig  jt_convert(jt_ctx *c, const Sig &in, int out_fmt);                   // audioconvert.c semantics
+Sig  jt_downmix(jt_ctx *c, const void *d_in, int64_t n_frames, int channels, int fmt, int rate);
+void jt_raw_frame_stats(jt_ctx *c, const void *d_in, int64_t n_frames, int channels, int fmt, int frame_size,
+                        double *d_sumsq, double *d_peak, int64_t n_src_frames);   // a2, per decoder frame
+Sig  jt_volume(jt_ctx *c, const Sig &in, double volume_linear);           // af_volume.c
+Sig  jt_gain_f64(jt_ctx *c, const Sig &in, double gain);                  // loudnorm linear mode
+Sig  jt_slice(const Sig &in, int64_t start, int64_t count);               // atrim (view, no copy)
+Sig  jt_pad_zero(jt_ctx *c, const Sig &in, int64_t n_total);              // asetnsamples pad=1
+
+// ---- k_swr.cu -----------------------------------------------------------------------------
+struct SwrPlan {
+    int in_rate = 0, out_rate = 0, phase_count = 0, filter_length = 0, div = 0;
+    std::vector<double> bank;   // phase_count x filter_length
+    bool identity = false;
+    int64_t out_count(int64_t n_in) const;        // outputs produced after n_in inputs, no flush
+    int64_t out_count_flush(int64_t n_in) const;  // total with end reflection
+    int64_t first_tap(int64_t m) const;           // input index of output m's first tap
+};
+SwrPlan jt_swr_plan(int in_rate, int out_rate);
+// resample whole stream; work_fmt = JT_FMT_FLT or JT_FMT_DBL (swr's internal format); returns work_fmt signal
+Sig  jt_swr_resample(jt_ctx *c, const Sig &in, const SwrPlan &p, int work_fmt, bool flush);
+// per-tick max |oversampled| (ebur128 true peak): d_tick_tp[k] = max over outputs first available at tick k
+void jt_swr_tick_absmax(jt_ctx *c, const Sig &in, const SwrPlan &p, int tick, int64_t n_ticks, double *d_tick_tp);
+
+// ---- k_r128.cu ----------------------------------------------------------------------------
+struct R128Result {      // host copies
+    std::vector<double> M, S, sp_cum, tp_cum;   // per tick
+    double I = -70, LRA = 0, LRA_low = 0, LRA_high = 0;
+    int64_t n_ticks = 0;
+};
+void jt_ebur128(jt_ctx *c, const Sig &in, bool dualmono, bool true_peak, R128Result &out);
+struct LoudnormMeter { double I, LRA, thresh, sample_peak; };
+void jt_loudnorm_meter(jt_ctx *c, const Sig &in_f64, bool dual_mono, LoudnormMeter &out);   // libavfilter/ebur128.c
+
+// ---- k_astats.cu --------------------------------------------------------------------------
+struct AstatsResult { double v[JT_AS_COUNT]; double overall_rms, overall_peak; double nb_samples; };
+void jt_astats(jt_ctx *c, const Sig &in, int64_t n_upto, AstatsResult &out);
+
+// ---- k_spectral.cu ------------------------------------------------------------------------
+// rows: n_hops x JT_SP_COUNT floats on the host
+void jt_aspectralstats(jt_ctx *c, const Sig &in_flt, int win_size, std::vector<float> &rows, int64_t &n_hops);
+
+// ---- k_biquad.cu --------------------------------------------------------------------------
+struct BiquadCoef { double b0, b1, b2, a1, a2; };
+BiquadCoef jt_biquad_design(bool highpass, double freq, double q, int rate, bool normalize);
+Sig  jt_biquad(jt_ctx *c, const Sig &in, const BiquadCoef &k, bool tdii, double mix);
+// 17-band batch (K20): per band highpass(lo) -> lowpass(hi) (direct form I) -> sum of squares / peak
+void jt_band_rms_batch(jt_ctx *c, const Sig &in, const double *lo, const double *hi, int n_bands,
+                       double *rms_db, int32_t *found);
+
+// ---- k_anlmdn.cu / k_afftdn.cu ------------------------------------------------------------
+Sig  jt_anlmdn(jt_ctx *c, const Sig &in_flt, double strength, double patch_s, double research_s, double smooth);
+struct AfftdnParams {
+    double nr = 12, nf = -50, rf = -38, ad = 0.5, fo = 1.0, bm = 1.25; int nt = 0; int tn = 0; int gs = 0;
+    bool has_bn = false; double bn[15] = {0};
+};
+Sig  jt_afftdn(jt_ctx *c, const Sig &in_flt, const AfftdnParams &p);
+
+// ---- k_dynamics.cu ------------------------------------------------------------------------
+struct GateParams { double threshold, ratio, attack, release, range, knee, makeup; int detection_rms; };
+struct CompParams { double threshold, ratio, attack, release, makeup, knee, mix; int detection_rms; };
+Sig  jt_agate(jt_ctx *c, const Sig &in_f64, const GateParams &p);
+Sig  jt_acompressor(jt_ctx *c, const Sig &in_f64, const CompParams &p);
+Sig  jt_deesser(jt_ctx *c, const Sig &in_f64, double intensity, double max_amount, double frequency);
+
+// ---- k_alimiter.cu / k_adeclick.cu --------------------------------------------------------
+struct LimiterParams { double limit, attack_ms, release_ms, level_in, level_out; int auto_level, asc, latency; double asc_level; };
+Sig  jt_alimiter(jt_ctx *c, const Sig &in_f64, const LimiterParams &p);
+Sig  jt_adeclick(jt_ctx *c, const Sig &in_f64, double window_ms, double overlap_pct, double ar_pct,
+                 double threshold, double burst_pct, int method_save);
+
+// ---- small helpers ------------------------------------------------------------------------
+double jt_wire(const char *fmt, double v);    // value as Go parses it back from FFmpeg printf
+static inline int jt_grid_for(int64_t work_items, int block, int num_sms, int max_waves = 64) {
+    int64_t g = (work_items + block - 1) / block;
+    int64_t cap = (int64_t)num_sms * max_waves;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}

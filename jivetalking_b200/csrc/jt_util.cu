@@ -1,0 +1,237 @@
+// Context management, device memory, sample-format conversion, downmix, raw frame
+// statistics, volume / gain / pad.  sm_100a.
+#include "jt_internal.h"
+#include "jt_device.cuh"
+#include <cstdio>
+#include <cstring>
+
+// ---------------------------------------------------------------------------------------
+// context / memory / launch bookkeeping
+// ---------------------------------------------------------------------------------------
+void *jt_dalloc_bytes(jt_ctx *c, size_t bytes)
+{
+    void *p = nullptr;
+    bytes = (bytes + 255) & ~size_t(255);
+    cudaError_t e = cudaMallocAsync(&p, bytes, c->stream);
+    if (e != cudaSuccess) JT_THROW(JT_ERR_NOMEM, "cudaMallocAsync(%zu): %s", bytes, cudaGetErrorString(e));
+    c->allocs.push_back(p);
+    return p;
+}
+
+void jt_release_all(jt_ctx *c)
+{
+    for (void *p : c->allocs) cudaFreeAsync(p, c->stream);
+    c->allocs.clear();
+}
+
+void jt_check_cancel(jt_ctx *c)
+{
+    if (c->cancel.load(std::memory_order_relaxed)) JT_THROW(JT_ERR_CANCELLED, "cancelled");
+}
+
+JtLaunch::JtLaunch(jt_ctx *ctx, const char *name, int n) : c(ctx)
+{
+    c->launches += n;
+    if (!c->timing) return;
+    for (size_t i = 0; i < c->slots.size(); i++) if (c->slots[i].name == name) { slot = (int)i; break; }
+    if (slot < 0) { c->slots.push_back(JtTimingSlot{name, 0, 0}); slot = (int)c->slots.size() - 1; }
+    c->slots[slot].launches += n;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    cudaEventRecord(a, c->stream);
+}
+JtLaunch::~JtLaunch()
+{
+    if (slot < 0) return;
+    cudaEventRecord(b, c->stream);
+    c->pending.push_back({a, b, slot});
+}
+void jt_flush_timing(jt_ctx *c)
+{
+    for (auto &p : c->pending) {
+        float ms = 0;
+        cudaEventSynchronize(p.b);
+        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) c->slots[p.slot].ms += ms;
+        cudaEventDestroy(p.a); cudaEventDestroy(p.b);
+    }
+    c->pending.clear();
+}
+
+// ---------------------------------------------------------------------------------------
+// format conversion (libswresample/audioconvert.c CONV_FUNC table)
+// ---------------------------------------------------------------------------------------
+template <class TI, class TO>
+__global__ void k_convert(const TI *__restrict__ in, TO *__restrict__ out, int64_t n)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) out[i] = jt_conv<TI, TO>(in[i]);
+}
+
+template <class TI, class TO>
+static Sig convert_t(jt_ctx *c, const Sig &in, int out_fmt)
+{
+    Sig o = in; o.fmt = out_fmt; o.d = jt_dalloc<TO>(c, in.n);
+    if (in.n > 0) {
+        JtLaunch L(c, "convert");
+        k_convert<TI, TO><<<jt_grid_for(in.n, 256, c->num_sms, 16), 256, 0, c->stream>>>((const TI *)in.d, (TO *)o.d, in.n);
+    }
+    return o;
+}
+
+Sig jt_convert(jt_ctx *c, const Sig &in, int out_fmt)
+{
+    if (in.fmt == out_fmt) return in;
+    switch (in.fmt * 16 + out_fmt) {
+    case JT_FMT_S16 * 16 + JT_FMT_FLT: return convert_t<int16_t, float>(c, in, out_fmt);
+    case JT_FMT_S16 * 16 + JT_FMT_DBL: return convert_t<int16_t, double>(c, in, out_fmt);
+    case JT_FMT_FLT * 16 + JT_FMT_DBL: return convert_t<float, double>(c, in, out_fmt);
+    case JT_FMT_FLT * 16 + JT_FMT_S16: return convert_t<float, int16_t>(c, in, out_fmt);
+    case JT_FMT_DBL * 16 + JT_FMT_FLT: return convert_t<double, float>(c, in, out_fmt);
+    case JT_FMT_DBL * 16 + JT_FMT_S16: return convert_t<double, int16_t>(c, in, out_fmt);
+    }
+    JT_THROW(JT_ERR_UNSUPPORTED, "sample format conversion %d -> %d", in.fmt, out_fmt);
+}
+
+// ---------------------------------------------------------------------------------------
+// aformat=channel_layouts=mono : swr rematrix (libswresample/rematrix.c).  Float formats use
+// 1/sqrt(2) per channel un-normalised, integer formats the normalised 0.5/0.5.
+// ---------------------------------------------------------------------------------------
+__global__ void k_downmix2_f32(const float2 *__restrict__ in, float *__restrict__ out, int64_t n)
+{
+    const float cf = 0.70710678118654752440f;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) { float2 v = in[i]; out[i] = __fadd_rn(__fmul_rn(v.x, cf), __fmul_rn(v.y, cf)); }
+}
+__global__ void k_downmix2_s16(const short2 *__restrict__ in, int16_t *__restrict__ out, int64_t n)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        short2 v = in[i];
+        int s = ((int)v.x * 16384 + (int)v.y * 16384 + 16384) >> 15;
+        out[i] = (int16_t)max(-32768, min(32767, s));
+    }
+}
+
+Sig jt_downmix(jt_ctx *c, const void *d_in, int64_t n, int channels, int fmt, int rate)
+{
+    Sig o; o.fmt = fmt; o.rate = rate; o.n = n;
+    if (fmt != JT_FMT_S16 && fmt != JT_FMT_FLT && fmt != JT_FMT_DBL)
+        JT_THROW(JT_ERR_UNSUPPORTED, "input sample format %d", fmt);
+    if (channels == 1) { o.d = const_cast<void *>(d_in); return o; }
+    if (channels != 2) JT_THROW(JT_ERR_UNSUPPORTED, "downmix from %d channels", channels);
+    if (fmt == JT_FMT_FLT) {
+        o.d = jt_dalloc<float>(c, n);
+        JtLaunch L(c, "downmix");
+        k_downmix2_f32<<<jt_grid_for(n, 256, c->num_sms, 16), 256, 0, c->stream>>>((const float2 *)d_in, (float *)o.d, n);
+    } else if (fmt == JT_FMT_S16) {
+        o.d = jt_dalloc<int16_t>(c, n);
+        JtLaunch L(c, "downmix");
+        k_downmix2_s16<<<jt_grid_for(n, 256, c->num_sms, 16), 256, 0, c->stream>>>((const short2 *)d_in, (int16_t *)o.d, n);
+    } else JT_THROW(JT_ERR_UNSUPPORTED, "stereo f64 downmix");
+    return o;
+}
+
+// ---------------------------------------------------------------------------------------
+// a2: per decoder frame sum of squares / peak over all channels pooled
+// (frameSumSquaresAndPeak, analyser_metrics.go:273-358).  One warp per frame.
+// ---------------------------------------------------------------------------------------
+template <class T>
+__global__ void k_raw_frame_stats(const T *__restrict__ in, int64_t n_total, int per_frame,
+                                  double *__restrict__ sumsq, double *__restrict__ peak, int64_t n_frames)
+{
+    const int warps_per_block = blockDim.x >> 5;
+    int64_t f = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const int64_t fstride = (int64_t)gridDim.x * warps_per_block;
+    for (; f < n_frames; f += fstride) {
+        int64_t s0 = f * (int64_t)per_frame;
+        int64_t s1 = min(s0 + per_frame, n_total);
+        double ss = 0, pk = 0;
+        for (int64_t i = s0 + lane; i < s1; i += 32) {
+            double v = jt_norm_f64(in[i]);
+            ss += v * v;
+            pk = fmax(pk, fabs(v));
+        }
+        for (int o = 16; o; o >>= 1) {
+            ss += __shfl_xor_sync(0xffffffffu, ss, o);
+            pk = fmax(pk, __shfl_xor_sync(0xffffffffu, pk, o));
+        }
+        if (lane == 0) { sumsq[f] = ss; peak[f] = pk; }
+    }
+}
+
+void jt_raw_frame_stats(jt_ctx *c, const void *d_in, int64_t n_frames, int channels, int fmt, int frame_size,
+                        double *d_sumsq, double *d_peak, int64_t n_src_frames)
+{
+    if (n_src_frames <= 0) return;
+    const int64_t n_total = n_frames * channels;
+    const int per = frame_size * channels;
+    const int grid = jt_grid_for(n_src_frames, 8, c->num_sms, 32);
+    JtLaunch L(c, "raw_frame_stats");
+    if (fmt == JT_FMT_S16) k_raw_frame_stats<int16_t><<<grid, 256, 0, c->stream>>>((const int16_t *)d_in, n_total, per, d_sumsq, d_peak, n_src_frames);
+    else if (fmt == JT_FMT_FLT) k_raw_frame_stats<float><<<grid, 256, 0, c->stream>>>((const float *)d_in, n_total, per, d_sumsq, d_peak, n_src_frames);
+    else k_raw_frame_stats<double><<<grid, 256, 0, c->stream>>>((const double *)d_in, n_total, per, d_sumsq, d_peak, n_src_frames);
+}
+
+// ---------------------------------------------------------------------------------------
+// volume (af_volume.c, precision=float: fltp * (float)volume) and loudnorm's linear gain
+// ---------------------------------------------------------------------------------------
+__global__ void k_scale_f32(const float *__restrict__ in, float *__restrict__ out, int64_t n, float g)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) out[i] = __fmul_rn(in[i], g);
+}
+__global__ void k_scale_f64(const double *__restrict__ in, double *__restrict__ out, int64_t n, double g)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) out[i] = __dmul_rn(in[i], g);
+}
+
+Sig jt_volume(jt_ctx *c, const Sig &in0, double volume)
+{
+    Sig in = jt_convert(c, in0, JT_FMT_FLT);
+    Sig o = in; o.d = jt_dalloc<float>(c, in.n);
+    if (in.n > 0) {
+        JtLaunch L(c, "volume");
+        k_scale_f32<<<jt_grid_for(in.n, 256, c->num_sms, 16), 256, 0, c->stream>>>((const float *)in.d, (float *)o.d, in.n, (float)volume);
+    }
+    return o;
+}
+
+Sig jt_gain_f64(jt_ctx *c, const Sig &in0, double gain)
+{
+    Sig in = jt_convert(c, in0, JT_FMT_DBL);
+    Sig o = in; o.d = jt_dalloc<double>(c, in.n);
+    if (in.n > 0) {
+        JtLaunch L(c, "loudnorm_linear_gain");
+        k_scale_f64<<<jt_grid_for(in.n, 256, c->num_sms, 16), 256, 0, c->stream>>>((const double *)in.d, (double *)o.d, in.n, gain);
+    }
+    return o;
+}
+
+Sig jt_slice(const Sig &in, int64_t start, int64_t count)
+{
+    Sig o = in;
+    if (start < 0) start = 0;
+    if (start > in.n) start = in.n;
+    if (count > in.n - start) count = in.n - start;
+    if (count < 0) count = 0;
+    o.n = count;
+    o.d = (char *)in.d + (size_t)start * jt_fmt_bytes(in.fmt);
+    return o;
+}
+
+Sig jt_pad_zero(jt_ctx *c, const Sig &in, int64_t n_total)
+{
+    if (n_total <= in.n) return in;
+    Sig o = in; o.n = n_total;
+    const size_t b = jt_fmt_bytes(in.fmt);
+    o.d = jt_dalloc_bytes(c, (size_t)n_total * b);
+    JT_CUDA(cudaMemcpyAsync(o.d, in.d, (size_t)in.n * b, cudaMemcpyDeviceToDevice, c->stream));
+    JT_CUDA(cudaMemsetAsync((char *)o.d + (size_t)in.n * b, 0, (size_t)(n_total - in.n) * b, c->stream));
+    return o;
+}

@@ -1,0 +1,180 @@
+// highpass / lowpass (libavfilter/af_biquads.c, RBJ cookbook, poles=2, width_type=q) in the
+// link's sample format: "highpass=f=80:poles=2:width_type=q:width=0.707:normalize=1:a=tdii",
+// "lowpass=f=20500:..." (reference: filters.go:740-769) and the 17-band region RMS batch
+// "highpass=f=lo:p=2,lowpass=f=hi:p=2,astats" (reference: analyser_bands.go:33,
+// analyser_noise_bands.go:15-52).
+// A biquad is a linear recurrence whose state decays like r^n (r = pole radius), so the
+// stream is cut into segments, one sequential lane each, started 48 time-constants early
+// from zero state: the result is the sequential one to below the format's rounding.
+#include "jt_internal.h"
+#include "jt_device.cuh"
+#include <cstdio>
+
+BiquadCoef jt_biquad_design(bool highpass, double freq, double q, int rate, bool normalize)
+{
+    const double w0 = 2 * M_PI * freq / rate;
+    const double alpha = sin(w0) / (2 * q);
+    double a0 = 1 + alpha, a1 = -2 * cos(w0), a2 = 1 - alpha, b0, b1, b2;
+    if (highpass) { b0 = (1 + cos(w0)) / 2; b1 = -(1 + cos(w0)); b2 = (1 + cos(w0)) / 2; }
+    else { b0 = (1 - cos(w0)) / 2; b1 = 1 - cos(w0); b2 = (1 - cos(w0)) / 2; }
+    a1 /= a0; a2 /= a0; b0 /= a0; b1 /= a0; b2 /= a0; a0 = 1;
+    if (normalize && fabs(b0 + b1 + b2) > 1e-6) {
+        const double factor = (a0 + a1 + a2) / (b0 + b1 + b2);
+        b0 *= factor; b1 *= factor; b2 *= factor;
+    }
+    return BiquadCoef{b0, b1, b2, a1, a2};
+}
+
+static int biquad_warmup(const BiquadCoef &k)
+{
+    // pole radius: complex pair -> sqrt(a2); real poles -> larger root magnitude
+    double r;
+    const double disc = k.a1 * k.a1 - 4 * k.a2;
+    if (disc < 0) r = sqrt(fabs(k.a2));
+    else r = std::max(fabs((-k.a1 + sqrt(disc)) / 2), fabs((-k.a1 - sqrt(disc)) / 2));
+    if (!(r < 1.0)) return 1 << 20;
+    const double tau = -1.0 / log(std::max(r, 1e-9));
+    double w = 48.0 * tau + 64;
+    if (w < 1024) w = 1024;
+    if (w > (1 << 20)) w = 1 << 20;
+    return (int)w;
+}
+
+template <class F> __device__ __forceinline__ F mul_rn(F a, F b);
+template <> __device__ __forceinline__ float mul_rn<float>(float a, float b) { return __fmul_rn(a, b); }
+template <> __device__ __forceinline__ double mul_rn<double>(double a, double b) { return __dmul_rn(a, b); }
+template <class F> __device__ __forceinline__ F add_rn(F a, F b);
+template <> __device__ __forceinline__ float add_rn<float>(float a, float b) { return __fadd_rn(a, b); }
+template <> __device__ __forceinline__ double add_rn<double>(double a, double b) { return __dadd_rn(a, b); }
+
+template <class T, class F> struct BqIO;
+template <> struct BqIO<float, float> { static __device__ __forceinline__ float out(float v) { return v; } };
+template <> struct BqIO<double, double> { static __device__ __forceinline__ double out(double v) { return v; } };
+template <> struct BqIO<int16_t, float> {       // need_clipping path: clamp, then C float->int16 conversion (truncation)
+    static __device__ __forceinline__ int16_t out(float v) { if (v < -32768.f) return -32768; if (v > 32767.f) return 32767; return (int16_t)(int)v; }
+};
+
+template <class F> struct BqState { F s0 = 0, s1 = 0, s2 = 0, s3 = 0; };
+
+// one step; TDII: state (w1,w2).  DI: state (i1,i2,o1,o2).  Unfused mul/add = the C code
+template <class F, bool TDII>
+__device__ __forceinline__ F bq_step(BqState<F> &s, F in, F b0, F b1, F b2, F na1, F na2, F wet, F dry)
+{
+    F out;
+    if (TDII) {
+        out = add_rn(mul_rn(b0, in), s.s0);
+        s.s0 = add_rn(add_rn(mul_rn(b1, in), s.s1), mul_rn(na1, out));
+        s.s1 = add_rn(mul_rn(b2, in), mul_rn(na2, out));
+    } else {
+        out = add_rn(add_rn(add_rn(add_rn(mul_rn(s.s1, b2), mul_rn(s.s0, b1)), mul_rn(in, b0)), mul_rn(s.s3, na2)), mul_rn(s.s2, na1));
+        s.s1 = s.s0; s.s0 = in; s.s3 = s.s2; s.s2 = out;
+    }
+    return add_rn(mul_rn(out, wet), mul_rn(in, dry));
+}
+
+template <class T, class F, bool TDII>
+__global__ void __launch_bounds__(64)
+k_biquad(const T *__restrict__ x, T *__restrict__ y, int64_t n, int seg, int warm,
+         F b0, F b1, F b2, F na1, F na2, F wet, F dry)
+{
+    const int64_t lane = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t s0 = lane * seg; if (s0 >= n) return;
+    const int64_t s1 = min(s0 + (int64_t)seg, n);
+    BqState<F> st;
+    int64_t i = max((int64_t)0, s0 - warm);
+    for (; i < s0; i++) (void)bq_step<F, TDII>(st, (F)x[i], b0, b1, b2, na1, na2, wet, dry);
+#pragma unroll 4
+    for (; i < s1; i++) y[i] = BqIO<T, F>::out(bq_step<F, TDII>(st, (F)x[i], b0, b1, b2, na1, na2, wet, dry));
+}
+
+template <class T, class F>
+static void launch_biquad(jt_ctx *c, const Sig &in, Sig &o, const BiquadCoef &k, bool tdii, double mix)
+{
+    const int seg = 8192, warm = biquad_warmup(k);
+    const int64_t lanes = (in.n + seg - 1) / seg;
+    const int grid = (int)((lanes + 63) / 64);
+    const F wet = (F)mix, dry = (F)(1. - wet);
+    JtLaunch L(c, "biquad");
+    if (tdii) k_biquad<T, F, true><<<grid, 64, 0, c->stream>>>((const T *)in.d, (T *)o.d, in.n, seg, warm, (F)k.b0, (F)k.b1, (F)k.b2, (F)-k.a1, (F)-k.a2, wet, dry);
+    else k_biquad<T, F, false><<<grid, 64, 0, c->stream>>>((const T *)in.d, (T *)o.d, in.n, seg, warm, (F)k.b0, (F)k.b1, (F)k.b2, (F)-k.a1, (F)-k.a2, wet, dry);
+}
+
+Sig jt_biquad(jt_ctx *c, const Sig &in, const BiquadCoef &k, bool tdii, double mix)
+{
+    Sig o = in; o.d = jt_dalloc_bytes(c, (size_t)std::max<int64_t>(in.n, 1) * jt_fmt_bytes(in.fmt));
+    if (in.n <= 0) return o;
+    if (in.fmt == JT_FMT_FLT) launch_biquad<float, float>(c, in, o, k, tdii, mix);
+    else if (in.fmt == JT_FMT_DBL) launch_biquad<double, double>(c, in, o, k, tdii, mix);
+    else if (in.fmt == JT_FMT_S16) launch_biquad<int16_t, float>(c, in, o, k, tdii, mix);
+    else JT_THROW(JT_ERR_UNSUPPORTED, "biquad on sample format %d", in.fmt);
+    return o;
+}
+
+// ---------------------------------------------------------------------------------------
+// K20: all bands x all segments in one launch.  lane = (band, segment); highpass(lo) then
+// lowpass(hi), both direct form I in the link format, then astats' sum of squares.
+// ---------------------------------------------------------------------------------------
+struct BandCoef { float hb0, hb1, hb2, hna1, hna2, lb0, lb1, lb2, lna1, lna2; double dh[5], dl[5]; };
+
+template <class T, class F>
+__global__ void __launch_bounds__(64)
+k_band_rms(const T *__restrict__ x, int64_t n, int seg, int warm, int64_t segs_per_band, int n_bands,
+           const BandCoef *__restrict__ coef, double *__restrict__ sumsq /* n_bands */)
+{
+    const int64_t lane = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double acc = 0;
+    const int band = (int)(lane / segs_per_band);
+    if (band < n_bands) {
+        const int64_t s0 = (lane % segs_per_band) * seg, s1 = min(s0 + (int64_t)seg, n);
+        const BandCoef k = coef[band];
+        F hb0, hb1, hb2, hna1, hna2, lb0, lb1, lb2, lna1, lna2;
+        if (sizeof(F) == 4) { hb0 = k.hb0; hb1 = k.hb1; hb2 = k.hb2; hna1 = k.hna1; hna2 = k.hna2; lb0 = k.lb0; lb1 = k.lb1; lb2 = k.lb2; lna1 = k.lna1; lna2 = k.lna2; }
+        else { hb0 = (F)k.dh[0]; hb1 = (F)k.dh[1]; hb2 = (F)k.dh[2]; hna1 = (F)k.dh[3]; hna2 = (F)k.dh[4]; lb0 = (F)k.dl[0]; lb1 = (F)k.dl[1]; lb2 = (F)k.dl[2]; lna1 = (F)k.dl[3]; lna2 = (F)k.dl[4]; }
+        BqState<F> sh, sl;
+        for (int64_t i = max((int64_t)0, s0 - warm); i < s1; i++) {
+            const T h = BqIO<T, F>::out(bq_step<F, false>(sh, (F)x[i], hb0, hb1, hb2, hna1, hna2, (F)1, (F)0));
+            const T l = BqIO<T, F>::out(bq_step<F, false>(sl, (F)h, lb0, lb1, lb2, lna1, lna2, (F)1, (F)0));
+            if (i >= s0) {
+                const double nd = sizeof(T) == 2 ? (double)l / 32767.0 : (double)l;
+                acc = fma(nd, nd, acc);
+            }
+        }
+    }
+    // lanes of one warp may straddle two bands only at band boundaries; add per lane
+    if (band < n_bands && acc != 0) atomicAdd(&sumsq[band], acc);
+}
+
+void jt_band_rms_batch(jt_ctx *c, const Sig &in, const double *lo, const double *hi, int n_bands, double *rms_db, int32_t *found)
+{
+    for (int b = 0; b < n_bands; b++) { rms_db[b] = 0; found[b] = 0; }
+    if (in.n <= 0) return;
+    std::vector<BandCoef> hc(n_bands);
+    int warm = 1024;
+    for (int b = 0; b < n_bands; b++) {
+        BiquadCoef h = jt_biquad_design(true, lo[b], 0.707, in.rate, false), l = jt_biquad_design(false, hi[b], 0.707, in.rate, false);
+        BandCoef &k = hc[b];
+        k.hb0 = (float)h.b0; k.hb1 = (float)h.b1; k.hb2 = (float)h.b2; k.hna1 = (float)-h.a1; k.hna2 = (float)-h.a2;
+        k.lb0 = (float)l.b0; k.lb1 = (float)l.b1; k.lb2 = (float)l.b2; k.lna1 = (float)-l.a1; k.lna2 = (float)-l.a2;
+        k.dh[0] = h.b0; k.dh[1] = h.b1; k.dh[2] = h.b2; k.dh[3] = -h.a1; k.dh[4] = -h.a2;
+        k.dl[0] = l.b0; k.dl[1] = l.b1; k.dl[2] = l.b2; k.dl[3] = -l.a1; k.dl[4] = -l.a2;
+        warm = std::max(warm, std::min(std::max(biquad_warmup(h), biquad_warmup(l)), 1 << 16));
+    }
+    BandCoef *d_coef = jt_dalloc<BandCoef>(c, n_bands);
+    double *d_sum = jt_dalloc<double>(c, n_bands);
+    JT_CUDA(cudaMemcpyAsync(d_coef, hc.data(), sizeof(BandCoef) * n_bands, cudaMemcpyHostToDevice, c->stream));
+    JT_CUDA(cudaMemsetAsync(d_sum, 0, sizeof(double) * n_bands, c->stream));
+    const int seg = 4096;
+    const int64_t spb = (in.n + seg - 1) / seg, lanes = spb * n_bands;
+    const int grid = (int)((lanes + 63) / 64);
+    {
+        JtLaunch L(c, "band_rms");
+        if (in.fmt == JT_FMT_FLT) k_band_rms<float, float><<<grid, 64, 0, c->stream>>>((const float *)in.d, in.n, seg, warm, spb, n_bands, d_coef, d_sum);
+        else if (in.fmt == JT_FMT_DBL) k_band_rms<double, double><<<grid, 64, 0, c->stream>>>((const double *)in.d, in.n, seg, warm, spb, n_bands, d_coef, d_sum);
+        else if (in.fmt == JT_FMT_S16) k_band_rms<int16_t, float><<<grid, 64, 0, c->stream>>>((const int16_t *)in.d, in.n, seg, warm, spb, n_bands, d_coef, d_sum);
+        else JT_THROW(JT_ERR_UNSUPPORTED, "band rms on sample format %d", in.fmt);
+    }
+    std::vector<double> hs(n_bands);
+    JT_CUDA(cudaMemcpyAsync(hs.data(), d_sum, sizeof(double) * n_bands, cudaMemcpyDeviceToHost, c->stream));
+    JT_CUDA(cudaStreamSynchronize(c->stream));
+    for (int b = 0; b < n_bands; b++) { rms_db[b] = jt_wire("%f", log10(sqrt(hs[b] / (double)in.n)) * 20); found[b] = 1; }
+}

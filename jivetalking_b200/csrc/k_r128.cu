@@ -1,0 +1,250 @@
+// BS.1770 meters.
+//   jt_ebur128        : FFmpeg's ebur128 filter (libavfilter/f_ebur128.c) as instantiated by
+//                       "ebur128=metadata=1:peak=sample+true:dualmono=true" (reference:
+//                       internal/processor/filters.go:626, analyser_output.go:18)
+//   jt_loudnorm_meter : the libebur128 port loudnorm uses (libavfilter/ebur128.c) for its
+//                       input_i / input_tp / input_lra / input_thresh (reference:
+//                       internal/processor/normalise.go:257-264,328-343)
+// Device: K-weighting + 100 ms mean-square / sample-peak partials, one sequential lane per
+// group of ticks with a 200 ms warm-up (the RLB high-pass forgets its state to < 1e-19 in
+// that time); true peak via k_swr.cu.  Host: windowing, gating, histograms, LRA on the
+// ~10 values per second the device produced (same split as the reference: FFmpeg emits
+// values, Go accumulates them).
+#include "jt_internal.h"
+#include "jt_device.cuh"
+#include <algorithm>
+#include <cstdio>
+
+struct KWeight { double pb0, pb1, pb2, pa1, pa2, rb0, rb1, rb2, ra1, ra2; double b[5], a[5]; };
+
+static KWeight kweight_design(int rate)
+{
+    KWeight k;
+    double f0 = 1681.974450955533, G = 3.999843853973347, Q = 0.7071752369554196;
+    double K = tan(M_PI * f0 / (double)rate);
+    double Vh = pow(10.0, G / 20.0), Vb = pow(Vh, 0.4996667741545416);
+    double a0 = 1.0 + K / Q + K * K;
+    k.pb0 = (Vh + Vb * K / Q + K * K) / a0;
+    k.pb1 = 2.0 * (K * K - Vh) / a0;
+    k.pb2 = (Vh - Vb * K / Q + K * K) / a0;
+    k.pa1 = 2.0 * (K * K - 1.0) / a0;
+    k.pa2 = (1.0 - K / Q + K * K) / a0;
+    f0 = 38.13547087602444; Q = 0.5003270373238773;
+    K = tan(M_PI * f0 / (double)rate);
+    k.rb0 = 1.0; k.rb1 = -2.0; k.rb2 = 1.0;
+    k.ra1 = 2.0 * (K * K - 1.0) / (1.0 + K / Q + K * K);
+    k.ra2 = (1.0 - K / Q + K * K) / (1.0 + K / Q + K * K);
+    const double pb[3] = {k.pb0, k.pb1, k.pb2}, pa[3] = {1.0, k.pa1, k.pa2};
+    const double rb[3] = {1.0, -2.0, 1.0}, ra[3] = {1.0, k.ra1, k.ra2};
+    k.b[0] = pb[0] * rb[0];
+    k.b[1] = pb[0] * rb[1] + pb[1] * rb[0];
+    k.b[2] = pb[0] * rb[2] + pb[1] * rb[1] + pb[2] * rb[0];
+    k.b[3] = pb[1] * rb[2] + pb[2] * rb[1];
+    k.b[4] = pb[2] * rb[2];
+    k.a[0] = pa[0] * ra[0];
+    k.a[1] = pa[0] * ra[1] + pa[1] * ra[0];
+    k.a[2] = pa[0] * ra[2] + pa[1] * ra[1] + pa[2] * ra[0];
+    k.a[3] = pa[1] * ra[2] + pa[2] * ra[1];
+    k.a[4] = pa[2] * ra[2];
+    return k;
+}
+
+// One lane = G consecutive ticks (plus WU warm-up ticks).  STRUCT 0: cascade of two direct
+// form I biquads (f_ebur128.c FILTER macro); STRUCT 1: 4th-order direct form II (ebur128.c).
+template <class TIN, int STRUCT>
+__global__ void __launch_bounds__(64)
+k_r128_ticks(const TIN *__restrict__ x, int64_t n, int tick, int64_t n_ticks_total, int G, int WU,
+             const __grid_constant__ KWeight kw, double *__restrict__ tick_pow, double *__restrict__ tick_peak)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t k0 = t * G;
+    if (k0 >= n_ticks_total) return;
+    const int64_t k1 = min(k0 + (int64_t)G, n_ticks_total);
+    int64_t i = max((int64_t)0, (k0 - WU) * (int64_t)tick);
+    double x1 = 0, x2 = 0, y1 = 0, y2 = 0, z1 = 0, z2 = 0;      // STRUCT 0
+    double v1 = 0, v2 = 0, v3 = 0, v4 = 0;                        // STRUCT 1
+    auto step = [&](double x0) -> double {
+        if (STRUCT == 0) {
+            double y0 = x0 * kw.pb0 + x1 * kw.pb1 + x2 * kw.pb2 - y1 * kw.pa1 - y2 * kw.pa2;
+            x2 = x1; x1 = x0;
+            double z0 = y0 * kw.rb0 + y1 * kw.rb1 + y2 * kw.rb2 - z1 * kw.ra1 - z2 * kw.ra2;
+            y2 = y1; y1 = y0; z2 = z1; z1 = z0;
+            return z0;
+        } else {
+            double v0 = x0 - kw.a[1] * v1 - kw.a[2] * v2 - kw.a[3] * v3 - kw.a[4] * v4;
+            double o = kw.b[0] * v0 + kw.b[1] * v1 + kw.b[2] * v2 + kw.b[3] * v3 + kw.b[4] * v4;
+            v4 = v3; v3 = v2; v2 = v1; v1 = v0;
+            return o;
+        }
+    };
+    const int64_t warm_end = k0 * (int64_t)tick;
+#pragma unroll 4
+    for (; i < warm_end; i++) (void)step(jt_as_f64(__ldg(x + i)));
+    for (int64_t k = k0; k < k1; k++) {
+        const int64_t e = min((k + 1) * (int64_t)tick, n);
+        double acc = 0.0, pk = 0.0;
+#pragma unroll 4
+        for (; i < e; i++) {
+            const double x0 = jt_as_f64(__ldg(x + i));
+            const double z = step(x0);
+            acc = fma(z, z, acc);
+            pk = fmax(pk, fabs(x0));
+        }
+        tick_pow[k] = acc;
+        tick_peak[k] = pk;
+    }
+}
+
+template <int STRUCT>
+static void run_ticks(jt_ctx *c, const Sig &in, int tick, int64_t n_ticks_total, const KWeight &kw,
+                      double *d_pow, double *d_peak)
+{
+    if (n_ticks_total <= 0) return;
+    const int G = 2, WU = 2;
+    const int64_t lanes = (n_ticks_total + G - 1) / G;
+    const int grid = (int)((lanes + 63) / 64);
+    JtLaunch L(c, "r128_kweight_ticks");
+    if (in.fmt == JT_FMT_S16) k_r128_ticks<int16_t, STRUCT><<<grid, 64, 0, c->stream>>>((const int16_t *)in.d, in.n, tick, n_ticks_total, G, WU, kw, d_pow, d_peak);
+    else if (in.fmt == JT_FMT_FLT) k_r128_ticks<float, STRUCT><<<grid, 64, 0, c->stream>>>((const float *)in.d, in.n, tick, n_ticks_total, G, WU, kw, d_pow, d_peak);
+    else k_r128_ticks<double, STRUCT><<<grid, 64, 0, c->stream>>>((const double *)in.d, in.n, tick, n_ticks_total, G, WU, kw, d_pow, d_peak);
+}
+
+// ---------------------------------------------------------------------------------------
+// ebur128 filter
+// ---------------------------------------------------------------------------------------
+#define ABS_THRES (-70)
+#define HIST_RES 100
+#define HIST_SIZE ((10 - ABS_THRES) * HIST_RES + 1)
+static inline double loudness_of(double e) { return -0.691 + 10 * log10(e); }
+static inline int hist_pos(double l) { int p = (int)((l - ABS_THRES) * HIST_RES); return p < 0 ? 0 : p > HIST_SIZE - 1 ? HIST_SIZE - 1 : p; }
+
+void jt_ebur128(jt_ctx *c, const Sig &in, bool dualmono, bool true_peak, R128Result &out)
+{
+    if (in.rate % 10) JT_THROW(JT_ERR_UNSUPPORTED, "ebur128 at %d Hz (rate must be a multiple of 10)", in.rate);
+    const int tick = in.rate / 10;
+    const int64_t nt = in.n / tick;
+    out = R128Result();
+    out.n_ticks = nt;
+    if (nt <= 0) return;
+    double *d_pow = jt_dalloc<double>(c, nt), *d_peak = jt_dalloc<double>(c, nt), *d_tp = jt_dalloc<double>(c, nt);
+    KWeight kw = kweight_design(in.rate);
+    run_ticks<0>(c, in, tick, nt, kw, d_pow, d_peak);
+    if (true_peak) {
+        if (in.rate == 192000) JT_CUDA(cudaMemcpyAsync(d_tp, d_peak, sizeof(double) * nt, cudaMemcpyDeviceToDevice, c->stream));
+        else { SwrPlan p = jt_swr_plan(in.rate, 192000); jt_swr_tick_absmax(c, in, p, tick, nt, d_tp); }
+    }
+    std::vector<double> hp(nt), hk(nt), ht(nt, 0.0);
+    JT_CUDA(cudaMemcpyAsync(hp.data(), d_pow, sizeof(double) * nt, cudaMemcpyDeviceToHost, c->stream));
+    JT_CUDA(cudaMemcpyAsync(hk.data(), d_peak, sizeof(double) * nt, cudaMemcpyDeviceToHost, c->stream));
+    if (true_peak) JT_CUDA(cudaMemcpyAsync(ht.data(), d_tp, sizeof(double) * nt, cudaMemcpyDeviceToHost, c->stream));
+    JT_CUDA(cudaStreamSynchronize(c->stream));
+
+    // host: f_ebur128.c filter_frame() tail, once per 100 ms
+    out.M.resize(nt); out.S.resize(nt); out.sp_cum.resize(nt); out.tp_cum.resize(nt);
+    std::vector<uint32_t> h400(HIST_SIZE, 0), h3000(HIST_SIZE, 0);
+    double kept400 = 0, kept3000 = 0; uint64_t nk400 = 0, nk3000 = 0;
+    double rel400 = 0, rel3000 = 0; bool any400 = false, any3000 = false;
+    const double pan_law = -3.01029995663978;
+    double sp = 0, tp = 0, w400 = 0, w3000 = 0;
+    for (int64_t k = 0; k < nt; k++) {
+        sp = std::max(sp, hk[k]); tp = std::max(tp, ht[k]);
+        out.sp_cum[k] = sp; out.tp_cum[k] = tp;
+        w400 += hp[k]; if (k >= 4) w400 -= hp[k - 4];
+        w3000 += hp[k]; if (k >= 30) w3000 -= hp[k - 30];
+        double p400 = 1e-12, p3000 = 1e-12;
+        if (k >= 3) { double s = 0; for (int j = 3; j >= 0; j--) s += hp[k - j]; p400 = (p400 + s) / (4.0 * tick); }
+        if (k >= 29) { double s = 0; for (int j = 29; j >= 0; j--) s += hp[k - j]; p3000 = (p3000 + s) / (30.0 * tick); }
+        double l400 = loudness_of(p400), l3000 = loudness_of(p3000);
+        if (l400 >= ABS_THRES) {
+            h400[hist_pos(l400)]++; kept400 += p400; nk400++;
+            double rt = kept400 / nk400; if (!rt) rt = 1e-12;
+            rel400 = loudness_of(rt) - 10; any400 = true;
+        }
+        if (l3000 >= ABS_THRES) {
+            h3000[hist_pos(l3000)]++; kept3000 += p3000; nk3000++;
+            double rt = kept3000 / nk3000; if (!rt) rt = 1e-12;
+            rel3000 = loudness_of(rt) - 20; any3000 = true;
+        }
+        if (dualmono) { l400 -= pan_law; l3000 -= pan_law; }
+        out.M[k] = l400; out.S[k] = l3000;
+    }
+    (void)w400; (void)w3000;
+    if (any400) {
+        double isum = 0; uint64_t nb = 0;
+        for (int i = hist_pos(rel400); i < HIST_SIZE; i++) {
+            const double loud = i / (double)HIST_RES + ABS_THRES;
+            nb += h400[i]; isum += h400[i] * exp2(3.32192809488736234787 * ((loud + 0.691) / 10.));
+        }
+        if (nb) { out.I = loudness_of(isum / nb); if (dualmono) out.I -= pan_law; }
+    }
+    if (any3000) {
+        uint64_t nb_powers = 0; const int pos = hist_pos(rel3000);
+        for (int i = pos; i < HIST_SIZE; i++) nb_powers += h3000[i];
+        if (nb_powers) {
+            uint64_t nn = 0, nb_pow = (uint64_t)(10 * nb_powers * 0.01 + 0.5);
+            for (int i = pos; i < HIST_SIZE; i++) { nn += h3000[i]; if (nn >= nb_pow) { out.LRA_low = i / (double)HIST_RES + ABS_THRES; break; } }
+            nn = nb_powers; nb_pow = (uint64_t)(95 * nb_powers * 0.01 + 0.5);
+            for (int i = HIST_SIZE - 1; i >= 0; i--) {
+                uint64_t cc = h3000[i]; nn -= std::min(nn, cc);
+                if (nn < nb_pow) { out.LRA_high = i / (double)HIST_RES + ABS_THRES; break; }
+            }
+            out.LRA = out.LRA_high - out.LRA_low;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// loudnorm's meter: libavfilter/ebur128.c (libebur128 port), block-list gating
+// ---------------------------------------------------------------------------------------
+void jt_loudnorm_meter(jt_ctx *c, const Sig &in0, bool dual_mono, LoudnormMeter &out)
+{
+    Sig in = in0;
+    const int s100 = (in.rate + 5) / 10;
+    const int64_t nfull = in.n / s100;
+    const int64_t nt = (in.n + s100 - 1) / s100;            // last partial tick only feeds the sample peak
+    out.I = -HUGE_VAL; out.LRA = 0; out.thresh = -70.0; out.sample_peak = 0;
+    if (nt <= 0) return;
+    double *d_pow = jt_dalloc<double>(c, nt), *d_peak = jt_dalloc<double>(c, nt);
+    KWeight kw = kweight_design(in.rate);
+    run_ticks<1>(c, in, s100, nt, kw, d_pow, d_peak);
+    std::vector<double> hp(nt), hk(nt);
+    JT_CUDA(cudaMemcpyAsync(hp.data(), d_pow, sizeof(double) * nt, cudaMemcpyDeviceToHost, c->stream));
+    JT_CUDA(cudaMemcpyAsync(hk.data(), d_peak, sizeof(double) * nt, cudaMemcpyDeviceToHost, c->stream));
+    JT_CUDA(cudaStreamSynchronize(c->stream));
+    for (int64_t k = 0; k < nt; k++) out.sample_peak = std::max(out.sample_peak, hk[k]);
+
+    const double wgt = dual_mono ? 2.0 : 1.0;
+    const double abs_thr = pow(10.0, (-70.0 + 0.691) / 10.0);
+    // gating blocks: 400 ms every 100 ms
+    double sum = 0; uint64_t cnt = 0;
+    std::vector<double> blocks; blocks.reserve(nfull);
+    for (int64_t k = 3; k < nfull; k++) {
+        double e = wgt * (hp[k - 3] + hp[k - 2] + hp[k - 1] + hp[k]) / (4.0 * s100);
+        if (e >= abs_thr) { blocks.push_back(e); sum += e; cnt++; }
+    }
+    if (cnt) {
+        double rel = sum / cnt * 0.1;            // RELATIVE_GATE_FACTOR = 10^(-10/10)
+        out.thresh = 10 * log10(rel) - 0.691;
+        double g = 0; uint64_t gc = 0;
+        for (double e : blocks) if (e >= rel) { g += e; gc++; }
+        out.I = gc ? 10 * log10(g / gc) - 0.691 : -HUGE_VAL;
+    }
+    // short-term blocks: 3 s, first at 3 s then every 1 s (short_term_frame_counter 30 -> 20)
+    std::vector<double> st;
+    for (int64_t k = 29; k < nfull; k += 10) {
+        double s = 0; for (int j = 29; j >= 0; j--) s += hp[k - j];
+        double e = wgt * s / (30.0 * s100);
+        if (e >= abs_thr) st.push_back(e);
+    }
+    if (!st.empty()) {
+        std::sort(st.begin(), st.end());
+        double p = 0; for (double e : st) p += e; p /= st.size();
+        const double integ = 0.01 * p;              // -20 LU
+        size_t first = 0; while (first < st.size() && st[first] < integ) first++;
+        const size_t sz = st.size() - first;
+        if (sz) {
+            double h = st[first + (size_t)((sz - 1) * 0.95 + 0.5)], l = st[first + (size_t)((sz - 1) * 0.1 + 0.5)];
+            out.LRA = (10 * log10(h) - 0.691) - (10 * log10(l) - 0.691);
+        }
+    }
+}

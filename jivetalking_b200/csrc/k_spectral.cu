@@ -1,0 +1,199 @@
+// aspectralstats (libavfilter/af_aspectralstats.c): win 2048, hann, hop 1024, 13 statistics per
+// hop in float32 ("aspectralstats=win_size=2048:win_func=hann:measure=all", reference:
+// filters.go:625; formulas docs/Spectral-Metrics-Reference.md:9-33).
+// One CTA per hop: the 2048-point window is staged in shared memory, transformed by an
+// in-place radix-2 FFT (twiddles from a read-only table), the 1024 magnitudes are reduced
+// with warp shuffles.  Flux needs the previous hop's magnitudes, so magnitudes go to HBM
+// once and a second tiny kernel forms the differences.
+#include "jt_internal.h"
+#include "jt_device.cuh"
+#include <cfloat>
+
+#define SP_THREADS 256
+
+template <int K> __device__ __forceinline__ void block_sum(float (&v)[K], float (*red)[K])
+{
+#pragma unroll
+    for (int k = 0; k < K; k++) v[k] = jt_warp_sum(v[k]);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < K; k++) red[w][k] = v[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        float s = 0;
+        for (int i = 0; i < SP_THREADS / 32; i++) s += red[i][k];
+        v[k] = s;
+    }
+}
+
+__global__ void __launch_bounds__(SP_THREADS)
+k_spectral(const float *__restrict__ x, int64_t n, int win, int rate, int64_t n_hops,
+           const float2 *__restrict__ tw, const float *__restrict__ lut,
+           float *__restrict__ mags, float *__restrict__ rows)
+{
+    extern __shared__ float2 sbuf[];                 // win complex
+    __shared__ float red[SP_THREADS / 32][8];
+    __shared__ float s_scan[SP_THREADS / 32];
+    __shared__ int s_idx;
+    const int hop = win / 2, size = win / 2;
+    int logn = 0; while ((1 << logn) < win) logn++;
+    for (int64_t h = blockIdx.x; h < n_hops; h += gridDim.x) {
+        const int64_t w0 = (h - 1) * (int64_t)hop;  // window start sample
+        __syncthreads();
+        for (int i = threadIdx.x; i < win; i += SP_THREADS) {
+            const int64_t s = w0 + i;
+            const float v = (s >= 0 && s < n) ? __fmul_rn(x[s], lut[i]) : 0.f;
+            sbuf[__brev((unsigned)i) >> (32 - logn)] = make_float2(v, 0.f);
+        }
+        __syncthreads();
+        for (int len = 2; len <= win; len <<= 1) {
+            const int half = len >> 1, tstep = win / len;
+            for (int b = threadIdx.x; b < win / 2; b += SP_THREADS) {
+                const int k = b & (half - 1), i = ((b - k) << 1) + k;
+                const float2 w = tw[k * tstep];
+                const float2 a = sbuf[i], bb = sbuf[i + half];
+                const float tr = __fsub_rn(__fmul_rn(bb.x, w.x), __fmul_rn(bb.y, w.y));
+                const float ti = __fadd_rn(__fmul_rn(bb.x, w.y), __fmul_rn(bb.y, w.x));
+                sbuf[i] = make_float2(a.x + tr, a.y + ti);
+                sbuf[i + half] = make_float2(a.x - tr, a.y - ti);
+            }
+            __syncthreads();
+        }
+        // magnitudes of the lower half, pre-scaled by 1/win
+        const float wscale = 1.f / win;
+        float *smag = (float *)sbuf;                 // reuse: write after all reads of this thread's bins
+        float m[4];
+        const int per = size / SP_THREADS;           // 4 for win 2048
+        float2 c4[4];
+        for (int j = 0; j < per; j++) c4[j] = sbuf[threadIdx.x * per + j];
+        __syncthreads();
+        for (int j = 0; j < per; j++) {
+            m[j] = hypotf(__fmul_rn(c4[j].x, wscale), __fmul_rn(c4[j].y, wscale));
+            smag[threadIdx.x * per + j] = m[j];
+            mags[h * (int64_t)size + threadIdx.x * per + j] = m[j];
+        }
+        __syncthreads();
+        const float mag0 = smag[0];
+        const float scale = (rate / 2) / (float)size;
+        const float mean_freq = size * 0.5f;
+        // pass 1
+        float r1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        float mx = 0.f;
+        for (int j = 0; j < per; j++) {
+            const int nn = threadIdx.x * per + j; const float v = m[j];
+            r1[0] += v;                                   // sum
+            r1[1] += v * nn * scale;                      // centroid num
+            r1[2] += v * logf(v + FLT_EPSILON);           // entropy num
+            const float ve = FLT_EPSILON + v;
+            r1[3] += logf(ve);                            // flatness log-sum
+            r1[4] += ve;                                  // flatness den
+            if (nn >= 1) { r1[5] += (v - mag0) / nn; r1[6] += v; }   // decrease
+            const float q = (nn - mean_freq) / mean_freq; r1[7] += q * q;   // slope den
+            mx = fmaxf(mx, v);
+        }
+        block_sum<8>(r1, red);
+        mx = jt_warp_max(mx);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) s_scan[threadIdx.x >> 5] = mx;
+        __syncthreads();
+        mx = 0.f; for (int i = 0; i < SP_THREADS / 32; i++) mx = fmaxf(mx, s_scan[i]);
+        const float sum = r1[0], mean = sum / size;
+        const float centroid = sum <= FLT_EPSILON ? 1.f : r1[1] / sum;
+        // pass 2
+        float r2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int j = 0; j < per; j++) {
+            const int nn = threadIdx.x * per + j; const float v = m[j];
+            const float dm = v - mean; r2[0] += dm * dm;                 // variance
+            const float df = nn * scale - centroid, df2 = df * df;
+            r2[1] += v * df2; r2[2] += v * (df2 * df); r2[3] += v * (df2 * df2);
+            r2[4] += ((nn - mean_freq) / mean_freq) * dm;               // slope num
+        }
+        block_sum<8>(r2, red);
+        // rolloff: first bin where the running sum reaches 85 % of the total
+        float run = m[0]; float loc[4]; loc[0] = run;
+        for (int j = 1; j < per; j++) { run += m[j]; loc[j] = run; }
+        float incl = run;                                  // warp inclusive scan of per-thread totals
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        for (int o = 1; o < 32; o <<= 1) { float t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        __syncthreads();
+        if (lane == 31) s_scan[wid] = incl;
+        if (threadIdx.x == 0) s_idx = 0x7fffffff;
+        __syncthreads();
+        float woff = 0; for (int i = 0; i < wid; i++) woff += s_scan[i];
+        const float excl = woff + incl - run;
+        const float norm = sum * 0.85f;
+        int first = 0x7fffffff;
+        for (int j = per - 1; j >= 0; j--) if (excl + loc[j] >= norm) first = threadIdx.x * per + j;
+        if (first != 0x7fffffff) atomicMin(&s_idx, first);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float *r = rows + h * JT_SP_COUNT;
+            const float spread = sum <= FLT_EPSILON ? 1.f : sqrtf(r2[1] / sum);
+            r[JT_SP_mean] = mean;
+            r[JT_SP_variance] = r2[0] / size;
+            r[JT_SP_centroid] = centroid;
+            r[JT_SP_spread] = spread;
+            float den = sum * (spread * spread * spread);
+            r[JT_SP_skewness] = den <= FLT_EPSILON ? 1.f : r2[2] / den;
+            den = sum * ((spread * spread) * (spread * spread));
+            r[JT_SP_kurtosis] = den <= FLT_EPSILON ? 1.f : r2[3] / den;
+            den = logf((float)size);
+            r[JT_SP_entropy] = den <= FLT_EPSILON ? 1.f : -r1[2] / den;
+            { float num = expf(r1[3] / size), d2 = r1[4] / size; r[JT_SP_flatness] = d2 <= FLT_EPSILON ? 0.f : num / d2; }
+            r[JT_SP_crest] = mean <= FLT_EPSILON ? 0.f : mx / mean;
+            r[JT_SP_flux] = 0.f;                          // second kernel
+            r[JT_SP_slope] = fabsf(r1[7]) <= FLT_EPSILON ? 0.f : r2[4] / r1[7];
+            r[JT_SP_decrease] = r1[6] <= FLT_EPSILON ? 0.f : r1[5] / r1[6];
+            r[JT_SP_rolloff] = scale * (s_idx == 0x7fffffff ? 0 : s_idx);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_spectral_flux(const float *__restrict__ mags, int size, int64_t n_hops, float *__restrict__ rows)
+{
+    __shared__ float sw[8];
+    for (int64_t h = blockIdx.x; h < n_hops; h += gridDim.x) {
+        float s = 0;
+        for (int i = threadIdx.x; i < size; i += 256) {
+            const float a = mags[h * size + i], b = h > 0 ? mags[(h - 1) * size + i] : 0.f;
+            const float d = a - b; s += d * d;
+        }
+        s = jt_warp_sum(s);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) sw[threadIdx.x >> 5] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) { float t = 0; for (int i = 0; i < 8; i++) t += sw[i]; rows[h * JT_SP_COUNT + JT_SP_flux] = sqrtf(t); }
+    }
+}
+
+void jt_aspectralstats(jt_ctx *c, const Sig &in0, int win, std::vector<float> &rows, int64_t &n_hops)
+{
+    Sig in = jt_convert(c, in0, JT_FMT_FLT);
+    const int hop = win / 2;
+    n_hops = (in.n + hop - 1) / hop;
+    rows.assign((size_t)std::max<int64_t>(n_hops, 0) * JT_SP_COUNT, 0.f);
+    if (n_hops <= 0) return;
+    if (win < 1024 || (win & (win - 1)) || (win / 2) % SP_THREADS || win / 2 / SP_THREADS > 4)
+        JT_THROW(JT_ERR_UNSUPPORTED, "aspectralstats win_size %d", win);
+    std::vector<float2> tw(win / 2); std::vector<float> lut(win);
+    for (int k = 0; k < win / 2; k++) { double a = -2.0 * M_PI * k / win; tw[k] = make_float2((float)cos(a), (float)sin(a)); }
+    for (int i = 0; i < win; i++) lut[i] = (float)(.5 * (1 - cos(2 * M_PI * i / (win - 1))));
+    float2 *d_tw = jt_dalloc<float2>(c, win / 2); float *d_lut = jt_dalloc<float>(c, win);
+    JT_CUDA(cudaMemcpyAsync(d_tw, tw.data(), sizeof(float2) * win / 2, cudaMemcpyHostToDevice, c->stream));
+    JT_CUDA(cudaMemcpyAsync(d_lut, lut.data(), sizeof(float) * win, cudaMemcpyHostToDevice, c->stream));
+    float *d_mags = jt_dalloc<float>(c, (size_t)n_hops * (win / 2));
+    float *d_rows = jt_dalloc<float>(c, (size_t)n_hops * JT_SP_COUNT);
+    const int grid = jt_grid_for(n_hops, 1, c->num_sms, 16);
+    {
+        JtLaunch L(c, "aspectralstats", 2);
+        k_spectral<<<grid, SP_THREADS, sizeof(float2) * win, c->stream>>>((const float *)in.d, in.n, win, in.rate, n_hops, d_tw, d_lut, d_mags, d_rows);
+        k_spectral_flux<<<grid, 256, 0, c->stream>>>(d_mags, win / 2, n_hops, d_rows);
+    }
+    JT_CUDA(cudaMemcpyAsync(rows.data(), d_rows, sizeof(float) * rows.size(), cudaMemcpyDeviceToHost, c->stream));
+    JT_CUDA(cudaStreamSynchronize(c->stream));
+}

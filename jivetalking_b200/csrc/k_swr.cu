@@ -1,0 +1,299 @@
+// Polyphase resampler with libswresample's default design (kaiser-windowed sinc,
+// filter_size 32, phase_shift 10, cutoff 0.97, exact_rational), used for
+//   - ebur128's 192 kHz true-peak oversampler          (reference: filters.go:626)
+//   - the aformat=sample_rates=44100 output stage       (reference: filters.go:706-710)
+//   - loudnorm's forced 192 kHz input (dynamic mode)    (reference: normalise.go:257-264)
+// Output m reads taps x[first_tap(m) .. +L) with swr's start mirror x[-k]=x[k] and end
+// reflection x[n+j]=x[n-1-j].
+//
+// Mapping: one output "period" q holds phase_count outputs and consumes `div` inputs, so
+// out[q*pc + r] = sum_i x[q*div - c + o_r + i] * F[ph_r][i] with o_r, ph_r depending on r
+// only.  Small phase counts (48k->192k: pc = 4) run thread-per-period with the whole
+// filter bank passed as a __grid_constant__ kernel parameter, so every DFMA takes its
+// coefficient straight from the constant bank: 1 LDS + pc DFMA per tap.  Large phase
+// counts (44.1k->192k: 640, 48k->44.1k: 147) run warp-per-r / lane-per-period so the
+// coefficient load is warp-uniform and the x reads are a padded conflict-free stride.
+#include "jt_internal.h"
+#include "jt_device.cuh"
+#include <cstdio>
+
+// ---------------------------------------------------------------------------------------
+// host: filter design (libswresample/resample.c build_filter, SWR_FILTER_TYPE_KAISER)
+// ---------------------------------------------------------------------------------------
+static double bessel_i0(double x)
+{
+    double y = x * x / 4.0, t = 1.0, sum = 1.0;
+    for (int k = 1; k < 200; k++) { t *= y / ((double)k * k); sum += t; if (t < sum * 1e-18) break; }
+    return sum;
+}
+static int64_t gcd_i64(int64_t a, int64_t b) { while (b) { int64_t t = a % b; a = b; b = t; } return a; }
+
+SwrPlan jt_swr_plan(int in_rate, int out_rate)
+{
+    SwrPlan p; p.in_rate = in_rate; p.out_rate = out_rate;
+    if (in_rate == out_rate) { p.identity = true; p.phase_count = 1; p.filter_length = 1; p.div = 1; return p; }
+    const int filter_size = 32, phase_shift = 10;
+    const double cutoff = 0.97, beta = 9.0;
+    double factor = std::fmin((double)out_rate * cutoff / in_rate, 1.0);
+    int64_t g = gcd_i64(out_rate, in_rate);
+    int64_t pc = out_rate / g;
+    if (pc > (1 << phase_shift))
+        JT_THROW(JT_ERR_UNSUPPORTED, "resample %d -> %d needs swr's linear-interpolated path (phase count %lld > 1024)",
+                 in_rate, out_rate, (long long)pc);
+    p.phase_count = (int)pc;
+    p.filter_length = std::max((int)std::ceil(filter_size / factor), 1);
+    p.div = (int)(((int64_t)in_rate * pc) / out_rate);
+    const int L = p.filter_length, center = (L - 1) / 2;
+    const int ph_nb = pc % 2 ? (int)pc : (int)pc / 2 + 1;
+    p.bank.assign((size_t)(pc + 1) * L, 0.0);
+    std::vector<double> tab(L), sin_lut(ph_nb, 0.0);
+    double norm = 0;
+    if (factor == 1.0)
+        for (int ph = 0; ph < ph_nb; ph++) sin_lut[ph] = sin(M_PI * ph / pc) * (center & 1 ? 1 : -1);
+    for (int ph = 0; ph < ph_nb; ph++) {
+        double s = sin_lut[ph];
+        for (int i = 0; i < L; i++) {
+            double x = M_PI * ((double)(i - center) - (double)ph / pc) * factor, y;
+            if (x == 0) y = 1.0; else if (factor == 1.0) y = s / x; else y = sin(x) / x;
+            double w = 2.0 * x / (factor * L * M_PI);
+            y *= bessel_i0(beta * sqrt(std::fmax(1 - w * w, 0)));
+            tab[i] = y; s = -s;
+            if (!ph) norm += y;
+        }
+        for (int i = 0; i < L; i++) p.bank[(size_t)ph * L + i] = tab[i] / norm;
+        if (pc % 2 == 0)
+            for (int i = 0; i < L; i++) p.bank[(size_t)(pc - ph) * L + L - 1 - i] = p.bank[(size_t)ph * L + i];
+    }
+    p.bank.resize((size_t)pc * L);
+    return p;
+}
+
+static int64_t avail_outputs(const SwrPlan &p, int64_t n_avail)
+{
+    const int64_t pc = p.phase_count, L = p.filter_length, c = (L - 1) / 2;
+    int64_t span = (1 + n_avail - L) * pc + pc * c;
+    if (span <= 0) return 0;
+    return (span + p.div - 1) / p.div;
+}
+int64_t SwrPlan::first_tap(int64_t m) const
+{
+    const int64_t pc = phase_count, c = (filter_length - 1) / 2;
+    return jt_floordiv(-pc * c + m * (int64_t)div, pc);
+}
+int64_t SwrPlan::out_count(int64_t n_in) const
+{
+    if (identity) return n_in;
+    if (n_in < filter_length + 1) return 0;
+    return avail_outputs(*this, n_in);
+}
+int64_t SwrPlan::out_count_flush(int64_t n_in) const
+{
+    if (identity) return n_in;
+    int64_t m0 = out_count(n_in);
+    int64_t cnt = n_in - first_tap(m0);
+    if (cnt > filter_length) cnt = filter_length;
+    if (cnt < 0) cnt = 0;
+    return avail_outputs(*this, n_in + (cnt + 1) / 2);
+}
+
+// ---------------------------------------------------------------------------------------
+// device
+// ---------------------------------------------------------------------------------------
+template <class TIN, class TW> __device__ __forceinline__ TW swr_load(const TIN *x, int64_t idx, int64_t n)
+{
+    if (idx < 0) idx = -idx; else if (idx >= n) idx = 2 * n - 1 - idx;
+    idx = idx < 0 ? 0 : (idx >= n ? n - 1 : idx);
+    return (TW)jt_as_f64(x[idx]);
+}
+template <> __device__ __forceinline__ float swr_load<int16_t, float>(const int16_t *x, int64_t idx, int64_t n)
+{
+    if (idx < 0) idx = -idx; else if (idx >= n) idx = 2 * n - 1 - idx;
+    idx = idx < 0 ? 0 : (idx >= n ? n - 1 : idx);
+    return jt_conv<int16_t, float>(x[idx]);
+}
+
+template <int PC> struct SmallBank { double f[PC * 32]; };
+
+enum { SWR_MODE_STORE = 0, SWR_MODE_TICKMAX = 1 };
+
+// thread <-> period q, all PC phases in registers; L == 32, div == 1 (integer upsampling)
+template <class TIN, int PC, int MODE>
+__global__ void __launch_bounds__(256)
+k_swr_small(const TIN *__restrict__ x, int64_t n, int64_t n_periods, int64_t n_out,
+            const __grid_constant__ SmallBank<PC> bank, double *__restrict__ out,
+            double *__restrict__ tick_max, int tick, int64_t n_ticks)
+{
+    constexpr int L = 32, C = (L - 1) / 2;
+    __shared__ double sx[256 + L];
+    const int64_t tiles = (n_periods + 255) / 256;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int64_t q0 = tile * 256;
+        const int64_t base = q0 - C;                 // first tap of period q0
+        __syncthreads();
+        for (int i = threadIdx.x; i < 256 + L; i += 256) sx[i] = swr_load<TIN, double>(x, base + i, n);
+        __syncthreads();
+        const int64_t q = q0 + threadIdx.x;
+        double acc[PC];
+#pragma unroll
+        for (int r = 0; r < PC; r++) acc[r] = 0.0;
+#pragma unroll
+        for (int i = 0; i < L; i++) {
+            const double v = sx[threadIdx.x + i];
+#pragma unroll
+            for (int r = 0; r < PC; r++) acc[r] = fma(v, bank.f[r * L + i], acc[r]);
+        }
+        if (MODE == SWR_MODE_STORE) {
+            if (q < n_periods) {
+#pragma unroll
+                for (int r = 0; r < PC; r++) { int64_t m = q * PC + r; if (m < n_out) out[m] = acc[r]; }
+            }
+        } else {
+            double mx = 0.0; int64_t k = -1;
+            if (q < n_periods) {
+#pragma unroll
+                for (int r = 0; r < PC; r++) { int64_t m = q * PC + r; if (m < n_out) mx = fmax(mx, fabs(acc[r])); }
+                int64_t need = q - C + L; if (need < L + 1) need = L + 1;     // inputs swr must have seen
+                k = (need + tick - 1) / tick - 1;
+            }
+            const int64_t k0 = __shfl_sync(0xffffffffu, k, 0);
+            const bool uni = __all_sync(0xffffffffu, k == k0);
+            if (uni) {
+                mx = jt_warp_max(mx);
+                if ((threadIdx.x & 31) == 0 && k0 >= 0 && k0 < n_ticks) jt_atomic_max_nonneg(&tick_max[k0], mx);
+            } else if (k >= 0 && k < n_ticks) jt_atomic_max_nonneg(&tick_max[k], mx);
+        }
+    }
+}
+
+// generic: lane <-> period, warp <-> r; x tile in padded shared memory, bank in global (uniform loads)
+template <class TIN, class TW, int MODE>
+__global__ void __launch_bounds__(256)
+k_swr_generic(const TIN *__restrict__ x, int64_t n, int64_t n_periods, int64_t n_out,
+              int pc, int L, int div, const TW *__restrict__ bank, TW *__restrict__ out,
+              double *__restrict__ tick_max, int tick, int64_t n_ticks, int span)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TW *sx = (TW *)smem_raw;
+    const int c = (L - 1) / 2;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int64_t tiles = (n_periods + 31) / 32;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int64_t q0 = tile * 32;
+        const int64_t base = q0 * div - c;
+        __syncthreads();
+        for (int i = threadIdx.x; i < span; i += blockDim.x) sx[i + (i >> 5)] = swr_load<TIN, TW>(x, base + i, n);
+        __syncthreads();
+        const int64_t q = q0 + lane;
+        double cur_max = 0.0; int64_t cur_k = -1;
+        for (int r = warp; r < pc; r += nwarp) {
+            const int o_r = (int)(((int64_t)r * div) / pc);
+            const int ph = (int)(((int64_t)r * div) % pc);
+            const TW *f = bank + (size_t)ph * L;
+            const int s0 = lane * div + o_r;
+            TW a0 = 0, a1 = 0;
+            int i = 0;
+            for (; i + 1 < L; i += 2) {
+                int ia = s0 + i, ib = ia + 1;
+                a0 = fma(sx[ia + (ia >> 5)], __ldg(f + i), a0);
+                a1 = fma(sx[ib + (ib >> 5)], __ldg(f + i + 1), a1);
+            }
+            if (i < L) { int ia = s0 + i; a0 = fma(sx[ia + (ia >> 5)], __ldg(f + i), a0); }
+            const TW v = a0 + a1;
+            const int64_t m = q * pc + r;
+            if (q < n_periods && m < n_out) {
+                if (MODE == SWR_MODE_STORE) out[m] = v;
+                else {
+                    int64_t need = q * div - c + o_r + L; if (need < L + 1) need = L + 1;
+                    const int64_t k = (need + tick - 1) / tick - 1;
+                    if (k != cur_k) {
+                        if (cur_k >= 0 && cur_k < n_ticks) jt_atomic_max_nonneg(&tick_max[cur_k], cur_max);
+                        cur_k = k; cur_max = 0.0;
+                    }
+                    cur_max = fmax(cur_max, fabs((double)v));
+                }
+            }
+        }
+        if (MODE == SWR_MODE_TICKMAX && cur_k >= 0 && cur_k < n_ticks) jt_atomic_max_nonneg(&tick_max[cur_k], cur_max);
+    }
+}
+
+template <class TIN, int MODE>
+static void launch_small(jt_ctx *c, const Sig &in, const SwrPlan &p, int64_t n_out, double *out,
+                         double *tick_max, int tick, int64_t n_ticks)
+{
+    const int64_t n_periods = (n_out + p.phase_count - 1) / p.phase_count;
+    const int grid = jt_grid_for(n_periods, 256, c->num_sms, 16);
+#define SMALL_CASE(PCV) case PCV: { SmallBank<PCV> b; for (int i = 0; i < PCV * 32; i++) b.f[i] = p.bank[i]; \
+        k_swr_small<TIN, PCV, MODE><<<grid, 256, 0, c->stream>>>((const TIN *)in.d, in.n, n_periods, n_out, b, out, tick_max, tick, n_ticks); } break;
+    switch (p.phase_count) { SMALL_CASE(2) SMALL_CASE(4) SMALL_CASE(6) SMALL_CASE(8) default: JT_THROW(JT_ERR_UNSUPPORTED, "small pc"); }
+#undef SMALL_CASE
+}
+
+template <class TIN, class TW, int MODE>
+static void launch_generic(jt_ctx *c, const Sig &in, const SwrPlan &p, int64_t n_out, TW *out,
+                           double *tick_max, int tick, int64_t n_ticks)
+{
+    const size_t nb = (size_t)p.phase_count * p.filter_length;
+    TW *d_bank = jt_dalloc<TW>(c, nb);
+    std::vector<TW> hb(nb);
+    for (size_t i = 0; i < nb; i++) hb[i] = (TW)p.bank[i];
+    JT_CUDA(cudaMemcpyAsync(d_bank, hb.data(), nb * sizeof(TW), cudaMemcpyHostToDevice, c->stream));
+    JT_CUDA(cudaStreamSynchronize(c->stream));   // hb is a stack-lifetime staging buffer
+    const int64_t n_periods = (n_out + p.phase_count - 1) / p.phase_count;
+    const int span = 32 * p.div + p.filter_length + p.div;
+    const size_t smem = (size_t)(span + (span >> 5) + 2) * sizeof(TW);
+    auto kfn = k_swr_generic<TIN, TW, MODE>;
+    JT_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = jt_grid_for((n_periods + 31) / 32, 1, c->num_sms, 8);
+    kfn<<<grid, 256, smem, c->stream>>>((const TIN *)in.d, in.n, n_periods, n_out, p.phase_count, p.filter_length, p.div,
+                                          d_bank, out, tick_max, tick, n_ticks, span);
+}
+
+static bool small_path(const SwrPlan &p) { return p.div == 1 && p.filter_length == 32 && (p.phase_count == 2 || p.phase_count == 4 || p.phase_count == 6 || p.phase_count == 8); }
+
+Sig jt_swr_resample(jt_ctx *c, const Sig &in, const SwrPlan &p, int work_fmt, bool flush)
+{
+    if (p.identity) return jt_convert(c, in, work_fmt);
+    const int64_t n_out = flush ? p.out_count_flush(in.n) : p.out_count(in.n);
+    Sig o; o.fmt = work_fmt; o.rate = p.out_rate; o.n = n_out;
+    o.d = jt_dalloc_bytes(c, (size_t)std::max<int64_t>(n_out, 1) * jt_fmt_bytes(work_fmt));
+    if (n_out <= 0) return o;
+    JtLaunch Lc(c, "swr_resample");
+    if (work_fmt == JT_FMT_DBL) {
+        if (small_path(p)) {
+            if (in.fmt == JT_FMT_S16) launch_small<int16_t, SWR_MODE_STORE>(c, in, p, n_out, (double *)o.d, nullptr, 1, 0);
+            else if (in.fmt == JT_FMT_FLT) launch_small<float, SWR_MODE_STORE>(c, in, p, n_out, (double *)o.d, nullptr, 1, 0);
+            else launch_small<double, SWR_MODE_STORE>(c, in, p, n_out, (double *)o.d, nullptr, 1, 0);
+        } else {
+            if (in.fmt == JT_FMT_S16) launch_generic<int16_t, double, SWR_MODE_STORE>(c, in, p, n_out, (double *)o.d, nullptr, 1, 0);
+            else if (in.fmt == JT_FMT_FLT) launch_generic<float, double, SWR_MODE_STORE>(c, in, p, n_out, (double *)o.d, nullptr, 1, 0);
+            else launch_generic<double, double, SWR_MODE_STORE>(c, in, p, n_out, (double *)o.d, nullptr, 1, 0);
+        }
+    } else if (work_fmt == JT_FMT_FLT) {
+        if (in.fmt == JT_FMT_S16) launch_generic<int16_t, float, SWR_MODE_STORE>(c, in, p, n_out, (float *)o.d, nullptr, 1, 0);
+        else if (in.fmt == JT_FMT_FLT) launch_generic<float, float, SWR_MODE_STORE>(c, in, p, n_out, (float *)o.d, nullptr, 1, 0);
+        else JT_THROW(JT_ERR_UNSUPPORTED, "f64 -> f32-internal resample");
+    } else JT_THROW(JT_ERR_UNSUPPORTED, "swr work format %d", work_fmt);
+    return o;
+}
+
+void jt_swr_tick_absmax(jt_ctx *c, const Sig &in, const SwrPlan &p, int tick, int64_t n_ticks, double *d_tick_tp)
+{
+    JT_CUDA(cudaMemsetAsync(d_tick_tp, 0, sizeof(double) * (size_t)std::max<int64_t>(n_ticks, 1), c->stream));
+    if (n_ticks <= 0) return;
+    // outputs swr has produced once n_ticks*tick inputs were fed (ebur128 never flushes)
+    const int64_t fed = n_ticks * (int64_t)tick;
+    Sig v = in; v.n = std::min(in.n, fed);
+    const int64_t n_out = p.out_count(v.n);
+    if (n_out <= 0) return;
+    JtLaunch Lc(c, "truepeak_oversample");
+    if (small_path(p)) {
+        if (v.fmt == JT_FMT_S16) launch_small<int16_t, SWR_MODE_TICKMAX>(c, v, p, n_out, nullptr, d_tick_tp, tick, n_ticks);
+        else if (v.fmt == JT_FMT_FLT) launch_small<float, SWR_MODE_TICKMAX>(c, v, p, n_out, nullptr, d_tick_tp, tick, n_ticks);
+        else launch_small<double, SWR_MODE_TICKMAX>(c, v, p, n_out, nullptr, d_tick_tp, tick, n_ticks);
+    } else {
+        if (v.fmt == JT_FMT_S16) launch_generic<int16_t, double, SWR_MODE_TICKMAX>(c, v, p, n_out, (double *)nullptr, d_tick_tp, tick, n_ticks);
+        else if (v.fmt == JT_FMT_FLT) launch_generic<float, double, SWR_MODE_TICKMAX>(c, v, p, n_out, (double *)nullptr, d_tick_tp, tick, n_ticks);
+        else launch_generic<double, double, SWR_MODE_TICKMAX>(c, v, p, n_out, (double *)nullptr, d_tick_tp, tick, n_ticks);
+    }
+}

@@ -1,0 +1,302 @@
+"""ctypes binding to libjtdsp.so (include/jtdsp.h) -- the B200 CUDA replacement for the
+FFmpeg filter graphs jivetalking drives through setupFilterGraph / runFilterGraph
+(reference: internal/processor/frame_processor.go:64-216).
+
+This module is plumbing for tests and bench.py; the product is the shared library.  It
+fails loudly when the library is missing or no CUDA device is present: there is no CPU
+path (and it never imports oracle/).
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libjtdsp.so")
+
+FMT_S16, FMT_S32, FMT_FLT, FMT_DBL = 1, 2, 3, 4
+_NP_OF_FMT = {FMT_S16: np.int16, FMT_FLT: np.float32, FMT_DBL: np.float64}
+_FMT_OF_NP = {np.dtype(np.int16): FMT_S16, np.dtype(np.float32): FMT_FLT, np.dtype(np.float64): FMT_DBL}
+
+AS_NAMES = ["Dynamic_range", "RMS_level", "Peak_level", "RMS_trough", "RMS_peak", "DC_offset", "Flat_factor",
+            "Crest_factor", "Zero_crossings_rate", "Zero_crossings", "Max_difference", "Min_difference",
+            "Mean_difference", "RMS_difference", "Entropy", "Min_level", "Max_level", "Noise_floor",
+            "Noise_floor_count", "Bit_depth", "Number_of_samples"]
+SP_NAMES = ["mean", "variance", "centroid", "spread", "skewness", "kurtosis", "entropy", "flatness", "crest",
+            "flux", "slope", "decrease", "rolloff"]
+AS_COUNT, SP_COUNT = len(AS_NAMES), len(SP_NAMES)
+
+ERRORS = {0: "JT_OK", -1: "JT_ERR_INVALID_ARG", -2: "JT_ERR_CUDA", -3: "JT_ERR_NOMEM", -4: "JT_ERR_SPEC",
+          -5: "JT_ERR_UNSUPPORTED", -6: "JT_ERR_CANCELLED", -7: "JT_ERR_BUFFER"}
+
+
+class JtError(RuntimeError):
+    def __init__(self, code, detail=""):
+        self.code = code
+        super().__init__(f"{ERRORS.get(code, code)}: {detail}")
+
+
+class FrameMeta(C.Structure):
+    _fields_ = [("first_sample", C.c_int64), ("nb_samples", C.c_int32), ("reserved", C.c_int32),
+                ("r128_M", C.c_double), ("r128_S", C.c_double), ("r128_I", C.c_double), ("r128_LRA", C.c_double),
+                ("r128_LRA_low", C.c_double), ("r128_LRA_high", C.c_double),
+                ("r128_true_peak", C.c_double), ("r128_sample_peak", C.c_double),
+                ("astats", C.c_double * AS_COUNT),
+                ("astats_overall_RMS_level", C.c_double), ("astats_overall_Peak_level", C.c_double),
+                ("spectral", C.c_double * SP_COUNT)]
+
+
+class LoudnormStats(C.Structure):
+    _fields_ = [("input_i", C.c_double), ("input_tp", C.c_double), ("input_lra", C.c_double), ("input_thresh", C.c_double),
+                ("output_i", C.c_double), ("output_tp", C.c_double), ("output_lra", C.c_double), ("output_thresh", C.c_double),
+                ("target_offset", C.c_double), ("normalization_type", C.c_int32), ("valid", C.c_int32)]
+
+    def as_dict(self):
+        return {f: getattr(self, f) for f, _ in self._fields_}
+
+
+class Interval(C.Structure):
+    _fields_ = [("timestamp_s", C.c_double), ("rms_level", C.c_double), ("peak_level", C.c_double),
+                ("spectral", C.c_double * SP_COUNT), ("spectral_found", C.c_int32), ("frame_count", C.c_int32),
+                ("momentary_lufs", C.c_double), ("short_term_lufs", C.c_double), ("true_peak", C.c_double),
+                ("sample_peak", C.c_double)]
+
+
+class Measurements(C.Structure):
+    _fields_ = [("input_i", C.c_double), ("input_tp", C.c_double), ("input_sp", C.c_double), ("input_lra", C.c_double),
+                ("last_m", C.c_double), ("last_s", C.c_double), ("astats", C.c_double * AS_COUNT),
+                ("spectral_mean", C.c_double * SP_COUNT), ("spectral_frames", C.c_int64), ("sink_frames", C.c_int64),
+                ("duration_s", C.c_double)]
+
+    def as_dict(self):
+        d = {k: getattr(self, k) for k in ("input_i", "input_tp", "input_sp", "input_lra", "last_m", "last_s",
+                                          "spectral_frames", "sink_frames", "duration_s")}
+        d["astats"] = {n: self.astats[i] for i, n in enumerate(AS_NAMES)}
+        d["spectral_mean"] = {n: self.spectral_mean[i] for i, n in enumerate(SP_NAMES)}
+        return d
+
+
+class ProcessResult(C.Structure):
+    _fields_ = [("input", Measurements), ("filtered", Measurements), ("final", Measurements),
+                ("pass3", LoudnormStats), ("pass4", LoudnormStats),
+                ("limiter_ceiling_db", C.c_double), ("limiter_pregain_db", C.c_double), ("gain_db", C.c_double),
+                ("effective_target_i", C.c_double),
+                ("limiter_needed", C.c_int32), ("limiter_clamped", C.c_int32), ("linear_possible", C.c_int32),
+                ("reserved", C.c_int32), ("n_out", C.c_int64)]
+
+
+_lib = None
+_P, _I64, _INT = C.c_void_p, C.c_int64, C.c_int
+
+
+def lib():
+    """Load libjtdsp.so; raises (never falls back) when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    L.jt_version.restype = _INT
+    L.jt_create.argtypes = [_INT, C.POINTER(_P)]
+    L.jt_destroy.argtypes = [_P]
+    L.jt_strerror.restype = C.c_char_p
+    L.jt_strerror.argtypes = [_INT]
+    L.jt_last_error.restype = C.c_char_p
+    L.jt_last_error.argtypes = [_P]
+    L.jt_cancel.argtypes = [_P]
+    g = [_P, C.c_char_p, _P, _I64, _INT, _INT, _INT, _INT, _P, _I64, C.POINTER(_I64), C.POINTER(_INT), C.POINTER(_INT),
+         C.POINTER(FrameMeta), _I64, C.POINTER(_I64), C.POINTER(LoudnormStats)]
+    L.jt_run_graph.argtypes = g
+    L.jt_run_graph_dev.argtypes = g
+    L.jt_graph_max_out_frames.restype = _I64
+    L.jt_graph_max_out_frames.argtypes = [C.c_char_p, _I64, _INT]
+    L.jt_graph_max_meta.restype = _I64
+    L.jt_graph_max_meta.argtypes = [C.c_char_p, _I64, _INT, _INT]
+    L.jt_analyse.argtypes = [_P, _P, _I64, _INT, _INT, _INT, _INT, C.POINTER(Measurements), C.POINTER(Interval), _I64,
+                             C.POINTER(_I64)]
+    L.jt_band_rms.argtypes = [_P, _P, _I64, _INT, _INT, _INT, C.c_double, C.c_double, _P, _P, _INT, _P, _P]
+    pa = [_P, _P, _I64, _INT, _INT, _INT, C.c_char_p, _P, _I64, C.POINTER(ProcessResult)]
+    L.jt_process_audio.argtypes = pa
+    L.jt_process_audio_dev.argtypes = pa
+    L.jt_build_pass3_spec.argtypes = [C.c_double] * 5 + [C.c_char_p, C.c_size_t, C.POINTER(ProcessResult)]
+    L.jt_build_pass4_spec.argtypes = [C.POINTER(ProcessResult), C.POINTER(LoudnormStats), C.c_double, C.c_double,
+                                      C.c_double, _INT, C.c_char_p, C.c_size_t, C.POINTER(C.c_double),
+                                      C.POINTER(C.c_double)]
+    L.jt_default_pass2_spec.argtypes = [C.c_char_p, C.c_size_t]
+    L.jt_pass1_spec.argtypes = [C.c_char_p, C.c_size_t]
+    L.jt_loudnorm_stats_json.argtypes = [C.POINTER(LoudnormStats), C.c_char_p, C.c_size_t]
+    L.jt_launch_count.restype = _I64
+    L.jt_launch_count.argtypes = [_P]
+    L.jt_reset_launch_count.argtypes = [_P]
+    L.jt_enable_kernel_timing.argtypes = [_P, _INT]
+    L.jt_kernel_timing.restype = C.c_char_p
+    L.jt_kernel_timing.argtypes = [_P, _INT, C.POINTER(C.c_double), C.POINTER(_I64)]
+    _lib = L
+    return L
+
+
+def pass1_spec():
+    b = C.create_string_buffer(4096)
+    lib().jt_pass1_spec(b, len(b))
+    return b.value.decode()
+
+
+def default_pass2_spec():
+    b = C.create_string_buffer(4096)
+    lib().jt_default_pass2_spec(b, len(b))
+    return b.value.decode()
+
+
+def meta_to_dict(m):
+    d = {k: getattr(m, k) for k in ("first_sample", "nb_samples", "r128_M", "r128_S", "r128_I", "r128_LRA",
+                                    "r128_LRA_low", "r128_LRA_high", "r128_true_peak", "r128_sample_peak",
+                                    "astats_overall_RMS_level", "astats_overall_Peak_level")}
+    d["astats"] = {n: m.astats[i] for i, n in enumerate(AS_NAMES)}
+    d["spectral"] = {n: m.spectral[i] for i, n in enumerate(SP_NAMES)}
+    return d
+
+
+class Context:
+    """One jt_ctx (one CUDA stream).  Mirrors a per-worker config clone (filters.go:368-373)."""
+
+    def __init__(self, device=0):
+        self._h = _P(None)
+        rc = lib().jt_create(device, C.byref(self._h))
+        if rc != 0:
+            raise JtError(rc, lib().jt_strerror(rc).decode() + " (no CPU fallback)")
+
+    def close(self):
+        if self._h:
+            lib().jt_destroy(self._h)
+            self._h = _P(None)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc):
+        if rc != 0:
+            raise JtError(rc, lib().jt_last_error(self._h).decode())
+
+    # -- S4 -------------------------------------------------------------------------------
+    def run_graph(self, spec, pcm, rate, channels=1, frame_size=4096, want_pcm=True, want_meta=True):
+        """pcm: numpy array (int16 / float32 / float64), interleaved if channels > 1.
+        Returns dict(pcm, rate, fmt, meta=[FrameMeta...], loudnorm=LoudnormStats)."""
+        pcm = np.ascontiguousarray(pcm)
+        fmt = _FMT_OF_NP[pcm.dtype]
+        n = pcm.size // channels
+        bspec = spec.encode()
+        cap = lib().jt_graph_max_out_frames(bspec, n, rate)
+        mcap = lib().jt_graph_max_meta(bspec, n, rate, frame_size)
+        out = np.zeros(cap, dtype=np.float64) if want_pcm else None     # 8 bytes/sample holds any format
+        meta = (FrameMeta * mcap)() if want_meta else None
+        n_out, n_meta, orate, ofmt = _I64(0), _I64(0), _INT(0), _INT(0)
+        ln = LoudnormStats()
+        rc = lib().jt_run_graph(self._h, bspec, pcm.ctypes.data_as(_P), n, rate, channels, fmt, frame_size,
+                                out.ctypes.data_as(_P) if want_pcm else None, cap, C.byref(n_out), C.byref(orate),
+                                C.byref(ofmt), meta, mcap, C.byref(n_meta), C.byref(ln))
+        self._check(rc)
+        res = dict(rate=orate.value, fmt=ofmt.value, n_out=n_out.value, loudnorm=ln, pcm=None, meta=[])
+        if want_pcm:
+            dt = _NP_OF_FMT[ofmt.value]
+            res["pcm"] = out.view(np.uint8)[: n_out.value * np.dtype(dt).itemsize].view(dt).copy()
+        if want_meta:
+            res["meta"] = [meta[i] for i in range(n_meta.value)]
+        return res
+
+    def analyse(self, pcm, rate, channels=1, frame_size=4096):
+        pcm = np.ascontiguousarray(pcm)
+        fmt = _FMT_OF_NP[pcm.dtype]
+        n = pcm.size // channels
+        cap = int(n / rate / 0.25) + 8
+        iv = (Interval * cap)()
+        n_iv = _I64(0)
+        m = Measurements()
+        rc = lib().jt_analyse(self._h, pcm.ctypes.data_as(_P), n, rate, channels, fmt, frame_size, C.byref(m), iv, cap,
+                              C.byref(n_iv))
+        self._check(rc)
+        return m, [iv[i] for i in range(n_iv.value)]
+
+    def band_rms(self, pcm, rate, start_s, duration_s, lo_hz, hi_hz, channels=1):
+        pcm = np.ascontiguousarray(pcm)
+        fmt = _FMT_OF_NP[pcm.dtype]
+        lo = np.ascontiguousarray(lo_hz, dtype=np.float64)
+        hi = np.ascontiguousarray(hi_hz, dtype=np.float64)
+        out = np.zeros(len(lo))
+        found = np.zeros(len(lo), dtype=np.int32)
+        rc = lib().jt_band_rms(self._h, pcm.ctypes.data_as(_P), pcm.size // channels, rate, channels, fmt, start_s,
+                               duration_s, lo.ctypes.data_as(_P), hi.ctypes.data_as(_P), len(lo),
+                               out.ctypes.data_as(_P), found.ctypes.data_as(_P))
+        self._check(rc)
+        return out, found
+
+    def process_audio(self, pcm, rate, channels=1, pass2_spec=None):
+        """Full four-pass chain.  Returns (int16 mono 44.1 kHz array, ProcessResult)."""
+        pcm = np.ascontiguousarray(pcm)
+        fmt = _FMT_OF_NP[pcm.dtype]
+        n = pcm.size // channels
+        cap = int(n * 44100 / rate) + 3 * 4096
+        out = np.zeros(cap, dtype=np.int16)
+        res = ProcessResult()
+        rc = lib().jt_process_audio(self._h, pcm.ctypes.data_as(_P), n, rate, channels, fmt,
+                                    pass2_spec.encode() if pass2_spec else None, out.ctypes.data_as(_P), cap,
+                                    C.byref(res))
+        self._check(rc)
+        return out[: res.n_out].copy(), res
+
+    # -- raw pointer variants for bench.py (torch owns the memory) ----------------------------
+    def process_audio_ptr(self, in_ptr, n, rate, channels, fmt, out_ptr, out_cap, on_device, pass2_spec=None):
+        res = ProcessResult()
+        fn = lib().jt_process_audio_dev if on_device else lib().jt_process_audio
+        rc = fn(self._h, _P(in_ptr), n, rate, channels, fmt, pass2_spec.encode() if pass2_spec else None, _P(out_ptr),
+                out_cap, C.byref(res))
+        self._check(rc)
+        return res
+
+    def launch_count(self):
+        return lib().jt_launch_count(self._h)
+
+    def reset_counters(self):
+        lib().jt_reset_launch_count(self._h)
+
+    def enable_timing(self, on=True):
+        lib().jt_enable_kernel_timing(self._h, 1 if on else 0)
+
+    def kernel_timings(self):
+        out, i = [], 0
+        while True:
+            ms, ln = C.c_double(0), _I64(0)
+            name = lib().jt_kernel_timing(self._h, i, C.byref(ms), C.byref(ln))
+            if not name:
+                break
+            out.append((name.decode(), ms.value, ln.value))
+            i += 1
+        return out
+
+
+def build_pass3_spec(output_i, output_tp, target_i=-16.0, target_tp=-1.0, target_lra=20.0):
+    b = C.create_string_buffer(4096)
+    plan = ProcessResult()
+    rc = lib().jt_build_pass3_spec(output_i, output_tp, target_i, target_tp, target_lra, b, len(b), C.byref(plan))
+    if rc:
+        raise JtError(rc)
+    return b.value.decode(), plan
+
+
+def build_pass4_spec(plan, pass3_stats, target_i=-16.0, target_tp=-1.0, target_lra=20.0, source_rate=44100):
+    b = C.create_string_buffer(8192)
+    eff, off = C.c_double(0), C.c_double(0)
+    rc = lib().jt_build_pass4_spec(C.byref(plan), C.byref(pass3_stats), target_i, target_tp, target_lra, source_rate, b,
+                                   len(b), C.byref(eff), C.byref(off))
+    if rc:
+        raise JtError(rc)
+    return b.value.decode(), eff.value, off.value

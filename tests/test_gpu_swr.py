@@ -1,0 +1,50 @@
+"""GPU parity: polyphase resampler / format conversion kernels vs the oracle and vs the real
+libswresample golden vectors."""
+import os
+import numpy as np
+import pytest
+import jt_oracle as O
+from jivetalking_b200 import gpudsp
+
+pytestmark = pytest.mark.gpu
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "swr_golden.npz"))
+
+
+@pytest.mark.parametrize("rates", [(48000, 192000), (48000, 44100), (44100, 192000), (96000, 44100)])
+def test_aresample_f64_vs_real_swr_golden(ctx, rates):
+    x = G["in_noise"]
+    ref = G[f"dbl_noise_{rates[0]}_{rates[1]}_1"]
+    got = ctx.run_graph(f"aresample={rates[1]}", x, rates[0], want_meta=False)
+    assert got["rate"] == rates[1] and got["fmt"] == gpudsp.FMT_DBL
+    assert len(got["pcm"]) == len(ref)
+    assert np.max(np.abs(got["pcm"] - ref)) < 1e-14
+
+
+def test_output_stage_48k_to_s16_44k(ctx):
+    rng = np.random.default_rng(11)
+    x = (rng.standard_normal(100003) * 0.25)
+    got = ctx.run_graph("aformat=sample_rates=44100:channel_layouts=mono:sample_fmts=s16,asetnsamples=n=4096", x, 48000)
+    y = O.swr_resample(x, 48000, 44100, flush=True)
+    exp = np.zeros(len(y), dtype=np.int16)
+    O.lib().orc_conv_f64_to_s16(O._ptr(y), len(y), O._ptr(exp))
+    pad = (-len(exp)) % 4096
+    exp = np.concatenate([exp, np.zeros(pad, dtype=np.int16)])
+    assert got["fmt"] == gpudsp.FMT_S16 and got["rate"] == 44100
+    assert len(got["pcm"]) == len(exp)
+    d = np.abs(got["pcm"].astype(int) - exp.astype(int))
+    assert d.max() <= 1 and np.count_nonzero(d) < 5          # rounding ties only
+    assert [m.nb_samples for m in got.get("meta", [])] == []
+
+
+def test_s16_to_192k_uses_f32_internal(ctx):
+    # loudnorm dynamic mode on s16 input: swr resamples in FLTP (swresample.c int_sample_fmt rule)
+    s16 = G["in_s16"]
+    got = ctx.run_graph("loudnorm=I=-16.0:TP=-1.0:LRA=20.0:dual_mono=true:print_format=json", s16, 44100, want_pcm=False, want_meta=False)
+    assert got["loudnorm"].valid == 1 and got["loudnorm"].normalization_type == 1
+    assert got["rate"] == 192000
+
+
+def test_stereo_downmix_matches_real_swr(ctx):
+    st = G["in_stereo_f32"]
+    got = ctx.run_graph("aformat=channel_layouts=mono", st, 48000, channels=2, want_meta=False)
+    assert np.max(np.abs(got["pcm"] - G["stereo_f32_to_mono"])) < 1.2e-7
