@@ -1,0 +1,197 @@
+// agate, acompressor, deesser (libavfilter/af_agate.c, af_sidechaincompress.c, af_deesser.c), f64:
+//   "agate=threshold=..:ratio=..:attack=5.00:release=200:range=..:knee=3.0:detection=rms:makeup=1.0"
+//   "acompressor=threshold=..:ratio=3.0:attack=10:release=200:makeup=1.00:knee=4.0:detection=rms:mix=1.00"
+//   "deesser=i=..:m=0.50:f=0.80"               (reference: filters.go:869-932)
+// Gate and compressor are a switching one-pole envelope follower (sequential, ~2 FLOP per
+// sample) followed by a memoryless log-domain gain law (parallel, ~2 transcendental calls per
+// sample).  The follower env' = env + (d-env)*(d>env ? a : r) is a contraction with factor
+// (1 - min(a,r)) per sample, so the stream is cut into segments, one lane each, started
+// 37/min(a,r) samples early from zero: after the warm-up the lane's state equals the
+// sequential state to the last bit of f64.  The gain law then runs fully parallel.
+// The de-esser is a per-sample nonlinear recurrence (Airwindows DeEss) and runs as lanes too.
+#include "jt_internal.h"
+#include "jt_device.cuh"
+
+#define FAKE_INFINITY (65536.0 * 65536.0)
+
+// ---- switching envelope follower ----------------------------------------------------------
+__global__ void __launch_bounds__(64)
+k_envelope(const double *__restrict__ x, double *__restrict__ env, int64_t n, int seg, int warm,
+           double attack_coeff, double release_coeff, int rms)
+{
+    const int64_t lane = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t s0 = lane * seg; if (s0 >= n) return;
+    const int64_t s1 = min(s0 + (int64_t)seg, n);
+    double e = 0.0;
+    int64_t i = max((int64_t)0, s0 - warm);
+#pragma unroll 4
+    for (; i < s0; i++) {
+        double d = fabs(x[i]); if (rms) d *= d;
+        e += (d - e) * (d > e ? attack_coeff : release_coeff);
+    }
+#pragma unroll 4
+    for (; i < s1; i++) {
+        double d = fabs(x[i]); if (rms) d *= d;
+        e += (d - e) * (d > e ? attack_coeff : release_coeff);
+        env[i] = e;
+    }
+}
+
+static double *run_envelope(jt_ctx *c, const Sig &in, double attack_ms, double release_ms, int rms)
+{
+    const double ac = std::fmin(1., 1. / (attack_ms * in.rate / 4000.)), rc = std::fmin(1., 1. / (release_ms * in.rate / 4000.));
+    double *env = jt_dalloc<double>(c, in.n);
+    const double cmin = std::fmin(ac, rc);
+    int64_t warm = cmin >= 1.0 ? 1 : (int64_t)std::ceil(37.0 / -std::log1p(-cmin)) + 16;
+    if (warm > (1 << 22)) warm = 1 << 22;
+    const int seg = 32768;
+    const int64_t lanes = (in.n + seg - 1) / seg;
+    JtLaunch L(c, "envelope_follower");
+    k_envelope<<<(int)((lanes + 63) / 64), 64, 0, c->stream>>>((const double *)in.d, env, in.n, seg, (int)warm, ac, rc, rms);
+    return env;
+}
+
+__device__ __forceinline__ double hermite_interpolation(double x, double x0, double x1, double p0, double p1, double m0, double m1)
+{
+    const double width = x1 - x0, t = (x - x0) / width;
+    m0 *= width; m1 *= width;
+    const double t2 = t * t, t3 = t2 * t;
+    const double ct0 = p0, ct1 = m0, ct2 = -3 * p0 - 2 * m0 + 3 * p1 - m1, ct3 = 2 * p0 + m0 - 2 * p1 + m1;
+    return ct3 * t3 + ct2 * t2 + ct1 * t + ct0;
+}
+
+struct GateK { double ratio, thres, knee, knee_start, knee_stop, lin_knee_stop, range, makeup; };
+
+__global__ void __launch_bounds__(256)
+k_gate_apply(const double *__restrict__ x, const double *__restrict__ env, double *__restrict__ y, int64_t n, GateK k)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double ls = env[i]; double gain = 1.0;
+        if (ls > 0.0 && ls < k.lin_knee_stop) {
+            const double slope = log(ls);
+            double tratio = k.ratio;
+            if (fabs(k.ratio - FAKE_INFINITY) < 1.0) tratio = 1000.;
+            double g = (slope - k.thres) * tratio + k.thres;
+            if (k.knee > 1. && slope > k.knee_start)
+                g = hermite_interpolation(slope, k.knee_start, k.knee_stop, ((k.knee_start - k.thres) * tratio + k.thres), k.knee_stop, tratio, 1.);
+            gain = fmax(k.range, exp(g - slope));
+        }
+        y[i] = x[i] * (1.0 * gain * k.makeup);
+    }
+}
+
+Sig jt_agate(jt_ctx *c, const Sig &in, const GateParams &p)
+{
+    if (in.fmt != JT_FMT_DBL) JT_THROW(JT_ERR_INVALID_ARG, "agate expects f64 input");
+    Sig o = in; o.d = jt_dalloc<double>(c, in.n);
+    if (in.n <= 0) return o;
+    double *env = run_envelope(c, in, p.attack, p.release, p.detection_rms);
+    GateK k;
+    double lin_threshold = p.threshold; const double lin_knee_sqrt = sqrt(p.knee);
+    if (p.detection_rms) lin_threshold *= lin_threshold;
+    k.lin_knee_stop = lin_threshold * lin_knee_sqrt;
+    const double lin_knee_start = lin_threshold / lin_knee_sqrt;
+    k.thres = log(lin_threshold); k.knee_start = log(lin_knee_start); k.knee_stop = log(k.lin_knee_stop);
+    k.ratio = p.ratio; k.knee = p.knee; k.range = p.range; k.makeup = p.makeup;
+    JtLaunch L(c, "agate_gain");
+    k_gate_apply<<<jt_grid_for(in.n, 256, c->num_sms, 16), 256, 0, c->stream>>>((const double *)in.d, env, (double *)o.d, in.n, k);
+    return o;
+}
+
+struct CompK { double ratio, thres, knee, knee_start, knee_stop, compressed_knee_stop, detector, makeup, mix; int rms; };
+
+__global__ void __launch_bounds__(256)
+k_comp_apply(const double *__restrict__ x, const double *__restrict__ env, double *__restrict__ y, int64_t n, CompK k)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double ls = env[i]; double gain = 1.0;
+        if (ls > 0.0 && ls > k.detector) {
+            double slope = log(ls), g, delta;
+            if (k.rms) slope *= 0.5;
+            if (fabs(k.ratio - FAKE_INFINITY) < 1.0) { g = k.thres; delta = 0.0; }
+            else { g = (slope - k.thres) / k.ratio + k.thres; delta = 1.0 / k.ratio; }
+            if (k.knee > 1.0 && slope < k.knee_stop)
+                g = hermite_interpolation(slope, k.knee_start, k.knee_stop, k.knee_start, k.compressed_knee_stop, 1.0, delta);
+            gain = exp(g - slope);
+        }
+        y[i] = x[i] * 1.0 * (gain * k.makeup * k.mix + (1. - k.mix));
+    }
+}
+
+Sig jt_acompressor(jt_ctx *c, const Sig &in, const CompParams &p)
+{
+    if (in.fmt != JT_FMT_DBL) JT_THROW(JT_ERR_INVALID_ARG, "acompressor expects f64 input");
+    Sig o = in; o.d = jt_dalloc<double>(c, in.n);
+    if (in.n <= 0) return o;
+    double *env = run_envelope(c, in, p.attack, p.release, p.detection_rms);
+    CompK k;
+    k.thres = log(p.threshold);
+    const double lin_knee_start = p.threshold / sqrt(p.knee), lin_knee_stop = p.threshold * sqrt(p.knee);
+    k.knee_start = log(lin_knee_start); k.knee_stop = log(lin_knee_stop);
+    k.compressed_knee_stop = (k.knee_stop - k.thres) / p.ratio + k.thres;
+    k.detector = p.detection_rms ? lin_knee_start * lin_knee_start : lin_knee_start;
+    k.ratio = p.ratio; k.knee = p.knee; k.makeup = p.makeup; k.mix = p.mix; k.rms = p.detection_rms;
+    JtLaunch L(c, "acompressor_gain");
+    k_comp_apply<<<jt_grid_for(in.n, 256, c->num_sms, 16), 256, 0, c->stream>>>((const double *)in.d, env, (double *)o.d, in.n, k);
+    return o;
+}
+
+// ---- de-esser -----------------------------------------------------------------------------
+__global__ void __launch_bounds__(64)
+k_deesser(const double *__restrict__ x, double *__restrict__ y, int64_t n, int seg, int warm,
+          double intensity, double maxdess, double iirAmount)
+{
+    const int64_t lane = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t s0 = lane * seg; if (s0 >= n) return;
+    const int64_t s1 = min(s0 + (int64_t)seg, n);
+    double s1v = 0, s2v = 0, s3v = 0, ratioA = 1.0, ratioB = 1.0, iirA = 0, iirB = 0;
+    int64_t i = max((int64_t)0, s0 - warm);
+    for (; i < s1; i++) {
+        double sample = x[i];
+        s3v = s2v; s2v = s1v; s1v = sample;
+        const double m1 = (s1v - s2v) * ((s1v - s2v) / 1.3);
+        const double m2 = (s2v - s3v) * ((s1v - s2v) / 1.3);
+        double sense = (m1 - m2) * ((m1 - m2) / 1.3);
+        const double attackspeed = 7.0 + sense * 1024;
+        sense = 1.0 + intensity * intensity * sense;
+        sense = fmin(sense, intensity);
+        const double recovery = 1.0 + (0.01 / sense);
+        const double offset = 1.0 - fabs(sample);
+        if (i & 1) {        // flip starts at 0 -> B on even samples, A on odd samples
+            iirA = (iirA * (1.0 - (offset * iirAmount))) + (sample * (offset * iirAmount));
+            if (ratioA < sense) ratioA = ((ratioA * attackspeed) + sense) / (attackspeed + 1.0);
+            else ratioA = 1.0 + ((ratioA - 1.0) / recovery);
+            ratioA = fmin(ratioA, maxdess);
+            sample = iirA + ((sample - iirA) / ratioA);
+        } else {
+            iirB = (iirB * (1.0 - (offset * iirAmount))) + (sample * (offset * iirAmount));
+            if (ratioB < sense) ratioB = ((ratioB * attackspeed) + sense) / (attackspeed + 1.0);
+            else ratioB = 1.0 + ((ratioB - 1.0) / recovery);
+            ratioB = fmin(ratioB, maxdess);
+            sample = iirB + ((sample - iirB) / ratioB);
+        }
+        if (i >= s0) y[i] = sample;
+    }
+}
+
+Sig jt_deesser(jt_ctx *c, const Sig &in, double intensity_opt, double max_opt, double freq_opt)
+{
+    if (in.fmt != JT_FMT_DBL) JT_THROW(JT_ERR_INVALID_ARG, "deesser expects f64 input");
+    Sig o = in; o.d = jt_dalloc<double>(c, in.n);
+    if (in.n <= 0) return o;
+    const double overallscale = in.rate < 44100 ? 44100.0 / in.rate : in.rate / 44100.0;
+    const double intensity = pow(intensity_opt, 5) * (8192 / overallscale);
+    const double maxdess = 1.0 / pow(10.0, ((max_opt - 1.0) * 48.0) / 20);
+    const double iirAmount = pow(freq_opt, 2) / overallscale;
+    // slowest-forgetting state: ratio release, factor 1/(1 + 0.01/sense) per two samples with sense <= maxdess
+    int64_t warm = (int64_t)(37.0 * 2.0 * std::fmax(maxdess, 1.0) / 0.01) + 64;
+    if (warm & 1) warm++;                                     // keep the A/B alternation phase
+    if (warm > (1 << 22)) warm = 1 << 22;
+    const int seg = 32768;
+    const int64_t lanes = (in.n + seg - 1) / seg;
+    JtLaunch L(c, "deesser");
+    k_deesser<<<(int)((lanes + 63) / 64), 64, 0, c->stream>>>((const double *)in.d, (double *)o.d, in.n, seg, (int)warm, intensity, maxdess, iirAmount);
+    return o;
+}

@@ -121,3 +121,97 @@ def aspectralstats(x, rate, win_size=2048):
     rows = np.zeros((max(cap, 1), NSPEC), dtype=np.float32)
     k = lib().orc_aspectralstats(_ptr(x), len(x), rate, win_size, _ptr(rows), cap)
     return rows[:k]
+
+
+# ---- Pass-2 / Pass-4 filters ---------------------------------------------------------------
+_D = C.c_double
+
+
+def _proto(name, restype, argtypes):
+    f = getattr(lib(), name)
+    f.restype = restype
+    f.argtypes = argtypes
+    return f
+
+
+def biquad(x, rate, kind, freq, q=0.707, normalize=False, tdii=False, mix=1.0):
+    x = np.ascontiguousarray(x)
+    c = np.zeros(5)
+    _proto("orc_biquad_design", None, [C.c_int, _D, _D, C.c_int, C.c_int, _P])(1 if kind == "highpass" else 0, freq, q, rate, int(normalize), _ptr(c))
+    name = {np.dtype(np.float32): "orc_biquad_f32", np.dtype(np.float64): "orc_biquad_f64", np.dtype(np.int16): "orc_biquad_s16"}[x.dtype]
+    out = np.zeros_like(x)
+    _proto(name, None, [_P, _P, _I64, _P, C.c_int, _D])(_ptr(x), _ptr(out), len(x), _ptr(c), int(tdii), mix)
+    return out
+
+
+def agate(x, rate, threshold, ratio, attack, release, range_, knee, makeup=1.0, detection_rms=True):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.zeros_like(x)
+    _proto("orc_agate", None, [_P, _P, _I64, C.c_int] + [_D] * 7 + [C.c_int])(_ptr(x), _ptr(out), len(x), rate, threshold, ratio, attack, release, range_, knee, makeup, int(detection_rms))
+    return out
+
+
+def acompressor(x, rate, threshold, ratio, attack, release, makeup, knee, mix=1.0, detection_rms=True):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.zeros_like(x)
+    _proto("orc_acompressor", None, [_P, _P, _I64, C.c_int] + [_D] * 7 + [C.c_int])(_ptr(x), _ptr(out), len(x), rate, threshold, ratio, attack, release, makeup, knee, mix, int(detection_rms))
+    return out
+
+
+def deesser(x, rate, i, m=0.5, f=0.5):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.zeros_like(x)
+    _proto("orc_deesser", None, [_P, _P, _I64, C.c_int, _D, _D, _D])(_ptr(x), _ptr(out), len(x), rate, i, m, f)
+    return out
+
+
+def volume_f32(x, volume):
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    out = np.zeros_like(x)
+    _proto("orc_volume_f32", None, [_P, _P, _I64, _D])(_ptr(x), _ptr(out), len(x), volume)
+    return out
+
+
+def anlmdn(x, rate, s=0.00001, p=0.002, r=0.006, m=11.0):
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    out = np.zeros_like(x)
+    _proto("orc_anlmdn", C.c_int, [_P, _P, _I64, C.c_int, _D, _D, _D, _D])(_ptr(x), _ptr(out), len(x), rate, s, p, r, m)
+    return out
+
+
+def alimiter(x, rate, limit, attack=5.0, release=50.0, level_in=1.0, level_out=1.0, level=True, asc=False, asc_level=0.5):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.zeros_like(x)
+    r = _proto("orc_alimiter", C.c_int, [_P, _P, _I64, C.c_int, _D, _D, _D, _D, _D, C.c_int, C.c_int, _D])(
+        _ptr(x), _ptr(out), len(x), rate, limit, attack, release, level_in, level_out, int(level), int(asc), asc_level)
+    assert r >= 0
+    return out
+
+
+def adeclick(x, rate, w=55.0, o=75.0, a=2.0, t=2.0, b=2.0, method_save=True):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.zeros_like(x)
+    det = _I64(0)
+    r = _proto("orc_adeclick", _I64, [_P, _P, _I64, C.c_int, _D, _D, _D, _D, _D, C.c_int, C.POINTER(_I64)])(
+        _ptr(x), _ptr(out), len(x), rate, w, o, a, t, b, int(method_save), C.byref(det))
+    assert r == len(x), r
+    return out, det.value
+
+
+def loudnorm_meter(x, rate, dual_mono=True):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    o = np.zeros(4)
+    _proto("orc_loudnorm_meter", C.c_int, [_P, _I64, C.c_int, C.c_int, _P])(_ptr(x), len(x), rate, int(dual_mono), _ptr(o))
+    return dict(I=o[0], LRA=o[1], thresh=o[2], sample_peak=o[3])
+
+
+def afftdn(x, rate, nr=12.0, nf=-50.0, nt=0, bn=None, tn=False, ad=0.5, fo=1.0, bm=1.25):
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    out = np.zeros_like(x)
+    bnp = None
+    if bn is not None:
+        bna = np.zeros(15)
+        bna[:len(bn)] = bn[:15]
+        bnp = _ptr(bna)
+    _proto("orc_afftdn", C.c_int, [_P, _P, _I64, C.c_int, _D, _D, C.c_int, _P, C.c_int, _D, _D, _D])(_ptr(x), _ptr(out), len(x), rate, nr, nf, nt, bnp, int(tn), ad, fo, bm)
+    return out

@@ -1,0 +1,101 @@
+"""GPU parity for the whole Pass 2 / Pass 3 / Pass 4 graphs and the four-pass driver
+(ProcessAudio, processor.go:78-216) against the oracle chain, on seeded synthetic input."""
+import math
+import numpy as np
+import pytest
+import oracle_graph as OG
+from jivetalking_b200 import gpudsp, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def rms(a):
+    return float(np.sqrt(np.mean(np.square(a.astype(np.float64))))) if len(a) else 0.0
+
+
+def pcm_close_s16(g, e):
+    assert g.dtype == np.int16 and e.dtype == np.int16 and len(g) == len(e)
+    d = (g.astype(np.int32) - e.astype(np.int32)) / 32768.0
+    assert rms(d) < 1e-4, rms(d)                 # north_star tolerance: 1e-4 RMS of full scale
+    assert np.max(np.abs(d)) < 2e-3
+
+
+GOLDEN_ADAPTIVE = [  # adaptive_test.go:109-124 (Pass-2 golden spec strings), wrapped like BuildFilterSpec does
+    "highpass=f=80:poles=2:width_type=q:width=0.707:normalize=1:a=tdii,lowpass=f=20500:poles=2:width_type=q:width=0.707:normalize=1,"
+    "anlmdn=s=0.00001:p=0.0060:r=0.0058:m=11,afftdn=nr=12:nt=w:tn=0:nf=-58,"
+    "agate=threshold=0.019953:ratio=2.0:attack=5.00:release=200:range=0.1995:knee=3.0:detection=rms:makeup=1.0,"
+    "acompressor=threshold=0.031623:ratio=3.0:attack=10:release=200:makeup=1.00:knee=4.0:detection=rms:mix=1.00",
+]
+
+
+def wrap_pass2(core, deesser=""):
+    return ("aformat=channel_layouts=mono," + core + deesser +
+            ",astats=metadata=1:measure_perchannel=all,aspectralstats=win_size=2048:win_func=hann:measure=all,"
+            "ebur128=metadata=1:peak=sample+true:dualmono=true:target=-16,"
+            "aformat=sample_rates=44100:channel_layouts=mono:sample_fmts=s16,asetnsamples=n=4096")
+
+
+@pytest.fixture(scope="module")
+def speech():
+    return synth.speech_like(40.0, 48000, seed=12345)
+
+
+def test_pass2_default_spec(ctx, speech):
+    spec = gpudsp.default_pass2_spec()
+    got = ctx.run_graph(spec, speech, 48000)
+    exp = OG.run_spec(spec, speech, 48000)
+    pcm_close_s16(got["pcm"], exp["pcm"])
+    assert len(got["pcm"]) % 4096 == 0
+    OG.assert_meta_close(got["meta"], exp["meta"], spectral_rtol=5e-3)
+
+
+def test_pass2_golden_adaptive_spec_with_deesser(ctx, speech):
+    spec = wrap_pass2(GOLDEN_ADAPTIVE[0], ",deesser=i=0.35:m=0.50:f=0.80")
+    got = ctx.run_graph(spec, speech, 48000)
+    exp = OG.run_spec(spec, speech, 48000)
+    pcm_close_s16(got["pcm"], exp["pcm"])
+    OG.assert_meta_close(got["meta"], exp["meta"], spectral_rtol=5e-3)
+
+
+def test_pass2_stereo_96k(ctx):
+    x = synth.stereo_from_mono(synth.speech_like(8.0, 96000, seed=21))
+    spec = gpudsp.default_pass2_spec()
+    got = ctx.run_graph(spec, x, 96000, channels=2)
+    exp = OG.run_spec(spec, x, 96000, channels=2)
+    pcm_close_s16(got["pcm"], exp["pcm"])
+
+
+def test_full_four_pass_chain(ctx, speech):
+    pcm, res = ctx.process_audio(speech, 48000)
+    # oracle: same orchestration in Python
+    p2 = OG.run_spec(gpudsp.default_pass2_spec(), speech, 48000)
+    last = [m for m in p2["meta"] if not math.isnan(m["I"])][-1]
+    out_i = last["I"]
+    out_tp = -120.0 if last["true_peak"] <= 0 else 20 * math.log10(last["true_peak"])
+    spec3, plan = gpudsp.build_pass3_spec(out_i, out_tp)
+    p3 = OG.run_spec(spec3, p2["pcm"], 44100, want_pcm=False)
+    st = gpudsp.LoudnormStats()
+    for k in ("input_i", "input_tp", "input_lra", "input_thresh"):
+        setattr(st, k, p3["loudnorm"][k])
+    spec4, eff, off = gpudsp.build_pass4_spec(plan, st)
+    p4 = OG.run_spec(spec4, p2["pcm"], 44100)
+    assert abs(res.filtered.input_i - out_i) < 0.011 and abs(res.filtered.input_tp - out_tp) < 0.2
+    for k in ("input_i", "input_tp", "input_lra", "input_thresh"):
+        assert abs(getattr(res.pass3, k) - p3["loudnorm"][k]) < 5e-3, k
+    assert res.pass4.normalization_type == p4["loudnorm"]["normalization_type"] == 0
+    pcm_close_s16(pcm, p4["pcm"])
+    fin = [m for m in p4["meta"] if not math.isnan(m["I"])][-1]
+    assert abs(res.final.input_i - fin["I"]) < 0.011
+    assert abs(res.final.input_lra - fin["LRA"]) < 0.05
+    # the chain's purpose (filters.go:75-82): -16 LUFS +-0.5 LU, true peak under -1 dBTP
+    assert abs(res.final.input_i - (-16.0)) <= 0.5
+    assert res.final.input_tp <= -1.0 + 0.1
+    assert res.n_out == len(pcm) and len(pcm) % 4096 == 0
+
+
+def test_cancel_and_reuse(ctx):
+    x = synth.speech_like(2.0, 48000, seed=1)
+    a = ctx.run_graph(gpudsp.pass1_spec(), x, 48000, want_pcm=False)
+    b = ctx.run_graph(gpudsp.pass1_spec(), x, 48000, want_pcm=False)
+    assert [m.r128_M for m in a["meta"][5:10]] == [m.r128_M for m in b["meta"][5:10]]     # deterministic, ctx reusable
+    assert ctx.launch_count() > 0
