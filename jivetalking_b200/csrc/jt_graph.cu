@@ -85,7 +85,7 @@ std::vector<FilterNode> jt_parse_spec(const std::string &spec)
 
 double jt_wire(const char *fmt, double v)
 {
-    char b[128];
+    char b[512];          // "%f" of DBL_MAX (astats Min_difference on a 1-sample stream) is 316 characters
     snprintf(b, sizeof(b), fmt, v);
     return strtod(b, nullptr);
 }

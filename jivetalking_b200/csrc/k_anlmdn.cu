@@ -14,9 +14,9 @@
 #include "jt_device.cuh"
 
 #define NLM_CHUNK 32
-#define NLM_MAXWARPS 16
+#define NLM_MAXWARPS 32
 
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(1024)
 k_anlmdn(const float *__restrict__ x, float *__restrict__ y, int64_t n, int K, int S, float sw, float smooth,
          float lut_scale, int64_t n_hops)
 {
@@ -91,7 +91,7 @@ Sig jt_anlmdn(jt_ctx *c, const Sig &in, double strength, double patch_s, double 
     if (K < 1 || S < 1) JT_THROW(JT_ERR_INVALID_ARG, "anlmdn patch/research too small for %d Hz", in.rate);
     const int H = 2 * K + 1, N = H + 2 * (K + S);
     const int threads = ((2 * S + 31) / 32) * 32;
-    if (threads > 512) JT_THROW(JT_ERR_UNSUPPORTED, "anlmdn research radius %d samples (max 256)", S);
+    if (threads > 1024) JT_THROW(JT_ERR_UNSUPPORTED, "anlmdn research radius %d samples (max 512)", S);
     Sig o = in; o.d = jt_dalloc<float>(c, in.n);
     if (in.n <= 0) return o;
     const float m = (float)smooth_m, a = (float)strength;

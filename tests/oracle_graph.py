@@ -341,11 +341,14 @@ def _close(a, b, atol, rtol=0.0):
 
 ASTATS_TOL = {  # (atol, rtol) on the "%f"-printed values
     "Noise_floor_count": (1e9, 0.0),     # ties on equal window maxima are float-representation dependent
+    "Dynamic_range": (0.02, 0.0),        # 20log10(2*peak / smallest non-zero |sample|): the smallest f64 sample of a
+                                         # processed stream is itself rounding noise
+    "Min_difference": (1e-9, 1e-6), "Flat_factor": (1e-3, 0.0),
     "Entropy": (2e-6, 0), "Zero_crossings": (0, 0), "Bit_depth": (0, 0), "Number_of_samples": (0, 0),
 }
 
 
-def assert_meta_close(got, exp, spectral_rtol=2e-3, spectral_atol=1e-9):
+def assert_meta_close(got, exp, spectral_rtol=2e-3, spectral_atol=1e-9, astats_atol=2e-6):
     """got: list of gpudsp.FrameMeta; exp: list of dicts from analysis_meta()."""
     assert len(got) == len(exp), (len(got), len(exp))
     # signed statistics (skewness, slope, decrease) cancel towards 0: scale their absolute tolerance
@@ -360,13 +363,13 @@ def assert_meta_close(got, exp, spectral_rtol=2e-3, spectral_atol=1e-9):
                              ("sample_peak", g.r128_sample_peak, e["sample_peak"])):
             assert _close(gv, ev, 0.0011), (i, name, gv, ev)
         for k in range(13):
-            assert _close(g.spectral[k], e["spectral"][k], spectral_atol + 2e-4 * col_scale[k], spectral_rtol), (i, "spectral", k, g.spectral[k], e["spectral"][k])
+            assert _close(g.spectral[k], e["spectral"][k], spectral_atol + 2e-4 * col_scale[k] + (2e-4 if k in (4, 5) else 0.0), spectral_rtol), (i, "spectral", k, g.spectral[k], e["spectral"][k])
         if e["astats"] is None:
             assert all(math.isnan(g.astats[k]) for k in range(len(AS_NAMES))), (i, "unexpected astats")
         else:
             if not e.get("overall_only"):
                 for k, name in enumerate(AS_NAMES):
-                    atol, rtol = ASTATS_TOL.get(name, (2e-6, 1e-9))
+                    atol, rtol = ASTATS_TOL.get(name, (astats_atol, 1e-9 if astats_atol < 1e-5 else 1e-4))
                     assert _close(g.astats[k], e["astats"][name], atol, rtol), (i, name, g.astats[k], e["astats"][name])
-            assert _close(g.astats_overall_RMS_level, e["astats"]["RMS_level"], 2e-6), (i, "overall rms")
-            assert _close(g.astats_overall_Peak_level, e["astats"]["Peak_level"], 2e-6), (i, "overall peak")
+            assert _close(g.astats_overall_RMS_level, e["astats"]["RMS_level"], astats_atol), (i, "overall rms")
+            assert _close(g.astats_overall_Peak_level, e["astats"]["Peak_level"], astats_atol), (i, "overall peak")
