@@ -456,13 +456,17 @@ static void process_device(jt_ctx *c, const void *d_in, int64_t n_frames, int ra
     jt_process_result R; memset(&R, 0, sizeof(R));
     const double tI = -16.0, tTP = -1.0, tLRA = 20.0;          // defaultLoudnormConfig, filters.go:523-532
     // Pass 1
+    size_t mark = c->allocs.size();
     analyse_device(c, d_in, n_frames, rate, channels, fmt, 4096, &R.input, nullptr, 0, nullptr);
+    jt_release_since(c, mark, nullptr);
     jt_check_cancel(c);
     // Pass 2
     GraphResult g2;
     jt_graph_run(c, pass2_spec ? pass2_spec : PASS2_DEFAULT_SPEC, d_in, n_frames, rate, channels, fmt, 4096, true, true, g2);
     { MeasAcc a; for (auto &m : g2.meta) a.add(m); a.finish((double)g2.out.n / g2.out.rate); R.filtered = a.m; }
     if (g2.out.fmt != JT_FMT_S16 || g2.out.rate != 44100) JT_THROW(JT_ERR_SPEC, "Pass-2 spec must end in the s16/44.1 kHz output stage (processor.go:379-384)");
+    jt_release_since(c, mark, g2.out.d);          // keep only the Pass-2 output ("the FLAC on disk")
+    mark = c->allocs.size();
     jt_check_cancel(c);
     // Pass 3: the Pass-2 output is re-read as the s16 FLAC the reference wrote (processor.go:126-146)
     char spec3[1024], spec4[4096];
@@ -471,6 +475,7 @@ static void process_device(jt_ctx *c, const void *d_in, int64_t n_frames, int ra
     GraphResult g3;
     jt_graph_run(c, spec3, g2.out.d, g2.out.n, 44100, 1, JT_FMT_S16, 4096, false, false, g3);
     R.pass3 = g3.ln;
+    jt_release_since(c, mark, nullptr);
     const double mI = jt_wire("%.2f", R.pass3.input_i);
     if (std::isinf(mI) || std::isnan(mI) || mI < -70.0) JT_THROW(JT_ERR_INVALID_ARG, "cannot normalise silent audio (measured %.1f LUFS)", mI);
     jt_check_cancel(c);

@@ -40,6 +40,7 @@ struct JtError { int code; std::string msg; };
 void *jt_dalloc_bytes(jt_ctx *c, size_t bytes);
 template <class T> static inline T *jt_dalloc(jt_ctx *c, size_t n) { return (T *)jt_dalloc_bytes(c, (n ? n : 1) * sizeof(T)); }
 void jt_release_all(jt_ctx *c);
+void jt_release_since(jt_ctx *c, size_t mark, const void *keep);   // free allocations made after `mark`, except the one holding `keep`
 void jt_check_cancel(jt_ctx *c);
 void jt_flush_timing(jt_ctx *c);
 

@@ -4,6 +4,7 @@
 #include "jt_device.cuh"
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 
 // ---------------------------------------------------------------------------------------
 // context / memory / launch bookkeeping
@@ -22,6 +23,16 @@ void jt_release_all(jt_ctx *c)
 {
     for (void *p : c->allocs) cudaFreeAsync(p, c->stream);
     c->allocs.clear();
+}
+
+void jt_release_since(jt_ctx *c, size_t mark, const void *keep)
+{
+    std::vector<void *> kept(c->allocs.begin(), c->allocs.begin() + std::min(mark, c->allocs.size()));
+    for (size_t i = mark; i < c->allocs.size(); i++) {
+        if (c->allocs[i] == keep) kept.push_back(c->allocs[i]);
+        else cudaFreeAsync(c->allocs[i], c->stream);
+    }
+    c->allocs.swap(kept);
 }
 
 void jt_check_cancel(jt_ctx *c)

@@ -1,4 +1,4 @@
-"""Test-side composition of the CPU oracle (oracle/) into the sink-frame metadata wire the
+"""ORACLE (test infrastructure only): composition of the CPU oracle filters (oracle/*.c) into the sink-frame metadata wire the
 reference reads (analyser_metrics.go:432-483), independent of the product's C++ executor.
 Frame cadence follows libavfilter's re-framing rules as described in SURVEY.md 8a-bis:
 4096-sample decoder frames -> astats stamps (cumulative at frame end) -> aspectralstats
