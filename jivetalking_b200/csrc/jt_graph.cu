@@ -83,12 +83,60 @@ std::vector<FilterNode> jt_parse_spec(const std::string &spec)
     return nodes;
 }
 
-double jt_wire(const char *fmt, double v)
+static double wire_slow(const char *fmt, double v)
 {
     char b[512];          // "%f" of DBL_MAX (astats Min_difference on a 1-sample stream) is 316 characters
     snprintf(b, sizeof(b), fmt, v);
     return strtod(b, nullptr);
 }
+
+// snprintf + strtod round trip without the text: scale to an integer, round, scale back.  Powers of ten
+// up to 1e22 are exact doubles and IEEE division / multiplication round once, so q / 10^k is the double
+// nearest to the printed decimal -- exactly what strtod returns.  Values whose scaled fraction sits within
+// 1e-6 of a rounding tie (where printf's exact-decimal rounding could differ) take the text path.
+static const double kPow10[23] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15,
+                                  1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+static bool wire_fixed(double v, int decimals, double *out)
+{
+    if (!std::isfinite(v) || fabs(v) > 1e9) return false;
+    const double t = v * kPow10[decimals], r = nearbyint(t);
+    if (fabs(fabs(t - r) - 0.5) < 1e-6) return false;
+    *out = r / kPow10[decimals];
+    return true;
+}
+static bool wire_g6(double v, double *out)
+{
+    if (v == 0.0) { *out = v; return true; }
+    if (!std::isfinite(v)) return false;
+    const double a = fabs(v);
+    if (a < 1e-15 || a > 1e15) return false;
+    int e = (int)floor(log10(a));
+    for (int pass = 0; pass < 2; pass++) {
+        const int k = 5 - e;                                  // scale so that 6 significant digits are integral
+        const double t = k >= 0 ? a * kPow10[k] : a / kPow10[-k];
+        if (t < 99999.5 - 1e-3) { e--; continue; }
+        if (t >= 999999.5 - 1e-3) { if (t < 999999.5 + 1e-3) return false; e++; continue; }
+        const double r = nearbyint(t);
+        if (fabs(fabs(t - r) - 0.5) < 1e-6) return false;
+        const double m = k >= 0 ? r / kPow10[k] : r * kPow10[-k];
+        *out = v < 0 ? -m : m;
+        return true;
+    }
+    return false;
+}
+
+double jt_wire(const char *fmt, double v)
+{
+    double o;
+    if (fmt[0] == '%' && fmt[1] == '.' && fmt[2] == '3' && fmt[3] == 'f' && !fmt[4]) { if (wire_fixed(v, 3, &o)) return o; }
+    else if (fmt[0] == '%' && fmt[1] == '.' && fmt[2] == '2' && fmt[3] == 'f' && !fmt[4]) { if (wire_fixed(v, 2, &o)) return o; }
+    else if (fmt[0] == '%' && fmt[1] == 'f' && !fmt[2]) { if (wire_fixed(v, 6, &o)) return o; }
+    else if (fmt[0] == '%' && fmt[1] == 'g' && !fmt[2]) { if (wire_g6(v, &o)) return o; }
+    return wire_slow(fmt, v);
+}
+double jt_wire_text(const char *fmt, double v) { return wire_slow(fmt, v); }
+// test hook (tests/test_wire.py): fast path vs the literal snprintf/strtod round trip
+extern "C" double jt_debug_wire(const char *fmt, double v, int text) { return text ? wire_slow(fmt, v) : jt_wire(fmt, v); }
 
 // ---------------------------------------------------------------------------------------
 // frame bookkeeping
