@@ -294,6 +294,7 @@ static void analyse_device(jt_ctx *c, const void *d_in, int64_t n_frames, int ra
         JT_CUDA(cudaStreamSynchronize(c->stream));
     }
     MeasAcc acc;
+    JtHost hacc(c, "interval_accumulation");
     struct IvAcc { int frameCount = 0; double rawSS = 0; int64_t rawN = 0; double rawPeak = 0; double spec[JT_SP_COUNT] = {0}; bool specFound = false;
                    double mSum = 0, sSum = 0, tpMax = 0, spMax = 0; } ia;
     auto reset = [&]() { ia = IvAcc(); ia.tpMax = -120.0; ia.spMax = -120.0; };

@@ -459,6 +459,7 @@ void jt_graph_run(jt_ctx *c, const std::string &spec, const void *d_in, int64_t 
 
     // ---- sink-frame metadata ------------------------------------------------------------
     if (!want_meta) return;
+    JtHost hmeta(c, "meta_assembly");
     const size_t nf = E.frames.size();
     res.meta.resize(nf); res.meta_ready.resize(nf);
     int64_t last_tick = -1; long last_astats_frame = -1;

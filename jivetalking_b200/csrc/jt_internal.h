@@ -51,6 +51,14 @@ struct JtLaunch {
     ~JtLaunch();
 };
 
+// Host-side wall time of a section (only when kernel timing is enabled): shows up as a
+// "host:<name>" slot next to the kernel groups so bench.py can account for the non-kernel time.
+struct JtHost {
+    jt_ctx *c; int slot = -1; double t0 = 0;
+    JtHost(jt_ctx *ctx, const char *name);
+    ~JtHost();
+};
+
 // ---- device-resident mono signal --------------------------------------------------------
 struct Sig {
     int fmt = 0;        // JT_FMT_S16 / FLT / DBL

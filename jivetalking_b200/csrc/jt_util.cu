@@ -56,6 +56,18 @@ JtLaunch::~JtLaunch()
     cudaEventRecord(b, c->stream);
     c->pending.push_back({a, b, slot});
 }
+#include <chrono>
+static double host_now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+JtHost::JtHost(jt_ctx *ctx, const char *name) : c(ctx)
+{
+    if (!c->timing) return;
+    std::string nm = std::string("host:") + name;
+    for (size_t i = 0; i < c->slots.size(); i++) if (c->slots[i].name == nm) { slot = (int)i; break; }
+    if (slot < 0) { c->slots.push_back(JtTimingSlot{nm, 0, 0}); slot = (int)c->slots.size() - 1; }
+    t0 = host_now_ms();
+}
+JtHost::~JtHost() { if (slot >= 0) { c->slots[slot].ms += host_now_ms() - t0; c->slots[slot].launches++; } }
+
 void jt_flush_timing(jt_ctx *c)
 {
     for (auto &p : c->pending) {

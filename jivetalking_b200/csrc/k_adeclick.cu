@@ -2,215 +2,276 @@
 // "adeclick=t=1.7:w=55:o=50:m=s" (reference: filters.go:947-962, 513-521).
 // Per window: AR model (autocorrelation + Levinson-Durbin), prediction-error click detector
 // with burst fusion, least-squares interpolation of the flagged samples (LDL^T solve).
-// Every window depends on the input only -> one WARP per window, windows fully parallel.
-// All sums run in the scalar code's order with unfused multiply/add, so the result is
-// bit-identical to a sequential run.  The interpolation matrix is banded in click order
-// (entries vanish when two clicks are more than ar_order samples apart, and the LDL^T
-// fill-in provably stays inside the band), so the factorisation touches only the band:
-// same arithmetic, O(n*order^2) instead of O(n^3).
+// Every window depends on the input only, so each phase gets the parallelism that suits it:
+//   A  autocorrelation      CTA per window, one thread per lag, window staged in shared memory
+//   B  Levinson-Durbin      one thread per window (a 48-step dependent recursion, 131k windows/hour)
+//   C  detector + fusion    CTA per window, one thread per sample, click bitmap
+//   E  interpolation        warp per window: right-looking banded LDL^T in a 49x49 shared-memory ring
+//                           with the forward substitution fused, then the back substitution
+// Every sum runs in the scalar code's order with unfused multiply/add, so results are bit-identical
+// to a sequential run (tests assert equality).  The interpolation matrix is banded in click order
+// (two clicks more than ar_order samples apart do not couple, and LDL^T fill-in provably stays inside
+// the band): the right-looking update applies to element (j,i) exactly the subtractions
+// x -= (D_k*L_ik)*L_jk, k ascending, that the scalar left-looking loop applies.
 #include "jt_internal.h"
 #include "jt_device.cuh"
 
-#define DC_WARPS 4
-
-struct DcConst { int W, hop, skip, order, burst, bw; double threshold; };
+struct DcConst { int W, hop, skip, order, burst, bw, nwords; double threshold; };
 
 __device__ __forceinline__ double jdmul(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double jdadd(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ double jdsub(double a, double b) { return __dsub_rn(a, b); }
 
+// sample j of window w: the fifo is `skip` zeros followed by the stream; past the fifo's end
+// av_audio_fifo_peek leaves the previous peek's samples in place
+__device__ __forceinline__ double dc_sample(const double *__restrict__ x, int64_t n, int64_t w, int j, const DcConst &K)
+{
+    const int64_t fifo_len = (int64_t)K.skip + n;
+    int64_t ws = w;
+    if (w * (int64_t)K.hop + j >= fifo_len) ws = (fifo_len - 1 - j) >= 0 ? (fifo_len - 1 - j) / K.hop : -1;
+    if (ws < 0) return 0.0;
+    const int64_t s = ws * (int64_t)K.hop + j - K.skip;
+    return (s >= 0 && s < n) ? x[s] : 0.0;
+}
+
+// ---- A: autocorrelation -------------------------------------------------------------------
+__global__ void __launch_bounds__(64)
+k_dc_autocorr(const double *__restrict__ x, int64_t n, int64_t n_windows, DcConst K, double *__restrict__ r_out)
+{
+    extern __shared__ double s_in[];
+    for (int64_t w = blockIdx.x; w < n_windows; w += gridDim.x) {
+        __syncthreads();
+        for (int j = threadIdx.x; j < K.W; j += blockDim.x) s_in[j] = dc_sample(x, n, w, j, K);
+        __syncthreads();
+        const int l = threadIdx.x;
+        if (l <= K.order) {
+            double v = 0.0;
+            for (int j = l; j < K.W; j++) v = jdadd(v, jdmul(s_in[j], s_in[j - l]));
+            r_out[w * K.bw + l] = jdmul(v, 1. / K.W);
+        }
+    }
+}
+
+// ---- B: Levinson-Durbin (af_adeclick.c autoregression()) -----------------------------------
+#define DC_MAXORDER 128
+__global__ void __launch_bounds__(128)
+k_dc_levinson(const double *__restrict__ r_in, int64_t n_windows, DcConst K, double *__restrict__ acoef, double *__restrict__ sigmae)
+{
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_windows) return;
+    double r[DC_MAXORDER + 1], a[DC_MAXORDER + 1], k[DC_MAXORDER + 1];
+    const int order = K.order;
+    for (int i = 0; i <= order; i++) { r[i] = r_in[w * K.bw + i]; a[i] = 0.0; }
+    k[0] = a[0] = -r[1] / r[0];
+    double alpha = jdmul(r[0], jdsub(1., jdmul(k[0], k[0])));
+    for (int i = 1; i < order; i++) {
+        double eps = 0.;
+        for (int j = 0; j < i; j++) eps = jdadd(eps, jdmul(a[j], r[i - j]));
+        eps = jdadd(eps, r[i + 1]);
+        k[i] = -eps / alpha;
+        alpha = jdmul(alpha, jdsub(1., jdmul(k[i], k[i])));
+        for (int j = i - 1; j >= 0; j--) k[j] = jdadd(a[j], jdmul(k[i], a[i - j - 1]));
+        for (int j = 0; j <= i; j++) a[j] = k[j];
+    }
+    k[0] = 1.;
+    for (int i = 1; i <= order; i++) k[i] = a[i - 1];
+    bool finite = true;
+    for (int i = 0; i <= order; i++) { acoef[w * K.bw + i] = k[i]; finite = finite && isfinite(k[i]); }
+    sigmae[2 * w] = sqrt(alpha);
+    sigmae[2 * w + 1] = finite ? 1.0 : 0.0;
+}
+
+// ---- C: detector, burst fusion, edge clearing -> click bitmap + count ------------------------
+__global__ void __launch_bounds__(256)
+k_dc_detect(const double *__restrict__ x, int64_t n, int64_t n_windows, DcConst K, const double *__restrict__ acoef,
+            const double *__restrict__ sigmae, unsigned *__restrict__ bits_out, int *__restrict__ count_out)
+{
+    extern __shared__ double s_in[];                 // W samples, then order+1 coefficients
+    __shared__ unsigned s_bits[160], s_fill[160];
+    __shared__ int s_cnt;
+    double *kc = s_in + K.W;
+    for (int64_t w = blockIdx.x; w < n_windows; w += gridDim.x) {
+        __syncthreads();
+        const bool finite = sigmae[2 * w + 1] != 0.0;
+        if (!finite) {          // acoefficients not finite: the window passes through untouched
+            for (int j = threadIdx.x; j < K.nwords; j += blockDim.x) bits_out[w * K.nwords + j] = 0u;
+            if (threadIdx.x == 0) count_out[w] = 0;
+            continue;
+        }
+        for (int j = threadIdx.x; j < K.W; j += blockDim.x) s_in[j] = dc_sample(x, n, w, j, K);
+        for (int j = threadIdx.x; j <= K.order; j += blockDim.x) kc[j] = acoef[w * K.bw + j];
+        if (threadIdx.x == 0) s_cnt = 0;
+        __syncthreads();
+        const double thr = jdmul(sigmae[2 * w], K.threshold);
+        for (int i0 = 0; i0 < K.nwords * 32; i0 += blockDim.x) {
+            const int i = i0 + threadIdx.x; bool cflag = false;
+            if (i < K.W) {
+                double d = 0.0;
+                if (i >= K.order) for (int j = 0; j <= K.order; j++) d = jdadd(d, jdmul(kc[j], s_in[i - j]));
+                cflag = fabs(d) > thr;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, cflag);
+            if ((threadIdx.x & 31) == 0 && (i >> 5) < K.nwords) s_bits[i >> 5] = m;
+        }
+        __syncthreads();
+        // burst fusion: a gap between two consecutive original clicks at most `burst` apart is filled
+        for (int wd = threadIdx.x; wd < K.nwords; wd += blockDim.x) {
+            unsigned add = 0;
+            for (int b = 0; b < 32; b++) {
+                const int i = wd * 32 + b; if (i >= K.W) break;
+                if ((s_bits[wd] >> b) & 1u) continue;
+                int p = -1, q = -1;
+                for (int d = 1; d <= K.burst && p < 0; d++) { const int j = i - d; if (j >= 0 && ((s_bits[j >> 5] >> (j & 31)) & 1u)) p = j; }
+                if (p < 0) continue;
+                for (int d = 1; d <= K.burst && q < 0; d++) { const int j = i + d; if (j < K.W && ((s_bits[j >> 5] >> (j & 31)) & 1u)) q = j; }
+                if (q >= 0 && q - p <= K.burst) add |= 1u << b;
+            }
+            s_fill[wd] = add;
+        }
+        __syncthreads();
+        for (int wd = threadIdx.x; wd < K.nwords; wd += blockDim.x) {
+            unsigned m = s_bits[wd] | s_fill[wd];
+            for (int b = 0; b < 32; b++) { const int i = wd * 32 + b; if (i < K.order || i >= K.W - K.order) m &= ~(1u << b); }
+            bits_out[w * K.nwords + wd] = m;
+            if (m) atomicAdd(&s_cnt, __popc(m));
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) count_out[w] = s_cnt;
+    }
+}
+
+// ---- E: interpolation ----------------------------------------------------------------------
+#define DC_WARPS 4
 __global__ void __launch_bounds__(DC_WARPS * 32)
-k_adeclick(const double *__restrict__ x, double *__restrict__ y, int64_t n, int64_t n_windows, DcConst K,
-           double *__restrict__ scratch /* per warp: matrix n*bw + vector + yv + out */, size_t scratch_per_warp)
+k_dc_interp(const double *__restrict__ x, double *__restrict__ y, int64_t n, int64_t n_windows, DcConst K,
+            const double *__restrict__ acoef, const unsigned *__restrict__ bits_in, const int *__restrict__ count_in,
+            double *__restrict__ scratch, size_t scratch_per_warp, int *__restrict__ next_window)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int W = K.W, order = K.order, bw = K.bw;
-    const int nwords = (W + 31) / 32;
-    const size_t per_warp = (size_t)W * 8 + (size_t)nwords * 4 + (size_t)W * 2 + (size_t)4 * (order + 1) * 8 + 16;
-    unsigned char *base = smem_raw + (size_t)warp * ((per_warp + 15) & ~(size_t)15);
-    double *in = (double *)base;
-    double *r = in + W, *a = r + (order + 1), *kc = a + (order + 1), *aux = kc + (order + 1);
-    unsigned *bits = (unsigned *)(aux + (order + 1));
-    unsigned short *index = (unsigned short *)(bits + nwords);
-    const int64_t gw = (int64_t)blockIdx.x * DC_WARPS + warp, gstride = (int64_t)gridDim.x * DC_WARPS;
-    double *M = scratch + (size_t)gw * scratch_per_warp;       // persistent warps: gw < total warps launched
-    const int64_t fifo_len = (int64_t)K.skip + n;
-
-    for (int64_t w = gw; w < n_windows; w += gstride) {
-        const int64_t fpos = w * (int64_t)K.hop;
-        __syncwarp();
-        // window content; past the fifo's end av_audio_fifo_peek leaves the previous peek's samples
-        for (int j = lane; j < W; j += 32) {
-            int64_t ws = w;
-            if (fpos + j >= fifo_len) ws = (fifo_len - 1 - j) >= 0 ? (fifo_len - 1 - j) / K.hop : -1;
-            double v = 0.0;
-            if (ws >= 0) { const int64_t s = ws * (int64_t)K.hop + j - K.skip; if (s >= 0 && s < n) v = x[s]; }
-            in[j] = v;
-        }
-        for (int j = lane; j < nwords; j += 32) bits[j] = 0u;
-        __syncwarp();
-        // autocorrelation: one lane per lag, scalar order
-        for (int l0 = 0; l0 <= order; l0 += 32) {
-            const int l = l0 + lane;
-            if (l <= order) {
-                double v = 0.0;
-                for (int j = l; j < W; j++) v = jdadd(v, jdmul(in[j], in[j - l]));
-                r[l] = jdmul(v, 1. / W);
-            }
-        }
-        __syncwarp();
-        double sigmae = 0.0;
-        if (lane == 0) {        // Levinson-Durbin (af_adeclick.c autoregression())
-            for (int i = 0; i < order; i++) a[i] = 0.0;
-            kc[0] = a[0] = -r[1] / r[0];
-            double alpha = jdmul(r[0], jdsub(1., jdmul(kc[0], kc[0])));
-            for (int i = 1; i < order; i++) {
-                double eps = 0.;
-                for (int j = 0; j < i; j++) eps = jdadd(eps, jdmul(a[j], r[i - j]));
-                eps = jdadd(eps, r[i + 1]);
-                kc[i] = -eps / alpha;
-                alpha = jdmul(alpha, jdsub(1., jdmul(kc[i], kc[i])));
-                for (int j = i - 1; j >= 0; j--) kc[j] = jdadd(a[j], jdmul(kc[i], a[i - j - 1]));
-                for (int j = 0; j <= i; j++) a[j] = kc[j];
-            }
-            kc[0] = 1.;
-            for (int i = 1; i <= order; i++) kc[i] = a[i - 1];
-            sigmae = sqrt(alpha);
-        }
-        sigmae = __shfl_sync(0xffffffffu, sigmae, 0);
-        __syncwarp();
-        bool finite = true;
-        for (int i = lane; i <= order; i += 32) finite = finite && isfinite(kc[i]);
-        finite = __all_sync(0xffffffffu, finite);
-        int nclk = 0;
-        if (finite) {
-            // detection + threshold
-            const double thr = jdmul(sigmae, K.threshold);
-            for (int i0 = 0; i0 < W; i0 += 32) {
-                const int i = i0 + lane; bool c = false;
-                if (i < W && i >= order) {
-                    double d = 0.0;
-                    for (int j = 0; j <= order; j++) d = jdadd(d, jdmul(kc[j], in[i - j]));
-                    c = fabs(d) > thr;
-                } else if (i < W) c = fabs(0.0) > thr;
-                const unsigned m = __ballot_sync(0xffffffffu, c);
-                if (lane == 0) bits[i0 >> 5] = m;
-            }
-            __syncwarp();
-            // burst fusion: fill gaps between consecutive original clicks at most `burst` apart
-            unsigned fill[4] = {0, 0, 0, 0};       // this lane's words (W <= 4096)
-            for (int wd = lane, q = 0; wd < nwords; wd += 32, q++) {
-                unsigned add = 0;
-                for (int b = 0; b < 32; b++) {
-                    const int i = wd * 32 + b; if (i >= W) break;
-                    if ((bits[wd] >> b) & 1u) continue;
-                    int p = -1, qn = -1;
-                    for (int d = 1; d <= K.burst && p < 0; d++) { const int j = i - d; if (j >= 0 && ((bits[j >> 5] >> (j & 31)) & 1u)) p = j; }
-                    if (p < 0) continue;
-                    for (int d = 1; d <= K.burst && qn < 0; d++) { const int j = i + d; if (j < W && ((bits[j >> 5] >> (j & 31)) & 1u)) qn = j; }
-                    if (qn >= 0 && qn - p <= K.burst) add |= 1u << b;
-                }
-                if (q < 4) fill[q] = add;
-            }
-            __syncwarp();
-            for (int wd = lane, q = 0; wd < nwords; wd += 32, q++) if (q < 4) bits[wd] |= fill[q];
-            __syncwarp();
-            // clear the edges, compact the ordered index list
-            for (int wd = lane; wd < nwords; wd += 32) {
-                unsigned m = bits[wd];
-                for (int b = 0; b < 32; b++) { const int i = wd * 32 + b; if (i < order || i >= W - order) m &= ~(1u << b); }
-                bits[wd] = m;
-            }
-            __syncwarp();
-            int basec = 0;
-            for (int w0 = 0; w0 < nwords; w0 += 32) {
-                const int wd = w0 + lane;
-                const unsigned m = wd < nwords ? bits[wd] : 0u;
-                const int cnt = __popc(m);
-                int incl = cnt;
-                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-                int pos = basec + incl - cnt;
-                unsigned mm = m;
-                while (mm) { const int b = __ffs(mm) - 1; mm &= mm - 1; index[pos++] = (unsigned short)(wd * 32 + b); }
-                basec += __shfl_sync(0xffffffffu, incl, 31);
-            }
-            nclk = basec;
-            __syncwarp();
-        }
-        if (finite && nclk > 0) {
-            double *vec = M + (size_t)nclk * bw, *yv = vec + nclk, *outv = yv + nclk;
-            // aux = autocorrelation of the AR coefficients
-            for (int l0 = 0; l0 <= order; l0 += 32) {
-                const int l = l0 + lane;
-                if (l <= order) { double v = 0.0; for (int j = l; j <= order; j++) v = jdadd(v, jdmul(kc[j], kc[j - l])); aux[l] = jdmul(v, 1.); }
-            }
-            __syncwarp();
-            // banded matrix rows + right-hand side
-            for (int i = lane; i < nclk; i += 32) {
-                const int ii = index[i];
-                for (int cidx = 0; cidx < bw; cidx++) {
-                    const int k = i - (bw - 1) + cidx;
-                    double v = 0.0;
-                    if (k >= 0) { const int d = ii - (int)index[k]; if (d <= order) v = aux[d]; }
-                    M[(size_t)i * bw + cidx] = v;
-                }
-                double value = 0.;
-                for (int j = -order; j <= order; j++) {
-                    const int p = ii - j;
-                    if (!((bits[p >> 5] >> (p & 31)) & 1u)) value = jdsub(value, jdmul(in[p], aux[j < 0 ? -j : j]));
-                }
-                vec[i] = value;
-            }
-            __syncwarp();
-            // LDL^T inside the band.  entry (j,k) lives at M[j*bw + (k - j + bw - 1)]
-#define MAT(j, k) M[(size_t)(j) * bw + ((k) - (j) + bw - 1)]
-            bool ok = true;
-            for (int i = 0; i < nclk && ok; i++) {
-                double value = 0.0;
-                if (lane == 0) {
-                    value = MAT(i, i);
-                    for (int j = max(0, i - (bw - 1)); j < i; j++) value = jdsub(value, jdmul(jdmul(MAT(j, j), MAT(i, j)), MAT(i, j)));
-                    MAT(i, i) = value;
-                }
-                value = __shfl_sync(0xffffffffu, value, 0);
-                if (value == 0.) { ok = false; break; }
-                __syncwarp();
-                for (int j0 = i + 1; j0 < min(nclk, i + bw); j0 += 32) {
-                    const int j = j0 + lane;
-                    if (j < min(nclk, i + bw)) {
-                        double xv = MAT(j, i);
-                        for (int k = max(0, j - (bw - 1)); k < i; k++) xv = jdsub(xv, jdmul(jdmul(MAT(k, k), MAT(i, k)), MAT(j, k)));
-                        MAT(j, i) = xv / value;
-                    }
-                }
-                __syncwarp();
-            }
-            if (ok) {
-                if (lane == 0) {
-                    for (int i = 0; i < nclk; i++) {
-                        double value = vec[i];
-                        for (int j = max(0, i - (bw - 1)); j < i; j++) value = jdsub(value, jdmul(MAT(i, j), yv[j]));
-                        yv[i] = value;
-                    }
-                    for (int i = nclk - 1; i >= 0; i--) {
-                        double o = yv[i] / MAT(i, i);
-                        for (int j = i + 1; j < min(nclk, i + bw); j++) o = jdsub(o, jdmul(MAT(j, i), outv[j]));
-                        outv[i] = o;
-                    }
-                }
-                __syncwarp();
-                for (int i = lane; i < nclk; i += 32) in[index[i]] = outv[i];
-                __syncwarp();
-            }
-#undef MAT
-        }
-        // overlap-save: this window contributes hop samples starting at `skip`
-        for (int j = lane; j < K.hop; j += 32) {
-            const int64_t q = w * (int64_t)K.hop + j;
-            if (q < n) y[q] = in[K.skip + j];
-        }
+    const int order = K.order, bw = K.bw;                    // ring is bw x bw
+    __shared__ unsigned char s_pa[2048], s_pb[2048];   // pair table (a, b), b <= a <= 63, ordered by a then b
+    const int npairs_full = order * (order + 1) / 2;
+    for (int p = threadIdx.x; p < npairs_full; p += blockDim.x) {
+        int a = 1; while (a * (a + 1) / 2 <= p) a++;
+        s_pa[p] = (unsigned char)a; s_pb[p] = (unsigned char)(p - a * (a - 1) / 2 + 1);
     }
+    __syncthreads();
+    const size_t per_warp = ((size_t)bw * bw + 3 * (size_t)bw) * sizeof(double);
+    double *ring = (double *)(smem_raw + (size_t)warp * per_warp);
+    double *kc = ring + (size_t)bw * bw, *aux = kc + bw, *oring = aux + bw;
+    const int64_t gw = (int64_t)blockIdx.x * DC_WARPS + warp;
+    double *S = scratch + (size_t)gw * scratch_per_warp;
+    // scratch layout: Lg[nmax][order], Dg[nmax], vec[nmax], outv[nmax], idx (as int)[nmax]
+    const size_t nmax = (size_t)K.W;
+    double *Lg = S, *Dg = Lg + nmax * order, *vec = Dg + nmax, *outv = vec + nmax;
+    int *idx = (int *)(outv + nmax);
+#define RING(j, i) ring[(size_t)((j) % bw) * bw + ((i) % bw)]
+
+    for (;;) {
+        int64_t w = 0;
+        if (lane == 0) w = atomicAdd(next_window, 1);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        if (w >= n_windows) break;
+        const int nclk = count_in[w];
+        if (nclk <= 0) continue;
+        __syncwarp();
+        // ordered index list from the bitmap
+        int basec = 0;
+        for (int w0 = 0; w0 < K.nwords; w0 += 32) {
+            const int wd = w0 + lane;
+            const unsigned m = wd < K.nwords ? bits_in[w * K.nwords + wd] : 0u;
+            const int cnt = __popc(m);
+            int incl = cnt;
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+            int pos = basec + incl - cnt;
+            unsigned mm = m;
+            while (mm) { const int b = __ffs(mm) - 1; mm &= mm - 1; idx[pos++] = wd * 32 + b; }
+            basec += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        for (int l = lane; l <= order; l += 32) kc[l] = acoef[w * bw + l];
+        __syncwarp();
+        // aux = autocorrelation of the AR coefficients (scale 1)
+        for (int l = lane; l <= order; l += 32) {
+            double v = 0.0;
+            for (int j = l; j <= order; j++) v = jdadd(v, jdmul(kc[j], kc[j - l]));
+            aux[l] = jdmul(v, 1.);
+        }
+        __syncwarp();
+        // right-hand side: known neighbours of every click
+        for (int i = lane; i < nclk; i += 32) {
+            const int ii = idx[i];
+            double value = 0.;
+            for (int j = -order; j <= order; j++) {
+                const int p = ii - j;
+                const unsigned wordv = bits_in[w * K.nwords + (p >> 5)];
+                if (!((wordv >> (p & 31)) & 1u)) value = jdsub(value, jdmul(dc_sample(x, n, w, p, K), aux[j < 0 ? -j : j]));
+            }
+            vec[i] = value;
+        }
+        __syncwarp();
+        // rows 0 .. order enter the ring: A(j,i) = aux[idx_j - idx_i] inside the band, else 0
+        auto load_row = [&](int j) {
+            if (j >= nclk) return;
+            const int ij = idx[j];
+            for (int t = lane; t < bw; t += 32) {
+                const int i = j - t;
+                if (i < 0) break;
+                const int d = ij - idx[i];
+                RING(j, i) = d <= order ? aux[d] : 0.0;
+            }
+        };
+        for (int j = 0; j <= order; j++) load_row(j);
+        __syncwarp();
+        bool ok = true;
+        for (int k = 0; k < nclk; k++) {
+            const double Dk = RING(k, k);
+            if (Dk == 0.) { ok = false; break; }
+            const int amax = min(order, nclk - 1 - k);
+            const double yk = vec[k];
+            // column k: L(j,k) = A'(j,k) / D_k ; forward substitution v_j -= L(j,k) * y_k
+            for (int a = lane + 1; a <= amax; a += 32) {
+                const double L = RING(k + a, k) / Dk;
+                RING(k + a, k) = L;
+                Lg[(size_t)k * order + (a - 1)] = L;
+                vec[k + a] = jdsub(vec[k + a], jdmul(L, yk));
+            }
+            if (lane == 0) Dg[k] = Dk;
+            __syncwarp();
+            // trailing update: A'(k+a, k+b) -= (D_k * L(k+b,k)) * L(k+a,k), 1 <= b <= a <= amax
+            const int npairs = amax * (amax + 1) / 2;
+            for (int p = lane; p < npairs; p += 32) {
+                const int a = s_pa[p], b = s_pb[p];
+                const double Lb = RING(k + b, k), La = RING(k + a, k);
+                RING(k + a, k + b) = jdsub(RING(k + a, k + b), jdmul(jdmul(Dk, Lb), La));
+            }
+            __syncwarp();
+            load_row(k + bw);               // row k+order+1 takes the slot row k leaves
+            __syncwarp();
+        }
+        if (!ok) continue;                  // factorisation hit a zero pivot: af_adeclick.c leaves the window as is
+        // back substitution: out_i = y_i / D_i - sum_{j>i} L(j,i) * out_j, j ascending
+        for (int i = nclk - 1; i >= 0; i--) {
+            const int amax = min(order, nclk - 1 - i);
+            double prod0 = 0.0, prod1 = 0.0;
+            if (lane < amax) prod0 = jdmul(Lg[(size_t)i * order + lane], oring[(i + 1 + lane) % bw]);
+            if (lane + 32 < amax) prod1 = jdmul(Lg[(size_t)i * order + lane + 32], oring[(i + 33 + lane) % bw]);
+            double o = vec[i] / Dg[i];
+            for (int a = 0; a < amax; a++) {
+                const double pr = __shfl_sync(0xffffffffu, a < 32 ? prod0 : prod1, a & 31);
+                o = jdsub(o, pr);
+            }
+            if (lane == 0) { oring[i % bw] = o; outv[i] = o; }
+            __syncwarp();
+        }
+        // only the hop-sized middle of the window is emitted (overlap-save)
+        for (int i = lane; i < nclk; i += 32) {
+            const int p = idx[i] - K.skip;
+            if (p >= 0 && p < K.hop) { const int64_t q = w * (int64_t)K.hop + p; if (q < n) y[q] = outv[i]; }
+        }
+        __syncwarp();
+    }
+#undef RING
 }
 
 Sig jt_adeclick(jt_ctx *c, const Sig &in, double w_ms, double overlap_pct, double ar_pct, double threshold, double burst_pct, int method_save)
@@ -220,28 +281,40 @@ Sig jt_adeclick(jt_ctx *c, const Sig &in, double w_ms, double overlap_pct, doubl
     DcConst K;
     K.W = (int)(in.rate * w_ms / 1000.);
     if (K.W < 100) JT_THROW(JT_ERR_INVALID_ARG, "adeclick window too small");
-    if (K.W > 4096) JT_THROW(JT_ERR_UNSUPPORTED, "adeclick window of %d samples (max 4096)", K.W);
+    if (K.W > 5120) JT_THROW(JT_ERR_UNSUPPORTED, "adeclick window of %d samples (max 5120)", K.W);
     K.order = std::max((int)(K.W * ar_pct / 100.), 1);
+    if (K.order > 63) JT_THROW(JT_ERR_UNSUPPORTED, "adeclick AR order %d (max 63)", K.order);
     K.burst = (int)(K.W * burst_pct / 1000.);
     K.hop = (int)(K.W * (1. - (overlap_pct / 100.)));
     if (K.hop < 1) JT_THROW(JT_ERR_INVALID_ARG, "adeclick overlap too large");
-    K.skip = (K.W - K.hop) / 2; K.bw = K.order + 1; K.threshold = threshold;
+    K.skip = (K.W - K.hop) / 2; K.bw = K.order + 1; K.threshold = threshold; K.nwords = (K.W + 31) / 32;
     Sig o = in; o.d = jt_dalloc<double>(c, in.n);
     if (in.n <= 0) return o;
-    const int64_t n_windows = (in.n + K.hop - 1) / K.hop;
-    const int nwords = (K.W + 31) / 32;
-    size_t per_warp = (size_t)K.W * 8 + (size_t)nwords * 4 + (size_t)K.W * 2 + (size_t)4 * (K.order + 1) * 8 + 16;
-    per_warp = (per_warp + 15) & ~(size_t)15;
-    const size_t smem = per_warp * DC_WARPS;
-    if (smem > 220 * 1024) JT_THROW(JT_ERR_UNSUPPORTED, "adeclick window needs %zu bytes of shared memory", smem);
-    JT_CUDA(cudaFuncSetAttribute(k_adeclick, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (220 * 1024) / smem));
-    int grid = (int)std::min<int64_t>((n_windows + DC_WARPS - 1) / DC_WARPS, (int64_t)c->num_sms * per_sm);
-    if (grid < 1) grid = 1;
+    const int64_t nw = (in.n + K.hop - 1) / K.hop;
+    double *d_r = jt_dalloc<double>(c, (size_t)nw * K.bw), *d_a = jt_dalloc<double>(c, (size_t)nw * K.bw), *d_sig = jt_dalloc<double>(c, (size_t)nw * 2);
+    unsigned *d_bits = jt_dalloc<unsigned>(c, (size_t)nw * K.nwords);
+    int *d_cnt = jt_dalloc<int>(c, nw + 1);
+    int *d_next = d_cnt + nw;
+    JT_CUDA(cudaMemsetAsync(d_next, 0, sizeof(int), c->stream));
+    // the windows pass through except where clicks are repaired: out = in, then E overwrites
+    JT_CUDA(cudaMemcpyAsync(o.d, in.d, sizeof(double) * (size_t)in.n, cudaMemcpyDeviceToDevice, c->stream));
+    const size_t smemA = sizeof(double) * K.W, smemC = sizeof(double) * (K.W + K.bw);
+    JT_CUDA(cudaFuncSetAttribute(k_dc_autocorr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
+    JT_CUDA(cudaFuncSetAttribute(k_dc_detect, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC));
+    const size_t per_warp = ((size_t)K.bw * K.bw + 3 * (size_t)K.bw) * sizeof(double);
+    const size_t smemE = per_warp * DC_WARPS;
+    JT_CUDA(cudaFuncSetAttribute(k_dc_interp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemE));
+    int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / (smemE + 4096)));
+    int gridE = (int)std::min<int64_t>((nw + DC_WARPS - 1) / DC_WARPS, (int64_t)c->num_sms * per_sm);
+    if (gridE < 1) gridE = 1;
     const size_t nmax = (size_t)K.W;
-    const size_t scratch_per_warp = nmax * K.bw + 3 * nmax;
-    double *scratch = jt_dalloc<double>(c, scratch_per_warp * (size_t)grid * DC_WARPS);
-    JtLaunch L(c, "adeclick");
-    k_adeclick<<<grid, DC_WARPS * 32, smem, c->stream>>>((const double *)in.d, (double *)o.d, in.n, n_windows, K, scratch, scratch_per_warp);
+    const size_t scratch_per_warp = nmax * K.order + 3 * nmax + (nmax + 1) / 2 + 8;
+    double *scratch = jt_dalloc<double>(c, scratch_per_warp * (size_t)gridE * DC_WARPS);
+    JtLaunch L(c, "adeclick", 4);
+    k_dc_autocorr<<<jt_grid_for(nw, 1, c->num_sms, 64), 64, smemA, c->stream>>>((const double *)in.d, in.n, nw, K, d_r);
+    k_dc_levinson<<<(int)((nw + 127) / 128), 128, 0, c->stream>>>(d_r, nw, K, d_a, d_sig);
+    k_dc_detect<<<jt_grid_for(nw, 1, c->num_sms, 32), 256, smemC, c->stream>>>((const double *)in.d, in.n, nw, K, d_a, d_sig, d_bits, d_cnt);
+    k_dc_interp<<<gridE, DC_WARPS * 32, smemE, c->stream>>>((const double *)in.d, (double *)o.d, in.n, nw, K, d_a, d_bits, d_cnt,
+                                                            scratch, scratch_per_warp, d_next);
     return o;
 }

@@ -105,12 +105,24 @@ k_afftdn_fwd(const float *__restrict__ x, int64_t n, int64_t n_hops, AfConst K, 
 }
 
 // F2: max_var before / after each hop's floor update
-__global__ void k_afftdn_floor(const double *__restrict__ cand, int64_t n_hops, double nf0, double floor_, int track,
-                               double *__restrict__ mv_pre, double *__restrict__ mv_post)
+// The floor recurrence nf' = flag ? 0.1*cand + 0.9*nf : nf is affine in nf, so one CTA scans it:
+// each thread composes its slice of hops into (A, B), thread 0 chains the 1024 slices, every
+// thread replays its slice from its true entry value.
+__global__ void __launch_bounds__(1024)
+k_afftdn_floor(const double *__restrict__ cand, int64_t n_hops, double nf0, double floor_, int track,
+               double *__restrict__ mv_pre, double *__restrict__ mv_post)
 {
-    if (blockIdx.x || threadIdx.x) return;
-    double nf = nf0;
-    for (int64_t h = 0; h < n_hops; h++) {
+    __shared__ double sA[1024], sB[1024], sIn[1024];
+    const int t = threadIdx.x;
+    const int64_t per = (n_hops + 1023) / 1024, h0 = t * per, h1 = min(h0 + per, n_hops);
+    double A = 1.0, B = 0.0;
+    if (track) for (int64_t h = h0; h < h1; h++) if (cand[2 * h + 1] != 0.0) { A *= 0.9; B = 0.1 * cand[2 * h] + B * 0.9; }
+    sA[t] = A; sB[t] = B;
+    __syncthreads();
+    if (t == 0) { double nf = nf0; for (int i = 0; i < 1024; i++) { sIn[i] = nf; nf = sA[i] * nf + sB[i]; } }
+    __syncthreads();
+    double nf = sIn[t];
+    for (int64_t h = h0; h < h1; h++) {
         mv_pre[h] = floor_ * exp((100.0 + nf) * AF_C);
         if (track && cand[2 * h + 1] != 0.0) nf = 0.1 * cand[2 * h] + nf * 0.9;
         mv_post[h] = floor_ * exp((100.0 + nf) * AF_C);
@@ -334,7 +346,7 @@ Sig jt_afftdn(jt_ctx *c, const Sig &in, const AfftdnParams &P)
     {
         JtLaunch L(c, "afftdn", 4);
         k_afftdn_fwd<<<jt_grid_for(n_hops, 1, c->num_sms, 16), AF_THREADS, smem1, c->stream>>>((const float *)in.d, in.n, n_hops, K, d_window, d_tw, d_spec, P.tn, d_cand);
-        k_afftdn_floor<<<1, 1, 0, c->stream>>>(d_cand, n_hops, P.nf, K.floor_, P.tn, d_pre, d_post);
+        k_afftdn_floor<<<1, 1024, 0, c->stream>>>(d_cand, n_hops, P.nf, K.floor_, P.tn, d_pre, d_post);
         k_afftdn_core<<<(int)((n_hops + chunk - 1) / chunk), AF_THREADS, smem3, c->stream>>>(d_spec, n_hops, chunk, warm, K, d_rel, d_blo, d_b2b, d_alpha, d_beta, d_spread, d_pre, d_post, d_tw, d_frames);
         k_afftdn_ola<<<jt_grid_for(in.n, 256, c->num_sms, 16), 256, 0, c->stream>>>(d_frames, d_window, in.n, n_hops, K.A, K.W, (float *)o.d);
     }

@@ -11,30 +11,41 @@
 // The de-esser is a per-sample nonlinear recurrence (Airwindows DeEss) and runs as lanes too.
 #include "jt_internal.h"
 #include "jt_device.cuh"
+#include "jt_lanes.cuh"
 
 #define FAKE_INFINITY (65536.0 * 65536.0)
 
 // ---- switching envelope follower ----------------------------------------------------------
+#define ENV_R 64
 __global__ void __launch_bounds__(64)
 k_envelope(const double *__restrict__ x, double *__restrict__ env, int64_t n, int seg, int warm,
            double attack_coeff, double release_coeff, int rms)
 {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int warp = threadIdx.x >> 5;
+    unsigned char *wsm = smem + (size_t)warp * (LaneStage<double, ENV_R>::WARP_BYTES + LaneStore<double, ENV_R>::WARP_BYTES);
     const int64_t lane = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t s0 = lane * seg; if (s0 >= n) return;
-    const int64_t s1 = min(s0 + (int64_t)seg, n);
+    const int64_t s0 = min(lane * seg, n), s1 = min(s0 + (int64_t)seg, n);
+    const int64_t begin = max((int64_t)0, s0 - warm);
+    LaneStage<double, ENV_R> in; LaneStore<double, ENV_R> out;
+    in.init(wsm, x + begin, lane * seg < n ? s1 - begin : 0);
+    out.init(wsm + LaneStage<double, ENV_R>::WARP_BYTES, env + s0);
     double e = 0.0;
-    int64_t i = max((int64_t)0, s0 - warm);
+    in.prefetch();
+    for (int tile = 0; tile < in.ntiles; tile++) {
+        in.prefetch();
+        const double *row = in.wait(tile);
+        const int nv = in.valid(tile);
+        const int64_t i0 = begin + (int64_t)tile * ENV_R;
 #pragma unroll 4
-    for (; i < s0; i++) {
-        double d = fabs(x[i]); if (rms) d *= d;
-        e += (d - e) * (d > e ? attack_coeff : release_coeff);
+        for (int k = 0; k < nv; k++) {
+            double d = fabs(row[k]); if (rms) d *= d;
+            e += (d - e) * (d > e ? attack_coeff : release_coeff);
+            if (i0 + k >= s0) out.put(e);
+        }
+        in.release();
     }
-#pragma unroll 4
-    for (; i < s1; i++) {
-        double d = fabs(x[i]); if (rms) d *= d;
-        e += (d - e) * (d > e ? attack_coeff : release_coeff);
-        env[i] = e;
-    }
+    out.finish();
 }
 
 static double *run_envelope(jt_ctx *c, const Sig &in, double attack_ms, double release_ms, int rms)
@@ -47,7 +58,9 @@ static double *run_envelope(jt_ctx *c, const Sig &in, double attack_ms, double r
     const int seg = 32768;
     const int64_t lanes = (in.n + seg - 1) / seg;
     JtLaunch L(c, "envelope_follower");
-    k_envelope<<<(int)((lanes + 63) / 64), 64, 0, c->stream>>>((const double *)in.d, env, in.n, seg, (int)warm, ac, rc, rms);
+    const size_t smem = 2 * (LaneStage<double, ENV_R>::WARP_BYTES + LaneStore<double, ENV_R>::WARP_BYTES);
+    JT_CUDA(cudaFuncSetAttribute(k_envelope, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_envelope<<<(int)((lanes + 63) / 64), 64, smem, c->stream>>>((const double *)in.d, env, in.n, seg, (int)warm, ac, rc, rms);
     return env;
 }
 

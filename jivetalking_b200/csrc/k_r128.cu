@@ -140,6 +140,7 @@ void jt_ebur128(jt_ctx *c, const Sig &in, bool dualmono, bool true_peak, R128Res
     JT_CUDA(cudaStreamSynchronize(c->stream));
 
     // host: f_ebur128.c filter_frame() tail, once per 100 ms
+    JtHost hfin(c, "r128_finalize");
     out.M.resize(nt); out.S.resize(nt); out.sp_cum.resize(nt); out.tp_cum.resize(nt);
     std::vector<uint32_t> h400(HIST_SIZE, 0), h3000(HIST_SIZE, 0);
     double kept400 = 0, kept3000 = 0; uint64_t nk400 = 0, nk3000 = 0;

@@ -28,7 +28,22 @@ static double bessel_i0(double x)
 }
 static int64_t gcd_i64(int64_t a, int64_t b) { while (b) { int64_t t = a % b; a = b; b = t; } return a; }
 
+static SwrPlan swr_plan_design(int in_rate, int out_rate);
+
+// The design is a pure function of the two rates (~20k Bessel evaluations for 44.1k -> 192k):
+// memoised process-wide, immutable once built.
+#include <mutex>
 SwrPlan jt_swr_plan(int in_rate, int out_rate)
+{
+    static std::mutex mu;
+    static std::map<std::pair<int, int>, SwrPlan> cache;
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find({in_rate, out_rate});
+    if (it == cache.end()) it = cache.emplace(std::make_pair(in_rate, out_rate), swr_plan_design(in_rate, out_rate)).first;
+    return it->second;
+}
+
+static SwrPlan swr_plan_design(int in_rate, int out_rate)
 {
     SwrPlan p; p.in_rate = in_rate; p.out_rate = out_rate;
     if (in_rate == out_rate) { p.identity = true; p.phase_count = 1; p.filter_length = 1; p.div = 1; return p; }

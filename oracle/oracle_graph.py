@@ -370,6 +370,8 @@ def assert_meta_close(got, exp, spectral_rtol=2e-3, spectral_atol=1e-9, astats_a
             if not e.get("overall_only"):
                 for k, name in enumerate(AS_NAMES):
                     atol, rtol = ASTATS_TOL.get(name, (astats_atol, 1e-9 if astats_atol < 1e-5 else 1e-4))
+                    if astats_atol >= 1e-5 and name in ("Zero_crossings", "Zero_crossings_rate", "Entropy"):
+                        atol, rtol = 1e-6, 1e-3       # samples hovering around zero flip sign with float round-off
                     assert _close(g.astats[k], e["astats"][name], atol, rtol), (i, name, g.astats[k], e["astats"][name])
             assert _close(g.astats_overall_RMS_level, e["astats"]["RMS_level"], astats_atol), (i, "overall rms")
             assert _close(g.astats_overall_Peak_level, e["astats"]["Peak_level"], astats_atol), (i, "overall peak")
