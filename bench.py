@@ -193,7 +193,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    x = make_input(12345 + rank, args.minutes)                      # C2 / C3: seeds 12345 + rank
+    from jivetalking_b200 import shard
+    my_files = shard.assign_files(world, rank, world)               # one file per GPU (configs[2])
+    x = make_input(shard.stream_seed(12345, my_files[0]), args.minutes)   # C2 / C3: seeds 12345 + file index
     n = len(x)
     h_in = torch.from_numpy(x).pin_memory()
     d_in = h_in.cuda(non_blocking=False)

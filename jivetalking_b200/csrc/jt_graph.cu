@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <climits>
+#include <thread>
 
 // ---------------------------------------------------------------------------------------
 // parsing
@@ -181,7 +182,7 @@ struct Exec {
     jt_ctx *c; Sig cur; int link_fmt; std::vector<FrameRef> frames;
     // analysis products
     bool has_astats = false, has_spec = false, has_r128 = false, astats_overall_only = false;
-    Sig astats_sig; R128Result r128; std::vector<float> spec_rows; int64_t spec_hops = 0;
+    Sig astats_sig, spec_sig; int spec_win = 2048; R128Result r128; std::vector<float> spec_rows; int64_t spec_hops = 0;
     void storage(int fmt) { cur = jt_convert(c, cur, fmt); link_fmt = fmt; }
     void materialise() { if (cur.fmt != link_fmt) cur = jt_convert(c, cur, link_fmt); }
 };
@@ -435,8 +436,7 @@ void jt_graph_run(jt_ctx *c, const std::string &spec, const void *d_in, int64_t 
             const int win = (int)f.num("win_size", "", 2048);
             if (f.str("win_func", "", "hann") != "hann" && f.str("win_func", "", "hann") != "hanning") JT_THROW(JT_ERR_UNSUPPORTED, "aspectralstats win_func");
             if (f.num("overlap", "", 0.5) != 0.5) JT_THROW(JT_ERR_UNSUPPORTED, "aspectralstats overlap");
-            if (want_meta) jt_aspectralstats(c, E.cur, win, E.spec_rows, E.spec_hops);
-            E.has_spec = true;
+            E.has_spec = true; E.spec_sig = E.cur; E.spec_win = win;    // computed once the sink cadence is known
             E.frames = reframe(E.frames, E.cur.n, win / 2);
             for (size_t j = 0; j < E.frames.size(); j++) E.frames[j].hop = (int32_t)j;
         } else if (f.name == "ebur128") {
@@ -459,39 +459,64 @@ void jt_graph_run(jt_ctx *c, const std::string &spec, const void *d_in, int64_t 
 
     // ---- sink-frame metadata ------------------------------------------------------------
     if (!want_meta) return;
-    JtHost hmeta(c, "meta_assembly");
     const size_t nf = E.frames.size();
+    if (E.has_spec) {
+        // aspectralstats emits one row per 1024-sample hop, but a sink frame only ever shows the row of the
+        // hop holding its first sample: compute just those (plus predecessors for the flux term)
+        std::vector<int64_t> wanted; wanted.reserve(nf);
+        for (size_t i = 0; i < nf; i++) if (E.frames[i].hop >= 0) wanted.push_back(E.frames[i].hop);
+        jt_aspectralstats(c, E.spec_sig, E.spec_win, E.spec_rows, E.spec_hops, &wanted);
+    }
+    JtHost hmeta(c, "meta_assembly");
     res.meta.resize(nf); res.meta_ready.resize(nf);
     int64_t last_tick = -1; long last_astats_frame = -1;
     for (size_t i = 0; i < nf; i++) {
         if (E.frames[i].tick >= 0) last_tick = std::max<int64_t>(last_tick, E.frames[i].tick);
         if (E.frames[i].astats_pos >= 0) last_astats_frame = (long)i;
     }
-    for (size_t i = 0; i < nf; i++) {
-        const FrameRef &fr = E.frames[i];
-        jt_frame_meta &m = res.meta[i];
-        double *dp = &m.r128_M;
-        const size_t ndbl = (sizeof(jt_frame_meta) - offsetof(jt_frame_meta, r128_M)) / sizeof(double);
-        for (size_t k = 0; k < ndbl; k++) dp[k] = NAN;
-        m.first_sample = fr.start; m.nb_samples = fr.nb; m.reserved = 0;
-        res.meta_ready[i] = fr.ready;
-        if (E.has_r128 && fr.tick >= 0 && fr.tick < E.r128.n_ticks) {
-            const int64_t k = fr.tick;
-            m.r128_M = jt_wire("%.3f", E.r128.M[k]); m.r128_S = jt_wire("%.3f", E.r128.S[k]);
-            m.r128_sample_peak = jt_wire("%.3f", E.r128.sp_cum[k]);
-            m.r128_true_peak = jt_wire("%.3f", E.r128.tp_cum[k]);
-            if (k == last_tick) {
-                m.r128_I = jt_wire("%.3f", E.r128.I); m.r128_LRA = jt_wire("%.3f", E.r128.LRA);
-                m.r128_LRA_low = jt_wire("%.3f", E.r128.LRA_low); m.r128_LRA_high = jt_wire("%.3f", E.r128.LRA_high);
+    // records are independent: the printf-rounding of ~20 values per sink frame is spread over host threads
+    auto fill = [&](size_t i0, size_t i1) {
+        for (size_t i = i0; i < i1; i++) {
+            const FrameRef &fr = E.frames[i];
+            jt_frame_meta &m = res.meta[i];
+            double *dp = &m.r128_M;
+            const size_t ndbl = (sizeof(jt_frame_meta) - offsetof(jt_frame_meta, r128_M)) / sizeof(double);
+            for (size_t k = 0; k < ndbl; k++) dp[k] = NAN;
+            m.first_sample = fr.start; m.nb_samples = fr.nb; m.reserved = 0;
+            res.meta_ready[i] = fr.ready;
+            if (E.has_r128 && fr.tick >= 0 && fr.tick < E.r128.n_ticks) {
+                const int64_t k = fr.tick;
+                m.r128_M = jt_wire("%.3f", E.r128.M[k]); m.r128_S = jt_wire("%.3f", E.r128.S[k]);
+                m.r128_sample_peak = jt_wire("%.3f", E.r128.sp_cum[k]);
+                m.r128_true_peak = jt_wire("%.3f", E.r128.tp_cum[k]);
+                if (k == last_tick) {
+                    m.r128_I = jt_wire("%.3f", E.r128.I); m.r128_LRA = jt_wire("%.3f", E.r128.LRA);
+                    m.r128_LRA_low = jt_wire("%.3f", E.r128.LRA_low); m.r128_LRA_high = jt_wire("%.3f", E.r128.LRA_high);
+                }
             }
+            if (E.has_spec && fr.hop >= 0 && fr.hop < E.spec_hops)
+                for (int k = 0; k < JT_SP_COUNT; k++) m.spectral[k] = jt_wire("%g", (double)E.spec_rows[(size_t)fr.hop * JT_SP_COUNT + k]);
         }
-        if (E.has_spec && fr.hop >= 0 && fr.hop < E.spec_hops)
-            for (int k = 0; k < JT_SP_COUNT; k++) m.spectral[k] = jt_wire("%g", (double)E.spec_rows[(size_t)fr.hop * JT_SP_COUNT + k]);
-        if (E.has_astats && (long)i == last_astats_frame) {
-            AstatsResult a; jt_astats(c, E.astats_sig, fr.astats_pos, a);
-            if (!E.astats_overall_only) for (int k = 0; k < JT_AS_COUNT; k++) m.astats[k] = std::isnan(a.v[k]) ? NAN : jt_wire("%f", a.v[k]);
-            m.astats_overall_RMS_level = jt_wire("%f", a.overall_rms);
-            m.astats_overall_Peak_level = jt_wire("%f", a.overall_peak);
-        }
+    };
+    const unsigned hw = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+    std::vector<std::thread> pool;
+    if (nf < 8192 || hw == 1) fill(0, nf);
+    else {
+        const size_t per = (nf + hw - 1) / hw;
+        for (unsigned t = 0; t < hw; t++) { const size_t a = t * per, b = std::min(nf, a + per); if (a < b) pool.emplace_back(fill, a, b); }
+    }
+    // the astats kernels (GPU) run while the host threads format the records
+    AstatsResult a; bool have_a = false; JtError aerr{0, ""};
+    if (E.has_astats && last_astats_frame >= 0) {
+        try { jt_astats(c, E.astats_sig, E.frames[last_astats_frame].astats_pos, a); have_a = true; }
+        catch (const JtError &e) { aerr = e; }
+    }
+    for (auto &t : pool) t.join();
+    if (aerr.code) throw aerr;
+    if (have_a) {
+        jt_frame_meta &m = res.meta[last_astats_frame];
+        if (!E.astats_overall_only) for (int k = 0; k < JT_AS_COUNT; k++) m.astats[k] = std::isnan(a.v[k]) ? NAN : jt_wire("%f", a.v[k]);
+        m.astats_overall_RMS_level = jt_wire("%f", a.overall_rms);
+        m.astats_overall_Peak_level = jt_wire("%f", a.overall_peak);
     }
 }

@@ -109,7 +109,9 @@ void jt_astats(jt_ctx *c, const Sig &in, int64_t n_upto, AstatsResult &out);
 
 // ---- k_spectral.cu ------------------------------------------------------------------------
 // rows: n_hops x JT_SP_COUNT floats on the host
-void jt_aspectralstats(jt_ctx *c, const Sig &in_flt, int win_size, std::vector<float> &rows, int64_t &n_hops);
+// wanted != nullptr: only those hops (and their predecessors, for flux) are computed; other rows stay 0
+void jt_aspectralstats(jt_ctx *c, const Sig &in_flt, int win_size, std::vector<float> &rows, int64_t &n_hops,
+                       const std::vector<int64_t> *wanted = nullptr);
 
 // ---- k_biquad.cu --------------------------------------------------------------------------
 struct BiquadCoef { double b0, b1, b2, a1, a2; };

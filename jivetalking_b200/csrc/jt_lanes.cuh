@@ -7,8 +7,10 @@
 // owns one row of a shared-memory tile and asks for the next R elements of its own range with a
 // single 1-D bulk copy (cp.async.bulk.shared::cluster.global -> SASS UBLKCP) that completes on
 // an mbarrier; tiles are double-buffered, so a row of R elements is in flight while the previous
-// one is being consumed.  Rows that are too short or not 16-byte aligned are filled with plain
-// loads by their own lane.
+// one is being consumed.  A lane's range is given in "virtual" coordinates: elements outside
+// [lo, hi) read as zero (stream start / zero tail), rows near those edges are filled with plain
+// loads by their own lane, and a source that is not 16-byte aligned is fetched from the aligned
+// address below it (the row has 16 bytes of slack) and exposed with the matching offset.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -42,22 +44,24 @@ __device__ __forceinline__ void jt_tma_load_1d(void *dst_smem, const void *src_g
 template <class T, int R>
 struct LaneStage {
     static_assert((R * sizeof(T)) % 16 == 0, "row must be a multiple of 16 bytes");
-    static constexpr int ROW = R + 16 / (int)sizeof(T);                 // padded row, still 16-byte aligned
+    static constexpr int PAD = 16 / (int)sizeof(T);
+    static constexpr int ROW = R + PAD;                                  // 16 bytes of slack per row
     static constexpr size_t WARP_BYTES = 2 * 32 * (size_t)ROW * sizeof(T) + 32;
 
     T *buf;                 // [2][32][ROW]
     uint64_t *bar;          // [2]
-    const T *src;           // this lane's range
-    int64_t count;          // elements in the range
-    int issued;             // tiles issued so far
-    int ntiles;             // warp-uniform: max over lanes of ceil(count / R)
+    const T *src;           // address of virtual element 0 (may lie outside the array)
+    int64_t count, lo, hi;  // virtual length; real data only for lo <= i < hi, zero elsewhere
+    int shift;              // elements between the 16-byte boundary below src and src
+    int issued, ntiles;     // ntiles is warp-uniform: max over lanes of ceil(count / R)
 
     // smem: WARP_BYTES for this warp, 16-byte aligned.  All 32 lanes must call.
-    __device__ __forceinline__ void init(unsigned char *smem, const T *lane_src, int64_t lane_count)
+    __device__ __forceinline__ void init(unsigned char *smem, const T *virt0, int64_t lane_count, int64_t real_lo, int64_t real_hi)
     {
         buf = (T *)smem;
         bar = (uint64_t *)(smem + 2 * 32 * (size_t)ROW * sizeof(T));
-        src = lane_src; count = lane_count < 0 ? 0 : lane_count; issued = 0;
+        src = virt0; count = lane_count < 0 ? 0 : lane_count; lo = real_lo; hi = real_hi; issued = 0;
+        shift = (int)((((uintptr_t)virt0) & 15) / sizeof(T));
         int64_t nt = (count + R - 1) / R;
         for (int o = 16; o; o >>= 1) { int64_t v = __shfl_xor_sync(0xffffffffu, nt, o); nt = v > nt ? v : nt; }
         ntiles = (int)nt;
@@ -65,6 +69,10 @@ struct LaneStage {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
+    }
+    __device__ __forceinline__ void init(unsigned char *smem, const T *lane_src, int64_t lane_count)
+    {
+        init(smem, lane_src, lane_count, 0, lane_count);
     }
     __device__ __forceinline__ int valid(int tile) const
     {
@@ -78,24 +86,24 @@ struct LaneStage {
         const int t = issued, b = t & 1, lane = threadIdx.x & 31;
         const int n = valid(t);
         T *row = buf + ((size_t)b * 32 + lane) * ROW;
-        const T *g = src + (int64_t)t * R;
-        const bool tma = n == R && (((uintptr_t)g) & 15) == 0;
-        unsigned bytes = tma ? (unsigned)(R * sizeof(T)) : 0u;
+        const int64_t v0 = (int64_t)t * R;                               // first virtual element of the tile
+        const bool tma = n == R && v0 - shift >= lo && v0 + R + PAD - shift <= hi;
+        const unsigned bytes = tma ? (unsigned)((R + (shift ? PAD : 0)) * sizeof(T)) : 0u;
         unsigned total = bytes;
         for (int o = 16; o; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
         if (lane == 0) jt_mbar_expect_tx(&bar[b], total);
         __syncwarp();
-        if (tma) jt_tma_load_1d(row, g, bytes, &bar[b]);
-        else for (int i = 0; i < n; i++) row[i] = g[i];
+        if (tma) jt_tma_load_1d(row, src + v0 - shift, bytes, &bar[b]);
+        else for (int i = 0; i < n; i++) { const int64_t v = v0 + i; row[shift + i] = (v >= lo && v < hi) ? src[v] : (T)0; }
         issued++;
     }
-    // wait for `tile`, return this lane's row
+    // wait for `tile`, return this lane's row (element k of the tile at [k])
     __device__ __forceinline__ const T *wait(int tile)
     {
         const int b = tile & 1;
         jt_mbar_wait(&bar[b], (unsigned)((tile >> 1) & 1));
         __syncwarp();
-        return buf + ((size_t)b * 32 + (threadIdx.x & 31)) * ROW;
+        return buf + ((size_t)b * 32 + (threadIdx.x & 31)) * ROW + shift;
     }
     __device__ __forceinline__ void release() { __syncwarp(); }
 };
@@ -135,6 +143,8 @@ struct LaneStore {
         }
         dst += filled; filled = 0;
     }
+    // the caller wrote n elements straight into row(): hand the row over
+    __device__ __forceinline__ void commit(int n) { filled = n; flush(); }
     __device__ __forceinline__ void put(T v)
     {
         row()[filled++] = v;

@@ -3,29 +3,30 @@
 // scripts/anlmdn-matrix-spike.sh:292-320).  K = p*fs patch radius, S = r*fs search radius,
 // hops of H = 2K+1 samples, 2S lags per output sample.  The dominant Pass-2 cost.
 //
-// One CTA per hop, one thread per lag.  The hop's window (H + 2(K+S) floats) is staged in
-// shared memory; every thread keeps its lag's running patch distance in a register and
-// updates it with the same unfused float operations, in the same order, as the scalar C
-// (full SSD at the hop's first sample, then add-new/subtract-old), so distances are
-// bit-identical to a sequential run.  Weighted sums are reduced per warp with shuffles
-// (skipped when no lane of the warp is inside the smoothing cut-off) and combined across
-// warps once per 32 samples.
+// One CTA per hop, one thread per PAIR of lags (j = i-S+v and j = i+1+v share the two patch-edge
+// samples of i).  The hop's window (H + 2(K+S) floats) is staged in shared memory; every thread
+// keeps its lags' running patch distances in registers and updates them with the same unfused
+// float operations, in the same order, as the scalar C (full SSD at the hop's first sample,
+// then add-new/subtract-old), so distances are bit-identical to a sequential run.  Weighted
+// sums are reduced per warp with shuffles (skipped when no lane of the warp is inside the
+// smoothing cut-off) and combined across warps once per 32 samples.
 #include "jt_internal.h"
 #include "jt_device.cuh"
 
 #define NLM_CHUNK 32
-#define NLM_MAXWARPS 32
+#define NLM_MAXWARPS 16
 
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(512)
 k_anlmdn(const float *__restrict__ x, float *__restrict__ y, int64_t n, int K, int S, float sw, float smooth,
-         float lut_scale, int64_t n_hops)
+         float lut_scale, float inv_lut_scale, int64_t n_hops)
 {
     extern __shared__ float win[];                       // N floats
     __shared__ float part[NLM_CHUNK][NLM_MAXWARPS][2];
     const int H = 2 * K + 1, N = H + 2 * (K + S), offset = N - H;
     const int v = threadIdx.x, lane = v & 31, warp = v >> 5, nwarp = blockDim.x >> 5;
-    const bool active = v < 2 * S;
+    const bool active = v < S;
     const float *f = win + K;
+    const int dj1 = -S + v, dj2 = 1 + v;                 // lag v and lag v+S of the scalar loop
     for (int64_t h = blockIdx.x; h < n_hops; h += gridDim.x) {
         const int64_t pos = h * (int64_t)H;
         const int nb = (int)min((int64_t)H, n - pos);
@@ -35,32 +36,43 @@ k_anlmdn(const float *__restrict__ x, float *__restrict__ y, int64_t n, int K, i
             win[j] = (s >= 0 && s < pos + nb) ? x[s] : 0.f;
         }
         __syncthreads();
-        // lag v: j = i - S + v + (v >= S)
-        const int dj = active ? (-S + v + (v >= S ? 1 : 0)) : 0;
-        float cache = 0.f;
+        float c1 = 0.f, c2 = 0.f;
         if (active) {
-            const int i = S, j = i + dj;
-            float d = 0.f;
-            for (int k = -K; k <= K; k++) { const float t = __fsub_rn(f[i + k], f[j + k]); d = __fadd_rn(d, __fmul_rn(t, t)); }
-            cache = d;
+            const float *fi = f + S, *f1 = fi + dj1, *f2 = fi + dj2;
+            float d1 = 0.f, d2 = 0.f;
+            for (int k = -K; k <= K; k++) {
+                const float a = fi[k];
+                const float t1 = __fsub_rn(a, f1[k]), t2 = __fsub_rn(a, f2[k]);
+                d1 = __fadd_rn(d1, __fmul_rn(t1, t1)); d2 = __fadd_rn(d2, __fmul_rn(t2, t2));
+            }
+            c1 = d1; c2 = d2;
         }
         for (int c0 = 0; c0 < H; c0 += NLM_CHUNK) {
             const int cn = min(NLM_CHUNK, H - c0);
-            for (int ci = 0; ci < cn; ci++) {
-                const int i = S + c0 + ci, j = i + dj;
+            const float *fi = f + S + c0;
+            for (int ci = 0; ci < cn; ci++, fi++) {
                 float pw = 0.f, qw = 0.f; bool in = false;
                 if (active) {
-                    if (i != S) {
-                        const float a = __fsub_rn(f[i - K - 1], f[j - K - 1]), b = __fsub_rn(f[i + K], f[j + K]);
-                        cache = __fadd_rn(cache, __fadd_rn(-__fmul_rn(a, a), __fmul_rn(b, b)));
+                    const float *f1 = fi + dj1, *f2 = fi + dj2;
+                    if (c0 + ci != 0) {
+                        const float ao = fi[-K - 1], an = fi[K];
+                        const float a1 = __fsub_rn(ao, f1[-K - 1]), b1 = __fsub_rn(an, f1[K]);
+                        const float a2 = __fsub_rn(ao, f2[-K - 1]), b2 = __fsub_rn(an, f2[K]);
+                        c1 = __fadd_rn(c1, __fadd_rn(-__fmul_rn(a1, a1), __fmul_rn(b1, b1)));
+                        c2 = __fadd_rn(c2, __fadd_rn(-__fmul_rn(a2, a2), __fmul_rn(b2, b2)));
                     }
-                    float distance = cache;
-                    if (distance < 0.f) cache = distance = 0.f;
-                    float w = __fmul_rn(distance, sw);
-                    if (!(w >= smooth)) {
-                        const unsigned idx = (unsigned)__fmul_rn(w, lut_scale);
-                        w = expf(__fdiv_rn(-(float)idx, lut_scale));
-                        pw = __fmul_rn(w, f[j]); qw = w; in = true;
+                    if (c1 < 0.f) c1 = 0.f;
+                    if (c2 < 0.f) c2 = 0.f;
+                    const float w1 = __fmul_rn(c1, sw), w2 = __fmul_rn(c2, sw);
+                    if (!(w1 >= smooth)) {
+                        const unsigned idx = (unsigned)__fmul_rn(w1, lut_scale);
+                        const float w = __expf(-(float)idx * inv_lut_scale);
+                        pw = __fmul_rn(w, f1[0]); qw = w; in = true;
+                    }
+                    if (!(w2 >= smooth)) {
+                        const unsigned idx = (unsigned)__fmul_rn(w2, lut_scale);
+                        const float w = __expf(-(float)idx * inv_lut_scale);
+                        pw += __fmul_rn(w, f2[0]); qw += w; in = true;
                     }
                 }
                 if (__any_sync(0xffffffffu, in)) {
@@ -90,8 +102,8 @@ Sig jt_anlmdn(jt_ctx *c, const Sig &in, double strength, double patch_s, double 
     const int S = (int)rescale_near(llround(research_s * 1e6), in.rate, 1000000);
     if (K < 1 || S < 1) JT_THROW(JT_ERR_INVALID_ARG, "anlmdn patch/research too small for %d Hz", in.rate);
     const int H = 2 * K + 1, N = H + 2 * (K + S);
-    const int threads = ((2 * S + 31) / 32) * 32;
-    if (threads > 1024) JT_THROW(JT_ERR_UNSUPPORTED, "anlmdn research radius %d samples (max 512)", S);
+    const int threads = std::max(32, ((S + 31) / 32) * 32);
+    if (threads > 512) JT_THROW(JT_ERR_UNSUPPORTED, "anlmdn research radius %d samples (max 512)", S);
     Sig o = in; o.d = jt_dalloc<float>(c, in.n);
     if (in.n <= 0) return o;
     const float m = (float)smooth_m, a = (float)strength;
@@ -103,6 +115,6 @@ Sig jt_anlmdn(jt_ctx *c, const Sig &in, double strength, double patch_s, double 
     JT_CUDA(cudaFuncSetAttribute(k_anlmdn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
     const int grid = jt_grid_for(n_hops, 1, c->num_sms, 64);
     JtLaunch L(c, "anlmdn");
-    k_anlmdn<<<grid, threads, smem, c->stream>>>((const float *)in.d, (float *)o.d, in.n, K, S, sw, smooth, lut_scale, n_hops);
+    k_anlmdn<<<grid, threads, smem, c->stream>>>((const float *)in.d, (float *)o.d, in.n, K, S, sw, smooth, lut_scale, 1.f / lut_scale, n_hops);
     return o;
 }

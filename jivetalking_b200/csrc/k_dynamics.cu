@@ -16,8 +16,9 @@
 #define FAKE_INFINITY (65536.0 * 65536.0)
 
 // ---- switching envelope follower ----------------------------------------------------------
-#define ENV_R 64
-__global__ void __launch_bounds__(64)
+#define ENV_R 128
+#define ENV_THREADS 32
+__global__ void __launch_bounds__(ENV_THREADS)
 k_envelope(const double *__restrict__ x, double *__restrict__ env, int64_t n, int seg, int warm,
            double attack_coeff, double release_coeff, int rms)
 {
@@ -30,6 +31,9 @@ k_envelope(const double *__restrict__ x, double *__restrict__ env, int64_t n, in
     LaneStage<double, ENV_R> in; LaneStore<double, ENV_R> out;
     in.init(wsm, x + begin, lane * seg < n ? s1 - begin : 0);
     out.init(wsm + LaneStage<double, ENV_R>::WARP_BYTES, env + s0);
+    // warm and seg are multiples of ENV_R, so a tile is either all warm-up or all output: the inner
+    // loops are branch-free and free of asm barriers, which lets ptxas hoist the shared-memory loads
+    // and overlap everything except the 3-op carried chain e -> (d-e) -> *coeff -> +e
     double e = 0.0;
     in.prefetch();
     for (int tile = 0; tile < in.ntiles; tile++) {
@@ -37,12 +41,27 @@ k_envelope(const double *__restrict__ x, double *__restrict__ env, int64_t n, in
         const double *row = in.wait(tile);
         const int nv = in.valid(tile);
         const int64_t i0 = begin + (int64_t)tile * ENV_R;
-#pragma unroll 4
-        for (int k = 0; k < nv; k++) {
-            double d = fabs(row[k]); if (rms) d *= d;
-            e += (d - e) * (d > e ? attack_coeff : release_coeff);
-            if (i0 + k >= s0) out.put(e);
+        const bool emit = i0 >= s0;
+        double *orow = out.row();
+        int k = 0;
+        // register blocks of 8: all loads and detector values first, then only the carried chain
+        for (; k + 8 <= nv; k += 8) {
+            double d[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) { const double v = row[k + j]; d[j] = rms ? v * v : fabs(v); }
+#pragma unroll
+            for (int j = 0; j < 8; j++) { e += (d[j] - e) * (d[j] > e ? attack_coeff : release_coeff); d[j] = e; }
+            if (emit) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) orow[k + j] = d[j];
+            }
         }
+        for (; k < nv; k++) {
+            const double v = row[k], dd = rms ? v * v : fabs(v);
+            e += (dd - e) * (dd > e ? attack_coeff : release_coeff);
+            if (emit) orow[k] = e;
+        }
+        if (emit) out.commit(nv);
         in.release();
     }
     out.finish();
@@ -55,12 +74,13 @@ static double *run_envelope(jt_ctx *c, const Sig &in, double attack_ms, double r
     const double cmin = std::fmin(ac, rc);
     int64_t warm = cmin >= 1.0 ? 1 : (int64_t)std::ceil(37.0 / -std::log1p(-cmin)) + 16;
     if (warm > (1 << 22)) warm = 1 << 22;
-    const int seg = 32768;
+    warm = (warm + ENV_R - 1) / ENV_R * ENV_R;                 // tile-aligned (see the kernel)
+    const int seg = 16384;
     const int64_t lanes = (in.n + seg - 1) / seg;
     JtLaunch L(c, "envelope_follower");
-    const size_t smem = 2 * (LaneStage<double, ENV_R>::WARP_BYTES + LaneStore<double, ENV_R>::WARP_BYTES);
+    const size_t smem = (ENV_THREADS / 32) * (LaneStage<double, ENV_R>::WARP_BYTES + LaneStore<double, ENV_R>::WARP_BYTES);
     JT_CUDA(cudaFuncSetAttribute(k_envelope, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_envelope<<<(int)((lanes + 63) / 64), 64, smem, c->stream>>>((const double *)in.d, env, in.n, seg, (int)warm, ac, rc, rms);
+    k_envelope<<<(int)((lanes + ENV_THREADS - 1) / ENV_THREADS), ENV_THREADS, smem, c->stream>>>((const double *)in.d, env, in.n, seg, (int)warm, ac, rc, rms);
     return env;
 }
 

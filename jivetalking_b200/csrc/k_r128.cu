@@ -12,6 +12,7 @@
 // values, Go accumulates them).
 #include "jt_internal.h"
 #include "jt_device.cuh"
+#include "jt_lanes.cuh"
 #include <algorithm>
 #include <cstdio>
 
@@ -56,11 +57,16 @@ __global__ void __launch_bounds__(64)
 k_r128_ticks(const TIN *__restrict__ x, int64_t n, int tick, int64_t n_ticks_total, int G, int WU,
              const __grid_constant__ KWeight kw, double *__restrict__ tick_pow, double *__restrict__ tick_peak)
 {
+    constexpr int R = 512 / (int)sizeof(TIN);                    // 512-byte rows
+    extern __shared__ __align__(16) unsigned char smem[];
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t k0 = t * G;
-    if (k0 >= n_ticks_total) return;
+    const bool live = t * G < n_ticks_total;
+    const int64_t k0 = min(t * G, n_ticks_total);
     const int64_t k1 = min(k0 + (int64_t)G, n_ticks_total);
-    int64_t i = max((int64_t)0, (k0 - WU) * (int64_t)tick);
+    const int64_t begin = max((int64_t)0, (k0 - WU) * (int64_t)tick);
+    const int64_t end = live ? min(k1 * (int64_t)tick, n) : begin;
+    LaneStage<TIN, R> in;
+    in.init(smem + (size_t)(threadIdx.x >> 5) * LaneStage<TIN, R>::WARP_BYTES, x + begin, end - begin);
     double x1 = 0, x2 = 0, y1 = 0, y2 = 0, z1 = 0, z2 = 0;      // STRUCT 0
     double v1 = 0, v2 = 0, v3 = 0, v4 = 0;                        // STRUCT 1
     auto step = [&](double x0) -> double {
@@ -78,20 +84,54 @@ k_r128_ticks(const TIN *__restrict__ x, int64_t n, int tick, int64_t n_ticks_tot
         }
     };
     const int64_t warm_end = k0 * (int64_t)tick;
-#pragma unroll 4
-    for (; i < warm_end; i++) (void)step(jt_as_f64(__ldg(x + i)));
-    for (int64_t k = k0; k < k1; k++) {
-        const int64_t e = min((k + 1) * (int64_t)tick, n);
-        double acc = 0.0, pk = 0.0;
-#pragma unroll 4
-        for (; i < e; i++) {
-            const double x0 = jt_as_f64(__ldg(x + i));
-            const double z = step(x0);
-            acc = fma(z, z, acc);
-            pk = fmax(pk, fabs(x0));
+    int64_t k = k0, tick_end = min((k0 + 1) * (int64_t)tick, n);
+    double acc = 0.0, pk = 0.0;
+    in.prefetch();
+    for (int tile = 0; tile < in.ntiles; tile++) {
+        in.prefetch();
+        const TIN *row = in.wait(tile);
+        const int nv = in.valid(tile);
+        int64_t i = begin + (int64_t)tile * R;
+        int q = 0;
+        // branch-free runs: [warm-up run] then runs that end at a tick boundary
+        while (q < nv) {
+            if (i < warm_end) {
+                const int run = (int)min((int64_t)(nv - q), warm_end - i);
+                int r = 0;
+                for (; r + 8 <= run; r += 8) {          // loads first, then the recurrence
+                    double v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) v[j] = jt_as_f64(row[q + r + j]);
+#pragma unroll
+                    for (int j = 0; j < 8; j++) (void)step(v[j]);
+                }
+                for (; r < run; r++) (void)step(jt_as_f64(row[q + r]));
+                q += run; i += run;
+            } else {
+                const int run = (int)min((int64_t)(nv - q), tick_end - i);
+                int r = 0;
+                for (; r + 8 <= run; r += 8) {
+                    double v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) v[j] = jt_as_f64(row[q + r + j]);
+#pragma unroll
+                    for (int j = 0; j < 8; j++) { const double z = step(v[j]); acc = fma(z, z, acc); pk = fmax(pk, fabs(v[j])); }
+                }
+                for (; r < run; r++) {
+                    const double x0 = jt_as_f64(row[q + r]);
+                    const double z = step(x0);
+                    acc = fma(z, z, acc);
+                    pk = fmax(pk, fabs(x0));
+                }
+                q += run; i += run;
+                if (i == tick_end) {
+                    tick_pow[k] = acc; tick_peak[k] = pk;
+                    acc = 0.0; pk = 0.0; k++;
+                    tick_end = min((k + 1) * (int64_t)tick, n);
+                }
+            }
         }
-        tick_pow[k] = acc;
-        tick_peak[k] = pk;
+        in.release();
     }
 }
 
@@ -104,9 +144,14 @@ static void run_ticks(jt_ctx *c, const Sig &in, int tick, int64_t n_ticks_total,
     const int64_t lanes = (n_ticks_total + G - 1) / G;
     const int grid = (int)((lanes + 63) / 64);
     JtLaunch L(c, "r128_kweight_ticks");
-    if (in.fmt == JT_FMT_S16) k_r128_ticks<int16_t, STRUCT><<<grid, 64, 0, c->stream>>>((const int16_t *)in.d, in.n, tick, n_ticks_total, G, WU, kw, d_pow, d_peak);
-    else if (in.fmt == JT_FMT_FLT) k_r128_ticks<float, STRUCT><<<grid, 64, 0, c->stream>>>((const float *)in.d, in.n, tick, n_ticks_total, G, WU, kw, d_pow, d_peak);
-    else k_r128_ticks<double, STRUCT><<<grid, 64, 0, c->stream>>>((const double *)in.d, in.n, tick, n_ticks_total, G, WU, kw, d_pow, d_peak);
+#define R128_LAUNCH(T) do { \
+        const size_t smem = 2 * LaneStage<T, 512 / (int)sizeof(T)>::WARP_BYTES; \
+        JT_CUDA(cudaFuncSetAttribute(k_r128_ticks<T, STRUCT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_r128_ticks<T, STRUCT><<<grid, 64, smem, c->stream>>>((const T *)in.d, in.n, tick, n_ticks_total, G, WU, kw, d_pow, d_peak); } while (0)
+    if (in.fmt == JT_FMT_S16) R128_LAUNCH(int16_t);
+    else if (in.fmt == JT_FMT_FLT) R128_LAUNCH(float);
+    else R128_LAUNCH(double);
+#undef R128_LAUNCH
 }
 
 // ---------------------------------------------------------------------------------------

@@ -8,6 +8,8 @@
 #include "jt_internal.h"
 #include "jt_device.cuh"
 #include <cfloat>
+#include <algorithm>
+#include <cstring>
 
 #define SP_THREADS 256
 
@@ -31,7 +33,7 @@ template <int K> __device__ __forceinline__ void block_sum(float (&v)[K], float 
 }
 
 __global__ void __launch_bounds__(SP_THREADS)
-k_spectral(const float *__restrict__ x, int64_t n, int win, int rate, int64_t n_hops,
+k_spectral(const float *__restrict__ x, int64_t n, int win, int rate, int64_t n_items, const int64_t *__restrict__ list,
            const float2 *__restrict__ tw, const float *__restrict__ lut,
            float *__restrict__ mags, float *__restrict__ rows)
 {
@@ -41,7 +43,8 @@ k_spectral(const float *__restrict__ x, int64_t n, int win, int rate, int64_t n_
     __shared__ int s_idx;
     const int hop = win / 2, size = win / 2;
     int logn = 0; while ((1 << logn) < win) logn++;
-    for (int64_t h = blockIdx.x; h < n_hops; h += gridDim.x) {
+    for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x) {
+        const int64_t h = list ? list[it] : it;     // hop index of this item
         const int64_t w0 = (h - 1) * (int64_t)hop;  // window start sample
         __syncthreads();
         for (int i = threadIdx.x; i < win; i += SP_THREADS) {
@@ -74,7 +77,7 @@ k_spectral(const float *__restrict__ x, int64_t n, int win, int rate, int64_t n_
         for (int j = 0; j < per; j++) {
             m[j] = hypotf(__fmul_rn(c4[j].x, wscale), __fmul_rn(c4[j].y, wscale));
             smag[threadIdx.x * per + j] = m[j];
-            mags[h * (int64_t)size + threadIdx.x * per + j] = m[j];
+            mags[it * (int64_t)size + threadIdx.x * per + j] = m[j];
         }
         __syncthreads();
         const float mag0 = smag[0];
@@ -131,7 +134,7 @@ k_spectral(const float *__restrict__ x, int64_t n, int win, int rate, int64_t n_
         if (first != 0x7fffffff) atomicMin(&s_idx, first);
         __syncthreads();
         if (threadIdx.x == 0) {
-            float *r = rows + h * JT_SP_COUNT;
+            float *r = rows + it * JT_SP_COUNT;
             const float spread = sum <= FLT_EPSILON ? 1.f : sqrtf(r2[1] / sum);
             r[JT_SP_mean] = mean;
             r[JT_SP_variance] = r2[0] / size;
@@ -154,13 +157,14 @@ k_spectral(const float *__restrict__ x, int64_t n, int win, int rate, int64_t n_
 }
 
 __global__ void __launch_bounds__(256)
-k_spectral_flux(const float *__restrict__ mags, int size, int64_t n_hops, float *__restrict__ rows)
+k_spectral_flux(const float *__restrict__ mags, int size, int64_t n_items, const int64_t *__restrict__ prev, float *__restrict__ rows)
 {
     __shared__ float sw[8];
-    for (int64_t h = blockIdx.x; h < n_hops; h += gridDim.x) {
+    for (int64_t h = blockIdx.x; h < n_items; h += gridDim.x) {
+        const int64_t pb = prev ? prev[h] : h - 1;      // item holding the previous hop's magnitudes (-1: none, zeros)
         float s = 0;
         for (int i = threadIdx.x; i < size; i += 256) {
-            const float a = mags[h * size + i], b = h > 0 ? mags[(h - 1) * size + i] : 0.f;
+            const float a = mags[h * size + i], b = pb >= 0 ? mags[pb * size + i] : 0.f;
             const float d = a - b; s += d * d;
         }
         s = jt_warp_sum(s);
@@ -171,7 +175,7 @@ k_spectral_flux(const float *__restrict__ mags, int size, int64_t n_hops, float 
     }
 }
 
-void jt_aspectralstats(jt_ctx *c, const Sig &in0, int win, std::vector<float> &rows, int64_t &n_hops)
+void jt_aspectralstats(jt_ctx *c, const Sig &in0, int win, std::vector<float> &rows, int64_t &n_hops, const std::vector<int64_t> *wanted)
 {
     Sig in = jt_convert(c, in0, JT_FMT_FLT);
     const int hop = win / 2;
@@ -180,20 +184,47 @@ void jt_aspectralstats(jt_ctx *c, const Sig &in0, int win, std::vector<float> &r
     if (n_hops <= 0) return;
     if (win < 1024 || (win & (win - 1)) || (win / 2) % SP_THREADS || win / 2 / SP_THREADS > 4)
         JT_THROW(JT_ERR_UNSUPPORTED, "aspectralstats win_size %d", win);
+    // Only hops a sink frame will ever show are computed (the reference sees one hop per 100 ms frame,
+    // SURVEY 7.3), each with its predecessor for the flux term.
+    std::vector<int64_t> items, prev;
+    if (wanted) {
+        std::vector<int64_t> w;
+        for (int64_t h : *wanted) if (h >= 0 && h < n_hops) { w.push_back(h); if (h > 0) w.push_back(h - 1); }
+        std::sort(w.begin(), w.end());
+        w.erase(std::unique(w.begin(), w.end()), w.end());
+        items.swap(w);
+        prev.resize(items.size());
+        for (size_t i = 0; i < items.size(); i++) prev[i] = (i > 0 && items[i - 1] == items[i] - 1) ? (int64_t)i - 1 : -1;
+        if (items.empty()) return;
+    }
+    const int64_t n_items = wanted ? (int64_t)items.size() : n_hops;
     std::vector<float2> tw(win / 2); std::vector<float> lut(win);
     for (int k = 0; k < win / 2; k++) { double a = -2.0 * M_PI * k / win; tw[k] = make_float2((float)cos(a), (float)sin(a)); }
     for (int i = 0; i < win; i++) lut[i] = (float)(.5 * (1 - cos(2 * M_PI * i / (win - 1))));
     float2 *d_tw = jt_dalloc<float2>(c, win / 2); float *d_lut = jt_dalloc<float>(c, win);
     JT_CUDA(cudaMemcpyAsync(d_tw, tw.data(), sizeof(float2) * win / 2, cudaMemcpyHostToDevice, c->stream));
     JT_CUDA(cudaMemcpyAsync(d_lut, lut.data(), sizeof(float) * win, cudaMemcpyHostToDevice, c->stream));
-    float *d_mags = jt_dalloc<float>(c, (size_t)n_hops * (win / 2));
-    float *d_rows = jt_dalloc<float>(c, (size_t)n_hops * JT_SP_COUNT);
-    const int grid = jt_grid_for(n_hops, 1, c->num_sms, 16);
+    int64_t *d_items = nullptr, *d_prev = nullptr;
+    if (wanted) {
+        d_items = jt_dalloc<int64_t>(c, n_items); d_prev = jt_dalloc<int64_t>(c, n_items);
+        JT_CUDA(cudaMemcpyAsync(d_items, items.data(), sizeof(int64_t) * n_items, cudaMemcpyHostToDevice, c->stream));
+        JT_CUDA(cudaMemcpyAsync(d_prev, prev.data(), sizeof(int64_t) * n_items, cudaMemcpyHostToDevice, c->stream));
+    }
+    float *d_mags = jt_dalloc<float>(c, (size_t)n_items * (win / 2));
+    float *d_rows = jt_dalloc<float>(c, (size_t)n_items * JT_SP_COUNT);
+    const int grid = jt_grid_for(n_items, 1, c->num_sms, 16);
     {
         JtLaunch L(c, "aspectralstats", 2);
-        k_spectral<<<grid, SP_THREADS, sizeof(float2) * win, c->stream>>>((const float *)in.d, in.n, win, in.rate, n_hops, d_tw, d_lut, d_mags, d_rows);
-        k_spectral_flux<<<grid, 256, 0, c->stream>>>(d_mags, win / 2, n_hops, d_rows);
+        k_spectral<<<grid, SP_THREADS, sizeof(float2) * win, c->stream>>>((const float *)in.d, in.n, win, in.rate, n_items, d_items, d_tw, d_lut, d_mags, d_rows);
+        k_spectral_flux<<<grid, 256, 0, c->stream>>>(d_mags, win / 2, n_items, d_prev, d_rows);
     }
-    JT_CUDA(cudaMemcpyAsync(rows.data(), d_rows, sizeof(float) * rows.size(), cudaMemcpyDeviceToHost, c->stream));
-    JT_CUDA(cudaStreamSynchronize(c->stream));
+    if (!wanted) {
+        JT_CUDA(cudaMemcpyAsync(rows.data(), d_rows, sizeof(float) * rows.size(), cudaMemcpyDeviceToHost, c->stream));
+        JT_CUDA(cudaStreamSynchronize(c->stream));
+    } else {
+        std::vector<float> packed((size_t)n_items * JT_SP_COUNT);
+        JT_CUDA(cudaMemcpyAsync(packed.data(), d_rows, sizeof(float) * packed.size(), cudaMemcpyDeviceToHost, c->stream));
+        JT_CUDA(cudaStreamSynchronize(c->stream));
+        for (int64_t i = 0; i < n_items; i++) memcpy(&rows[(size_t)items[i] * JT_SP_COUNT], &packed[(size_t)i * JT_SP_COUNT], sizeof(float) * JT_SP_COUNT);
+    }
 }
