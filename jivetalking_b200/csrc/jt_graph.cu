@@ -196,7 +196,7 @@ static int swr_internal_fmt(int in_fmt, int out_fmt)
     return JT_FMT_DBL;
 }
 
-static void do_resample(Exec &E, int out_rate, int out_fmt /* 0 = keep link format */)
+static void do_resample(Exec &E, int out_rate, int out_fmt /* 0 = keep link format */, bool keep_work_fmt = false)
 {
     jt_ctx *c = E.c;
     const int in_link = E.link_fmt;
@@ -212,7 +212,7 @@ static void do_resample(Exec &E, int out_rate, int out_fmt /* 0 = keep link form
     // swr converts to its internal format first, then resamples
     Sig src = E.cur;
     if (work == JT_FMT_FLT && src.fmt == JT_FMT_DBL) src = jt_convert(c, src, JT_FMT_FLT);
-    Sig r = jt_swr_resample(c, src, p, work, true);
+    Sig r = jt_swr_resample(c, src, p, work, true, out_fmt);
     // frames: one output frame per input frame (aresample filter_frame), then the EOF flush frame
     std::vector<FrameRef> nf; int64_t done = 0;
     for (const FrameRef &f : E.frames) {
@@ -222,8 +222,9 @@ static void do_resample(Exec &E, int out_rate, int out_fmt /* 0 = keep link form
     if (r.n > done) { FrameRef o; o.start = done; o.nb = (int32_t)(r.n - done); o.ready = INT64_MAX; nf.push_back(o); }
     (void)n_in;
     E.frames.swap(nf);
-    E.cur = r; E.link_fmt = work;
-    if (out_fmt != work) E.storage(out_fmt);
+    E.cur = r; E.link_fmt = r.fmt;            // r.fmt == out_fmt when the kernel converted on store
+    // keep_work_fmt: the consumer widens on load (f32 -> f64 is exact), so the converted copy is never materialised
+    if (out_fmt != r.fmt && !keep_work_fmt) E.storage(out_fmt);
 }
 
 static std::vector<double> parse_bn(const std::string &s)
@@ -420,7 +421,7 @@ void jt_graph_run(jt_ctx *c, const std::string &spec, const void *d_in, int64_t 
             } else {
                 // dynamic mode: af_loudnorm.c query_formats forces the input link to 192 kHz / dbl
                 if (want_pcm || !last) JT_THROW(JT_ERR_UNSUPPORTED, "loudnorm dynamic mode with audio output (linear-mode preconditions not met: measured_I=%g measured_TP=%g measured_LRA=%g measured_thresh=%g)", mI, mTP, mLRA, mTh);
-                do_resample(E, 192000, JT_FMT_DBL);
+                do_resample(E, 192000, JT_FMT_DBL, true);
                 jt_loudnorm_meter(c, E.cur, dual, mi);
                 res.ln.normalization_type = 1;
                 res.ln.output_i = res.ln.output_tp = res.ln.output_lra = res.ln.output_thresh = res.ln.target_offset = NAN;

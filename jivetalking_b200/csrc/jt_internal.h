@@ -89,7 +89,8 @@ struct SwrPlan {
 };
 SwrPlan jt_swr_plan(int in_rate, int out_rate);
 // resample whole stream; work_fmt = JT_FMT_FLT or JT_FMT_DBL (swr's internal format); returns work_fmt signal
-Sig  jt_swr_resample(jt_ctx *c, const Sig &in, const SwrPlan &p, int work_fmt, bool flush);
+// fuse_out_fmt = JT_FMT_S16 lets the f32 path store s16 directly (the result's fmt says what was produced)
+Sig  jt_swr_resample(jt_ctx *c, const Sig &in, const SwrPlan &p, int work_fmt, bool flush, int fuse_out_fmt = 0);
 // per-tick max |oversampled| (ebur128 true peak): d_tick_tp[k] = max over outputs first available at tick k
 void jt_swr_tick_absmax(jt_ctx *c, const Sig &in, const SwrPlan &p, int tick, int64_t n_ticks, double *d_tick_tp);
 

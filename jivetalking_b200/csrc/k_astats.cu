@@ -10,6 +10,7 @@
 //      block prefix/suffix maxima
 #include "jt_internal.h"
 #include "jt_device.cuh"
+#include "jt_lanes.cuh"
 #include <cfloat>
 #include <cstdio>
 
@@ -133,75 +134,197 @@ k_astats_b(const T *__restrict__ x, int64_t n, double gmin, double gmax, unsigne
     }
 }
 
-// C1: per block of BS samples, zero-state end value of avg = avg*mult + (1-mult)*nd^2
+// C1: per block of BS samples, zero-state end value of avg = avg*mult + (1-mult)*nd^2.
+// One lane per block; each lane's samples arrive as TMA-staged 256-byte rows (jt_lanes.cuh).
+#define AS_BS 1024
+template <class T> struct AsRow { static constexpr int R = 256 / (int)sizeof(T); };
 template <class T>
-__global__ void k_astats_c1(const T *__restrict__ x, int64_t n, int BS, double mult, double *__restrict__ fin)
+__global__ void __launch_bounds__(64)
+k_astats_c1(const T *__restrict__ x, int64_t n, double mult, double *__restrict__ fin)
 {
+    constexpr int R = AsRow<T>::R;
+    extern __shared__ __align__(16) unsigned char smem[];
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t s = b * BS; if (s >= n) return;
-    const int64_t e = min(s + BS, n);
+    const int64_t s = min(b * AS_BS, n), e = min(s + AS_BS, n);
+    LaneStage<T, R> in;
+    in.init(smem + (size_t)(threadIdx.x >> 5) * LaneStage<T, R>::WARP_BYTES, x + s, e - s);
     double avg = 0; const double om = 1.0 - mult;
-    for (int64_t i = s; i < e; i++) { const double nd = AsTraits<T>::nd(x[i]); avg = avg * mult + om * nd * nd; }
-    fin[b] = avg;
+    in.prefetch();
+    for (int tile = 0; tile < in.ntiles; tile++) {
+        in.prefetch();
+        const T *row = in.wait(tile);
+        const int nv = in.valid(tile);
+        int k = 0;
+        for (; k + 8 <= nv; k += 8) {
+            double q[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) { const double nd = AsTraits<T>::nd(row[k + j]); q[j] = om * nd * nd; }
+#pragma unroll
+            for (int j = 0; j < 8; j++) avg = avg * mult + q[j];
+        }
+        for (; k < nv; k++) { const double nd = AsTraits<T>::nd(row[k]); avg = avg * mult + om * nd * nd; }
+        in.release();
+    }
+    if (e > s) fin[b] = avg;
 }
-// carry[b] = state entering block b
-__global__ void k_astats_carry(const double *__restrict__ fin, double *__restrict__ carry, int64_t nb, double mult_bs)
+// carry[b] = state entering block b.  cy' = cy * M + fin[b] is affine in cy: each thread composes its
+// slice of blocks, thread 0 chains the 1024 slices, every thread replays its slice from its true entry value.
+__global__ void __launch_bounds__(1024)
+k_astats_carry(const double *__restrict__ fin, double *__restrict__ carry, int64_t nb, double mult_bs)
 {
-    if (blockIdx.x || threadIdx.x) return;
-    double cy = 0;
-    for (int64_t b = 0; b < nb; b++) { carry[b] = cy; cy = cy * mult_bs + fin[b]; }
+    __shared__ double sA[1024], sB[1024], sIn[1024];
+    const int t = threadIdx.x;
+    const int64_t per = (nb + 1023) / 1024, h0 = min((int64_t)t * per, nb), h1 = min(h0 + per, nb);
+    double A = 1.0, B = 0.0;
+    for (int64_t h = h0; h < h1; h++) { A *= mult_bs; B = B * mult_bs + fin[h]; }
+    sA[t] = A; sB[t] = B;
+    __syncthreads();
+    if (t == 0) { double cy = 0; for (int i = 0; i < 1024; i++) { sIn[i] = cy; cy = sA[i] * cy + sB[i]; } }
+    __syncthreads();
+    double cy = sIn[t];
+    for (int64_t h = h0; h < h1; h++) { carry[h] = cy; cy = cy * mult_bs + fin[h]; }
 }
 template <class T>
-__global__ void k_astats_c2(const T *__restrict__ x, int64_t n, int BS, double mult, const double *__restrict__ carry,
-                            int64_t tc, double *__restrict__ mm /* [0]=min (init DBL_MAX), [1]=max */)
+__global__ void __launch_bounds__(64)
+k_astats_c2(const T *__restrict__ x, int64_t n, double mult, const double *__restrict__ carry,
+            int64_t tc, double *__restrict__ mm /* [0]=min (init DBL_MAX), [1]=max */)
 {
+    constexpr int R = AsRow<T>::R;
+    extern __shared__ __align__(16) unsigned char smem[];
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t s = b * BS;
+    const int64_t s = min(b * AS_BS, n), e = min(s + AS_BS, n);
+    LaneStage<T, R> in;
+    in.init(smem + (size_t)(threadIdx.x >> 5) * LaneStage<T, R>::WARP_BYTES, x + s, e - s);
     double lo = DBL_MAX, hi = 0;
-    if (s < n) {
-        const int64_t e = min(s + BS, n);
-        double avg = carry[b]; const double om = 1.0 - mult;
-        for (int64_t i = s; i < e; i++) {
-            const double nd = AsTraits<T>::nd(x[i]); avg = avg * mult + om * nd * nd;
-            if (i >= tc) { lo = fmin(lo, avg); hi = fmax(hi, avg); }
+    double avg = e > s ? carry[b] : 0.0; const double om = 1.0 - mult;
+    in.prefetch();
+    for (int tile = 0; tile < in.ntiles; tile++) {
+        in.prefetch();
+        const T *row = in.wait(tile);
+        const int nv = in.valid(tile);
+        const int64_t i0 = s + (int64_t)tile * R;
+        if (i0 >= tc) {
+            // avg >= 0: non-negative doubles order like their bit patterns, so min / max run on the integer
+            // pipe (f64 min/max issue at a third of the f64 add rate on sm_100a, profiles/ubench_r1.txt)
+            unsigned long long ulo = (unsigned long long)__double_as_longlong(lo), uhi = (unsigned long long)__double_as_longlong(hi);
+            int k = 0;
+            for (; k + 8 <= nv; k += 8) {
+                double q[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) { const double nd = AsTraits<T>::nd(row[k + j]); q[j] = om * nd * nd; }
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    avg = avg * mult + q[j];
+                    const unsigned long long u = (unsigned long long)__double_as_longlong(avg);
+                    ulo = min(ulo, u); uhi = max(uhi, u);
+                }
+            }
+            for (; k < nv; k++) {
+                const double nd = AsTraits<T>::nd(row[k]); avg = avg * mult + om * nd * nd;
+                const unsigned long long u = (unsigned long long)__double_as_longlong(avg);
+                ulo = min(ulo, u); uhi = max(uhi, u);
+            }
+            lo = __longlong_as_double((long long)ulo); hi = __longlong_as_double((long long)uhi);
+        } else {
+            for (int k = 0; k < nv; k++) {
+                const double nd = AsTraits<T>::nd(row[k]); avg = avg * mult + om * nd * nd;
+                if (i0 + k >= tc) { lo = fmin(lo, avg); hi = fmax(hi, avg); }
+            }
         }
+        in.release();
     }
     lo = jt_warp_min(lo); hi = jt_warp_max(hi);
     if ((threadIdx.x & 31) == 0) { jt_atomic_min_nonneg(&mm[0], lo); jt_atomic_max_nonneg(&mm[1], hi); }
 }
 
-// D1: per tc-sized block prefix / suffix maxima of |nd|
+// D: Noise_floor = min over window ends i >= tc-1 of max |nd| over [i-tc+1, i], and how often that minimum
+// occurs.  van Herk / Gil-Werman with tc-sized blocks, one CTA per block b: the window ending at offset j of
+// block b is (suffix of block b-1 from offset j+1) U (prefix of block b up to j); both running maxima are
+// block-parallel scans in shared memory, nothing but the per-block (min, count) pair is written.
+#define AS_NF_THREADS 256
+__device__ __forceinline__ float as_block_excl_scan_max(float v, float *s_w)
+{   // exclusive forward scan of max over the CTA's threads (values >= 0)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float inc = v;
+    for (int o = 1; o < 32; o <<= 1) { const float t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc = fmaxf(inc, t); }
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    float base = 0.f;
+    for (int w = 0; w < warp; w++) base = fmaxf(base, s_w[w]);
+    float exc = __shfl_up_sync(0xffffffffu, inc, 1); if (lane == 0) exc = 0.f;
+    __syncthreads();
+    return fmaxf(base, exc);
+}
 template <class T>
-__global__ void k_astats_d1(const T *__restrict__ x, int64_t n, int tc, float *__restrict__ P, float *__restrict__ S)
+__global__ void __launch_bounds__(AS_NF_THREADS)
+k_astats_nf(const T *__restrict__ x, int64_t n, int tc, float *__restrict__ bmin, unsigned *__restrict__ bcnt)
 {
-    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t s = b * tc; if (s >= n) return;
-    const int64_t e = min(s + tc, n);
-    float m = 0;
-    for (int64_t i = s; i < e; i++) { m = fmaxf(m, (float)fabs(AsTraits<T>::nd(x[i]))); P[i] = m; }
-    m = 0;
-    for (int64_t i = e - 1; i >= s; i--) { m = fmaxf(m, (float)fabs(AsTraits<T>::nd(x[i]))); S[i] = m; }
+    extern __shared__ float sm_nf[];                 // suf[tc + 1], pre[tc]
+    __shared__ float s_w[AS_NF_THREADS / 32];
+    __shared__ float s_red[AS_NF_THREADS / 32]; __shared__ unsigned s_cnt[AS_NF_THREADS / 32];
+    float *suf = sm_nf, *pre = sm_nf + tc + 1;
+    const int t = threadIdx.x, per = (tc + AS_NF_THREADS - 1) / AS_NF_THREADS;
+    for (int64_t b = blockIdx.x; b * tc < n; b += gridDim.x) {
+        const int64_t s = b * tc;
+        const int len = (int)min((int64_t)tc, n - s);
+        __syncthreads();
+        for (int j = t; j < tc; j += AS_NF_THREADS) {
+            suf[j] = b > 0 ? (float)fabs(AsTraits<T>::nd(x[s - tc + j])) : 0.f;
+            pre[j] = j < len ? (float)fabs(AsTraits<T>::nd(x[s + j])) : 0.f;
+        }
+        if (t == 0) suf[tc] = 0.f;
+        __syncthreads();
+        // prefix maxima of the current block: thread t owns [t*per, (t+1)*per)
+        {
+            const int j0 = min(t * per, tc), j1 = min(j0 + per, tc);
+            float m = 0.f;
+            for (int j = j0; j < j1; j++) { m = fmaxf(m, pre[j]); pre[j] = m; }
+            const float base = as_block_excl_scan_max(m, s_w);
+            for (int j = j0; j < j1; j++) pre[j] = fmaxf(pre[j], base);
+        }
+        // suffix maxima of the previous block: thread t owns the mirrored range, scanned right to left
+        {
+            const int r0 = min(t * per, tc), r1 = min(r0 + per, tc);        // mirrored offsets
+            float m = 0.f;
+            for (int r = r0; r < r1; r++) { const int j = tc - 1 - r; m = fmaxf(m, suf[j]); suf[j] = m; }
+            const float base = as_block_excl_scan_max(m, s_w);
+            for (int r = r0; r < r1; r++) { const int j = tc - 1 - r; suf[j] = fmaxf(suf[j], base); }
+        }
+        __syncthreads();
+        // windows ending in this block: offsets j with s + j >= tc - 1
+        const int jlo = b == 0 ? tc - 1 : 0;
+        float lo = FLT_MAX;
+        for (int j = jlo + t; j < len; j += AS_NF_THREADS) lo = fminf(lo, fmaxf(suf[j + 1], pre[j]));
+        for (int o = 16; o; o >>= 1) lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        if ((t & 31) == 0) s_red[t >> 5] = lo;
+        __syncthreads();
+        float g = FLT_MAX;
+        for (int w = 0; w < AS_NF_THREADS / 32; w++) g = fminf(g, s_red[w]);
+        unsigned c = 0;
+        for (int j = jlo + t; j < len; j += AS_NF_THREADS) c += (fmaxf(suf[j + 1], pre[j]) == g);
+        for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if ((t & 31) == 0) s_cnt[t >> 5] = c;
+        __syncthreads();
+        if (t == 0) { unsigned tot = 0; for (int w = 0; w < AS_NF_THREADS / 32; w++) tot += s_cnt[w]; bmin[b] = g; bcnt[b] = tot; }
+    }
 }
-__global__ void __launch_bounds__(256)
-k_astats_d2(const float *__restrict__ P, const float *__restrict__ S, int64_t n, int tc, float *__restrict__ gmin)
+__global__ void __launch_bounds__(1024)
+k_astats_nf_reduce(const float *__restrict__ bmin, const unsigned *__restrict__ bcnt, int64_t nblk, float *__restrict__ gmin,
+                   unsigned long long *__restrict__ cnt)
 {
+    __shared__ float s_m[32]; __shared__ unsigned long long s_c[32];
     float lo = FLT_MAX;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = tc - 1 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        lo = fminf(lo, fmaxf(S[i - tc + 1], P[i]));
+    for (int64_t i = threadIdx.x; i < nblk; i += 1024) lo = fminf(lo, bmin[i]);
     for (int o = 16; o; o >>= 1) lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-    if ((threadIdx.x & 31) == 0) atomicMin((unsigned int *)gmin, __float_as_uint(lo));
-}
-__global__ void __launch_bounds__(256)
-k_astats_d3(const float *__restrict__ P, const float *__restrict__ S, int64_t n, int tc, const float *__restrict__ gmin,
-            unsigned long long *__restrict__ cnt)
-{
-    const float g = *gmin; unsigned long long c = 0;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = tc - 1 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        c += (fmaxf(S[i - tc + 1], P[i]) == g);
+    if ((threadIdx.x & 31) == 0) s_m[threadIdx.x >> 5] = lo;
+    __syncthreads();
+    float g = FLT_MAX; for (int w = 0; w < 32; w++) g = fminf(g, s_m[w]);
+    unsigned long long c = 0;
+    for (int64_t i = threadIdx.x; i < nblk; i += 1024) if (bmin[i] == g) c += bcnt[i];
     for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    if ((threadIdx.x & 31) == 0 && c) atomicAdd(cnt, c);
+    if ((threadIdx.x & 31) == 0) s_c[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) { unsigned long long tot = 0; for (int w = 0; w < 32; w++) tot += s_c[w]; *gmin = g; *cnt = tot; }
 }
 
 template <class T>
@@ -234,28 +357,32 @@ static void astats_t(jt_ctx *c, const Sig &in, int64_t n, AstatsResult &out)
     { JtLaunch L(c, "astats"); k_astats_b<T><<<gridA, 256, 0, c->stream>>>(x, n, r.mn, r.mx, d_counts); }
     // C: exponential mean square min/max
     double *d_mm = jt_dalloc<double>(c, 2);
-    const int BS = 4096; const int64_t nb = (n + BS - 1) / BS;
+    const int BS = AS_BS; const int64_t nb = (n + BS - 1) / BS;
     double h_mm[2] = {DBL_MAX, 0.0};
     JT_CUDA(cudaMemcpyAsync(d_mm, h_mm, sizeof(h_mm), cudaMemcpyHostToDevice, c->stream));
     if (n > tc) {
         double *d_fin = jt_dalloc<double>(c, nb), *d_carry = jt_dalloc<double>(c, nb);
         JtLaunch L(c, "astats", 3);
-        k_astats_c1<T><<<(int)((nb + 63) / 64), 64, 0, c->stream>>>(x, n, BS, mult, d_fin);
-        k_astats_carry<<<1, 1, 0, c->stream>>>(d_fin, d_carry, nb, pow(mult, (double)BS));
-        k_astats_c2<T><<<(int)((nb + 63) / 64), 64, 0, c->stream>>>(x, n, BS, mult, d_carry, tc, d_mm);
+        const size_t smemC = 2 * LaneStage<T, AsRow<T>::R>::WARP_BYTES;
+        JT_CUDA(cudaFuncSetAttribute(k_astats_c1<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC));
+        JT_CUDA(cudaFuncSetAttribute(k_astats_c2<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC));
+        k_astats_c1<T><<<(int)((nb + 63) / 64), 64, smemC, c->stream>>>(x, n, mult, d_fin);
+        k_astats_carry<<<1, 1024, 0, c->stream>>>(d_fin, d_carry, nb, pow(mult, (double)BS));
+        k_astats_c2<T><<<(int)((nb + 63) / 64), 64, smemC, c->stream>>>(x, n, mult, d_carry, tc, d_mm);
     }
     // D: noise floor
     float *d_nf = jt_dalloc<float>(c, 1);
     float h_nf = FLT_MAX;
     JT_CUDA(cudaMemcpyAsync(d_nf, &h_nf, sizeof(float), cudaMemcpyHostToDevice, c->stream));
     if (n >= tc) {
-        float *P = jt_dalloc<float>(c, n), *S = jt_dalloc<float>(c, n);
         const int64_t nbt = (n + tc - 1) / tc;
-        const int gridD = jt_grid_for(n - tc + 1, 256, c->num_sms, 8);
-        JtLaunch L(c, "astats", 3);
-        k_astats_d1<T><<<(int)((nbt + 63) / 64), 64, 0, c->stream>>>(x, n, tc, P, S);
-        k_astats_d2<<<gridD, 256, 0, c->stream>>>(P, S, n, tc, d_nf);
-        k_astats_d3<<<gridD, 256, 0, c->stream>>>(P, S, n, tc, d_nf, d_counts + 4);
+        float *d_bmin = jt_dalloc<float>(c, nbt); unsigned *d_bcnt = jt_dalloc<unsigned>(c, nbt);
+        const size_t smemD = sizeof(float) * (2 * (size_t)tc + 1);
+        if (smemD > 200 * 1024) JT_THROW(JT_ERR_UNSUPPORTED, "astats at %d Hz (50 ms window of %d samples)", in.rate, tc);
+        JT_CUDA(cudaFuncSetAttribute(k_astats_nf<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemD));
+        JtLaunch L(c, "astats", 2);
+        k_astats_nf<T><<<jt_grid_for(nbt, 1, c->num_sms, 32), AS_NF_THREADS, smemD, c->stream>>>(x, n, tc, d_bmin, d_bcnt);
+        k_astats_nf_reduce<<<1, 1024, 0, c->stream>>>(d_bmin, d_bcnt, nbt, d_nf, d_counts + 4);
     }
     std::vector<unsigned long long> hist(AS_HIST + 8);
     JT_CUDA(cudaMemcpyAsync(hist.data(), d_hist, sizeof(unsigned long long) * (AS_HIST + 8), cudaMemcpyDeviceToHost, c->stream));

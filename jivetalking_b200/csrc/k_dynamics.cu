@@ -16,8 +16,19 @@
 #define FAKE_INFINITY (65536.0 * 65536.0)
 
 // ---- switching envelope follower ----------------------------------------------------------
-#define ENV_R 128
+#define ENV_R 32            // 256-byte rows: ~35 KB of staging per warp, so 6 warps (192 lanes) fit one SM
 #define ENV_THREADS 32
+// env' = env + (d - env) * (d > env ? attack : release), rounded like the scalar C (no contraction).
+// Both branches are evaluated and the sign of (d - env) selects, so the carried chain is
+// sub -> mul -> add -> select (~28 cycles at 8.2 cycles per dependent f64 op, profiles/ubench_r1.txt)
+// instead of sub -> compare -> select -> mul -> add.
+__device__ __forceinline__ double env_step(double e, double d, double attack_coeff, double release_coeff)
+{
+    const double t = __dsub_rn(d, e);
+    const double ea = __dadd_rn(e, __dmul_rn(t, attack_coeff)), er = __dadd_rn(e, __dmul_rn(t, release_coeff));
+    return d > e ? ea : er;
+}
+
 __global__ void __launch_bounds__(ENV_THREADS)
 k_envelope(const double *__restrict__ x, double *__restrict__ env, int64_t n, int seg, int warm,
            double attack_coeff, double release_coeff, int rms)
@@ -50,7 +61,7 @@ k_envelope(const double *__restrict__ x, double *__restrict__ env, int64_t n, in
 #pragma unroll
             for (int j = 0; j < 8; j++) { const double v = row[k + j]; d[j] = rms ? v * v : fabs(v); }
 #pragma unroll
-            for (int j = 0; j < 8; j++) { e += (d[j] - e) * (d[j] > e ? attack_coeff : release_coeff); d[j] = e; }
+            for (int j = 0; j < 8; j++) { e = env_step(e, d[j], attack_coeff, release_coeff); d[j] = e; }
             if (emit) {
 #pragma unroll
                 for (int j = 0; j < 8; j++) orow[k + j] = d[j];
@@ -58,7 +69,7 @@ k_envelope(const double *__restrict__ x, double *__restrict__ env, int64_t n, in
         }
         for (; k < nv; k++) {
             const double v = row[k], dd = rms ? v * v : fabs(v);
-            e += (dd - e) * (dd > e ? attack_coeff : release_coeff);
+            e = env_step(e, dd, attack_coeff, release_coeff);
             if (emit) orow[k] = e;
         }
         if (emit) out.commit(nv);
@@ -75,7 +86,11 @@ static double *run_envelope(jt_ctx *c, const Sig &in, double attack_ms, double r
     int64_t warm = cmin >= 1.0 ? 1 : (int64_t)std::ceil(37.0 / -std::log1p(-cmin)) + 16;
     if (warm > (1 << 22)) warm = 1 << 22;
     warm = (warm + ENV_R - 1) / ENV_R * ENV_R;                 // tile-aligned (see the kernel)
-    const int seg = 16384;
+    // one wave: as many lanes as the GPU holds at once (6 single-warp CTAs per SM), never shorter than 4096 samples
+    const int64_t slots = (int64_t)c->num_sms * 6 * ENV_THREADS;
+    int64_t seg64 = std::max<int64_t>(4096, (in.n + slots - 1) / slots);
+    seg64 = std::min<int64_t>((seg64 + ENV_R - 1) / ENV_R * ENV_R, 1 << 20);
+    const int seg = (int)seg64;
     const int64_t lanes = (in.n + seg - 1) / seg;
     JtLaunch L(c, "envelope_follower");
     const size_t smem = (ENV_THREADS / 32) * (LaneStage<double, ENV_R>::WARP_BYTES + LaneStore<double, ENV_R>::WARP_BYTES);

@@ -232,6 +232,235 @@ k_swr_generic(const TIN *__restrict__ x, int64_t n, int64_t n_periods, int64_t n
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// f32-internal path, coefficients in registers ("slot" kernel).
+// Phases that read the same input window form a slot: when upsampling (pc > div) slot s = o holds the
+// R = 4..5 phases r with floor(r*div/pc) == o; when downsampling every phase is its own slot (R = 1).
+// Thread <-> slot for the whole launch: its R*L coefficients stay in registers, and for every period q
+// it reads the window x[q*div - c + o .. +L) from the CTA's staged tile (consecutive slots read
+// consecutive addresses: conflict-free) -- 1 LDS per R FFMA.  Outputs of QB consecutive periods are
+// one contiguous run out[q*pc .. (q+QB)*pc): they are collected in shared memory and leave as full
+// coalesced rows, converted to the link format on the way (s16 for the 44.1 kHz output stage).
+// ---------------------------------------------------------------------------------------
+template <class TIN, class TOUT, int L, int R, int QB>
+__global__ void __launch_bounds__(160, 2)
+k_swr_slot_f32(const TIN *__restrict__ x, int64_t n, int64_t n_periods, int64_t n_out, int pc, int div, int nslots, int qc,
+               const float *__restrict__ bank, TOUT *__restrict__ out)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int c = (L - 1) / 2;
+    const int span = qc * div + L + div;
+    float *sx = (float *)smem_raw;                       // span floats
+    float *so = sx + ((span + 3) & ~3);                  // QB * pc floats
+    const int s = threadIdx.x;
+    const bool live = s < nslots;
+    // this slot's phases: r in [rlo, rlo + cnt), all with input offset `off`
+    int rlo = 0, cnt = 0, off = 0;
+    if (live) {
+        if (R == 1) { rlo = s; cnt = 1; off = (int)(((int64_t)s * div) / pc); }
+        else { rlo = (int)(((int64_t)s * pc + div - 1) / div); const int rhi = (int)(((int64_t)(s + 1) * pc + div - 1) / div); cnt = min(rhi, pc) - rlo; off = s; }
+    }
+    float cf[R][L];
+#pragma unroll
+    for (int j = 0; j < R; j++) {
+        const int r = rlo + (j < cnt ? j : 0);
+        const int ph = (int)(((int64_t)r * div) % pc);
+#pragma unroll
+        for (int i = 0; i < L; i++) cf[j][i] = (live && j < cnt) ? bank[(size_t)ph * L + i] : 0.f;
+    }
+    const int64_t chunks = (n_periods + qc - 1) / qc;
+    for (int64_t ch = blockIdx.x; ch < chunks; ch += gridDim.x) {
+        const int64_t qa = ch * qc;
+        const int nq = (int)min((int64_t)qc, n_periods - qa);
+        const int64_t base = qa * div - c;
+        __syncthreads();
+        for (int i = threadIdx.x; i < span; i += blockDim.x) sx[i] = swr_load<TIN, float>(x, base + i, n);
+        __syncthreads();
+        for (int q0 = 0; q0 < nq; q0 += QB) {
+            float acc[QB][R];
+#pragma unroll
+            for (int b = 0; b < QB; b++)
+#pragma unroll
+                for (int j = 0; j < R; j++) acc[b][j] = 0.f;
+            if (live) {
+                const float *w = sx + q0 * div + off;
+#pragma unroll
+                for (int i = 0; i < L; i++) {
+#pragma unroll
+                    for (int b = 0; b < QB; b++) {
+                        const float v = w[b * div + i];          // periods past nq read staged slack or stale data: never stored
+#pragma unroll
+                        for (int j = 0; j < R; j++) acc[b][j] = fmaf(v, cf[j][i], acc[b][j]);
+                    }
+                }
+#pragma unroll
+                for (int b = 0; b < QB; b++)
+#pragma unroll
+                    for (int j = 0; j < R; j++) if (j < cnt) so[b * pc + rlo + j] = acc[b][j];
+            }
+            __syncthreads();
+            const int nb = min(QB, nq - q0);
+            const int64_t m0 = (qa + q0) * (int64_t)pc;
+            const int64_t lim = min((int64_t)nb * pc, n_out - m0);
+            for (int i = threadIdx.x; i < lim; i += blockDim.x) out[m0 + i] = jt_conv<float, TOUT>(so[i]);
+            __syncthreads();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// f64 path ("q-lane" kernel): lane <-> period q (two periods per lane, 32 apart), warp <-> slot.
+// The R phases of a slot share each x load, coefficient loads are warp-uniform 16-byte loads.
+// ---------------------------------------------------------------------------------------
+template <class TIN, int MODE, int RMAX>
+__global__ void __launch_bounds__(256)
+k_swr_qlane_f64(const TIN *__restrict__ x, int64_t n, int64_t n_periods, int64_t n_out,
+                int pc, int L, int div, int nslots, const double *__restrict__ bank, double *__restrict__ out,
+                double *__restrict__ tick_max, int tick, int64_t n_ticks, int span)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *sx = (double *)smem_raw;
+    const int c = (L - 1) / 2;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int64_t tiles = (n_periods + 63) / 64;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int64_t q0 = tile * 64;
+        const int64_t base = q0 * div - c;
+        __syncthreads();
+        for (int i = threadIdx.x; i < span; i += blockDim.x) sx[i + (i >> 5)] = swr_load<TIN, double>(x, base + i, n);
+        __syncthreads();
+        double cur_max[2] = {0.0, 0.0}; int64_t cur_k[2] = {-1, -1};
+        for (int s = warp; s < nslots; s += nwarp) {
+            int rlo, cnt, off;
+            if (RMAX == 1) { rlo = s; cnt = 1; off = (int)(((int64_t)s * div) / pc); }
+            else { rlo = (int)(((int64_t)s * pc + div - 1) / div); const int rhi = (int)(((int64_t)(s + 1) * pc + div - 1) / div); cnt = min(rhi, pc) - rlo; off = s; }
+            const double *f[RMAX];
+#pragma unroll
+            for (int j = 0; j < RMAX; j++) { const int r = rlo + (j < cnt ? j : 0); f[j] = bank + (size_t)(((int64_t)r * div) % pc) * L; }
+            double acc[2][RMAX];
+#pragma unroll
+            for (int t = 0; t < 2; t++)
+#pragma unroll
+                for (int j = 0; j < RMAX; j++) acc[t][j] = 0.0;
+            const int sA = lane * div + off, sB = sA + 32 * div;
+            for (int i = 0; i < L; i += 2) {
+                const int a0 = sA + i, a1 = a0 + 1, b0 = sB + i, b1 = b0 + 1;
+                const double xa0 = sx[a0 + (a0 >> 5)], xa1 = sx[a1 + (a1 >> 5)], xb0 = sx[b0 + (b0 >> 5)], xb1 = sx[b1 + (b1 >> 5)];
+#pragma unroll
+                for (int j = 0; j < RMAX; j++) {
+                    if (j < cnt) {
+                        const double2 cc = __ldg((const double2 *)(f[j] + i));
+                        acc[0][j] = fma(xa0, cc.x, acc[0][j]); acc[1][j] = fma(xb0, cc.x, acc[1][j]);
+                        acc[0][j] = fma(xa1, cc.y, acc[0][j]); acc[1][j] = fma(xb1, cc.y, acc[1][j]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < 2; t++) {
+                const int64_t q = q0 + lane + 32 * t;
+                if (q >= n_periods) continue;
+                if (MODE == SWR_MODE_STORE) {
+#pragma unroll
+                    for (int j = 0; j < RMAX; j++) { const int64_t m = q * pc + rlo + j; if (j < cnt && m < n_out) out[m] = acc[t][j]; }
+                } else {
+                    double mx = 0.0; bool any = false;
+#pragma unroll
+                    for (int j = 0; j < RMAX; j++) { const int64_t m = q * pc + rlo + j; if (j < cnt && m < n_out) { mx = fmax(mx, fabs(acc[t][j])); any = true; } }
+                    if (any) {
+                        int64_t need = q * div - c + off + L; if (need < L + 1) need = L + 1;
+                        const int64_t k = (need + tick - 1) / tick - 1;
+                        if (k != cur_k[t]) {
+                            if (cur_k[t] >= 0 && cur_k[t] < n_ticks) jt_atomic_max_nonneg(&tick_max[cur_k[t]], cur_max[t]);
+                            cur_k[t] = k; cur_max[t] = 0.0;
+                        }
+                        cur_max[t] = fmax(cur_max[t], mx);
+                    }
+                }
+            }
+        }
+        if (MODE == SWR_MODE_TICKMAX) {
+#pragma unroll
+            for (int t = 0; t < 2; t++) if (cur_k[t] >= 0 && cur_k[t] < n_ticks) jt_atomic_max_nonneg(&tick_max[cur_k[t]], cur_max[t]);
+        }
+    }
+}
+
+// device copy of the filter bank in the work format, cached per context (the plan is immutable)
+template <class TW>
+static const TW *device_bank(jt_ctx *c, const SwrPlan &p)
+{
+    const size_t nb = (size_t)p.phase_count * p.filter_length;
+    TW *d_bank = jt_dalloc<TW>(c, nb);
+    std::vector<TW> hb(nb);
+    for (size_t i = 0; i < nb; i++) hb[i] = (TW)p.bank[i];
+    JT_CUDA(cudaMemcpyAsync(d_bank, hb.data(), nb * sizeof(TW), cudaMemcpyHostToDevice, c->stream));
+    JT_CUDA(cudaStreamSynchronize(c->stream));   // hb is a stack-lifetime staging buffer
+    return d_bank;
+}
+
+static bool slot_path_ok(const SwrPlan &p)
+{
+    const int L = p.filter_length;
+    const bool up = p.phase_count > p.div;
+    const int nslots = up ? p.div : p.phase_count;
+    if (nslots < 32 || nslots > 160) return false;
+    if (up) return L == 32 && (p.phase_count + p.div - 1) / p.div <= 5;
+    return L == 36 || L == 72;
+}
+
+template <class TIN, class TOUT>
+static void launch_slot_f32(jt_ctx *c, const Sig &in, const SwrPlan &p, int64_t n_out, TOUT *out)
+{
+    const float *d_bank = device_bank<float>(c, p);
+    const int pc = p.phase_count, div = p.div, L = p.filter_length;
+    const bool up = pc > div;
+    const int nslots = up ? div : pc;
+    const int64_t n_periods = (n_out + pc - 1) / pc;
+    constexpr int QB = 2;
+    int qc = std::max(QB, std::min(64, (40 * 1024) / div / QB * QB));      // periods staged per chunk (~160 KB of floats at most)
+    const int span = qc * div + L + div;
+    const size_t smem = sizeof(float) * (((size_t)span + 3) / 4 * 4 + (size_t)QB * pc) + 16;
+    const int grid = jt_grid_for((n_periods + qc - 1) / qc, 1, c->num_sms, 8);
+#define SLOT_LAUNCH(LV, RV) do { auto kfn = k_swr_slot_f32<TIN, TOUT, LV, RV, QB>; \
+        JT_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        kfn<<<grid, 160, smem, c->stream>>>((const TIN *)in.d, in.n, n_periods, n_out, pc, div, nslots, qc, d_bank, out); } while (0)
+    if (up) SLOT_LAUNCH(32, 5);
+    else if (L == 36) SLOT_LAUNCH(36, 1);
+    else SLOT_LAUNCH(72, 1);
+#undef SLOT_LAUNCH
+}
+
+template <class TIN, int MODE>
+static void launch_qlane_f64(jt_ctx *c, const Sig &in, const SwrPlan &p, int64_t n_out, double *out,
+                             double *tick_max, int tick, int64_t n_ticks)
+{
+    const double *d_bank = device_bank<double>(c, p);
+    const int pc = p.phase_count, div = p.div, L = p.filter_length;
+    const bool up = pc > div;
+    const int nslots = up ? div : pc;
+    const int64_t n_periods = (n_out + pc - 1) / pc;
+    const int span = 64 * div + L + div;
+    const size_t smem = (size_t)(span + (span >> 5) + 2) * sizeof(double);
+    const int grid = jt_grid_for((n_periods + 63) / 64, 1, c->num_sms, 8);
+    if (up) {
+        auto kfn = k_swr_qlane_f64<TIN, MODE, 5>;
+        JT_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kfn<<<grid, 256, smem, c->stream>>>((const TIN *)in.d, in.n, n_periods, n_out, pc, L, div, nslots, d_bank, out, tick_max, tick, n_ticks, span);
+    } else {
+        auto kfn = k_swr_qlane_f64<TIN, MODE, 1>;
+        JT_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kfn<<<grid, 256, smem, c->stream>>>((const TIN *)in.d, in.n, n_periods, n_out, pc, L, div, nslots, d_bank, out, tick_max, tick, n_ticks, span);
+    }
+}
+static bool qlane_path_ok(const SwrPlan &p)
+{
+    const bool up = p.phase_count > p.div;
+    if (p.filter_length % 2) return false;
+    if (up && (p.phase_count + p.div - 1) / p.div > 5) return false;
+    const size_t span = 64 * (size_t)p.div + p.filter_length + p.div;
+    return (span + (span >> 5) + 2) * sizeof(double) <= 200 * 1024;
+}
+
 template <class TIN, int MODE>
 static void launch_small(jt_ctx *c, const Sig &in, const SwrPlan &p, int64_t n_out, double *out,
                          double *tick_max, int tick, int64_t n_ticks)
@@ -266,12 +495,14 @@ static void launch_generic(jt_ctx *c, const Sig &in, const SwrPlan &p, int64_t n
 
 static bool small_path(const SwrPlan &p) { return p.div == 1 && p.filter_length == 32 && (p.phase_count == 2 || p.phase_count == 4 || p.phase_count == 6 || p.phase_count == 8); }
 
-Sig jt_swr_resample(jt_ctx *c, const Sig &in, const SwrPlan &p, int work_fmt, bool flush)
+Sig jt_swr_resample(jt_ctx *c, const Sig &in, const SwrPlan &p, int work_fmt, bool flush, int fuse_out_fmt)
 {
     if (p.identity) return jt_convert(c, in, work_fmt);
     const int64_t n_out = flush ? p.out_count_flush(in.n) : p.out_count(in.n);
-    Sig o; o.fmt = work_fmt; o.rate = p.out_rate; o.n = n_out;
-    o.d = jt_dalloc_bytes(c, (size_t)std::max<int64_t>(n_out, 1) * jt_fmt_bytes(work_fmt));
+    // the f32 slot kernel converts on store: the 44.1 kHz / s16 output stage never materialises its float stream
+    const bool fuse_s16 = work_fmt == JT_FMT_FLT && fuse_out_fmt == JT_FMT_S16 && slot_path_ok(p) && in.fmt != JT_FMT_DBL;
+    Sig o; o.fmt = fuse_s16 ? JT_FMT_S16 : work_fmt; o.rate = p.out_rate; o.n = n_out;
+    o.d = jt_dalloc_bytes(c, (size_t)std::max<int64_t>(n_out, 1) * jt_fmt_bytes(o.fmt));
     if (n_out <= 0) return o;
     JtLaunch Lc(c, "swr_resample");
     if (work_fmt == JT_FMT_DBL) {
@@ -279,15 +510,29 @@ Sig jt_swr_resample(jt_ctx *c, const Sig &in, const SwrPlan &p, int work_fmt, bo
             if (in.fmt == JT_FMT_S16) launch_small<int16_t, SWR_MODE_STORE>(c, in, p, n_out, (double *)o.d, nullptr, 1, 0);
             else if (in.fmt == JT_FMT_FLT) launch_small<float, SWR_MODE_STORE>(c, in, p, n_out, (double *)o.d, nullptr, 1, 0);
             else launch_small<double, SWR_MODE_STORE>(c, in, p, n_out, (double *)o.d, nullptr, 1, 0);
+        } else if (qlane_path_ok(p)) {
+            if (in.fmt == JT_FMT_S16) launch_qlane_f64<int16_t, SWR_MODE_STORE>(c, in, p, n_out, (double *)o.d, nullptr, 1, 0);
+            else if (in.fmt == JT_FMT_FLT) launch_qlane_f64<float, SWR_MODE_STORE>(c, in, p, n_out, (double *)o.d, nullptr, 1, 0);
+            else launch_qlane_f64<double, SWR_MODE_STORE>(c, in, p, n_out, (double *)o.d, nullptr, 1, 0);
         } else {
             if (in.fmt == JT_FMT_S16) launch_generic<int16_t, double, SWR_MODE_STORE>(c, in, p, n_out, (double *)o.d, nullptr, 1, 0);
             else if (in.fmt == JT_FMT_FLT) launch_generic<float, double, SWR_MODE_STORE>(c, in, p, n_out, (double *)o.d, nullptr, 1, 0);
             else launch_generic<double, double, SWR_MODE_STORE>(c, in, p, n_out, (double *)o.d, nullptr, 1, 0);
         }
     } else if (work_fmt == JT_FMT_FLT) {
-        if (in.fmt == JT_FMT_S16) launch_generic<int16_t, float, SWR_MODE_STORE>(c, in, p, n_out, (float *)o.d, nullptr, 1, 0);
-        else if (in.fmt == JT_FMT_FLT) launch_generic<float, float, SWR_MODE_STORE>(c, in, p, n_out, (float *)o.d, nullptr, 1, 0);
-        else JT_THROW(JT_ERR_UNSUPPORTED, "f64 -> f32-internal resample");
+        if (in.fmt == JT_FMT_DBL) JT_THROW(JT_ERR_UNSUPPORTED, "f64 -> f32-internal resample");
+        if (slot_path_ok(p)) {
+            if (fuse_s16) {
+                if (in.fmt == JT_FMT_S16) launch_slot_f32<int16_t, int16_t>(c, in, p, n_out, (int16_t *)o.d);
+                else launch_slot_f32<float, int16_t>(c, in, p, n_out, (int16_t *)o.d);
+            } else {
+                if (in.fmt == JT_FMT_S16) launch_slot_f32<int16_t, float>(c, in, p, n_out, (float *)o.d);
+                else launch_slot_f32<float, float>(c, in, p, n_out, (float *)o.d);
+            }
+        } else {
+            if (in.fmt == JT_FMT_S16) launch_generic<int16_t, float, SWR_MODE_STORE>(c, in, p, n_out, (float *)o.d, nullptr, 1, 0);
+            else launch_generic<float, float, SWR_MODE_STORE>(c, in, p, n_out, (float *)o.d, nullptr, 1, 0);
+        }
     } else JT_THROW(JT_ERR_UNSUPPORTED, "swr work format %d", work_fmt);
     return o;
 }
@@ -306,6 +551,10 @@ void jt_swr_tick_absmax(jt_ctx *c, const Sig &in, const SwrPlan &p, int tick, in
         if (v.fmt == JT_FMT_S16) launch_small<int16_t, SWR_MODE_TICKMAX>(c, v, p, n_out, nullptr, d_tick_tp, tick, n_ticks);
         else if (v.fmt == JT_FMT_FLT) launch_small<float, SWR_MODE_TICKMAX>(c, v, p, n_out, nullptr, d_tick_tp, tick, n_ticks);
         else launch_small<double, SWR_MODE_TICKMAX>(c, v, p, n_out, nullptr, d_tick_tp, tick, n_ticks);
+    } else if (qlane_path_ok(p)) {
+        if (v.fmt == JT_FMT_S16) launch_qlane_f64<int16_t, SWR_MODE_TICKMAX>(c, v, p, n_out, nullptr, d_tick_tp, tick, n_ticks);
+        else if (v.fmt == JT_FMT_FLT) launch_qlane_f64<float, SWR_MODE_TICKMAX>(c, v, p, n_out, nullptr, d_tick_tp, tick, n_ticks);
+        else launch_qlane_f64<double, SWR_MODE_TICKMAX>(c, v, p, n_out, nullptr, d_tick_tp, tick, n_ticks);
     } else {
         if (v.fmt == JT_FMT_S16) launch_generic<int16_t, double, SWR_MODE_TICKMAX>(c, v, p, n_out, (double *)nullptr, d_tick_tp, tick, n_ticks);
         else if (v.fmt == JT_FMT_FLT) launch_generic<float, double, SWR_MODE_TICKMAX>(c, v, p, n_out, (double *)nullptr, d_tick_tp, tick, n_ticks);

@@ -92,8 +92,10 @@ def test_full_four_pass_chain(ctx, speech):
     assert len(pcm) == len(p4["pcm"]) and rms(d) < 1e-4, rms(d)
     # ... while on IDENTICAL Pass-2 samples the Pass-3 / Pass-4 graphs agree tightly
     g3 = ctx.run_graph(spec3, p2["pcm"], 44100, want_pcm=False, want_meta=False)
+    # (input_tp is the peak of the f32-internal 192 kHz resample: the 32 taps are summed in another order than the
+    #  oracle's even/odd split -- as libswresample's own SIMD paths do -- so it carries one f32 ulp, ~1e-6 dB)
     for k in ("input_i", "input_tp", "input_lra", "input_thresh"):
-        assert abs(getattr(g3["loudnorm"], k) - p3["loudnorm"][k]) < 1e-6, k
+        assert abs(getattr(g3["loudnorm"], k) - p3["loudnorm"][k]) < (1e-5 if k == "input_tp" else 1e-6), k
     g4 = ctx.run_graph(spec4, p2["pcm"], 44100)
     pcm_close_s16(g4["pcm"], p4["pcm"])
     OG.assert_meta_close(g4["meta"], p4["meta"], spectral_rtol=5e-3)
