@@ -184,6 +184,9 @@ int jt_build_pass4_spec(const jt_process_result *plan, const jt_loudnorm_stats *
 int jt_default_pass2_spec(char *buf, size_t cap);
 int jt_pass1_spec(char *buf, size_t cap);
 
+/* the cudaStream_t (as void *) every kernel and copy of this context is issued on, so a caller can order its own
+ * device work against it or bracket calls with CUDA events */
+void   *jt_cuda_stream(const jt_ctx *ctx);
 /* kernel launches since jt_create / since the last reset (bench.py's gpu_launches) */
 int64_t jt_launch_count(const jt_ctx *ctx);
 void    jt_reset_launch_count(jt_ctx *ctx);

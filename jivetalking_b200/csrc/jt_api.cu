@@ -65,6 +65,7 @@ extern "C" void jt_destroy(jt_ctx *c)
 
 extern "C" const char *jt_last_error(const jt_ctx *c) { return c ? c->last_error.c_str() : ""; }
 extern "C" void jt_cancel(jt_ctx *c) { if (c) c->cancel.store(1); }
+extern "C" void *jt_cuda_stream(const jt_ctx *c) { return c ? (void *)c->stream : nullptr; }
 extern "C" int64_t jt_launch_count(const jt_ctx *c) { return c ? c->launches : 0; }
 extern "C" void jt_reset_launch_count(jt_ctx *c) { if (c) { c->launches = 0; jt_flush_timing(c); for (auto &s : c->slots) { s.ms = 0; s.launches = 0; } } }
 extern "C" void jt_enable_kernel_timing(jt_ctx *c, int on) { if (c) c->timing = on != 0; }

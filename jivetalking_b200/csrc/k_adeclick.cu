@@ -310,10 +310,13 @@ Sig jt_adeclick(jt_ctx *c, const Sig &in, double w_ms, double overlap_pct, doubl
     const size_t nmax = (size_t)K.W;
     const size_t scratch_per_warp = nmax * K.order + 3 * nmax + (nmax + 1) / 2 + 8;
     double *scratch = jt_dalloc<double>(c, scratch_per_warp * (size_t)gridE * DC_WARPS);
-    JtLaunch L(c, "adeclick", 4);
-    k_dc_autocorr<<<jt_grid_for(nw, 1, c->num_sms, 64), 64, smemA, c->stream>>>((const double *)in.d, in.n, nw, K, d_r);
-    k_dc_levinson<<<(int)((nw + 127) / 128), 128, 0, c->stream>>>(d_r, nw, K, d_a, d_sig);
-    k_dc_detect<<<jt_grid_for(nw, 1, c->num_sms, 32), 256, smemC, c->stream>>>((const double *)in.d, in.n, nw, K, d_a, d_sig, d_bits, d_cnt);
+    { JtLaunch L(c, "adeclick:autocorr");
+    k_dc_autocorr<<<jt_grid_for(nw, 1, c->num_sms, 64), 64, smemA, c->stream>>>((const double *)in.d, in.n, nw, K, d_r); }
+    { JtLaunch L(c, "adeclick:levinson");
+    k_dc_levinson<<<(int)((nw + 127) / 128), 128, 0, c->stream>>>(d_r, nw, K, d_a, d_sig); }
+    { JtLaunch L(c, "adeclick:detect");
+    k_dc_detect<<<jt_grid_for(nw, 1, c->num_sms, 32), 256, smemC, c->stream>>>((const double *)in.d, in.n, nw, K, d_a, d_sig, d_bits, d_cnt); }
+    JtLaunch L(c, "adeclick:interp");
     k_dc_interp<<<gridE, DC_WARPS * 32, smemE, c->stream>>>((const double *)in.d, (double *)o.d, in.n, nw, K, d_a, d_bits, d_cnt,
                                                             scratch, scratch_per_warp, d_next);
     return o;

@@ -6,12 +6,17 @@
 //
 // The filter's only cross-hop state is (a) prior[bin], a contraction (factor <= 0.39 per hop),
 // (b) prior_band_excit[band], a contraction (factor beta <= 0.78), (c) the tracked noise floor
-// (tn=1), which depends on the INPUT spectra only.  So:
-//   F1  one CTA per hop: window, forward FFT (shared-memory radix-2), spectrum -> HBM;
-//       with tn=1 also the hop's flatness / floor candidate
-//   F2  one thread: noise-floor recurrence over hops (tn=1)
-//   F3  one CTA per chunk of hops (+128 warm-up hops): the gain recursion, band masking,
-//       gain limiting, inverse FFT -> windowed frames in HBM
+// (tn=1), which depends on the INPUT spectra only.  So the per-hop work is cut along its data
+// dependences instead of being walked hop by hop:
+//   F1  forward FFT, two hops per transform (hop 2p as the real part, hop 2p+1 as the imaginary part of
+//       one complex Stockham radix-4 FFT in shared memory, separated by symmetry); with tn=1 also each
+//       hop's flatness test and floor candidate.  Fully parallel over hop pairs.
+//   F2  noise-floor recurrence over hops as an affine scan (tn=1)
+//   F3a a-priori-SNR gain recursion: one thread per BIN walks a chunk of hops (+128 warm-up hops),
+//       coalesced across bins -> gain[hop][bin], clean[hop][bin]
+//   F3b band excitation: per-band sums (bin order, as the scalar code), the per-band recursion over hops
+//       (+128 warm-up hops) and the spreading matrix -> amt[hop][band]
+//   F3c gain limiting, spectrum scaling and the inverse FFT, again two hops per transform -> windowed frames
 //   F4  overlap-add of the three frames covering each output sample (f64, hop order)
 #include "jt_internal.h"
 #include "jt_device.cuh"
@@ -27,78 +32,140 @@ struct AfConst {
     double floor_, gain_scale, max_gain, ratio, floor_offset;
 };
 
-__device__ __forceinline__ void af_fft(float2 *s, const float2 *__restrict__ tw, int n, bool inverse)
-{   // in-place radix-2 DIT on bit-reversed input (caller stores bit-reversed)
-    for (int len = 2; len <= n; len <<= 1) {
-        const int half = len >> 1, tstep = n / len;
-        for (int b = threadIdx.x; b < n / 2; b += blockDim.x) {
-            const int k = b & (half - 1), i = ((b - k) << 1) + k;
-            float2 w = tw[k * tstep]; if (inverse) w.y = -w.y;
-            const float2 a = s[i], bb = s[i + half];
-            const float tr = __fsub_rn(__fmul_rn(bb.x, w.x), __fmul_rn(bb.y, w.y));
-            const float ti = __fadd_rn(__fmul_rn(bb.x, w.y), __fmul_rn(bb.y, w.x));
-            s[i] = make_float2(a.x + tr, a.y + ti);
-            s[i + half] = make_float2(a.x - tr, a.y - ti);
+__device__ __forceinline__ float2 af_cmul(float2 a, float2 w) { return make_float2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x); }
+
+// Stockham autosort FFT of n = 2^k points in shared memory (natural order in and out): radix-4 passes and,
+// for odd k, one final radix-2 pass, ping-ponging between `a` and `b`.  tw[j] = exp(-2*pi*i*j/n), j < n.
+// Returns the buffer holding the result; ends with a barrier.
+template <bool INV>
+__device__ __forceinline__ float2 *af_fft(float2 *a, float2 *b, const float2 *__restrict__ tw, int n)
+{
+    float2 *src = a, *dst = b;
+    int ns = 1;
+    const int q = n >> 2;
+    for (; ns * 4 <= n; ns <<= 2) {
+        const int tstep = n / (ns * 4);
+        for (int j = threadIdx.x; j < q; j += blockDim.x) {
+            const int k = j & (ns - 1), t = k * tstep;
+            float2 v0 = src[j], v1 = src[j + q], v2 = src[j + 2 * q], v3 = src[j + 3 * q];
+            float2 w1 = tw[t], w2 = tw[2 * t], w3 = tw[3 * t];
+            if (INV) { w1.y = -w1.y; w2.y = -w2.y; w3.y = -w3.y; }
+            v1 = af_cmul(v1, w1); v2 = af_cmul(v2, w2); v3 = af_cmul(v3, w3);
+            const float2 a0 = make_float2(v0.x + v2.x, v0.y + v2.y), a1 = make_float2(v0.x - v2.x, v0.y - v2.y);
+            const float2 a2 = make_float2(v1.x + v3.x, v1.y + v3.y), d3 = make_float2(v1.x - v3.x, v1.y - v3.y);
+            const float2 a3 = INV ? make_float2(-d3.y, d3.x) : make_float2(d3.y, -d3.x);      // (+/-)i * (v1 - v3)
+            const int j0 = ((j - k) << 2) + k;
+            dst[j0] = make_float2(a0.x + a2.x, a0.y + a2.y);
+            dst[j0 + ns] = make_float2(a1.x + a3.x, a1.y + a3.y);
+            dst[j0 + 2 * ns] = make_float2(a0.x - a2.x, a0.y - a2.y);
+            dst[j0 + 3 * ns] = make_float2(a1.x - a3.x, a1.y - a3.y);
         }
         __syncthreads();
+        float2 *t = src; src = dst; dst = t;
+    }
+    if (ns < n) {                                   // ns == n / 2
+        const int h = n >> 1;
+        for (int j = threadIdx.x; j < h; j += blockDim.x) {
+            float2 w = tw[j]; if (INV) w.y = -w.y;
+            const float2 v0 = src[j], v1 = af_cmul(src[j + h], w);
+            dst[j] = make_float2(v0.x + v1.x, v0.y + v1.y);
+            dst[j + h] = make_float2(v0.x - v1.x, v0.y - v1.y);
+        }
+        __syncthreads();
+        float2 *t = src; src = dst; dst = t;
+    }
+    return src;
+}
+
+// block-wide sum / max of NV doubles per thread at once (one barrier pair)
+template <int NV, bool MAX>
+__device__ __forceinline__ void af_block_reduce(double (&v)[NV], double (*red)[8])
+{
+#pragma unroll
+    for (int i = 0; i < NV; i++) v[i] = MAX ? jt_warp_max(v[i]) : jt_warp_sum(v[i]);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; i++) red[threadIdx.x >> 5][i] = v[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; i++) {
+        double s = 0;
+        for (int w = 0; w < AF_THREADS / 32; w++) s = MAX ? fmax(s, red[w][i]) : s + red[w][i];
+        v[i] = s;
     }
 }
 
-__device__ __forceinline__ double af_block_sum(double v, double *red)
-{
-    v = jt_warp_sum(v);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    double s = 0; for (int i = 0; i < AF_THREADS / 32; i++) s += red[i];
-    return s;
-}
-__device__ __forceinline__ double af_block_max(double v, double *red)
-{
-    v = jt_warp_max(v);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-    __syncthreads();
-    double s = 0; for (int i = 0; i < AF_THREADS / 32; i++) s = fmax(s, red[i]);
-    return s;
-}
-
-// F1: forward transform of every hop; optional noise-floor candidate (track_noise)
-__global__ void __launch_bounds__(AF_THREADS)
+// F1: forward transform of hop pairs; optional noise-floor candidates (track_noise)
+__global__ void __launch_bounds__(AF_THREADS, 2)
 k_afftdn_fwd(const float *__restrict__ x, int64_t n, int64_t n_hops, AfConst K, const double *__restrict__ window,
-             const float2 *__restrict__ tw, float2 *__restrict__ spectra, int track, double *__restrict__ cand /* 2 per hop: new_floor, flag */)
+             const float2 *__restrict__ tw_g, float2 *__restrict__ spectra, int track, double *__restrict__ cand /* 2 per hop: new_floor, flag */)
 {
-    extern __shared__ float2 sb[];
-    __shared__ double red[AF_THREADS / 32];
-    int logn = 0; while ((1 << logn) < K.FL) logn++;
-    for (int64_t h = blockIdx.x; h < n_hops; h += gridDim.x) {
-        const int64_t w0 = (h - 2) * (int64_t)K.A, avail = min(n, (h + 1) * (int64_t)K.A);
+    extern __shared__ float2 sm[];
+    __shared__ double red[AF_THREADS / 32][8];
+    const int N = K.FL, t = threadIdx.x;
+    float2 *bufA = sm, *bufB = sm + N, *tw = sm + 2 * N;
+    for (int i = t; i < N; i += AF_THREADS) tw[i] = tw_g[i];
+    const int64_t n_pairs = (n_hops + 1) / 2;
+    for (int64_t pr = blockIdx.x; pr < n_pairs; pr += gridDim.x) {
+        const int64_t h0 = 2 * pr, h1 = h0 + 1;
+        const bool has1 = h1 < n_hops;
+        const int64_t wa = (h0 - 2) * (int64_t)K.A, ava = min(n, (h0 + 1) * (int64_t)K.A);
+        const int64_t wb = (h1 - 2) * (int64_t)K.A, avb = min(n, (h1 + 1) * (int64_t)K.A);
         __syncthreads();
-        for (int m = threadIdx.x; m < K.FL; m += AF_THREADS) {
-            float v = 0.f;
-            if (m < K.W) { const int64_t s = w0 + m; if (s >= 0 && s < avail) v = (float)(window[m] * (double)x[s] * 8388608.0); }
-            sb[__brev((unsigned)m) >> (32 - logn)] = make_float2(v, 0.f);
+        for (int m = t; m < N; m += AF_THREADS) {
+            float a = 0.f, b = 0.f;
+            if (m < K.W) {
+                const double wv = window[m];
+                const int64_t sa = wa + m, sb = wb + m;
+                if (sa >= 0 && sa < ava) a = (float)(wv * (double)x[sa] * 8388608.0);
+                if (has1 && sb >= 0 && sb < avb) b = (float)(wv * (double)x[sb] * 8388608.0);
+            }
+            bufA[m] = make_float2(a, b);
         }
         __syncthreads();
-        af_fft(sb, tw, K.FL, false);
-        for (int i = threadIdx.x; i < K.bins; i += AF_THREADS) spectra[h * (int64_t)K.bins + i] = sb[i];
-        if (track) {
-            double num = 0, den = 0, cnt = 0;
-            for (int i = threadIdx.x; i < K.bins; i += AF_THREADS) {
-                const double v = hypot((double)sb[i].x, (double)sb[i].y);
-                if (v > K.floor_) { num += log(v); den += v; cnt += 1; }
+        const float2 *Z = af_fft<false>(bufA, bufB, tw, N);
+        // separate the two real transforms: A[k] = (Z[k] + conj(Z[N-k])) / 2, B[k] = (Z[k] - conj(Z[N-k])) / 2i
+        double mga[AF_MAXOWN], mgb[AF_MAXOWN];
+#pragma unroll
+        for (int j = 0; j < AF_MAXOWN; j++) {
+            const int k = t + j * AF_THREADS;
+            mga[j] = mgb[j] = -1.0;
+            if (k < K.bins) {
+                const float2 zk = Z[k], zn = Z[(N - k) & (N - 1)];
+                const float2 fa = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
+                const float2 fb = make_float2(0.5f * (zk.y + zn.y), 0.5f * (zn.x - zk.x));
+                spectra[h0 * (int64_t)K.bins + k] = fa;
+                if (has1) spectra[h1 * (int64_t)K.bins + k] = fb;
+                if (track) { mga[j] = hypot((double)fa.x, (double)fa.y); mgb[j] = hypot((double)fb.x, (double)fb.y); }
             }
-            num = af_block_sum(num, red); den = af_block_sum(den, red); cnt = af_block_sum(cnt, red);
-            const double size = fmax(cnt, 1.0);
-            num = exp(num / size); den /= size;
-            double off = 0;
-            for (int i = threadIdx.x; i < K.bins; i += AF_THREADS) off = fmax(off, fabs(hypot((double)sb[i].x, (double)sb[i].y) - den));
-            off = af_block_max(off, red);
-            if (threadIdx.x == 0) {
-                const double flat = num / den;
-                double nf = 10.0 * log10(den) - 100.0 + K.floor_offset * (off / den);
-                nf = fmin(fmax(nf, -90.), -20.);
-                cand[2 * h] = nf; cand[2 * h + 1] = (flat > 0.8) ? 1.0 : 0.0;
+        }
+        if (track) {
+            double sums[6] = {0, 0, 0, 0, 0, 0};          // num, den, count for each of the two hops
+#pragma unroll
+            for (int j = 0; j < AF_MAXOWN; j++) {
+                if (mga[j] > K.floor_) { sums[0] += log(mga[j]); sums[1] += mga[j]; sums[2] += 1; }
+                if (mgb[j] > K.floor_) { sums[3] += log(mgb[j]); sums[4] += mgb[j]; sums[5] += 1; }
+            }
+            af_block_reduce<6, false>(sums, red);
+            const double size_a = fmax(sums[2], 1.0), size_b = fmax(sums[5], 1.0);
+            const double num_a = exp(sums[0] / size_a), den_a = sums[1] / size_a;
+            const double num_b = exp(sums[3] / size_b), den_b = sums[4] / size_b;
+            double off[2] = {0, 0};
+#pragma unroll
+            for (int j = 0; j < AF_MAXOWN; j++) {
+                if (mga[j] >= 0) off[0] = fmax(off[0], fabs(mga[j] - den_a));
+                if (mgb[j] >= 0) off[1] = fmax(off[1], fabs(mgb[j] - den_b));
+            }
+            af_block_reduce<2, true>(off, red);
+            if (t == 0) {
+                double nf = 10.0 * log10(den_a) - 100.0 + K.floor_offset * (off[0] / den_a);
+                cand[2 * h0] = fmin(fmax(nf, -90.), -20.); cand[2 * h0 + 1] = (num_a / den_a > 0.8) ? 1.0 : 0.0;
+                if (has1) {
+                    nf = 10.0 * log10(den_b) - 100.0 + K.floor_offset * (off[1] / den_b);
+                    cand[2 * h1] = fmin(fmax(nf, -90.), -20.); cand[2 * h1 + 1] = (num_b / den_b > 0.8) ? 1.0 : 0.0;
+                }
             }
         }
     }
@@ -136,87 +203,141 @@ __device__ __forceinline__ double af_limit_gain(double a, double b)
     return 1.0;
 }
 
-// F3: the recursion over a chunk of hops
-__global__ void __launch_bounds__(AF_THREADS)
-k_afftdn_core(const float2 *__restrict__ spectra, int64_t n_hops, int chunk, int warm, AfConst K,
-              const double *__restrict__ rel_var, const int *__restrict__ band_lo /* nbands+1 */,
-              const int *__restrict__ bin2band, const double *__restrict__ band_alpha, const double *__restrict__ band_beta,
-              const double *__restrict__ spread, const double *__restrict__ mv_pre, const double *__restrict__ mv_post,
-              const float2 *__restrict__ tw, float *__restrict__ frames)
+// F3a: a-priori SNR recursion, one thread per bin over a chunk of hops (warm-up hops first)
+#define AF_GAIN_THREADS 128
+__global__ void __launch_bounds__(AF_GAIN_THREADS)
+k_afftdn_gain(const float2 *__restrict__ spectra, int64_t n_hops, int chunk, int warm, AfConst K,
+              const double *__restrict__ rel_var, const double *__restrict__ mv_pre,
+              double *__restrict__ gain, double *__restrict__ clean)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2 *sb = (float2 *)smem_raw;                               // FL complex (inverse transform)
-    double *clean = (double *)(smem_raw + sizeof(float2) * K.FL);  // bins
-    __shared__ double s_be[AF_MAXBANDS], s_amt[AF_MAXBANDS];
-    const int t = threadIdx.x;
+    const int i = blockIdx.x * AF_GAIN_THREADS + threadIdx.x;
+    if (i >= K.bins) return;
+    const int64_t h_out0 = (int64_t)blockIdx.y * chunk;
+    if (h_out0 >= n_hops) return;
+    const int64_t h_out1 = min(h_out0 + chunk, n_hops), h_begin = max((int64_t)0, h_out0 - warm);
+    const double rv = rel_var[i];
+    double prior = 0.0;
+    auto step = [&](int64_t h, float2 sp) {
+        const double ratio = (h == 0) ? 1.0 : K.ratio, rratio = 1.0 - ratio;
+        const double mag = hypot((double)sp.x, (double)sp.y), power = mag * mag;
+        const double abs_var = fmax(mv_pre[h] * rv, 1.0);
+        const double mav = power / abs_var;
+        const double nmav = ratio * prior + rratio * fmax(mav - 1.0, 0.0);
+        const double g = nmav / (1.0 + nmav), sg = g * g;
+        prior = mav * sg;
+        if (h >= h_out0) { gain[h * (int64_t)K.bins + i] = g; clean[h * (int64_t)K.bins + i] = power * sg; }
+    };
+    int64_t h = h_begin;
+    for (; h + 4 <= h_out1; h += 4) {             // four loads in flight ahead of the carried chain
+        float2 sp[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) sp[u] = spectra[(h + u) * (int64_t)K.bins + i];
+#pragma unroll
+        for (int u = 0; u < 4; u++) step(h + u, sp[u]);
+    }
+    for (; h < h_out1; h++) step(h, spectra[h * (int64_t)K.bins + i]);
+}
+
+// F3b-1: band excitation before the recursion: raw[hop][band] = sum of clean over the band's bins, in bin order
+__global__ void __launch_bounds__(256)
+k_afftdn_bandsum(const double *__restrict__ clean, int64_t n_hops, AfConst K, const int *__restrict__ band_lo /* nbands+1 */,
+                 double *__restrict__ raw)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t h = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; h < n_hops; h += warps) {
+        const double *row = clean + h * (int64_t)K.bins;
+        for (int b = lane; b < K.nbands; b += 32) {
+            double be = 0.0;
+            const int lo = band_lo[b], hi = band_lo[b + 1];
+            for (int i = lo; i < hi; i++) be += row[i];
+            raw[h * (int64_t)K.nbands + b] = be;
+        }
+    }
+}
+
+// F3b-2: per-band recursion over a chunk of hops (warm-up hops first), then the spreading matrix
+__global__ void __launch_bounds__(256)
+k_afftdn_bandrec(const double *__restrict__ raw, int64_t n_hops, int chunk, int warm, AfConst K,
+                 const double *__restrict__ band_alpha, const double *__restrict__ band_beta, const double *__restrict__ spread,
+                 double *__restrict__ amt)
+{
+    extern __shared__ double sbe[];                         // (chunk + warm) x nbands, then nbands x nbands
+    const int nb = K.nbands, t = threadIdx.x;
+    double *ssp = sbe + (size_t)(chunk + warm) * nb;
     const int64_t h_out0 = (int64_t)blockIdx.x * chunk;
     if (h_out0 >= n_hops) return;
-    const int64_t h_out1 = min(h_out0 + chunk, n_hops);
-    const int64_t h_begin = max((int64_t)0, h_out0 - warm);
-    int logn = 0; while ((1 << logn) < K.FL) logn++;
-    // per-thread bins: t, t + 512, ... (bins <= AF_MAXOWN * 512)
-    constexpr int nb_own = AF_MAXOWN;
-    int bidx[AF_MAXOWN];
-    double prior[AF_MAXOWN], rv[AF_MAXOWN], gain[AF_MAXOWN];
-    float2 sp[AF_MAXOWN];
-#pragma unroll
-    for (int k = 0; k < nb_own; k++) { bidx[k] = t + k * AF_THREADS; prior[k] = 0.0; gain[k] = 0.0; sp[k] = make_float2(0.f, 0.f); rv[k] = bidx[k] < K.bins ? rel_var[bidx[k]] : 1.0; }
-    double prior_be = 0.0;                                          // thread b < nbands owns band b
-    const double alpha = t < K.nbands ? band_alpha[t] : 0, beta = t < K.nbands ? band_beta[t] : 0;
-    const int blo = t < K.nbands ? band_lo[t] : 0, bhi = t < K.nbands ? band_lo[t + 1] : 0;
+    const int64_t h_out1 = min(h_out0 + chunk, n_hops), h_begin = max((int64_t)0, h_out0 - warm);
+    const int nh = (int)(h_out1 - h_begin);
+    for (int i = t; i < nh * nb; i += blockDim.x) sbe[i] = raw[h_begin * nb + i];
+    for (int i = t; i < nb * nb; i += blockDim.x) ssp[i] = spread[i];
+    __syncthreads();
+    if (t < nb) {
+        const double alpha = band_alpha[t], beta = band_beta[t];
+        double prev = 0.0;
+        for (int h = 0; h < nh; h++) {
+            double be = sbe[h * nb + t];
+            be = fmax(be, alpha * be + beta * prev);
+            prev = be;
+            sbe[h * nb + t] = be;
+        }
+    }
+    __syncthreads();
+    const int skip = (int)(h_out0 - h_begin);
+    for (int i = t; i < (nh - skip) * nb; i += blockDim.x) {
+        const int h = skip + i / nb, j = i % nb;
+        double a = 0.0;
+        for (int k = 0; k < nb; k++) a += ssp[j * nb + k] * sbe[h * nb + k];
+        amt[(h_begin + h) * nb + j] = a;
+    }
+}
 
-    for (int64_t h = h_begin; h < h_out1; h++) {
-        const double ratio = (h == 0) ? 1.0 : K.ratio, rratio = 1.0 - ratio;
-        const double mvp = mv_pre[h], mvq = mv_post[h];
-#pragma unroll
-        for (int k = 0; k < nb_own; k++) {
-            const int i = bidx[k]; if (i >= K.bins) continue;
-            sp[k] = spectra[h * (int64_t)K.bins + i];
-            const double mag = hypot((double)sp[k].x, (double)sp[k].y), power = mag * mag;
-            const double abs_var = fmax(mvp * rv[k], 1.0);
-            const double mav = power / abs_var;
-            const double nmav = ratio * prior[k] + rratio * fmax(mav - 1.0, 0.0);
-            const double g = nmav / (1.0 + nmav), sg = g * g;
-            prior[k] = mav * sg;
-            clean[i] = power * sg;
-            gain[k] = g;
-        }
+// F3c: gain limiting against the masking threshold, spectrum scaling, inverse transform of hop pairs
+__global__ void __launch_bounds__(AF_THREADS)
+k_afftdn_synth(const float2 *__restrict__ spectra, const double *__restrict__ gain, const double *__restrict__ amt,
+               int64_t n_hops, AfConst K, const double *__restrict__ rel_var, const int *__restrict__ bin2band,
+               const double *__restrict__ mv_post, const float2 *__restrict__ tw_g, float *__restrict__ frames)
+{
+    extern __shared__ float2 sm[];
+    const int N = K.FL, t = threadIdx.x;
+    float2 *bufA = sm, *bufB = sm + N, *tw = sm + 2 * N;
+    for (int i = t; i < N; i += AF_THREADS) tw[i] = tw_g[i];
+    const int64_t n_pairs = (n_hops + 1) / 2;
+    for (int64_t pr = blockIdx.x; pr < n_pairs; pr += gridDim.x) {
+        const int64_t h0 = 2 * pr;
+        const bool has1 = h0 + 1 < n_hops;
         __syncthreads();
-        if (t < K.nbands) {
-            double be = 0.0;
-            for (int i = blo; i < bhi; i++) be += clean[i];
-            be = fmax(be, alpha * be + beta * prior_be);
-            prior_be = be;
-            s_be[t] = be;
-        }
-        __syncthreads();
-        if (h >= h_out0) {
-            if (t < K.nbands) {
-                double a = 0.0;
-                for (int k = 0; k < K.nbands; k++) a += spread[t * K.nbands + k] * s_be[k];
-                s_amt[t] = a;
-            }
-            __syncthreads();
+        for (int k = t; k < K.bins; k += AF_THREADS) {
+            const double rv = rel_var[k];
+            const int band = bin2band[k];
+            float2 X[2];
 #pragma unroll
-            for (int k = 0; k < nb_own; k++) {
-                const int i = bidx[k]; if (i >= K.bins) continue;
-                const double amt = s_amt[bin2band[i]];
-                const double abs_var = fmax(mvq * rv[k], 1.0), min_abs_var = K.gain_scale * abs_var;
-                double g = gain[k];
-                if (amt > abs_var) g = 1.0;
-                else if (amt > min_abs_var) g = af_limit_gain(g, sqrt(abs_var / amt));
+            for (int u = 0; u < 2; u++) {
+                X[u] = make_float2(0.f, 0.f);
+                const int64_t h = h0 + u;
+                if (u == 1 && !has1) continue;
+                const float2 sp = spectra[h * (int64_t)K.bins + k];
+                double g = gain[h * (int64_t)K.bins + k];
+                const double am = amt[h * (int64_t)K.nbands + band];
+                const double abs_var = fmax(mv_post[h] * rv, 1.0), min_abs_var = K.gain_scale * abs_var;
+                if (am > abs_var) g = 1.0;
+                else if (am > min_abs_var) g = af_limit_gain(g, sqrt(abs_var / am));
                 else g = af_limit_gain(g, K.max_gain);
                 const float ng = (float)g;
-                float2 v = make_float2(__fmul_rn(sp[k].x, ng), __fmul_rn(sp[k].y, ng));
-                if (i == 0 || i == K.FL2) v.y = 0.f;
-                sb[__brev((unsigned)i) >> (32 - logn)] = v;
-                if (i > 0 && i < K.FL2) sb[__brev((unsigned)(K.FL - i)) >> (32 - logn)] = make_float2(v.x, -v.y);
+                X[u] = make_float2(__fmul_rn(sp.x, ng), __fmul_rn(sp.y, ng));
+                if (k == 0 || k == K.FL2) X[u].y = 0.f;
             }
-            __syncthreads();
-            af_fft(sb, tw, K.FL, true);
-            for (int m = t; m < K.W; m += AF_THREADS) frames[h * (int64_t)K.W + m] = sb[m].x;
+            // Z = Xa + i*Xb on the lower half, conj(Xa) + i*conj(Xb) mirrored: Re(ifft) = frame a, Im(ifft) = frame b
+            bufA[k] = make_float2(X[0].x - X[1].y, X[0].y + X[1].x);
+            if (k > 0 && k < K.FL2) bufA[N - k] = make_float2(X[0].x + X[1].y, X[1].x - X[0].y);
         }
         __syncthreads();
+        const float2 *z = af_fft<true>(bufA, bufB, tw, N);
+        for (int m = t; m < K.W; m += AF_THREADS) {
+            const float2 v = z[m];
+            frames[h0 * (int64_t)K.W + m] = v.x;
+            if (has1) frames[(h0 + 1) * (int64_t)K.W + m] = v.y;
+        }
     }
 }
 
@@ -270,7 +391,7 @@ Sig jt_afftdn(jt_ctx *c, const Sig &in, const AfftdnParams &P)
     K.A = (int)(sample_rate / 80); K.W = 3 * K.A;
     K.FL = 1; while (K.FL <= K.W) K.FL <<= 1;
     K.FL2 = K.FL / 2; K.bins = K.FL2 + 1;
-    if (K.FL < 512 || K.bins > AF_MAXOWN * AF_THREADS) JT_THROW(JT_ERR_UNSUPPORTED, "afftdn at %d Hz (transform length %d)", in.rate, K.FL);
+    if (K.FL < 512 || K.bins > AF_MAXOWN * AF_THREADS || K.FL > 8192) JT_THROW(JT_ERR_UNSUPPORTED, "afftdn at %d Hz (transform length %d)", in.rate, K.FL);
     K.ratio = P.ad; K.floor_offset = P.fo;
     std::vector<double> window(K.W); double sum = 0;
     { const double wscale = sqrt(8.0 / (9.0 * K.FL)); for (int i = 0; i < K.W; i++) { double d = sin(i * M_PI / K.W); d *= wscale * d; window[i] = d; sum += d * d; } }
@@ -324,8 +445,8 @@ Sig jt_afftdn(jt_ctx *c, const Sig &in, const AfftdnParams &P)
           rel_var[m] = exp((d5 * d3 + band_noise * d4) * AF_C);
       } }
     K.max_gain = exp(P.nr * (0.5 * AF_C)); K.gain_scale = 1.0 / (K.max_gain * K.max_gain);
-    std::vector<float2> tw(K.FL / 2);
-    for (int k = 0; k < K.FL / 2; k++) { const double a = -2.0 * M_PI * k / K.FL; tw[k] = make_float2((float)cos(a), (float)sin(a)); }
+    std::vector<float2> tw(K.FL);                   // full circle: the radix-4 passes use w, w^2, w^3
+    for (int k = 0; k < K.FL; k++) { const double a = -2.0 * M_PI * k / K.FL; tw[k] = make_float2((float)cos(a), (float)sin(a)); }
 
     const int64_t n_hops = (in.n + K.A - 1) / K.A;
     auto up = [&](const void *h, size_t bytes) { void *d = jt_dalloc_bytes(c, bytes); JT_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, c->stream)); return d; };
@@ -338,16 +459,34 @@ Sig jt_afftdn(jt_ctx *c, const Sig &in, const AfftdnParams &P)
     double *d_spread = (double *)up(spread.data(), sizeof(double) * nb * nb);
     JT_CUDA(cudaStreamSynchronize(c->stream));          // host vectors above are locals
     float2 *d_spec = jt_dalloc<float2>(c, (size_t)n_hops * K.bins);
+    double *d_gain = jt_dalloc<double>(c, (size_t)n_hops * K.bins), *d_clean = jt_dalloc<double>(c, (size_t)n_hops * K.bins);
+    double *d_raw = jt_dalloc<double>(c, (size_t)n_hops * nb), *d_amt = jt_dalloc<double>(c, (size_t)n_hops * nb);
     float *d_frames = jt_dalloc<float>(c, (size_t)n_hops * K.W);
     double *d_cand = jt_dalloc<double>(c, (size_t)n_hops * 2), *d_pre = jt_dalloc<double>(c, n_hops), *d_post = jt_dalloc<double>(c, n_hops);
-    const size_t smem1 = sizeof(float2) * K.FL, smem3 = sizeof(float2) * K.FL + sizeof(double) * (K.bins + 1);
-    JT_CUDA(cudaFuncSetAttribute(k_afftdn_core, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
-    const int chunk = 384, warm = 128;
+    const size_t smem_fft = sizeof(float2) * 3 * (size_t)K.FL;
+    JT_CUDA(cudaFuncSetAttribute(k_afftdn_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fft));
+    JT_CUDA(cudaFuncSetAttribute(k_afftdn_synth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fft));
+    const int warm = 128;                             // 0.39^128, 0.78^128: both recursions have forgotten their start
+    const int chunk_gain = 768, chunk_band = 256;
+    const size_t smem_band = sizeof(double) * ((size_t)(chunk_band + warm) * nb + (size_t)nb * nb);
+    JT_CUDA(cudaFuncSetAttribute(k_afftdn_bandrec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_band));
+    const int64_t n_pairs = (n_hops + 1) / 2;
+    const int fft_per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / (smem_fft + 1024)));
+    const int grid_fft = (int)std::min<int64_t>(n_pairs, (int64_t)c->num_sms * fft_per_sm * 4);
     {
-        JtLaunch L(c, "afftdn", 4);
-        k_afftdn_fwd<<<jt_grid_for(n_hops, 1, c->num_sms, 16), AF_THREADS, smem1, c->stream>>>((const float *)in.d, in.n, n_hops, K, d_window, d_tw, d_spec, P.tn, d_cand);
-        k_afftdn_floor<<<1, 1024, 0, c->stream>>>(d_cand, n_hops, P.nf, K.floor_, P.tn, d_pre, d_post);
-        k_afftdn_core<<<(int)((n_hops + chunk - 1) / chunk), AF_THREADS, smem3, c->stream>>>(d_spec, n_hops, chunk, warm, K, d_rel, d_blo, d_b2b, d_alpha, d_beta, d_spread, d_pre, d_post, d_tw, d_frames);
+        { JtLaunch L(c, "afftdn:fwd");
+          k_afftdn_fwd<<<grid_fft, AF_THREADS, smem_fft, c->stream>>>((const float *)in.d, in.n, n_hops, K, d_window, d_tw, d_spec, P.tn, d_cand); }
+        { JtLaunch L(c, "afftdn:floor");
+          k_afftdn_floor<<<1, 1024, 0, c->stream>>>(d_cand, n_hops, P.nf, K.floor_, P.tn, d_pre, d_post); }
+        { JtLaunch L(c, "afftdn:gain");
+          dim3 g((K.bins + AF_GAIN_THREADS - 1) / AF_GAIN_THREADS, (unsigned)((n_hops + chunk_gain - 1) / chunk_gain));
+          k_afftdn_gain<<<g, AF_GAIN_THREADS, 0, c->stream>>>(d_spec, n_hops, chunk_gain, warm, K, d_rel, d_pre, d_gain, d_clean); }
+        { JtLaunch L(c, "afftdn:bands", 2);
+          k_afftdn_bandsum<<<jt_grid_for(n_hops * 32, 256, c->num_sms, 16), 256, 0, c->stream>>>(d_clean, n_hops, K, d_blo, d_raw);
+          k_afftdn_bandrec<<<(int)((n_hops + chunk_band - 1) / chunk_band), 256, smem_band, c->stream>>>(d_raw, n_hops, chunk_band, warm, K, d_alpha, d_beta, d_spread, d_amt); }
+        { JtLaunch L(c, "afftdn:synth");
+          k_afftdn_synth<<<grid_fft, AF_THREADS, smem_fft, c->stream>>>(d_spec, d_gain, d_amt, n_hops, K, d_rel, d_b2b, d_post, d_tw, d_frames); }
+        JtLaunch L(c, "afftdn:ola");
         k_afftdn_ola<<<jt_grid_for(in.n, 256, c->num_sms, 16), 256, 0, c->stream>>>(d_frames, d_window, in.n, n_hops, K.A, K.W, (float *)o.d);
     }
     return o;

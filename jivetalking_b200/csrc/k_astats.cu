@@ -341,7 +341,7 @@ static void astats_t(jt_ctx *c, const Sig &in, int64_t n, AstatsResult &out)
     unsigned long long *d_hist = jt_dalloc<unsigned long long>(c, AS_HIST + 8);
     unsigned long long *d_counts = d_hist + AS_HIST;     // 4 counts + noise-floor count
     JT_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * (AS_HIST + 8), c->stream));
-    { JtLaunch L(c, "astats"); k_astats_a<T><<<gridA, 256, 0, c->stream>>>(x, n, d_parts, d_hist); }
+    { JtLaunch L(c, "astats:sums_hist"); k_astats_a<T><<<gridA, 256, 0, c->stream>>>(x, n, d_parts, d_hist); }
     std::vector<AsPartA> parts(gridA);
     JT_CUDA(cudaMemcpyAsync(parts.data(), d_parts, sizeof(AsPartA) * gridA, cudaMemcpyDeviceToHost, c->stream));
     JT_CUDA(cudaStreamSynchronize(c->stream));
@@ -354,7 +354,7 @@ static void astats_t(jt_ctx *c, const Sig &in, int64_t n, AstatsResult &out)
         r.zero_runs += b.zero_runs; r.mask |= b.mask;
     }
     // B: extrema counts
-    { JtLaunch L(c, "astats"); k_astats_b<T><<<gridA, 256, 0, c->stream>>>(x, n, r.mn, r.mx, d_counts); }
+    { JtLaunch L(c, "astats:extrema_runs"); k_astats_b<T><<<gridA, 256, 0, c->stream>>>(x, n, r.mn, r.mx, d_counts); }
     // C: exponential mean square min/max
     double *d_mm = jt_dalloc<double>(c, 2);
     const int BS = AS_BS; const int64_t nb = (n + BS - 1) / BS;
@@ -362,7 +362,7 @@ static void astats_t(jt_ctx *c, const Sig &in, int64_t n, AstatsResult &out)
     JT_CUDA(cudaMemcpyAsync(d_mm, h_mm, sizeof(h_mm), cudaMemcpyHostToDevice, c->stream));
     if (n > tc) {
         double *d_fin = jt_dalloc<double>(c, nb), *d_carry = jt_dalloc<double>(c, nb);
-        JtLaunch L(c, "astats", 3);
+        JtLaunch L(c, "astats:rms_scan", 3);
         const size_t smemC = 2 * LaneStage<T, AsRow<T>::R>::WARP_BYTES;
         JT_CUDA(cudaFuncSetAttribute(k_astats_c1<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC));
         JT_CUDA(cudaFuncSetAttribute(k_astats_c2<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC));
@@ -380,7 +380,7 @@ static void astats_t(jt_ctx *c, const Sig &in, int64_t n, AstatsResult &out)
         const size_t smemD = sizeof(float) * (2 * (size_t)tc + 1);
         if (smemD > 200 * 1024) JT_THROW(JT_ERR_UNSUPPORTED, "astats at %d Hz (50 ms window of %d samples)", in.rate, tc);
         JT_CUDA(cudaFuncSetAttribute(k_astats_nf<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemD));
-        JtLaunch L(c, "astats", 2);
+        JtLaunch L(c, "astats:noise_floor", 2);
         k_astats_nf<T><<<jt_grid_for(nbt, 1, c->num_sms, 32), AS_NF_THREADS, smemD, c->stream>>>(x, n, tc, d_bmin, d_bcnt);
         k_astats_nf_reduce<<<1, 1024, 0, c->stream>>>(d_bmin, d_bcnt, nbt, d_nf, d_counts + 4);
     }

@@ -16,12 +16,15 @@
 #define FAKE_INFINITY (65536.0 * 65536.0)
 
 // ---- switching envelope follower ----------------------------------------------------------
-#define ENV_R 32            // 256-byte rows: ~35 KB of staging per warp, so 6 warps (192 lanes) fit one SM
+#define ENV_R 128           // input rows of 1 KB: two in flight per lane cover the bulk-copy latency of a 28-cycle/sample walk
+#define ENV_RO 32           // output rows of 256 B
 #define ENV_THREADS 32
+typedef LaneStage<double, ENV_R> EnvIn;
+typedef LaneStore<double, ENV_RO> EnvOut;
 // env' = env + (d - env) * (d > env ? attack : release), rounded like the scalar C (no contraction).
-// Both branches are evaluated and the sign of (d - env) selects, so the carried chain is
+// Both branches are evaluated and the comparison selects, so the carried chain is
 // sub -> mul -> add -> select (~28 cycles at 8.2 cycles per dependent f64 op, profiles/ubench_r1.txt)
-// instead of sub -> compare -> select -> mul -> add.
+// instead of compare -> select -> sub -> mul -> add.
 __device__ __forceinline__ double env_step(double e, double d, double attack_coeff, double release_coeff)
 {
     const double t = __dsub_rn(d, e);
@@ -35,16 +38,16 @@ k_envelope(const double *__restrict__ x, double *__restrict__ env, int64_t n, in
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int warp = threadIdx.x >> 5;
-    unsigned char *wsm = smem + (size_t)warp * (LaneStage<double, ENV_R>::WARP_BYTES + LaneStore<double, ENV_R>::WARP_BYTES);
+    unsigned char *wsm = smem + (size_t)warp * (EnvIn::WARP_BYTES + EnvOut::WARP_BYTES);
     const int64_t lane = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t s0 = min(lane * seg, n), s1 = min(s0 + (int64_t)seg, n);
     const int64_t begin = max((int64_t)0, s0 - warm);
-    LaneStage<double, ENV_R> in; LaneStore<double, ENV_R> out;
+    EnvIn in; EnvOut out;
     in.init(wsm, x + begin, lane * seg < n ? s1 - begin : 0);
-    out.init(wsm + LaneStage<double, ENV_R>::WARP_BYTES, env + s0);
+    out.init(wsm + EnvIn::WARP_BYTES, env + s0);
     // warm and seg are multiples of ENV_R, so a tile is either all warm-up or all output: the inner
-    // loops are branch-free and free of asm barriers, which lets ptxas hoist the shared-memory loads
-    // and overlap everything except the 3-op carried chain e -> (d-e) -> *coeff -> +e
+    // loops are branch-free, which lets ptxas hoist the shared-memory loads and overlap everything
+    // except the carried chain
     double e = 0.0;
     in.prefetch();
     for (int tile = 0; tile < in.ntiles; tile++) {
@@ -53,26 +56,29 @@ k_envelope(const double *__restrict__ x, double *__restrict__ env, int64_t n, in
         const int nv = in.valid(tile);
         const int64_t i0 = begin + (int64_t)tile * ENV_R;
         const bool emit = i0 >= s0;
-        double *orow = out.row();
-        int k = 0;
-        // register blocks of 8: all loads and detector values first, then only the carried chain
-        for (; k + 8 <= nv; k += 8) {
-            double d[8];
+        for (int k0 = 0; k0 < nv; k0 += ENV_RO) {
+            const int nb = min(ENV_RO, nv - k0);
+            double *orow = out.row();
+            int k = 0;
+            // register blocks of 8: all loads and detector values first, then only the carried chain
+            for (; k + 8 <= nb; k += 8) {
+                double d[8];
 #pragma unroll
-            for (int j = 0; j < 8; j++) { const double v = row[k + j]; d[j] = rms ? v * v : fabs(v); }
+                for (int j = 0; j < 8; j++) { const double v = row[k0 + k + j]; d[j] = rms ? v * v : fabs(v); }
 #pragma unroll
-            for (int j = 0; j < 8; j++) { e = env_step(e, d[j], attack_coeff, release_coeff); d[j] = e; }
-            if (emit) {
+                for (int j = 0; j < 8; j++) { e = env_step(e, d[j], attack_coeff, release_coeff); d[j] = e; }
+                if (emit) {
 #pragma unroll
-                for (int j = 0; j < 8; j++) orow[k + j] = d[j];
+                    for (int j = 0; j < 8; j++) orow[k + j] = d[j];
+                }
             }
+            for (; k < nb; k++) {
+                const double v = row[k0 + k], dd = rms ? v * v : fabs(v);
+                e = env_step(e, dd, attack_coeff, release_coeff);
+                if (emit) orow[k] = e;
+            }
+            if (emit) out.commit(nb);
         }
-        for (; k < nv; k++) {
-            const double v = row[k], dd = rms ? v * v : fabs(v);
-            e = env_step(e, dd, attack_coeff, release_coeff);
-            if (emit) orow[k] = e;
-        }
-        if (emit) out.commit(nv);
         in.release();
     }
     out.finish();
@@ -86,14 +92,17 @@ static double *run_envelope(jt_ctx *c, const Sig &in, double attack_ms, double r
     int64_t warm = cmin >= 1.0 ? 1 : (int64_t)std::ceil(37.0 / -std::log1p(-cmin)) + 16;
     if (warm > (1 << 22)) warm = 1 << 22;
     warm = (warm + ENV_R - 1) / ENV_R * ENV_R;                 // tile-aligned (see the kernel)
-    // one wave: as many lanes as the GPU holds at once (6 single-warp CTAs per SM), never shorter than 4096 samples
-    const int64_t slots = (int64_t)c->num_sms * 6 * ENV_THREADS;
-    int64_t seg64 = std::max<int64_t>(4096, (in.n + slots - 1) / slots);
+    // Every lane re-reads `warm` samples before its segment (37 release time constants, ~89k samples at
+    // 200 ms / 48 kHz), so short segments multiply the HBM traffic while long ones leave the GPU to a handful
+    // of lanes.  84 KB of staging per warp lets 2 warps share an SM: the segment is sized so that all lanes
+    // run in one wave (20480 samples at one hour of audio: 5.3x re-read), never below 16384.
+    const int64_t slots = (int64_t)c->num_sms * 2 * ENV_THREADS;
+    int64_t seg64 = std::max<int64_t>(16384, (in.n + slots - 1) / slots);
     seg64 = std::min<int64_t>((seg64 + ENV_R - 1) / ENV_R * ENV_R, 1 << 20);
     const int seg = (int)seg64;
     const int64_t lanes = (in.n + seg - 1) / seg;
     JtLaunch L(c, "envelope_follower");
-    const size_t smem = (ENV_THREADS / 32) * (LaneStage<double, ENV_R>::WARP_BYTES + LaneStore<double, ENV_R>::WARP_BYTES);
+    const size_t smem = (ENV_THREADS / 32) * (EnvIn::WARP_BYTES + EnvOut::WARP_BYTES);
     JT_CUDA(cudaFuncSetAttribute(k_envelope, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_envelope<<<(int)((lanes + ENV_THREADS - 1) / ENV_THREADS), ENV_THREADS, smem, c->stream>>>((const double *)in.d, env, in.n, seg, (int)warm, ac, rc, rms);
     return env;

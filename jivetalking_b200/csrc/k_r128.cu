@@ -143,7 +143,7 @@ static void run_ticks(jt_ctx *c, const Sig &in, int tick, int64_t n_ticks_total,
     const int G = 2, WU = 2;
     const int64_t lanes = (n_ticks_total + G - 1) / G;
     const int grid = (int)((lanes + 63) / 64);
-    JtLaunch L(c, "r128_kweight_ticks");
+    JtLaunch L(c, in.rate >= 176400 ? "r128_kweight_ticks:192k" : "r128_kweight_ticks");
 #define R128_LAUNCH(T) do { \
         const size_t smem = 2 * LaneStage<T, 512 / (int)sizeof(T)>::WARP_BYTES; \
         JT_CUDA(cudaFuncSetAttribute(k_r128_ticks<T, STRUCT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \

@@ -504,7 +504,9 @@ Sig jt_swr_resample(jt_ctx *c, const Sig &in, const SwrPlan &p, int work_fmt, bo
     Sig o; o.fmt = fuse_s16 ? JT_FMT_S16 : work_fmt; o.rate = p.out_rate; o.n = n_out;
     o.d = jt_dalloc_bytes(c, (size_t)std::max<int64_t>(n_out, 1) * jt_fmt_bytes(o.fmt));
     if (n_out <= 0) return o;
-    JtLaunch Lc(c, "swr_resample");
+    const char *kind = work_fmt == JT_FMT_DBL ? (small_path(p) ? "swr_resample:small_f64" : qlane_path_ok(p) ? "swr_resample:qlane_f64" : "swr_resample:generic")
+                                              : (slot_path_ok(p) ? (p.phase_count > p.div ? "swr_resample:slot_f32_up" : "swr_resample:slot_f32_down") : "swr_resample:generic");
+    JtLaunch Lc(c, kind);
     if (work_fmt == JT_FMT_DBL) {
         if (small_path(p)) {
             if (in.fmt == JT_FMT_S16) launch_small<int16_t, SWR_MODE_STORE>(c, in, p, n_out, (double *)o.d, nullptr, 1, 0);
@@ -546,7 +548,7 @@ void jt_swr_tick_absmax(jt_ctx *c, const Sig &in, const SwrPlan &p, int tick, in
     Sig v = in; v.n = std::min(in.n, fed);
     const int64_t n_out = p.out_count(v.n);
     if (n_out <= 0) return;
-    JtLaunch Lc(c, "truepeak_oversample");
+    JtLaunch Lc(c, small_path(p) ? "truepeak_oversample:small_f64" : qlane_path_ok(p) ? "truepeak_oversample:qlane_f64" : "truepeak_oversample:generic");
     if (small_path(p)) {
         if (v.fmt == JT_FMT_S16) launch_small<int16_t, SWR_MODE_TICKMAX>(c, v, p, n_out, nullptr, d_tick_tp, tick, n_ticks);
         else if (v.fmt == JT_FMT_FLT) launch_small<float, SWR_MODE_TICKMAX>(c, v, p, n_out, nullptr, d_tick_tp, tick, n_ticks);

@@ -126,6 +126,8 @@ def lib():
     L.jt_default_pass2_spec.argtypes = [C.c_char_p, C.c_size_t]
     L.jt_pass1_spec.argtypes = [C.c_char_p, C.c_size_t]
     L.jt_loudnorm_stats_json.argtypes = [C.POINTER(LoudnormStats), C.c_char_p, C.c_size_t]
+    L.jt_cuda_stream.restype = _P
+    L.jt_cuda_stream.argtypes = [_P]
     L.jt_launch_count.restype = _I64
     L.jt_launch_count.argtypes = [_P]
     L.jt_reset_launch_count.argtypes = [_P]
@@ -261,6 +263,10 @@ class Context:
                 out_cap, C.byref(res))
         self._check(rc)
         return res
+
+    def cuda_stream(self):
+        """cudaStream_t the context launches on (for event timing / torch.cuda.ExternalStream)."""
+        return lib().jt_cuda_stream(self._h)
 
     def launch_count(self):
         return lib().jt_launch_count(self._h)
