@@ -165,7 +165,7 @@ k_dc_interp(const double *__restrict__ x, double *__restrict__ y, int64_t n, int
     // scratch layout: Lg[nmax][order], Dg[nmax], vec[nmax], outv[nmax], idx (as int)[nmax]
     const size_t nmax = (size_t)K.W;
     double *Lg = S, *Dg = Lg + nmax * order, *vec = Dg + nmax, *outv = vec + nmax;
-    int *idx = (int *)(outv + nmax);
+    int *idx = (int *)(outv + nmax), *am = idx + 2 * ((nmax + 1) / 2);
 #define RING(j, i) ring[(size_t)((j) % bw) * bw + ((i) % bw)]
 
     for (;;) {
@@ -227,7 +227,16 @@ k_dc_interp(const double *__restrict__ x, double *__restrict__ y, int64_t n, int
         for (int k = 0; k < nclk; k++) {
             const double Dk = RING(k, k);
             if (Dk == 0.) { ok = false; break; }
-            const int amax = min(order, nclk - 1 - k);
+            // rows coupled to click k: later clicks at most `order` samples away.  Everything below them in
+            // column k is an exact zero of the factor (two clicks further apart never couple, fill-in stays
+            // inside this profile), and x - 0*y == x bit for bit, so those updates are skipped.
+            int amax;
+            {
+                const int ik = idx[k], j0 = k + 1 + lane, j1 = j0 + 32;
+                const bool c0 = j0 < nclk && idx[j0] - ik <= order, c1 = j1 < nclk && j1 - k <= order && idx[j1] - ik <= order;
+                amax = __popc(__ballot_sync(0xffffffffu, c0)) + __popc(__ballot_sync(0xffffffffu, c1));
+            }
+            if (lane == 0) am[k] = amax;
             const double yk = vec[k];
             // column k: L(j,k) = A'(j,k) / D_k ; forward substitution v_j -= L(j,k) * y_k
             for (int a = lane + 1; a <= amax; a += 32) {
@@ -251,8 +260,9 @@ k_dc_interp(const double *__restrict__ x, double *__restrict__ y, int64_t n, int
         }
         if (!ok) continue;                  // factorisation hit a zero pivot: af_adeclick.c leaves the window as is
         // back substitution: out_i = y_i / D_i - sum_{j>i} L(j,i) * out_j, j ascending
+        __syncwarp();
         for (int i = nclk - 1; i >= 0; i--) {
-            const int amax = min(order, nclk - 1 - i);
+            const int amax = am[i];
             double prod0 = 0.0, prod1 = 0.0;
             if (lane < amax) prod0 = jdmul(Lg[(size_t)i * order + lane], oring[(i + 1 + lane) % bw]);
             if (lane + 32 < amax) prod1 = jdmul(Lg[(size_t)i * order + lane + 32], oring[(i + 33 + lane) % bw]);
@@ -308,7 +318,7 @@ Sig jt_adeclick(jt_ctx *c, const Sig &in, double w_ms, double overlap_pct, doubl
     int gridE = (int)std::min<int64_t>((nw + DC_WARPS - 1) / DC_WARPS, (int64_t)c->num_sms * per_sm);
     if (gridE < 1) gridE = 1;
     const size_t nmax = (size_t)K.W;
-    const size_t scratch_per_warp = nmax * K.order + 3 * nmax + (nmax + 1) / 2 + 8;
+    const size_t scratch_per_warp = nmax * K.order + 3 * nmax + 2 * ((nmax + 1) / 2) + 8;
     double *scratch = jt_dalloc<double>(c, scratch_per_warp * (size_t)gridE * DC_WARPS);
     { JtLaunch L(c, "adeclick:autocorr");
     k_dc_autocorr<<<jt_grid_for(nw, 1, c->num_sms, 64), 64, smemA, c->stream>>>((const double *)in.d, in.n, nw, K, d_r); }

@@ -7,26 +7,51 @@
 // samples of i).  The hop's window (H + 2(K+S) floats) is staged in shared memory; every thread
 // keeps its lags' running patch distances in registers and updates them with the same unfused
 // float operations, in the same order, as the scalar C (full SSD at the hop's first sample,
-// then add-new/subtract-old), so distances are bit-identical to a sequential run.  Weighted
-// sums are reduced per warp with shuffles (skipped when no lane of the warp is inside the
-// smoothing cut-off) and combined across warps once per 32 samples.
+// then add-new/subtract-old), so distances are bit-identical to a sequential run.
+// The kernel is instruction-issue bound (ncu: 91 % issue-active), so the steady state is written
+// for instruction count: eight samples per loop trip, every load a base register + immediate
+// (with win[] indices: old/new patch edge of i = S+t-1 / S+t+2K, of lag v = t+v-1 / t+v+2K, of lag
+// v+S+1 = t+v+S / t+v+S+2K+1), one warp vote per eight samples for the rare samples where any lag
+// falls inside the smoothing cut-off.  Only then are weights computed and reduced per warp with
+// shuffles; partial sums of the warps are combined once per 32 samples (double-buffered: one
+// barrier per 32 samples).
 #include "jt_internal.h"
 #include "jt_device.cuh"
 
 #define NLM_CHUNK 32
+#define NLM_U 8
 #define NLM_MAXWARPS 16
 
-__global__ void __launch_bounds__(512)
-k_anlmdn(const float *__restrict__ x, float *__restrict__ y, int64_t n, int K, int S, float sw, float smooth,
-         float lut_scale, float inv_lut_scale, int64_t n_hops)
+struct NlmK { float sw, smooth, lut_scale, inv_lut_scale; };
+
+// weights of one sample for this thread's two lags; returns true when either lag is inside the cut-off
+__device__ __forceinline__ bool nlm_weights(float c1, float c2, float x1, float x2, const NlmK &k, float &pw, float &qw)
 {
-    extern __shared__ float win[];                       // N floats
-    __shared__ float part[NLM_CHUNK][NLM_MAXWARPS][2];
+    pw = 0.f; qw = 0.f; bool in = false;
+    const float w1 = __fmul_rn(c1, k.sw), w2 = __fmul_rn(c2, k.sw);
+    if (!(w1 >= k.smooth)) {
+        const unsigned idx = (unsigned)__fmul_rn(w1, k.lut_scale);
+        const float w = __expf(-(float)idx * k.inv_lut_scale);
+        pw = __fmul_rn(w, x1); qw = w; in = true;
+    }
+    if (!(w2 >= k.smooth)) {
+        const unsigned idx = (unsigned)__fmul_rn(w2, k.lut_scale);
+        const float w = __expf(-(float)idx * k.inv_lut_scale);
+        pw += __fmul_rn(w, x2); qw += w; in = true;
+    }
+    return in;
+}
+
+__global__ void __launch_bounds__(512)
+k_anlmdn(const float *__restrict__ x, float *__restrict__ y, int64_t n, int K, int S, NlmK P, int64_t n_hops)
+{
+    extern __shared__ float win[];                       // N floats (+ slack read by clamped idle lanes)
+    __shared__ float part[2][NLM_CHUNK][NLM_MAXWARPS][2];
     const int H = 2 * K + 1, N = H + 2 * (K + S), offset = N - H;
-    const int v = threadIdx.x, lane = v & 31, warp = v >> 5, nwarp = blockDim.x >> 5;
-    const bool active = v < S;
-    const float *f = win + K;
-    const int dj1 = -S + v, dj2 = 1 + v;                 // lag v and lag v+S of the scalar loop
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const bool live = (int)threadIdx.x < S;
+    const int v = live ? threadIdx.x : S - 1;            // idle lanes of the last warp shadow lag S-1 and never contribute
+    const int K2 = 2 * K;
     for (int64_t h = blockIdx.x; h < n_hops; h += gridDim.x) {
         const int64_t pos = h * (int64_t)H;
         const int nb = (int)min((int64_t)H, n - pos);
@@ -36,59 +61,99 @@ k_anlmdn(const float *__restrict__ x, float *__restrict__ y, int64_t n, int K, i
             win[j] = (s >= 0 && s < pos + nb) ? x[s] : 0.f;
         }
         __syncthreads();
+        // full patch distances at the hop's first sample (t = 0): sum over k = -K..K in order
         float c1 = 0.f, c2 = 0.f;
-        if (active) {
-            const float *fi = f + S, *f1 = fi + dj1, *f2 = fi + dj2;
-            float d1 = 0.f, d2 = 0.f;
-            for (int k = -K; k <= K; k++) {
-                const float a = fi[k];
-                const float t1 = __fsub_rn(a, f1[k]), t2 = __fsub_rn(a, f2[k]);
-                d1 = __fadd_rn(d1, __fmul_rn(t1, t1)); d2 = __fadd_rn(d2, __fmul_rn(t2, t2));
+        {
+            const float *a = win + S, *p1 = win + v, *p2 = win + v + S + 1;
+            int k = 0;
+            for (; k + 8 <= H; k += 8) {
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const float av = a[k + u];
+                    const float t1 = __fsub_rn(av, p1[k + u]), t2 = __fsub_rn(av, p2[k + u]);
+                    c1 = __fadd_rn(c1, __fmul_rn(t1, t1)); c2 = __fadd_rn(c2, __fmul_rn(t2, t2));
+                }
             }
-            c1 = d1; c2 = d2;
+            for (; k < H; k++) {
+                const float av = a[k];
+                const float t1 = __fsub_rn(av, p1[k]), t2 = __fsub_rn(av, p2[k]);
+                c1 = __fadd_rn(c1, __fmul_rn(t1, t1)); c2 = __fadd_rn(c2, __fmul_rn(t2, t2));
+            }
         }
-        for (int c0 = 0; c0 < H; c0 += NLM_CHUNK) {
-            const int cn = min(NLM_CHUNK, H - c0);
-            const float *fi = f + S + c0;
-            for (int ci = 0; ci < cn; ci++, fi++) {
-                float pw = 0.f, qw = 0.f; bool in = false;
-                if (active) {
-                    const float *f1 = fi + dj1, *f2 = fi + dj2;
-                    if (c0 + ci != 0) {
-                        const float ao = fi[-K - 1], an = fi[K];
-                        const float a1 = __fsub_rn(ao, f1[-K - 1]), b1 = __fsub_rn(an, f1[K]);
-                        const float a2 = __fsub_rn(ao, f2[-K - 1]), b2 = __fsub_rn(an, f2[K]);
+        // sample t = 0 is a chunk of its own, then chunks of 32 samples starting at t = 1
+        int pb = 0;
+        for (int c0 = 0; c0 < H; c0 = (c0 == 0) ? 1 : c0 + NLM_CHUNK, pb ^= 1) {
+            const int cn = c0 == 0 ? 1 : min(NLM_CHUNK, H - c0);
+            part[pb][lane][warp][0] = 0.f; part[pb][lane][warp][1] = 0.f;
+            __syncwarp();
+            if (c0 == 0) {
+                if (c1 < 0.f) c1 = 0.f;
+                if (c2 < 0.f) c2 = 0.f;
+                float pw, qw;
+                const bool in = nlm_weights(c1, c2, win[K + v], win[K + v + S + 1], P, pw, qw) && live;
+                if (__any_sync(0xffffffffu, in)) {
+                    if (!in) { pw = 0.f; qw = 0.f; }
+                    for (int o = 16; o; o >>= 1) { pw += __shfl_xor_sync(0xffffffffu, pw, o); qw += __shfl_xor_sync(0xffffffffu, qw, o); }
+                    if (lane == 0) { part[pb][0][warp][0] = pw; part[pb][0][warp][1] = qw; }
+                }
+            } else {
+                const float *q0 = win + c0 + v - 1, *q1 = q0 + K2 + 1, *q2 = q0 + S + 1, *q3 = q2 + K2 + 1;
+                const float *u0 = win + S + c0 - 1, *u1 = u0 + K2 + 1;
+                const float *x1 = win + K + c0 + v, *x2 = x1 + S + 1;
+                int ci = 0;
+                for (; ci + NLM_U <= cn; ci += NLM_U) {
+                    float d1[NLM_U], d2[NLM_U];
+                    bool any = false;
+#pragma unroll
+                    for (int u = 0; u < NLM_U; u++) {
+                        const float ao = u0[ci + u], an = u1[ci + u];
+                        const float a1 = __fsub_rn(ao, q0[ci + u]), b1 = __fsub_rn(an, q1[ci + u]);
+                        const float a2 = __fsub_rn(ao, q2[ci + u]), b2 = __fsub_rn(an, q3[ci + u]);
                         c1 = __fadd_rn(c1, __fadd_rn(-__fmul_rn(a1, a1), __fmul_rn(b1, b1)));
                         c2 = __fadd_rn(c2, __fadd_rn(-__fmul_rn(a2, a2), __fmul_rn(b2, b2)));
+                        if (c1 < 0.f) c1 = 0.f;
+                        if (c2 < 0.f) c2 = 0.f;
+                        d1[u] = c1; d2[u] = c2;
+                        any |= !(__fmul_rn(c1, P.sw) >= P.smooth) || !(__fmul_rn(c2, P.sw) >= P.smooth);
                     }
-                    if (c1 < 0.f) c1 = 0.f;
-                    if (c2 < 0.f) c2 = 0.f;
-                    const float w1 = __fmul_rn(c1, sw), w2 = __fmul_rn(c2, sw);
-                    if (!(w1 >= smooth)) {
-                        const unsigned idx = (unsigned)__fmul_rn(w1, lut_scale);
-                        const float w = __expf(-(float)idx * inv_lut_scale);
-                        pw = __fmul_rn(w, f1[0]); qw = w; in = true;
-                    }
-                    if (!(w2 >= smooth)) {
-                        const unsigned idx = (unsigned)__fmul_rn(w2, lut_scale);
-                        const float w = __expf(-(float)idx * inv_lut_scale);
-                        pw += __fmul_rn(w, f2[0]); qw += w; in = true;
+                    if (__any_sync(0xffffffffu, any && live)) {
+#pragma unroll
+                        for (int u = 0; u < NLM_U; u++) {
+                            float pw, qw;
+                            const bool in = nlm_weights(d1[u], d2[u], x1[ci + u], x2[ci + u], P, pw, qw) && live;
+                            if (!__any_sync(0xffffffffu, in)) continue;
+                            if (!in) { pw = 0.f; qw = 0.f; }
+                            for (int o = 16; o; o >>= 1) { pw += __shfl_xor_sync(0xffffffffu, pw, o); qw += __shfl_xor_sync(0xffffffffu, qw, o); }
+                            if (lane == 0) { part[pb][ci + u][warp][0] = pw; part[pb][ci + u][warp][1] = qw; }
+                        }
                     }
                 }
-                if (__any_sync(0xffffffffu, in)) {
+                for (; ci < cn; ci++) {
+                    const float ao = u0[ci], an = u1[ci];
+                    const float a1 = __fsub_rn(ao, q0[ci]), b1 = __fsub_rn(an, q1[ci]);
+                    const float a2 = __fsub_rn(ao, q2[ci]), b2 = __fsub_rn(an, q3[ci]);
+                    c1 = __fadd_rn(c1, __fadd_rn(-__fmul_rn(a1, a1), __fmul_rn(b1, b1)));
+                    c2 = __fadd_rn(c2, __fadd_rn(-__fmul_rn(a2, a2), __fmul_rn(b2, b2)));
+                    if (c1 < 0.f) c1 = 0.f;
+                    if (c2 < 0.f) c2 = 0.f;
+                    float pw, qw;
+                    const bool in = nlm_weights(c1, c2, x1[ci], x2[ci], P, pw, qw) && live;
+                    if (!__any_sync(0xffffffffu, in)) continue;
+                    if (!in) { pw = 0.f; qw = 0.f; }
                     for (int o = 16; o; o >>= 1) { pw += __shfl_xor_sync(0xffffffffu, pw, o); qw += __shfl_xor_sync(0xffffffffu, qw, o); }
-                } else { pw = 0.f; qw = 0.f; }
-                if (lane == 0) { part[ci][warp][0] = pw; part[ci][warp][1] = qw; }
+                    if (lane == 0) { part[pb][ci][warp][0] = pw; part[pb][ci][warp][1] = qw; }
+                }
             }
             __syncthreads();
-            if (threadIdx.x < cn) {
+            // the first cn threads combine the warps' partial sums of this chunk while the others move on:
+            // the next chunk writes the other half of part[], and is itself followed by a barrier
+            if ((int)threadIdx.x < cn) {
                 const int ci = threadIdx.x, t = c0 + ci;
-                float P = 0.f, Q = 0.f;
-                for (int w = 0; w < nwarp; w++) { P += part[ci][w][0]; Q += part[ci][w][1]; }
-                P = __fadd_rn(P, f[S + t]); Q = __fadd_rn(Q, 1.f);
-                if (t < nb) y[pos + t] = __fdiv_rn(P, Q);
+                float Ps = 0.f, Qs = 0.f;
+                for (int w = 0; w < nwarp; w++) { Ps += part[pb][ci][w][0]; Qs += part[pb][ci][w][1]; }
+                Ps = __fadd_rn(Ps, win[K + S + t]); Qs = __fadd_rn(Qs, 1.f);
+                if (t < nb) y[pos + t] = __fdiv_rn(Ps, Qs);
             }
-            __syncthreads();
         }
     }
 }
@@ -111,10 +176,11 @@ Sig jt_anlmdn(jt_ctx *c, const Sig &in, double strength, double patch_s, double 
     const float sw = (65536.f / (4 * K + 2)) / sqrtf(a);
     const float smooth = fminf(m, (float)(1 << 20) / lut_scale);
     const int64_t n_hops = (in.n + H - 1) / H;
-    const size_t smem = sizeof(float) * N;
+    const size_t smem = sizeof(float) * (N + 64);
     JT_CUDA(cudaFuncSetAttribute(k_anlmdn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
     const int grid = jt_grid_for(n_hops, 1, c->num_sms, 64);
     JtLaunch L(c, "anlmdn");
-    k_anlmdn<<<grid, threads, smem, c->stream>>>((const float *)in.d, (float *)o.d, in.n, K, S, sw, smooth, lut_scale, 1.f / lut_scale, n_hops);
+    NlmK P; P.sw = sw; P.smooth = smooth; P.lut_scale = lut_scale; P.inv_lut_scale = 1.f / lut_scale;
+    k_anlmdn<<<grid, threads, smem, c->stream>>>((const float *)in.d, (float *)o.d, in.n, K, S, P, n_hops);
     return o;
 }

