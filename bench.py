@@ -266,12 +266,14 @@ def main():
     e2e = total_samples / t_e2e
     peak, peak_src = measured_peaks()
     timings.sort(key=lambda t: -t[1])
+    gaps = [t for t in timings if t[0].startswith("gap:")]
+    timings = [t for t in timings if not t[0].startswith("gap:")]
     gpu_timings = [t for t in timings if not t[0].startswith("host:")]
     dom = gpu_timings[0] if gpu_timings else ("none", 0.0, 0)
     dom_ms_per_step = dom[1] / args.steps
     dom_bytes = KERNEL_BYTES.get(dom[0].split(":")[0], 8.0) * n
     achieved = dom_bytes / (dom_ms_per_step * 1e-3) / 1e9 if dom_ms_per_step > 0 else 0.0
-    kernel_ms = sum(t[1] for t in timings) / args.steps
+    kernel_ms = sum(t[1] for t in gpu_timings) / args.steps
     line = {
         "metric": "samples/s full 4-pass chain", "value": value, "unit": "samples/s", "realtime_x": value / RATE,
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps,
@@ -291,6 +293,8 @@ def main():
                      "note": "dominant kernel is FP32-ALU/latency bound, not HBM bound (DESIGN.md)"},
         "kernels_ms_per_step": {t[0]: round(t[1] / args.steps, 3) for t in timings},
         "kernel_ms_total_per_step": kernel_ms,
+        "device_idle_ms_per_step": {g[0][4:]: round(g[1] / args.steps, 3) for g in sorted(gaps, key=lambda g: -g[1])[:12]},
+        "device_idle_ms_total_per_step": sum(g[1] for g in gaps) / args.steps,
         "clocks": clocks.summary(),
         "result": {"final_lufs": res.final.input_i, "final_dbtp": res.final.input_tp, "final_lra": res.final.input_lra,
                    "n_out": int(res.n_out), "limiter_needed": int(res.limiter_needed), "pass4_type": int(res.pass4.normalization_type)},

@@ -6,8 +6,9 @@
 // DRAM latency, not by the recurrence.  LaneStage fixes that with the TMA engine: each lane
 // owns one row of a shared-memory tile and asks for the next R elements of its own range with a
 // single 1-D bulk copy (cp.async.bulk.shared::cluster.global -> SASS UBLKCP) that completes on
-// an mbarrier; tiles are double-buffered, so a row of R elements is in flight while the previous
-// one is being consumed.  A lane's range is given in "virtual" coordinates: elements outside
+// an mbarrier; tiles sit in a ring of NS buffers, NS - 1 rows in flight while one is being consumed.
+// A lane's bulk copy takes 2700 (256 B) to 4100 (1 KB) cycles to land (scripts/ubench/lanes.cu), so a
+// walk that spends c cycles per element needs (NS - 1) * R * c above that to stay compute-bound.  A lane's range is given in "virtual" coordinates: elements outside
 // [lo, hi) read as zero (stream start / zero tail), rows near those edges are filled with plain
 // loads by their own lane, and a source that is not 16-byte aligned is fetched from the aligned
 // address below it (the row has 16 bytes of slack) and exposed with the matching offset.
@@ -41,15 +42,16 @@ __device__ __forceinline__ void jt_tma_load_1d(void *dst_smem, const void *src_g
                  ::"r"(jt_smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(jt_smem_u32(bar)) : "memory");
 }
 
-template <class T, int R>
+template <class T, int R, int NS = 2>
 struct LaneStage {
     static_assert((R * sizeof(T)) % 16 == 0, "row must be a multiple of 16 bytes");
+    static_assert(NS >= 2 && NS <= 8, "2..8 stages");
     static constexpr int PAD = 16 / (int)sizeof(T);
     static constexpr int ROW = R + PAD;                                  // 16 bytes of slack per row
-    static constexpr size_t WARP_BYTES = 2 * 32 * (size_t)ROW * sizeof(T) + 32;
+    static constexpr size_t WARP_BYTES = NS * 32 * (size_t)ROW * sizeof(T) + 64;
 
-    T *buf;                 // [2][32][ROW]
-    uint64_t *bar;          // [2]
+    T *buf;                 // [NS][32][ROW]
+    uint64_t *bar;          // [NS]
     const T *src;           // address of virtual element 0 (may lie outside the array)
     int64_t count, lo, hi;  // virtual length; real data only for lo <= i < hi, zero elsewhere
     int shift;              // elements between the 16-byte boundary below src and src
@@ -59,13 +61,13 @@ struct LaneStage {
     __device__ __forceinline__ void init(unsigned char *smem, const T *virt0, int64_t lane_count, int64_t real_lo, int64_t real_hi)
     {
         buf = (T *)smem;
-        bar = (uint64_t *)(smem + 2 * 32 * (size_t)ROW * sizeof(T));
+        bar = (uint64_t *)(smem + NS * 32 * (size_t)ROW * sizeof(T));
         src = virt0; count = lane_count < 0 ? 0 : lane_count; lo = real_lo; hi = real_hi; issued = 0;
         shift = (int)((((uintptr_t)virt0) & 15) / sizeof(T));
         int64_t nt = (count + R - 1) / R;
         for (int o = 16; o; o >>= 1) { int64_t v = __shfl_xor_sync(0xffffffffu, nt, o); nt = v > nt ? v : nt; }
         ntiles = (int)nt;
-        if ((threadIdx.x & 31) == 0) { jt_mbar_init(&bar[0], 1); jt_mbar_init(&bar[1], 1); }
+        if ((threadIdx.x & 31) < NS) jt_mbar_init(&bar[threadIdx.x & 31], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
@@ -79,11 +81,11 @@ struct LaneStage {
         const int64_t rem = count - (int64_t)tile * R;
         return rem <= 0 ? 0 : (rem < R ? (int)rem : R);
     }
-    // issue the next tile (no-op past the end); the buffer it overwrites must have been released
+    // issue the next tile (no-op past the end); the buffer it overwrites (tile - NS) must have been released
     __device__ __forceinline__ void prefetch()
     {
         if (issued >= ntiles) return;
-        const int t = issued, b = t & 1, lane = threadIdx.x & 31;
+        const int t = issued, b = t % NS, lane = threadIdx.x & 31;
         const int n = valid(t);
         T *row = buf + ((size_t)b * 32 + lane) * ROW;
         const int64_t v0 = (int64_t)t * R;                               // first virtual element of the tile
@@ -97,11 +99,17 @@ struct LaneStage {
         else for (int i = 0; i < n; i++) { const int64_t v = v0 + i; row[shift + i] = (v >= lo && v < hi) ? src[v] : (T)0; }
         issued++;
     }
+    // fill the pipeline: NS - 1 tiles in flight; afterwards call prefetch() once per consumed tile, before wait()
+    __device__ __forceinline__ void prime()
+    {
+#pragma unroll
+        for (int i = 0; i < NS - 1; i++) prefetch();
+    }
     // wait for `tile`, return this lane's row (element k of the tile at [k])
     __device__ __forceinline__ const T *wait(int tile)
     {
-        const int b = tile & 1;
-        jt_mbar_wait(&bar[b], (unsigned)((tile >> 1) & 1));
+        const int b = tile % NS;
+        jt_mbar_wait(&bar[b], (unsigned)((tile / NS) & 1));
         __syncwarp();
         return buf + ((size_t)b * 32 + (threadIdx.x & 31)) * ROW + shift;
     }

@@ -70,12 +70,25 @@ JtHost::~JtHost() { if (slot >= 0) { c->slots[slot].ms += host_now_ms() - t0; c-
 
 void jt_flush_timing(jt_ctx *c)
 {
+    // pending[] is in stream order: besides each group's own duration, the device-idle time between one
+    // group's end and the next group's start is booked to "gap:<next group>" (host work, syncs, copies)
+    cudaEvent_t prev_end = nullptr;
+    std::vector<cudaEvent_t> done;
     for (auto &p : c->pending) {
         float ms = 0;
         cudaEventSynchronize(p.b);
         if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) c->slots[p.slot].ms += ms;
-        cudaEventDestroy(p.a); cudaEventDestroy(p.b);
+        if (prev_end && cudaEventElapsedTime(&ms, prev_end, p.a) == cudaSuccess && ms > 0.f) {
+            const std::string nm = "gap:" + c->slots[p.slot].name;
+            int gs = -1;
+            for (size_t i = 0; i < c->slots.size(); i++) if (c->slots[i].name == nm) { gs = (int)i; break; }
+            if (gs < 0) { c->slots.push_back(JtTimingSlot{nm, 0, 0}); gs = (int)c->slots.size() - 1; }
+            c->slots[gs].ms += ms; c->slots[gs].launches++;
+        }
+        done.push_back(p.a);
+        prev_end = p.b;
     }
+    for (auto &p : c->pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     c->pending.clear();
 }
 

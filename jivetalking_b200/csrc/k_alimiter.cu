@@ -16,8 +16,8 @@
 #include "jt_lanes.cuh"
 
 #define LIM_MAXBUF 512
-#define LIM_R 64
-typedef LaneStage<double, LIM_R> LimIn;
+#define LIM_R 32
+typedef LaneStage<double, LIM_R, 4> LimIn;      // 256-byte rows, 4-deep ring (x2 views) + output rows: 87 KB per warp
 typedef LaneStore<double, LIM_R> LimOut;
 
 __global__ void __launch_bounds__(64)
@@ -49,7 +49,7 @@ k_alimiter(const double *__restrict__ x, double *__restrict__ y, int64_t n, int 
     const double rr = rate * release;                    // divided by, as the scalar code does
     auto inp = [&](int64_t s) -> double { return (s >= 0 && s < n) ? x[s] * level_in : 0.0; };
 
-    A.prefetch(); B.prefetch();
+    A.prime(); B.prime();
     for (int tile = 0; tile < A.ntiles; tile++) {
         A.prefetch(); B.prefetch();
         const double *ra = A.wait(tile), *rb = B.wait(tile);
@@ -154,7 +154,9 @@ Sig jt_alimiter(jt_ctx *c, const Sig &in, const LimiterParams &p)
     if (bs > LIM_MAXBUF) JT_THROW(JT_ERR_UNSUPPORTED, "alimiter lookahead of %d samples (max %d)", bs, LIM_MAXBUF);
     Sig o = in; o.d = jt_dalloc<double>(c, in.n);
     if (in.n <= 0) return o;
-    const int seg = 16384;
+    // one wave: 2 warps per SM hold their staging at once; segments grow before a second wave would start
+    const int64_t slots = (int64_t)c->num_sms * 2 * 32;
+    const int seg = (int)std::min<int64_t>(((std::max<int64_t>(16384, (in.n + slots - 1) / slots) + LIM_R - 1) / LIM_R) * LIM_R, 1 << 24);
     int warm = (int)(in.rate * (0.5 + 2 * release + 2 * attack)) + 2 * bs;
     warm = (warm + LIM_R - 1) / LIM_R * LIM_R;                  // tile-aligned (see the kernel)
     const int64_t lanes = (in.n + seg - 1) / seg;

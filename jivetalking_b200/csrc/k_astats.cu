@@ -146,10 +146,10 @@ k_astats_c1(const T *__restrict__ x, int64_t n, double mult, double *__restrict_
     extern __shared__ __align__(16) unsigned char smem[];
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t s = min(b * AS_BS, n), e = min(s + AS_BS, n);
-    LaneStage<T, R> in;
-    in.init(smem + (size_t)(threadIdx.x >> 5) * LaneStage<T, R>::WARP_BYTES, x + s, e - s);
+    LaneStage<T, R, 2> in;
+    in.init(smem + (size_t)(threadIdx.x >> 5) * LaneStage<T, R, 2>::WARP_BYTES, x + s, e - s);
     double avg = 0; const double om = 1.0 - mult;
-    in.prefetch();
+    in.prime();
     for (int tile = 0; tile < in.ntiles; tile++) {
         in.prefetch();
         const T *row = in.wait(tile);
@@ -193,11 +193,11 @@ k_astats_c2(const T *__restrict__ x, int64_t n, double mult, const double *__res
     extern __shared__ __align__(16) unsigned char smem[];
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t s = min(b * AS_BS, n), e = min(s + AS_BS, n);
-    LaneStage<T, R> in;
-    in.init(smem + (size_t)(threadIdx.x >> 5) * LaneStage<T, R>::WARP_BYTES, x + s, e - s);
+    LaneStage<T, R, 2> in;
+    in.init(smem + (size_t)(threadIdx.x >> 5) * LaneStage<T, R, 2>::WARP_BYTES, x + s, e - s);
     double lo = DBL_MAX, hi = 0;
     double avg = e > s ? carry[b] : 0.0; const double om = 1.0 - mult;
-    in.prefetch();
+    in.prime();
     for (int tile = 0; tile < in.ntiles; tile++) {
         in.prefetch();
         const T *row = in.wait(tile);
@@ -363,7 +363,7 @@ static void astats_t(jt_ctx *c, const Sig &in, int64_t n, AstatsResult &out)
     if (n > tc) {
         double *d_fin = jt_dalloc<double>(c, nb), *d_carry = jt_dalloc<double>(c, nb);
         JtLaunch L(c, "astats:rms_scan", 3);
-        const size_t smemC = 2 * LaneStage<T, AsRow<T>::R>::WARP_BYTES;
+        const size_t smemC = 2 * LaneStage<T, AsRow<T>::R, 2>::WARP_BYTES;
         JT_CUDA(cudaFuncSetAttribute(k_astats_c1<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC));
         JT_CUDA(cudaFuncSetAttribute(k_astats_c2<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC));
         k_astats_c1<T><<<(int)((nb + 63) / 64), 64, smemC, c->stream>>>(x, n, mult, d_fin);

@@ -16,10 +16,10 @@
 #define FAKE_INFINITY (65536.0 * 65536.0)
 
 // ---- switching envelope follower ----------------------------------------------------------
-#define ENV_R 128           // input rows of 1 KB: two in flight per lane cover the bulk-copy latency of a 28-cycle/sample walk
+#define ENV_R 128           // input rows of 1 KB, double-buffered (a 4-deep ring of 512 B rows measured 20 % slower)
 #define ENV_RO 32           // output rows of 256 B
 #define ENV_THREADS 32
-typedef LaneStage<double, ENV_R> EnvIn;
+typedef LaneStage<double, ENV_R, 2> EnvIn;
 typedef LaneStore<double, ENV_RO> EnvOut;
 // env' = env + (d - env) * (d > env ? attack : release), rounded like the scalar C (no contraction).
 // Both branches are evaluated and the comparison selects, so the carried chain is
@@ -49,7 +49,7 @@ k_envelope(const double *__restrict__ x, double *__restrict__ env, int64_t n, in
     // loops are branch-free, which lets ptxas hoist the shared-memory loads and overlap everything
     // except the carried chain
     double e = 0.0;
-    in.prefetch();
+    in.prime();
     for (int tile = 0; tile < in.ntiles; tile++) {
         in.prefetch();
         const double *row = in.wait(tile);

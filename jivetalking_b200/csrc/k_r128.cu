@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(64)
 k_r128_ticks(const TIN *__restrict__ x, int64_t n, int tick, int64_t n_ticks_total, int G, int WU,
              const __grid_constant__ KWeight kw, double *__restrict__ tick_pow, double *__restrict__ tick_peak)
 {
-    constexpr int R = 512 / (int)sizeof(TIN);                    // 512-byte rows
+    constexpr int R = 512 / (int)sizeof(TIN);                    // 512-byte rows, double-buffered
     extern __shared__ __align__(16) unsigned char smem[];
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = t * G < n_ticks_total;
@@ -65,8 +65,8 @@ k_r128_ticks(const TIN *__restrict__ x, int64_t n, int tick, int64_t n_ticks_tot
     const int64_t k1 = min(k0 + (int64_t)G, n_ticks_total);
     const int64_t begin = max((int64_t)0, (k0 - WU) * (int64_t)tick);
     const int64_t end = live ? min(k1 * (int64_t)tick, n) : begin;
-    LaneStage<TIN, R> in;
-    in.init(smem + (size_t)(threadIdx.x >> 5) * LaneStage<TIN, R>::WARP_BYTES, x + begin, end - begin);
+    LaneStage<TIN, R, 2> in;
+    in.init(smem + (size_t)(threadIdx.x >> 5) * LaneStage<TIN, R, 2>::WARP_BYTES, x + begin, end - begin);
     double x1 = 0, x2 = 0, y1 = 0, y2 = 0, z1 = 0, z2 = 0;      // STRUCT 0
     double v1 = 0, v2 = 0, v3 = 0, v4 = 0;                        // STRUCT 1
     auto step = [&](double x0) -> double {
@@ -86,7 +86,7 @@ k_r128_ticks(const TIN *__restrict__ x, int64_t n, int tick, int64_t n_ticks_tot
     const int64_t warm_end = k0 * (int64_t)tick;
     int64_t k = k0, tick_end = min((k0 + 1) * (int64_t)tick, n);
     double acc = 0.0, pk = 0.0;
-    in.prefetch();
+    in.prime();
     for (int tile = 0; tile < in.ntiles; tile++) {
         in.prefetch();
         const TIN *row = in.wait(tile);
@@ -140,12 +140,16 @@ static void run_ticks(jt_ctx *c, const Sig &in, int tick, int64_t n_ticks_total,
                       double *d_pow, double *d_peak)
 {
     if (n_ticks_total <= 0) return;
-    const int G = 2, WU = 2;
+    // 34 KB of staging per warp: 6 warps per SM.  Two ticks per lane (plus two of warm-up) unless that would
+    // need a second wave of CTAs; then the lanes grow instead.
+    const int WU = 2;
+    const int64_t slots = (int64_t)c->num_sms * 6 * 32;
+    const int G = (int)std::max<int64_t>(2, (n_ticks_total + slots - 1) / slots);
     const int64_t lanes = (n_ticks_total + G - 1) / G;
     const int grid = (int)((lanes + 63) / 64);
     JtLaunch L(c, in.rate >= 176400 ? "r128_kweight_ticks:192k" : "r128_kweight_ticks");
 #define R128_LAUNCH(T) do { \
-        const size_t smem = 2 * LaneStage<T, 512 / (int)sizeof(T)>::WARP_BYTES; \
+        const size_t smem = 2 * LaneStage<T, 512 / (int)sizeof(T), 2>::WARP_BYTES; \
         JT_CUDA(cudaFuncSetAttribute(k_r128_ticks<T, STRUCT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         k_r128_ticks<T, STRUCT><<<grid, 64, smem, c->stream>>>((const T *)in.d, in.n, tick, n_ticks_total, G, WU, kw, d_pow, d_peak); } while (0)
     if (in.fmt == JT_FMT_S16) R128_LAUNCH(int16_t);
