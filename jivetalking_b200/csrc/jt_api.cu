@@ -59,6 +59,10 @@ extern "C" void jt_destroy(jt_ctx *c)
     jt_flush_timing(c);
     if (c->pin_in) cudaFreeHost(c->pin_in);
     if (c->pin_out) cudaFreeHost(c->pin_out);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (auto &kv : c->dev_tables) cudaFree(kv.second);
+    for (auto &b : c->pin_blocks) cudaFreeHost(b.first);
+    for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
     delete c;
 }
@@ -279,21 +283,34 @@ extern "C" int jt_default_pass2_spec(char *buf, size_t cap) { return copy_str(PA
 // ---------------------------------------------------------------------------------------
 // Pass 1 with the interval accumulation of collectAnalysisFrames (analyser.go:571-638)
 // ---------------------------------------------------------------------------------------
-static void analyse_device(jt_ctx *c, const void *d_in, int64_t n_frames, int rate, int channels, int fmt, int F,
-                           jt_measurements *out, jt_interval *iv, int64_t iv_cap, int64_t *n_iv)
+struct AnalysePending { GraphRun g; double *h_ss = nullptr, *h_pk = nullptr; int64_t nsrc = 0, n_frames = 0; int rate = 0, channels = 0, F = 4096; cudaEvent_t ev = nullptr; };
+
+// Pass 1, device part: raw per-frame statistics (a2) and the Pass-1 graph; nothing here waits for the GPU
+static void analyse_enqueue(jt_ctx *c, const void *d_in, int64_t n_frames, int rate, int channels, int fmt, int F, AnalysePending &ap)
 {
     if (F <= 0) F = 4096;
+    ap.F = F; ap.n_frames = n_frames; ap.rate = rate; ap.channels = channels;
     const int64_t nsrc = (n_frames + F - 1) / F;
+    ap.nsrc = nsrc;
     double *d_ss = jt_dalloc<double>(c, nsrc), *d_pk = jt_dalloc<double>(c, nsrc);
     jt_raw_frame_stats(c, d_in, n_frames, channels, fmt, F, d_ss, d_pk, nsrc);
-    std::vector<double> ss(nsrc), pk(nsrc);
-    GraphResult g;
-    jt_graph_run(c, PASS1_SPEC, d_in, n_frames, rate, channels, fmt, F, false, true, g);
+    ap.h_ss = jt_pinned<double>(c, nsrc); ap.h_pk = jt_pinned<double>(c, nsrc);
     if (nsrc) {
-        JT_CUDA(cudaMemcpyAsync(ss.data(), d_ss, sizeof(double) * nsrc, cudaMemcpyDeviceToHost, c->stream));
-        JT_CUDA(cudaMemcpyAsync(pk.data(), d_pk, sizeof(double) * nsrc, cudaMemcpyDeviceToHost, c->stream));
-        JT_CUDA(cudaStreamSynchronize(c->stream));
+        JT_CUDA(cudaMemcpyAsync(ap.h_ss, d_ss, sizeof(double) * nsrc, cudaMemcpyDeviceToHost, c->stream));
+        JT_CUDA(cudaMemcpyAsync(ap.h_pk, d_pk, sizeof(double) * nsrc, cudaMemcpyDeviceToHost, c->stream));
     }
+    ap.ev = jt_record_event(c);
+    jt_graph_enqueue(c, PASS1_SPEC, d_in, n_frames, rate, channels, fmt, F, false, true, ap.g);
+}
+
+// Pass 1, host part: metadata assembly and the Go-side accumulation (collectAnalysisFrames, analyser.go:571-638)
+static void analyse_finish(jt_ctx *c, AnalysePending &ap, jt_measurements *out, jt_interval *iv, int64_t iv_cap, int64_t *n_iv)
+{
+    const int64_t nsrc = ap.nsrc, n_frames = ap.n_frames; const int rate = ap.rate, channels = ap.channels, F = ap.F;
+    GraphResult g;
+    jt_graph_finish(c, ap.g, g);
+    JT_CUDA(cudaEventSynchronize(ap.ev));
+    const double *ss = ap.h_ss, *pk = ap.h_pk;
     MeasAcc acc;
     JtHost hacc(c, "interval_accumulation");
     struct IvAcc { int frameCount = 0; double rawSS = 0; int64_t rawN = 0; double rawPeak = 0; double spec[JT_SP_COUNT] = {0}; bool specFound = false;
@@ -344,6 +361,14 @@ static void analyse_device(jt_ctx *c, const void *d_in, int64_t n_frames, int ra
     acc.finish((double)n_frames / rate);
     if (out) *out = acc.m;
     if (n_iv) *n_iv = n_int;
+}
+
+static void analyse_device(jt_ctx *c, const void *d_in, int64_t n_frames, int rate, int channels, int fmt, int F,
+                           jt_measurements *out, jt_interval *iv, int64_t iv_cap, int64_t *n_iv)
+{
+    AnalysePending ap;
+    analyse_enqueue(c, d_in, n_frames, rate, channels, fmt, F, ap);
+    analyse_finish(c, ap, out, iv, iv_cap, n_iv);
 }
 
 extern "C" int jt_analyse(jt_ctx *c, const void *pcm_in, int64_t n_frames, int rate, int channels, int fmt, int frame_size,
@@ -452,32 +477,55 @@ extern "C" int jt_build_pass4_spec(const jt_process_result *plan, const jt_loudn
 // ---------------------------------------------------------------------------------------
 // the four-pass chain (ProcessAudio, processor.go:78-216)
 // ---------------------------------------------------------------------------------------
+// The four passes are data-dependent only through a handful of scalars (Pass 3 is planned from Pass 2's I / TP,
+// Pass 4 from Pass 3's loudnorm measurement), so the host-side assembly of one pass's metadata runs while the
+// GPU is already working on the next pass: graphs are enqueued (jt_graph_enqueue) ahead of being finished.
 static void process_device(jt_ctx *c, const void *d_in, int64_t n_frames, int rate, int channels, int fmt, const char *pass2_spec,
                            int16_t *pcm_out, bool out_on_device, int64_t cap, jt_process_result *res)
 {
     jt_process_result R; memset(&R, 0, sizeof(R));
     const double tI = -16.0, tTP = -1.0, tLRA = 20.0;          // defaultLoudnormConfig, filters.go:523-532
-    // Pass 1
-    size_t mark = c->allocs.size();
-    analyse_device(c, d_in, n_frames, rate, channels, fmt, 4096, &R.input, nullptr, 0, nullptr);
+    const size_t mark = c->allocs.size();
+    // Pass 1 and Pass 2: device work (Pass 2 reads the input only; its spec comes from the caller)
+    AnalysePending p1;
+    analyse_enqueue(c, d_in, n_frames, rate, channels, fmt, 4096, p1);
     jt_release_since(c, mark, nullptr);
     jt_check_cancel(c);
-    // Pass 2
-    GraphResult g2;
-    jt_graph_run(c, pass2_spec ? pass2_spec : PASS2_DEFAULT_SPEC, d_in, n_frames, rate, channels, fmt, 4096, true, true, g2);
-    { MeasAcc a; for (auto &m : g2.meta) a.add(m); a.finish((double)g2.out.n / g2.out.rate); R.filtered = a.m; }
+    GraphRun g2;
+    jt_graph_enqueue(c, pass2_spec ? pass2_spec : PASS2_DEFAULT_SPEC, d_in, n_frames, rate, channels, fmt, 4096, true, true, g2);
     if (g2.out.fmt != JT_FMT_S16 || g2.out.rate != 44100) JT_THROW(JT_ERR_SPEC, "Pass-2 spec must end in the s16/44.1 kHz output stage (processor.go:379-384)");
     jt_release_since(c, mark, g2.out.d);          // keep only the Pass-2 output ("the FLAC on disk")
-    mark = c->allocs.size();
+    // Pass 1: host part, while the GPU runs Pass 2
+    analyse_finish(c, p1, &R.input, nullptr, 0, nullptr);
     jt_check_cancel(c);
-    // Pass 3: the Pass-2 output is re-read as the s16 FLAC the reference wrote (processor.go:126-146)
+    // Pass 3 is planned from Pass 2's integrated loudness and true peak as the sink frames report them
+    // (last-seen values of lavfi.r128.I / true_peak, "%.3f": analyser_metrics.go:898-923)
+    double out_i = 0.0, out_tp = 0.0;
+    {
+        const R128Result &r = jt_graph_r128_early(c, g2);
+        int64_t last_tick = -1;
+        for (const FrameRef &fr : g2.frames) if (fr.tick >= 0 && fr.tick < r.n_ticks) last_tick = std::max<int64_t>(last_tick, fr.tick);
+        if (last_tick >= 0) { out_i = jt_wire("%.3f", r.I); out_tp = ratio_db(jt_wire("%.3f", r.tp_cum[last_tick])); }
+    }
     char spec3[1024], spec4[4096];
-    int rc = jt_build_pass3_spec(R.filtered.input_i, R.filtered.input_tp, tI, tTP, tLRA, spec3, sizeof(spec3), &R);
+    int rc = jt_build_pass3_spec(out_i, out_tp, tI, tTP, tLRA, spec3, sizeof(spec3), &R);
     if (rc) JT_THROW(rc, "pass-3 spec");
-    GraphResult g3;
-    jt_graph_run(c, spec3, g2.out.d, g2.out.n, 44100, 1, JT_FMT_S16, 4096, false, false, g3);
-    R.pass3 = g3.ln;
-    jt_release_since(c, mark, nullptr);
+    // Pass 3: the Pass-2 output is re-read as the s16 FLAC the reference wrote (processor.go:126-146)
+    const size_t mark3 = c->allocs.size();
+    GraphRun g3;
+    jt_graph_enqueue(c, spec3, g2.out.d, g2.out.n, 44100, 1, JT_FMT_S16, 4096, false, false, g3);
+    jt_release_since(c, mark3, nullptr);
+    // Pass 2: host part, while the GPU finishes Pass 2's analysis tail and runs Pass 3
+    {
+        GraphResult r2;
+        jt_graph_finish(c, g2, r2);
+        MeasAcc a; for (auto &m : r2.meta) a.add(m); a.finish((double)g2.out.n / g2.out.rate); R.filtered = a.m;
+    }
+    {
+        GraphResult r3;
+        jt_graph_finish(c, g3, r3);
+        R.pass3 = r3.ln;
+    }
     const double mI = jt_wire("%.2f", R.pass3.input_i);
     if (std::isinf(mI) || std::isnan(mI) || mI < -70.0) JT_THROW(JT_ERR_INVALID_ARG, "cannot normalise silent audio (measured %.1f LUFS)", mI);
     jt_check_cancel(c);
@@ -486,17 +534,21 @@ static void process_device(jt_ctx *c, const void *d_in, int64_t n_frames, int ra
     rc = jt_build_pass4_spec(&R, &R.pass3, tI, tTP, tLRA, 44100, spec4, sizeof(spec4), &eff, &off);
     if (rc) JT_THROW(rc, "pass-4 spec");
     R.effective_target_i = eff; R.linear_possible = eff == tI;
-    GraphResult g4;
-    jt_graph_run(c, spec4, g2.out.d, g2.out.n, 44100, 1, JT_FMT_S16, 4096, true, true, g4);
-    { MeasAcc a; for (auto &m : g4.meta) a.add(m); a.finish((double)g4.out.n / g4.out.rate); R.final = a.m; }
-    R.pass4 = g4.ln;
+    GraphRun g4;
+    jt_graph_enqueue(c, spec4, g2.out.d, g2.out.n, 44100, 1, JT_FMT_S16, 4096, true, true, g4);
     R.n_out = g4.out.n;
-    if (pcm_out) {
+    if (pcm_out) {                                 // the result leaves while the host assembles Pass 4's metadata
         if (g4.out.n > cap) JT_THROW(JT_ERR_BUFFER, "pcm_out holds %lld samples, chain produced %lld", (long long)cap, (long long)g4.out.n);
         const size_t ob = (size_t)g4.out.n * sizeof(int16_t);
-        if (out_on_device) { if (ob) JT_CUDA(cudaMemcpyAsync(pcm_out, g4.out.d, ob, cudaMemcpyDeviceToDevice, c->stream)); }
-        else download(c, pcm_out, g4.out.d, ob);
+        if (ob) JT_CUDA(cudaMemcpyAsync(pcm_out, g4.out.d, ob, out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
     }
+    {
+        GraphResult r4;
+        jt_graph_finish(c, g4, r4);
+        MeasAcc a; for (auto &m : r4.meta) a.add(m); a.finish((double)g4.out.n / g4.out.rate); R.final = a.m;
+        R.pass4 = r4.ln;
+    }
+    JT_CUDA(cudaStreamSynchronize(c->stream));
     if (res) *res = R;
 }
 

@@ -182,7 +182,7 @@ struct Exec {
     jt_ctx *c; Sig cur; int link_fmt; std::vector<FrameRef> frames;
     // analysis products
     bool has_astats = false, has_spec = false, has_r128 = false, astats_overall_only = false;
-    Sig astats_sig, spec_sig; int spec_win = 2048; R128Result r128; std::vector<float> spec_rows; int64_t spec_hops = 0;
+    Sig astats_sig, spec_sig; int spec_win = 2048;
     void storage(int fmt) { cur = jt_convert(c, cur, fmt); link_fmt = fmt; }
     void materialise() { if (cur.fmt != link_fmt) cur = jt_convert(c, cur, link_fmt); }
 };
@@ -242,11 +242,19 @@ static std::vector<double> parse_bn(const std::string &s)
 void jt_graph_run(jt_ctx *c, const std::string &spec, const void *d_in, int64_t n_frames, int rate, int channels,
                   int fmt, int frame_size, bool want_pcm, bool want_meta, GraphResult &res)
 {
+    GraphRun g;
+    jt_graph_enqueue(c, spec, d_in, n_frames, rate, channels, fmt, frame_size, want_pcm, want_meta, g);
+    jt_graph_finish(c, g, res);
+}
+
+void jt_graph_enqueue(jt_ctx *c, const std::string &spec, const void *d_in, int64_t n_frames, int rate, int channels,
+                      int fmt, int frame_size, bool want_pcm, bool want_meta, GraphRun &g)
+{
     if (n_frames < 0 || rate <= 0 || channels <= 0) JT_THROW(JT_ERR_INVALID_ARG, "bad stream description");
     if (frame_size <= 0) frame_size = 4096;
     std::vector<FilterNode> nodes = jt_parse_spec(spec);
-    res = GraphResult();
-    memset(&res.ln, 0, sizeof(res.ln));
+    g = GraphRun();
+    g.want_meta = want_meta;
 
     Exec E; E.c = c;
     bool have_mono = false;
@@ -408,25 +416,18 @@ void jt_graph_run(jt_ctx *c, const std::string &spec, const void *d_in, int64_t 
                 const double off = I - mI, off_tp = mTP + off;
                 if (mTP != 99 && mTh != -70 && mLRA != 0 && mI != 0 && off_tp <= TP && mLRA <= LRA) { lin_mode = true; offset = off; }
             }
-            res.ln.valid = 1;
-            LoudnormMeter mi, mo;
+            g.has_ln = true; g.ln_linear = lin_mode; g.ln_I = I;
             if (lin_mode) {
                 E.materialise(); E.storage(JT_FMT_DBL);
-                jt_loudnorm_meter(c, E.cur, dual, mi);
+                jt_loudnorm_meter_launch(c, E.cur, dual, g.ln_in);
                 E.cur = jt_gain_f64(c, E.cur, pow(10., offset / 20.));
-                jt_loudnorm_meter(c, E.cur, dual, mo);
-                res.ln.normalization_type = 0;
-                res.ln.output_i = mo.I; res.ln.output_tp = 20. * log10(mo.sample_peak); res.ln.output_lra = mo.LRA; res.ln.output_thresh = mo.thresh;
-                res.ln.target_offset = I - mo.I;
+                jt_loudnorm_meter_launch(c, E.cur, dual, g.ln_out);
             } else {
                 // dynamic mode: af_loudnorm.c query_formats forces the input link to 192 kHz / dbl
                 if (want_pcm || !last) JT_THROW(JT_ERR_UNSUPPORTED, "loudnorm dynamic mode with audio output (linear-mode preconditions not met: measured_I=%g measured_TP=%g measured_LRA=%g measured_thresh=%g)", mI, mTP, mLRA, mTh);
                 do_resample(E, 192000, JT_FMT_DBL, true);
-                jt_loudnorm_meter(c, E.cur, dual, mi);
-                res.ln.normalization_type = 1;
-                res.ln.output_i = res.ln.output_tp = res.ln.output_lra = res.ln.output_thresh = res.ln.target_offset = NAN;
+                jt_loudnorm_meter_launch(c, E.cur, dual, g.ln_in);
             }
-            res.ln.input_i = mi.I; res.ln.input_tp = 20. * log10(mi.sample_peak); res.ln.input_lra = mi.LRA; res.ln.input_thresh = mi.thresh;
         } else if (f.name == "astats") {
             E.materialise();
             E.has_astats = true; E.astats_sig = E.cur;
@@ -445,7 +446,7 @@ void jt_graph_run(jt_ctx *c, const std::string &spec, const void *d_in, int64_t 
             const bool tp = peak.find("true") != std::string::npos;
             const bool dual = f.flag("dualmono", "", false);
             // input link is dbl; s16/flt storage widens exactly on load
-            if (want_meta) jt_ebur128(c, E.cur, dual, tp, E.r128);
+            if (want_meta) jt_ebur128_launch(c, E.cur, dual, tp, g.r128p);
             E.has_r128 = true; E.link_fmt = JT_FMT_DBL;
             const int tick = E.cur.rate / 10;
             E.frames = reframe(E.frames, E.cur.n, tick);
@@ -456,47 +457,83 @@ void jt_graph_run(jt_ctx *c, const std::string &spec, const void *d_in, int64_t 
     }
     if (!have_mono) JT_THROW(JT_ERR_UNSUPPORTED, "%d-channel graph without a mono downmix", channels);
     if (E.cur.d && want_pcm) E.materialise();
-    res.out = E.cur; if (E.cur.d) res.out.fmt = E.cur.fmt; else res.out.fmt = E.link_fmt;
-
-    // ---- sink-frame metadata ------------------------------------------------------------
+    g.out = E.cur; g.out.fmt = E.cur.d ? E.cur.fmt : E.link_fmt;
+    g.frames.swap(E.frames);
+    g.has_astats = E.has_astats; g.has_spec = E.has_spec; g.has_r128 = E.has_r128; g.astats_overall_only = E.astats_overall_only;
+    g.astats_sig = E.astats_sig; g.spec_sig = E.spec_sig; g.spec_win = E.spec_win;
     if (!want_meta) return;
-    const size_t nf = E.frames.size();
-    if (E.has_spec) {
+    // ---- analysis kernels whose input cadence depends on the final sink framing -------------
+    const size_t nf = g.frames.size();
+    if (g.has_spec) {
         // aspectralstats emits one row per 1024-sample hop, but a sink frame only ever shows the row of the
         // hop holding its first sample: compute just those (plus predecessors for the flux term)
         std::vector<int64_t> wanted; wanted.reserve(nf);
-        for (size_t i = 0; i < nf; i++) if (E.frames[i].hop >= 0) wanted.push_back(E.frames[i].hop);
-        jt_aspectralstats(c, E.spec_sig, E.spec_win, E.spec_rows, E.spec_hops, &wanted);
+        for (size_t i = 0; i < nf; i++) if (g.frames[i].hop >= 0) wanted.push_back(g.frames[i].hop);
+        jt_aspectralstats_launch(c, g.spec_sig, g.spec_win, &wanted, g.specp);
     }
+    for (size_t i = 0; i < nf; i++) if (g.frames[i].astats_pos >= 0) g.last_astats_frame = (long)i;
+    if (g.has_astats && g.last_astats_frame >= 0) jt_astats_launch(c, g.astats_sig, g.frames[g.last_astats_frame].astats_pos, g.astp);
+}
+
+const R128Result &jt_graph_r128_early(jt_ctx *c, GraphRun &g)
+{
+    if (!g.r128_done) { if (g.has_r128 && g.want_meta) jt_ebur128_finish(c, g.r128p, g.r128); g.r128_done = true; }
+    return g.r128;
+}
+
+void jt_graph_finish(jt_ctx *c, GraphRun &g, GraphResult &res)
+{
+    res = GraphResult();
+    memset(&res.ln, 0, sizeof(res.ln));
+    res.out = g.out;
+    if (g.has_ln) {
+        LoudnormMeter mi, mo;
+        jt_loudnorm_meter_finish(c, g.ln_in, mi);
+        res.ln.valid = 1;
+        if (g.ln_linear) {
+            jt_loudnorm_meter_finish(c, g.ln_out, mo);
+            res.ln.normalization_type = 0;
+            res.ln.output_i = mo.I; res.ln.output_tp = 20. * log10(mo.sample_peak); res.ln.output_lra = mo.LRA; res.ln.output_thresh = mo.thresh;
+            res.ln.target_offset = g.ln_I - mo.I;
+        } else {
+            res.ln.normalization_type = 1;
+            res.ln.output_i = res.ln.output_tp = res.ln.output_lra = res.ln.output_thresh = res.ln.target_offset = NAN;
+        }
+        res.ln.input_i = mi.I; res.ln.input_tp = 20. * log10(mi.sample_peak); res.ln.input_lra = mi.LRA; res.ln.input_thresh = mi.thresh;
+    }
+    if (!g.want_meta) return;
+    const R128Result &r128 = jt_graph_r128_early(c, g);
+    std::vector<float> spec_rows; int64_t spec_hops = 0;
+    if (g.has_spec) jt_aspectralstats_finish(c, g.specp, spec_rows, spec_hops);
+    const std::vector<FrameRef> &frames = g.frames;
+    const size_t nf = frames.size();
     JtHost hmeta(c, "meta_assembly");
     res.meta.resize(nf); res.meta_ready.resize(nf);
-    int64_t last_tick = -1; long last_astats_frame = -1;
-    for (size_t i = 0; i < nf; i++) {
-        if (E.frames[i].tick >= 0) last_tick = std::max<int64_t>(last_tick, E.frames[i].tick);
-        if (E.frames[i].astats_pos >= 0) last_astats_frame = (long)i;
-    }
+    int64_t last_tick = -1;
+    for (size_t i = 0; i < nf; i++) if (frames[i].tick >= 0) last_tick = std::max<int64_t>(last_tick, frames[i].tick);
+    const long last_astats_frame = g.last_astats_frame;
     // records are independent: the printf-rounding of ~20 values per sink frame is spread over host threads
     auto fill = [&](size_t i0, size_t i1) {
         for (size_t i = i0; i < i1; i++) {
-            const FrameRef &fr = E.frames[i];
+            const FrameRef &fr = frames[i];
             jt_frame_meta &m = res.meta[i];
             double *dp = &m.r128_M;
             const size_t ndbl = (sizeof(jt_frame_meta) - offsetof(jt_frame_meta, r128_M)) / sizeof(double);
             for (size_t k = 0; k < ndbl; k++) dp[k] = NAN;
             m.first_sample = fr.start; m.nb_samples = fr.nb; m.reserved = 0;
             res.meta_ready[i] = fr.ready;
-            if (E.has_r128 && fr.tick >= 0 && fr.tick < E.r128.n_ticks) {
+            if (g.has_r128 && fr.tick >= 0 && fr.tick < r128.n_ticks) {
                 const int64_t k = fr.tick;
-                m.r128_M = jt_wire("%.3f", E.r128.M[k]); m.r128_S = jt_wire("%.3f", E.r128.S[k]);
-                m.r128_sample_peak = jt_wire("%.3f", E.r128.sp_cum[k]);
-                m.r128_true_peak = jt_wire("%.3f", E.r128.tp_cum[k]);
+                m.r128_M = jt_wire("%.3f", r128.M[k]); m.r128_S = jt_wire("%.3f", r128.S[k]);
+                m.r128_sample_peak = jt_wire("%.3f", r128.sp_cum[k]);
+                m.r128_true_peak = jt_wire("%.3f", r128.tp_cum[k]);
                 if (k == last_tick) {
-                    m.r128_I = jt_wire("%.3f", E.r128.I); m.r128_LRA = jt_wire("%.3f", E.r128.LRA);
-                    m.r128_LRA_low = jt_wire("%.3f", E.r128.LRA_low); m.r128_LRA_high = jt_wire("%.3f", E.r128.LRA_high);
+                    m.r128_I = jt_wire("%.3f", r128.I); m.r128_LRA = jt_wire("%.3f", r128.LRA);
+                    m.r128_LRA_low = jt_wire("%.3f", r128.LRA_low); m.r128_LRA_high = jt_wire("%.3f", r128.LRA_high);
                 }
             }
-            if (E.has_spec && fr.hop >= 0 && fr.hop < E.spec_hops)
-                for (int k = 0; k < JT_SP_COUNT; k++) m.spectral[k] = jt_wire("%g", (double)E.spec_rows[(size_t)fr.hop * JT_SP_COUNT + k]);
+            if (g.has_spec && fr.hop >= 0 && fr.hop < spec_hops)
+                for (int k = 0; k < JT_SP_COUNT; k++) m.spectral[k] = jt_wire("%g", (double)spec_rows[(size_t)fr.hop * JT_SP_COUNT + k]);
         }
     };
     const unsigned hw = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
@@ -506,17 +543,16 @@ void jt_graph_run(jt_ctx *c, const std::string &spec, const void *d_in, int64_t 
         const size_t per = (nf + hw - 1) / hw;
         for (unsigned t = 0; t < hw; t++) { const size_t a = t * per, b = std::min(nf, a + per); if (a < b) pool.emplace_back(fill, a, b); }
     }
-    // the astats kernels (GPU) run while the host threads format the records
     AstatsResult a; bool have_a = false; JtError aerr{0, ""};
-    if (E.has_astats && last_astats_frame >= 0) {
-        try { jt_astats(c, E.astats_sig, E.frames[last_astats_frame].astats_pos, a); have_a = true; }
+    if (g.has_astats && last_astats_frame >= 0) {
+        try { jt_astats_finish(c, g.astp, a); have_a = true; }
         catch (const JtError &e) { aerr = e; }
     }
     for (auto &t : pool) t.join();
     if (aerr.code) throw aerr;
     if (have_a) {
         jt_frame_meta &m = res.meta[last_astats_frame];
-        if (!E.astats_overall_only) for (int k = 0; k < JT_AS_COUNT; k++) m.astats[k] = std::isnan(a.v[k]) ? NAN : jt_wire("%f", a.v[k]);
+        if (!g.astats_overall_only) for (int k = 0; k < JT_AS_COUNT; k++) m.astats[k] = std::isnan(a.v[k]) ? NAN : jt_wire("%f", a.v[k]);
         m.astats_overall_RMS_level = jt_wire("%f", a.overall_rms);
         m.astats_overall_Peak_level = jt_wire("%f", a.overall_peak);
     }

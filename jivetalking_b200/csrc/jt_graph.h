@@ -33,6 +33,28 @@ struct GraphResult {
     jt_loudnorm_stats ln;
 };
 
+// A graph whose kernels and device->host copies have been enqueued but whose host part (windowing / gating of the
+// tick values, statistics, sink-frame metadata) has not run yet.  jt_graph_enqueue never waits for the device;
+// jt_graph_finish does.  In between the caller can enqueue the next graph so the GPU stays busy while the host
+// assembles this one's metadata (jt_graph_r128_early gives the loudness values the next pass is planned from).
+struct GraphRun {
+    std::vector<FrameRef> frames;
+    Sig out; int out_fmt = 0;
+    bool want_meta = false;
+    bool has_astats = false, has_spec = false, has_r128 = false, astats_overall_only = false;
+    Sig astats_sig, spec_sig; int spec_win = 2048;
+    R128Pending r128p; SpectralPending specp; AstatsPending astp;
+    long last_astats_frame = -1;
+    R128Result r128; bool r128_done = false;
+    // loudnorm
+    bool has_ln = false, ln_linear = false; double ln_I = 0;
+    LoudnormPending ln_in, ln_out;
+};
+void jt_graph_enqueue(jt_ctx *c, const std::string &spec, const void *d_in, int64_t n_frames, int rate, int channels,
+                      int fmt, int frame_size, bool want_pcm, bool want_meta, GraphRun &g);
+const R128Result &jt_graph_r128_early(jt_ctx *c, GraphRun &g);     // waits for the ebur128 values only
+void jt_graph_finish(jt_ctx *c, GraphRun &g, GraphResult &res);
+
 // d_in: device pointer to interleaved input.  want_pcm=false lets measure-only graphs skip
 // work whose only product is discarded audio (loudnorm dynamic mode in Pass 3).
 void jt_graph_run(jt_ctx *c, const std::string &spec, const void *d_in, int64_t n_frames, int rate, int channels,

@@ -29,6 +29,11 @@ struct jt_ctx {
     std::vector<void *> host_allocs;   // pinned staging
     void *pin_in = nullptr; size_t pin_in_bytes = 0;
     void *pin_out = nullptr; size_t pin_out_bytes = 0;
+    // immutable device tables (filter banks, twiddles, windows), content-addressed: steady-state calls upload nothing
+    std::map<std::string, void *> dev_tables;
+    // pinned host arena for small device->host results (tick energies, statistics rows); reset per API call
+    std::vector<std::pair<char *, size_t>> pin_blocks; size_t pin_block = 0, pin_used = 0;
+    std::vector<cudaEvent_t> event_pool; size_t events_used = 0;
 };
 
 struct JtError { int code; std::string msg; };
@@ -40,6 +45,14 @@ struct JtError { int code; std::string msg; };
 void *jt_dalloc_bytes(jt_ctx *c, size_t bytes);
 template <class T> static inline T *jt_dalloc(jt_ctx *c, size_t n) { return (T *)jt_dalloc_bytes(c, (n ? n : 1) * sizeof(T)); }
 void jt_release_all(jt_ctx *c);
+// device copy of an immutable host table, cached for the life of the context (keyed by tag + content hash)
+const void *jt_dev_table(jt_ctx *c, const char *tag, const void *host, size_t bytes);
+template <class T> static inline const T *jt_dev_table(jt_ctx *c, const char *tag, const std::vector<T> &v) { return (const T *)jt_dev_table(c, tag, v.data(), v.size() * sizeof(T)); }
+// pinned host scratch valid until the end of the current API call
+void *jt_pinned_bytes(jt_ctx *c, size_t bytes);
+template <class T> static inline T *jt_pinned(jt_ctx *c, size_t n) { return (T *)jt_pinned_bytes(c, (n ? n : 1) * sizeof(T)); }
+// an event (timing disabled) recorded on the context's stream now; owned by the context, recycled per API call
+cudaEvent_t jt_record_event(jt_ctx *c);
 void jt_release_since(jt_ctx *c, size_t mark, const void *keep);   // free allocations made after `mark`, except the one holding `keep`
 void jt_check_cancel(jt_ctx *c);
 void jt_flush_timing(jt_ctx *c);
@@ -101,18 +114,33 @@ struct R128Result {      // host copies
     int64_t n_ticks = 0;
 };
 void jt_ebur128(jt_ctx *c, const Sig &in, bool dualmono, bool true_peak, R128Result &out);
+// launch / finish halves: the kernels and the device->host copies of the per-tick values are enqueued by
+// *_launch; *_finish waits for them (only them) and runs the host part.  Lets the caller keep the GPU busy.
+struct R128Pending { int64_t nt = 0; int tick = 0; bool dualmono = false, true_peak = false; double *hp = nullptr, *hk = nullptr, *ht = nullptr; cudaEvent_t ev = nullptr; };
+void jt_ebur128_launch(jt_ctx *c, const Sig &in, bool dualmono, bool true_peak, R128Pending &pd);
+void jt_ebur128_finish(jt_ctx *c, R128Pending &pd, R128Result &out);
 struct LoudnormMeter { double I, LRA, thresh, sample_peak; };
-void jt_loudnorm_meter(jt_ctx *c, const Sig &in_f64, bool dual_mono, LoudnormMeter &out);   // libavfilter/ebur128.c
+void jt_loudnorm_meter(jt_ctx *c, const Sig &in, bool dual_mono, LoudnormMeter &out);   // libavfilter/ebur128.c
+struct LoudnormPending { int64_t nt = 0, nfull = 0; int s100 = 0; bool dual_mono = false; double *hp = nullptr, *hk = nullptr; cudaEvent_t ev = nullptr; };
+void jt_loudnorm_meter_launch(jt_ctx *c, const Sig &in, bool dual_mono, LoudnormPending &pd);
+void jt_loudnorm_meter_finish(jt_ctx *c, LoudnormPending &pd, LoudnormMeter &out);
 
 // ---- k_astats.cu --------------------------------------------------------------------------
 struct AstatsResult { double v[JT_AS_COUNT]; double overall_rms, overall_peak; double nb_samples; };
 void jt_astats(jt_ctx *c, const Sig &in, int64_t n_upto, AstatsResult &out);
+struct AstatsPending { int64_t n = 0; int fmt = 0, rate = 0, tc = 0; void *host = nullptr; cudaEvent_t ev = nullptr; };
+void jt_astats_launch(jt_ctx *c, const Sig &in, int64_t n_upto, AstatsPending &pd);
+void jt_astats_finish(jt_ctx *c, AstatsPending &pd, AstatsResult &out);
 
 // ---- k_spectral.cu ------------------------------------------------------------------------
 // rows: n_hops x JT_SP_COUNT floats on the host
 // wanted != nullptr: only those hops (and their predecessors, for flux) are computed; other rows stay 0
 void jt_aspectralstats(jt_ctx *c, const Sig &in_flt, int win_size, std::vector<float> &rows, int64_t &n_hops,
                        const std::vector<int64_t> *wanted = nullptr);
+
+struct SpectralPending { int64_t n_hops = 0, n_items = 0; bool sparse = false; std::vector<int64_t> items; float *h_rows = nullptr; cudaEvent_t ev = nullptr; };
+void jt_aspectralstats_launch(jt_ctx *c, const Sig &in_flt, int win_size, const std::vector<int64_t> *wanted, SpectralPending &pd);
+void jt_aspectralstats_finish(jt_ctx *c, SpectralPending &pd, std::vector<float> &rows, int64_t &n_hops);
 
 // ---- k_biquad.cu --------------------------------------------------------------------------
 struct BiquadCoef { double b0, b1, b2, a1, a2; };

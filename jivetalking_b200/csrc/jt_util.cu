@@ -23,6 +23,51 @@ void jt_release_all(jt_ctx *c)
 {
     for (void *p : c->allocs) cudaFreeAsync(p, c->stream);
     c->allocs.clear();
+    c->pin_block = 0; c->pin_used = 0; c->events_used = 0;       // the API call that owned them is over
+}
+
+const void *jt_dev_table(jt_ctx *c, const char *tag, const void *host, size_t bytes)
+{
+    uint64_t h = 1469598103934665603ull;                           // FNV-1a over the content
+    const unsigned char *b = (const unsigned char *)host;
+    for (size_t i = 0; i < bytes; i++) { h ^= b[i]; h *= 1099511628211ull; }
+    char key[160];
+    snprintf(key, sizeof(key), "%s:%zu:%016llx", tag, bytes, (unsigned long long)h);
+    auto it = c->dev_tables.find(key);
+    if (it != c->dev_tables.end()) return it->second;
+    void *d = nullptr;
+    if (cudaMalloc(&d, bytes ? bytes : 16) != cudaSuccess) JT_THROW(JT_ERR_NOMEM, "cudaMalloc(%zu) for table %s", bytes, tag);
+    if (bytes && cudaMemcpy(d, host, bytes, cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(d); JT_THROW(JT_ERR_CUDA, "table upload %s", tag); }
+    c->dev_tables[key] = d;
+    return d;
+}
+
+void *jt_pinned_bytes(jt_ctx *c, size_t bytes)
+{
+    bytes = (bytes + 255) & ~size_t(255);
+    while (c->pin_block < c->pin_blocks.size()) {
+        auto &blk = c->pin_blocks[c->pin_block];
+        if (c->pin_used + bytes <= blk.second) { void *p = blk.first + c->pin_used; c->pin_used += bytes; return p; }
+        c->pin_block++; c->pin_used = 0;
+    }
+    const size_t cap = std::max<size_t>(bytes, 8u << 20);
+    char *p = nullptr;
+    if (cudaHostAlloc((void **)&p, cap, cudaHostAllocDefault) != cudaSuccess) JT_THROW(JT_ERR_NOMEM, "cudaHostAlloc(%zu)", cap);
+    c->pin_blocks.push_back({p, cap});
+    c->pin_block = c->pin_blocks.size() - 1; c->pin_used = bytes;
+    return p;
+}
+
+cudaEvent_t jt_record_event(jt_ctx *c)
+{
+    if (c->events_used == c->event_pool.size()) {
+        cudaEvent_t e;
+        JT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->event_pool.push_back(e);
+    }
+    cudaEvent_t e = c->event_pool[c->events_used++];
+    JT_CUDA(cudaEventRecord(e, c->stream));
+    return e;
 }
 
 void jt_release_since(jt_ctx *c, size_t mark, const void *keep)

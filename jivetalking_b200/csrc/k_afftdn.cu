@@ -449,15 +449,13 @@ Sig jt_afftdn(jt_ctx *c, const Sig &in, const AfftdnParams &P)
     for (int k = 0; k < K.FL; k++) { const double a = -2.0 * M_PI * k / K.FL; tw[k] = make_float2((float)cos(a), (float)sin(a)); }
 
     const int64_t n_hops = (in.n + K.A - 1) / K.A;
-    auto up = [&](const void *h, size_t bytes) { void *d = jt_dalloc_bytes(c, bytes); JT_CUDA(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, c->stream)); return d; };
-    double *d_window = (double *)up(window.data(), sizeof(double) * K.W);
-    float2 *d_tw = (float2 *)up(tw.data(), sizeof(float2) * tw.size());
-    double *d_rel = (double *)up(rel_var.data(), sizeof(double) * K.bins);
-    int *d_blo = (int *)up(band_lo.data(), sizeof(int) * (nb + 1));
-    int *d_b2b = (int *)up(bin2band.data(), sizeof(int) * K.bins);
-    double *d_alpha = (double *)up(alpha.data(), sizeof(double) * nb), *d_beta = (double *)up(beta.data(), sizeof(double) * nb);
-    double *d_spread = (double *)up(spread.data(), sizeof(double) * nb * nb);
-    JT_CUDA(cudaStreamSynchronize(c->stream));          // host vectors above are locals
+    const double *d_window = jt_dev_table(c, "afftdn_window", window);
+    const float2 *d_tw = jt_dev_table(c, "afftdn_tw", tw);
+    const double *d_rel = jt_dev_table(c, "afftdn_relvar", rel_var);
+    const int *d_blo = jt_dev_table(c, "afftdn_bandlo", band_lo);
+    const int *d_b2b = jt_dev_table(c, "afftdn_bin2band", bin2band);
+    const double *d_alpha = jt_dev_table(c, "afftdn_alpha", alpha), *d_beta = jt_dev_table(c, "afftdn_beta", beta);
+    const double *d_spread = jt_dev_table(c, "afftdn_spread", spread);
     float2 *d_spec = jt_dalloc<float2>(c, (size_t)n_hops * K.bins);
     double *d_gain = jt_dalloc<double>(c, (size_t)n_hops * K.bins), *d_clean = jt_dalloc<double>(c, (size_t)n_hops * K.bins);
     double *d_raw = jt_dalloc<double>(c, (size_t)n_hops * nb), *d_amt = jt_dalloc<double>(c, (size_t)n_hops * nb);

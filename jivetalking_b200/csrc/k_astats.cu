@@ -101,8 +101,9 @@ k_astats_a(const T *__restrict__ x, int64_t n, AsPartA *__restrict__ parts, unsi
 // counts[0..3] = min_count, max_count, min_runs (sum of run^2), max_runs
 template <class T>
 __global__ void __launch_bounds__(256)
-k_astats_b(const T *__restrict__ x, int64_t n, double gmin, double gmax, unsigned long long *__restrict__ counts)
+k_astats_b(const T *__restrict__ x, int64_t n, const AsPartA *__restrict__ total, unsigned long long *__restrict__ counts)
 {
+    const double gmin = total->mn, gmax = total->mx;
     unsigned long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -132,6 +133,23 @@ k_astats_b(const T *__restrict__ x, int64_t n, double gmin, double gmax, unsigne
         if (c0) atomicAdd(&counts[0], c0); if (c1) atomicAdd(&counts[1], c1);
         if (c2) atomicAdd(&counts[2], c2); if (c3) atomicAdd(&counts[3], c3);
     }
+}
+
+// combine the per-CTA partials of pass A (fixed order: deterministic) and initialise the min / max cells of C and D
+__global__ void __launch_bounds__(32)
+k_astats_reduce(const AsPartA *__restrict__ parts, int nparts, AsPartA *__restrict__ total, double *__restrict__ mm, float *__restrict__ nf)
+{
+    if (threadIdx.x) return;
+    AsPartA r = parts[0];
+    for (int i = 1; i < nparts; i++) {
+        const AsPartA b = parts[i];
+        r.sum += b.sum; r.sumsq += b.sumsq; r.diff_sum += b.diff_sum; r.diff_sumsq += b.diff_sumsq;
+        r.mn = fmin(r.mn, b.mn); r.mx = fmax(r.mx, b.mx); r.min_nz = fmin(r.min_nz, b.min_nz);
+        r.min_diff = fmin(r.min_diff, b.min_diff); r.max_diff = fmax(r.max_diff, b.max_diff);
+        r.zero_runs += b.zero_runs; r.mask |= b.mask;
+    }
+    *total = r;
+    mm[0] = DBL_MAX; mm[1] = 0.0; *nf = FLT_MAX;
 }
 
 // C1: per block of BS samples, zero-state end value of avg = avg*mult + (1-mult)*nd^2.
@@ -327,39 +345,31 @@ k_astats_nf_reduce(const float *__restrict__ bmin, const unsigned *__restrict__ 
     if (threadIdx.x == 0) { unsigned long long tot = 0; for (int w = 0; w < 32; w++) tot += s_c[w]; *gmin = g; *cnt = tot; }
 }
 
+struct AstatsHost { AsPartA total; unsigned long long hist[AS_HIST + 8]; double mm[2]; float nf; };
+
 template <class T>
-static void astats_t(jt_ctx *c, const Sig &in, int64_t n, AstatsResult &out)
+static void astats_launch_t(jt_ctx *c, const Sig &in, int64_t n, AstatsPending &pd)
 {
     const T *x = (const T *)in.d;
     const double time_constant = 0.05;
     const int tc = (int)std::fmax(time_constant * in.rate + .5, 1);
     const double mult = exp((-1 / time_constant / in.rate));
-    const int maxbits = in.fmt == JT_FMT_S16 ? 16 : in.fmt == JT_FMT_FLT ? 32 : 64;
+    pd.n = n; pd.fmt = in.fmt; pd.rate = in.rate; pd.tc = tc;
 
     const int gridA = jt_grid_for(n, 256, c->num_sms, 8);
-    AsPartA *d_parts = jt_dalloc<AsPartA>(c, gridA);
+    AsPartA *d_parts = jt_dalloc<AsPartA>(c, gridA + 1), *d_total = d_parts + gridA;
     unsigned long long *d_hist = jt_dalloc<unsigned long long>(c, AS_HIST + 8);
     unsigned long long *d_counts = d_hist + AS_HIST;     // 4 counts + noise-floor count
-    JT_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * (AS_HIST + 8), c->stream));
-    { JtLaunch L(c, "astats:sums_hist"); k_astats_a<T><<<gridA, 256, 0, c->stream>>>(x, n, d_parts, d_hist); }
-    std::vector<AsPartA> parts(gridA);
-    JT_CUDA(cudaMemcpyAsync(parts.data(), d_parts, sizeof(AsPartA) * gridA, cudaMemcpyDeviceToHost, c->stream));
-    JT_CUDA(cudaStreamSynchronize(c->stream));
-    AsPartA r = parts[0];
-    for (int i = 1; i < gridA; i++) {
-        const AsPartA &b = parts[i];
-        r.sum += b.sum; r.sumsq += b.sumsq; r.diff_sum += b.diff_sum; r.diff_sumsq += b.diff_sumsq;
-        r.mn = std::fmin(r.mn, b.mn); r.mx = std::fmax(r.mx, b.mx); r.min_nz = std::fmin(r.min_nz, b.min_nz);
-        r.min_diff = std::fmin(r.min_diff, b.min_diff); r.max_diff = std::fmax(r.max_diff, b.max_diff);
-        r.zero_runs += b.zero_runs; r.mask |= b.mask;
-    }
-    // B: extrema counts
-    { JtLaunch L(c, "astats:extrema_runs"); k_astats_b<T><<<gridA, 256, 0, c->stream>>>(x, n, r.mn, r.mx, d_counts); }
-    // C: exponential mean square min/max
     double *d_mm = jt_dalloc<double>(c, 2);
+    float *d_nf = jt_dalloc<float>(c, 1);
+    JT_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * (AS_HIST + 8), c->stream));
+    { JtLaunch L(c, "astats:sums_hist", 2);
+      k_astats_a<T><<<gridA, 256, 0, c->stream>>>(x, n, d_parts, d_hist);
+      k_astats_reduce<<<1, 32, 0, c->stream>>>(d_parts, gridA, d_total, d_mm, d_nf); }
+    // B: extrema counts
+    { JtLaunch L(c, "astats:extrema_runs"); k_astats_b<T><<<gridA, 256, 0, c->stream>>>(x, n, d_total, d_counts); }
+    // C: exponential mean square min/max
     const int BS = AS_BS; const int64_t nb = (n + BS - 1) / BS;
-    double h_mm[2] = {DBL_MAX, 0.0};
-    JT_CUDA(cudaMemcpyAsync(d_mm, h_mm, sizeof(h_mm), cudaMemcpyHostToDevice, c->stream));
     if (n > tc) {
         double *d_fin = jt_dalloc<double>(c, nb), *d_carry = jt_dalloc<double>(c, nb);
         JtLaunch L(c, "astats:rms_scan", 3);
@@ -371,9 +381,6 @@ static void astats_t(jt_ctx *c, const Sig &in, int64_t n, AstatsResult &out)
         k_astats_c2<T><<<(int)((nb + 63) / 64), 64, smemC, c->stream>>>(x, n, mult, d_carry, tc, d_mm);
     }
     // D: noise floor
-    float *d_nf = jt_dalloc<float>(c, 1);
-    float h_nf = FLT_MAX;
-    JT_CUDA(cudaMemcpyAsync(d_nf, &h_nf, sizeof(float), cudaMemcpyHostToDevice, c->stream));
     if (n >= tc) {
         const int64_t nbt = (n + tc - 1) / tc;
         float *d_bmin = jt_dalloc<float>(c, nbt); unsigned *d_bcnt = jt_dalloc<unsigned>(c, nbt);
@@ -384,16 +391,31 @@ static void astats_t(jt_ctx *c, const Sig &in, int64_t n, AstatsResult &out)
         k_astats_nf<T><<<jt_grid_for(nbt, 1, c->num_sms, 32), AS_NF_THREADS, smemD, c->stream>>>(x, n, tc, d_bmin, d_bcnt);
         k_astats_nf_reduce<<<1, 1024, 0, c->stream>>>(d_bmin, d_bcnt, nbt, d_nf, d_counts + 4);
     }
-    std::vector<unsigned long long> hist(AS_HIST + 8);
-    JT_CUDA(cudaMemcpyAsync(hist.data(), d_hist, sizeof(unsigned long long) * (AS_HIST + 8), cudaMemcpyDeviceToHost, c->stream));
-    JT_CUDA(cudaMemcpyAsync(h_mm, d_mm, sizeof(h_mm), cudaMemcpyDeviceToHost, c->stream));
-    JT_CUDA(cudaMemcpyAsync(&h_nf, d_nf, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-    JT_CUDA(cudaStreamSynchronize(c->stream));
+    AstatsHost *h = (AstatsHost *)jt_pinned_bytes(c, sizeof(AstatsHost));
+    pd.host = h;
+    JT_CUDA(cudaMemcpyAsync(&h->total, d_total, sizeof(AsPartA), cudaMemcpyDeviceToHost, c->stream));
+    JT_CUDA(cudaMemcpyAsync(h->hist, d_hist, sizeof(unsigned long long) * (AS_HIST + 8), cudaMemcpyDeviceToHost, c->stream));
+    JT_CUDA(cudaMemcpyAsync(h->mm, d_mm, sizeof(double) * 2, cudaMemcpyDeviceToHost, c->stream));
+    JT_CUDA(cudaMemcpyAsync(&h->nf, d_nf, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    pd.ev = jt_record_event(c);
+}
 
+void jt_astats_finish(jt_ctx *c, AstatsPending &pd, AstatsResult &out)
+{
+    for (int i = 0; i < JT_AS_COUNT; i++) out.v[i] = NAN;
+    out.overall_rms = out.overall_peak = NAN; out.nb_samples = 0;
+    if (pd.n <= 0 || !pd.host) return;
+    JT_CUDA(cudaEventSynchronize(pd.ev));
+    const AstatsHost *h = (const AstatsHost *)pd.host;
+    const AsPartA &r = h->total;
+    const unsigned long long *hist = h->hist;
+    const int64_t n = pd.n; const int tc = pd.tc;
+    const int maxbits = pd.fmt == JT_FMT_S16 ? 16 : pd.fmt == JT_FMT_FLT ? 32 : 64;
+    const float h_nf = h->nf;
     const double N = (double)n;
-    const double scale = in.fmt == JT_FMT_S16 ? 32767.0 : 1.0;
+    const double scale = pd.fmt == JT_FMT_S16 ? 32767.0 : 1.0;
     const double nmin = r.mn / scale, nmax = r.mx / scale;
-    double min_s2 = h_mm[0], max_s2 = h_mm[1];
+    double min_s2 = h->mm[0], max_s2 = h->mm[1];
     if (n <= tc) min_s2 = max_s2 = r.sumsq / N;      // af_astats.c: fewer samples than the window
     const double min_count = (double)hist[AS_HIST + 0], max_count = (double)hist[AS_HIST + 1];
     const double min_runs = (double)hist[AS_HIST + 2], max_runs = (double)hist[AS_HIST + 3];
@@ -427,13 +449,17 @@ static void astats_t(jt_ctx *c, const Sig &in, int64_t n, AstatsResult &out)
 #undef DB
 }
 
+void jt_astats_launch(jt_ctx *c, const Sig &in, int64_t n_upto, AstatsPending &pd)
+{
+    pd = AstatsPending();
+    const int64_t n = std::min(n_upto, in.n);
+    if (n <= 0) return;
+    if (in.fmt == JT_FMT_S16) astats_launch_t<int16_t>(c, in, n, pd);
+    else if (in.fmt == JT_FMT_FLT) astats_launch_t<float>(c, in, n, pd);
+    else astats_launch_t<double>(c, in, n, pd);
+}
+
 void jt_astats(jt_ctx *c, const Sig &in, int64_t n_upto, AstatsResult &out)
 {
-    int64_t n = std::min(n_upto, in.n);
-    for (int i = 0; i < JT_AS_COUNT; i++) out.v[i] = NAN;
-    out.overall_rms = out.overall_peak = NAN; out.nb_samples = 0;
-    if (n <= 0) return;
-    if (in.fmt == JT_FMT_S16) astats_t<int16_t>(c, in, n, out);
-    else if (in.fmt == JT_FMT_FLT) astats_t<float>(c, in, n, out);
-    else astats_t<double>(c, in, n, out);
+    AstatsPending pd; jt_astats_launch(c, in, n_upto, pd); jt_astats_finish(c, pd, out);
 }

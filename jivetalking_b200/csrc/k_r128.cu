@@ -167,13 +167,12 @@ static void run_ticks(jt_ctx *c, const Sig &in, int tick, int64_t n_ticks_total,
 static inline double loudness_of(double e) { return -0.691 + 10 * log10(e); }
 static inline int hist_pos(double l) { int p = (int)((l - ABS_THRES) * HIST_RES); return p < 0 ? 0 : p > HIST_SIZE - 1 ? HIST_SIZE - 1 : p; }
 
-void jt_ebur128(jt_ctx *c, const Sig &in, bool dualmono, bool true_peak, R128Result &out)
+void jt_ebur128_launch(jt_ctx *c, const Sig &in, bool dualmono, bool true_peak, R128Pending &pd)
 {
     if (in.rate % 10) JT_THROW(JT_ERR_UNSUPPORTED, "ebur128 at %d Hz (rate must be a multiple of 10)", in.rate);
-    const int tick = in.rate / 10;
-    const int64_t nt = in.n / tick;
-    out = R128Result();
-    out.n_ticks = nt;
+    pd = R128Pending();
+    pd.tick = in.rate / 10; pd.nt = in.n / pd.tick; pd.dualmono = dualmono; pd.true_peak = true_peak;
+    const int tick = pd.tick; const int64_t nt = pd.nt;
     if (nt <= 0) return;
     double *d_pow = jt_dalloc<double>(c, nt), *d_peak = jt_dalloc<double>(c, nt), *d_tp = jt_dalloc<double>(c, nt);
     KWeight kw = kweight_design(in.rate);
@@ -182,11 +181,24 @@ void jt_ebur128(jt_ctx *c, const Sig &in, bool dualmono, bool true_peak, R128Res
         if (in.rate == 192000) JT_CUDA(cudaMemcpyAsync(d_tp, d_peak, sizeof(double) * nt, cudaMemcpyDeviceToDevice, c->stream));
         else { SwrPlan p = jt_swr_plan(in.rate, 192000); jt_swr_tick_absmax(c, in, p, tick, nt, d_tp); }
     }
-    std::vector<double> hp(nt), hk(nt), ht(nt, 0.0);
-    JT_CUDA(cudaMemcpyAsync(hp.data(), d_pow, sizeof(double) * nt, cudaMemcpyDeviceToHost, c->stream));
-    JT_CUDA(cudaMemcpyAsync(hk.data(), d_peak, sizeof(double) * nt, cudaMemcpyDeviceToHost, c->stream));
-    if (true_peak) JT_CUDA(cudaMemcpyAsync(ht.data(), d_tp, sizeof(double) * nt, cudaMemcpyDeviceToHost, c->stream));
-    JT_CUDA(cudaStreamSynchronize(c->stream));
+    pd.hp = jt_pinned<double>(c, nt); pd.hk = jt_pinned<double>(c, nt); pd.ht = jt_pinned<double>(c, nt);
+    JT_CUDA(cudaMemcpyAsync(pd.hp, d_pow, sizeof(double) * nt, cudaMemcpyDeviceToHost, c->stream));
+    JT_CUDA(cudaMemcpyAsync(pd.hk, d_peak, sizeof(double) * nt, cudaMemcpyDeviceToHost, c->stream));
+    if (true_peak) JT_CUDA(cudaMemcpyAsync(pd.ht, d_tp, sizeof(double) * nt, cudaMemcpyDeviceToHost, c->stream));
+    pd.ev = jt_record_event(c);
+}
+
+void jt_ebur128_finish(jt_ctx *c, R128Pending &pd, R128Result &out)
+{
+    out = R128Result();
+    const int64_t nt = pd.nt; const int tick = pd.tick; const bool dualmono = pd.dualmono;
+    out.n_ticks = nt;
+    if (nt <= 0) return;
+    JT_CUDA(cudaEventSynchronize(pd.ev));
+    const double *hp = pd.hp, *hk = pd.hk;
+    std::vector<double> zero_tp;
+    const double *ht = pd.ht;
+    if (!pd.true_peak) { zero_tp.assign(nt, 0.0); ht = zero_tp.data(); }
 
     // host: f_ebur128.c filter_frame() tail, once per 100 ms
     JtHost hfin(c, "r128_finalize");
@@ -246,21 +258,29 @@ void jt_ebur128(jt_ctx *c, const Sig &in, bool dualmono, bool true_peak, R128Res
 // ---------------------------------------------------------------------------------------
 // loudnorm's meter: libavfilter/ebur128.c (libebur128 port), block-list gating
 // ---------------------------------------------------------------------------------------
-void jt_loudnorm_meter(jt_ctx *c, const Sig &in0, bool dual_mono, LoudnormMeter &out)
+void jt_loudnorm_meter_launch(jt_ctx *c, const Sig &in, bool dual_mono, LoudnormPending &pd)
 {
-    Sig in = in0;
-    const int s100 = (in.rate + 5) / 10;
-    const int64_t nfull = in.n / s100;
-    const int64_t nt = (in.n + s100 - 1) / s100;            // last partial tick only feeds the sample peak
+    pd = LoudnormPending();
+    pd.s100 = (in.rate + 5) / 10; pd.dual_mono = dual_mono;
+    pd.nfull = in.n / pd.s100;
+    pd.nt = (in.n + pd.s100 - 1) / pd.s100;                // last partial tick only feeds the sample peak
+    if (pd.nt <= 0) return;
+    double *d_pow = jt_dalloc<double>(c, pd.nt), *d_peak = jt_dalloc<double>(c, pd.nt);
+    KWeight kw = kweight_design(in.rate);
+    run_ticks<1>(c, in, pd.s100, pd.nt, kw, d_pow, d_peak);
+    pd.hp = jt_pinned<double>(c, pd.nt); pd.hk = jt_pinned<double>(c, pd.nt);
+    JT_CUDA(cudaMemcpyAsync(pd.hp, d_pow, sizeof(double) * pd.nt, cudaMemcpyDeviceToHost, c->stream));
+    JT_CUDA(cudaMemcpyAsync(pd.hk, d_peak, sizeof(double) * pd.nt, cudaMemcpyDeviceToHost, c->stream));
+    pd.ev = jt_record_event(c);
+}
+
+void jt_loudnorm_meter_finish(jt_ctx *c, LoudnormPending &pd, LoudnormMeter &out)
+{
+    const int s100 = pd.s100; const int64_t nfull = pd.nfull, nt = pd.nt; const bool dual_mono = pd.dual_mono;
     out.I = -HUGE_VAL; out.LRA = 0; out.thresh = -70.0; out.sample_peak = 0;
     if (nt <= 0) return;
-    double *d_pow = jt_dalloc<double>(c, nt), *d_peak = jt_dalloc<double>(c, nt);
-    KWeight kw = kweight_design(in.rate);
-    run_ticks<1>(c, in, s100, nt, kw, d_pow, d_peak);
-    std::vector<double> hp(nt), hk(nt);
-    JT_CUDA(cudaMemcpyAsync(hp.data(), d_pow, sizeof(double) * nt, cudaMemcpyDeviceToHost, c->stream));
-    JT_CUDA(cudaMemcpyAsync(hk.data(), d_peak, sizeof(double) * nt, cudaMemcpyDeviceToHost, c->stream));
-    JT_CUDA(cudaStreamSynchronize(c->stream));
+    JT_CUDA(cudaEventSynchronize(pd.ev));
+    const double *hp = pd.hp, *hk = pd.hk;
     for (int64_t k = 0; k < nt; k++) out.sample_peak = std::max(out.sample_peak, hk[k]);
 
     const double wgt = dual_mono ? 2.0 : 1.0;
@@ -297,4 +317,13 @@ void jt_loudnorm_meter(jt_ctx *c, const Sig &in0, bool dual_mono, LoudnormMeter 
             out.LRA = (10 * log10(h) - 0.691) - (10 * log10(l) - 0.691);
         }
     }
+}
+
+void jt_ebur128(jt_ctx *c, const Sig &in, bool dualmono, bool true_peak, R128Result &out)
+{
+    R128Pending pd; jt_ebur128_launch(c, in, dualmono, true_peak, pd); jt_ebur128_finish(c, pd, out);
+}
+void jt_loudnorm_meter(jt_ctx *c, const Sig &in, bool dual_mono, LoudnormMeter &out)
+{
+    LoudnormPending pd; jt_loudnorm_meter_launch(c, in, dual_mono, pd); jt_loudnorm_meter_finish(c, pd, out);
 }

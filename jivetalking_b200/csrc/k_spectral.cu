@@ -175,40 +175,43 @@ k_spectral_flux(const float *__restrict__ mags, int size, int64_t n_items, const
     }
 }
 
-void jt_aspectralstats(jt_ctx *c, const Sig &in0, int win, std::vector<float> &rows, int64_t &n_hops, const std::vector<int64_t> *wanted)
+void jt_aspectralstats_launch(jt_ctx *c, const Sig &in0, int win, const std::vector<int64_t> *wanted, SpectralPending &pd)
 {
+    pd = SpectralPending();
     Sig in = jt_convert(c, in0, JT_FMT_FLT);
     const int hop = win / 2;
-    n_hops = (in.n + hop - 1) / hop;
-    rows.assign((size_t)std::max<int64_t>(n_hops, 0) * JT_SP_COUNT, 0.f);
-    if (n_hops <= 0) return;
+    pd.n_hops = (in.n + hop - 1) / hop;
+    pd.sparse = wanted != nullptr;
+    if (pd.n_hops <= 0) return;
     if (win < 1024 || (win & (win - 1)) || (win / 2) % SP_THREADS || win / 2 / SP_THREADS > 4)
         JT_THROW(JT_ERR_UNSUPPORTED, "aspectralstats win_size %d", win);
     // Only hops a sink frame will ever show are computed (the reference sees one hop per 100 ms frame,
     // SURVEY 7.3), each with its predecessor for the flux term.
-    std::vector<int64_t> items, prev;
+    std::vector<int64_t> prev;
     if (wanted) {
         std::vector<int64_t> w;
-        for (int64_t h : *wanted) if (h >= 0 && h < n_hops) { w.push_back(h); if (h > 0) w.push_back(h - 1); }
+        for (int64_t h : *wanted) if (h >= 0 && h < pd.n_hops) { w.push_back(h); if (h > 0) w.push_back(h - 1); }
         std::sort(w.begin(), w.end());
         w.erase(std::unique(w.begin(), w.end()), w.end());
-        items.swap(w);
-        prev.resize(items.size());
-        for (size_t i = 0; i < items.size(); i++) prev[i] = (i > 0 && items[i - 1] == items[i] - 1) ? (int64_t)i - 1 : -1;
-        if (items.empty()) return;
+        pd.items.swap(w);
+        prev.resize(pd.items.size());
+        for (size_t i = 0; i < pd.items.size(); i++) prev[i] = (i > 0 && pd.items[i - 1] == pd.items[i] - 1) ? (int64_t)i - 1 : -1;
+        if (pd.items.empty()) return;
     }
-    const int64_t n_items = wanted ? (int64_t)items.size() : n_hops;
+    const int64_t n_items = wanted ? (int64_t)pd.items.size() : pd.n_hops;
+    pd.n_items = n_items;
     std::vector<float2> tw(win / 2); std::vector<float> lut(win);
     for (int k = 0; k < win / 2; k++) { double a = -2.0 * M_PI * k / win; tw[k] = make_float2((float)cos(a), (float)sin(a)); }
     for (int i = 0; i < win; i++) lut[i] = (float)(.5 * (1 - cos(2 * M_PI * i / (win - 1))));
-    float2 *d_tw = jt_dalloc<float2>(c, win / 2); float *d_lut = jt_dalloc<float>(c, win);
-    JT_CUDA(cudaMemcpyAsync(d_tw, tw.data(), sizeof(float2) * win / 2, cudaMemcpyHostToDevice, c->stream));
-    JT_CUDA(cudaMemcpyAsync(d_lut, lut.data(), sizeof(float) * win, cudaMemcpyHostToDevice, c->stream));
+    const float2 *d_tw = jt_dev_table(c, "spectral_tw", tw); const float *d_lut = jt_dev_table(c, "spectral_hann", lut);
     int64_t *d_items = nullptr, *d_prev = nullptr;
     if (wanted) {
-        d_items = jt_dalloc<int64_t>(c, n_items); d_prev = jt_dalloc<int64_t>(c, n_items);
-        JT_CUDA(cudaMemcpyAsync(d_items, items.data(), sizeof(int64_t) * n_items, cudaMemcpyHostToDevice, c->stream));
-        JT_CUDA(cudaMemcpyAsync(d_prev, prev.data(), sizeof(int64_t) * n_items, cudaMemcpyHostToDevice, c->stream));
+        // the two index lists go through pinned staging so that the copy is truly asynchronous
+        int64_t *h_idx = jt_pinned<int64_t>(c, 2 * (size_t)n_items);
+        memcpy(h_idx, pd.items.data(), sizeof(int64_t) * n_items);
+        memcpy(h_idx + n_items, prev.data(), sizeof(int64_t) * n_items);
+        d_items = jt_dalloc<int64_t>(c, 2 * (size_t)n_items); d_prev = d_items + n_items;
+        JT_CUDA(cudaMemcpyAsync(d_items, h_idx, sizeof(int64_t) * 2 * n_items, cudaMemcpyHostToDevice, c->stream));
     }
     float *d_mags = jt_dalloc<float>(c, (size_t)n_items * (win / 2));
     float *d_rows = jt_dalloc<float>(c, (size_t)n_items * JT_SP_COUNT);
@@ -218,13 +221,22 @@ void jt_aspectralstats(jt_ctx *c, const Sig &in0, int win, std::vector<float> &r
         k_spectral<<<grid, SP_THREADS, sizeof(float2) * win, c->stream>>>((const float *)in.d, in.n, win, in.rate, n_items, d_items, d_tw, d_lut, d_mags, d_rows);
         k_spectral_flux<<<grid, 256, 0, c->stream>>>(d_mags, win / 2, n_items, d_prev, d_rows);
     }
-    if (!wanted) {
-        JT_CUDA(cudaMemcpyAsync(rows.data(), d_rows, sizeof(float) * rows.size(), cudaMemcpyDeviceToHost, c->stream));
-        JT_CUDA(cudaStreamSynchronize(c->stream));
-    } else {
-        std::vector<float> packed((size_t)n_items * JT_SP_COUNT);
-        JT_CUDA(cudaMemcpyAsync(packed.data(), d_rows, sizeof(float) * packed.size(), cudaMemcpyDeviceToHost, c->stream));
-        JT_CUDA(cudaStreamSynchronize(c->stream));
-        for (int64_t i = 0; i < n_items; i++) memcpy(&rows[(size_t)items[i] * JT_SP_COUNT], &packed[(size_t)i * JT_SP_COUNT], sizeof(float) * JT_SP_COUNT);
-    }
+    pd.h_rows = jt_pinned<float>(c, (size_t)n_items * JT_SP_COUNT);
+    JT_CUDA(cudaMemcpyAsync(pd.h_rows, d_rows, sizeof(float) * (size_t)n_items * JT_SP_COUNT, cudaMemcpyDeviceToHost, c->stream));
+    pd.ev = jt_record_event(c);
+}
+
+void jt_aspectralstats_finish(jt_ctx *c, SpectralPending &pd, std::vector<float> &rows, int64_t &n_hops)
+{
+    n_hops = pd.n_hops;
+    rows.assign((size_t)std::max<int64_t>(n_hops, 0) * JT_SP_COUNT, 0.f);
+    if (n_hops <= 0 || pd.n_items <= 0 || !pd.h_rows) return;
+    JT_CUDA(cudaEventSynchronize(pd.ev));
+    if (!pd.sparse) memcpy(rows.data(), pd.h_rows, sizeof(float) * rows.size());
+    else for (int64_t i = 0; i < pd.n_items; i++) memcpy(&rows[(size_t)pd.items[i] * JT_SP_COUNT], &pd.h_rows[(size_t)i * JT_SP_COUNT], sizeof(float) * JT_SP_COUNT);
+}
+
+void jt_aspectralstats(jt_ctx *c, const Sig &in0, int win, std::vector<float> &rows, int64_t &n_hops, const std::vector<int64_t> *wanted)
+{
+    SpectralPending pd; jt_aspectralstats_launch(c, in0, win, wanted, pd); jt_aspectralstats_finish(c, pd, rows, n_hops);
 }

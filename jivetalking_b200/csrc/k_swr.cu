@@ -390,12 +390,9 @@ template <class TW>
 static const TW *device_bank(jt_ctx *c, const SwrPlan &p)
 {
     const size_t nb = (size_t)p.phase_count * p.filter_length;
-    TW *d_bank = jt_dalloc<TW>(c, nb);
     std::vector<TW> hb(nb);
     for (size_t i = 0; i < nb; i++) hb[i] = (TW)p.bank[i];
-    JT_CUDA(cudaMemcpyAsync(d_bank, hb.data(), nb * sizeof(TW), cudaMemcpyHostToDevice, c->stream));
-    JT_CUDA(cudaStreamSynchronize(c->stream));   // hb is a stack-lifetime staging buffer
-    return d_bank;
+    return jt_dev_table(c, sizeof(TW) == 4 ? "swr_bank_f32" : "swr_bank_f64", hb);
 }
 
 static bool slot_path_ok(const SwrPlan &p)
@@ -477,12 +474,7 @@ template <class TIN, class TW, int MODE>
 static void launch_generic(jt_ctx *c, const Sig &in, const SwrPlan &p, int64_t n_out, TW *out,
                            double *tick_max, int tick, int64_t n_ticks)
 {
-    const size_t nb = (size_t)p.phase_count * p.filter_length;
-    TW *d_bank = jt_dalloc<TW>(c, nb);
-    std::vector<TW> hb(nb);
-    for (size_t i = 0; i < nb; i++) hb[i] = (TW)p.bank[i];
-    JT_CUDA(cudaMemcpyAsync(d_bank, hb.data(), nb * sizeof(TW), cudaMemcpyHostToDevice, c->stream));
-    JT_CUDA(cudaStreamSynchronize(c->stream));   // hb is a stack-lifetime staging buffer
+    const TW *d_bank = device_bank<TW>(c, p);
     const int64_t n_periods = (n_out + p.phase_count - 1) / p.phase_count;
     const int span = 32 * p.div + p.filter_length + p.div;
     const size_t smem = (size_t)(span + (span >> 5) + 2) * sizeof(TW);
