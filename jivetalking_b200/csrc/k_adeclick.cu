@@ -157,16 +157,19 @@ k_dc_interp(const double *__restrict__ x, double *__restrict__ y, int64_t n, int
         s_pa[p] = (unsigned char)a; s_pb[p] = (unsigned char)(p - a * (a - 1) / 2 + 1);
     }
     __syncthreads();
-    const size_t per_warp = ((size_t)bw * bw + 3 * (size_t)bw) * sizeof(double);
+    const size_t per_warp = ((size_t)bw * bw + 3 * (size_t)bw + (size_t)((K.nwords + 1) / 2)) * sizeof(double);
     double *ring = (double *)(smem_raw + (size_t)warp * per_warp);
-    double *kc = ring + (size_t)bw * bw, *aux = kc + bw, *oring = aux + bw;
+    double *kc = ring + (size_t)bw * bw, *aux = kc + bw, *vring = aux + bw;     // vring: right-hand side / forward-substituted values of rows k .. k+order
+    unsigned *sbits = (unsigned *)(vring + bw);                                  // the window's click bitmap
     const int64_t gw = (int64_t)blockIdx.x * DC_WARPS + warp;
     double *S = scratch + (size_t)gw * scratch_per_warp;
     // scratch layout: Lg[nmax][order], Dg[nmax], vec[nmax], outv[nmax], idx (as int)[nmax]
     const size_t nmax = (size_t)K.W;
-    double *Lg = S, *Dg = Lg + nmax * order, *vec = Dg + nmax, *outv = vec + nmax;
+    double *Lg = S, *yd = Lg + nmax * order, *vec = yd + nmax, *outv = vec + nmax;      // yd[i] = y_i / D_i
     int *idx = (int *)(outv + nmax), *am = idx + 2 * ((nmax + 1) / 2);
-#define RING(j, i) ring[(size_t)((j) % bw) * bw + ((i) % bw)]
+    // ring slot of matrix index k + a given rk = k % bw (a <= order < bw): no integer division in the inner loops
+#define WRAP(v) ((v) >= bw ? (v) - bw : (v))
+#define RINGS(r, cidx) ring[(size_t)(r) * bw + (cidx)]
 
     for (;;) {
         int64_t w = 0;
@@ -181,6 +184,7 @@ k_dc_interp(const double *__restrict__ x, double *__restrict__ y, int64_t n, int
         for (int w0 = 0; w0 < K.nwords; w0 += 32) {
             const int wd = w0 + lane;
             const unsigned m = wd < K.nwords ? bits_in[w * K.nwords + wd] : 0u;
+            if (wd < K.nwords) sbits[wd] = m;
             const int cnt = __popc(m);
             int incl = cnt;
             for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
@@ -198,34 +202,45 @@ k_dc_interp(const double *__restrict__ x, double *__restrict__ y, int64_t n, int
             aux[l] = jdmul(v, 1.);
         }
         __syncwarp();
-        // right-hand side: known neighbours of every click
-        for (int i = lane; i < nclk; i += 32) {
-            const int ii = idx[i];
-            double value = 0.;
-            for (int j = -order; j <= order; j++) {
-                const int p = ii - j;
-                const unsigned wordv = bits_in[w * K.nwords + (p >> 5)];
-                if (!((wordv >> (p & 31)) & 1u)) value = jdsub(value, jdmul(dc_sample(x, n, w, p, K), aux[j < 0 ? -j : j]));
+        // right-hand side: known neighbours of every click, j = -order .. order (sample p = ii - j descending).
+        // Interior windows read the stream directly; only the first / last windows need the fifo edge rules.
+        {
+            const int64_t f0 = w * (int64_t)K.hop, s_base = f0 - K.skip;
+            const bool interior = f0 + K.W <= (int64_t)K.skip + n && s_base >= 0 && s_base + K.W <= n;
+            const double *xw = x + s_base;
+            for (int i = lane; i < nclk; i += 32) {
+                const int ii = idx[i];
+                double value = 0.;
+                for (int j = -order; j <= order; j++) {
+                    const int p = ii - j;
+                    if (!((sbits[p >> 5] >> (p & 31)) & 1u)) {
+                        const double xs = interior ? xw[p] : dc_sample(x, n, w, p, K);
+                        value = jdsub(value, jdmul(xs, aux[j < 0 ? -j : j]));
+                    }
+                }
+                vec[i] = value;
             }
-            vec[i] = value;
         }
         __syncwarp();
-        // rows 0 .. order enter the ring: A(j,i) = aux[idx_j - idx_i] inside the band, else 0
-        auto load_row = [&](int j) {
+        // row j enters the ring (slot rj): A(j,i) = aux[idx_j - idx_i] for the earlier clicks i it couples to
+        // (at most `order` samples away); slots outside that profile are never read.  Its right-hand side enters vring.
+        auto load_row = [&](int j, int rj) {
             if (j >= nclk) return;
             const int ij = idx[j];
-            for (int t = lane; t < bw; t += 32) {
-                const int i = j - t;
-                if (i < 0) break;
-                const int d = ij - idx[i];
-                RING(j, i) = d <= order ? aux[d] : 0.0;
+            for (int t0 = 0; t0 < bw; t0 += 32) {
+                const int t = t0 + lane, i = j - t;
+                const int d = (t < bw && i >= 0) ? ij - idx[i] : order + 1;
+                if (d <= order) RINGS(rj, WRAP(rj + bw - t)) = aux[d];
+                if (!__ballot_sync(0xffffffffu, d <= order && lane == 31)) break;      // sorted: nothing further couples
             }
+            if (lane == 0) vring[rj] = vec[j];
         };
-        for (int j = 0; j <= order; j++) load_row(j);
+        for (int j = 0; j <= order; j++) load_row(j, j);
         __syncwarp();
         bool ok = true;
+        int rk = 0;
         for (int k = 0; k < nclk; k++) {
-            const double Dk = RING(k, k);
+            const double Dk = RINGS(rk, rk);
             if (Dk == 0.) { ok = false; break; }
             // rows coupled to click k: later clicks at most `order` samples away.  Everything below them in
             // column k is an exact zero of the factor (two clicks further apart never couple, fill-in stays
@@ -236,44 +251,59 @@ k_dc_interp(const double *__restrict__ x, double *__restrict__ y, int64_t n, int
                 const bool c0 = j0 < nclk && idx[j0] - ik <= order, c1 = j1 < nclk && j1 - k <= order && idx[j1] - ik <= order;
                 amax = __popc(__ballot_sync(0xffffffffu, c0)) + __popc(__ballot_sync(0xffffffffu, c1));
             }
-            if (lane == 0) am[k] = amax;
-            const double yk = vec[k];
+            const double yk = vring[rk];
             // column k: L(j,k) = A'(j,k) / D_k ; forward substitution v_j -= L(j,k) * y_k
             for (int a = lane + 1; a <= amax; a += 32) {
-                const double L = RING(k + a, k) / Dk;
-                RING(k + a, k) = L;
+                const int ra = WRAP(rk + a);
+                const double L = RINGS(ra, rk) / Dk;
+                RINGS(ra, rk) = L;
                 Lg[(size_t)k * order + (a - 1)] = L;
-                vec[k + a] = jdsub(vec[k + a], jdmul(L, yk));
+                vring[ra] = jdsub(vring[ra], jdmul(L, yk));
             }
-            if (lane == 0) Dg[k] = Dk;
+            if (lane == 0) { yd[k] = yk / Dk; am[k] = amax; }
             __syncwarp();
             // trailing update: A'(k+a, k+b) -= (D_k * L(k+b,k)) * L(k+a,k), 1 <= b <= a <= amax
             const int npairs = amax * (amax + 1) / 2;
             for (int p = lane; p < npairs; p += 32) {
-                const int a = s_pa[p], b = s_pb[p];
-                const double Lb = RING(k + b, k), La = RING(k + a, k);
-                RING(k + a, k + b) = jdsub(RING(k + a, k + b), jdmul(jdmul(Dk, Lb), La));
+                const int ra = WRAP(rk + s_pa[p]), rb = WRAP(rk + s_pb[p]);
+                const double Lb = RINGS(rb, rk), La = RINGS(ra, rk);
+                RINGS(ra, rb) = jdsub(RINGS(ra, rb), jdmul(jdmul(Dk, Lb), La));
             }
+            load_row(k + bw, rk);           // row k+order+1 takes the slot row k leaves (no trailing update touches it)
             __syncwarp();
-            load_row(k + bw);               // row k+order+1 takes the slot row k leaves
-            __syncwarp();
+            rk = rk + 1 == bw ? 0 : rk + 1;
         }
         if (!ok) continue;                  // factorisation hit a zero pivot: af_adeclick.c leaves the window as is
-        // back substitution: out_i = y_i / D_i - sum_{j>i} L(j,i) * out_j, j ascending
-        __syncwarp();
-        for (int i = nclk - 1; i >= 0; i--) {
-            const int amax = am[i];
-            double prod0 = 0.0, prod1 = 0.0;
-            if (lane < amax) prod0 = jdmul(Lg[(size_t)i * order + lane], oring[(i + 1 + lane) % bw]);
-            if (lane + 32 < amax) prod1 = jdmul(Lg[(size_t)i * order + lane + 32], oring[(i + 33 + lane) % bw]);
-            double o = vec[i] / Dg[i];
-            for (int a = 0; a < amax; a++) {
-                const double pr = __shfl_sync(0xffffffffu, a < 32 ? prod0 : prod1, a & 31);
-                o = jdsub(o, pr);
+        // back substitution: out_i = y_i / D_i - sum_{j>i} L(j,i) * out_j, j ascending.  Lane a keeps out_{i+1+a}
+        // (and out_{i+33+a}) in registers; moving to i-1 shifts them up by one lane.
+        {
+            double win0 = 0.0, win1 = 0.0;
+            int amax = am[nclk - 1];
+            double o_y = yd[nclk - 1];
+            double L0 = lane < amax ? Lg[(size_t)(nclk - 1) * order + lane] : 0.0;
+            double L1 = lane + 32 < amax ? Lg[(size_t)(nclk - 1) * order + lane + 32] : 0.0;
+            for (int i = nclk - 1; i >= 0; i--) {
+                // next row's operands are fetched before this row's dependent chain starts
+                int amax_n = 0; double oy_n = 0.0, L0n = 0.0, L1n = 0.0;
+                if (i > 0) {
+                    amax_n = am[i - 1]; oy_n = yd[i - 1];
+                    if (lane < amax_n) L0n = Lg[(size_t)(i - 1) * order + lane];
+                    if (lane + 32 < amax_n) L1n = Lg[(size_t)(i - 1) * order + lane + 32];
+                }
+                const double prod0 = jdmul(L0, win0), prod1 = jdmul(L1, win1);
+                double o = o_y;
+                for (int a = 0; a < amax; a++) {
+                    const double pr = __shfl_sync(0xffffffffu, a < 32 ? prod0 : prod1, a & 31);
+                    o = jdsub(o, pr);
+                }
+                if (lane == 0) outv[i] = o;
+                const double carry = __shfl_sync(0xffffffffu, win0, 31);
+                win1 = __shfl_up_sync(0xffffffffu, win1, 1); if (lane == 0) win1 = carry;
+                win0 = __shfl_up_sync(0xffffffffu, win0, 1); if (lane == 0) win0 = o;
+                amax = amax_n; o_y = oy_n; L0 = L0n; L1 = L1n;
             }
-            if (lane == 0) { oring[i % bw] = o; outv[i] = o; }
-            __syncwarp();
         }
+        __syncwarp();
         // only the hop-sized middle of the window is emitted (overlap-save)
         for (int i = lane; i < nclk; i += 32) {
             const int p = idx[i] - K.skip;
@@ -281,7 +311,8 @@ k_dc_interp(const double *__restrict__ x, double *__restrict__ y, int64_t n, int
         }
         __syncwarp();
     }
-#undef RING
+#undef RINGS
+#undef WRAP
 }
 
 Sig jt_adeclick(jt_ctx *c, const Sig &in, double w_ms, double overlap_pct, double ar_pct, double threshold, double burst_pct, int method_save)
@@ -311,7 +342,7 @@ Sig jt_adeclick(jt_ctx *c, const Sig &in, double w_ms, double overlap_pct, doubl
     const size_t smemA = sizeof(double) * K.W, smemC = sizeof(double) * (K.W + K.bw);
     JT_CUDA(cudaFuncSetAttribute(k_dc_autocorr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
     JT_CUDA(cudaFuncSetAttribute(k_dc_detect, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC));
-    const size_t per_warp = ((size_t)K.bw * K.bw + 3 * (size_t)K.bw) * sizeof(double);
+    const size_t per_warp = ((size_t)K.bw * K.bw + 3 * (size_t)K.bw + (size_t)((K.nwords + 1) / 2)) * sizeof(double);
     const size_t smemE = per_warp * DC_WARPS;
     JT_CUDA(cudaFuncSetAttribute(k_dc_interp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemE));
     int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / (smemE + 4096)));

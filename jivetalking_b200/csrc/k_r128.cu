@@ -69,23 +69,32 @@ k_r128_ticks(const TIN *__restrict__ x, int64_t n, int tick, int64_t n_ticks_tot
     in.init(smem + (size_t)(threadIdx.x >> 5) * LaneStage<TIN, R, 2>::WARP_BYTES, x + begin, end - begin);
     double x1 = 0, x2 = 0, y1 = 0, y2 = 0, z1 = 0, z2 = 0;      // STRUCT 0
     double v1 = 0, v2 = 0, v3 = 0, v4 = 0;                        // STRUCT 1
+    // One warp per scheduler: the walk is bound by the dependent-issue latency of f64 (8 cycles), so the
+    // recurrences are written with the newest state entering LAST -- the feed-forward part and the older
+    // feedback terms are off the carried chain, which is then one DFMA per biquad per sample.
     auto step = [&](double x0) -> double {
         if (STRUCT == 0) {
-            double y0 = x0 * kw.pb0 + x1 * kw.pb1 + x2 * kw.pb2 - y1 * kw.pa1 - y2 * kw.pa2;
+            const double t = fma(x2, kw.pb2, fma(x1, kw.pb1, x0 * kw.pb0));
+            const double y0 = fma(-y1, kw.pa1, fma(-y2, kw.pa2, t));
             x2 = x1; x1 = x0;
-            double z0 = y0 * kw.rb0 + y1 * kw.rb1 + y2 * kw.rb2 - z1 * kw.ra1 - z2 * kw.ra2;
+            const double s = fma(y2, kw.rb2, fma(y1, kw.rb1, y0 * kw.rb0));
+            const double z0 = fma(-z1, kw.ra1, fma(-z2, kw.ra2, s));
             y2 = y1; y1 = y0; z2 = z1; z1 = z0;
             return z0;
         } else {
-            double v0 = x0 - kw.a[1] * v1 - kw.a[2] * v2 - kw.a[3] * v3 - kw.a[4] * v4;
-            double o = kw.b[0] * v0 + kw.b[1] * v1 + kw.b[2] * v2 + kw.b[3] * v3 + kw.b[4] * v4;
+            const double v0 = fma(-kw.a[1], v1, fma(-kw.a[2], v2, fma(-kw.a[3], v3, fma(-kw.a[4], v4, x0))));
+            const double o = fma(kw.b[0], v0, fma(kw.b[1], v1, fma(kw.b[2], v2, fma(kw.b[3], v3, kw.b[4] * v4))));
             v4 = v3; v3 = v2; v2 = v1; v1 = v0;
             return o;
         }
     };
+    // sample peak as an integer maximum of the magnitude bits (non-negative doubles order like their bit
+    // patterns; f64 min / max issue at a third of the add rate, profiles/ubench_r1.txt)
+    unsigned long long pkb = 0ull;
+    auto peak_in = [&](double v) { const unsigned long long b = (unsigned long long)__double_as_longlong(v) & 0x7fffffffffffffffull; pkb = b > pkb ? b : pkb; };
     const int64_t warm_end = k0 * (int64_t)tick;
     int64_t k = k0, tick_end = min((k0 + 1) * (int64_t)tick, n);
-    double acc = 0.0, pk = 0.0;
+    double acc = 0.0;
     in.prime();
     for (int tile = 0; tile < in.ntiles; tile++) {
         in.prefetch();
@@ -115,18 +124,18 @@ k_r128_ticks(const TIN *__restrict__ x, int64_t n, int tick, int64_t n_ticks_tot
 #pragma unroll
                     for (int j = 0; j < 8; j++) v[j] = jt_as_f64(row[q + r + j]);
 #pragma unroll
-                    for (int j = 0; j < 8; j++) { const double z = step(v[j]); acc = fma(z, z, acc); pk = fmax(pk, fabs(v[j])); }
+                    for (int j = 0; j < 8; j++) { const double z = step(v[j]); acc = fma(z, z, acc); peak_in(v[j]); }
                 }
                 for (; r < run; r++) {
                     const double x0 = jt_as_f64(row[q + r]);
                     const double z = step(x0);
                     acc = fma(z, z, acc);
-                    pk = fmax(pk, fabs(x0));
+                    peak_in(x0);
                 }
                 q += run; i += run;
                 if (i == tick_end) {
-                    tick_pow[k] = acc; tick_peak[k] = pk;
-                    acc = 0.0; pk = 0.0; k++;
+                    tick_pow[k] = acc; tick_peak[k] = __longlong_as_double((long long)pkb);
+                    acc = 0.0; pkb = 0ull; k++;
                     tick_end = min((k + 1) * (int64_t)tick, n);
                 }
             }

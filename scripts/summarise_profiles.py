@@ -12,7 +12,7 @@ G = os.path.join(ROOT, "gpurun_out")
 P = os.path.join(ROOT, "profiles")
 os.makedirs(P, exist_ok=True)
 out = [f"# ncu summary {tag}", "",
-       "Command: `ncu --metrics gpu__time_duration.sum --clock-control none --csv python bench.py --minutes 10 --steps 1 --warmup 1 --no-cpu-baseline`",
+       "Command: `ncu --metrics gpu__time_duration.sum --clock-control none --csv python bench.py --minutes <M> --steps 1 --warmup 1 --no-cpu-baseline`",
        "(per-launch times are cold-cache and serialised: compare SHARES with bench.py's `kernels_ms_per_step`, not absolutes)", ""]
 src = os.path.join(G, f"launches_{tag}.csv")
 if os.path.exists(src):
@@ -51,7 +51,7 @@ for f in sorted(os.listdir(G)):
         if len(r) < 3:
             continue
         hdr, units, vals = r[0], r[1], r[2]
-        out += [f"## `ncu --set full` : {f[len('prof_' + tag + '_'):-8]} (one launch, 10 min stream)", "", "| metric | value |", "|---|---:|"]
+        out += [f"## `ncu --set full` : {f[len('prof_' + tag + '_'):-8]} (one launch)", "", "| metric | value |", "|---|---:|"]
         for w in WANT:
             if w in hdr:
                 i = hdr.index(w)
