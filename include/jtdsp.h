@@ -146,6 +146,24 @@ int jt_analyse(jt_ctx *ctx, const void *pcm_in, int64_t n_frames, int sample_rat
                int sample_fmt, int frame_size,
                jt_measurements *out, jt_interval *intervals, int64_t interval_cap, int64_t *n_intervals);
 
+/* ---- one long stream over several GPUs (BASELINE.json configs[3]) -------------------------------
+ * Each rank analyses one contiguous chunk of the stream: frames [own_first, own_first + owned), handed over
+ * inside a local buffer [local_first, local_first + n_local) that adds context on both sides (one
+ * jt_analyse_chunk_unit of left context in mid-stream, >= 4096 frames of right context before the stream's
+ * end; own_first, local_first and every chunk length but the last are multiples of the unit).  The result is
+ * an opaque, position-independent blob of MERGEABLE values (per-tick K-weighted energy / sample peak / true
+ * peak, per-decoder-frame raw sums, the spectral rows its sink frames show, partial astats).  The ranks
+ * exchange blobs with one all-gather (ncclAllGather / MPI_Allgather on bytes) and any of them calls
+ * jt_analyse_merge (host only) to obtain what jt_analyse returns for the whole stream: windows, gating, LRA
+ * and intervals are evaluated on the merged values, so they do not depend on the chunking. */
+int64_t jt_analyse_chunk_unit(int sample_rate);
+int64_t jt_analyse_chunk_bytes(int64_t owned_frames, int sample_rate);        /* upper bound of a blob */
+int jt_analyse_chunk(jt_ctx *ctx, const void *pcm_local, int64_t n_local, int sample_rate, int channels, int sample_fmt,
+                     int64_t local_first, int64_t own_first, int64_t owned, int64_t total_frames,
+                     void *blob, int64_t blob_cap, int64_t *blob_bytes);
+int jt_analyse_merge(int n_chunks, const void *const *blobs,
+                     jt_measurements *out, jt_interval *intervals, int64_t interval_cap, int64_t *n_intervals);
+
 /* 17-band region RMS (measureSpeechBandRMS analyser_bands.go:33-104): n_bands (lo,hi) pairs
  * over region [start_s, start_s+duration_s); rms_db[i] = lavfi.astats.Overall.RMS_level,
  * found[i] = 0 when the reference would have seen no metadata. */

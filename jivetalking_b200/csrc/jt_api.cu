@@ -303,14 +303,11 @@ static void analyse_enqueue(jt_ctx *c, const void *d_in, int64_t n_frames, int r
     jt_graph_enqueue(c, PASS1_SPEC, d_in, n_frames, rate, channels, fmt, F, false, true, ap.g);
 }
 
-// Pass 1, host part: metadata assembly and the Go-side accumulation (collectAnalysisFrames, analyser.go:571-638)
-static void analyse_finish(jt_ctx *c, AnalysePending &ap, jt_measurements *out, jt_interval *iv, int64_t iv_cap, int64_t *n_iv)
+// The Go-side accumulation of Pass 1 (collectAnalysisFrames, analyser.go:571-638) over the sink-frame records `g`
+// and the raw per-source-frame statistics (a2): whole-file accumulators + 250 ms IntervalSamples.
+static void analyse_accumulate(jt_ctx *c, const GraphResult &g, const double *ss, const double *pk, int64_t nsrc, int64_t n_frames,
+                               int rate, int channels, int F, jt_measurements *out, jt_interval *iv, int64_t iv_cap, int64_t *n_iv)
 {
-    const int64_t nsrc = ap.nsrc, n_frames = ap.n_frames; const int rate = ap.rate, channels = ap.channels, F = ap.F;
-    GraphResult g;
-    jt_graph_finish(c, ap.g, g);
-    JT_CUDA(cudaEventSynchronize(ap.ev));
-    const double *ss = ap.h_ss, *pk = ap.h_pk;
     MeasAcc acc;
     JtHost hacc(c, "interval_accumulation");
     struct IvAcc { int frameCount = 0; double rawSS = 0; int64_t rawN = 0; double rawPeak = 0; double spec[JT_SP_COUNT] = {0}; bool specFound = false;
@@ -363,6 +360,16 @@ static void analyse_finish(jt_ctx *c, AnalysePending &ap, jt_measurements *out, 
     if (n_iv) *n_iv = n_int;
 }
 
+
+// Pass 1, host part: metadata assembly, then the accumulation
+static void analyse_finish(jt_ctx *c, AnalysePending &ap, jt_measurements *out, jt_interval *iv, int64_t iv_cap, int64_t *n_iv)
+{
+    GraphResult g;
+    jt_graph_finish(c, ap.g, g);
+    JT_CUDA(cudaEventSynchronize(ap.ev));
+    analyse_accumulate(c, g, ap.h_ss, ap.h_pk, ap.nsrc, ap.n_frames, ap.rate, ap.channels, ap.F, out, iv, iv_cap, n_iv);
+}
+
 static void analyse_device(jt_ctx *c, const void *d_in, int64_t n_frames, int rate, int channels, int fmt, int F,
                            jt_measurements *out, jt_interval *iv, int64_t iv_cap, int64_t *n_iv)
 {
@@ -380,6 +387,168 @@ extern "C" int jt_analyse(jt_ctx *c, const void *pcm_in, int64_t n_frames, int r
         const void *d_in = upload(c, pcm_in, (size_t)n_frames * channels * jt_fmt_bytes(fmt));
         analyse_device(c, d_in, n_frames, rate, channels, fmt, frame_size, out, iv, iv_cap, n_iv);
     });
+}
+
+// ---------------------------------------------------------------------------------------
+// One long stream over several GPUs (BASELINE.json configs[3]): every rank analyses a contiguous
+// chunk (plus context) with jt_analyse_chunk, the blobs are exchanged with ONE all-gather, and any rank turns
+// them into the jt_measurements / intervals a single-GPU jt_analyse gives with jt_analyse_merge.  What is
+// exchanged are the mergeable per-tick / per-hop / per-frame values, not finished statistics: 400 ms / 3 s
+// windows, gating and LRA percentiles are evaluated on the merged tick list, so chunking does not change them.
+// ---------------------------------------------------------------------------------------
+#define JT_CHUNK_MAGIC 0x4a54434855 /* "JTCHU" */
+struct JtChunkHdr {
+    int64_t magic, bytes, total_frames, first, owned;
+    int32_t rate, channels, fmt, frame_size, tick, link_fmt, tc, reserved;
+    int64_t tick0, n_ticks, src0, n_src, n_rows, astats_bytes, astats_n, astats_upto;
+};
+// astats is cumulative and a sink frame shows the snapshot of the decoder frame holding its first sample: the whole-file
+// values are those of the LAST sink frame, i.e. statistics of samples [0, upto) with upto possibly short of the end
+static int64_t pass1_astats_upto(int64_t total, int tick, int F)
+{
+    if (total <= 0) return 0;
+    const int64_t s_last = (total - 1) / tick * tick;
+    return std::min<int64_t>((s_last / F + 1) * (int64_t)F, total);
+}
+static int64_t gcd64(int64_t a, int64_t b) { while (b) { int64_t t = a % b; a = b; b = t; } return a; }
+
+extern "C" int64_t jt_analyse_chunk_unit(int rate)
+{   // chunk boundaries: whole 100 ms ticks, whole 4096-sample decoder frames, whole 1024-sample spectral hops
+    if (rate <= 0 || rate % 10) return 0;
+    const int64_t tick = rate / 10;
+    return tick / gcd64(tick, 4096) * 4096;
+}
+extern "C" int64_t jt_analyse_chunk_bytes(int64_t owned_frames, int rate)
+{
+    if (rate <= 0 || rate % 10 || owned_frames < 0) return 0;
+    const int64_t nt = owned_frames / (rate / 10) + 2, ns = owned_frames / 4096 + 2;
+    return (int64_t)sizeof(JtChunkHdr) + nt * (3 * 8 + 8 + JT_SP_COUNT * 4) + ns * 16 + (int64_t)jt_astats_host_bytes() + 64;
+}
+
+extern "C" int jt_analyse_chunk(jt_ctx *c, const void *pcm_local, int64_t n_local, int rate, int channels, int fmt,
+                                int64_t local_first, int64_t own_first, int64_t owned, int64_t total_frames,
+                                void *blob, int64_t blob_cap, int64_t *blob_bytes)
+{
+    return guarded(c, [&]() {
+        const int F = 4096;
+        const int64_t U = jt_analyse_chunk_unit(rate);
+        if (!pcm_local || !blob || U <= 0) JT_THROW(JT_ERR_INVALID_ARG, "null argument or unsupported rate");
+        if (fmt != JT_FMT_S16 && fmt != JT_FMT_FLT && fmt != JT_FMT_DBL) JT_THROW(JT_ERR_UNSUPPORTED, "input sample format %d", fmt);
+        if (own_first % U || local_first % U || local_first > own_first || own_first + owned > total_frames || owned <= 0 ||
+            local_first + n_local < own_first + owned || local_first + n_local > total_frames)
+            JT_THROW(JT_ERR_INVALID_ARG, "chunk [%lld,+%lld) / local [%lld,+%lld): boundaries must be multiples of jt_analyse_chunk_unit = %lld frames",
+                     (long long)own_first, (long long)owned, (long long)local_first, (long long)n_local, (long long)U);
+        const bool last = own_first + owned == total_frames;
+        if (!last && owned % U) JT_THROW(JT_ERR_INVALID_ARG, "only the last chunk may hold a partial unit");
+        if (own_first > 0 && own_first - local_first < U) JT_THROW(JT_ERR_INVALID_ARG, "a chunk in mid-stream needs one unit (%lld frames) of left context", (long long)U);
+        if (!last && local_first + n_local - (own_first + owned) < 4096) JT_THROW(JT_ERR_INVALID_ARG, "a chunk before the stream's end needs >= 4096 frames of right context");
+        const int tick = rate / 10;
+        const int64_t off = own_first - local_first;
+        const void *d_in = upload(c, pcm_local, (size_t)n_local * channels * jt_fmt_bytes(fmt));
+        // a2: raw per-decoder-frame statistics of the owned frames
+        const int64_t nsrc = (owned + F - 1) / F;
+        double *d_ss = jt_dalloc<double>(c, nsrc), *d_pk = jt_dalloc<double>(c, nsrc);
+        jt_raw_frame_stats(c, (const char *)d_in + (size_t)off * channels * jt_fmt_bytes(fmt), owned, channels, fmt, F, d_ss, d_pk, nsrc);
+        double *h_ss = jt_pinned<double>(c, nsrc), *h_pk = jt_pinned<double>(c, nsrc);
+        JT_CUDA(cudaMemcpyAsync(h_ss, d_ss, sizeof(double) * nsrc, cudaMemcpyDeviceToHost, c->stream));
+        JT_CUDA(cudaMemcpyAsync(h_pk, d_pk, sizeof(double) * nsrc, cudaMemcpyDeviceToHost, c->stream));
+        // the Pass-1 filters on the local stream (aformat mono -> astats -> aspectralstats -> ebur128)
+        Sig mono = jt_downmix(c, d_in, n_local, channels, fmt, rate);
+        const int64_t as_upto = pass1_astats_upto(total_frames, tick, F);
+        const int64_t as_n = std::max<int64_t>(0, std::min(own_first + owned, as_upto) - own_first);
+        AstatsPending ap; jt_astats_chunk_launch(c, mono, off, as_n, own_first, ap);
+        // sink frames (100 ms, the last one possibly partial) whose first sample is owned, and the hop each shows
+        const int64_t tick0 = own_first / tick;
+        const int64_t n_sink = (owned + tick - 1) / tick, n_ticks = last ? (total_frames / tick - tick0) : owned / tick;
+        std::vector<int64_t> wanted(n_sink);
+        for (int64_t k = 0; k < n_sink; k++) wanted[k] = (own_first + k * tick) / 1024 - local_first / 1024;
+        SpectralPending sp; jt_aspectralstats_launch(c, mono, 2048, &wanted, sp);
+        R128Pending rp; jt_ebur128_launch(c, mono, true, true, rp);
+        // ---- wait, pack ----
+        std::vector<float> rows; int64_t n_hops = 0;
+        jt_aspectralstats_finish(c, sp, rows, n_hops);
+        JT_CUDA(cudaStreamSynchronize(c->stream));
+        JtChunkHdr h; memset(&h, 0, sizeof(h));
+        h.magic = JT_CHUNK_MAGIC; h.total_frames = total_frames; h.first = own_first; h.owned = owned;
+        h.rate = rate; h.channels = channels; h.fmt = fmt; h.frame_size = F; h.tick = tick; h.link_fmt = mono.fmt; h.tc = ap.tc;
+        h.tick0 = tick0; h.n_ticks = std::max<int64_t>(n_ticks, 0); h.src0 = own_first / F; h.n_src = nsrc; h.n_rows = n_sink;
+        h.astats_bytes = (int64_t)jt_astats_host_bytes(); h.astats_n = ap.host ? as_n : 0; h.astats_upto = as_upto;
+        if (!h.tc) h.tc = (int)std::fmax(0.05 * rate + .5, 1);
+        const int64_t need = (int64_t)sizeof(h) + h.n_ticks * 24 + nsrc * 16 + n_sink * (8 + JT_SP_COUNT * 4) + h.astats_bytes;
+        if (need > blob_cap) JT_THROW(JT_ERR_BUFFER, "chunk blob needs %lld bytes", (long long)need);
+        h.bytes = need;
+        char *w = (char *)blob;
+        memcpy(w, &h, sizeof(h)); w += sizeof(h);
+        const int64_t lt0 = off / tick;                       // local index of the first owned tick
+        if (h.n_ticks > 0 && lt0 + h.n_ticks > rp.nt) JT_THROW(JT_ERR_INVALID_ARG, "internal: local tick range");
+        memcpy(w, rp.hp + lt0, 8 * h.n_ticks); w += 8 * h.n_ticks;
+        memcpy(w, rp.hk + lt0, 8 * h.n_ticks); w += 8 * h.n_ticks;
+        memcpy(w, rp.ht + lt0, 8 * h.n_ticks); w += 8 * h.n_ticks;
+        memcpy(w, h_ss, 8 * nsrc); w += 8 * nsrc;
+        memcpy(w, h_pk, 8 * nsrc); w += 8 * nsrc;
+        for (int64_t k = 0; k < n_sink; k++) { const int64_t gh = (own_first + k * tick) / 1024; memcpy(w, &gh, 8); w += 8; }
+        for (int64_t k = 0; k < n_sink; k++) {
+            const int64_t lh = wanted[k];
+            if (lh >= 0 && lh < n_hops) memcpy(w, &rows[(size_t)lh * JT_SP_COUNT], JT_SP_COUNT * 4); else memset(w, 0, JT_SP_COUNT * 4);
+            w += JT_SP_COUNT * 4;
+        }
+        if (ap.host) memcpy(w, ap.host, h.astats_bytes); else memset(w, 0, h.astats_bytes);
+        if (blob_bytes) *blob_bytes = need;
+    });
+}
+
+extern "C" int jt_analyse_merge(int n_chunks, const void *const *blobs, jt_measurements *out, jt_interval *iv, int64_t iv_cap, int64_t *n_iv)
+{
+    if (n_chunks <= 0 || !blobs) return JT_ERR_INVALID_ARG;
+    try {
+        std::vector<const JtChunkHdr *> hs;
+        for (int i = 0; i < n_chunks; i++) {
+            const JtChunkHdr *h = (const JtChunkHdr *)blobs[i];
+            if (!h || h->magic != JT_CHUNK_MAGIC) return JT_ERR_INVALID_ARG;
+            hs.push_back(h);
+        }
+        std::sort(hs.begin(), hs.end(), [](const JtChunkHdr *a, const JtChunkHdr *b) { return a->first < b->first; });
+        const JtChunkHdr &h0 = *hs[0];
+        int64_t expect = 0;
+        for (const JtChunkHdr *h : hs) {
+            if (h->first != expect || h->rate != h0.rate || h->channels != h0.channels || h->total_frames != h0.total_frames || h->fmt != h0.fmt)
+                return JT_ERR_INVALID_ARG;                      // chunks must tile the stream
+            expect = h->first + h->owned;
+        }
+        if (expect != h0.total_frames) return JT_ERR_INVALID_ARG;
+        const int64_t total = h0.total_frames; const int rate = h0.rate, tick = h0.tick, F = h0.frame_size;
+        const int64_t nt = total / tick, nsrc = (total + F - 1) / F, n_hops = (total + 1023) / 1024;
+        std::vector<double> hp(nt), hk(nt), ht(nt), ss(nsrc), pk(nsrc);
+        std::vector<float> rows((size_t)n_hops * JT_SP_COUNT, 0.f);
+        std::vector<char> as(jt_astats_host_bytes());
+        bool first_as = true;
+        for (const JtChunkHdr *h : hs) {
+            const char *r = (const char *)h + sizeof(JtChunkHdr);
+            if (h->tick0 + h->n_ticks > nt || h->src0 + h->n_src > nsrc) return JT_ERR_INVALID_ARG;
+            memcpy(&hp[h->tick0], r, 8 * h->n_ticks); r += 8 * h->n_ticks;
+            memcpy(&hk[h->tick0], r, 8 * h->n_ticks); r += 8 * h->n_ticks;
+            memcpy(&ht[h->tick0], r, 8 * h->n_ticks); r += 8 * h->n_ticks;
+            memcpy(&ss[h->src0], r, 8 * h->n_src); r += 8 * h->n_src;
+            memcpy(&pk[h->src0], r, 8 * h->n_src); r += 8 * h->n_src;
+            const char *hops = r; r += 8 * h->n_rows;
+            for (int64_t k = 0; k < h->n_rows; k++) {
+                int64_t gh; memcpy(&gh, hops + 8 * k, 8);
+                if (gh >= 0 && gh < n_hops) memcpy(&rows[(size_t)gh * JT_SP_COUNT], r + (size_t)k * JT_SP_COUNT * 4, JT_SP_COUNT * 4);
+            }
+            r += (size_t)h->n_rows * JT_SP_COUNT * 4;
+            if ((size_t)h->astats_bytes != as.size()) return JT_ERR_INVALID_ARG;
+            if (h->astats_n > 0) { if (first_as) { memcpy(as.data(), r, as.size()); first_as = false; } else jt_astats_host_merge(as.data(), r); }
+        }
+        R128Result r128;
+        jt_ebur128_host_finalize(nullptr, hp.data(), hk.data(), ht.data(), nt, tick, true, r128);
+        AstatsResult ar;
+        jt_astats_host_finalize(first_as ? nullptr : as.data(), h0.astats_upto, h0.link_fmt, h0.tc, ar);
+        GraphResult g;
+        jt_pass1_records(nullptr, total, rate, F, r128, rows, n_hops, &ar, g);
+        analyse_accumulate(nullptr, g, ss.data(), pk.data(), nsrc, total, rate, h0.channels, F, out, iv, iv_cap, n_iv);
+    } catch (const JtError &e) { return e.code; }
+    catch (const std::bad_alloc &) { return JT_ERR_NOMEM; }
+    return JT_OK;
 }
 
 // ---------------------------------------------------------------------------------------

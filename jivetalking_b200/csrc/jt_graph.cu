@@ -481,6 +481,46 @@ const R128Result &jt_graph_r128_early(jt_ctx *c, GraphRun &g)
     return g.r128;
 }
 
+// one jt_frame_meta per sink frame from the per-tick / per-hop products (astats is added by the caller);
+// records are independent: the printf-rounding of ~20 values per sink frame is spread over host threads in `pool`
+static void assemble_records(const std::vector<FrameRef> &frames, bool has_r128, const R128Result &r128, bool has_spec,
+                             const std::vector<float> &spec_rows, int64_t spec_hops, GraphResult &res, std::vector<std::thread> &pool)
+{
+    const size_t nf = frames.size();
+    res.meta.resize(nf); res.meta_ready.resize(nf);
+    int64_t last_tick = -1;
+    for (size_t i = 0; i < nf; i++) if (frames[i].tick >= 0) last_tick = std::max<int64_t>(last_tick, frames[i].tick);
+    auto fill = [&frames, has_r128, &r128, has_spec, &spec_rows, spec_hops, &res, last_tick](size_t i0, size_t i1) {
+        for (size_t i = i0; i < i1; i++) {
+            const FrameRef &fr = frames[i];
+            jt_frame_meta &m = res.meta[i];
+            double *dp = &m.r128_M;
+            const size_t ndbl = (sizeof(jt_frame_meta) - offsetof(jt_frame_meta, r128_M)) / sizeof(double);
+            for (size_t k = 0; k < ndbl; k++) dp[k] = NAN;
+            m.first_sample = fr.start; m.nb_samples = fr.nb; m.reserved = 0;
+            res.meta_ready[i] = fr.ready;
+            if (has_r128 && fr.tick >= 0 && fr.tick < r128.n_ticks) {
+                const int64_t k = fr.tick;
+                m.r128_M = jt_wire("%.3f", r128.M[k]); m.r128_S = jt_wire("%.3f", r128.S[k]);
+                m.r128_sample_peak = jt_wire("%.3f", r128.sp_cum[k]);
+                m.r128_true_peak = jt_wire("%.3f", r128.tp_cum[k]);
+                if (k == last_tick) {
+                    m.r128_I = jt_wire("%.3f", r128.I); m.r128_LRA = jt_wire("%.3f", r128.LRA);
+                    m.r128_LRA_low = jt_wire("%.3f", r128.LRA_low); m.r128_LRA_high = jt_wire("%.3f", r128.LRA_high);
+                }
+            }
+            if (has_spec && fr.hop >= 0 && fr.hop < spec_hops)
+                for (int k = 0; k < JT_SP_COUNT; k++) m.spectral[k] = jt_wire("%g", (double)spec_rows[(size_t)fr.hop * JT_SP_COUNT + k]);
+        }
+    };
+    const unsigned hw = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+    if (nf < 8192 || hw == 1) fill(0, nf);
+    else {
+        const size_t per = (nf + hw - 1) / hw;
+        for (unsigned t = 0; t < hw; t++) { const size_t a = t * per, b = std::min(nf, a + per); if (a < b) pool.emplace_back(fill, a, b); }
+    }
+}
+
 void jt_graph_finish(jt_ctx *c, GraphRun &g, GraphResult &res)
 {
     res = GraphResult();
@@ -506,43 +546,10 @@ void jt_graph_finish(jt_ctx *c, GraphRun &g, GraphResult &res)
     std::vector<float> spec_rows; int64_t spec_hops = 0;
     if (g.has_spec) jt_aspectralstats_finish(c, g.specp, spec_rows, spec_hops);
     const std::vector<FrameRef> &frames = g.frames;
-    const size_t nf = frames.size();
     JtHost hmeta(c, "meta_assembly");
-    res.meta.resize(nf); res.meta_ready.resize(nf);
-    int64_t last_tick = -1;
-    for (size_t i = 0; i < nf; i++) if (frames[i].tick >= 0) last_tick = std::max<int64_t>(last_tick, frames[i].tick);
     const long last_astats_frame = g.last_astats_frame;
-    // records are independent: the printf-rounding of ~20 values per sink frame is spread over host threads
-    auto fill = [&](size_t i0, size_t i1) {
-        for (size_t i = i0; i < i1; i++) {
-            const FrameRef &fr = frames[i];
-            jt_frame_meta &m = res.meta[i];
-            double *dp = &m.r128_M;
-            const size_t ndbl = (sizeof(jt_frame_meta) - offsetof(jt_frame_meta, r128_M)) / sizeof(double);
-            for (size_t k = 0; k < ndbl; k++) dp[k] = NAN;
-            m.first_sample = fr.start; m.nb_samples = fr.nb; m.reserved = 0;
-            res.meta_ready[i] = fr.ready;
-            if (g.has_r128 && fr.tick >= 0 && fr.tick < r128.n_ticks) {
-                const int64_t k = fr.tick;
-                m.r128_M = jt_wire("%.3f", r128.M[k]); m.r128_S = jt_wire("%.3f", r128.S[k]);
-                m.r128_sample_peak = jt_wire("%.3f", r128.sp_cum[k]);
-                m.r128_true_peak = jt_wire("%.3f", r128.tp_cum[k]);
-                if (k == last_tick) {
-                    m.r128_I = jt_wire("%.3f", r128.I); m.r128_LRA = jt_wire("%.3f", r128.LRA);
-                    m.r128_LRA_low = jt_wire("%.3f", r128.LRA_low); m.r128_LRA_high = jt_wire("%.3f", r128.LRA_high);
-                }
-            }
-            if (g.has_spec && fr.hop >= 0 && fr.hop < spec_hops)
-                for (int k = 0; k < JT_SP_COUNT; k++) m.spectral[k] = jt_wire("%g", (double)spec_rows[(size_t)fr.hop * JT_SP_COUNT + k]);
-        }
-    };
-    const unsigned hw = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
     std::vector<std::thread> pool;
-    if (nf < 8192 || hw == 1) fill(0, nf);
-    else {
-        const size_t per = (nf + hw - 1) / hw;
-        for (unsigned t = 0; t < hw; t++) { const size_t a = t * per, b = std::min(nf, a + per); if (a < b) pool.emplace_back(fill, a, b); }
-    }
+    assemble_records(frames, g.has_r128, r128, g.has_spec, spec_rows, spec_hops, res, pool);
     AstatsResult a; bool have_a = false; JtError aerr{0, ""};
     if (g.has_astats && last_astats_frame >= 0) {
         try { jt_astats_finish(c, g.astp, a); have_a = true; }
@@ -556,4 +563,32 @@ void jt_graph_finish(jt_ctx *c, GraphRun &g, GraphResult &res)
         m.astats_overall_RMS_level = jt_wire("%f", a.overall_rms);
         m.astats_overall_Peak_level = jt_wire("%f", a.overall_peak);
     }
+}
+
+// Pass-1 sink-frame records of a stream whose per-tick / per-hop / astats products were computed elsewhere (several
+// GPUs, jt_analyse_chunk): the frame cadence of Pass1FilterOrder (filters.go:42-45) is pure integer bookkeeping.
+void jt_pass1_records(jt_ctx *c, int64_t n_frames, int rate, int frame_size, const R128Result &r128,
+                      const std::vector<float> &spec_rows, int64_t spec_hops, const AstatsResult *astats, GraphResult &res)
+{
+    res = GraphResult();
+    memset(&res.ln, 0, sizeof(res.ln));
+    std::vector<FrameRef> frames = source_frames(n_frames, frame_size);
+    for (FrameRef &fr : frames) fr.astats_pos = fr.start + fr.nb;                       // astats
+    frames = reframe(frames, n_frames, 1024);                                          // aspectralstats win 2048
+    for (size_t j = 0; j < frames.size(); j++) frames[j].hop = (int32_t)j;
+    const int tick = rate / 10;
+    frames = reframe(frames, n_frames, tick);                                          // ebur128 metadata=1
+    for (size_t k = 0; k < frames.size(); k++) if (frames[k].nb == tick) frames[k].tick = (int32_t)k;
+    std::vector<std::thread> pool;
+    assemble_records(frames, true, r128, true, spec_rows, spec_hops, res, pool);
+    for (auto &t : pool) t.join();
+    long last_astats_frame = -1;
+    for (size_t i = 0; i < frames.size(); i++) if (frames[i].astats_pos >= 0) last_astats_frame = (long)i;
+    if (astats && last_astats_frame >= 0) {
+        jt_frame_meta &m = res.meta[last_astats_frame];
+        for (int k = 0; k < JT_AS_COUNT; k++) m.astats[k] = std::isnan(astats->v[k]) ? NAN : jt_wire("%f", astats->v[k]);
+        m.astats_overall_RMS_level = jt_wire("%f", astats->overall_rms);
+        m.astats_overall_Peak_level = jt_wire("%f", astats->overall_peak);
+    }
+    (void)c;
 }

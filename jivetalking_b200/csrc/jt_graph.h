@@ -55,6 +55,9 @@ void jt_graph_enqueue(jt_ctx *c, const std::string &spec, const void *d_in, int6
 const R128Result &jt_graph_r128_early(jt_ctx *c, GraphRun &g);     // waits for the ebur128 values only
 void jt_graph_finish(jt_ctx *c, GraphRun &g, GraphResult &res);
 
+void jt_pass1_records(jt_ctx *c, int64_t n_frames, int rate, int frame_size, const R128Result &r128,
+                      const std::vector<float> &spec_rows, int64_t spec_hops, const AstatsResult *astats, GraphResult &res);
+
 // d_in: device pointer to interleaved input.  want_pcm=false lets measure-only graphs skip
 // work whose only product is discarded audio (loudnorm dynamic mode in Pass 3).
 void jt_graph_run(jt_ctx *c, const std::string &spec, const void *d_in, int64_t n_frames, int rate, int channels,

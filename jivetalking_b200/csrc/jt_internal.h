@@ -119,6 +119,8 @@ void jt_ebur128(jt_ctx *c, const Sig &in, bool dualmono, bool true_peak, R128Res
 struct R128Pending { int64_t nt = 0; int tick = 0; bool dualmono = false, true_peak = false; double *hp = nullptr, *hk = nullptr, *ht = nullptr; cudaEvent_t ev = nullptr; };
 void jt_ebur128_launch(jt_ctx *c, const Sig &in, bool dualmono, bool true_peak, R128Pending &pd);
 void jt_ebur128_finish(jt_ctx *c, R128Pending &pd, R128Result &out);
+void jt_ebur128_host_finalize(jt_ctx *c, const double *tick_pow, const double *tick_peak, const double *tick_tp_or_null,
+                              int64_t n_ticks, int tick, bool dualmono, R128Result &out);
 struct LoudnormMeter { double I, LRA, thresh, sample_peak; };
 void jt_loudnorm_meter(jt_ctx *c, const Sig &in, bool dual_mono, LoudnormMeter &out);   // libavfilter/ebur128.c
 struct LoudnormPending { int64_t nt = 0, nfull = 0; int s100 = 0; bool dual_mono = false; double *hp = nullptr, *hk = nullptr; cudaEvent_t ev = nullptr; };
@@ -131,6 +133,12 @@ void jt_astats(jt_ctx *c, const Sig &in, int64_t n_upto, AstatsResult &out);
 struct AstatsPending { int64_t n = 0; int fmt = 0, rate = 0, tc = 0; void *host = nullptr; cudaEvent_t ev = nullptr; };
 void jt_astats_launch(jt_ctx *c, const Sig &in, int64_t n_upto, AstatsPending &pd);
 void jt_astats_finish(jt_ctx *c, AstatsPending &pd, AstatsResult &out);
+// one chunk of a longer stream: samples [own0, own0 + own_n) of `in` are stream samples [global_first, ...); the
+// partial statistics (pd.host, jt_astats_host_bytes() bytes) merge across chunks and finalise on any host
+void jt_astats_chunk_launch(jt_ctx *c, const Sig &in, int64_t own0, int64_t own_n, int64_t global_first, AstatsPending &pd);
+size_t jt_astats_host_bytes();
+void jt_astats_host_merge(void *dst, const void *src);
+void jt_astats_host_finalize(const void *host, int64_t n, int fmt, int tc, AstatsResult &out);
 
 // ---- k_spectral.cu ------------------------------------------------------------------------
 // rows: n_hops x JT_SP_COUNT floats on the host

@@ -105,7 +105,7 @@ JtLaunch::~JtLaunch()
 static double host_now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 JtHost::JtHost(jt_ctx *ctx, const char *name) : c(ctx)
 {
-    if (!c->timing) return;
+    if (!c || !c->timing) return;
     std::string nm = std::string("host:") + name;
     for (size_t i = 0; i < c->slots.size(); i++) if (c->slots[i].name == nm) { slot = (int)i; break; }
     if (slot < 0) { c->slots.push_back(JtTimingSlot{nm, 0, 0}); slot = (int)c->slots.size() - 1; }

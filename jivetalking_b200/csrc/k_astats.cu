@@ -40,8 +40,8 @@ template <> struct AsTraits<double> {
 
 template <class T>
 __global__ void __launch_bounds__(256)
-k_astats_a(const T *__restrict__ x, int64_t n, AsPartA *__restrict__ parts, unsigned long long *__restrict__ ghist)
-{
+k_astats_a(const T *__restrict__ x, int64_t n, AsPartA *__restrict__ parts, unsigned long long *__restrict__ ghist, int64_t back)
+{   // back: samples readable BEFORE x[0] (a chunk of a longer stream); 0 = x[0] starts the stream
     __shared__ unsigned int shist[AS_HIST];
     __shared__ AsPartA swarp[8];
     for (int i = threadIdx.x; i < AS_HIST; i += blockDim.x) shist[i] = 0;
@@ -58,11 +58,11 @@ k_astats_a(const T *__restrict__ x, int64_t n, AsPartA *__restrict__ parts, unsi
         if (d != 0) {
             a.min_nz = fmin(a.min_nz, fabs(d));
             int64_t j = i - 1;
-            while (j >= 0 && AsTraits<T>::d(x[j]) == 0) j--;
-            const double prev = j >= 0 ? AsTraits<T>::d(x[j]) : 0.0;
+            while (j >= -back && AsTraits<T>::d(x[j]) == 0) j--;
+            const double prev = j >= -back ? AsTraits<T>::d(x[j]) : 0.0;
             a.zero_runs += ((d > 0) != (prev > 0));
         }
-        if (i > 0) {
+        if (i > 0 || back > 0) {
             const double df = d - AsTraits<T>::d(x[i - 1]), ad = fabs(df);
             a.min_diff = fmin(a.min_diff, ad); a.max_diff = fmax(a.max_diff, ad);
             a.diff_sum += ad; a.diff_sumsq = fma(df, df, a.diff_sumsq);
@@ -348,9 +348,12 @@ k_astats_nf_reduce(const float *__restrict__ bmin, const unsigned *__restrict__ 
 struct AstatsHost { AsPartA total; unsigned long long hist[AS_HIST + 8]; double mm[2]; float nf; };
 
 template <class T>
-static void astats_launch_t(jt_ctx *c, const Sig &in, int64_t n, AstatsPending &pd)
+static void astats_launch_t(jt_ctx *c, const Sig &in, int64_t n, AstatsPending &pd, int64_t own0 = 0, int64_t global_first = 0)
 {
-    const T *x = (const T *)in.d;
+    // chunk mode (own0 > 0): statistics of samples [own0, own0 + n) of `in`, which are samples
+    // [global_first, global_first + n) of a longer stream; the samples before own0 are context only
+    const T *x = (const T *)in.d + own0;
+    const int64_t back = own0;
     const double time_constant = 0.05;
     const int tc = (int)std::fmax(time_constant * in.rate + .5, 1);
     const double mult = exp((-1 / time_constant / in.rate));
@@ -364,31 +367,38 @@ static void astats_launch_t(jt_ctx *c, const Sig &in, int64_t n, AstatsPending &
     float *d_nf = jt_dalloc<float>(c, 1);
     JT_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * (AS_HIST + 8), c->stream));
     { JtLaunch L(c, "astats:sums_hist", 2);
-      k_astats_a<T><<<gridA, 256, 0, c->stream>>>(x, n, d_parts, d_hist);
+      k_astats_a<T><<<gridA, 256, 0, c->stream>>>(x, n, d_parts, d_hist, back);
       k_astats_reduce<<<1, 32, 0, c->stream>>>(d_parts, gridA, d_total, d_mm, d_nf); }
     // B: extrema counts
     { JtLaunch L(c, "astats:extrema_runs"); k_astats_b<T><<<gridA, 256, 0, c->stream>>>(x, n, d_total, d_counts); }
     // C: exponential mean square min/max
-    const int BS = AS_BS; const int64_t nb = (n + BS - 1) / BS;
-    if (n > tc) {
+    // the 50 ms exponential window is warmed up over the context (>= 37 time constants for an exact carry-in)
+    const int64_t wu = std::min<int64_t>(back, 40 * (int64_t)tc);
+    const T *xc = x - wu; const int64_t nc = n + wu;
+    const int64_t track_from = std::max<int64_t>(wu, (int64_t)tc - (global_first - wu));
+    const int BS = AS_BS; const int64_t nb = (nc + BS - 1) / BS;
+    if (global_first + n > tc) {
         double *d_fin = jt_dalloc<double>(c, nb), *d_carry = jt_dalloc<double>(c, nb);
         JtLaunch L(c, "astats:rms_scan", 3);
         const size_t smemC = 2 * LaneStage<T, AsRow<T>::R, 2>::WARP_BYTES;
         JT_CUDA(cudaFuncSetAttribute(k_astats_c1<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC));
         JT_CUDA(cudaFuncSetAttribute(k_astats_c2<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC));
-        k_astats_c1<T><<<(int)((nb + 63) / 64), 64, smemC, c->stream>>>(x, n, mult, d_fin);
+        k_astats_c1<T><<<(int)((nb + 63) / 64), 64, smemC, c->stream>>>(xc, nc, mult, d_fin);
         k_astats_carry<<<1, 1024, 0, c->stream>>>(d_fin, d_carry, nb, pow(mult, (double)BS));
-        k_astats_c2<T><<<(int)((nb + 63) / 64), 64, smemC, c->stream>>>(x, n, mult, d_carry, tc, d_mm);
+        k_astats_c2<T><<<(int)((nb + 63) / 64), 64, smemC, c->stream>>>(xc, nc, mult, d_carry, track_from, d_mm);
     }
     // D: noise floor
-    if (n >= tc) {
-        const int64_t nbt = (n + tc - 1) / tc;
+    // windows END in the owned range; a chunk in mid-stream takes the tc-1 samples before it as the first windows' body
+    const int64_t nfb = std::min<int64_t>(back, tc - 1);
+    const T *xn = x - nfb; const int64_t nn = n + nfb;
+    if (nn >= tc) {
+        const int64_t nbt = (nn + tc - 1) / tc;
         float *d_bmin = jt_dalloc<float>(c, nbt); unsigned *d_bcnt = jt_dalloc<unsigned>(c, nbt);
         const size_t smemD = sizeof(float) * (2 * (size_t)tc + 1);
         if (smemD > 200 * 1024) JT_THROW(JT_ERR_UNSUPPORTED, "astats at %d Hz (50 ms window of %d samples)", in.rate, tc);
         JT_CUDA(cudaFuncSetAttribute(k_astats_nf<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemD));
         JtLaunch L(c, "astats:noise_floor", 2);
-        k_astats_nf<T><<<jt_grid_for(nbt, 1, c->num_sms, 32), AS_NF_THREADS, smemD, c->stream>>>(x, n, tc, d_bmin, d_bcnt);
+        k_astats_nf<T><<<jt_grid_for(nbt, 1, c->num_sms, 32), AS_NF_THREADS, smemD, c->stream>>>(xn, nn, tc, d_bmin, d_bcnt);
         k_astats_nf_reduce<<<1, 1024, 0, c->stream>>>(d_bmin, d_bcnt, nbt, d_nf, d_counts + 4);
     }
     AstatsHost *h = (AstatsHost *)jt_pinned_bytes(c, sizeof(AstatsHost));
@@ -406,14 +416,44 @@ void jt_astats_finish(jt_ctx *c, AstatsPending &pd, AstatsResult &out)
     out.overall_rms = out.overall_peak = NAN; out.nb_samples = 0;
     if (pd.n <= 0 || !pd.host) return;
     JT_CUDA(cudaEventSynchronize(pd.ev));
-    const AstatsHost *h = (const AstatsHost *)pd.host;
+    jt_astats_host_finalize(pd.host, pd.n, pd.fmt, pd.tc, out);
+}
+
+size_t jt_astats_host_bytes() { return sizeof(AstatsHost); }
+
+// merge the partial statistics of a later chunk into `dst` (chunks in stream order)
+void jt_astats_host_merge(void *dst_, const void *src_)
+{
+    AstatsHost &d = *(AstatsHost *)dst_; const AstatsHost &s = *(const AstatsHost *)src_;
+    // Peak_count / Flat_factor runs and the noise-floor count belong to whoever holds the global extreme
+    const bool same_mn = s.total.mn == d.total.mn, same_mx = s.total.mx == d.total.mx;
+    if (s.total.mn < d.total.mn) { d.hist[AS_HIST + 0] = s.hist[AS_HIST + 0]; d.hist[AS_HIST + 2] = s.hist[AS_HIST + 2]; }
+    else if (same_mn) { d.hist[AS_HIST + 0] += s.hist[AS_HIST + 0]; d.hist[AS_HIST + 2] += s.hist[AS_HIST + 2]; }
+    if (s.total.mx > d.total.mx) { d.hist[AS_HIST + 1] = s.hist[AS_HIST + 1]; d.hist[AS_HIST + 3] = s.hist[AS_HIST + 3]; }
+    else if (same_mx) { d.hist[AS_HIST + 1] += s.hist[AS_HIST + 1]; d.hist[AS_HIST + 3] += s.hist[AS_HIST + 3]; }
+    if (s.nf < d.nf) { d.nf = s.nf; d.hist[AS_HIST + 4] = s.hist[AS_HIST + 4]; }
+    else if (s.nf == d.nf) d.hist[AS_HIST + 4] += s.hist[AS_HIST + 4];
+    AsPartA &r = d.total; const AsPartA &b = s.total;
+    r.sum += b.sum; r.sumsq += b.sumsq; r.diff_sum += b.diff_sum; r.diff_sumsq += b.diff_sumsq;
+    r.mn = std::fmin(r.mn, b.mn); r.mx = std::fmax(r.mx, b.mx); r.min_nz = std::fmin(r.min_nz, b.min_nz);
+    r.min_diff = std::fmin(r.min_diff, b.min_diff); r.max_diff = std::fmax(r.max_diff, b.max_diff);
+    r.zero_runs += b.zero_runs; r.mask |= b.mask;
+    for (int i = 0; i < AS_HIST; i++) d.hist[i] += s.hist[i];
+    d.mm[0] = std::fmin(d.mm[0], s.mm[0]); d.mm[1] = std::fmax(d.mm[1], s.mm[1]);
+}
+
+void jt_astats_host_finalize(const void *host, int64_t n, int fmt, int tc, AstatsResult &out)
+{
+    for (int i = 0; i < JT_AS_COUNT; i++) out.v[i] = NAN;
+    out.overall_rms = out.overall_peak = NAN; out.nb_samples = 0;
+    if (n <= 0 || !host) return;
+    const AstatsHost *h = (const AstatsHost *)host;
     const AsPartA &r = h->total;
     const unsigned long long *hist = h->hist;
-    const int64_t n = pd.n; const int tc = pd.tc;
-    const int maxbits = pd.fmt == JT_FMT_S16 ? 16 : pd.fmt == JT_FMT_FLT ? 32 : 64;
+    const int maxbits = fmt == JT_FMT_S16 ? 16 : fmt == JT_FMT_FLT ? 32 : 64;
     const float h_nf = h->nf;
     const double N = (double)n;
-    const double scale = pd.fmt == JT_FMT_S16 ? 32767.0 : 1.0;
+    const double scale = fmt == JT_FMT_S16 ? 32767.0 : 1.0;
     const double nmin = r.mn / scale, nmax = r.mx / scale;
     double min_s2 = h->mm[0], max_s2 = h->mm[1];
     if (n <= tc) min_s2 = max_s2 = r.sumsq / N;      // af_astats.c: fewer samples than the window
@@ -462,4 +502,13 @@ void jt_astats_launch(jt_ctx *c, const Sig &in, int64_t n_upto, AstatsPending &p
 void jt_astats(jt_ctx *c, const Sig &in, int64_t n_upto, AstatsResult &out)
 {
     AstatsPending pd; jt_astats_launch(c, in, n_upto, pd); jt_astats_finish(c, pd, out);
+}
+
+void jt_astats_chunk_launch(jt_ctx *c, const Sig &in, int64_t own0, int64_t own_n, int64_t global_first, AstatsPending &pd)
+{
+    pd = AstatsPending();
+    if (own_n <= 0 || own0 < 0 || own0 + own_n > in.n) return;
+    if (in.fmt == JT_FMT_S16) astats_launch_t<int16_t>(c, in, own_n, pd, own0, global_first);
+    else if (in.fmt == JT_FMT_FLT) astats_launch_t<float>(c, in, own_n, pd, own0, global_first);
+    else astats_launch_t<double>(c, in, own_n, pd, own0, global_first);
 }

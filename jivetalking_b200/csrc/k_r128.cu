@@ -200,14 +200,24 @@ void jt_ebur128_launch(jt_ctx *c, const Sig &in, bool dualmono, bool true_peak, 
 void jt_ebur128_finish(jt_ctx *c, R128Pending &pd, R128Result &out)
 {
     out = R128Result();
-    const int64_t nt = pd.nt; const int tick = pd.tick; const bool dualmono = pd.dualmono;
+    out.n_ticks = pd.nt;
+    if (pd.nt <= 0) return;
+    JT_CUDA(cudaEventSynchronize(pd.ev));
+    jt_ebur128_host_finalize(c, pd.hp, pd.hk, pd.true_peak ? pd.ht : nullptr, pd.nt, pd.tick, pd.dualmono, out);
+}
+
+// f_ebur128.c filter_frame() tail over the per-tick values (K-weighted energy, sample peak, true peak of each
+// 100 ms tick): windowing, gating histograms, LRA.  Pure host code: also the merge step when the ticks of one
+// stream were produced by several GPUs.
+void jt_ebur128_host_finalize(jt_ctx *c, const double *hp, const double *hk, const double *ht_or_null, int64_t nt, int tick,
+                              bool dualmono, R128Result &out)
+{
+    out = R128Result();
     out.n_ticks = nt;
     if (nt <= 0) return;
-    JT_CUDA(cudaEventSynchronize(pd.ev));
-    const double *hp = pd.hp, *hk = pd.hk;
     std::vector<double> zero_tp;
-    const double *ht = pd.ht;
-    if (!pd.true_peak) { zero_tp.assign(nt, 0.0); ht = zero_tp.data(); }
+    const double *ht = ht_or_null;
+    if (!ht) { zero_tp.assign(nt, 0.0); ht = zero_tp.data(); }
 
     // host: f_ebur128.c filter_frame() tail, once per 100 ms
     JtHost hfin(c, "r128_finalize");

@@ -115,6 +115,12 @@ def lib():
     L.jt_graph_max_meta.argtypes = [C.c_char_p, _I64, _INT, _INT]
     L.jt_analyse.argtypes = [_P, _P, _I64, _INT, _INT, _INT, _INT, C.POINTER(Measurements), C.POINTER(Interval), _I64,
                              C.POINTER(_I64)]
+    L.jt_analyse_chunk_unit.restype = _I64
+    L.jt_analyse_chunk_unit.argtypes = [_INT]
+    L.jt_analyse_chunk_bytes.restype = _I64
+    L.jt_analyse_chunk_bytes.argtypes = [_I64, _INT]
+    L.jt_analyse_chunk.argtypes = [_P, _P, _I64, _INT, _INT, _INT, _I64, _I64, _I64, _I64, _P, _I64, C.POINTER(_I64)]
+    L.jt_analyse_merge.argtypes = [_INT, C.POINTER(_P), C.POINTER(Measurements), C.POINTER(Interval), _I64, C.POINTER(_I64)]
     L.jt_band_rms.argtypes = [_P, _P, _I64, _INT, _INT, _INT, C.c_double, C.c_double, _P, _P, _INT, _P, _P]
     pa = [_P, _P, _I64, _INT, _INT, _INT, C.c_char_p, _P, _I64, C.POINTER(ProcessResult)]
     L.jt_process_audio.argtypes = pa
@@ -228,6 +234,18 @@ class Context:
         self._check(rc)
         return m, [iv[i] for i in range(n_iv.value)]
 
+    def analyse_chunk(self, pcm_local, rate, channels, local_first, own_first, owned, total_frames):
+        """One chunk of a long stream (include/jtdsp.h: jt_analyse_chunk).  Returns the mergeable blob (bytes)."""
+        pcm_local = np.ascontiguousarray(pcm_local)
+        fmt = _FMT_OF_NP[pcm_local.dtype]
+        cap = lib().jt_analyse_chunk_bytes(owned, rate)
+        buf = C.create_string_buffer(cap)
+        n = _I64(0)
+        rc = lib().jt_analyse_chunk(self._h, pcm_local.ctypes.data_as(_P), pcm_local.size // channels, rate, channels, fmt,
+                                    local_first, own_first, owned, total_frames, buf, cap, C.byref(n))
+        self._check(rc)
+        return buf.raw[: n.value]
+
     def band_rms(self, pcm, rate, start_s, duration_s, lo_hz, hi_hz, channels=1):
         pcm = np.ascontiguousarray(pcm)
         fmt = _FMT_OF_NP[pcm.dtype]
@@ -287,6 +305,24 @@ class Context:
             out.append((name.decode(), ms.value, ln.value))
             i += 1
         return out
+
+
+def analyse_chunk_unit(rate):
+    return lib().jt_analyse_chunk_unit(rate)
+
+
+def analyse_merge(blobs, total_frames, rate):
+    """Host-only merge of jt_analyse_chunk blobs -> (Measurements, [Interval]) of the whole stream."""
+    keep = [C.create_string_buffer(b, len(b)) for b in blobs]
+    arr = (_P * len(keep))(*[C.cast(k, _P) for k in keep])
+    cap = int(total_frames / rate / 0.25) + 8
+    iv = (Interval * cap)()
+    n_iv = _I64(0)
+    m = Measurements()
+    rc = lib().jt_analyse_merge(len(keep), arr, C.byref(m), iv, cap, C.byref(n_iv))
+    if rc:
+        raise JtError(rc, lib().jt_strerror(rc).decode())
+    return m, [iv[i] for i in range(n_iv.value)]
 
 
 def build_pass3_spec(output_i, output_tp, target_i=-16.0, target_tp=-1.0, target_lra=20.0):

@@ -49,3 +49,56 @@ def test_two_rank_sharding_and_timing():
 def test_single_process_is_identity():
     assert shard.job_throughput(10.0, 2.0) == (5.0, 10.0, 2.0)
     assert shard.assign_files(3, 0, 1) == [0, 1, 2]
+
+
+# ---- one stream over several ranks (configs[3]): chunk planning, the all-gather, merge validation -----------
+def test_stream_chunk_plan_tiles_the_stream():
+    from jivetalking_b200 import gpudsp
+    for rate in (44100, 48000, 96000):
+        unit = gpudsp.analyse_chunk_unit(rate)
+        assert unit % (rate // 10) == 0 and unit % 4096 == 0 and unit % 1024 == 0
+        for total in (1, unit - 1, unit, 7 * unit + 123, 64 * unit):
+            for world in (1, 2, 3, 8):
+                chunks = shard.plan_stream_chunks(total, unit, world)
+                assert len(chunks) == world and chunks[0][0] == 0
+                end = 0
+                for first, owned in chunks:
+                    assert first == end and (first % unit == 0 or owned == 0)
+                    end = first + owned
+                assert end == total
+                sizes = [o for _, o in chunks if o and o % unit == 0]
+                assert not sizes or max(sizes) - min(sizes) <= unit
+                lo, hi = shard.local_range(*chunks[-1], total, unit)
+                assert 0 <= lo <= chunks[-1][0] and hi <= total
+
+
+def _gather_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    blob = bytes([rank + 1]) * (10 + 7 * rank)          # ragged sizes
+    got = shard.allgather_blobs(blob)
+    out.put((rank, got))
+    dist.destroy_process_group()
+
+
+def test_allgather_of_ragged_blobs_two_ranks():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gather_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in range(world):
+        assert res[r] == [b"\x01" * 10, b"\x02" * 17]
+
+
+def test_merge_rejects_blobs_that_do_not_tile():
+    import pytest
+    from jivetalking_b200 import gpudsp
+    with pytest.raises(gpudsp.JtError):
+        gpudsp.analyse_merge([b"\x00" * 256], 48000, 48000)     # no magic
