@@ -7,6 +7,7 @@
 // once and a second tiny kernel forms the differences.
 #include "jt_internal.h"
 #include "jt_device.cuh"
+#include "jt_fft.cuh"
 #include <cfloat>
 #include <algorithm>
 #include <cstring>
@@ -32,126 +33,132 @@ template <int K> __device__ __forceinline__ void block_sum(float (&v)[K], float 
     }
 }
 
+// Two items (hops) per CTA trip: hop A is the real part and hop B the imaginary part of ONE complex Stockham
+// radix-4 transform (jt_fft.cuh); the two real spectra are separated by symmetry and reduced one after the other.
 __global__ void __launch_bounds__(SP_THREADS)
 k_spectral(const float *__restrict__ x, int64_t n, int win, int rate, int64_t n_items, const int64_t *__restrict__ list,
-           const float2 *__restrict__ tw, const float *__restrict__ lut,
+           const float2 *__restrict__ tw_g, const float *__restrict__ lut,
            float *__restrict__ mags, float *__restrict__ rows)
 {
-    extern __shared__ float2 sbuf[];                 // win complex
+    extern __shared__ float2 sbuf[];                 // bufA[win], bufB[win], tw[win], smag[win/2 floats]
     __shared__ float red[SP_THREADS / 32][8];
     __shared__ float s_scan[SP_THREADS / 32];
     __shared__ int s_idx;
+    float2 *bufA = sbuf, *bufB = sbuf + win, *tw = sbuf + 2 * win;
+    float *smag = (float *)(sbuf + 3 * win);
     const int hop = win / 2, size = win / 2;
-    int logn = 0; while ((1 << logn) < win) logn++;
-    for (int64_t it = blockIdx.x; it < n_items; it += gridDim.x) {
-        const int64_t h = list ? list[it] : it;     // hop index of this item
-        const int64_t w0 = (h - 1) * (int64_t)hop;  // window start sample
+    for (int i = threadIdx.x; i < win; i += SP_THREADS) tw[i] = tw_g[i];
+    const int64_t n_pairs = (n_items + 1) / 2;
+    for (int64_t pr = blockIdx.x; pr < n_pairs; pr += gridDim.x) {
+        const int64_t itA = 2 * pr, itB = itA + 1;
+        const bool hasB = itB < n_items;
+        const int64_t hA = list ? list[itA] : itA, hB = hasB ? (list ? list[itB] : itB) : 0;
+        const int64_t wA = (hA - 1) * (int64_t)hop, wB = (hB - 1) * (int64_t)hop;      // window start samples
         __syncthreads();
         for (int i = threadIdx.x; i < win; i += SP_THREADS) {
-            const int64_t s = w0 + i;
-            const float v = (s >= 0 && s < n) ? __fmul_rn(x[s], lut[i]) : 0.f;
-            sbuf[__brev((unsigned)i) >> (32 - logn)] = make_float2(v, 0.f);
+            const float l = lut[i];
+            const int64_t sa = wA + i, sb = wB + i;
+            const float va = (sa >= 0 && sa < n) ? __fmul_rn(x[sa], l) : 0.f;
+            const float vb = (hasB && sb >= 0 && sb < n) ? __fmul_rn(x[sb], l) : 0.f;
+            bufA[i] = make_float2(va, vb);
         }
         __syncthreads();
-        for (int len = 2; len <= win; len <<= 1) {
-            const int half = len >> 1, tstep = win / len;
-            for (int b = threadIdx.x; b < win / 2; b += SP_THREADS) {
-                const int k = b & (half - 1), i = ((b - k) << 1) + k;
-                const float2 w = tw[k * tstep];
-                const float2 a = sbuf[i], bb = sbuf[i + half];
-                const float tr = __fsub_rn(__fmul_rn(bb.x, w.x), __fmul_rn(bb.y, w.y));
-                const float ti = __fadd_rn(__fmul_rn(bb.x, w.y), __fmul_rn(bb.y, w.x));
-                sbuf[i] = make_float2(a.x + tr, a.y + ti);
-                sbuf[i + half] = make_float2(a.x - tr, a.y - ti);
+        const float2 *Z = af_fft<false>(bufA, bufB, tw, win);
+        const float wscale = 1.f / win;
+        const int per = size / SP_THREADS;           // 4 for win 2048
+        float mA[4], mB[4];
+        for (int j = 0; j < per; j++) {
+            const int k = threadIdx.x * per + j;
+            const float2 zk = Z[k], zn = Z[(win - k) & (win - 1)];
+            const float2 fa = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
+            const float2 fb = make_float2(0.5f * (zk.y + zn.y), 0.5f * (zn.x - zk.x));
+            mA[j] = hypotf(__fmul_rn(fa.x, wscale), __fmul_rn(fa.y, wscale));
+            mB[j] = hypotf(__fmul_rn(fb.x, wscale), __fmul_rn(fb.y, wscale));
+        }
+        for (int u = 0; u < 2; u++) {
+            if (u == 1 && !hasB) break;
+            const int64_t it = u ? itB : itA;
+            float m[4];
+            for (int j = 0; j < per; j++) m[j] = u ? mB[j] : mA[j];
+            __syncthreads();
+            for (int j = 0; j < per; j++) {
+                smag[threadIdx.x * per + j] = m[j];
+                mags[it * (int64_t)size + threadIdx.x * per + j] = m[j];
             }
             __syncthreads();
-        }
-        // magnitudes of the lower half, pre-scaled by 1/win
-        const float wscale = 1.f / win;
-        float *smag = (float *)sbuf;                 // reuse: write after all reads of this thread's bins
-        float m[4];
-        const int per = size / SP_THREADS;           // 4 for win 2048
-        float2 c4[4];
-        for (int j = 0; j < per; j++) c4[j] = sbuf[threadIdx.x * per + j];
-        __syncthreads();
-        for (int j = 0; j < per; j++) {
-            m[j] = hypotf(__fmul_rn(c4[j].x, wscale), __fmul_rn(c4[j].y, wscale));
-            smag[threadIdx.x * per + j] = m[j];
-            mags[it * (int64_t)size + threadIdx.x * per + j] = m[j];
-        }
-        __syncthreads();
-        const float mag0 = smag[0];
-        const float scale = (rate / 2) / (float)size;
-        const float mean_freq = size * 0.5f;
-        // pass 1
-        float r1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        float mx = 0.f;
-        for (int j = 0; j < per; j++) {
-            const int nn = threadIdx.x * per + j; const float v = m[j];
-            r1[0] += v;                                   // sum
-            r1[1] += v * nn * scale;                      // centroid num
-            r1[2] += v * logf(v + FLT_EPSILON);           // entropy num
-            const float ve = FLT_EPSILON + v;
-            r1[3] += logf(ve);                            // flatness log-sum
-            r1[4] += ve;                                  // flatness den
-            if (nn >= 1) { r1[5] += (v - mag0) / nn; r1[6] += v; }   // decrease
-            const float q = (nn - mean_freq) / mean_freq; r1[7] += q * q;   // slope den
-            mx = fmaxf(mx, v);
-        }
-        block_sum<8>(r1, red);
-        mx = jt_warp_max(mx);
-        __syncthreads();
-        if ((threadIdx.x & 31) == 0) s_scan[threadIdx.x >> 5] = mx;
-        __syncthreads();
-        mx = 0.f; for (int i = 0; i < SP_THREADS / 32; i++) mx = fmaxf(mx, s_scan[i]);
-        const float sum = r1[0], mean = sum / size;
-        const float centroid = sum <= FLT_EPSILON ? 1.f : r1[1] / sum;
-        // pass 2
-        float r2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        for (int j = 0; j < per; j++) {
-            const int nn = threadIdx.x * per + j; const float v = m[j];
-            const float dm = v - mean; r2[0] += dm * dm;                 // variance
-            const float df = nn * scale - centroid, df2 = df * df;
-            r2[1] += v * df2; r2[2] += v * (df2 * df); r2[3] += v * (df2 * df2);
-            r2[4] += ((nn - mean_freq) / mean_freq) * dm;               // slope num
-        }
-        block_sum<8>(r2, red);
-        // rolloff: first bin where the running sum reaches 85 % of the total
-        float run = m[0]; float loc[4]; loc[0] = run;
-        for (int j = 1; j < per; j++) { run += m[j]; loc[j] = run; }
-        float incl = run;                                  // warp inclusive scan of per-thread totals
-        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-        for (int o = 1; o < 32; o <<= 1) { float t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-        __syncthreads();
-        if (lane == 31) s_scan[wid] = incl;
-        if (threadIdx.x == 0) s_idx = 0x7fffffff;
-        __syncthreads();
-        float woff = 0; for (int i = 0; i < wid; i++) woff += s_scan[i];
-        const float excl = woff + incl - run;
-        const float norm = sum * 0.85f;
-        int first = 0x7fffffff;
-        for (int j = per - 1; j >= 0; j--) if (excl + loc[j] >= norm) first = threadIdx.x * per + j;
-        if (first != 0x7fffffff) atomicMin(&s_idx, first);
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            float *r = rows + it * JT_SP_COUNT;
-            const float spread = sum <= FLT_EPSILON ? 1.f : sqrtf(r2[1] / sum);
-            r[JT_SP_mean] = mean;
-            r[JT_SP_variance] = r2[0] / size;
-            r[JT_SP_centroid] = centroid;
-            r[JT_SP_spread] = spread;
-            float den = sum * (spread * spread * spread);
-            r[JT_SP_skewness] = den <= FLT_EPSILON ? 1.f : r2[2] / den;
-            den = sum * ((spread * spread) * (spread * spread));
-            r[JT_SP_kurtosis] = den <= FLT_EPSILON ? 1.f : r2[3] / den;
-            den = logf((float)size);
-            r[JT_SP_entropy] = den <= FLT_EPSILON ? 1.f : -r1[2] / den;
-            { float num = expf(r1[3] / size), d2 = r1[4] / size; r[JT_SP_flatness] = d2 <= FLT_EPSILON ? 0.f : num / d2; }
-            r[JT_SP_crest] = mean <= FLT_EPSILON ? 0.f : mx / mean;
-            r[JT_SP_flux] = 0.f;                          // second kernel
-            r[JT_SP_slope] = fabsf(r1[7]) <= FLT_EPSILON ? 0.f : r2[4] / r1[7];
-            r[JT_SP_decrease] = r1[6] <= FLT_EPSILON ? 0.f : r1[5] / r1[6];
-            r[JT_SP_rolloff] = scale * (s_idx == 0x7fffffff ? 0 : s_idx);
+            const float mag0 = smag[0];
+            const float scale = (rate / 2) / (float)size;
+            const float mean_freq = size * 0.5f;
+            // pass 1
+            float r1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            float mx = 0.f;
+            for (int j = 0; j < per; j++) {
+                const int nn = threadIdx.x * per + j; const float v = m[j];
+                r1[0] += v;                                   // sum
+                r1[1] += v * nn * scale;                      // centroid num
+                r1[2] += v * logf(v + FLT_EPSILON);           // entropy num
+                const float ve = FLT_EPSILON + v;
+                r1[3] += logf(ve);                            // flatness log-sum
+                r1[4] += ve;                                  // flatness den
+                if (nn >= 1) { r1[5] += (v - mag0) / nn; r1[6] += v; }   // decrease
+                const float q = (nn - mean_freq) / mean_freq; r1[7] += q * q;   // slope den
+                mx = fmaxf(mx, v);
+            }
+            block_sum<8>(r1, red);
+            mx = jt_warp_max(mx);
+            __syncthreads();
+            if ((threadIdx.x & 31) == 0) s_scan[threadIdx.x >> 5] = mx;
+            __syncthreads();
+            mx = 0.f; for (int i = 0; i < SP_THREADS / 32; i++) mx = fmaxf(mx, s_scan[i]);
+            const float sum = r1[0], mean = sum / size;
+            const float centroid = sum <= FLT_EPSILON ? 1.f : r1[1] / sum;
+            // pass 2
+            float r2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            for (int j = 0; j < per; j++) {
+                const int nn = threadIdx.x * per + j; const float v = m[j];
+                const float dm = v - mean; r2[0] += dm * dm;                 // variance
+                const float df = nn * scale - centroid, df2 = df * df;
+                r2[1] += v * df2; r2[2] += v * (df2 * df); r2[3] += v * (df2 * df2);
+                r2[4] += ((nn - mean_freq) / mean_freq) * dm;               // slope num
+            }
+            block_sum<8>(r2, red);
+            // rolloff: first bin where the running sum reaches 85 % of the total
+            float run = m[0]; float loc[4]; loc[0] = run;
+            for (int j = 1; j < per; j++) { run += m[j]; loc[j] = run; }
+            float incl = run;                                  // warp inclusive scan of per-thread totals
+            const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+            for (int o = 1; o < 32; o <<= 1) { float t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+            __syncthreads();
+            if (lane == 31) s_scan[wid] = incl;
+            if (threadIdx.x == 0) s_idx = 0x7fffffff;
+            __syncthreads();
+            float woff = 0; for (int i = 0; i < wid; i++) woff += s_scan[i];
+            const float excl = woff + incl - run;
+            const float norm = sum * 0.85f;
+            int first = 0x7fffffff;
+            for (int j = per - 1; j >= 0; j--) if (excl + loc[j] >= norm) first = threadIdx.x * per + j;
+            if (first != 0x7fffffff) atomicMin(&s_idx, first);
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                float *r = rows + it * JT_SP_COUNT;
+                const float spread = sum <= FLT_EPSILON ? 1.f : sqrtf(r2[1] / sum);
+                r[JT_SP_mean] = mean;
+                r[JT_SP_variance] = r2[0] / size;
+                r[JT_SP_centroid] = centroid;
+                r[JT_SP_spread] = spread;
+                float den = sum * (spread * spread * spread);
+                r[JT_SP_skewness] = den <= FLT_EPSILON ? 1.f : r2[2] / den;
+                den = sum * ((spread * spread) * (spread * spread));
+                r[JT_SP_kurtosis] = den <= FLT_EPSILON ? 1.f : r2[3] / den;
+                den = logf((float)size);
+                r[JT_SP_entropy] = den <= FLT_EPSILON ? 1.f : -r1[2] / den;
+                { float num = expf(r1[3] / size), d2 = r1[4] / size; r[JT_SP_flatness] = d2 <= FLT_EPSILON ? 0.f : num / d2; }
+                r[JT_SP_crest] = mean <= FLT_EPSILON ? 0.f : mx / mean;
+                r[JT_SP_flux] = 0.f;                          // second kernel
+                r[JT_SP_slope] = fabsf(r1[7]) <= FLT_EPSILON ? 0.f : r2[4] / r1[7];
+                r[JT_SP_decrease] = r1[6] <= FLT_EPSILON ? 0.f : r1[5] / r1[6];
+                r[JT_SP_rolloff] = scale * (s_idx == 0x7fffffff ? 0 : s_idx);
+            }
         }
     }
 }
@@ -200,8 +207,8 @@ void jt_aspectralstats_launch(jt_ctx *c, const Sig &in0, int win, const std::vec
     }
     const int64_t n_items = wanted ? (int64_t)pd.items.size() : pd.n_hops;
     pd.n_items = n_items;
-    std::vector<float2> tw(win / 2); std::vector<float> lut(win);
-    for (int k = 0; k < win / 2; k++) { double a = -2.0 * M_PI * k / win; tw[k] = make_float2((float)cos(a), (float)sin(a)); }
+    std::vector<float2> tw(win); std::vector<float> lut(win);
+    for (int k = 0; k < win; k++) { double a = -2.0 * M_PI * k / win; tw[k] = make_float2((float)cos(a), (float)sin(a)); }
     for (int i = 0; i < win; i++) lut[i] = (float)(.5 * (1 - cos(2 * M_PI * i / (win - 1))));
     const float2 *d_tw = jt_dev_table(c, "spectral_tw", tw); const float *d_lut = jt_dev_table(c, "spectral_hann", lut);
     int64_t *d_items = nullptr, *d_prev = nullptr;
@@ -215,10 +222,12 @@ void jt_aspectralstats_launch(jt_ctx *c, const Sig &in0, int win, const std::vec
     }
     float *d_mags = jt_dalloc<float>(c, (size_t)n_items * (win / 2));
     float *d_rows = jt_dalloc<float>(c, (size_t)n_items * JT_SP_COUNT);
-    const int grid = jt_grid_for(n_items, 1, c->num_sms, 16);
+    const int grid = jt_grid_for((n_items + 1) / 2, 1, c->num_sms, 8);
+    const size_t smem_sp = sizeof(float2) * 3 * (size_t)win + sizeof(float) * (win / 2);
+    JT_CUDA(cudaFuncSetAttribute(k_spectral, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sp));
     {
         JtLaunch L(c, "aspectralstats", 2);
-        k_spectral<<<grid, SP_THREADS, sizeof(float2) * win, c->stream>>>((const float *)in.d, in.n, win, in.rate, n_items, d_items, d_tw, d_lut, d_mags, d_rows);
+        k_spectral<<<grid, SP_THREADS, smem_sp, c->stream>>>((const float *)in.d, in.n, win, in.rate, n_items, d_items, d_tw, d_lut, d_mags, d_rows);
         k_spectral_flux<<<grid, 256, 0, c->stream>>>(d_mags, win / 2, n_items, d_prev, d_rows);
     }
     pd.h_rows = jt_pinned<float>(c, (size_t)n_items * JT_SP_COUNT);

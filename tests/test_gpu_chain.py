@@ -114,3 +114,26 @@ def test_cancel_and_reuse(ctx):
     b = ctx.run_graph(gpudsp.pass1_spec(), x, 48000, want_pcm=False)
     assert [m.r128_M for m in a["meta"][5:10]] == [m.r128_M for m in b["meta"][5:10]]     # deterministic, ctx reusable
     assert ctx.launch_count() > 0
+
+
+# a7: MeasureOutputRegions / measureOutputRegionFromReader (analyser_output.go:95-313) -- the region graph of
+# analyser_output.go:18 on the s16 44.1 kHz Pass-2 / Pass-4 output, room-tone and speech regions
+REGION_SPEC = ("atrim=start=%f:duration=%f,asetpts=PTS-STARTPTS,astats=metadata=1:measure_perchannel=0,"
+               "aspectralstats=measure=all,ebur128=metadata=1:peak=sample+true")
+
+
+@pytest.mark.parametrize("start,duration", [(0.0, 8.0), (12.25, 10.0), (31.7, 60.0), (39.99, 5.0)])
+def test_output_region_measure(ctx, speech, start, duration):
+    pcm = np.clip(np.round(synth.speech_like(40.0, 44100, seed=4242) * 32768.0), -32768, 32767).astype(np.int16)
+    spec = REGION_SPEC % (start, duration)
+    got = ctx.run_graph(spec, pcm, 44100, want_pcm=False)
+    exp = OG.run_spec(spec, pcm, 44100, want_pcm=False)
+    OG.assert_meta_close(got["meta"], exp["meta"])
+    # what the reference keeps of it (analyser_output.go:134-169): last M / S / TP / SP, astats Overall, spectral means
+    last = [m for m in got["meta"] if not math.isnan(m.r128_M)]
+    elast = [m for m in exp["meta"] if not math.isnan(m["M"])]
+    assert len(last) == len(elast)
+    if last:
+        assert abs(last[-1].r128_M - elast[-1]["M"]) < 0.0011 and abs(last[-1].r128_true_peak - elast[-1]["true_peak"]) < 0.0011
+    ov = [m for m in got["meta"] if not math.isnan(m.astats_overall_RMS_level)]
+    assert len(ov) == 1 and all(math.isnan(v) for v in ov[0].astats)         # measure_perchannel=0: Overall keys only

@@ -27,7 +27,9 @@ def check_equal(m, iv, m1, iv1):
     for k in ("input_i", "input_tp", "input_sp", "input_lra", "last_m", "last_s", "sink_frames", "spectral_frames", "duration_s"):
         assert getattr(m, k) == getattr(m1, k), (k, getattr(m, k), getattr(m1, k))
     for k, name in enumerate(gpudsp.SP_NAMES):
-        assert same(m.spectral_mean[k], m1.spectral_mean[k], 1e-12), (name, m.spectral_mean[k], m1.spectral_mean[k])
+        # two hops share one complex FFT, and WHICH hops are paired depends on the cut: f32 round-off of the partner
+        # hop leaks in at the 1e-7 level (then "%g" prints 6 digits)
+        assert same(m.spectral_mean[k], m1.spectral_mean[k], 2e-5), (name, m.spectral_mean[k], m1.spectral_mean[k])
     for k, name in enumerate(gpudsp.AS_NAMES):
         if name in EXACT_ASTATS:
             assert same(m.astats[k], m1.astats[k], 1e-9), (name, m.astats[k], m1.astats[k])
@@ -40,7 +42,7 @@ def check_equal(m, iv, m1, iv1):
                   "frame_count", "spectral_found"):
             assert getattr(a, k) == getattr(b, k), (k, getattr(a, k), getattr(b, k))
         for k in range(gpudsp.SP_COUNT):
-            assert a.spectral[k] == b.spectral[k]
+            assert same(a.spectral[k], b.spectral[k], 2e-5), (k, a.spectral[k], b.spectral[k])
 
 
 @pytest.fixture(scope="module")
