@@ -42,11 +42,6 @@ extern "C" int jt_create(int device, jt_ctx **out)
     jt_ctx *c = new jt_ctx();
     c->device = device; c->num_sms = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return JT_ERR_CUDA; }
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-        uint64_t thr = UINT64_MAX;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-    }
     *out = c;
     return JT_OK;
 }
@@ -61,6 +56,7 @@ extern "C" void jt_destroy(jt_ctx *c)
     if (c->pin_out) cudaFreeHost(c->pin_out);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (auto &kv : c->dev_tables) cudaFree(kv.second);
+    for (auto &sl : c->slabs) cudaFree(sl.base);
     for (auto &b : c->pin_blocks) cudaFreeHost(b.first);
     for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }

@@ -26,6 +26,13 @@ struct jt_ctx {
     struct Pending { cudaEvent_t a, b; int slot; };
     std::vector<Pending> pending;
     std::vector<void *> allocs;        // freed by jt_release_all at the end of each API call
+    // Device arena: slabs from cudaMalloc, first-fit free lists.  Everything runs on ONE stream, so a block may be
+    // handed out again as soon as it is released on the host -- later work is ordered behind its last user -- and
+    // steady-state steps never enter the driver's allocator (whose pool growth showed up as 60-450 ms stalls).
+    struct Slab { char *base = nullptr; size_t size = 0; std::map<size_t, size_t> free_list; };   // offset -> length
+    std::vector<Slab> slabs;
+    std::map<void *, size_t> live;     // pointer -> bytes
+    size_t live_bytes = 0, peak_bytes = 0;
     std::vector<void *> host_allocs;   // pinned staging
     void *pin_in = nullptr; size_t pin_in_bytes = 0;
     void *pin_out = nullptr; size_t pin_out_bytes = 0;

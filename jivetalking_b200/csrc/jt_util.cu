@@ -3,27 +3,92 @@
 #include "jt_internal.h"
 #include "jt_device.cuh"
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <iterator>
 
 // ---------------------------------------------------------------------------------------
 // context / memory / launch bookkeeping
 // ---------------------------------------------------------------------------------------
+static void *arena_take(jt_ctx *c, size_t bytes)
+{
+    for (auto &sl : c->slabs) {
+        for (auto it = sl.free_list.begin(); it != sl.free_list.end(); ++it) {
+            if (it->second < bytes) continue;
+            const size_t off = it->first, len = it->second;
+            sl.free_list.erase(it);
+            if (len > bytes) sl.free_list[off + bytes] = len - bytes;
+            return sl.base + off;
+        }
+    }
+    return nullptr;
+}
+
+static void arena_give(jt_ctx *c, void *p, size_t bytes)
+{
+    for (auto &sl : c->slabs) {
+        if ((char *)p < sl.base || (char *)p >= sl.base + sl.size) continue;
+        size_t off = (char *)p - sl.base, len = bytes;
+        auto nx = sl.free_list.lower_bound(off);
+        if (nx != sl.free_list.end() && off + len == nx->first) { len += nx->second; nx = sl.free_list.erase(nx); }
+        if (nx != sl.free_list.begin()) { auto pv = std::prev(nx); if (pv->first + pv->second == off) { off = pv->first; len += pv->second; sl.free_list.erase(pv); } }
+        sl.free_list[off] = len;
+        return;
+    }
+}
+
 void *jt_dalloc_bytes(jt_ctx *c, size_t bytes)
 {
-    void *p = nullptr;
-    bytes = (bytes + 255) & ~size_t(255);
-    cudaError_t e = cudaMallocAsync(&p, bytes, c->stream);
-    if (e != cudaSuccess) JT_THROW(JT_ERR_NOMEM, "cudaMallocAsync(%zu): %s", bytes, cudaGetErrorString(e));
+    bytes = (std::max<size_t>(bytes, 1) + 511) & ~size_t(511);
+    void *p = arena_take(c, bytes);
+    if (!p) {
+        // grow: a new slab at least as large as everything allocated so far (the arena doubles), so a stream of a
+        // given length settles after its first step; jt_release_all then merges the slabs into one
+        size_t total = 0; for (auto &sl : c->slabs) total += sl.size;
+        const size_t want = std::max<size_t>(std::max<size_t>(bytes, total), (size_t)256 << 20);
+        jt_ctx::Slab sl;
+        cudaError_t e = cudaMalloc((void **)&sl.base, want);
+        sl.size = want;
+        if (e != cudaSuccess && want > bytes) { cudaGetLastError(); e = cudaMalloc((void **)&sl.base, bytes); sl.size = bytes; }
+        if (e != cudaSuccess) { cudaGetLastError(); JT_THROW(JT_ERR_NOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e)); }
+        sl.free_list[0] = sl.size;
+        c->slabs.push_back(sl);
+        p = arena_take(c, bytes);
+    }
+    c->live[p] = bytes; c->live_bytes += bytes; c->peak_bytes = std::max(c->peak_bytes, c->live_bytes);
     c->allocs.push_back(p);
     return p;
 }
 
+static void arena_release(jt_ctx *c, void *p)
+{
+    auto it = c->live.find(p);
+    if (it == c->live.end()) return;
+    c->live_bytes -= it->second;
+    arena_give(c, p, it->second);
+    c->live.erase(it);
+}
+
 void jt_release_all(jt_ctx *c)
 {
-    for (void *p : c->allocs) cudaFreeAsync(p, c->stream);
+    for (void *p : c->allocs) arena_release(c, p);
     c->allocs.clear();
     c->pin_block = 0; c->pin_used = 0; c->events_used = 0;       // the API call that owned them is over
+    // several slabs (the arena grew during this call): replace them by one that holds the call's peak with headroom
+    if (c->slabs.size() > 1 && c->live.empty()) {
+        cudaStreamSynchronize(c->stream);
+        size_t total = 0; for (auto &sl : c->slabs) { total += sl.size; cudaFree(sl.base); }
+        c->slabs.clear();
+        jt_ctx::Slab sl;
+        size_t want = std::max(total, c->peak_bytes + c->peak_bytes / 4);
+        if (cudaMalloc((void **)&sl.base, want) != cudaSuccess) {
+            cudaGetLastError(); want = c->peak_bytes + ((size_t)64 << 20);
+            if (cudaMalloc((void **)&sl.base, want) != cudaSuccess) { cudaGetLastError(); return; }
+        }
+        sl.size = want; sl.free_list[0] = want;
+        c->slabs.push_back(sl);
+    }
 }
 
 const void *jt_dev_table(jt_ctx *c, const char *tag, const void *host, size_t bytes)
@@ -75,7 +140,7 @@ void jt_release_since(jt_ctx *c, size_t mark, const void *keep)
     std::vector<void *> kept(c->allocs.begin(), c->allocs.begin() + std::min(mark, c->allocs.size()));
     for (size_t i = mark; i < c->allocs.size(); i++) {
         if (c->allocs[i] == keep) kept.push_back(c->allocs[i]);
-        else cudaFreeAsync(c->allocs[i], c->stream);
+        else arena_release(c, c->allocs[i]);
     }
     c->allocs.swap(kept);
 }
@@ -129,6 +194,9 @@ void jt_flush_timing(jt_ctx *c)
             for (size_t i = 0; i < c->slots.size(); i++) if (c->slots[i].name == nm) { gs = (int)i; break; }
             if (gs < 0) { c->slots.push_back(JtTimingSlot{nm, 0, 0}); gs = (int)c->slots.size() - 1; }
             c->slots[gs].ms += ms; c->slots[gs].launches++;
+            if (ms > 50.f && getenv("JT_DEBUG_GAPS"))
+                fprintf(stderr, "[jtdsp] device idle %.1f ms before %s (kernel group #%zu of %zu since the last flush)\n", ms,
+                        c->slots[p.slot].name.c_str(), (size_t)(&p - &c->pending[0]), c->pending.size());
         }
         done.push_back(p.a);
         prev_end = p.b;

@@ -22,7 +22,7 @@
 #define NLM_U 8
 #define NLM_MAXWARPS 16
 
-struct NlmK { float sw, smooth, lut_scale, inv_lut_scale; };
+struct NlmK { float sw, smooth, lut_scale, inv_lut_scale, maybe; };   // maybe: distances below it MAY pass d*sw < smooth (superset test)
 
 // weights of one sample for this thread's two lags; returns true when either lag is inside the cut-off
 __device__ __forceinline__ bool nlm_weights(float c1, float c2, float x1, float x2, const NlmK &k, float &pw, float &qw)
@@ -111,10 +111,9 @@ k_anlmdn(const float *__restrict__ x, float *__restrict__ y, int64_t n, int K, i
                         const float a2 = __fsub_rn(ao, q2[ci + u]), b2 = __fsub_rn(an, q3[ci + u]);
                         c1 = __fadd_rn(c1, __fadd_rn(-__fmul_rn(a1, a1), __fmul_rn(b1, b1)));
                         c2 = __fadd_rn(c2, __fadd_rn(-__fmul_rn(a2, a2), __fmul_rn(b2, b2)));
-                        if (c1 < 0.f) c1 = 0.f;
-                        if (c2 < 0.f) c2 = 0.f;
+                        c1 = fmaxf(c1, 0.f); c2 = fmaxf(c2, 0.f);        // "if (d < 0) d = 0"
                         d1[u] = c1; d2[u] = c2;
-                        any |= !(__fmul_rn(c1, P.sw) >= P.smooth) || !(__fmul_rn(c2, P.sw) >= P.smooth);
+                        any |= !(fminf(c1, c2) >= P.maybe);            // cheap superset of (d * sw < smooth); the exact test follows
                     }
                     if (__any_sync(0xffffffffu, any && live)) {
 #pragma unroll
@@ -181,6 +180,7 @@ Sig jt_anlmdn(jt_ctx *c, const Sig &in, double strength, double patch_s, double 
     const int grid = jt_grid_for(n_hops, 1, c->num_sms, 64);
     JtLaunch L(c, "anlmdn");
     NlmK P; P.sw = sw; P.smooth = smooth; P.lut_scale = lut_scale; P.inv_lut_scale = 1.f / lut_scale;
+    P.maybe = (smooth / sw) * 1.0001f;
     k_anlmdn<<<grid, threads, smem, c->stream>>>((const float *)in.d, (float *)o.d, in.n, K, S, P, n_hops);
     return o;
 }
