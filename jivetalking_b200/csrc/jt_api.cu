@@ -680,12 +680,8 @@ static void process_device(jt_ctx *c, const void *d_in, int64_t n_frames, int ra
     GraphRun g3;
     jt_graph_enqueue(c, spec3, g2.out.d, g2.out.n, 44100, 1, JT_FMT_S16, 4096, false, false, g3);
     jt_release_since(c, mark3, nullptr);
-    // Pass 2: host part, while the GPU finishes Pass 2's analysis tail and runs Pass 3
-    {
-        GraphResult r2;
-        jt_graph_finish(c, g2, r2);
-        MeasAcc a; for (auto &m : r2.meta) a.add(m); a.finish((double)g2.out.n / g2.out.rate); R.filtered = a.m;
-    }
+    // Pass 3's four numbers gate everything that follows: wait for them first (the GPU is still busy with Pass 2's
+    // analysis tail and Pass 3 itself), so Pass 4 can be enqueued before any other host work
     {
         GraphResult r3;
         jt_graph_finish(c, g3, r3);
@@ -702,6 +698,12 @@ static void process_device(jt_ctx *c, const void *d_in, int64_t n_frames, int ra
     GraphRun g4;
     jt_graph_enqueue(c, spec4, g2.out.d, g2.out.n, 44100, 1, JT_FMT_S16, 4096, true, true, g4);
     R.n_out = g4.out.n;
+    // Pass 2: host part (sink-frame records, accumulators), while the GPU runs Pass 4
+    {
+        GraphResult r2;
+        jt_graph_finish(c, g2, r2);
+        MeasAcc a; for (auto &m : r2.meta) a.add(m); a.finish((double)g2.out.n / g2.out.rate); R.filtered = a.m;
+    }
     if (pcm_out) {                                 // the result leaves while the host assembles Pass 4's metadata
         if (g4.out.n > cap) JT_THROW(JT_ERR_BUFFER, "pcm_out holds %lld samples, chain produced %lld", (long long)cap, (long long)g4.out.n);
         const size_t ob = (size_t)g4.out.n * sizeof(int16_t);
