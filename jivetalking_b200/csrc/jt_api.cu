@@ -651,18 +651,17 @@ static void process_device(jt_ctx *c, const void *d_in, int64_t n_frames, int ra
     jt_process_result R; memset(&R, 0, sizeof(R));
     const double tI = -16.0, tTP = -1.0, tLRA = 20.0;          // defaultLoudnormConfig, filters.go:523-532
     const size_t mark = c->allocs.size();
-    // Pass 1 and Pass 2: device work (Pass 2 reads the input only; its spec comes from the caller)
-    AnalysePending p1;
-    analyse_enqueue(c, d_in, n_frames, rate, channels, fmt, 4096, p1);
-    jt_release_since(c, mark, nullptr);
-    jt_check_cancel(c);
+    // Pass 1 and Pass 2: device work.  Both read the input only (Pass 2's spec comes from the caller), so Pass 2's
+    // long kernels go first and the integer bookkeeping of Pass 1's 200 000 frames happens behind them
     GraphRun g2;
     jt_graph_enqueue(c, pass2_spec ? pass2_spec : PASS2_DEFAULT_SPEC, d_in, n_frames, rate, channels, fmt, 4096, true, true, g2);
     if (g2.out.fmt != JT_FMT_S16 || g2.out.rate != 44100) JT_THROW(JT_ERR_SPEC, "Pass-2 spec must end in the s16/44.1 kHz output stage (processor.go:379-384)");
     jt_release_since(c, mark, g2.out.d);          // keep only the Pass-2 output ("the FLAC on disk")
-    // Pass 1: host part, while the GPU runs Pass 2
-    analyse_finish(c, p1, &R.input, nullptr, 0, nullptr);
     jt_check_cancel(c);
+    const size_t mark1 = c->allocs.size();
+    AnalysePending p1;
+    analyse_enqueue(c, d_in, n_frames, rate, channels, fmt, 4096, p1);
+    jt_release_since(c, mark1, nullptr);
     // Pass 3 is planned from Pass 2's integrated loudness and true peak as the sink frames report them
     // (last-seen values of lavfi.r128.I / true_peak, "%.3f": analyser_metrics.go:898-923)
     double out_i = 0.0, out_tp = 0.0;
@@ -680,6 +679,9 @@ static void process_device(jt_ctx *c, const void *d_in, int64_t n_frames, int ra
     GraphRun g3;
     jt_graph_enqueue(c, spec3, g2.out.d, g2.out.n, 44100, 1, JT_FMT_S16, 4096, false, false, g3);
     jt_release_since(c, mark3, nullptr);
+    // Pass 1: host part, while the GPU runs Pass 1 and Pass 3
+    analyse_finish(c, p1, &R.input, nullptr, 0, nullptr);
+    jt_check_cancel(c);
     // Pass 3's four numbers gate everything that follows: wait for them first (the GPU is still busy with Pass 2's
     // analysis tail and Pass 3 itself), so Pass 4 can be enqueued before any other host work
     {

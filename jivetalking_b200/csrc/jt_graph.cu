@@ -145,6 +145,7 @@ extern "C" double jt_debug_wire(const char *fmt, double v, int text) { return te
 static std::vector<FrameRef> source_frames(int64_t n, int F)
 {
     std::vector<FrameRef> v;
+    v.reserve((size_t)((n + F - 1) / std::max(F, 1)));
     for (int64_t s = 0; s < n; s += F) {
         FrameRef f; f.start = s; f.nb = (int32_t)std::min<int64_t>(F, n - s); f.ready = s + f.nb;
         v.push_back(f);
@@ -158,6 +159,7 @@ static std::vector<FrameRef> source_frames(int64_t n, int F)
 static std::vector<FrameRef> reframe(const std::vector<FrameRef> &old, int64_t n, int F)
 {
     std::vector<FrameRef> v;
+    v.reserve((size_t)((n + F - 1) / std::max(F, 1)));
     size_t a = 0, b = 0;
     for (int64_t s = 0; s < n; s += F) {
         FrameRef f; f.start = s; f.nb = (int32_t)std::min<int64_t>(F, n - s);

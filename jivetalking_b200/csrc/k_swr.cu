@@ -131,51 +131,64 @@ template <int PC> struct SmallBank { double f[PC * 32]; };
 
 enum { SWR_MODE_STORE = 0, SWR_MODE_TICKMAX = 1 };
 
-// thread <-> period q, all PC phases in registers; L == 32, div == 1 (integer upsampling)
+// thread <-> TWO periods (2t, 2t+1), all PC phases of both in registers; L == 32, div == 1 (integer
+// upsampling).  The two periods share 31 of their 32 taps' samples, so one shared-memory load feeds 2*PC DFMA
+// instead of PC (the kernel was bound by 64-bit shared-memory loads as much as by the FP64 pipe); the tile is
+// staged as even / odd samples so that the lanes of a load read consecutive addresses.
 template <class TIN, int PC, int MODE>
 __global__ void __launch_bounds__(256)
 k_swr_small(const TIN *__restrict__ x, int64_t n, int64_t n_periods, int64_t n_out,
             const __grid_constant__ SmallBank<PC> bank, double *__restrict__ out,
             double *__restrict__ tick_max, int tick, int64_t n_ticks)
 {
-    constexpr int L = 32, C = (L - 1) / 2;
-    __shared__ double sx[256 + L];
-    const int64_t tiles = (n_periods + 255) / 256;
+    constexpr int L = 32, C = (L - 1) / 2, TP = 512;              // periods per tile
+    __shared__ double sev[TP / 2 + L], sod[TP / 2 + L];          // x[base + 2k], x[base + 2k + 1]
+    const int64_t tiles = (n_periods + TP - 1) / TP;
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const int64_t q0 = tile * 256;
+        const int64_t q0 = tile * TP;
         const int64_t base = q0 - C;                 // first tap of period q0
         __syncthreads();
-        for (int i = threadIdx.x; i < 256 + L; i += 256) sx[i] = swr_load<TIN, double>(x, base + i, n);
-        __syncthreads();
-        const int64_t q = q0 + threadIdx.x;
-        double acc[PC];
-#pragma unroll
-        for (int r = 0; r < PC; r++) acc[r] = 0.0;
-#pragma unroll
-        for (int i = 0; i < L; i++) {
-            const double v = sx[threadIdx.x + i];
-#pragma unroll
-            for (int r = 0; r < PC; r++) acc[r] = fma(v, bank.f[r * L + i], acc[r]);
+        for (int i = threadIdx.x; i < TP + L; i += 256) {
+            const double v = swr_load<TIN, double>(x, base + i, n);
+            if (i & 1) sod[i >> 1] = v; else sev[i >> 1] = v;
         }
-        if (MODE == SWR_MODE_STORE) {
-            if (q < n_periods) {
+        __syncthreads();
+        double acc[2][PC];
 #pragma unroll
-                for (int r = 0; r < PC; r++) { int64_t m = q * PC + r; if (m < n_out) out[m] = acc[r]; }
-            }
-        } else {
-            double mx = 0.0; int64_t k = -1;
-            if (q < n_periods) {
+        for (int r = 0; r < PC; r++) { acc[0][r] = 0.0; acc[1][r] = 0.0; }
+        // sample x[2t + i], i = 0 .. L: tap i of period 2t and tap i-1 of period 2t+1 (sums stay in tap order)
 #pragma unroll
-                for (int r = 0; r < PC; r++) { int64_t m = q * PC + r; if (m < n_out) mx = fmax(mx, fabs(acc[r])); }
-                int64_t need = q - C + L; if (need < L + 1) need = L + 1;     // inputs swr must have seen
-                k = (need + tick - 1) / tick - 1;
+        for (int i = 0; i <= L; i++) {
+            const double v = (i & 1) ? sod[threadIdx.x + (i >> 1)] : sev[threadIdx.x + (i >> 1)];
+#pragma unroll
+            for (int r = 0; r < PC; r++) {
+                if (i < L) acc[0][r] = fma(v, bank.f[r * L + i], acc[0][r]);
+                if (i >= 1) acc[1][r] = fma(v, bank.f[r * L + i - 1], acc[1][r]);
             }
-            const int64_t k0 = __shfl_sync(0xffffffffu, k, 0);
-            const bool uni = __all_sync(0xffffffffu, k == k0);
-            if (uni) {
-                mx = jt_warp_max(mx);
-                if ((threadIdx.x & 31) == 0 && k0 >= 0 && k0 < n_ticks) jt_atomic_max_nonneg(&tick_max[k0], mx);
-            } else if (k >= 0 && k < n_ticks) jt_atomic_max_nonneg(&tick_max[k], mx);
+        }
+#pragma unroll
+        for (int p = 0; p < 2; p++) {
+            const int64_t q = q0 + 2 * threadIdx.x + p;
+            if (MODE == SWR_MODE_STORE) {
+                if (q < n_periods) {
+#pragma unroll
+                    for (int r = 0; r < PC; r++) { int64_t m = q * PC + r; if (m < n_out) out[m] = acc[p][r]; }
+                }
+            } else {
+                double mx = 0.0; int64_t k = -1;
+                if (q < n_periods) {
+#pragma unroll
+                    for (int r = 0; r < PC; r++) { int64_t m = q * PC + r; if (m < n_out) mx = fmax(mx, fabs(acc[p][r])); }
+                    int64_t need = q - C + L; if (need < L + 1) need = L + 1;     // inputs swr must have seen
+                    k = (need + tick - 1) / tick - 1;
+                }
+                const int64_t k0 = __shfl_sync(0xffffffffu, k, 0);
+                const bool uni = __all_sync(0xffffffffu, k == k0);
+                if (uni) {
+                    mx = jt_warp_max(mx);
+                    if ((threadIdx.x & 31) == 0 && k0 >= 0 && k0 < n_ticks) jt_atomic_max_nonneg(&tick_max[k0], mx);
+                } else if (k >= 0 && k < n_ticks) jt_atomic_max_nonneg(&tick_max[k], mx);
+            }
         }
     }
 }
@@ -463,7 +476,7 @@ static void launch_small(jt_ctx *c, const Sig &in, const SwrPlan &p, int64_t n_o
                          double *tick_max, int tick, int64_t n_ticks)
 {
     const int64_t n_periods = (n_out + p.phase_count - 1) / p.phase_count;
-    const int grid = jt_grid_for(n_periods, 256, c->num_sms, 16);
+    const int grid = jt_grid_for(n_periods, 512, c->num_sms, 16);
 #define SMALL_CASE(PCV) case PCV: { SmallBank<PCV> b; for (int i = 0; i < PCV * 32; i++) b.f[i] = p.bank[i]; \
         k_swr_small<TIN, PCV, MODE><<<grid, 256, 0, c->stream>>>((const TIN *)in.d, in.n, n_periods, n_out, b, out, tick_max, tick, n_ticks); } break;
     switch (p.phase_count) { SMALL_CASE(2) SMALL_CASE(4) SMALL_CASE(6) SMALL_CASE(8) default: JT_THROW(JT_ERR_UNSUPPORTED, "small pc"); }
