@@ -141,7 +141,7 @@ k_dc_detect(const double *__restrict__ x, int64_t n, int64_t n_windows, DcConst 
 }
 
 // ---- E: interpolation ----------------------------------------------------------------------
-#define DC_WARPS 4
+#define DC_WARPS 5          // 20.7 KB of ring per warp: two 5-warp CTAs fill an SM's 227 KB
 __global__ void __launch_bounds__(DC_WARPS * 32)
 k_dc_interp(const double *__restrict__ x, double *__restrict__ y, int64_t n, int64_t n_windows, DcConst K,
             const double *__restrict__ acoef, const unsigned *__restrict__ bits_in, const int *__restrict__ count_in,
@@ -345,7 +345,7 @@ Sig jt_adeclick(jt_ctx *c, const Sig &in, double w_ms, double overlap_pct, doubl
     const size_t per_warp = ((size_t)K.bw * K.bw + 3 * (size_t)K.bw + (size_t)((K.nwords + 1) / 2)) * sizeof(double);
     const size_t smemE = per_warp * DC_WARPS;
     JT_CUDA(cudaFuncSetAttribute(k_dc_interp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemE));
-    int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / (smemE + 4096)));
+    int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (227 * 1024) / (smemE + 4096 + 1024)));
     int gridE = (int)std::min<int64_t>((nw + DC_WARPS - 1) / DC_WARPS, (int64_t)c->num_sms * per_sm);
     if (gridE < 1) gridE = 1;
     const size_t nmax = (size_t)K.W;

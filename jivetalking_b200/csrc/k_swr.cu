@@ -356,6 +356,8 @@ k_swr_qlane_f64(const TIN *__restrict__ x, int64_t n, int64_t n_periods, int64_t
 #pragma unroll
                 for (int j = 0; j < RMAX; j++) acc[t][j] = 0.0;
             const int sA = lane * div + off, sB = sA + 32 * div;
+            // eight taps per trip: the warp-uniform coefficient loads of a trip are issued together, ahead of the FMAs
+#pragma unroll 4
             for (int i = 0; i < L; i += 2) {
                 const int a0 = sA + i, a1 = a0 + 1, b0 = sB + i, b1 = b0 + 1;
                 const double xa0 = sx[a0 + (a0 >> 5)], xa1 = sx[a1 + (a1 >> 5)], xb0 = sx[b0 + (b0 >> 5)], xb1 = sx[b1 + (b1 >> 5)];
