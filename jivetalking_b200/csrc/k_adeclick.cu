@@ -211,12 +211,15 @@ k_dc_interp(const double *__restrict__ x, double *__restrict__ y, int64_t n, int
             for (int i = lane; i < nclk; i += 32) {
                 const int ii = idx[i];
                 double value = 0.;
+                // a flagged neighbour contributes a +0.0 product (value - 0.0 == value bit for bit), so the products
+                // of four taps are formed ahead of the subtraction chain instead of one multiply per dependent step
+#pragma unroll 4
                 for (int j = -order; j <= order; j++) {
                     const int p = ii - j;
-                    if (!((sbits[p >> 5] >> (p & 31)) & 1u)) {
-                        const double xs = interior ? xw[p] : dc_sample(x, n, w, p, K);
-                        value = jdsub(value, jdmul(xs, aux[j < 0 ? -j : j]));
-                    }
+                    const bool known = !((sbits[p >> 5] >> (p & 31)) & 1u);
+                    const double xs = interior ? xw[p] : dc_sample(x, n, w, p, K);
+                    const double pr = known ? jdmul(xs, aux[j < 0 ? -j : j]) : 0.0;
+                    value = jdsub(value, pr);
                 }
                 vec[i] = value;
             }
@@ -233,9 +236,9 @@ k_dc_interp(const double *__restrict__ x, double *__restrict__ y, int64_t n, int
                 if (d <= order) RINGS(rj, WRAP(rj + bw - t)) = aux[d];
                 if (!__ballot_sync(0xffffffffu, d <= order && lane == 31)) break;      // sorted: nothing further couples
             }
-            if (lane == 0) vring[rj] = vec[j];
         };
         for (int j = 0; j <= order; j++) load_row(j, j);
+        for (int j = lane; j <= order && j < nclk; j += 32) vring[j] = vec[j];
         __syncwarp();
         bool ok = true;
         int rk = 0;
@@ -252,6 +255,7 @@ k_dc_interp(const double *__restrict__ x, double *__restrict__ y, int64_t n, int
                 amax = __popc(__ballot_sync(0xffffffffu, c0)) + __popc(__ballot_sync(0xffffffffu, c1));
             }
             const double yk = vring[rk];
+            const double v_in = (lane == 0 && k + bw < nclk) ? vec[k + bw] : 0.0;      // right-hand side of the row entering below: fetched early
             // column k: L(j,k) = A'(j,k) / D_k ; forward substitution v_j -= L(j,k) * y_k
             for (int a = lane + 1; a <= amax; a += 32) {
                 const int ra = WRAP(rk + a);
@@ -260,7 +264,7 @@ k_dc_interp(const double *__restrict__ x, double *__restrict__ y, int64_t n, int
                 Lg[(size_t)k * order + (a - 1)] = L;
                 vring[ra] = jdsub(vring[ra], jdmul(L, yk));
             }
-            if (lane == 0) { yd[k] = yk / Dk; am[k] = amax; }
+            if (lane == 0) { yd[k] = yk; outv[k] = Dk; am[k] = amax; }      // y_k / D_k is formed after the loop, off the critical path
             __syncwarp();
             // trailing update: A'(k+a, k+b) -= (D_k * L(k+b,k)) * L(k+a,k), 1 <= b <= a <= amax
             const int npairs = amax * (amax + 1) / 2;
@@ -270,10 +274,14 @@ k_dc_interp(const double *__restrict__ x, double *__restrict__ y, int64_t n, int
                 RINGS(ra, rb) = jdsub(RINGS(ra, rb), jdmul(jdmul(Dk, Lb), La));
             }
             load_row(k + bw, rk);           // row k+order+1 takes the slot row k leaves (no trailing update touches it)
+            if (lane == 0 && k + bw < nclk) vring[rk] = v_in;
             __syncwarp();
             rk = rk + 1 == bw ? 0 : rk + 1;
         }
         if (!ok) continue;                  // factorisation hit a zero pivot: af_adeclick.c leaves the window as is
+        __syncwarp();
+        for (int i = lane; i < nclk; i += 32) yd[i] = yd[i] / outv[i];
+        __syncwarp();
         // back substitution: out_i = y_i / D_i - sum_{j>i} L(j,i) * out_j, j ascending.  Lane a keeps out_{i+1+a}
         // (and out_{i+33+a}) in registers; moving to i-1 shifts them up by one lane.
         {

@@ -17,7 +17,7 @@
 
 #define LIM_MAXBUF 512
 #define LIM_R 32
-typedef LaneStage<double, LIM_R, 4> LimIn;      // 256-byte rows, 4-deep ring (x2 views) + output rows: 87 KB per warp
+typedef LaneStage<double, LIM_R, 2> LimIn;      // 256-byte rows, double-buffered (x2 views) + output rows: 52 KB per warp
 typedef LaneStore<double, LIM_R> LimOut;
 
 __global__ void __launch_bounds__(64)
@@ -154,9 +154,10 @@ Sig jt_alimiter(jt_ctx *c, const Sig &in, const LimiterParams &p)
     if (bs > LIM_MAXBUF) JT_THROW(JT_ERR_UNSUPPORTED, "alimiter lookahead of %d samples (max %d)", bs, LIM_MAXBUF);
     Sig o = in; o.d = jt_dalloc<double>(c, in.n);
     if (in.n <= 0) return o;
-    // one wave: 2 warps per SM hold their staging at once; segments grow before a second wave would start
-    const int64_t slots = (int64_t)c->num_sms * 2 * 32;
-    const int seg = (int)std::min<int64_t>(((std::max<int64_t>(16384, (in.n + slots - 1) / slots) + LIM_R - 1) / LIM_R) * LIM_R, 1 << 24);
+    // one wave: 4 warps per SM hold their staging at once (the walk is latency-bound per lane, and every lane pays
+    // the 0.6 s warm-up, so more, shorter lanes finish sooner); segments grow before a second wave would start
+    const int64_t slots = (int64_t)c->num_sms * 4 * 32;
+    const int seg = (int)std::min<int64_t>(((std::max<int64_t>(4096, (in.n + slots - 1) / slots) + LIM_R - 1) / LIM_R) * LIM_R, 1 << 24);
     int warm = (int)(in.rate * (0.5 + 2 * release + 2 * attack)) + 2 * bs;
     warm = (warm + LIM_R - 1) / LIM_R * LIM_R;                  // tile-aligned (see the kernel)
     const int64_t lanes = (in.n + seg - 1) / seg;
