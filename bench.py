@@ -43,6 +43,26 @@ KERNEL_BYTES = {
 }
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch on the 60 min stream, from the `ncu --set full` captures
+# summarised in profiles/ncu_r1h.md (cold-cache replay; None where the kernel was not captured)
+NCU_TRAFFIC_BYTES_60MIN = {
+    "adeclick:interp": 1.627476e9 + 0.732643e9,
+    "anlmdn": 0.693577e9 + 0.652757e9,
+    "afftdn:fwd": 0.702286e9 + 2.324030e9,
+    "alimiter": 3.293223e9 + 1.231703e9,
+    "swr_resample:qlane_f64": 0.705825e9 + 1.226726e9,
+    "envelope_follower": 8.088364e9 + 1.335775e9,          # profiles/ncu_r1d.md
+    "r128_kweight_ticks": 1.383083e9 + 0.006421e9,         # profiles/ncu_r1d.md
+}
+# what actually bounds each group; the contract's roofline is reported against HBM regardless
+KERNEL_BOUND = {
+    "adeclick:interp": "latency (10 warps/SM, shared-memory round trips of the banded LDL^T k-loop)",
+    "anlmdn": "FP32 issue / shared-memory bandwidth",
+    "envelope_follower": "f64 dependent-issue latency (one warp per scheduler)",
+    "afftdn:fwd": "barriers of the shared-memory FFT + f64 tracking statistics",
+}
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -287,10 +307,13 @@ def main():
         "timing": {"method": "CUDA events on the library stream around the K steps (max over ranks)",
                    "wall_ms_per_step": 1e3 * t_wall / args.steps, "e2e_wall_ms_per_step": 1e3 * t_e2e_wall / args.steps},
         "roofline": {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak if peak else None, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak if peak else None,
+                     "traffic": NCU_TRAFFIC_BYTES_60MIN.get(dom[0]) if args.minutes == 60 else None,
+                     "traffic_source": "profiles/ncu_r1h.md (bytes per launch, ncu --set full)", "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": dom_bytes,
                      "kernel_ms_per_step": dom_ms_per_step, "kernel_share_of_step": dom_ms_per_step / (1e3 * t_dev / args.steps),
                      "chain_frac": (BYTES_PER_SAMPLE_4PASS * n / (t_dev / args.steps) / 1e9) / peak,
-                     "note": "dominant kernel is FP32-ALU/latency bound, not HBM bound (DESIGN.md)"},
+                     "note": "not HBM bound: " + KERNEL_BOUND.get(dom[0], "latency / issue bound (DESIGN.md section 5)")},
         "kernels_ms_per_step": {t[0]: round(t[1] / args.steps, 3) for t in timings},
         "kernel_ms_total_per_step": kernel_ms,
         "device_idle_ms_per_step": {g[0][4:]: round(g[1] / args.steps, 3) for g in sorted(gaps, key=lambda g: -g[1])[:12]},
