@@ -153,6 +153,11 @@ k_swr_small(const TIN *__restrict__ x, int64_t n, int64_t n_periods, int64_t n_o
             if (i & 1) sod[i >> 1] = v; else sev[i >> 1] = v;
         }
         __syncthreads();
+        int64_t tile_k = 0, tile_lim = 0;
+        if (MODE == SWR_MODE_TICKMAX) {
+            int64_t nd0 = q0 - C + L; if (nd0 < L + 1) nd0 = L + 1;
+            tile_k = (nd0 + tick - 1) / tick - 1; tile_lim = (tile_k + 1) * (int64_t)tick;
+        }
         double acc[2][PC];
 #pragma unroll
         for (int r = 0; r < PC; r++) { acc[0][r] = 0.0; acc[1][r] = 0.0; }
@@ -180,7 +185,8 @@ k_swr_small(const TIN *__restrict__ x, int64_t n, int64_t n_periods, int64_t n_o
 #pragma unroll
                     for (int r = 0; r < PC; r++) { int64_t m = q * PC + r; if (m < n_out) mx = fmax(mx, fabs(acc[p][r])); }
                     int64_t need = q - C + L; if (need < L + 1) need = L + 1;     // inputs swr must have seen
-                    k = (need + tick - 1) / tick - 1;
+                    // one division per tile (warp-uniform operands), a compare per period: a tile spans 512 inputs, less than a tick
+                    k = tick >= TP + L + 2 ? (need > tile_lim ? tile_k + 1 : tile_k) : (need + tick - 1) / tick - 1;
                 }
                 const int64_t k0 = __shfl_sync(0xffffffffu, k, 0);
                 const bool uni = __all_sync(0xffffffffu, k == k0);
@@ -400,6 +406,120 @@ k_swr_qlane_f64(const TIN *__restrict__ x, int64_t n, int64_t n_periods, int64_t
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// f64 path, one PHASE per thread with its L coefficients in registers (64-72 registers), looping over the
+// periods of a staged tile: 1 shared-memory load per DFMA and no coefficient traffic at all.  The q-lane kernel
+// above re-fetches every coefficient row through the L1 for every tile and was bound by that latency (ncu:
+// long-scoreboard 5.4 per issue, FP64 pipe 7 %).  Consecutive phases read (almost) the same window, so the
+// lanes of a load hit a handful of addresses: conflict-free.  STORE collects QB periods in shared memory and
+// writes full rows; TICKMAX keeps a per-thread running maximum per 100 ms tick.
+// ---------------------------------------------------------------------------------------
+template <class TW> static const TW *device_bank(jt_ctx *c, const SwrPlan &p);
+
+template <class TIN, int L, int MODE, int NT>
+__global__ void __launch_bounds__(NT, NT > 320 ? 1 : 2)
+k_swr_phase_f64(const TIN *__restrict__ x, int64_t n, int64_t n_periods, int64_t n_out, int pc, int div, int qc,
+                const double *__restrict__ bank, double *__restrict__ out,
+                double *__restrict__ tick_max, int tick, int64_t n_ticks)
+{
+    constexpr int QB = 2;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int c = (L - 1) / 2;
+    const int span = qc * div + L + div;
+    double *sx = (double *)smem_raw;                     // span doubles
+    double *so = sx + span;                              // QB * pc doubles (STORE)
+    const int r = threadIdx.x;
+    const bool live = r < pc;
+    const int off = live ? (int)(((int64_t)r * div) / pc) : 0;
+    double cf[L];
+    {
+        const int ph = live ? (int)(((int64_t)r * div) % pc) : 0;
+#pragma unroll
+        for (int i = 0; i < L; i++) cf[i] = live ? bank[(size_t)ph * L + i] : 0.0;
+    }
+    const int64_t chunks = (n_periods + qc - 1) / qc;
+    for (int64_t ch = blockIdx.x; ch < chunks; ch += gridDim.x) {
+        const int64_t qa = ch * qc;
+        const int nq = (int)min((int64_t)qc, n_periods - qa);
+        const int64_t base = qa * div - c;
+        __syncthreads();
+        for (int i = threadIdx.x; i < span; i += NT) sx[i] = swr_load<TIN, double>(x, base + i, n);
+        __syncthreads();
+        // tick of an output = ceil(need / tick) - 1 with need = inputs swr must have seen: it grows by div per period,
+        // so it is tracked with a compare per output instead of a 64-bit division (which cost more than the 32 DFMAs)
+        double cur_max = 0.0; int64_t cur_k = -1;
+        int64_t need = qa * div - c + off + L, lim = 0;
+        if (MODE == SWR_MODE_TICKMAX) {
+            const int64_t nd = need < L + 1 ? L + 1 : need;
+            cur_k = (nd + tick - 1) / tick - 1; lim = (cur_k + 1) * (int64_t)tick;
+        }
+        for (int q0 = 0; q0 < nq; q0 += QB) {
+            double acc[QB];
+#pragma unroll
+            for (int b = 0; b < QB; b++) acc[b] = 0.0;
+            const double *w = sx + q0 * div + off;
+#pragma unroll
+            for (int i = 0; i < L; i++) {
+#pragma unroll
+                for (int b = 0; b < QB; b++) acc[b] = fma(w[b * div + i], cf[i], acc[b]);      // periods past nq read slack: never used
+                if ((i & 7) == 7) asm volatile("" ::: "memory");     // keep at most 8 taps of loads in flight: the registers hold the coefficients
+            }
+            if (MODE == SWR_MODE_STORE) {
+                if (live) {
+#pragma unroll
+                    for (int b = 0; b < QB; b++) so[b * pc + r] = acc[b];
+                }
+                __syncthreads();
+                const int nb = min(QB, nq - q0);
+                const int64_t m0 = (qa + q0) * (int64_t)pc;
+                const int64_t lim = min((int64_t)nb * pc, n_out - m0);
+                for (int i = threadIdx.x; i < lim; i += NT) out[m0 + i] = so[i];
+                __syncthreads();
+            } else if (live) {
+#pragma unroll
+                for (int b = 0; b < QB; b++) {
+                    const int64_t q = qa + q0 + b, m = q * pc + r;
+                    if (q0 + b < nq && m < n_out) {
+                        const int64_t nd = need + (int64_t)(q0 + b) * div;           // (values below L+1 clamp to L+1: same tick 0)
+                        while (nd > lim) {
+                            if (cur_k >= 0 && cur_k < n_ticks && cur_max > 0.0) jt_atomic_max_nonneg(&tick_max[cur_k], cur_max);
+                            cur_k++; lim += tick; cur_max = 0.0;
+                        }
+                        cur_max = fmax(cur_max, fabs(acc[b]));
+                    }
+                }
+            }
+        }
+        if (MODE == SWR_MODE_TICKMAX && cur_k >= 0 && cur_k < n_ticks) jt_atomic_max_nonneg(&tick_max[cur_k], cur_max);
+    }
+}
+
+static bool phase_path_ok(const SwrPlan &p)
+{
+    const int L = p.filter_length;
+    if (!(L == 32 || L == 36 || L == 72)) return false;
+    return p.phase_count >= 32 && p.phase_count <= 640 && p.div >= 2;
+}
+
+template <class TIN, int MODE>
+static void launch_phase_f64(jt_ctx *c, const Sig &in, const SwrPlan &p, int64_t n_out, double *out,
+                             double *tick_max, int tick, int64_t n_ticks)
+{
+    const double *d_bank = device_bank<double>(c, p);
+    const int pc = p.phase_count, div = p.div, L = p.filter_length;
+    const int64_t n_periods = (n_out + pc - 1) / pc;
+    int qc = std::max(2, std::min(64, (10 * 1024) / div / 2 * 2));        // periods per staged tile (~80 KB of doubles at most)
+    const int span = qc * div + L + div;
+    const size_t smem = sizeof(double) * ((size_t)span + (MODE == SWR_MODE_STORE ? 2 * (size_t)pc : 0)) + 16;
+    const int grid = jt_grid_for((n_periods + qc - 1) / qc, 1, c->num_sms, 8);
+#define PHASE_LAUNCH(LV, NTV) do { auto kfn = k_swr_phase_f64<TIN, LV, MODE, NTV>; \
+        JT_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        kfn<<<grid, NTV, smem, c->stream>>>((const TIN *)in.d, in.n, n_periods, n_out, pc, div, qc, d_bank, out, tick_max, tick, n_ticks); } while (0)
+    if (pc <= 160) { if (L == 32) PHASE_LAUNCH(32, 160); else if (L == 36) PHASE_LAUNCH(36, 160); else PHASE_LAUNCH(72, 160); }
+    else { if (L == 32) PHASE_LAUNCH(32, 640); else if (L == 36) PHASE_LAUNCH(36, 640); else PHASE_LAUNCH(72, 640); }
+#undef PHASE_LAUNCH
+}
+
 // device copy of the filter bank in the work format, cached per context (the plan is immutable)
 template <class TW>
 static const TW *device_bank(jt_ctx *c, const SwrPlan &p)
@@ -511,7 +631,7 @@ Sig jt_swr_resample(jt_ctx *c, const Sig &in, const SwrPlan &p, int work_fmt, bo
     Sig o; o.fmt = fuse_s16 ? JT_FMT_S16 : work_fmt; o.rate = p.out_rate; o.n = n_out;
     o.d = jt_dalloc_bytes(c, (size_t)std::max<int64_t>(n_out, 1) * jt_fmt_bytes(o.fmt));
     if (n_out <= 0) return o;
-    const char *kind = work_fmt == JT_FMT_DBL ? (small_path(p) ? "swr_resample:small_f64" : qlane_path_ok(p) ? "swr_resample:qlane_f64" : "swr_resample:generic")
+    const char *kind = work_fmt == JT_FMT_DBL ? (small_path(p) ? "swr_resample:small_f64" : phase_path_ok(p) ? "swr_resample:phase_f64" : qlane_path_ok(p) ? "swr_resample:qlane_f64" : "swr_resample:generic")
                                               : (slot_path_ok(p) ? (p.phase_count > p.div ? "swr_resample:slot_f32_up" : "swr_resample:slot_f32_down") : "swr_resample:generic");
     JtLaunch Lc(c, kind);
     if (work_fmt == JT_FMT_DBL) {
@@ -519,6 +639,10 @@ Sig jt_swr_resample(jt_ctx *c, const Sig &in, const SwrPlan &p, int work_fmt, bo
             if (in.fmt == JT_FMT_S16) launch_small<int16_t, SWR_MODE_STORE>(c, in, p, n_out, (double *)o.d, nullptr, 1, 0);
             else if (in.fmt == JT_FMT_FLT) launch_small<float, SWR_MODE_STORE>(c, in, p, n_out, (double *)o.d, nullptr, 1, 0);
             else launch_small<double, SWR_MODE_STORE>(c, in, p, n_out, (double *)o.d, nullptr, 1, 0);
+        } else if (phase_path_ok(p)) {
+            if (in.fmt == JT_FMT_S16) launch_phase_f64<int16_t, SWR_MODE_STORE>(c, in, p, n_out, (double *)o.d, nullptr, 1, 0);
+            else if (in.fmt == JT_FMT_FLT) launch_phase_f64<float, SWR_MODE_STORE>(c, in, p, n_out, (double *)o.d, nullptr, 1, 0);
+            else launch_phase_f64<double, SWR_MODE_STORE>(c, in, p, n_out, (double *)o.d, nullptr, 1, 0);
         } else if (qlane_path_ok(p)) {
             if (in.fmt == JT_FMT_S16) launch_qlane_f64<int16_t, SWR_MODE_STORE>(c, in, p, n_out, (double *)o.d, nullptr, 1, 0);
             else if (in.fmt == JT_FMT_FLT) launch_qlane_f64<float, SWR_MODE_STORE>(c, in, p, n_out, (double *)o.d, nullptr, 1, 0);
@@ -555,11 +679,15 @@ void jt_swr_tick_absmax(jt_ctx *c, const Sig &in, const SwrPlan &p, int tick, in
     Sig v = in; v.n = std::min(in.n, fed);
     const int64_t n_out = p.out_count(v.n);
     if (n_out <= 0) return;
-    JtLaunch Lc(c, small_path(p) ? "truepeak_oversample:small_f64" : qlane_path_ok(p) ? "truepeak_oversample:qlane_f64" : "truepeak_oversample:generic");
+    JtLaunch Lc(c, small_path(p) ? "truepeak_oversample:small_f64" : phase_path_ok(p) ? "truepeak_oversample:phase_f64" : qlane_path_ok(p) ? "truepeak_oversample:qlane_f64" : "truepeak_oversample:generic");
     if (small_path(p)) {
         if (v.fmt == JT_FMT_S16) launch_small<int16_t, SWR_MODE_TICKMAX>(c, v, p, n_out, nullptr, d_tick_tp, tick, n_ticks);
         else if (v.fmt == JT_FMT_FLT) launch_small<float, SWR_MODE_TICKMAX>(c, v, p, n_out, nullptr, d_tick_tp, tick, n_ticks);
         else launch_small<double, SWR_MODE_TICKMAX>(c, v, p, n_out, nullptr, d_tick_tp, tick, n_ticks);
+    } else if (phase_path_ok(p)) {
+        if (v.fmt == JT_FMT_S16) launch_phase_f64<int16_t, SWR_MODE_TICKMAX>(c, v, p, n_out, nullptr, d_tick_tp, tick, n_ticks);
+        else if (v.fmt == JT_FMT_FLT) launch_phase_f64<float, SWR_MODE_TICKMAX>(c, v, p, n_out, nullptr, d_tick_tp, tick, n_ticks);
+        else launch_phase_f64<double, SWR_MODE_TICKMAX>(c, v, p, n_out, nullptr, d_tick_tp, tick, n_ticks);
     } else if (qlane_path_ok(p)) {
         if (v.fmt == JT_FMT_S16) launch_qlane_f64<int16_t, SWR_MODE_TICKMAX>(c, v, p, n_out, nullptr, d_tick_tp, tick, n_ticks);
         else if (v.fmt == JT_FMT_FLT) launch_qlane_f64<float, SWR_MODE_TICKMAX>(c, v, p, n_out, nullptr, d_tick_tp, tick, n_ticks);

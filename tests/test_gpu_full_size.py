@@ -29,7 +29,8 @@ def test_meters_are_linear_at_full_size(ctx, hour):
     assert abs((m2.input_tp - m1.input_tp) - db) < 0.1 and abs((m2.input_sp - m1.input_sp) - db) < 0.1
     assert abs(m2.input_lra - m1.input_lra) < 0.011
     assert len(iv1) == len(iv2) and 14000 < len(iv1) < 14100 and m1.sink_frames == 36000    # ~256 ms intervals, 100 ms sink frames
-    d = [b.momentary_lufs - a.momentary_lufs for a, b in zip(iv1, iv2) if a.momentary_lufs > -60]
+    # (the first intervals hold sink frames without an M key, which count as 0 in the interval mean: analyser_metrics.go:849-872)
+    d = [b.momentary_lufs - a.momentary_lufs for a, b in list(zip(iv1, iv2))[4:] if a.momentary_lufs > -60]
     assert abs(np.median(d) - db) < 0.002 and max(abs(v - db) for v in d) < 0.01
 
 
