@@ -44,14 +44,14 @@ KERNEL_BYTES = {
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch on the 60 min stream, from the `ncu --set full` captures
-# summarised in profiles/ncu_r1h.md (cold-cache replay; None where the kernel was not captured)
+# summarised in profiles/ncu_r1k.md / ncu_r1h.md (cold-cache replay; None where the kernel was not captured)
 NCU_TRAFFIC_BYTES_60MIN = {
-    "adeclick:interp": 1.627476e9 + 0.732643e9,
-    "anlmdn": 0.693577e9 + 0.652757e9,
+    "adeclick:interp": 1.661498e9 + 0.722141e9,            # profiles/ncu_r1k.md
+    "anlmdn": 0.706247e9 + 0.651037e9,                     # profiles/ncu_r1k.md
     "afftdn:fwd": 0.702286e9 + 2.324030e9,
     "alimiter": 3.293223e9 + 1.231703e9,
     "swr_resample:qlane_f64": 0.705825e9 + 1.226726e9,
-    "envelope_follower": 8.088364e9 + 1.335775e9,          # profiles/ncu_r1d.md
+    "envelope_follower": 8.088282e9 + 1.336265e9,          # profiles/ncu_r1k.md
     "r128_kweight_ticks": 1.383083e9 + 0.006421e9,         # profiles/ncu_r1d.md
 }
 # what actually bounds each group; the contract's roofline is reported against HBM regardless
@@ -309,7 +309,7 @@ def main():
         "roofline": {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak if peak else None,
                      "traffic": NCU_TRAFFIC_BYTES_60MIN.get(dom[0]) if args.minutes == 60 else None,
-                     "traffic_source": "profiles/ncu_r1h.md (bytes per launch, ncu --set full)", "peak_source": peak_src,
+                     "traffic_source": "profiles/ncu_r1k.md / ncu_r1h.md (bytes per launch, ncu --set full)", "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": dom_bytes,
                      "kernel_ms_per_step": dom_ms_per_step, "kernel_share_of_step": dom_ms_per_step / (1e3 * t_dev / args.steps),
                      "chain_frac": (BYTES_PER_SAMPLE_4PASS * n / (t_dev / args.steps) / 1e9) / peak,
