@@ -164,6 +164,44 @@ int jt_analyse_chunk(jt_ctx *ctx, const void *pcm_local, int64_t n_local, int sa
 int jt_analyse_merge(int n_chunks, const void *const *blobs,
                      jt_measurements *out, jt_interval *intervals, int64_t interval_cap, int64_t *n_intervals);
 
+/* ---- Passes 2, 3 and 4 of one long stream over several GPUs (configs[3]) ---------------------------
+ * jt_graph_chunk runs ANY spec jt_run_graph accepts (BuildFilterSpec filters.go:968-989, measureWithLoudnorm
+ * normalise.go:257-264, buildLoudnormFilterSpec normalise.go:1231-1334) on a window [local_first, +n_local) of the
+ * stream and returns (a) the OWNED part of the sink audio -- sink samples [*out_first, *out_first + *n_out), which
+ * tile the sink stream across chunks, the end-of-stream flush and the asetnsamples padding included in the last one --
+ * and (b) a blob of mergeable measurement values of the owned part (per-tick ebur128 energy / peaks, the spectral
+ * rows the stream's sink frames show, partial astats, loudnorm's per-100 ms meter values).  jt_graph_merge (host
+ * only) turns the blobs of all chunks into the sink-frame records / loudnorm JSON / accumulated measurements
+ * jt_run_graph gives for the whole stream: windows, gating, percentiles and the sink-frame cadence are evaluated on
+ * the merged values, so they do not depend on the chunking.
+ *
+ * Boundaries: own_first, local_first and every owned length but the last are multiples of
+ * jt_graph_chunk_unit(spec, rate) (whole 100 ms ticks on every measuring link, whole afftdn / adeclick hops, whole
+ * resampler periods).  Context: jt_graph_chunk_context() recommends the left / right context (input frames, multiples
+ * of the unit) that lets every contractive state of the chain (envelope followers, limiter, biquads, gain smoothing)
+ * forget the cut; a mid-stream chunk must bring at least 2 s on the left and 0.25 s on the right.
+ *
+ * The one state with unbounded memory, afftdn's tracked noise floor (tn=1), crosses chunk boundaries exactly: each
+ * chunk reduces its owned hops to an affine carry and the chunks exchange these 32-byte records through the
+ * callback set with jt_set_exchange -- an all-gather in rank order (ncclAllGather / MPI_Allgather) that EVERY rank
+ * must enter once per call of jt_graph_chunk whose spec makes jt_graph_exchanges() return 1 (ranks without a chunk
+ * send `bytes` zero bytes).  This is the only collective inside the data path. */
+typedef int (*jt_exchange_fn)(void *user, const void *send, int64_t bytes, void *recv_all /* n_ranks * bytes */);
+void    jt_set_exchange(jt_ctx *ctx, jt_exchange_fn fn, void *user, int n_ranks);
+int     jt_graph_exchanges(const char *filter_spec);
+int64_t jt_graph_chunk_unit(const char *filter_spec, int sample_rate);
+int     jt_graph_chunk_context(const char *filter_spec, int sample_rate, int64_t *left_frames, int64_t *right_frames);
+int64_t jt_graph_chunk_bytes(const char *filter_spec, int64_t owned_frames, int sample_rate);   /* upper bound of a blob */
+int jt_graph_chunk(jt_ctx *ctx, const char *filter_spec,
+                   const void *pcm_local, int64_t n_local, int sample_rate, int channels, int sample_fmt,
+                   int64_t local_first, int64_t own_first, int64_t owned, int64_t total_frames, int frame_size,
+                   void *pcm_out, int64_t pcm_out_cap_frames, int64_t *out_first, int64_t *n_out, int *out_rate, int *out_fmt,
+                   void *blob, int64_t blob_cap, int64_t *blob_bytes);
+int jt_graph_merge(const char *filter_spec, int64_t total_frames, int sample_rate, int channels, int sample_fmt,
+                   int frame_size, int n_chunks, const void *const *blobs,
+                   jt_frame_meta *meta, int64_t meta_cap, int64_t *n_meta,
+                   jt_loudnorm_stats *ln_stats, struct jt_measurements *accumulated);
+
 /* 17-band region RMS (measureSpeechBandRMS analyser_bands.go:33-104): n_bands (lo,hi) pairs
  * over region [start_s, start_s+duration_s); rms_db[i] = lavfi.astats.Overall.RMS_level,
  * found[i] = 0 when the reference would have seen no metadata. */

@@ -548,6 +548,370 @@ extern "C" int jt_analyse_merge(int n_chunks, const void *const *blobs, jt_measu
 }
 
 // ---------------------------------------------------------------------------------------
+// Passes 2-4 of one long stream over several GPUs: any graph on a window of the stream (jt_graph_chunk), host merge
+// of the chunks' measurement values (jt_graph_merge).  See include/jtdsp.h for the contract.
+// ---------------------------------------------------------------------------------------
+#define JT_GCHUNK_MAGIC 0x4a544743484b /* "JTGCHK" */
+struct JtGraphChunkHdr {
+    int64_t magic, bytes, total_frames, first, owned;
+    int32_t rate, channels, fmt, frame_size;
+    int64_t r_tick0, r_nticks;                  // ebur128: energy, sample peak, true peak per 100 ms tick
+    int64_t n_rows;                             // aspectralstats: (global hop, 13 floats) per row
+    int64_t astats_bytes, astats_n;             // partial astats over astats_n owned samples
+    int32_t astats_fmt, astats_tc;
+    int64_t li_tick0, li_nticks, lo_tick0, lo_nticks;   // loudnorm input / output meter: energy, peak per 100 ms
+    int64_t out_first, out_n;                   // owned sink samples
+};
+
+extern "C" void jt_set_exchange(jt_ctx *c, jt_exchange_fn fn, void *user, int n_ranks)
+{
+    if (!c) return;
+    c->exchange = fn; c->exchange_user = user; c->exchange_ranks = n_ranks > 0 ? n_ranks : 1;
+}
+
+static int64_t lcm64(int64_t a, int64_t b) { return a / gcd64(a, b) * b; }
+// smallest U with U * link_rate / rate a multiple of `grid` (positions on that link land on its grid)
+static int64_t unit_for(int rate, int link_rate, int64_t grid)
+{
+    const int64_t num = (int64_t)rate * grid;
+    return num / gcd64(num, link_rate);
+}
+
+struct ChunkGeometry { int64_t unit = 0; int exchanges = 0; };
+static ChunkGeometry chunk_geometry(const char *spec, int rate)
+{
+    ChunkGeometry G;
+    if (rate <= 0 || rate % 10) JT_THROW(JT_ERR_UNSUPPORTED, "chunked graphs need a rate that is a multiple of 10 (got %d)", rate);
+    int64_t U = rate / 10;
+    int r = rate;
+    for (const FilterNode &f : jt_parse_spec(spec ? spec : "")) {
+        int nr = r;
+        if (f.name == "aformat") nr = (int)f.num("sample_rates", "r", r);
+        else if (f.name == "aresample") { nr = (int)f.num("sample_rate", "", r); if (const std::string *p = f.get("")) nr = atoi(p->c_str()); }
+        else if (f.name == "afftdn") { U = lcm64(U, unit_for(rate, r, std::max(r / 80, 1))); if (f.flag("tn", "track_noise", false)) G.exchanges++; }
+        else if (f.name == "adeclick") {
+            const double w = f.num("w", "window", 55), o = f.num("o", "overlap", 75);
+            const int ws = (int)(r * w / 1000.), hop = std::max((int)(ws * (1. - o / 100.)), 1);
+            U = lcm64(U, unit_for(rate, r, hop));
+        } else if (f.name == "ebur128") { if (r % 10) JT_THROW(JT_ERR_UNSUPPORTED, "ebur128 at %d Hz", r); U = lcm64(U, unit_for(rate, r, r / 10)); }
+        else if (f.name == "loudnorm") {
+            const bool linear = f.flag("linear", "", true);
+            const double I = f.num("I", "i", -24), TP = f.num("TP", "tp", -2), LRA = f.num("LRA", "lra", 7);
+            const double mI = f.num("measured_I", "measured_i", 0), mTP = f.num("measured_TP", "measured_tp", 99);
+            const double mLRA = f.num("measured_LRA", "measured_lra", 0), mTh = f.num("measured_thresh", "", -70);
+            const bool lin_mode = linear && mTP != 99 && mTh != -70 && mLRA != 0 && mI != 0 && mTP + (I - mI) <= TP && mLRA <= LRA;
+            if (!lin_mode) nr = 192000;
+            U = lcm64(U, unit_for(rate, nr, (nr + 5) / 10));
+        } else if (f.name == "atrim") JT_THROW(JT_ERR_UNSUPPORTED, "atrim in a chunked graph");
+        if (nr != r) { if (nr <= 0) JT_THROW(JT_ERR_SPEC, "bad rate in %s", f.name.c_str()); U = lcm64(U, unit_for(rate, nr, 1)); r = nr; }
+        if (U > ((int64_t)1 << 40)) JT_THROW(JT_ERR_UNSUPPORTED, "chunk unit overflow");
+    }
+    G.unit = U;
+    return G;
+}
+
+extern "C" int64_t jt_graph_chunk_unit(const char *spec, int rate)
+{
+    try { return chunk_geometry(spec, rate).unit; } catch (const JtError &) { return 0; }
+}
+extern "C" int jt_graph_exchanges(const char *spec)
+{
+    try { return chunk_geometry(spec, 48000).exchanges; } catch (const JtError &) { return 0; }
+}
+extern "C" int jt_graph_chunk_context(const char *spec, int rate, int64_t *left, int64_t *right)
+{
+    try {
+        const int64_t U = chunk_geometry(spec, rate).unit;
+        // left: 37 time constants of the slowest envelope follower (200 ms release) = 7.4 s -> 8 s; right: look-ahead of
+        // the windowed filters (afftdn 37.5 ms, adeclick 55 ms, spectral 2048 samples, resampler taps) -> 1 s
+        if (left) *left = ((int64_t)8 * rate + U - 1) / U * U;
+        if (right) *right = ((int64_t)rate + U - 1) / U * U;
+    } catch (const JtError &e) { return e.code; }
+    return JT_OK;
+}
+extern "C" int64_t jt_graph_chunk_bytes(const char *spec, int64_t owned, int rate)
+{
+    (void)spec;
+    if (rate <= 0 || owned < 0) return 0;
+    // ticks on a link of at most 192 kHz (same count as on the input link), spectral rows: at most one per input tick
+    const int64_t nt = owned / std::max(rate / 10, 1) + 4;
+    return (int64_t)sizeof(JtGraphChunkHdr) + nt * (3 * 8 + 2 * 8 + 2 * 8 + 8 + JT_SP_COUNT * 4) + (int64_t)jt_astats_host_bytes() + 256;
+}
+
+extern "C" int jt_graph_chunk(jt_ctx *c, const char *spec, const void *pcm_local, int64_t n_local, int rate, int channels, int fmt,
+                              int64_t local_first, int64_t own_first, int64_t owned, int64_t total, int frame_size,
+                              void *pcm_out, int64_t cap, int64_t *out_first, int64_t *n_out, int *out_rate, int *out_fmt,
+                              void *blob, int64_t blob_cap, int64_t *blob_bytes)
+{
+    return guarded(c, [&]() {
+        if (!spec || !pcm_local) JT_THROW(JT_ERR_INVALID_ARG, "null spec or input");
+        if (fmt != JT_FMT_S16 && fmt != JT_FMT_FLT && fmt != JT_FMT_DBL) JT_THROW(JT_ERR_UNSUPPORTED, "input sample format %d", fmt);
+        if (frame_size <= 0) frame_size = 4096;
+        const ChunkGeometry G = chunk_geometry(spec, rate);
+        const int64_t U = G.unit;
+        if (owned <= 0 || own_first < 0 || own_first % U || local_first % U || local_first < 0 || local_first > own_first ||
+            own_first + owned > total || local_first + n_local < own_first + owned || local_first + n_local > total)
+            JT_THROW(JT_ERR_INVALID_ARG, "chunk [%lld,+%lld) / window [%lld,+%lld) of %lld: boundaries must be multiples of jt_graph_chunk_unit = %lld frames",
+                     (long long)own_first, (long long)owned, (long long)local_first, (long long)n_local, (long long)total, (long long)U);
+        const bool last = own_first + owned == total;
+        if (!last && owned % U) JT_THROW(JT_ERR_INVALID_ARG, "only the last chunk may hold a partial unit");
+        if (own_first > 0 && own_first - local_first < 2 * (int64_t)rate) JT_THROW(JT_ERR_INVALID_ARG, "a chunk in mid-stream needs >= 2 s of left context");
+        if (own_first == 0 && local_first != 0) JT_THROW(JT_ERR_INVALID_ARG, "bad window");
+        if (!last && local_first + n_local - (own_first + owned) < rate / 4 && local_first + n_local != total)
+            JT_THROW(JT_ERR_INVALID_ARG, "a chunk before the stream's end needs >= 0.25 s of right context");
+
+        // the whole stream's link sizes and sink-frame cadence (no device work)
+        GraphRun gd;
+        jt_graph_build(c, spec, nullptr, total, rate, channels, fmt, frame_size, pcm_out != nullptr, true, JT_GRAPH_DRY, nullptr, gd);
+        // the audio filters on the local window
+        GraphChunk ck; ck.local_first = local_first; ck.own_first = own_first; ck.owned = owned; ck.total = total; ck.rate = rate; ck.last = last;
+        ck.exchange = c->exchange; ck.exchange_user = c->exchange_user; ck.n_ranks = c->exchange_ranks;
+        const void *d_in = upload(c, pcm_local, (size_t)n_local * channels * jt_fmt_bytes(fmt));
+        GraphRun gl;
+        jt_graph_build(c, spec, d_in, n_local, rate, channels, fmt, frame_size, pcm_out != nullptr, false, JT_GRAPH_CHUNK, &ck, gl);
+
+        // positions of the window / the owned range on a link of rate r whose whole-stream length is n_link
+        struct Range { int64_t loc0, a, b; };          // link position of the window's first sample; owned = [a, b)
+        auto range_on = [&](int r, int64_t n_link) {
+            Range R; R.loc0 = ck.link_pos(local_first, r); R.a = ck.link_pos(own_first, r);
+            R.b = last ? n_link : ck.link_pos(own_first + owned, r);
+            if (R.b < R.a) R.b = R.a;
+            return R;
+        };
+        JtGraphChunkHdr h; memset(&h, 0, sizeof(h));
+        h.magic = JT_GCHUNK_MAGIC; h.total_frames = total; h.first = own_first; h.owned = owned;
+        h.rate = rate; h.channels = channels; h.fmt = fmt; h.frame_size = frame_size;
+
+        // ---- ebur128: per-tick values of the owned ticks (1 s of context ahead of them) ----
+        R128Pending rp; int64_t r_loc_tick0 = 0;
+        if (gd.has_r128 && blob) {
+            const Sig &sg = gl.r128_sig; const int tick = sg.rate / 10;
+            const Range R = range_on(sg.rate, gd.r128_sig.n);
+            const int64_t ctx = std::min<int64_t>(10 * (int64_t)tick, (R.a - R.loc0) / tick * tick);
+            const int64_t s0 = R.a - ctx - R.loc0;
+            if (R.a % tick || s0 < 0 || s0 > sg.n) JT_THROW(JT_ERR_INVALID_ARG, "internal: ebur128 tick grid");
+            jt_ebur128_launch(c, jt_slice(sg, s0, sg.n - s0), gd.r128_dual, gd.r128_tp, rp);
+            r_loc_tick0 = ctx / tick;
+            h.r_tick0 = R.a / tick;
+            h.r_nticks = last ? gd.r128_sig.n / tick - h.r_tick0 : (R.b - R.a) / tick;
+            if (h.r_nticks < 0) h.r_nticks = 0;
+            if (r_loc_tick0 + h.r_nticks > rp.nt) JT_THROW(JT_ERR_INVALID_ARG, "internal: local tick range (%lld + %lld > %lld)", (long long)r_loc_tick0, (long long)h.r_nticks, (long long)rp.nt);
+        }
+        // ---- aspectralstats: the rows the stream's sink frames show whose hop starts in the owned range ----
+        SpectralPending sp; std::vector<int64_t> want_g, want_l; bool have_sp = false;
+        if (gd.has_spec && blob) {
+            const Sig &sg = gl.spec_sig; const int hs = gd.spec_win / 2;
+            const Range R = range_on(sg.rate, gd.spec_sig.n);
+            int64_t s_g = R.a / hs * hs - 4 * (int64_t)hs;                              // window start, on the global hop grid
+            const int64_t lo_g = (R.loc0 + hs - 1) / hs * hs;
+            if (s_g < lo_g) s_g = lo_g;
+            for (const FrameRef &fr : gd.frames) if (fr.hop >= 0) {
+                const int64_t pos = (int64_t)fr.hop * hs;
+                if (pos >= R.a && pos < R.b && (want_g.empty() || want_g.back() != fr.hop)) want_g.push_back(fr.hop);
+            }
+            for (int64_t gh : want_g) want_l.push_back(gh - s_g / hs);
+            const int64_t s0 = s_g - R.loc0;
+            if (s0 < 0 || s0 > sg.n) JT_THROW(JT_ERR_INVALID_ARG, "internal: spectral window");
+            if (!want_l.empty()) { jt_aspectralstats_launch(c, jt_slice(sg, s0, sg.n - s0), gd.spec_win, &want_l, sp); have_sp = true; }
+        }
+        // ---- astats: partial statistics of the owned samples up to the last snapshot a sink frame shows ----
+        AstatsPending ap;
+        if (gd.has_astats && blob && gd.last_astats_frame >= 0) {
+            const Sig &sg = gl.astats_sig;
+            const Range R = range_on(sg.rate, gd.astats_sig.n);
+            const int64_t upto = gd.frames[gd.last_astats_frame].astats_pos;
+            const int64_t as_n = std::max<int64_t>(0, std::min(R.b, upto) - R.a);
+            if (as_n > 0) jt_astats_chunk_launch(c, sg, R.a - R.loc0, as_n, R.a, ap);
+            h.astats_n = ap.host ? as_n : 0; h.astats_fmt = sg.fmt; h.astats_tc = ap.tc ? ap.tc : (int)std::fmax(0.05 * sg.rate + .5, 1);
+        }
+        h.astats_bytes = (int64_t)jt_astats_host_bytes();
+        // ---- loudnorm meters ----
+        LoudnormPending li, lo; int64_t li_loc = 0, lo_loc = 0;
+        auto meter = [&](const Sig &sg, int64_t n_link, LoudnormPending &pd, int64_t &loc_tick0, int64_t &tick0, int64_t &nticks) {
+            const int s100 = (sg.rate + 5) / 10;
+            const Range R = range_on(sg.rate, n_link);
+            const int64_t ctx = std::min<int64_t>(10 * (int64_t)s100, (R.a - R.loc0) / s100 * s100);
+            const int64_t s0 = R.a - ctx - R.loc0;
+            if (R.a % s100 || s0 < 0 || s0 > sg.n) JT_THROW(JT_ERR_INVALID_ARG, "internal: loudnorm tick grid");
+            jt_loudnorm_meter_launch(c, jt_slice(sg, s0, sg.n - s0), gd.ln_dual, pd);
+            loc_tick0 = ctx / s100; tick0 = R.a / s100;
+            nticks = last ? (n_link + s100 - 1) / s100 - tick0 : (R.b - R.a) / s100;
+            if (nticks < 0) nticks = 0;
+            if (loc_tick0 + nticks > pd.nt) JT_THROW(JT_ERR_INVALID_ARG, "internal: local meter tick range");
+        };
+        if (gd.has_ln && blob) {
+            meter(gl.ln_in_sig, gd.ln_in_sig.n, li, li_loc, h.li_tick0, h.li_nticks);
+            if (gd.ln_linear) meter(gl.ln_out_sig, gd.ln_out_sig.n, lo, lo_loc, h.lo_tick0, h.lo_nticks);
+        }
+        // ---- the owned part of the sink audio ----
+        {
+            const Range R = range_on(gd.out.rate, gd.out.n);
+            h.out_first = R.a; h.out_n = R.b - R.a;
+            if (out_first) *out_first = R.a;
+            if (n_out) *n_out = h.out_n;
+            if (out_rate) *out_rate = gd.out.rate;
+            if (out_fmt) *out_fmt = gd.out.fmt;
+            if (pcm_out) {
+                if (h.out_n > cap) JT_THROW(JT_ERR_BUFFER, "pcm_out holds %lld frames, the chunk owns %lld", (long long)cap, (long long)h.out_n);
+                if (gl.out.fmt != gd.out.fmt || !gl.out.d) JT_THROW(JT_ERR_INVALID_ARG, "internal: sink format");
+                const size_t bs = jt_fmt_bytes(gl.out.fmt);
+                const int64_t s0 = R.a - R.loc0, have = std::max<int64_t>(0, std::min(h.out_n, gl.out.n - s0));
+                if (s0 < 0 || (!last && have < h.out_n)) JT_THROW(JT_ERR_INVALID_ARG, "internal: sink range (%lld of %lld)", (long long)have, (long long)h.out_n);
+                if (have) JT_CUDA(cudaMemcpyAsync(pcm_out, (const char *)gl.out.d + (size_t)s0 * bs, (size_t)have * bs, cudaMemcpyDeviceToHost, c->stream));
+                if (have < h.out_n) memset((char *)pcm_out + (size_t)have * bs, 0, (size_t)(h.out_n - have) * bs);     // asetnsamples padding
+            }
+        }
+        // ---- wait, pack ----
+        std::vector<float> rows; int64_t n_hops = 0;
+        if (have_sp) jt_aspectralstats_finish(c, sp, rows, n_hops);
+        JT_CUDA(cudaStreamSynchronize(c->stream));
+        if (!blob) { if (blob_bytes) *blob_bytes = 0; return; }
+        h.n_rows = have_sp ? (int64_t)want_g.size() : 0;
+        const int64_t need = (int64_t)sizeof(h) + h.r_nticks * 24 + h.n_rows * (8 + JT_SP_COUNT * 4) + h.astats_bytes + (h.li_nticks + h.lo_nticks) * 16;
+        if (need > blob_cap) JT_THROW(JT_ERR_BUFFER, "chunk blob needs %lld bytes", (long long)need);
+        h.bytes = need;
+        char *w = (char *)blob;
+        memcpy(w, &h, sizeof(h)); w += sizeof(h);
+        if (h.r_nticks > 0) {
+            memcpy(w, rp.hp + r_loc_tick0, 8 * h.r_nticks); w += 8 * h.r_nticks;
+            memcpy(w, rp.hk + r_loc_tick0, 8 * h.r_nticks); w += 8 * h.r_nticks;
+            if (gd.r128_tp) memcpy(w, rp.ht + r_loc_tick0, 8 * h.r_nticks); else memset(w, 0, 8 * h.r_nticks);
+            w += 8 * h.r_nticks;
+        }
+        for (int64_t k = 0; k < h.n_rows; k++) { memcpy(w, &want_g[k], 8); w += 8; }
+        for (int64_t k = 0; k < h.n_rows; k++) {
+            const int64_t lh = want_l[k];
+            if (lh >= 0 && lh < n_hops) memcpy(w, &rows[(size_t)lh * JT_SP_COUNT], JT_SP_COUNT * 4); else memset(w, 0, JT_SP_COUNT * 4);
+            w += JT_SP_COUNT * 4;
+        }
+        if (ap.host && h.astats_n > 0) memcpy(w, ap.host, h.astats_bytes); else memset(w, 0, h.astats_bytes);
+        w += h.astats_bytes;
+        if (h.li_nticks > 0) { memcpy(w, li.hp + li_loc, 8 * h.li_nticks); w += 8 * h.li_nticks; memcpy(w, li.hk + li_loc, 8 * h.li_nticks); w += 8 * h.li_nticks; }
+        if (h.lo_nticks > 0) { memcpy(w, lo.hp + lo_loc, 8 * h.lo_nticks); w += 8 * h.lo_nticks; memcpy(w, lo.hk + lo_loc, 8 * h.lo_nticks); w += 8 * h.lo_nticks; }
+        if (blob_bytes) *blob_bytes = need;
+    });
+}
+
+extern "C" int jt_graph_merge(const char *spec, int64_t total, int rate, int channels, int fmt, int frame_size,
+                              int n_chunks, const void *const *blobs, jt_frame_meta *meta, int64_t meta_cap, int64_t *n_meta,
+                              jt_loudnorm_stats *ln, jt_measurements *accumulated)
+{
+    if (n_chunks <= 0 || !blobs || !spec) return JT_ERR_INVALID_ARG;
+    try {
+        std::vector<const JtGraphChunkHdr *> hs;
+        for (int i = 0; i < n_chunks; i++) {
+            const JtGraphChunkHdr *h = (const JtGraphChunkHdr *)blobs[i];
+            if (!h || h->magic != JT_GCHUNK_MAGIC) return JT_ERR_INVALID_ARG;
+            hs.push_back(h);
+        }
+        std::sort(hs.begin(), hs.end(), [](const JtGraphChunkHdr *a, const JtGraphChunkHdr *b) { return a->first < b->first; });
+        int64_t expect = 0;
+        for (const JtGraphChunkHdr *h : hs) {
+            if (h->first != expect || h->rate != rate || h->channels != channels || h->total_frames != total || h->fmt != fmt) return JT_ERR_INVALID_ARG;
+            expect = h->first + h->owned;
+        }
+        if (expect != total) return JT_ERR_INVALID_ARG;             // chunks must tile the stream
+        if (frame_size <= 0) frame_size = 4096;
+        GraphRun gd;
+        jt_graph_build(nullptr, spec, nullptr, total, rate, channels, fmt, frame_size, false, true, JT_GRAPH_DRY, nullptr, gd);
+
+        const int64_t nt = gd.has_r128 ? gd.r128_sig.n / std::max(gd.r128_sig.rate / 10, 1) : 0;
+        const int hs_sp = gd.spec_win / 2;
+        const int64_t n_hops = gd.has_spec ? (gd.spec_sig.n + hs_sp - 1) / hs_sp : 0;
+        const int s_in = gd.has_ln ? (gd.ln_in_sig.rate + 5) / 10 : 1, s_out = gd.has_ln && gd.ln_linear ? (gd.ln_out_sig.rate + 5) / 10 : 1;
+        const int64_t li_nt = gd.has_ln ? (gd.ln_in_sig.n + s_in - 1) / s_in : 0, lo_nt = gd.has_ln && gd.ln_linear ? (gd.ln_out_sig.n + s_out - 1) / s_out : 0;
+        std::vector<double> hp(nt), hk(nt), ht(nt), lip(li_nt), lik(li_nt), lop(lo_nt), lok(lo_nt);
+        std::vector<float> rows((size_t)n_hops * JT_SP_COUNT, 0.f);
+        std::vector<char> as(jt_astats_host_bytes());
+        bool first_as = true; int as_fmt = 0, as_tc = 0;
+        int64_t got_r = 0, got_li = 0, got_lo = 0;
+        for (const JtGraphChunkHdr *h : hs) {
+            const char *r = (const char *)h + sizeof(JtGraphChunkHdr);
+            if (h->r_nticks < 0 || h->r_tick0 < 0 || h->r_tick0 + h->r_nticks > nt) return JT_ERR_INVALID_ARG;
+            if (h->r_nticks > 0) {
+                memcpy(&hp[h->r_tick0], r, 8 * h->r_nticks); r += 8 * h->r_nticks;
+                memcpy(&hk[h->r_tick0], r, 8 * h->r_nticks); r += 8 * h->r_nticks;
+                memcpy(&ht[h->r_tick0], r, 8 * h->r_nticks); r += 8 * h->r_nticks;
+                got_r += h->r_nticks;
+            }
+            const char *hops = r; r += 8 * h->n_rows;
+            for (int64_t k = 0; k < h->n_rows; k++) {
+                int64_t gh; memcpy(&gh, hops + 8 * k, 8);
+                if (gh >= 0 && gh < n_hops) memcpy(&rows[(size_t)gh * JT_SP_COUNT], r + (size_t)k * JT_SP_COUNT * 4, JT_SP_COUNT * 4);
+            }
+            r += (size_t)h->n_rows * JT_SP_COUNT * 4;
+            if ((size_t)h->astats_bytes != as.size()) return JT_ERR_INVALID_ARG;
+            if (h->astats_n > 0) {
+                if (first_as) { memcpy(as.data(), r, as.size()); first_as = false; as_fmt = h->astats_fmt; as_tc = h->astats_tc; }
+                else jt_astats_host_merge(as.data(), r);
+            }
+            r += h->astats_bytes;
+            if (h->li_nticks < 0 || h->li_tick0 + h->li_nticks > li_nt || h->lo_nticks < 0 || h->lo_tick0 + h->lo_nticks > lo_nt) return JT_ERR_INVALID_ARG;
+            if (h->li_nticks > 0) { memcpy(&lip[h->li_tick0], r, 8 * h->li_nticks); r += 8 * h->li_nticks; memcpy(&lik[h->li_tick0], r, 8 * h->li_nticks); r += 8 * h->li_nticks; got_li += h->li_nticks; }
+            if (h->lo_nticks > 0) { memcpy(&lop[h->lo_tick0], r, 8 * h->lo_nticks); r += 8 * h->lo_nticks; memcpy(&lok[h->lo_tick0], r, 8 * h->lo_nticks); r += 8 * h->lo_nticks; got_lo += h->lo_nticks; }
+        }
+        if (got_r != nt || got_li != li_nt || got_lo != lo_nt) return JT_ERR_INVALID_ARG;       // every tick exactly once
+
+        GraphResult res; memset(&res.ln, 0, sizeof(res.ln));
+        if (gd.has_ln) {
+            LoudnormMeter mi, mo;
+            jt_loudnorm_meter_host_finalize(lip.data(), lik.data(), li_nt, gd.ln_in_sig.n / s_in, s_in, gd.ln_dual, mi);
+            res.ln.valid = 1;
+            if (gd.ln_linear) {
+                jt_loudnorm_meter_host_finalize(lop.data(), lok.data(), lo_nt, gd.ln_out_sig.n / s_out, s_out, gd.ln_dual, mo);
+                res.ln.normalization_type = 0;
+                res.ln.output_i = mo.I; res.ln.output_tp = 20. * log10(mo.sample_peak); res.ln.output_lra = mo.LRA; res.ln.output_thresh = mo.thresh;
+                res.ln.target_offset = gd.ln_I - mo.I;
+            } else {
+                res.ln.normalization_type = 1;
+                res.ln.output_i = res.ln.output_tp = res.ln.output_lra = res.ln.output_thresh = res.ln.target_offset = NAN;
+            }
+            res.ln.input_i = mi.I; res.ln.input_tp = 20. * log10(mi.sample_peak); res.ln.input_lra = mi.LRA; res.ln.input_thresh = mi.thresh;
+        }
+        if (ln) *ln = res.ln;
+        R128Result r128;
+        if (gd.has_r128) jt_ebur128_host_finalize(nullptr, hp.data(), hk.data(), gd.r128_tp ? ht.data() : nullptr, nt, gd.r128_sig.rate / 10, gd.r128_dual, r128);
+        jt_assemble_records(gd.frames, gd.has_r128, r128, gd.has_spec, rows, n_hops, res);
+        if (gd.has_astats && gd.last_astats_frame >= 0 && !first_as) {
+            AstatsResult a;
+            jt_astats_host_finalize(as.data(), gd.frames[gd.last_astats_frame].astats_pos, as_fmt, as_tc, a);
+            jt_frame_meta &m = res.meta[gd.last_astats_frame];
+            if (!gd.astats_overall_only) for (int k = 0; k < JT_AS_COUNT; k++) m.astats[k] = std::isnan(a.v[k]) ? NAN : jt_wire("%f", a.v[k]);
+            m.astats_overall_RMS_level = jt_wire("%f", a.overall_rms);
+            m.astats_overall_Peak_level = jt_wire("%f", a.overall_peak);
+        }
+        if (n_meta) *n_meta = (int64_t)res.meta.size();
+        if (meta) {
+            if ((int64_t)res.meta.size() > meta_cap) return JT_ERR_BUFFER;
+            if (!res.meta.empty()) memcpy(meta, res.meta.data(), res.meta.size() * sizeof(jt_frame_meta));
+        }
+        if (accumulated) {
+            MeasAcc acc; for (auto &m : res.meta) acc.add(m);
+            acc.finish(gd.out.rate > 0 ? (double)gd.out.n / gd.out.rate : 0.0);
+            *accumulated = acc.m;
+        }
+    } catch (const JtError &e) { return e.code; }
+    catch (const std::bad_alloc &) { return JT_ERR_NOMEM; }
+    return JT_OK;
+}
+
+// test hook (tests/test_shard_gloo.py, tests/test_gpu_graph_shard.py): the device-free plan of a graph over a stream of
+// n frames -- sink length / rate / format, sink-frame count, lengths of the measuring links
+extern "C" int jt_debug_graph_plan(const char *spec, int64_t n, int rate, int channels, int fmt, int frame_size, int want_pcm, int64_t *out /* 10 */)
+{
+    if (!spec || !out) return JT_ERR_INVALID_ARG;
+    try {
+        GraphRun gd;
+        jt_graph_build(nullptr, spec, nullptr, n, rate, channels, fmt, frame_size, want_pcm != 0, true, JT_GRAPH_DRY, nullptr, gd);
+        out[0] = gd.out.n; out[1] = gd.out.rate; out[2] = gd.out.fmt; out[3] = (int64_t)gd.frames.size();
+        out[4] = gd.has_r128 ? gd.r128_sig.n : -1; out[5] = gd.has_spec ? gd.spec_sig.n : -1; out[6] = gd.has_astats ? gd.astats_sig.n : -1;
+        out[7] = gd.has_ln ? gd.ln_in_sig.n : -1; out[8] = gd.has_ln ? gd.ln_in_sig.rate : -1;
+        out[9] = gd.last_astats_frame >= 0 ? gd.frames[gd.last_astats_frame].astats_pos : -1;
+    } catch (const JtError &e) { return e.code; }
+    return JT_OK;
+}
+
+// ---------------------------------------------------------------------------------------
 // K20: band RMS batch (measureSpeechBandRMS, analyser_bands.go:33-104)
 // ---------------------------------------------------------------------------------------
 extern "C" int jt_band_rms(jt_ctx *c, const void *pcm_in, int64_t n_frames, int rate, int channels, int fmt,

@@ -185,8 +185,9 @@ struct Exec {
     // analysis products
     bool has_astats = false, has_spec = false, has_r128 = false, astats_overall_only = false;
     Sig astats_sig, spec_sig; int spec_win = 2048;
-    void storage(int fmt) { cur = jt_convert(c, cur, fmt); link_fmt = fmt; }
-    void materialise() { if (cur.fmt != link_fmt) cur = jt_convert(c, cur, link_fmt); }
+    bool dry = false;          // JT_GRAPH_DRY: sizes, formats and frame cadence only, no device work
+    void storage(int fmt) { if (dry) cur.fmt = fmt; else cur = jt_convert(c, cur, fmt); link_fmt = fmt; }
+    void materialise() { if (cur.fmt != link_fmt) { if (dry) cur.fmt = link_fmt; else cur = jt_convert(c, cur, link_fmt); } }
 };
 }
 
@@ -213,8 +214,10 @@ static void do_resample(Exec &E, int out_rate, int out_fmt /* 0 = keep link form
     const int64_t n_in = E.cur.n;
     // swr converts to its internal format first, then resamples
     Sig src = E.cur;
-    if (work == JT_FMT_FLT && src.fmt == JT_FMT_DBL) src = jt_convert(c, src, JT_FMT_FLT);
-    Sig r = jt_swr_resample(c, src, p, work, true, out_fmt);
+    if (work == JT_FMT_FLT && src.fmt == JT_FMT_DBL) { if (E.dry) src.fmt = JT_FMT_FLT; else src = jt_convert(c, src, JT_FMT_FLT); }
+    Sig r;
+    if (E.dry) { r = src; r.d = nullptr; r.rate = out_rate; r.n = p.out_count_flush(src.n); r.fmt = (work == JT_FMT_FLT && out_fmt == JT_FMT_S16) ? JT_FMT_S16 : work; }
+    else r = jt_swr_resample(c, src, p, work, true, out_fmt);
     // frames: one output frame per input frame (aresample filter_frame), then the EOF flush frame
     std::vector<FrameRef> nf; int64_t done = 0;
     for (const FrameRef &f : E.frames) {
@@ -252,27 +255,43 @@ void jt_graph_run(jt_ctx *c, const std::string &spec, const void *d_in, int64_t 
 void jt_graph_enqueue(jt_ctx *c, const std::string &spec, const void *d_in, int64_t n_frames, int rate, int channels,
                       int fmt, int frame_size, bool want_pcm, bool want_meta, GraphRun &g)
 {
+    jt_graph_build(c, spec, d_in, n_frames, rate, channels, fmt, frame_size, want_pcm, want_meta, JT_GRAPH_NORMAL, nullptr, g);
+}
+
+// mono view of the source: what jt_downmix returns, without the device work (dry runs)
+static Sig dry_mono(int64_t n_frames, int fmt, int rate) { Sig s; s.fmt = fmt; s.rate = rate; s.n = n_frames; s.d = nullptr; return s; }
+
+// mode NORMAL: the whole stream, analysis kernels launched here.
+// mode DRY   : no device work at all -- link sizes / formats and the sink-frame cadence of a stream of n_frames.
+// mode CHUNK : [d_in, +n_frames) is a window of a longer stream (jt_graph_chunk): the audio filters run on it as if it
+//              were a stream of its own, the signals the analysis filters see are recorded (GraphRun::*_sig) and their
+//              kernels are left to the caller, who knows which part of the window is owned; no end-of-stream padding.
+void jt_graph_build(jt_ctx *c, const std::string &spec, const void *d_in, int64_t n_frames, int rate, int channels,
+                    int fmt, int frame_size, bool want_pcm, bool want_meta, int mode, const GraphChunk *chunk, GraphRun &g)
+{
     if (n_frames < 0 || rate <= 0 || channels <= 0) JT_THROW(JT_ERR_INVALID_ARG, "bad stream description");
     if (frame_size <= 0) frame_size = 4096;
     std::vector<FilterNode> nodes = jt_parse_spec(spec);
     g = GraphRun();
     g.want_meta = want_meta;
+    const bool dry = mode == JT_GRAPH_DRY, chunked = mode == JT_GRAPH_CHUNK;
+    if (chunked) want_meta = false;              // the caller launches the analysis kernels on the owned part
 
-    Exec E; E.c = c;
+    Exec E; E.c = c; E.dry = dry;
     bool have_mono = false;
     const void *raw = d_in;
-    if (channels == 1) { E.cur = jt_downmix(c, raw, n_frames, 1, fmt, rate); have_mono = true; }
+    if (channels == 1) { E.cur = dry ? dry_mono(n_frames, fmt, rate) : jt_downmix(c, raw, n_frames, 1, fmt, rate); have_mono = true; }
     E.link_fmt = fmt;
     E.frames = source_frames(n_frames, frame_size);
 
     for (size_t ni = 0; ni < nodes.size(); ni++) {
         const FilterNode &f = nodes[ni];
         const bool last = ni + 1 == nodes.size();
-        jt_check_cancel(c);
+        if (!dry) jt_check_cancel(c);
         if (!have_mono) {
             // the only multi-channel-aware filter of the path is the leading downmix
             if (f.name == "aformat" && f.str("channel_layouts", "cl", "") == "mono") {
-                E.cur = jt_downmix(c, raw, n_frames, channels, fmt, rate);
+                E.cur = dry ? dry_mono(n_frames, fmt, rate) : jt_downmix(c, raw, n_frames, channels, fmt, rate);
                 have_mono = true;
             } else JT_THROW(JT_ERR_UNSUPPORTED, "filter %s on %d-channel audio (specs of this path start with aformat=channel_layouts=mono)", f.name.c_str(), channels);
         }
@@ -300,7 +319,7 @@ void jt_graph_enqueue(jt_ctx *c, const std::string &spec, const void *d_in, int6
             const int n = (int)f.num("n", "nb_out_samples", 1024);
             const bool pad = f.flag("p", "pad", true);
             E.frames = reframe(E.frames, E.cur.n, n);
-            if (pad && !E.frames.empty() && E.frames.back().nb < n) {
+            if (pad && !chunked && !E.frames.empty() && E.frames.back().nb < n) {
                 const int64_t tot = E.frames.back().start + n;
                 E.frames.back().nb = n;
                 if (E.cur.d) { E.materialise(); E.cur = jt_pad_zero(c, E.cur, tot); } else E.cur.n = tot;
@@ -318,8 +337,9 @@ void jt_graph_enqueue(jt_ctx *c, const std::string &spec, const void *d_in, int6
                 if (hi > lo) { FrameRef o = fr; o.start = lo - a; o.nb = (int32_t)(hi - lo); nf.push_back(o); }
             }
             E.frames.swap(nf);
+            if (chunked) JT_THROW(JT_ERR_UNSUPPORTED, "atrim in a chunked graph");
             E.materialise();
-            E.cur = jt_slice(E.cur, a, std::max<int64_t>(b - a, 0));
+            if (dry) E.cur.n = std::max<int64_t>(b - a, 0); else E.cur = jt_slice(E.cur, a, std::max<int64_t>(b - a, 0));
         } else if (f.name == "asetpts") {
             // timestamps only
         } else if (f.name == "highpass" || f.name == "lowpass") {
@@ -335,15 +355,15 @@ void jt_graph_enqueue(jt_ctx *c, const std::string &spec, const void *d_in, int6
             if (poles != 2 || wt != "q") JT_THROW(JT_ERR_UNSUPPORTED, "%s poles=%d width_type=%s", f.name.c_str(), poles, wt.c_str());
             if (tr != "di" && tr != "tdii") JT_THROW(JT_ERR_UNSUPPORTED, "biquad transform %s", tr.c_str());
             BiquadCoef k = jt_biquad_design(f.name == "highpass", freq, width, E.cur.rate, norm);
-            E.cur = jt_biquad(c, E.cur, k, tr == "tdii", mix);
+            if (!dry) E.cur = jt_biquad(c, E.cur, k, tr == "tdii", mix);
         } else if (f.name == "anlmdn") {
             E.materialise(); E.storage(JT_FMT_FLT);
             const std::string om = f.str("o", "output", "o");
             if (om != "o") JT_THROW(JT_ERR_UNSUPPORTED, "anlmdn output mode %s", om.c_str());
             const double s = f.num("s", "strength", 0.00001), p = f.num("p", "patch", 0.002), r = f.num("r", "research", 0.006), m = f.num("m", "smooth", 11.0);
-            Sig o = jt_anlmdn(c, E.cur, s, p, r, m);
+            if (!dry) E.cur = jt_anlmdn(c, E.cur, s, p, r, m);
             const int K = (int)llround(p * E.cur.rate);      // frames of H = 2K+1 samples
-            E.cur = o; E.frames = reframe(E.frames, E.cur.n, 2 * K + 1);
+            E.frames = reframe(E.frames, E.cur.n, 2 * K + 1);
         } else if (f.name == "afftdn") {
             E.materialise(); E.storage(JT_FMT_FLT);
             AfftdnParams p;
@@ -361,7 +381,17 @@ void jt_graph_enqueue(jt_ctx *c, const std::string &spec, const void *d_in, int6
             }
             const std::string om = f.str("om", "output_mode", "o");
             if (om != "o" && om != "output") JT_THROW(JT_ERR_UNSUPPORTED, "afftdn output mode %s", om.c_str());
-            E.cur = jt_afftdn(c, E.cur, p);
+            if (chunked && p.tn) {
+                // the tracked noise floor is the one state of the chain with unbounded memory: its carry crosses chunks
+                const int64_t A = E.cur.rate / 80;
+                const int64_t a = chunk->link_pos(chunk->own_first, E.cur.rate) - chunk->link_pos(chunk->local_first, E.cur.rate);
+                const int64_t b = chunk->last ? E.cur.n : chunk->link_pos(chunk->own_first + chunk->owned, E.cur.rate) - chunk->link_pos(chunk->local_first, E.cur.rate);
+                if (a % A) JT_THROW(JT_ERR_INVALID_ARG, "chunk boundary is not on afftdn's hop grid (%lld samples)", (long long)A);
+                AfftdnCarry cy; cy.hop0 = a / A; cy.hop1 = chunk->last ? (E.cur.n + A - 1) / A : (b + A - 1) / A;
+                cy.key = chunk->own_first; cy.fn = chunk->exchange; cy.user = chunk->exchange_user; cy.n_ranks = chunk->n_ranks;
+                E.cur = jt_afftdn(c, E.cur, p, &cy);
+                g.exchanges++;
+            } else if (!dry) E.cur = jt_afftdn(c, E.cur, p);
             E.frames = reframe(E.frames, E.cur.n, E.cur.rate / 80);
         } else if (f.name == "agate") {
             E.materialise(); E.storage(JT_FMT_DBL);
@@ -370,7 +400,7 @@ void jt_graph_enqueue(jt_ctx *c, const std::string &spec, const void *d_in, int6
             p.release = f.num("release", "", 250); p.range = f.num("range", "", 0.06125); p.knee = f.num("knee", "", 2.828427125);
             p.makeup = f.num("makeup", "", 1); p.detection_rms = f.str("detection", "", "rms") == "rms";
             if (f.num("level_in", "", 1) != 1 || f.str("mode", "", "downward") != "downward") JT_THROW(JT_ERR_UNSUPPORTED, "agate level_in/mode");
-            E.cur = jt_agate(c, E.cur, p);
+            if (!dry) E.cur = jt_agate(c, E.cur, p);
         } else if (f.name == "acompressor") {
             E.materialise(); E.storage(JT_FMT_DBL);
             CompParams p;
@@ -379,18 +409,19 @@ void jt_graph_enqueue(jt_ctx *c, const std::string &spec, const void *d_in, int6
             p.mix = f.num("mix", "", 1); p.detection_rms = f.str("detection", "", "rms") == "rms";
             if (f.num("level_in", "", 1) != 1 || f.str("mode", "", "downward") != "downward" || f.str("link", "", "average") != "average")
                 JT_THROW(JT_ERR_UNSUPPORTED, "acompressor level_in/mode/link");
-            E.cur = jt_acompressor(c, E.cur, p);
+            if (!dry) E.cur = jt_acompressor(c, E.cur, p);
         } else if (f.name == "deesser") {
             E.materialise(); E.storage(JT_FMT_DBL);
             if (f.str("s", "", "o") != "o") JT_THROW(JT_ERR_UNSUPPORTED, "deesser mode");
-            E.cur = jt_deesser(c, E.cur, f.num("i", "", 0.0), f.num("m", "", 0.5), f.num("f", "", 0.5));
+            if (!dry) E.cur = jt_deesser(c, E.cur, f.num("i", "", 0.0), f.num("m", "", 0.5), f.num("f", "", 0.5));
         } else if (f.name == "volume") {
             std::string v = f.str("volume", "", "1.0");
             if (const std::string *p = f.get("")) v = *p;
             char *end = nullptr; double g = strtod(v.c_str(), &end);
             if (end && !strcmp(end, "dB")) g = pow(10.0, g / 20.0); else if (end && *end) JT_THROW(JT_ERR_UNSUPPORTED, "volume expression '%s'", v.c_str());
             E.materialise();
-            E.cur = jt_volume(c, E.cur, g); E.link_fmt = JT_FMT_FLT;
+            if (dry) E.cur.fmt = JT_FMT_FLT; else E.cur = jt_volume(c, E.cur, g);
+            E.link_fmt = JT_FMT_FLT;
         } else if (f.name == "alimiter") {
             E.materialise(); E.storage(JT_FMT_DBL);
             LimiterParams p;
@@ -398,13 +429,13 @@ void jt_graph_enqueue(jt_ctx *c, const std::string &spec, const void *d_in, int6
             p.level_in = f.num("level_in", "", 1); p.level_out = f.num("level_out", "", 1); p.auto_level = f.flag("level", "", true);
             p.asc = f.flag("asc", "", false); p.asc_level = f.num("asc_level", "", 0.5); p.latency = f.flag("latency", "", false);
             if (!p.latency) JT_THROW(JT_ERR_UNSUPPORTED, "alimiter latency=0");
-            E.cur = jt_alimiter(c, E.cur, p);
+            if (!dry) E.cur = jt_alimiter(c, E.cur, p);
         } else if (f.name == "adeclick") {
             E.materialise(); E.storage(JT_FMT_DBL);
             const std::string m = f.str("m", "method", "a");
             const int save = (m == "s" || m == "save") ? 1 : 0;
             const double w = f.num("w", "window", 55), o = f.num("o", "overlap", 75);
-            E.cur = jt_adeclick(c, E.cur, w, o, f.num("a", "arorder", 2), f.num("t", "threshold", 2), f.num("b", "burst", 2), save);
+            if (!dry) E.cur = jt_adeclick(c, E.cur, w, o, f.num("a", "arorder", 2), f.num("t", "threshold", 2), f.num("b", "burst", 2), save);
             const int ws = (int)(E.cur.rate * w / 1000.), hop = (int)(ws * (1. - o / 100.));
             E.frames = reframe(E.frames, E.cur.n, std::max(hop, 1));
         } else if (f.name == "loudnorm") {
@@ -419,16 +450,20 @@ void jt_graph_enqueue(jt_ctx *c, const std::string &spec, const void *d_in, int6
                 if (mTP != 99 && mTh != -70 && mLRA != 0 && mI != 0 && off_tp <= TP && mLRA <= LRA) { lin_mode = true; offset = off; }
             }
             g.has_ln = true; g.ln_linear = lin_mode; g.ln_I = I;
+            g.ln_dual = dual;
             if (lin_mode) {
                 E.materialise(); E.storage(JT_FMT_DBL);
-                jt_loudnorm_meter_launch(c, E.cur, dual, g.ln_in);
-                E.cur = jt_gain_f64(c, E.cur, pow(10., offset / 20.));
-                jt_loudnorm_meter_launch(c, E.cur, dual, g.ln_out);
+                g.ln_in_sig = E.cur;
+                if (mode == JT_GRAPH_NORMAL) jt_loudnorm_meter_launch(c, E.cur, dual, g.ln_in);
+                if (!dry) E.cur = jt_gain_f64(c, E.cur, pow(10., offset / 20.));
+                g.ln_out_sig = E.cur;
+                if (mode == JT_GRAPH_NORMAL) jt_loudnorm_meter_launch(c, E.cur, dual, g.ln_out);
             } else {
                 // dynamic mode: af_loudnorm.c query_formats forces the input link to 192 kHz / dbl
                 if (want_pcm || !last) JT_THROW(JT_ERR_UNSUPPORTED, "loudnorm dynamic mode with audio output (linear-mode preconditions not met: measured_I=%g measured_TP=%g measured_LRA=%g measured_thresh=%g)", mI, mTP, mLRA, mTh);
                 do_resample(E, 192000, JT_FMT_DBL, true);
-                jt_loudnorm_meter_launch(c, E.cur, dual, g.ln_in);
+                g.ln_in_sig = E.cur;
+                if (mode == JT_GRAPH_NORMAL) jt_loudnorm_meter_launch(c, E.cur, dual, g.ln_in);
             }
         } else if (f.name == "astats") {
             E.materialise();
@@ -448,7 +483,8 @@ void jt_graph_enqueue(jt_ctx *c, const std::string &spec, const void *d_in, int6
             const bool tp = peak.find("true") != std::string::npos;
             const bool dual = f.flag("dualmono", "", false);
             // input link is dbl; s16/flt storage widens exactly on load
-            if (want_meta) jt_ebur128_launch(c, E.cur, dual, tp, g.r128p);
+            if (want_meta && mode == JT_GRAPH_NORMAL) jt_ebur128_launch(c, E.cur, dual, tp, g.r128p);
+            g.r128_sig = E.cur; g.r128_dual = dual; g.r128_tp = tp;
             E.has_r128 = true; E.link_fmt = JT_FMT_DBL;
             const int tick = E.cur.rate / 10;
             E.frames = reframe(E.frames, E.cur.n, tick);
@@ -463,7 +499,8 @@ void jt_graph_enqueue(jt_ctx *c, const std::string &spec, const void *d_in, int6
     g.frames.swap(E.frames);
     g.has_astats = E.has_astats; g.has_spec = E.has_spec; g.has_r128 = E.has_r128; g.astats_overall_only = E.astats_overall_only;
     g.astats_sig = E.astats_sig; g.spec_sig = E.spec_sig; g.spec_win = E.spec_win;
-    if (!want_meta) return;
+    for (size_t i = 0; i < g.frames.size(); i++) if (g.frames[i].astats_pos >= 0) g.last_astats_frame = (long)i;
+    if (!want_meta || mode != JT_GRAPH_NORMAL) return;
     // ---- analysis kernels whose input cadence depends on the final sink framing -------------
     const size_t nf = g.frames.size();
     if (g.has_spec) {
@@ -473,7 +510,6 @@ void jt_graph_enqueue(jt_ctx *c, const std::string &spec, const void *d_in, int6
         for (size_t i = 0; i < nf; i++) if (g.frames[i].hop >= 0) wanted.push_back(g.frames[i].hop);
         jt_aspectralstats_launch(c, g.spec_sig, g.spec_win, &wanted, g.specp);
     }
-    for (size_t i = 0; i < nf; i++) if (g.frames[i].astats_pos >= 0) g.last_astats_frame = (long)i;
     if (g.has_astats && g.last_astats_frame >= 0) jt_astats_launch(c, g.astats_sig, g.frames[g.last_astats_frame].astats_pos, g.astp);
 }
 
@@ -565,6 +601,14 @@ void jt_graph_finish(jt_ctx *c, GraphRun &g, GraphResult &res)
         m.astats_overall_RMS_level = jt_wire("%f", a.overall_rms);
         m.astats_overall_Peak_level = jt_wire("%f", a.overall_peak);
     }
+}
+
+void jt_assemble_records(const std::vector<FrameRef> &frames, bool has_r128, const R128Result &r128, bool has_spec,
+                         const std::vector<float> &spec_rows, int64_t spec_hops, GraphResult &res)
+{
+    std::vector<std::thread> pool;
+    assemble_records(frames, has_r128, r128, has_spec, spec_rows, spec_hops, res, pool);
+    for (auto &t : pool) t.join();
 }
 
 // Pass-1 sink-frame records of a stream whose per-tick / per-hop / astats products were computed elsewhere (several

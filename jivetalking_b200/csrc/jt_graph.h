@@ -47,9 +47,25 @@ struct GraphRun {
     long last_astats_frame = -1;
     R128Result r128; bool r128_done = false;
     // loudnorm
-    bool has_ln = false, ln_linear = false; double ln_I = 0;
+    bool has_ln = false, ln_linear = false, ln_dual = false; double ln_I = 0;
     LoudnormPending ln_in, ln_out;
+    // the signals the measuring filters see (DRY: sizes / formats only; CHUNK: device signals of the local window)
+    Sig r128_sig, ln_in_sig, ln_out_sig; bool r128_dual = false, r128_tp = false;
+    int exchanges = 0;          // cross-chunk exchange steps the graph went through (CHUNK)
 };
+
+enum { JT_GRAPH_NORMAL = 0, JT_GRAPH_DRY = 1, JT_GRAPH_CHUNK = 2 };
+// Where a local window sits in its stream (input-link sample indices) and how carries cross chunk boundaries
+struct GraphChunk {
+    int64_t local_first = 0, own_first = 0, owned = 0, total = 0; int rate = 0; bool last = false;
+    jt_exchange_fn exchange = nullptr; void *exchange_user = nullptr; int n_ranks = 1;
+    // position on a link running at `link_rate` of input-link position `pos` (exact: boundaries sit on the chunk unit)
+    int64_t link_pos(int64_t pos, int link_rate) const { return (int64_t)((__int128)pos * link_rate / rate); }
+};
+void jt_graph_build(jt_ctx *c, const std::string &spec, const void *d_in, int64_t n_frames, int rate, int channels,
+                    int fmt, int frame_size, bool want_pcm, bool want_meta, int mode, const GraphChunk *chunk, GraphRun &g);
+void jt_assemble_records(const std::vector<FrameRef> &frames, bool has_r128, const R128Result &r128, bool has_spec,
+                         const std::vector<float> &spec_rows, int64_t spec_hops, GraphResult &res);
 void jt_graph_enqueue(jt_ctx *c, const std::string &spec, const void *d_in, int64_t n_frames, int rate, int channels,
                       int fmt, int frame_size, bool want_pcm, bool want_meta, GraphRun &g);
 const R128Result &jt_graph_r128_early(jt_ctx *c, GraphRun &g);     // waits for the ebur128 values only

@@ -41,6 +41,8 @@ struct jt_ctx {
     // pinned host arena for small device->host results (tick energies, statistics rows); reset per API call
     std::vector<std::pair<char *, size_t>> pin_blocks; size_t pin_block = 0, pin_used = 0;
     std::vector<cudaEvent_t> event_pool; size_t events_used = 0;
+    // cross-chunk carries of a stream sharded over several contexts / GPUs (jt_set_exchange)
+    jt_exchange_fn exchange = nullptr; void *exchange_user = nullptr; int exchange_ranks = 1;
 };
 
 struct JtError { int code; std::string msg; };
@@ -133,6 +135,8 @@ void jt_loudnorm_meter(jt_ctx *c, const Sig &in, bool dual_mono, LoudnormMeter &
 struct LoudnormPending { int64_t nt = 0, nfull = 0; int s100 = 0; bool dual_mono = false; double *hp = nullptr, *hk = nullptr; cudaEvent_t ev = nullptr; };
 void jt_loudnorm_meter_launch(jt_ctx *c, const Sig &in, bool dual_mono, LoudnormPending &pd);
 void jt_loudnorm_meter_finish(jt_ctx *c, LoudnormPending &pd, LoudnormMeter &out);
+// host part over per-100 ms values (K-weighted energy, sample peak): nt ticks, the first nfull of them complete
+void jt_loudnorm_meter_host_finalize(const double *hp, const double *hk, int64_t nt, int64_t nfull, int s100, bool dual_mono, LoudnormMeter &out);
 
 // ---- k_astats.cu --------------------------------------------------------------------------
 struct AstatsResult { double v[JT_AS_COUNT]; double overall_rms, overall_peak; double nb_samples; };
@@ -171,7 +175,11 @@ struct AfftdnParams {
     double nr = 12, nf = -50, rf = -38, ad = 0.5, fo = 1.0, bm = 1.25; int nt = 0; int tn = 0; int gs = 0;
     bool has_bn = false; double bn[15] = {0};
 };
-Sig  jt_afftdn(jt_ctx *c, const Sig &in_flt, const AfftdnParams &p);
+// afftdn over a window of a longer stream: hops [hop0, hop1) of the window are owned; the tracked noise floor entering
+// hop0 is obtained by composing the affine carries of the chunks before this one (key = stream position), exchanged
+// through `fn` (an all-gather of fixed-size records; NULL = this chunk starts the stream / single chunk)
+struct AfftdnCarry { int64_t hop0 = 0, hop1 = 0, key = 0; jt_exchange_fn fn = nullptr; void *user = nullptr; int n_ranks = 1; };
+Sig  jt_afftdn(jt_ctx *c, const Sig &in_flt, const AfftdnParams &p, const AfftdnCarry *carry = nullptr);
 
 // ---- k_dynamics.cu ------------------------------------------------------------------------
 struct GateParams { double threshold, ratio, attack, release, range, knee, makeup; int detection_rms; };

@@ -22,6 +22,9 @@
 #include "jt_device.cuh"
 #include "jt_fft.cuh"
 #include <cstdio>
+#include <algorithm>
+#include <cstring>
+#include <vector>
 
 #define AF_THREADS 512
 #define AF_MAXBANDS 64
@@ -337,7 +340,16 @@ static double band_noise_extrapolated(const double *bn, double sample_rate)
     return sum;
 }
 
-Sig jt_afftdn(jt_ctx *c, const Sig &in, const AfftdnParams &P)
+// One chunk's view of the noise-floor recurrence nf' = flag ? 0.1*cand + 0.9*nf : nf: the affine map (A, B) of a run
+// of hops, composed on the host from the per-hop candidates.
+static void floor_affine(const double *cand, int64_t h0, int64_t h1, double &A, double &B)
+{
+    A = 1.0; B = 0.0;
+    for (int64_t h = h0; h < h1; h++) if (cand[2 * h + 1] != 0.0) { A *= 0.9; B = 0.1 * cand[2 * h] + B * 0.9; }
+}
+struct FloorCarryRec { int64_t key; double A, B; int64_t valid; };
+
+Sig jt_afftdn(jt_ctx *c, const Sig &in, const AfftdnParams &P, const AfftdnCarry *carry)
 {
     if (in.fmt != JT_FMT_FLT) JT_THROW(JT_ERR_INVALID_ARG, "afftdn expects float input");
     Sig o = in; o.d = jt_dalloc<float>(c, in.n);
@@ -430,8 +442,34 @@ Sig jt_afftdn(jt_ctx *c, const Sig &in, const AfftdnParams &P)
     {
         { JtLaunch L(c, "afftdn:fwd");
           k_afftdn_fwd<<<grid_fft, AF_THREADS, smem_fft, c->stream>>>((const float *)in.d, in.n, n_hops, K, d_window, d_tw, d_spec, P.tn, d_cand); }
+        double nf_start = P.nf;
+        if (carry && P.tn) {
+            // the floor entering the owned hops = the stream's initial floor pushed through every earlier chunk's
+            // affine carry; ONE exchange of (key, A, B) per chunk, the only data-path collective of the chain
+            std::vector<double> h_cand((size_t)n_hops * 2);
+            JT_CUDA(cudaMemcpyAsync(h_cand.data(), d_cand, sizeof(double) * 2 * n_hops, cudaMemcpyDeviceToHost, c->stream));
+            JT_CUDA(cudaStreamSynchronize(c->stream));
+            const int64_t h0 = std::min(std::max<int64_t>(carry->hop0, 0), n_hops), h1 = std::min(std::max(carry->hop1, h0), n_hops);
+            FloorCarryRec mine; mine.key = carry->key; mine.valid = 1;
+            floor_affine(h_cand.data(), h0, h1, mine.A, mine.B);
+            double entry = P.nf;
+            if (carry->fn) {
+                const int nr = std::max(carry->n_ranks, 1);
+                std::vector<FloorCarryRec> all((size_t)nr);
+                memset(all.data(), 0, sizeof(FloorCarryRec) * nr);
+                if (carry->fn(carry->user, &mine, (int64_t)sizeof(mine), all.data()) != 0) JT_THROW(JT_ERR_INVALID_ARG, "afftdn noise-floor exchange failed");
+                std::vector<FloorCarryRec> before;
+                for (const FloorCarryRec &r : all) if (r.valid && r.key < mine.key) before.push_back(r);
+                std::sort(before.begin(), before.end(), [](const FloorCarryRec &a, const FloorCarryRec &b) { return a.key < b.key; });
+                for (const FloorCarryRec &r : before) entry = r.A * entry + r.B;
+            } else if (h0 > 0) JT_THROW(JT_ERR_INVALID_ARG, "afftdn track_noise in a mid-stream chunk needs the exchange callback (jt_set_exchange)");
+            // start value for the window's first hop such that the recurrence arrives at `entry` on hop h0 (the context
+            // hops before h0 only warm up the contractive gain recursions)
+            double Ah, Bh; floor_affine(h_cand.data(), 0, h0, Ah, Bh);
+            nf_start = Ah > 1e-9 ? (entry - Bh) / Ah : P.nf;
+        }
         { JtLaunch L(c, "afftdn:floor");
-          k_afftdn_floor<<<1, 1024, 0, c->stream>>>(d_cand, n_hops, P.nf, K.floor_, P.tn, d_pre, d_post); }
+          k_afftdn_floor<<<1, 1024, 0, c->stream>>>(d_cand, n_hops, nf_start, K.floor_, P.tn, d_pre, d_post); }
         { JtLaunch L(c, "afftdn:gain");
           dim3 g((K.bins + AF_GAIN_THREADS - 1) / AF_GAIN_THREADS, (unsigned)((n_hops + chunk_gain - 1) / chunk_gain));
           k_afftdn_gain<<<g, AF_GAIN_THREADS, 0, c->stream>>>(d_spec, n_hops, chunk_gain, warm, K, d_rel, d_pre, d_gain, d_clean); }

@@ -295,11 +295,16 @@ void jt_loudnorm_meter_launch(jt_ctx *c, const Sig &in, bool dual_mono, Loudnorm
 
 void jt_loudnorm_meter_finish(jt_ctx *c, LoudnormPending &pd, LoudnormMeter &out)
 {
-    const int s100 = pd.s100; const int64_t nfull = pd.nfull, nt = pd.nt; const bool dual_mono = pd.dual_mono;
+    out.I = -HUGE_VAL; out.LRA = 0; out.thresh = -70.0; out.sample_peak = 0;
+    if (pd.nt <= 0) return;
+    JT_CUDA(cudaEventSynchronize(pd.ev));
+    jt_loudnorm_meter_host_finalize(pd.hp, pd.hk, pd.nt, pd.nfull, pd.s100, pd.dual_mono, out);
+}
+
+void jt_loudnorm_meter_host_finalize(const double *hp, const double *hk, int64_t nt, int64_t nfull, int s100, bool dual_mono, LoudnormMeter &out)
+{
     out.I = -HUGE_VAL; out.LRA = 0; out.thresh = -70.0; out.sample_peak = 0;
     if (nt <= 0) return;
-    JT_CUDA(cudaEventSynchronize(pd.ev));
-    const double *hp = pd.hp, *hk = pd.hk;
     for (int64_t k = 0; k < nt; k++) out.sample_peak = std::max(out.sample_peak, hk[k]);
 
     const double wgt = dual_mono ? 2.0 : 1.0;

@@ -121,6 +121,20 @@ def lib():
     L.jt_analyse_chunk_bytes.argtypes = [_I64, _INT]
     L.jt_analyse_chunk.argtypes = [_P, _P, _I64, _INT, _INT, _INT, _I64, _I64, _I64, _I64, _P, _I64, C.POINTER(_I64)]
     L.jt_analyse_merge.argtypes = [_INT, C.POINTER(_P), C.POINTER(Measurements), C.POINTER(Interval), _I64, C.POINTER(_I64)]
+    L.jt_set_exchange.argtypes = [_P, _P, _P, _INT]
+    L.jt_graph_exchanges.restype = _INT
+    L.jt_graph_exchanges.argtypes = [C.c_char_p]
+    L.jt_graph_chunk_unit.restype = _I64
+    L.jt_graph_chunk_unit.argtypes = [C.c_char_p, _INT]
+    L.jt_graph_chunk_context.argtypes = [C.c_char_p, _INT, C.POINTER(_I64), C.POINTER(_I64)]
+    L.jt_graph_chunk_bytes.restype = _I64
+    L.jt_graph_chunk_bytes.argtypes = [C.c_char_p, _I64, _INT]
+    L.jt_graph_chunk.argtypes = [_P, C.c_char_p, _P, _I64, _INT, _INT, _INT, _I64, _I64, _I64, _I64, _INT,
+                                 _P, _I64, C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_INT), C.POINTER(_INT),
+                                 _P, _I64, C.POINTER(_I64)]
+    L.jt_graph_merge.argtypes = [C.c_char_p, _I64, _INT, _INT, _INT, _INT, _INT, C.POINTER(_P),
+                                 C.POINTER(FrameMeta), _I64, C.POINTER(_I64), C.POINTER(LoudnormStats),
+                                 C.POINTER(Measurements)]
     L.jt_band_rms.argtypes = [_P, _P, _I64, _INT, _INT, _INT, C.c_double, C.c_double, _P, _P, _INT, _P, _P]
     pa = [_P, _P, _I64, _INT, _INT, _INT, C.c_char_p, _P, _I64, C.POINTER(ProcessResult)]
     L.jt_process_audio.argtypes = pa
@@ -246,6 +260,54 @@ class Context:
         self._check(rc)
         return buf.raw[: n.value]
 
+    def set_exchange(self, fn, n_ranks):
+        """fn(send: bytes) -> bytes of n_ranks records in rank order (an all-gather); None removes it.  The carries
+        of a sharded stream (afftdn's tracked noise floor) cross chunk boundaries through it (jt_set_exchange)."""
+        if fn is None:
+            self._xfn = None
+            lib().jt_set_exchange(self._h, None, None, 1)
+            return
+
+        def _cb(user, send, nbytes, recv):
+            try:
+                got = fn(C.string_at(send, nbytes))
+                if len(got) != nbytes * n_ranks:
+                    return -1
+                C.memmove(recv, got, len(got))
+                return 0
+            except Exception:          # an exception must not unwind through the C frames
+                import traceback
+                traceback.print_exc()
+                return -1
+
+        self._xfn = EXCHANGE_FN(_cb)          # keep the trampoline alive as long as the context uses it
+        lib().jt_set_exchange(self._h, C.cast(self._xfn, _P), None, n_ranks)
+
+    def graph_chunk(self, spec, pcm_local, rate, channels, local_first, own_first, owned, total_frames,
+                    frame_size=4096, want_pcm=True, want_blob=True):
+        """Any graph on a window of a longer stream (include/jtdsp.h: jt_graph_chunk).  Returns
+        dict(pcm=owned sink samples or None, out_first, n_out, rate, fmt, blob=bytes)."""
+        pcm_local = np.ascontiguousarray(pcm_local)
+        fmt = _FMT_OF_NP[pcm_local.dtype]
+        bspec = spec.encode()
+        n_local = pcm_local.size // channels
+        cap = lib().jt_graph_max_out_frames(bspec, owned, rate) + 4096
+        out = np.zeros(cap, dtype=np.float64) if want_pcm else None
+        bcap = lib().jt_graph_chunk_bytes(bspec, owned, rate)
+        buf = C.create_string_buffer(bcap) if want_blob else None
+        o_first, n_out, orate, ofmt, nb = _I64(0), _I64(0), _INT(0), _INT(0), _I64(0)
+        rc = lib().jt_graph_chunk(self._h, bspec, pcm_local.ctypes.data_as(_P), n_local, rate, channels, fmt,
+                                  local_first, own_first, owned, total_frames, frame_size,
+                                  out.ctypes.data_as(_P) if want_pcm else None, cap, C.byref(o_first), C.byref(n_out),
+                                  C.byref(orate), C.byref(ofmt), buf, bcap, C.byref(nb))
+        self._check(rc)
+        res = dict(out_first=o_first.value, n_out=n_out.value, rate=orate.value, fmt=ofmt.value, pcm=None,
+                   blob=buf.raw[: nb.value] if want_blob else b"")
+        if want_pcm:
+            dt = _NP_OF_FMT[ofmt.value]
+            res["pcm"] = out.view(np.uint8)[: n_out.value * np.dtype(dt).itemsize].view(dt).copy()
+        return res
+
     def band_rms(self, pcm, rate, start_s, duration_s, lo_hz, hi_hz, channels=1):
         pcm = np.ascontiguousarray(pcm)
         fmt = _FMT_OF_NP[pcm.dtype]
@@ -323,6 +385,42 @@ def analyse_merge(blobs, total_frames, rate):
     if rc:
         raise JtError(rc, lib().jt_strerror(rc).decode())
     return m, [iv[i] for i in range(n_iv.value)]
+
+
+EXCHANGE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p)
+
+
+def graph_chunk_unit(spec, rate):
+    return lib().jt_graph_chunk_unit(spec.encode(), rate)
+
+
+def graph_exchanges(spec):
+    return lib().jt_graph_exchanges(spec.encode())
+
+
+def graph_chunk_context(spec, rate):
+    """Recommended (left, right) context of a mid-stream chunk, input frames."""
+    le, ri = _I64(0), _I64(0)
+    rc = lib().jt_graph_chunk_context(spec.encode(), rate, C.byref(le), C.byref(ri))
+    if rc:
+        raise JtError(rc, lib().jt_strerror(rc).decode())
+    return le.value, ri.value
+
+
+def graph_merge(spec, blobs, total_frames, rate, channels=1, fmt=FMT_FLT, frame_size=4096, want_meta=True):
+    """Host-only merge of jt_graph_chunk blobs -> dict(meta=[FrameMeta], loudnorm, measurements) of the whole stream."""
+    bspec = spec.encode()
+    keep = [C.create_string_buffer(b, len(b)) for b in blobs]
+    arr = (_P * len(keep))(*[C.cast(k, _P) for k in keep])
+    mcap = lib().jt_graph_max_meta(bspec, total_frames, rate, frame_size) if want_meta else 0
+    meta = (FrameMeta * mcap)() if want_meta else None
+    n_meta = _I64(0)
+    ln, m = LoudnormStats(), Measurements()
+    rc = lib().jt_graph_merge(bspec, total_frames, rate, channels, fmt, frame_size, len(keep), arr, meta, mcap,
+                              C.byref(n_meta), C.byref(ln), C.byref(m))
+    if rc:
+        raise JtError(rc, lib().jt_strerror(rc).decode())
+    return dict(meta=[meta[i] for i in range(n_meta.value)] if want_meta else [], loudnorm=ln, measurements=m)
 
 
 def build_pass3_spec(output_i, output_tp, target_i=-16.0, target_tp=-1.0, target_lra=20.0):

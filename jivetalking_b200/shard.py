@@ -87,3 +87,142 @@ def analyse_stream_sharded(ctx, pcm, rate, channels=1, device=None):
         blob = ctx.analyse_chunk(pcm.reshape(-1)[lo * channels: hi * channels], rate, channels, lo, first, owned, total)
     blobs = [b for b in allgather_blobs(blob, device=device) if len(b)]
     return gpudsp.analyse_merge(blobs, total, rate)
+
+
+# ---- Passes 2-4 of one stream over several GPUs (configs[3]) ------------------------------------------
+# Every pass is a graph (a spec string) run on contiguous chunks with context (jt_graph_chunk); what crosses rank
+# boundaries is (1) afftdn's noise-floor carry, inside the pass, through the exchange callback, (2) one all-gather of
+# the chunks' measurement blobs per measuring pass, merged on every rank (jt_graph_merge), and (3) the Pass-2 output
+# itself (the reference's intermediate FLAC), gathered so that Pass 3/4 can cut their own chunk grid at 44.1 kHz.
+class LocalComm:
+    """All chunks in ONE process, run in stream order (tests on one GPU, and the reference for what the ranks of a
+    process group do collectively)."""
+
+    def __init__(self, n_chunks):
+        self.world = n_chunks
+        self._carries = []
+
+    def ranks(self):
+        return range(self.world)
+
+    def begin_pass(self):
+        self._carries = []
+
+    def exchange(self, send):
+        # chunk k enters after chunks 0..k-1: their records are known, later chunks' are not needed (the library
+        # only composes records with a smaller stream position)
+        self._carries.append(bytes(send))
+        return b"".join(self._carries) + bytes(len(send)) * (self.world - len(self._carries))
+
+    def gather_blobs(self, per_rank):
+        return [b for b in per_rank if len(b)]
+
+    def gather_pcm(self, per_rank):
+        import numpy as np
+        return np.concatenate([p for p in per_rank if p is not None and len(p)])
+
+
+class DistComm:
+    """One chunk per rank of the torch.distributed process group (NCCL on GPUs, gloo in the CPU tests)."""
+
+    def __init__(self, device=None):
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.device = device
+
+    def ranks(self):
+        return [self.rank]
+
+    def begin_pass(self):
+        pass
+
+    def exchange(self, send):
+        if self.world == 1:
+            return bytes(send)
+        t = torch.frombuffer(bytearray(send), dtype=torch.uint8)
+        if self.device is not None:
+            t = t.to(self.device)
+        parts = [torch.zeros_like(t) for _ in range(self.world)]
+        dist.all_gather(parts, t)
+        return b"".join(p.cpu().numpy().tobytes() for p in parts)
+
+    def gather_blobs(self, per_rank):
+        return [b for b in allgather_blobs(per_rank[0], device=self.device) if len(b)]
+
+    def gather_pcm(self, per_rank):
+        """Ragged all-gather of every rank's owned samples, in rank (= stream) order; bytes on the wire (gloo has no
+        int16 collectives, and NCCL does not care)."""
+        import numpy as np
+        a = np.ascontiguousarray(per_rank[0])
+        if self.world == 1:
+            return a
+        raw = a.view(np.uint8).reshape(-1)
+        n = torch.tensor([raw.size], dtype=torch.int64, device=self.device)
+        sizes = [torch.zeros_like(n) for _ in range(self.world)]
+        dist.all_gather(sizes, n)
+        cap = int(max(int(x[0]) for x in sizes))
+        buf = torch.zeros(cap, dtype=torch.uint8, device=self.device)
+        if raw.size:
+            buf[: raw.size] = torch.from_numpy(raw).to(buf.device)
+        parts = [torch.zeros_like(buf) for _ in range(self.world)]
+        dist.all_gather(parts, buf)
+        return np.concatenate([parts[r][: int(sizes[r][0])].cpu().numpy() for r in range(self.world)]).view(a.dtype)
+
+
+def run_graph_sharded(ctx, comm, spec, pcm, rate, channels=1, want_pcm=True, context=None):
+    """One graph over one stream, one chunk per rank of `comm`.  Returns (sink pcm of the whole stream or None,
+    merged dict(meta, loudnorm, measurements)) on every rank."""
+    from . import gpudsp
+    total = pcm.size // channels
+    unit = gpudsp.graph_chunk_unit(spec, rate)
+    left, right = context if context else gpudsp.graph_chunk_context(spec, rate)
+    chunks = plan_stream_chunks(total, unit, comm.world)
+    n_exch = gpudsp.graph_exchanges(spec)
+    ctx.set_exchange(comm.exchange, comm.world)
+    comm.begin_pass()
+    blobs, parts = [], []
+    try:
+        for r in comm.ranks():
+            first, owned = chunks[r]
+            if owned <= 0:                     # more ranks than units: stay in step with the collectives
+                for _ in range(n_exch):
+                    comm.exchange(bytes(32))
+                blobs.append(b"")
+                parts.append(None)
+                continue
+            lo = max(0, first - left)
+            hi = min(total, first + owned + right)
+            res = ctx.graph_chunk(spec, pcm.reshape(-1)[lo * channels: hi * channels], rate, channels, lo, first, owned,
+                                  total, want_pcm=want_pcm)
+            blobs.append(res["blob"])
+            parts.append(res["pcm"])
+    finally:
+        ctx.set_exchange(None, 1)
+    fmt = gpudsp._FMT_OF_NP[pcm.dtype]
+    merged = gpudsp.graph_merge(spec, comm.gather_blobs(blobs), total, rate, channels, fmt)
+    out = None
+    if want_pcm:
+        import numpy as np
+        dt = next(p.dtype for p in parts if p is not None)
+        out = comm.gather_pcm([p if p is not None else np.zeros(0, dtype=dt) for p in parts])
+    return out, merged
+
+
+def process_stream_sharded(ctx, comm, pcm, rate, channels=1, pass2_spec=None,
+                           target_i=-16.0, target_tp=-1.0, target_lra=20.0):
+    """The four-pass chain (ProcessAudio, processor.go:78-216) of ONE stream over the ranks of `comm`: what
+    jt_process_audio does on one GPU, with every pass cut into chunks.  Returns (int16 mono 44.1 kHz output,
+    dict(filtered, final, pass3, pass4, plan, specs)) on every rank.  Pass 1 is analyse_stream_sharded."""
+    from . import gpudsp
+    spec2 = pass2_spec or gpudsp.default_pass2_spec()
+    out2, mg2 = run_graph_sharded(ctx, comm, spec2, pcm, rate, channels, want_pcm=True)
+    filtered = mg2["measurements"]
+    spec3, plan = gpudsp.build_pass3_spec(filtered.input_i, filtered.input_tp, target_i, target_tp, target_lra)
+    _, mg3 = run_graph_sharded(ctx, comm, spec3, out2, 44100, 1, want_pcm=False)
+    p3 = mg3["loudnorm"]
+    if not (p3.input_i > -70.0):
+        raise gpudsp.JtError(-1, f"cannot normalise silent audio (measured {p3.input_i:.1f} LUFS)")
+    spec4, eff, off = gpudsp.build_pass4_spec(plan, p3, target_i, target_tp, target_lra, 44100)
+    out4, mg4 = run_graph_sharded(ctx, comm, spec4, out2, 44100, 1, want_pcm=True)
+    return out4, dict(filtered=filtered, final=mg4["measurements"], pass3=p3, pass4=mg4["loudnorm"], plan=plan,
+                      effective_target_i=eff, offset_db=off, specs=(spec2, spec3, spec4), pass2_pcm=out2)

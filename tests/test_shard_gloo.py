@@ -102,3 +102,71 @@ def test_merge_rejects_blobs_that_do_not_tile():
     from jivetalking_b200 import gpudsp
     with pytest.raises(gpudsp.JtError):
         gpudsp.analyse_merge([b"\x00" * 256], 48000, 48000)     # no magic
+
+
+# ---- Passes 2-4 of one stream over several ranks: geometry, the exchange, the PCM gather (host logic only) ---------
+def test_graph_chunk_geometry():
+    from jivetalking_b200 import gpudsp
+    p2 = gpudsp.default_pass2_spec()
+    assert gpudsp.graph_chunk_unit(p2, 48000) == 4800          # 100 ms ticks; afftdn hop 600 and the 160:147 period divide it
+    assert gpudsp.graph_chunk_unit(p2, 96000) == 9600
+    assert gpudsp.graph_exchanges(p2) == 1                     # afftdn tn=1: the tracked noise floor crosses the cuts
+    assert gpudsp.graph_exchanges(p2.replace("tn=1", "tn=0")) == 0
+    p3, plan = gpudsp.build_pass3_spec(-30.0, -3.0)
+    assert gpudsp.graph_chunk_unit(p3, 44100) == 4410          # 44.1 -> 192 kHz: 100 ms is 19200 samples there
+    st = gpudsp.LoudnormStats(input_i=-30.0, input_tp=-12.0, input_lra=5.0, input_thresh=-40.0, valid=1)
+    p4, _, _ = gpudsp.build_pass4_spec(plan, st)
+    assert gpudsp.graph_chunk_unit(p4, 44100) == 890820        # lcm(4410-sample tick, 1212-sample adeclick hop)
+    for spec, rate in ((p2, 48000), (p2, 96000), (p3, 44100), (p4, 44100)):
+        unit = gpudsp.graph_chunk_unit(spec, rate)
+        left, right = gpudsp.graph_chunk_context(spec, rate)
+        assert left % unit == 0 and right % unit == 0 and left >= 8 * rate and right >= rate
+    assert gpudsp.graph_chunk_unit("atrim=start=1,astats", 48000) == 0     # not chunkable
+
+
+def test_graph_merge_rejects_garbage():
+    import pytest
+    from jivetalking_b200 import gpudsp
+    with pytest.raises(gpudsp.JtError):
+        gpudsp.graph_merge(gpudsp.default_pass2_spec(), [b"\x00" * 512], 48000, 48000)
+
+
+def test_local_comm_feeds_earlier_carries_only():
+    comm = shard.LocalComm(3)
+    comm.begin_pass()
+    a = comm.exchange(b"A" * 32)
+    b = comm.exchange(b"B" * 32)
+    assert a == b"A" * 32 + bytes(64) and b == b"A" * 32 + b"B" * 32 + bytes(32)
+    comm.begin_pass()
+    assert comm.exchange(b"C" * 32)[:32] == b"C" * 32
+
+
+def _dist_comm_worker(rank, world, port, out):
+    import numpy as np
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    comm = shard.DistComm()
+    got = comm.exchange(bytes([rank + 1]) * 32)
+    pcm = comm.gather_pcm([np.arange(3 + 2 * rank, dtype=np.int16) + 100 * rank])
+    blobs = comm.gather_blobs([b"x" * (5 + rank)])
+    out.put((rank, got, pcm.tolist(), blobs))
+    dist.destroy_process_group()
+
+
+def test_dist_comm_exchange_and_gathers_two_ranks():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_dist_comm_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict((r, rest) for r, *rest in (q.get(timeout=120) for _ in range(world)))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in range(world):
+        got, pcm, blobs = res[r]
+        assert got == b"\x01" * 32 + b"\x02" * 32                      # rank order
+        assert pcm == [0, 1, 2, 100, 101, 102, 103, 104]                # ragged chunks, stream order
+        assert blobs == [b"x" * 5, b"x" * 6]
