@@ -283,16 +283,28 @@ class Context:
         self._xfn = EXCHANGE_FN(_cb)          # keep the trampoline alive as long as the context uses it
         lib().jt_set_exchange(self._h, C.cast(self._xfn, _P), None, n_ranks)
 
+    def _pinned_bytes(self, nbytes):
+        """Grow-only pinned host buffer owned by this context (torch provides the allocation): large results leave the
+        GPU at PCIe rate and no call zero-fills gigabytes of pageable memory."""
+        import torch
+        buf = getattr(self, "_pin", None)
+        if buf is None or buf.numel() < nbytes:
+            self._pin = buf = torch.empty(int(nbytes * 1.05) + 4096, dtype=torch.uint8, pin_memory=True)
+        return buf.numpy()
+
     def graph_chunk(self, spec, pcm_local, rate, channels, local_first, own_first, owned, total_frames,
-                    frame_size=4096, want_pcm=True, want_blob=True):
+                    frame_size=4096, want_pcm=True, want_blob=True, pinned=False):
         """Any graph on a window of a longer stream (include/jtdsp.h: jt_graph_chunk).  Returns
-        dict(pcm=owned sink samples or None, out_first, n_out, rate, fmt, blob=bytes)."""
+        dict(pcm=owned sink samples or None, out_first, n_out, rate, fmt, blob=bytes).  pinned=True: `pcm` is a view
+        into the context's pinned result buffer, valid until the next call with pinned=True."""
         pcm_local = np.ascontiguousarray(pcm_local)
         fmt = _FMT_OF_NP[pcm_local.dtype]
         bspec = spec.encode()
         n_local = pcm_local.size // channels
         cap = lib().jt_graph_max_out_frames(bspec, owned, rate) + 4096
-        out = np.zeros(cap, dtype=np.float64) if want_pcm else None
+        out = None
+        if want_pcm:
+            out = self._pinned_bytes(cap * 8) if pinned else np.empty(cap * 8, dtype=np.uint8)     # 8 bytes/sample holds any format
         bcap = lib().jt_graph_chunk_bytes(bspec, owned, rate)
         buf = C.create_string_buffer(bcap) if want_blob else None
         o_first, n_out, orate, ofmt, nb = _I64(0), _I64(0), _INT(0), _INT(0), _I64(0)
@@ -305,7 +317,7 @@ class Context:
                    blob=buf.raw[: nb.value] if want_blob else b"")
         if want_pcm:
             dt = _NP_OF_FMT[ofmt.value]
-            res["pcm"] = out.view(np.uint8)[: n_out.value * np.dtype(dt).itemsize].view(dt).copy()
+            res["pcm"] = out[: n_out.value * np.dtype(dt).itemsize].view(dt)
         return res
 
     def band_rms(self, pcm, rate, start_s, duration_s, lo_hz, hi_hz, channels=1):

@@ -117,6 +117,8 @@ class LocalComm:
     def gather_blobs(self, per_rank):
         return [b for b in per_rank if len(b)]
 
+    pinned_results = False
+
     def gather_pcm(self, per_rank):
         import numpy as np
         return np.concatenate([p for p in per_rank if p is not None and len(p)])
@@ -149,35 +151,51 @@ class DistComm:
     def gather_blobs(self, per_rank):
         return [b for b in allgather_blobs(per_rank[0], device=self.device) if len(b)]
 
+    pinned_results = True          # one chunk per pass and rank: it can stay in the context's pinned buffer until gathered
+
     def gather_pcm(self, per_rank):
-        """Ragged all-gather of every rank's owned samples, in rank (= stream) order; bytes on the wire (gloo has no
-        int16 collectives, and NCCL does not care)."""
+        """Ragged all-gather of every rank's owned samples, in rank (= stream) order: bytes on the wire (gloo has no
+        int16 collectives, NCCL does not care), one padded all-gather on the device, one device->host copy per part
+        straight into a pinned result."""
         import numpy as np
         a = np.ascontiguousarray(per_rank[0])
         if self.world == 1:
-            return a
+            return a.copy() if self.pinned_results else a
         raw = a.view(np.uint8).reshape(-1)
         n = torch.tensor([raw.size], dtype=torch.int64, device=self.device)
         sizes = [torch.zeros_like(n) for _ in range(self.world)]
         dist.all_gather(sizes, n)
-        cap = int(max(int(x[0]) for x in sizes))
-        buf = torch.zeros(cap, dtype=torch.uint8, device=self.device)
+        sizes = [int(x[0]) for x in sizes]
+        cap = max(max(sizes), 1)
+        buf = torch.empty(cap, dtype=torch.uint8, device=self.device)
         if raw.size:
-            buf[: raw.size] = torch.from_numpy(raw).to(buf.device)
-        parts = [torch.zeros_like(buf) for _ in range(self.world)]
-        dist.all_gather(parts, buf)
-        return np.concatenate([parts[r][: int(sizes[r][0])].cpu().numpy() for r in range(self.world)]).view(a.dtype)
+            buf[: raw.size].copy_(torch.from_numpy(raw), non_blocking=True)
+        allp = torch.empty(cap * self.world, dtype=torch.uint8, device=self.device)
+        dist.all_gather_into_tensor(allp, buf)
+        on_gpu = allp.is_cuda
+        res = torch.empty(sum(sizes), dtype=torch.uint8, pin_memory=on_gpu)
+        off = 0
+        for r in range(self.world):
+            res[off: off + sizes[r]].copy_(allp[r * cap: r * cap + sizes[r]], non_blocking=on_gpu)
+            off += sizes[r]
+        if on_gpu:
+            torch.cuda.synchronize(allp.device)
+        self._last_result = res            # keeps the pinned allocation alive as long as the caller may hold the view
+        return res.numpy().view(a.dtype)
 
 
-def run_graph_sharded(ctx, comm, spec, pcm, rate, channels=1, want_pcm=True, context=None):
+def run_graph_sharded(ctx, comm, spec, pcm, rate, channels=1, want_pcm=True, context=None, timings=None, tag="",
+                      want_meta=False):
     """One graph over one stream, one chunk per rank of `comm`.  Returns (sink pcm of the whole stream or None,
-    merged dict(meta, loudnorm, measurements)) on every rank."""
+    merged dict(meta, loudnorm, measurements)) on every rank; meta (the sink-frame records) only with want_meta."""
     from . import gpudsp
     total = pcm.size // channels
     unit = gpudsp.graph_chunk_unit(spec, rate)
     left, right = context if context else gpudsp.graph_chunk_context(spec, rate)
     chunks = plan_stream_chunks(total, unit, comm.world)
     n_exch = gpudsp.graph_exchanges(spec)
+    import time
+    t0 = time.perf_counter()
     ctx.set_exchange(comm.exchange, comm.world)
     comm.begin_pass()
     blobs, parts = [], []
@@ -193,36 +211,42 @@ def run_graph_sharded(ctx, comm, spec, pcm, rate, channels=1, want_pcm=True, con
             lo = max(0, first - left)
             hi = min(total, first + owned + right)
             res = ctx.graph_chunk(spec, pcm.reshape(-1)[lo * channels: hi * channels], rate, channels, lo, first, owned,
-                                  total, want_pcm=want_pcm)
+                                  total, want_pcm=want_pcm, pinned=comm.pinned_results)
             blobs.append(res["blob"])
             parts.append(res["pcm"])
     finally:
         ctx.set_exchange(None, 1)
+    t1 = time.perf_counter()
     fmt = gpudsp._FMT_OF_NP[pcm.dtype]
-    merged = gpudsp.graph_merge(spec, comm.gather_blobs(blobs), total, rate, channels, fmt)
+    merged = gpudsp.graph_merge(spec, comm.gather_blobs(blobs), total, rate, channels, fmt, want_meta=want_meta)
+    t2 = time.perf_counter()
     out = None
     if want_pcm:
         import numpy as np
         dt = next(p.dtype for p in parts if p is not None)
         out = comm.gather_pcm([p if p is not None else np.zeros(0, dtype=dt) for p in parts])
+    if timings is not None:
+        timings[tag + ":chunks"] = t1 - t0
+        timings[tag + ":blob_gather_merge"] = t2 - t1
+        timings[tag + ":pcm_gather"] = time.perf_counter() - t2
     return out, merged
 
 
 def process_stream_sharded(ctx, comm, pcm, rate, channels=1, pass2_spec=None,
-                           target_i=-16.0, target_tp=-1.0, target_lra=20.0):
+                           target_i=-16.0, target_tp=-1.0, target_lra=20.0, timings=None):
     """The four-pass chain (ProcessAudio, processor.go:78-216) of ONE stream over the ranks of `comm`: what
     jt_process_audio does on one GPU, with every pass cut into chunks.  Returns (int16 mono 44.1 kHz output,
     dict(filtered, final, pass3, pass4, plan, specs)) on every rank.  Pass 1 is analyse_stream_sharded."""
     from . import gpudsp
     spec2 = pass2_spec or gpudsp.default_pass2_spec()
-    out2, mg2 = run_graph_sharded(ctx, comm, spec2, pcm, rate, channels, want_pcm=True)
+    out2, mg2 = run_graph_sharded(ctx, comm, spec2, pcm, rate, channels, want_pcm=True, timings=timings, tag="pass2")
     filtered = mg2["measurements"]
     spec3, plan = gpudsp.build_pass3_spec(filtered.input_i, filtered.input_tp, target_i, target_tp, target_lra)
-    _, mg3 = run_graph_sharded(ctx, comm, spec3, out2, 44100, 1, want_pcm=False)
+    _, mg3 = run_graph_sharded(ctx, comm, spec3, out2, 44100, 1, want_pcm=False, timings=timings, tag="pass3")
     p3 = mg3["loudnorm"]
     if not (p3.input_i > -70.0):
         raise gpudsp.JtError(-1, f"cannot normalise silent audio (measured {p3.input_i:.1f} LUFS)")
     spec4, eff, off = gpudsp.build_pass4_spec(plan, p3, target_i, target_tp, target_lra, 44100)
-    out4, mg4 = run_graph_sharded(ctx, comm, spec4, out2, 44100, 1, want_pcm=True)
+    out4, mg4 = run_graph_sharded(ctx, comm, spec4, out2, 44100, 1, want_pcm=True, timings=timings, tag="pass4")
     return out4, dict(filtered=filtered, final=mg4["measurements"], pass3=p3, pass4=mg4["loudnorm"], plan=plan,
                       effective_target_i=eff, offset_db=off, specs=(spec2, spec3, spec4), pass2_pcm=out2)

@@ -90,7 +90,7 @@ def pass2_whole(ctx, stream48):
 def test_pass2_chunked_equals_whole_stream(ctx, stream48, pass2_whole, n_chunks):
     spec = gpudsp.default_pass2_spec()                       # afftdn tn=1: the noise-floor carry crosses every cut
     assert gpudsp.graph_exchanges(spec) == 1
-    out, mg = shard.run_graph_sharded(ctx, shard.LocalComm(n_chunks), spec, stream48, 48000)
+    out, mg = shard.run_graph_sharded(ctx, shard.LocalComm(n_chunks), spec, stream48, 48000, want_meta=True)
     pcm_same_s16(out, pass2_whole["pcm"])
     assert len(out) % 4096 == 0
     meta_same(mg["meta"], pass2_whole["meta"])
@@ -103,7 +103,7 @@ def test_pass2_chunked_96k_stereo(ctx):
     pcm = stereo_of(mono)
     spec = gpudsp.default_pass2_spec()
     whole = ctx.run_graph(spec, pcm, rate, channels=2)
-    out, mg = shard.run_graph_sharded(ctx, shard.LocalComm(3), spec, pcm, rate, channels=2)
+    out, mg = shard.run_graph_sharded(ctx, shard.LocalComm(3), spec, pcm, rate, channels=2, want_meta=True)
     pcm_same_s16(out, whole["pcm"])
     meta_same(mg["meta"], whole["meta"])
 
@@ -144,7 +144,7 @@ def test_pass4_chunked_equals_whole_stream(ctx, pass2_whole):
     spec4, _, _ = gpudsp.build_pass4_spec(plan, p3)
     whole = ctx.run_graph(spec4, x, 44100)
     assert whole["loudnorm"].normalization_type == 0
-    out, mg = shard.run_graph_sharded(ctx, shard.LocalComm(3), spec4, x, 44100)
+    out, mg = shard.run_graph_sharded(ctx, shard.LocalComm(3), spec4, x, 44100, want_meta=True)
     pcm_same_s16(out, whole["pcm"], frac_tol=2e-4)            # f64 stages on identical input: flips are rarer still
     meta_same(mg["meta"], whole["meta"])
     astats_same(mg["meta"], whole["meta"])
