@@ -240,6 +240,175 @@ int jt_build_pass4_spec(const jt_process_result *plan, const jt_loudnorm_stats *
 int jt_default_pass2_spec(char *buf, size_t cap);
 int jt_pass1_spec(char *buf, size_t cap);
 
+/* ---- Pass 1 -> Pass 2 host logic: voice-activity detector, region election, AdaptConfig, BuildFilterSpec --------
+ *   Pure host functions over the Pass-1 interval records; no device work, no jt_ctx.
+ * Durations are Go time.Duration values (int64 nanoseconds) so region arithmetic is exact. */
+typedef struct jt_region { int64_t start_ns, end_ns, duration_ns; } jt_region;   /* SpeechRegion / RoomToneRegion analyser.go:26-30,106-112 */
+
+typedef struct jt_region_sample {             /* RegionSample analyser.go:88-104 */
+    double rms_level, peak_level, crest_factor;
+    double spectral[JT_SP_COUNT];
+    double momentary_lufs, short_term_lufs, true_peak, sample_peak;
+} jt_region_sample;
+
+typedef struct jt_speech_candidate {          /* SpeechCandidateMetrics analyser.go:114-142 */
+    jt_region region;
+    jt_region_sample sample;
+    double voicing_density, body_band_rms, sib_band_rms, score;
+    int64_t original_start_ns, original_duration_ns;
+    int32_t bands_measured, was_refined;
+} jt_speech_candidate;
+
+#define JT_AFFTDN_BANDS 15                    /* afftdnBandCentresHz analyser_noise_bands.go:15-17 */
+typedef struct jt_noise_profile {             /* NoiseProfile analyser.go:49-81 */
+    int64_t start_ns, duration_ns;
+    double measured_noise_floor, peak_level, crest_factor, entropy;
+    double spectral[JT_SP_COUNT];
+    double band_noise[JT_AFFTDN_BANDS];
+    int32_t bands_measured, has_band_noise;
+    int32_t warning;                          /* 0 none, 1 short (< 8 s), 2 long (> 18 s): analyser_vad.go:590-594 */
+    int32_t reserved;
+} jt_noise_profile;
+
+enum { JT_FLOOR_ASTATS = 0, JT_FLOOR_RMS_ESTIMATE, JT_FLOOR_EBUR128_ESTIMATE, JT_FLOOR_VAD_PERCENTILE };
+
+/* What buildInputMeasurements + detectVoiceActivity + assignInputMeasurementSuggestions add to the Pass-1 result
+ * (NoiseMetrics / RegionMetrics, analyser.go:188-234; analyser.go:374-415; analyser_vad.go:728-783). */
+typedef struct jt_voice_activity {
+    double floor, floor_prescan, floor_astats, room_tone_detect_level, floored_fraction, reduction_headroom;
+    double split, margin;                     /* clamped Otsu split and hysteresis margin (the VAD log line) */
+    double voiced_low_percentile, noise_high_percentile, gate_separation_db;
+    int32_t floor_source, voice_activated, gap_tolerance, reserved;
+    int32_t has_noise_profile, has_room_tone_sample, has_speech_profile, speech_profile_index /* into candidates */;
+    int64_t n_speech_regions, n_candidates;
+    jt_region noise_region;                   /* elected (refined) low-cluster region */
+    jt_noise_profile noise_profile;
+    jt_region_sample room_tone_sample;        /* ElectedRoomToneSample */
+    jt_speech_candidate speech_profile;       /* copy of the elected candidate */
+} jt_voice_activity;
+
+/* buildInputMeasurements' noise seed (analyser.go:374-415, analyser_noise_seed.go:150-223) followed by
+ * detectVoiceActivity (analyser_vad.go:728-783) and assignInputMeasurementSuggestions (analyser.go:515-531).
+ * target_i is config.Loudnorm.TargetI (unused by the detector; kept for the reference's signature).
+ * speech_regions / candidates may be NULL (then only the counts are returned); JT_ERR_BUFFER when a cap is short. */
+int jt_detect_voice_activity(const jt_measurements *m, const jt_interval *intervals, int64_t n_intervals,
+                             jt_voice_activity *out,
+                             jt_region *speech_regions, int64_t regions_cap,
+                             jt_speech_candidate *candidates, int64_t candidates_cap);
+
+/* measureSpeechBands / measureNoiseBands results (analyser_bands.go:106-167, analyser_noise_bands.go:62-119) written
+ * onto the elected profiles.  rms[0..1] = body (1-3 kHz) and sibilant (6-9 kHz) band over the speech region,
+ * rms[2..16] = the 15 afftdn bands over the room-tone region; found[i] as jt_band_rms reports it.  Either half may
+ * be skipped by passing NULL. */
+int jt_apply_band_rms(jt_voice_activity *va, const double *speech_rms, const int32_t *speech_found,
+                      const double *noise_rms, const int32_t *noise_found);
+/* the 17 band edges in that order (speechBandPlan analyser_bands.go:98-103, afftdnBandEdgesHz analyser_noise_bands.go:34-52) */
+void jt_band_plan(double lo_hz[17], double hi_hz[17]);
+
+/* ---- EffectiveFilterConfig (filters.go:111-255,349) ---- */
+enum { JT_FILTER_DOWNMIX = 1, JT_FILTER_ANALYSIS, JT_FILTER_RESAMPLE, JT_FILTER_RUMBLE_HIGHPASS, JT_FILTER_BANDLIMIT_LOWPASS,
+       JT_FILTER_SPEECH_GATE, JT_FILTER_NOISE_REDUCTION, JT_FILTER_LEVELLING_COMPRESSOR, JT_FILTER_DEESSER };
+typedef struct jt_biquad_config { int32_t enabled, poles; double frequency, width, mix; char transform[8]; } jt_biquad_config;
+typedef struct jt_filter_config {
+    int32_t downmix_enabled, analysis_enabled;
+    int32_t resample_enabled, resample_rate, resample_frame_size, reserved0;
+    char    resample_format[8];
+    jt_biquad_config rumble_highpass, bandlimit_lowpass;
+    struct { int32_t enabled, afftdn_enabled, afftdn_track_noise, reserved;
+             double strength, patch_s, research_s, smooth, afftdn_noise_reduction, afftdn_noise_floor;
+             char afftdn_noise_type[8]; char afftdn_band_noise[136]; } noise_reduction;
+    struct { int32_t enabled, reserved; double threshold /* linear */, ratio, attack, release, range /* linear */, knee, makeup;
+             char detection[8]; } speech_gate;
+    struct { int32_t enabled, reserved; double threshold /* dB */, ratio, attack, release, makeup /* dB */, knee, mix; } levelling_compressor;
+    struct { int32_t enabled, reserved; double intensity, amount, frequency; } deesser;
+    struct { int32_t enabled, reserved; double threshold, window, overlap; char method[8]; } adeclick;
+    struct { int32_t enabled, dual_mono, linear, reserved; double target_i, target_tp, target_lra; } loudnorm;
+    int32_t n_filter_order;                   /* 0 = Pass2FilterOrder (filters.go:58-68) */
+    int32_t filter_order[12];                 /* JT_FILTER_* */
+    int32_t reserved1;
+} jt_filter_config;
+
+typedef struct jt_adapt_diagnostics {         /* AdaptiveDiagnostics filters.go:275-313 */
+    char   bandlimit_lp_reason[40];
+    double speech_gate_dynamic_range, speech_gate_quiet_speech_estimate, speech_gate_speech_separation,
+           speech_gate_speech_headroom, speech_gate_threshold_unclamped, speech_gate_depth_db;
+    char   speech_gate_clamp_reason[16];
+    int32_t speech_gate_narrow_gap, afftdn_enabled;
+    double afftdn_noise_floor_db;
+    char   afftdn_disable_reason[24];
+    char   afftdn_noise_type[8];
+} jt_adapt_diagnostics;
+
+void jt_default_filter_config(jt_filter_config *cfg);                 /* DefaultFilterConfig filters.go:353-355, 421-532 */
+/* AdaptConfig (adaptive.go:13-40): base may be NULL (defaults); diag may be NULL. */
+int jt_adapt_config(const jt_filter_config *base, const jt_measurements *m, const jt_voice_activity *va,
+                    jt_filter_config *out, jt_adapt_diagnostics *diag);
+/* BuildFilterSpec (filters.go:968-989) and the single-filter builders it calls (filters.go:607-960);
+ * jt_build_filter(cfg, JT_FILTER_*, ...) renders one of them ("" when the filter is disabled). */
+int jt_build_filter_spec(const jt_filter_config *cfg, char *buf, size_t cap);
+int jt_build_filter(const jt_filter_config *cfg, int filter_id, char *buf, size_t cap);
+int jt_build_adeclick_filter(const jt_filter_config *cfg, char *buf, size_t cap);     /* buildAdeclickFilter filters.go:940-956 */
+/* fmt.Sprintf("%g", v) as Go renders it (shortest round-trip digits) -- afftdn nr / nf in the spec (filters.go:806-826) */
+int jt_go_format_g(double v, char *buf, size_t cap);
+
+/* The detector's unit-tested stages (analyser_vad.go, analyser_candidates_*.go, analyser_noise_seed.go), exported so the
+ * parity tests can replay the reference's own table-driven cases.  axis: 0 = momentary LUFS, 1 = RMS. */
+int     jt_vad_detect(const jt_interval *intervals, int64_t n_intervals, double noise_floor_seed, jt_voice_activity *out,
+                      jt_region *speech_regions, int64_t regions_cap, jt_speech_candidate *candidates, int64_t candidates_cap);  /* detectVoiceActivity with a given seed */
+int64_t jt_vad_intervals_for_duration(int64_t d_ns, int64_t hop_ns);
+int     jt_vad_histogram(const jt_interval *iv, int64_t n, int axis, double bin_width,
+                         int32_t *bins, int64_t bins_cap, int64_t *n_bins, double *min_level, double *max_level, int64_t *count);
+double  jt_vad_otsu_split(const int32_t *bins, int64_t n_bins, double bin_width, double min_level, double max_level);
+double  jt_vad_hysteresis_margin(const int32_t *bins, int64_t n_bins, double bin_width, double min_level, double split);
+double  jt_vad_percentile_of_sorted(const double *sorted, int64_t n, double pct);
+double  jt_vad_percentile_floor(const double *sorted_levels, int64_t n, double seed);
+double  jt_vad_clamp_split(double split, double noise_floor, double p75);
+double  jt_vad_floored_fraction(const jt_interval *iv, int64_t n, int axis);
+int     jt_vad_is_speech_interval(const jt_interval *iv, double split, int axis);
+int     jt_vad_gap_tolerance(const uint8_t *flags, int64_t n, int64_t hop_ns);
+int64_t jt_vad_build_speech_runs(const jt_interval *iv, int64_t n, double split, double margin, int tol, int axis, int64_t hop_ns,
+                                 jt_region *runs, int64_t runs_cap);
+int     jt_vad_pick_low_cluster_region(const jt_interval *iv, int64_t n, double split, int axis, int64_t hop_ns, jt_region *out);
+int     jt_vad_gate_statistics(const jt_interval *iv, int64_t n, double split, int axis, const jt_region *speech_region /* or NULL */,
+                               double *voiced_low, double *noise_high, double *separation);
+int     jt_vad_estimate_noise_floor(const jt_interval *iv, int64_t n, double *noise_floor, double *silence_threshold);   /* 1 = ok */
+int     jt_vad_noise_profile(const jt_interval *iv, int64_t n, const jt_region *region, jt_noise_profile *out);          /* 1 = profile */
+int64_t jt_vad_intervals_in_range(const jt_interval *iv, int64_t n, int64_t start_ns, int64_t end_ns, int64_t *first);
+double  jt_vad_score_interval_window(const jt_interval *iv, int64_t n);
+double  jt_vad_score_speech_window(const jt_interval *iv, int64_t n);
+double  jt_vad_level_variance(const jt_interval *iv, int64_t n, int axis);
+double  jt_vad_score_candidate_grounded(const jt_speech_candidate *c, double noise_floor_db, double level_var);
+int     jt_vad_measure_candidate(const jt_interval *iv, int64_t n, const jt_region *region, jt_speech_candidate *out);    /* 1 = measured */
+int     jt_vad_refine_speech_region(const jt_interval *iv, int64_t n, const jt_region *candidate, jt_region *out);
+/* findBestSpeechRegion (analyser_candidates_speech.go:222-326): noise_floor_db = NoiseProfile.MeasuredNoiseFloor, or
+ * -INFINITY when there is no profile; returns 1 and *best when a region is elected */
+int     jt_vad_find_best_speech_region(const jt_interval *iv, int64_t n, const jt_region *regions, int64_t n_regions,
+                                       double noise_floor_db, jt_region *best, jt_speech_candidate *candidates, int64_t cap, int64_t *n_candidates);
+double  jt_adapt_gate_threshold(double voiced_low_percentile, double separation, int *narrow_gap);    /* calculateSpeechGateThreshold */
+double  jt_adapt_gate_threshold_no_profile(double floor, double room_tone_peak, double room_tone_crest, double ratio, double lufs_gap);
+int     jt_adapt_band_noise(const double *bands, int n, char *buf, size_t cap);                      /* buildAfftdnBandNoise */
+
+/* ---- S2 / S1 with the adaptive path on the library side ------------------------------------------------------------
+ * jt_analyse_adaptive = AnalyseAudio + AdaptConfig (analyser.go:325-372, processor.go:37-69): Pass 1, the detector, the
+ * 17 band RMS graphs over the elected regions (one launch), AdaptConfig and BuildFilterSpec.
+ * jt_process_audio_adaptive = ProcessAudio (processor.go:78-216) with that analysis feeding Pass 2. */
+typedef struct jt_analysis {
+    jt_measurements measurements;
+    jt_voice_activity voice_activity;
+    jt_filter_config config;
+    jt_adapt_diagnostics diagnostics;
+    char pass2_spec[2048];
+} jt_analysis;
+int jt_analyse_adaptive(jt_ctx *ctx, const void *pcm_in, int64_t n_frames, int sample_rate, int channels, int sample_fmt,
+                        int frame_size, const jt_filter_config *base,
+                        jt_analysis *out, jt_interval *intervals, int64_t interval_cap, int64_t *n_intervals);
+int jt_process_audio_adaptive(jt_ctx *ctx, const void *pcm_in, int64_t n_frames, int sample_rate, int channels, int sample_fmt,
+                        const jt_filter_config *base, int16_t *pcm_out, int64_t pcm_out_cap,
+                        jt_process_result *res, jt_analysis *analysis);
+int jt_process_audio_adaptive_dev(jt_ctx *ctx, const void *d_pcm_in, int64_t n_frames, int sample_rate, int channels, int sample_fmt,
+                        const jt_filter_config *base, int16_t *d_pcm_out, int64_t pcm_out_cap,
+                        jt_process_result *res, jt_analysis *analysis);
+
 /* the cudaStream_t (as void *) every kernel and copy of this context is issued on, so a caller can order its own
  * device work against it or bracket calls with CUDA events */
 void   *jt_cuda_stream(const jt_ctx *ctx);

@@ -1010,10 +1010,12 @@ extern "C" int jt_build_pass4_spec(const jt_process_result *plan, const jt_loudn
 // Pass 4 from Pass 3's loudnorm measurement), so the host-side assembly of one pass's metadata runs while the
 // GPU is already working on the next pass: graphs are enqueued (jt_graph_enqueue) ahead of being finished.
 static void process_device(jt_ctx *c, const void *d_in, int64_t n_frames, int rate, int channels, int fmt, const char *pass2_spec,
-                           int16_t *pcm_out, bool out_on_device, int64_t cap, jt_process_result *res)
+                           int16_t *pcm_out, bool out_on_device, int64_t cap, jt_process_result *res,
+                           const jt_measurements *pass1_done = nullptr, const jt_filter_config *cfg = nullptr)
 {
     jt_process_result R; memset(&R, 0, sizeof(R));
-    const double tI = -16.0, tTP = -1.0, tLRA = 20.0;          // defaultLoudnormConfig, filters.go:523-532
+    // defaultLoudnormConfig, filters.go:523-532 (or the caller's base config on the adaptive path)
+    const double tI = cfg ? cfg->loudnorm.target_i : -16.0, tTP = cfg ? cfg->loudnorm.target_tp : -1.0, tLRA = cfg ? cfg->loudnorm.target_lra : 20.0;
     const size_t mark = c->allocs.size();
     // Pass 1 and Pass 2: device work.  Both read the input only (Pass 2's spec comes from the caller), so Pass 2's
     // long kernels go first and the integer bookkeeping of Pass 1's 200 000 frames happens behind them
@@ -1024,8 +1026,10 @@ static void process_device(jt_ctx *c, const void *d_in, int64_t n_frames, int ra
     jt_check_cancel(c);
     const size_t mark1 = c->allocs.size();
     AnalysePending p1;
-    analyse_enqueue(c, d_in, n_frames, rate, channels, fmt, 4096, p1);
-    jt_release_since(c, mark1, nullptr);
+    if (!pass1_done) {
+        analyse_enqueue(c, d_in, n_frames, rate, channels, fmt, 4096, p1);
+        jt_release_since(c, mark1, nullptr);
+    }
     // Pass 3 is planned from Pass 2's integrated loudness and true peak as the sink frames report them
     // (last-seen values of lavfi.r128.I / true_peak, "%.3f": analyser_metrics.go:898-923)
     double out_i = 0.0, out_tp = 0.0;
@@ -1044,7 +1048,7 @@ static void process_device(jt_ctx *c, const void *d_in, int64_t n_frames, int ra
     jt_graph_enqueue(c, spec3, g2.out.d, g2.out.n, 44100, 1, JT_FMT_S16, 4096, false, false, g3);
     jt_release_since(c, mark3, nullptr);
     // Pass 1: host part, while the GPU runs Pass 1 and Pass 3
-    analyse_finish(c, p1, &R.input, nullptr, 0, nullptr);
+    if (pass1_done) R.input = *pass1_done; else analyse_finish(c, p1, &R.input, nullptr, 0, nullptr);
     jt_check_cancel(c);
     // Pass 3's four numbers gate everything that follows: wait for them first (the GPU is still busy with Pass 2's
     // analysis tail and Pass 3 itself), so Pass 4 can be enqueued before any other host work
@@ -1101,5 +1105,92 @@ extern "C" int jt_process_audio_dev(jt_ctx *c, const void *d_in, int64_t n_frame
     return guarded(c, [&]() {
         if (!d_in && n_frames > 0) JT_THROW(JT_ERR_INVALID_ARG, "null input");
         process_device(c, d_in, n_frames, rate, channels, fmt, pass2_spec, d_out, true, cap, res);
+    });
+}
+
+// ---------------------------------------------------------------------------------------
+// The adaptive path on the library side: AnalyseAudio + AdaptConfig (analyser.go:325-372, processor.go:37-69) and
+// ProcessAudio with the adapted Pass-2 spec (processor.go:78-216).  Pass 2 depends on Pass 1 through the detector,
+// so the two cannot overlap here as they do in process_device with a caller-supplied spec.
+// ---------------------------------------------------------------------------------------
+static void analyse_adaptive_device(jt_ctx *c, const void *d_in, int64_t n_frames, int rate, int channels, int fmt, int F,
+                                    const jt_filter_config *base, jt_analysis *out, jt_interval *iv_out, int64_t iv_cap, int64_t *n_iv_out)
+{
+    if (!out) JT_THROW(JT_ERR_INVALID_ARG, "null analysis");
+    memset(out, 0, sizeof(*out));
+    const size_t mark = c->allocs.size();
+    std::vector<jt_interval> own;
+    jt_interval *iv = iv_out; int64_t cap = iv_cap;
+    if (!iv) { cap = (int64_t)((double)n_frames / rate / 0.25) + 16; own.resize((size_t)cap); iv = own.data(); }
+    int64_t n_iv = 0;
+    analyse_device(c, d_in, n_frames, rate, channels, fmt, F, &out->measurements, iv, cap, &n_iv);
+    if (n_iv_out) *n_iv_out = n_iv;
+    if (out->measurements.sink_frames == 0 || std::isnan(out->measurements.input_i))
+        JT_THROW(JT_ERR_INVALID_ARG, "ebur128 measurements not found in metadata (analyser.go:397-399)");
+    int rc = jt_detect_voice_activity(&out->measurements, iv, n_iv, &out->voice_activity, nullptr, 0, nullptr, 0);
+    if (rc) JT_THROW(rc, "voice-activity detector");
+    jt_voice_activity &va = out->voice_activity;
+    // measureSpeechBands + measureNoiseBands: the 2 + 15 band graphs of analyser_bands.go:33 over the elected regions
+    double lo[17], hi[17]; jt_band_plan(lo, hi);
+    const bool want_speech = va.has_speech_profile && va.speech_profile.region.duration_ns > 0;
+    const bool want_noise = va.has_noise_profile && va.noise_profile.duration_ns > 0;
+    if (want_speech || want_noise) {
+        Sig mono = jt_downmix(c, d_in, n_frames, channels, fmt, rate);
+        auto region = [&](int64_t start_ns, int64_t dur_ns) {
+            // atrim=start=%f:duration=%f (analyser_bands.go:54-60): seconds printed with six decimals
+            const double st = jt_wire("%f", (double)(start_ns / 1000000000LL) + (double)(start_ns % 1000000000LL) / 1e9);
+            const double du = jt_wire("%f", (double)(dur_ns / 1000000000LL) + (double)(dur_ns % 1000000000LL) / 1e9);
+            const int64_t st_us = llround(st * 1e6), du_us = llround(du * 1e6);
+            const int64_t s0 = (st_us * rate + 500000) / 1000000, len = (du_us * rate + 500000) / 1000000;
+            return jt_slice(mono, s0, len);
+        };
+        double rms[17] = {0}; int32_t found[17] = {0};
+        if (want_speech) { Sig r = region(va.speech_profile.region.start_ns, va.speech_profile.region.duration_ns); jt_band_rms_batch(c, r, lo, hi, 2, rms, found); }
+        if (want_noise) { Sig r = region(va.noise_profile.start_ns, va.noise_profile.duration_ns); jt_band_rms_batch(c, r, lo + 2, hi + 2, 15, rms + 2, found + 2); }
+        jt_apply_band_rms(&va, want_speech ? rms : nullptr, want_speech ? found : nullptr, want_noise ? rms + 2 : nullptr, want_noise ? found + 2 : nullptr);
+    }
+    rc = jt_adapt_config(base, &out->measurements, &va, &out->config, &out->diagnostics);
+    if (rc) JT_THROW(rc, "AdaptConfig");
+    rc = jt_build_filter_spec(&out->config, out->pass2_spec, sizeof(out->pass2_spec));
+    if (rc) JT_THROW(rc, "BuildFilterSpec");
+    jt_release_since(c, mark, nullptr);
+}
+
+extern "C" int jt_analyse_adaptive(jt_ctx *c, const void *pcm_in, int64_t n_frames, int rate, int channels, int fmt, int frame_size,
+                                   const jt_filter_config *base, jt_analysis *out, jt_interval *iv, int64_t iv_cap, int64_t *n_iv)
+{
+    return guarded(c, [&]() {
+        if (!pcm_in && n_frames > 0) JT_THROW(JT_ERR_INVALID_ARG, "null input");
+        if (fmt != JT_FMT_S16 && fmt != JT_FMT_FLT && fmt != JT_FMT_DBL) JT_THROW(JT_ERR_UNSUPPORTED, "input sample format %d", fmt);
+        const void *d_in = upload(c, pcm_in, (size_t)n_frames * channels * jt_fmt_bytes(fmt));
+        analyse_adaptive_device(c, d_in, n_frames, rate, channels, fmt, frame_size, base, out, iv, iv_cap, n_iv);
+    });
+}
+
+static void process_adaptive_device(jt_ctx *c, const void *d_in, int64_t n_frames, int rate, int channels, int fmt, const jt_filter_config *base,
+                                    int16_t *pcm_out, bool out_on_device, int64_t cap, jt_process_result *res, jt_analysis *analysis)
+{
+    std::vector<jt_analysis> own(analysis ? 0 : 1);
+    jt_analysis *an = analysis ? analysis : own.data();
+    analyse_adaptive_device(c, d_in, n_frames, rate, channels, fmt, 4096, base, an, nullptr, 0, nullptr);
+    jt_check_cancel(c);
+    process_device(c, d_in, n_frames, rate, channels, fmt, an->pass2_spec, pcm_out, out_on_device, cap, res, &an->measurements, &an->config);
+}
+extern "C" int jt_process_audio_adaptive(jt_ctx *c, const void *pcm_in, int64_t n_frames, int rate, int channels, int fmt,
+                                         const jt_filter_config *base, int16_t *pcm_out, int64_t cap, jt_process_result *res, jt_analysis *analysis)
+{
+    return guarded(c, [&]() {
+        if (!pcm_in && n_frames > 0) JT_THROW(JT_ERR_INVALID_ARG, "null input");
+        if (fmt != JT_FMT_S16 && fmt != JT_FMT_FLT && fmt != JT_FMT_DBL) JT_THROW(JT_ERR_UNSUPPORTED, "input sample format %d", fmt);
+        const void *d_in = upload(c, pcm_in, (size_t)n_frames * channels * jt_fmt_bytes(fmt));
+        process_adaptive_device(c, d_in, n_frames, rate, channels, fmt, base, pcm_out, false, cap, res, analysis);
+    });
+}
+extern "C" int jt_process_audio_adaptive_dev(jt_ctx *c, const void *d_in, int64_t n_frames, int rate, int channels, int fmt,
+                                         const jt_filter_config *base, int16_t *d_out, int64_t cap, jt_process_result *res, jt_analysis *analysis)
+{
+    return guarded(c, [&]() {
+        if (!d_in && n_frames > 0) JT_THROW(JT_ERR_INVALID_ARG, "null input");
+        process_adaptive_device(c, d_in, n_frames, rate, channels, fmt, base, d_out, true, cap, res, analysis);
     });
 }

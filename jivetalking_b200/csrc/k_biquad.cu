@@ -13,6 +13,9 @@
 BiquadCoef jt_biquad_design(bool highpass, double freq, double q, int rate, bool normalize)
 {
     const double w0 = 2 * M_PI * freq / rate;
+    // af_biquads.c config_filter(): a corner at or past Nyquist (or a non-positive width) puts the filter in bypass
+    // ("Invalid frequency and/or width!") -- the top afftdn band (analyser_noise_bands.go:15-17) at 44.1 / 48 kHz
+    if (w0 > M_PI || w0 <= 0.0 || q <= 0.0) return BiquadCoef{1.0, 0.0, 0.0, 0.0, 0.0};
     const double alpha = sin(w0) / (2 * q);
     double a0 = 1 + alpha, a1 = -2 * cos(w0), a2 = 1 - alpha, b0, b1, b2;
     if (highpass) { b0 = (1 + cos(w0)) / 2; b1 = -(1 + cos(w0)); b2 = (1 + cos(w0)) / 2; }

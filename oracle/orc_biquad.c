@@ -14,6 +14,8 @@
 void orc_biquad_design(int highpass, double freq, double q, int rate, int normalize, double *c /* b0 b1 b2 a1 a2 */)
 {
     double w0 = 2 * M_PI * freq / rate;
+    /* config_filter(): s->bypass when w0 > pi, w0 <= 0 or width <= 0 -- frames pass through untouched */
+    if (w0 > M_PI || w0 <= 0.0 || q <= 0.0) { c[0] = 1; c[1] = c[2] = c[3] = c[4] = 0; return; }
     double alpha = sin(w0) / (2 * q);
     double a0 = 1 + alpha, a1 = -2 * cos(w0), a2 = 1 - alpha, b0, b1, b2;
     if (highpass) { b0 = (1 + cos(w0)) / 2; b1 = -(1 + cos(w0)); b2 = (1 + cos(w0)) / 2; }
