@@ -265,7 +265,7 @@ typedef struct jt_noise_profile {             /* NoiseProfile analyser.go:49-81 
     double measured_noise_floor, peak_level, crest_factor, entropy;
     double spectral[JT_SP_COUNT];
     double band_noise[JT_AFFTDN_BANDS];
-    int32_t bands_measured, has_band_noise;
+    int32_t bands_measured, n_band_noise;     /* len(BandNoise): 0 until measured, then 15 */
     int32_t warning;                          /* 0 none, 1 short (< 8 s), 2 long (> 18 s): analyser_vad.go:590-594 */
     int32_t reserved;
 } jt_noise_profile;
@@ -343,6 +343,7 @@ void jt_default_filter_config(jt_filter_config *cfg);                 /* Default
 /* AdaptConfig (adaptive.go:13-40): base may be NULL (defaults); diag may be NULL. */
 int jt_adapt_config(const jt_filter_config *base, const jt_measurements *m, const jt_voice_activity *va,
                     jt_filter_config *out, jt_adapt_diagnostics *diag);
+void jt_sanitize_config(jt_filter_config *cfg);                       /* sanitizeConfig adaptive.go:175-232 */
 /* BuildFilterSpec (filters.go:968-989) and the single-filter builders it calls (filters.go:607-960);
  * jt_build_filter(cfg, JT_FILTER_*, ...) renders one of them ("" when the filter is disabled). */
 int jt_build_filter_spec(const jt_filter_config *cfg, char *buf, size_t cap);

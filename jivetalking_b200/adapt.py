@@ -49,7 +49,7 @@ class SpeechCandidate(C.Structure):
 class NoiseProfile(C.Structure):
     _fields_ = [("start_ns", _I64), ("duration_ns", _I64), ("measured_noise_floor", _D), ("peak_level", _D),
                 ("crest_factor", _D), ("entropy", _D), ("spectral", _D * SP_COUNT), ("band_noise", _D * AFFTDN_BANDS),
-                ("bands_measured", _I32), ("has_band_noise", _I32), ("warning", _I32), ("reserved", _I32)]
+                ("bands_measured", _I32), ("n_band_noise", _I32), ("warning", _I32), ("reserved", _I32)]
 
 
 class VoiceActivity(C.Structure):
@@ -146,6 +146,8 @@ def _L():
     L.jt_default_filter_config.restype = None
     L.jt_adapt_config.argtypes = [C.POINTER(FilterConfig), C.POINTER(Measurements), C.POINTER(VoiceActivity),
                                   C.POINTER(FilterConfig), C.POINTER(AdaptDiagnostics)]
+    L.jt_sanitize_config.argtypes = [C.POINTER(FilterConfig)]
+    L.jt_sanitize_config.restype = None
     L.jt_build_filter_spec.argtypes = [C.POINTER(FilterConfig), C.c_char_p, C.c_size_t]
     L.jt_build_filter.argtypes = [C.POINTER(FilterConfig), _INT, C.c_char_p, C.c_size_t]
     L.jt_build_adeclick_filter.argtypes = [C.POINTER(FilterConfig), C.c_char_p, C.c_size_t]
@@ -446,6 +448,11 @@ def adapt_config(measurements, va, base=None):
     _check(_L().jt_adapt_config(C.byref(base) if base is not None else None, C.byref(measurements), C.byref(va),
                                 C.byref(out), C.byref(diag)))
     return out, diag
+
+
+def sanitize_config(cfg):
+    _L().jt_sanitize_config(C.byref(cfg))
+    return cfg
 
 
 def _str_call(fn, *args):

@@ -639,9 +639,31 @@ Meas go_meas(const jt_measurements *m)
     // Dynamics.* stay at Go's zero value unless astats reported (assignAstatsMeasurements analyser.go:417-443)
     Meas g; g.input_i = m->input_i; g.input_lra = m->input_lra;
     const bool found = !std::isnan(m->astats[JT_AS_Dynamic_range]);
-    g.rms_level = found && !std::isnan(m->astats[JT_AS_RMS_level]) ? m->astats[JT_AS_RMS_level] : 0.0;
-    g.peak_level = found && !std::isnan(m->astats[JT_AS_Peak_level]) ? m->astats[JT_AS_Peak_level] : 0.0;
+    // (astats writes all its keys or none, so a NaN next to a reported Dynamic_range is a parsed "nan", not an absent key)
+    g.rms_level = found ? m->astats[JT_AS_RMS_level] : 0.0;
+    g.peak_level = found ? m->astats[JT_AS_Peak_level] : 0.0;
     return g;
+}
+
+// sanitizeConfig (adaptive.go:175-232)
+void sanitize_config(jt_filter_config &c)
+{
+    auto &nr = c.noise_reduction; auto &gt = c.speech_gate; auto &k = c.levelling_compressor;
+    jt_filter_config def; defaults(def);
+    auto san_bq = [](jt_biquad_config &b, double f) { b.frequency = sanitize(b.frequency, f); b.width = sanitize(b.width, 0.707); b.mix = sanitize(b.mix, 1.0); };
+    san_bq(c.rumble_highpass, 80.0); san_bq(c.bandlimit_lowpass, 20500.0);
+    nr.strength = sanitize(nr.strength, def.noise_reduction.strength); nr.patch_s = sanitize(nr.patch_s, def.noise_reduction.patch_s);
+    nr.research_s = sanitize(nr.research_s, def.noise_reduction.research_s); nr.smooth = sanitize(nr.smooth, def.noise_reduction.smooth);
+    nr.afftdn_noise_reduction = sanitize(nr.afftdn_noise_reduction, def.noise_reduction.afftdn_noise_reduction);
+    nr.afftdn_noise_floor = sanitize(nr.afftdn_noise_floor, def.noise_reduction.afftdn_noise_floor);
+    if (!strcmp(nr.afftdn_noise_type, "custom") && !nr.afftdn_band_noise[0]) set_str(nr.afftdn_noise_type, sizeof(nr.afftdn_noise_type), "w");
+    if (!is_finite(gt.threshold) || gt.threshold <= 0) gt.threshold = 0.01;
+    gt.ratio = sanitize(gt.ratio, def.speech_gate.ratio); gt.attack = sanitize(gt.attack, def.speech_gate.attack);
+    gt.release = sanitize(gt.release, def.speech_gate.release); gt.range = sanitize(gt.range, def.speech_gate.range);
+    gt.knee = sanitize(gt.knee, def.speech_gate.knee); gt.makeup = sanitize(gt.makeup, def.speech_gate.makeup);
+    k.ratio = sanitize(k.ratio, 3.0); k.threshold = sanitize(k.threshold, -18.0); k.attack = sanitize(k.attack, 10); k.release = sanitize(k.release, 200);
+    k.makeup = sanitize(k.makeup, 0); k.knee = sanitize(k.knee, 4.0); k.mix = sanitize(k.mix, 1.0);
+    c.deesser.intensity = sanitize(c.deesser.intensity, 0.0); c.deesser.amount = sanitize(c.deesser.amount, 0.50); c.deesser.frequency = sanitize(c.deesser.frequency, 0.80);
 }
 
 void adapt(const jt_filter_config &base, const jt_measurements *m, const jt_voice_activity *va, jt_filter_config &c, jt_adapt_diagnostics &d)
@@ -664,7 +686,7 @@ void adapt(const jt_filter_config &base, const jt_measurements *m, const jt_voic
             const bool custom = va->has_noise_profile && va->noise_profile.bands_measured && !(va->gate_separation_db < 12.0) &&
                                 va->noise_profile.spectral[JT_SP_flatness] >= 0.45;             // useCustomAfftdnProfile adaptive.go:117-126
             if (custom) {
-                const std::string bn = band_noise(va->noise_profile.band_noise, va->noise_profile.has_band_noise ? JT_AFFTDN_BANDS : 0);
+                const std::string bn = band_noise(va->noise_profile.band_noise, std::min<int>(va->noise_profile.n_band_noise, JT_AFFTDN_BANDS));
                 if (!bn.empty()) { set_str(nr.afftdn_noise_type, sizeof(nr.afftdn_noise_type), "custom"); set_str(nr.afftdn_band_noise, sizeof(nr.afftdn_band_noise), bn.c_str()); }
             }
             set_str(d.afftdn_noise_type, sizeof(d.afftdn_noise_type), nr.afftdn_noise_type);
@@ -709,22 +731,7 @@ void adapt(const jt_filter_config &base, const jt_measurements *m, const jt_voic
         k.threshold = gomax(-45.0, gomin(rms + 9.0, -6.0));
     } else if (!is_finite(g.peak_level)) k.threshold = -18.0;
     else k.threshold = gomax(-45.0, gomin(g.peak_level - 20.0, -6.0));
-    // sanitizeConfig (adaptive.go:175-232)
-    jt_filter_config def; defaults(def);
-    auto san_bq = [](jt_biquad_config &b, double f) { b.frequency = sanitize(b.frequency, f); b.width = sanitize(b.width, 0.707); b.mix = sanitize(b.mix, 1.0); };
-    san_bq(c.rumble_highpass, 80.0); san_bq(c.bandlimit_lowpass, 20500.0);
-    nr.strength = sanitize(nr.strength, def.noise_reduction.strength); nr.patch_s = sanitize(nr.patch_s, def.noise_reduction.patch_s);
-    nr.research_s = sanitize(nr.research_s, def.noise_reduction.research_s); nr.smooth = sanitize(nr.smooth, def.noise_reduction.smooth);
-    nr.afftdn_noise_reduction = sanitize(nr.afftdn_noise_reduction, def.noise_reduction.afftdn_noise_reduction);
-    nr.afftdn_noise_floor = sanitize(nr.afftdn_noise_floor, def.noise_reduction.afftdn_noise_floor);
-    if (!strcmp(nr.afftdn_noise_type, "custom") && !nr.afftdn_band_noise[0]) set_str(nr.afftdn_noise_type, sizeof(nr.afftdn_noise_type), "w");
-    if (!is_finite(gt.threshold) || gt.threshold <= 0) gt.threshold = 0.01;
-    gt.ratio = sanitize(gt.ratio, def.speech_gate.ratio); gt.attack = sanitize(gt.attack, def.speech_gate.attack);
-    gt.release = sanitize(gt.release, def.speech_gate.release); gt.range = sanitize(gt.range, def.speech_gate.range);
-    gt.knee = sanitize(gt.knee, def.speech_gate.knee); gt.makeup = sanitize(gt.makeup, def.speech_gate.makeup);
-    k.ratio = sanitize(k.ratio, 3.0); k.threshold = sanitize(k.threshold, -18.0); k.attack = sanitize(k.attack, 10); k.release = sanitize(k.release, 200);
-    k.makeup = sanitize(k.makeup, 0); k.knee = sanitize(k.knee, 4.0); k.mix = sanitize(k.mix, 1.0);
-    c.deesser.intensity = sanitize(c.deesser.intensity, 0.0); c.deesser.amount = sanitize(c.deesser.amount, 0.50); c.deesser.frequency = sanitize(c.deesser.frequency, 0.80);
+    sanitize_config(c);
 }
 
 }  // namespace
@@ -835,7 +842,7 @@ extern "C" int jt_apply_band_rms(jt_voice_activity *va, const double *srms, cons
             va->noise_profile.band_noise[i] = nfound[i] ? nrms[i] : 0.0;       // an unmeasured band keeps Go's zero value
             if (nfound[i] && is_finite(nrms[i])) fin++;
         }
-        va->noise_profile.has_band_noise = 1;
+        va->noise_profile.n_band_noise = JT_AFFTDN_BANDS;
         va->noise_profile.bands_measured = fin >= 10;
     }
     return JT_OK;
@@ -852,6 +859,7 @@ extern "C" int jt_adapt_config(const jt_filter_config *base, const jt_measuremen
     *out = c; if (diag) *diag = d;
     return JT_OK;
 }
+extern "C" void jt_sanitize_config(jt_filter_config *c) { if (c) sanitize_config(*c); }
 extern "C" int jt_build_filter_spec(const jt_filter_config *c, char *buf, size_t cap) { return c ? copy_out(build_spec(*c), buf, cap) : copy_out("", buf, cap); }
 extern "C" int jt_build_filter(const jt_filter_config *c, int id, char *buf, size_t cap) { if (!c) return JT_ERR_INVALID_ARG; return copy_out(build_one(*c, id), buf, cap); }
 extern "C" int jt_build_adeclick_filter(const jt_filter_config *c, char *buf, size_t cap)
