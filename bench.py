@@ -195,6 +195,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--minutes", type=int, default=MINUTES)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-adaptive", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -272,6 +273,27 @@ def main():
     t_e2e_wall = time.perf_counter() - t0
     t_e2e = max(ev0.elapsed_time(ev1) * 1e-3, 0.0)
 
+    # ---- the adaptive path on the library side (Pass 1 -> detector -> 17 band graphs -> AdaptConfig -> Pass 2..4), reported
+    #      next to the headline; Pass 2 cannot overlap Pass 1 here because its spec depends on Pass 1's measurements ----------
+    adaptive = None
+    if rank == 0 and not args.no_adaptive:
+        from jivetalking_b200 import adapt
+        adapt.process_audio_adaptive_ptr(ctx, d_in.data_ptr(), n, RATE, 1, gpudsp.FMT_FLT, d_out.data_ptr(), out_cap, True)
+        torch.cuda.synchronize()
+        ev0.record(lib_stream)
+        for _ in range(args.steps):
+            res_a, an_a = adapt.process_audio_adaptive_ptr(ctx, d_in.data_ptr(), n, RATE, 1, gpudsp.FMT_FLT, d_out.data_ptr(), out_cap, True)
+        ev1.record(lib_stream)
+        torch.cuda.synchronize()
+        t_ad = ev0.elapsed_time(ev1) * 1e-3 / args.steps
+        va = an_a.voice_activity
+        adaptive = {"value": n / t_ad, "unit": "samples/s", "realtime_x": n / t_ad / RATE, "ms_per_step": 1e3 * t_ad,
+                    "entry": "jt_process_audio_adaptive_dev (ProcessAudio with AnalyseAudio + AdaptConfig inside the library)",
+                    "pass2_spec": an_a.pass2_spec.decode(), "speech_profile": bool(va.has_speech_profile),
+                    "noise_profile": bool(va.has_noise_profile), "voice_activated": bool(va.voice_activated),
+                    "noise_floor": va.floor, "final_lufs": res_a.final.input_i, "final_dbtp": res_a.final.input_tp}
+    barrier()
+
     if world > 1:
         tt = torch.tensor([t_dev, t_e2e], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -322,6 +344,8 @@ def main():
         "result": {"final_lufs": res.final.input_i, "final_dbtp": res.final.input_tp, "final_lra": res.final.input_lra,
                    "n_out": int(res.n_out), "limiter_needed": int(res.limiter_needed), "pass4_type": int(res.pass4.normalization_type)},
     }
+    if adaptive is not None:
+        line["adaptive"] = adaptive
     if not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         sec = 150.0                           # ~20 s of scalar CPU work per core (the oracle chain runs ~8x realtime/core)

@@ -518,3 +518,12 @@ def process_audio_adaptive(ctx, pcm, rate, channels=1, base=None):
                                               C.byref(base) if base is not None else None, out.ctypes.data_as(_P), cap,
                                               C.byref(res), C.byref(an)))
     return out[:res.n_out], res, an
+
+
+def process_audio_adaptive_ptr(ctx, in_ptr, n, rate, channels, fmt, out_ptr, out_cap, on_device, base=None):
+    """raw-pointer variant for bench.py (torch owns the memory) -> (ProcessResult, Analysis)"""
+    res, an = ProcessResult(), Analysis()
+    fn = _L().jt_process_audio_adaptive_dev if on_device else _L().jt_process_audio_adaptive
+    ctx._check(fn(ctx._h, _P(in_ptr), n, rate, channels, fmt, C.byref(base) if base is not None else None, _P(out_ptr), out_cap,
+                  C.byref(res), C.byref(an)))
+    return res, an

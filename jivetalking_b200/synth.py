@@ -106,3 +106,45 @@ def stereo_from_mono(x, delay=7, gain=0.9):
     out[0::2] = x
     out[1::2] = r
     return out
+
+
+def podcast_like(duration_s, rate=48000, seed=2024, dtype=np.float32, sibilance_db=None):
+    """speech_like()'s carrier with a conversational duty cycle: 12-25 s phrases separated by 4-9 s room-tone pauses
+    (one of 14 s), so more than a fifth of the 250 ms intervals is room tone -- what the reference's noise-floor seed
+    (top 20 % most room-tone-like intervals, analyser_noise_seed.go:150-223) needs to find the floor and its
+    voice-activity detector needs to elect a speech profile and a room-tone region.  sibilance_db adds a 6-9 kHz
+    noise band to the phrases at that level relative to the carrier (drives the de-esser branch)."""
+    n = int(duration_s * rate)
+    rng = np.random.default_rng(seed)
+    t = np.arange(n, dtype=np.float64) / rate
+    car = np.zeros(n)
+    for h, a in ((1, 1.0), (2, 0.6), (3, 0.45), (4, 0.3), (5, 0.22), (7, 0.15), (10, 0.1), (14, 0.06), (20, 0.04)):
+        car += a * np.sin(2 * np.pi * 180.0 * h * t + 0.37 * h)
+    car /= np.max(np.abs(car)) + 1e-12
+    if sibilance_db is not None:
+        w = lcg_uniform(n, seed + 77)
+        spec = np.fft.rfft(w)
+        f = np.fft.rfftfreq(n, 1.0 / rate)
+        spec[(f < 6000.0) | (f > 9000.0)] = 0.0
+        sib = np.fft.irfft(spec, n)
+        sib *= 10.0 ** (sibilance_db / 20.0) * np.sqrt(np.mean(car ** 2)) / (np.sqrt(np.mean(sib ** 2)) + 1e-30)
+        car = car + sib
+    syl = 0.6 + 0.4 * np.sin(2 * np.pi * (3.0 + 2.0 * rng.random()) * t) * np.sin(2 * np.pi * 0.31 * t + 1.0)
+    gain = np.zeros(n)
+    k = int(0.02 * rate)
+    ramp = 0.5 * (1.0 - np.cos(np.pi * (np.arange(k) + 0.5) / max(k, 1)))      # 0 -> 1
+    pos, first_pause = 3.0 + 2.0 * rng.random(), True
+    while pos < duration_s:
+        seg = 12.0 + 13.0 * rng.random()
+        a, b = int(pos * rate), min(int((pos + seg) * rate), n)
+        lvl = 10.0 ** (rng.choice([-26.0, -22.0, -18.0, -15.0]) / 20.0)
+        g = np.full(b - a, lvl)
+        m = min(k, (b - a) // 2)
+        if m > 0:
+            g[:m] *= ramp[:m]
+            g[-m:] *= ramp[:m][::-1]
+        gain[a:b] = g
+        pos += seg + (14.0 if first_pause else 4.0 + 5.0 * rng.random())
+        first_pause = False
+    x = car * syl * gain + 10.0 ** (-58.0 / 20.0) * lcg_uniform(n, seed)
+    return np.clip(x, -1.0, 1.0).astype(dtype)

@@ -98,6 +98,86 @@ def pass1_meta(x, rate, channels=1, frame_size=4096):
     return analysis_meta(mono, to_f32(mono), to_f64(mono), rate, ends)
 
 
+def pass1_analyse(x, rate, channels=1, frame_size=4096):
+    """ORACLE (test infrastructure) restatement of collectAnalysisFrames (analyser.go:538-650): the Go-side accumulation
+    of the Pass-1 sink-frame records into whole-file values and 250 ms IntervalSamples (analyser_metrics.go:165-420).
+    Returns (measurements dict, [interval dict]); interval["spectral"] is the 13-value mean in aspectralstats order."""
+    exp = pass1_meta(x, rate, channels, frame_size)
+    F = frame_size
+    n = len(x) // channels
+    if x.dtype == np.int16:
+        xs = x.astype(np.float64) / 32768.0
+    else:
+        xs = x.astype(np.float64)
+    xs = xs.reshape(n, channels) if channels > 1 else xs
+    nsrc = (n + F - 1) // F
+
+    def db(v):
+        return -120.0 if v <= 0 else 20 * math.log10(v)
+
+    def new_acc(first):
+        return dict(fc=0, ss=0.0, n=0, pk=0.0, M=0.0, S=0.0, tp=0.0 if first else -120.0, sp=0.0 if first else -120.0,
+                    spec=[0.0] * 13, found=False)
+
+    def fin(a, ts):
+        rms = math.sqrt(a["ss"] / a["n"]) if a["n"] else 0.0
+        fc = a["fc"]
+        return dict(ts_ns=ts, rms=-120.0 if (a["n"] == 0 or rms < 1e-5) else 20 * math.log10(rms),
+                    pk=20 * math.log10(a["pk"]) if a["pk"] > 0 else -120.0,
+                    M=a["M"] / fc if fc else 0.0, S=a["S"] / fc if fc else 0.0, tp=a["tp"], sp=a["sp"], fc=fc,
+                    spectral=[v / fc for v in a["spec"]] if fc else [0.0] * 13, found=a["found"])
+
+    whole = dict(I=NAN, M=NAN, S=NAN, LRA=NAN, tp=NAN, sp=NAN, astats=None, spec_sum=[0.0] * 13, spec_n=0)
+
+    def add_sink(acc, e):
+        tp = 0.0 if math.isnan(e["true_peak"]) else db(e["true_peak"])
+        sp = 0.0 if math.isnan(e["sample_peak"]) else db(e["sample_peak"])
+        if acc["fc"] == 0 or tp > acc["tp"]:
+            acc["tp"] = tp
+        if acc["fc"] == 0 or sp > acc["sp"]:
+            acc["sp"] = sp
+        for k, v in enumerate(e["spectral"]):
+            if not math.isnan(v):
+                acc["spec"][k] += v
+                acc["found"] = True
+        acc["M"] += 0.0 if math.isnan(e["M"]) else e["M"]
+        acc["S"] += 0.0 if math.isnan(e["S"]) else e["S"]
+        acc["fc"] += 1
+        if any(not math.isnan(v) for v in e["spectral"]):
+            whole["spec_n"] += 1
+            for k, v in enumerate(e["spectral"]):
+                whole["spec_sum"][k] += 0.0 if math.isnan(v) else v
+        for key, src in (("I", "I"), ("M", "M"), ("S", "S"), ("LRA", "LRA")):
+            if not math.isnan(e[src]):
+                whole[key] = e[src]
+        if not math.isnan(e["true_peak"]):
+            whole["tp"] = db(e["true_peak"])
+        if not math.isnan(e["sample_peak"]):
+            whole["sp"] = db(e["sample_peak"])
+        if e["astats"] is not None:
+            whole["astats"] = e["astats"]
+
+    intervals, acc, start_ns, pushed, sink = [], new_acc(True), 0, 0, 0
+    for f in range(nsrc):
+        t_ns = int(pushed / rate * 1e9)
+        seg = xs[pushed:pushed + F]
+        pushed += len(seg)
+        acc["ss"] += float(np.sum(seg * seg)); acc["n"] += seg.size
+        acc["pk"] = max(acc["pk"], float(np.max(np.abs(seg))) if seg.size else 0.0)
+        if t_ns - start_ns >= 250_000_000:
+            intervals.append(fin(acc, start_ns)); start_ns = t_ns; acc = new_acc(False)
+        while sink < len(exp) and exp[sink]["ready"] <= pushed:
+            add_sink(acc, exp[sink]); sink += 1
+    while sink < len(exp):
+        add_sink(acc, exp[sink]); sink += 1
+    if acc["n"] > 0:
+        intervals.append(fin(acc, start_ns))
+    meas = dict(input_i=whole["I"], input_tp=whole["tp"], input_sp=whole["sp"], input_lra=whole["LRA"], last_m=whole["M"], last_s=whole["S"],
+                astats=whole["astats"], spectral_mean=[v / whole["spec_n"] for v in whole["spec_sum"]] if whole["spec_n"] else [0.0] * 13,
+                sink_frames=len(exp), duration_s=n / rate)
+    return meas, intervals
+
+
 # ---------------------------------------------------------------------------------------------
 # whole-graph oracle: parses the reference's spec strings and chains the oracle filters with the
 # sample-format conversions libavfilter's negotiation would insert (SURVEY.md 7, hard part 4)

@@ -60,53 +60,19 @@ def test_digital_silence(ctx):
 
 
 def test_analyse_intervals(ctx):
-    """jt_analyse: interval accumulation of collectAnalysisFrames (analyser.go:571-638)."""
+    """jt_analyse: interval accumulation of collectAnalysisFrames (analyser.go:571-638) against the oracle's restatement
+    of the Go accumulation over the oracle's sink-frame records (oracle_graph.pass1_analyse)."""
     x = synth.reference_test_audio(5.0, 48000, 440.0, -23.0, -60.0, 2.0, 0.5)
     m, iv = ctx.analyse(x, 48000)
-    exp = OG.pass1_meta(x, 48000)
-    # re-run the Go accumulation on the oracle's records
-    F, rate = 4096, 48000
-    n = len(x)
-    xs = x.astype(np.float64) / 32768.0
-    nsrc = (n + F - 1) // F
-    intervals, acc, start_ns, pushed, sink = [], None, 0, 0, 0
-
-    def new_acc(first):
-        return dict(fc=0, ss=0.0, n=0, pk=0.0, M=0.0, S=0.0, tp=0.0 if first else -120.0, sp=0.0 if first else -120.0)
-    acc = new_acc(True)
-
-    def fin(a, ts):
-        rms = math.sqrt(a["ss"] / a["n"]) if a["n"] else 0.0
-        return dict(ts=ts * 1e-9, rms=-120.0 if (a["n"] == 0 or rms < 1e-5) else 20 * math.log10(rms),
-                    pk=20 * math.log10(a["pk"]) if a["pk"] > 0 else -120.0,
-                    M=a["M"] / a["fc"] if a["fc"] else 0.0, S=a["S"] / a["fc"] if a["fc"] else 0.0, tp=a["tp"], sp=a["sp"], fc=a["fc"])
-
-    def db(v):
-        return -120.0 if v <= 0 else 20 * math.log10(v)
-    for f in range(nsrc):
-        t_ns = int(pushed / rate * 1e9)
-        seg = xs[pushed:pushed + F]
-        pushed += len(seg)
-        acc["ss"] += float(np.sum(seg * seg)); acc["n"] += len(seg); acc["pk"] = max(acc["pk"], float(np.max(np.abs(seg))))
-        if t_ns - start_ns >= 250_000_000:
-            intervals.append(fin(acc, start_ns)); start_ns = t_ns; acc = new_acc(False)
-        while sink < len(exp) and exp[sink]["ready"] <= pushed:
-            e = exp[sink]; sink += 1
-            tp = 0.0 if math.isnan(e["true_peak"]) else db(e["true_peak"])
-            sp = 0.0 if math.isnan(e["sample_peak"]) else db(e["sample_peak"])
-            if acc["fc"] == 0 or tp > acc["tp"]: acc["tp"] = tp
-            if acc["fc"] == 0 or sp > acc["sp"]: acc["sp"] = sp
-            acc["M"] += 0.0 if math.isnan(e["M"]) else e["M"]; acc["S"] += 0.0 if math.isnan(e["S"]) else e["S"]
-            acc["fc"] += 1
-    while sink < len(exp):
-        e = exp[sink]; sink += 1
-        acc["M"] += 0.0 if math.isnan(e["M"]) else e["M"]; acc["S"] += 0.0 if math.isnan(e["S"]) else e["S"]; acc["fc"] += 1
-    if acc["n"] > 0:
-        intervals.append(fin(acc, start_ns))
+    meas, intervals = OG.pass1_analyse(x, 48000)
     assert len(iv) == len(intervals)
     for a, b in zip(iv, intervals):
-        assert abs(a.timestamp_s - b["ts"]) < 1e-9 and a.frame_count == b["fc"]
+        assert abs(a.timestamp_s - b["ts_ns"] * 1e-9) < 1e-9 and a.frame_count == b["fc"]
         assert abs(a.rms_level - b["rms"]) < 1e-6 and abs(a.peak_level - b["pk"]) < 1e-6
         assert abs(a.momentary_lufs - b["M"]) < 2e-3 and abs(a.short_term_lufs - b["S"]) < 2e-3
         assert abs(a.true_peak - b["tp"]) < 0.2 and abs(a.sample_peak - b["sp"]) < 0.2
-    assert abs(m.duration_s - 5.0) < 1e-9 and m.sink_frames == len(exp)
+        assert bool(a.spectral_found) == b["found"]
+        for k in range(gpudsp.SP_COUNT):
+            assert abs(a.spectral[k] - b["spectral"][k]) <= 2e-3 * abs(b["spectral"][k]) + 1e-9, (k, a.spectral[k], b["spectral"][k])
+    assert abs(m.duration_s - 5.0) < 1e-9 and m.sink_frames == meas["sink_frames"]
+    assert abs(m.input_i - meas["input_i"]) < 2e-3 and abs(m.input_lra - meas["input_lra"]) < 2e-3
