@@ -389,16 +389,30 @@ double  jt_adapt_gate_threshold(double voiced_low_percentile, double separation,
 double  jt_adapt_gate_threshold_no_profile(double floor, double room_tone_peak, double room_tone_crest, double ratio, double lufs_gap);
 int     jt_adapt_band_noise(const double *bands, int n, char *buf, size_t cap);                      /* buildAfftdnBandNoise */
 
+/* Region re-measure of a pass's output (measureOutputRegionFromReader analyser_output.go:95-233): the graph of
+ * analyser_output.go:18 over [start, start + duration) and the Go-side reduction to a RegionSample -- astats Overall RMS / peak
+ * (crest = peak - RMS), spectral means over frames that carry them, last M / S, true / sample peak in dB.
+ * *frames_processed = sink frames seen; JT_ERR_INVALID_ARG when the region is invalid or holds no frame. */
+int jt_measure_output_region(jt_ctx *ctx, const void *pcm, int64_t n_frames, int sample_rate, int channels, int sample_fmt,
+                             int64_t start_ns, int64_t duration_ns, jt_region_sample *out, int64_t *frames_processed);
+int jt_measure_output_region_dev(jt_ctx *ctx, const void *d_pcm, int64_t n_frames, int sample_rate, int channels, int sample_fmt,
+                             int64_t start_ns, int64_t duration_ns, jt_region_sample *out, int64_t *frames_processed);
+
 /* ---- S2 / S1 with the adaptive path on the library side ------------------------------------------------------------
  * jt_analyse_adaptive = AnalyseAudio + AdaptConfig (analyser.go:325-372, processor.go:37-69): Pass 1, the detector, the
  * 17 band RMS graphs over the elected regions (one launch), AdaptConfig and BuildFilterSpec.
  * jt_process_audio_adaptive = ProcessAudio (processor.go:78-216) with that analysis feeding Pass 2. */
+typedef struct jt_output_regions {           /* OutputMeasurements.RoomToneSample / SpeechSample analyser.go:318-326 */
+    jt_region_sample room_tone, speech;
+    int32_t has_room_tone, has_speech;
+} jt_output_regions;
 typedef struct jt_analysis {
     jt_measurements measurements;
     jt_voice_activity voice_activity;
     jt_filter_config config;
     jt_adapt_diagnostics diagnostics;
     char pass2_spec[2048];
+    jt_output_regions filtered_regions, final_regions;    /* jt_process_audio_adaptive only: MeasureOutputRegions on the Pass-2 / Pass-4 output */
 } jt_analysis;
 int jt_analyse_adaptive(jt_ctx *ctx, const void *pcm_in, int64_t n_frames, int sample_rate, int channels, int sample_fmt,
                         int frame_size, const jt_filter_config *base,

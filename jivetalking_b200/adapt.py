@@ -123,9 +123,14 @@ class AdaptDiagnostics(C.Structure):
                 ("afftdn_noise_floor_db", _D), ("afftdn_disable_reason", C.c_char * 24), ("afftdn_noise_type", C.c_char * 8)]
 
 
+class OutputRegions(C.Structure):
+    _fields_ = [("room_tone", RegionSample), ("speech", RegionSample), ("has_room_tone", _I32), ("has_speech", _I32)]
+
+
 class Analysis(C.Structure):
     _fields_ = [("measurements", Measurements), ("voice_activity", VoiceActivity), ("config", FilterConfig),
-                ("diagnostics", AdaptDiagnostics), ("pass2_spec", C.c_char * 2048)]
+                ("diagnostics", AdaptDiagnostics), ("pass2_spec", C.c_char * 2048),
+                ("filtered_regions", OutputRegions), ("final_regions", OutputRegions)]
 
 
 _bound = False
@@ -192,6 +197,9 @@ def _L():
     L.jt_adapt_gate_threshold_no_profile.restype = _D
     L.jt_adapt_gate_threshold_no_profile.argtypes = [_D] * 5
     L.jt_adapt_band_noise.argtypes = [_P, _INT, C.c_char_p, C.c_size_t]
+    mo = [_P, _P, _I64, _INT, _INT, _INT, _I64, _I64, C.POINTER(RegionSample), C.POINTER(_I64)]
+    L.jt_measure_output_region.argtypes = mo
+    L.jt_measure_output_region_dev.argtypes = mo
     L.jt_analyse_adaptive.argtypes = [_P, _P, _I64, _INT, _INT, _INT, _INT, C.POINTER(FilterConfig), C.POINTER(Analysis),
                                       PI, _I64, C.POINTER(_I64)]
     pa = [_P, _P, _I64, _INT, _INT, _INT, C.POINTER(FilterConfig), _P, _I64, C.POINTER(ProcessResult), C.POINTER(Analysis)]
@@ -504,6 +512,16 @@ def analyse_adaptive(ctx, pcm, rate, channels=1, frame_size=4096, base=None):
     ctx._check(_L().jt_analyse_adaptive(ctx._h, pcm.ctypes.data_as(_P), n, rate, channels, gpudsp._FMT_OF_NP[pcm.dtype], frame_size,
                                         C.byref(base) if base is not None else None, C.byref(out), iv, cap, C.byref(n_iv)))
     return out, list(iv[:n_iv.value])
+
+
+def measure_output_region(ctx, pcm, rate, start_ns, duration_ns, channels=1):
+    """measureOutputRegionFromReader -> (RegionSample, frames processed)"""
+    import numpy as np
+    pcm = np.ascontiguousarray(pcm)
+    out, frames = RegionSample(), _I64()
+    ctx._check(_L().jt_measure_output_region(ctx._h, pcm.ctypes.data_as(_P), pcm.size // channels, rate, channels,
+                                             gpudsp._FMT_OF_NP[pcm.dtype], int(start_ns), int(duration_ns), C.byref(out), C.byref(frames)))
+    return out, frames.value
 
 
 def process_audio_adaptive(ctx, pcm, rate, channels=1, base=None):

@@ -1004,6 +1004,78 @@ extern "C" int jt_build_pass4_spec(const jt_process_result *plan, const jt_loudn
 }
 
 // ---------------------------------------------------------------------------------------
+// a7: measureOutputRegionFromReader (analyser_output.go:95-233) -- the region graph of analyser_output.go:18 and the
+// Go-side reduction of its sink frames into a RegionSample
+// ---------------------------------------------------------------------------------------
+static double go_seconds(int64_t ns) { return (double)(ns / 1000000000LL) + (double)(ns % 1000000000LL) / 1e9; }     // time.Duration.Seconds
+
+static void region_measure_device(jt_ctx *c, const void *d_pcm, int64_t n_frames, int rate, int channels, int fmt,
+                                  int64_t start_ns, int64_t dur_ns, jt_region_sample *out, int64_t *frames_out)
+{
+    if (start_ns < 0) JT_THROW(JT_ERR_INVALID_ARG, "invalid region: negative start time");
+    if (dur_ns <= 0) JT_THROW(JT_ERR_INVALID_ARG, "invalid region: non-positive duration");
+    char spec[512];
+    snprintf(spec, sizeof(spec), "atrim=start=%f:duration=%f,asetpts=PTS-STARTPTS,astats=metadata=1:measure_perchannel=0,"
+                                 "aspectralstats=measure=all,ebur128=metadata=1:peak=sample+true", go_seconds(start_ns), go_seconds(dur_ns));
+    const size_t mark = c->allocs.size();
+    GraphResult g;
+    jt_graph_run(c, spec, d_pcm, n_frames, rate, channels, fmt, 4096, false, true, g);
+    jt_release_since(c, mark, nullptr);
+    double rms = 0, peak = 0, M = 0, S = 0, tp = 0, sp = 0, spec_sum[JT_SP_COUNT] = {0}; bool rms_found = false; int64_t spec_n = 0;
+    for (const jt_frame_meta &f : g.meta) {
+        if (!std::isnan(f.astats_overall_RMS_level)) { rms = f.astats_overall_RMS_level; rms_found = true; }
+        if (!std::isnan(f.astats_overall_Peak_level)) peak = f.astats_overall_Peak_level;
+        bool sf = false;
+        for (int k = 0; k < JT_SP_COUNT; k++) if (!std::isnan(f.spectral[k])) sf = true;
+        if (sf) { for (int k = 0; k < JT_SP_COUNT; k++) spec_sum[k] += std::isnan(f.spectral[k]) ? 0.0 : f.spectral[k]; spec_n++; }
+        if (!std::isnan(f.r128_M)) M = f.r128_M;
+        if (!std::isnan(f.r128_S)) S = f.r128_S;
+        if (!std::isnan(f.r128_true_peak)) tp = f.r128_true_peak;
+        if (!std::isnan(f.r128_sample_peak)) sp = f.r128_sample_peak;
+    }
+    if (frames_out) *frames_out = (int64_t)g.meta.size();
+    if (g.meta.empty()) JT_THROW(JT_ERR_INVALID_ARG, "no frames processed in region");
+    jt_region_sample r; memset(&r, 0, sizeof(r));
+    r.rms_level = rms_found ? rms : -60.0;                                   // conservative fallback (analyser_output.go:222-224)
+    r.peak_level = peak;
+    r.crest_factor = (rms_found && peak != 0) ? peak - rms : 0.0;            // lavfi.astats.Overall has no Crest_factor key
+    for (int k = 0; k < JT_SP_COUNT; k++) r.spectral[k] = spec_n ? spec_sum[k] / (double)spec_n : 0.0;
+    r.momentary_lufs = M; r.short_term_lufs = S; r.true_peak = ratio_db(tp); r.sample_peak = ratio_db(sp);
+    if (out) *out = r;
+}
+
+extern "C" int jt_measure_output_region(jt_ctx *c, const void *pcm, int64_t n_frames, int rate, int channels, int fmt,
+                                        int64_t start_ns, int64_t dur_ns, jt_region_sample *out, int64_t *frames)
+{
+    return guarded(c, [&]() {
+        if (!pcm && n_frames > 0) JT_THROW(JT_ERR_INVALID_ARG, "null input");
+        if (fmt != JT_FMT_S16 && fmt != JT_FMT_FLT && fmt != JT_FMT_DBL) JT_THROW(JT_ERR_UNSUPPORTED, "input sample format %d", fmt);
+        const void *d_in = upload(c, pcm, (size_t)n_frames * channels * jt_fmt_bytes(fmt));
+        region_measure_device(c, d_in, n_frames, rate, channels, fmt, start_ns, dur_ns, out, frames);
+    });
+}
+extern "C" int jt_measure_output_region_dev(jt_ctx *c, const void *d_pcm, int64_t n_frames, int rate, int channels, int fmt,
+                                        int64_t start_ns, int64_t dur_ns, jt_region_sample *out, int64_t *frames)
+{
+    return guarded(c, [&]() { region_measure_device(c, d_pcm, n_frames, rate, channels, fmt, start_ns, dur_ns, out, frames); });
+}
+
+// MeasureOutputRegions (analyser_output.go:261-297): the elected room-tone and speech regions of Pass 1 re-measured on a
+// pass's s16 output; a failing region is a warning, not an error (its sample stays absent)
+static void measure_output_regions(jt_ctx *c, const void *d_pcm, int64_t n, const jt_voice_activity &va, jt_output_regions *o)
+{
+    memset(o, 0, sizeof(*o));
+    if (va.has_noise_profile) {
+        try { region_measure_device(c, d_pcm, n, 44100, 1, JT_FMT_S16, va.noise_profile.start_ns, va.noise_profile.duration_ns, &o->room_tone, nullptr); o->has_room_tone = 1; }
+        catch (const JtError &e) { if (e.code == JT_ERR_CUDA || e.code == JT_ERR_CANCELLED) throw; }
+    }
+    if (va.has_speech_profile) {
+        try { region_measure_device(c, d_pcm, n, 44100, 1, JT_FMT_S16, va.speech_profile.region.start_ns, va.speech_profile.region.duration_ns, &o->speech, nullptr); o->has_speech = 1; }
+        catch (const JtError &e) { if (e.code == JT_ERR_CUDA || e.code == JT_ERR_CANCELLED) throw; }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // the four-pass chain (ProcessAudio, processor.go:78-216)
 // ---------------------------------------------------------------------------------------
 // The four passes are data-dependent only through a handful of scalars (Pass 3 is planned from Pass 2's I / TP,
@@ -1011,7 +1083,7 @@ extern "C" int jt_build_pass4_spec(const jt_process_result *plan, const jt_loudn
 // GPU is already working on the next pass: graphs are enqueued (jt_graph_enqueue) ahead of being finished.
 static void process_device(jt_ctx *c, const void *d_in, int64_t n_frames, int rate, int channels, int fmt, const char *pass2_spec,
                            int16_t *pcm_out, bool out_on_device, int64_t cap, jt_process_result *res,
-                           const jt_measurements *pass1_done = nullptr, const jt_filter_config *cfg = nullptr)
+                           const jt_measurements *pass1_done = nullptr, const jt_filter_config *cfg = nullptr, jt_analysis *an = nullptr)
 {
     jt_process_result R; memset(&R, 0, sizeof(R));
     // defaultLoudnormConfig, filters.go:523-532 (or the caller's base config on the adaptive path)
@@ -1084,6 +1156,10 @@ static void process_device(jt_ctx *c, const void *d_in, int64_t n_frames, int ra
         jt_graph_finish(c, g4, r4);
         MeasAcc a; for (auto &m : r4.meta) a.add(m); a.finish((double)g4.out.n / g4.out.rate); R.final = a.m;
         R.pass4 = r4.ln;
+    }
+    if (an) {                                      // processor.go:150-160 and normalise.go's Pass-4 re-measure of the same regions
+        measure_output_regions(c, g2.out.d, g2.out.n, an->voice_activity, &an->filtered_regions);
+        measure_output_regions(c, g4.out.d, g4.out.n, an->voice_activity, &an->final_regions);
     }
     JT_CUDA(cudaStreamSynchronize(c->stream));
     if (res) *res = R;
@@ -1174,7 +1250,7 @@ static void process_adaptive_device(jt_ctx *c, const void *d_in, int64_t n_frame
     jt_analysis *an = analysis ? analysis : own.data();
     analyse_adaptive_device(c, d_in, n_frames, rate, channels, fmt, 4096, base, an, nullptr, 0, nullptr);
     jt_check_cancel(c);
-    process_device(c, d_in, n_frames, rate, channels, fmt, an->pass2_spec, pcm_out, out_on_device, cap, res, &an->measurements, &an->config);
+    process_device(c, d_in, n_frames, rate, channels, fmt, an->pass2_spec, pcm_out, out_on_device, cap, res, &an->measurements, &an->config, an);
 }
 extern "C" int jt_process_audio_adaptive(jt_ctx *c, const void *pcm_in, int64_t n_frames, int rate, int channels, int fmt,
                                          const jt_filter_config *base, int16_t *pcm_out, int64_t cap, jt_process_result *res, jt_analysis *analysis)

@@ -178,6 +178,41 @@ def pass1_analyse(x, rate, channels=1, frame_size=4096):
     return meas, intervals
 
 
+REGION_SPEC = ("atrim=start=%f:duration=%f,asetpts=PTS-STARTPTS,astats=metadata=1:measure_perchannel=0,"
+               "aspectralstats=measure=all,ebur128=metadata=1:peak=sample+true")          # analyser_output.go:18
+
+
+def region_sample(pcm, rate, start_ns, dur_ns):
+    """ORACLE (test infrastructure) restatement of measureOutputRegionFromReader (analyser_output.go:95-233): the region
+    graph over the oracle filters and the Go-side reduction of its sink frames.  Returns (dict, frames processed)."""
+    def secs(ns):
+        return float(ns // 1_000_000_000) + float(ns % 1_000_000_000) / 1e9
+    exp = run_spec(REGION_SPEC % (secs(start_ns), secs(dur_ns)), pcm, rate, want_pcm=False)["meta"]
+    rms = peak = M = S = tp = sp = 0.0
+    rms_found, spec_sum, spec_n = False, [0.0] * 13, 0
+    for e in exp:
+        if e["astats"] is not None:
+            if not math.isnan(e["astats"]["RMS_level"]):
+                rms, rms_found = e["astats"]["RMS_level"], True
+            if not math.isnan(e["astats"]["Peak_level"]):
+                peak = e["astats"]["Peak_level"]
+        if any(not math.isnan(v) for v in e["spectral"]):
+            spec_n += 1
+            for k, v in enumerate(e["spectral"]):
+                spec_sum[k] += 0.0 if math.isnan(v) else v
+        M = e["M"] if not math.isnan(e["M"]) else M
+        S = e["S"] if not math.isnan(e["S"]) else S
+        tp = e["true_peak"] if not math.isnan(e["true_peak"]) else tp
+        sp = e["sample_peak"] if not math.isnan(e["sample_peak"]) else sp
+
+    def db(v):
+        return -120.0 if v <= 0 else 20 * math.log10(v)
+    out = dict(rms_level=rms if rms_found else -60.0, peak_level=peak, crest_factor=peak - rms if (rms_found and peak != 0) else 0.0,
+               spectral=[v / spec_n for v in spec_sum] if spec_n else [0.0] * 13, momentary_lufs=M, short_term_lufs=S,
+               true_peak=db(tp), sample_peak=db(sp))
+    return out, len(exp)
+
+
 # ---------------------------------------------------------------------------------------------
 # whole-graph oracle: parses the reference's spec strings and chains the oracle filters with the
 # sample-format conversions libavfilter's negotiation would insert (SURVEY.md 7, hard part 4)

@@ -147,6 +147,27 @@ def test_process_audio_adaptive(ctx, podcast, analysis):
     # the chain's purpose (filters.go:75-82): -16 LUFS +-0.5 LU, true peak at or under -1 dBTP
     assert abs(res.final.input_i - (-16.0)) <= 0.5 and res.final.input_tp <= -1.0 + 0.1
     assert len(pcm) % 4096 == 0 and res.n_out == len(pcm)
+    # a7: the elected regions re-measured on the Pass-2 and Pass-4 outputs (MeasureOutputRegions, processor.go:150-160)
+    va = an2.voice_activity
+    for regions, audio in ((an2.filtered_regions, got["pcm"]), (an2.final_regions, pcm)):
+        assert regions.has_room_tone and regions.has_speech
+        for sample, (st, du) in ((regions.room_tone, (va.noise_profile.start_ns, va.noise_profile.duration_ns)),
+                                 (regions.speech, (va.speech_profile.region.start_ns, va.speech_profile.region.duration_ns))):
+            o, frames = OG.region_sample(audio, 44100, st, du)
+            assert frames > 0
+            for k in ("rms_level", "peak_level", "crest_factor"):
+                assert abs(getattr(sample, k) - o[k]) < 2e-6, (k, getattr(sample, k), o[k])
+            for k in ("momentary_lufs", "short_term_lufs"):
+                assert abs(getattr(sample, k) - o[k]) < 0.0011, (k, getattr(sample, k), o[k])
+            for k in ("true_peak", "sample_peak"):
+                assert abs(getattr(sample, k) - o[k]) < 0.2, k           # linear peaks on a %.3f wire, in dB
+            for k in range(gpudsp.SP_COUNT):
+                assert abs(sample.spectral[k] - o["spectral"][k]) <= 2e-3 * abs(o["spectral"][k]) + 1e-9, (k, sample.spectral[k], o["spectral"][k])
+            # the ABI entry on host audio gives the same sample
+            s2, f2 = A.measure_output_region(ctx, audio, 44100, st, du)
+            assert bytes(s2) == bytes(sample) and f2 == frames
+    # noise reduction did its job in the room-tone region, speech came up to target
+    assert an2.final_regions.speech.rms_level > an2.voice_activity.speech_profile.sample.rms_level
 
 
 def test_voice_activated_capture_drops_afftdn(ctx):
