@@ -250,3 +250,50 @@ def process_stream_sharded(ctx, comm, pcm, rate, channels=1, pass2_spec=None,
     out4, mg4 = run_graph_sharded(ctx, comm, spec4, out2, 44100, 1, want_pcm=True, timings=timings, tag="pass4")
     return out4, dict(filtered=filtered, final=mg4["measurements"], pass3=p3, pass4=mg4["loudnorm"], plan=plan,
                       effective_target_i=eff, offset_db=off, specs=(spec2, spec3, spec4), pass2_pcm=out2)
+
+
+def adapt_stream_sharded(ctx, pcm, rate, channels=1, base=None, device=None):
+    """AnalyseAudio + AdaptConfig (analyser.go:325-372, adaptive.go:13-40) for ONE stream analysed by all ranks: Pass 1 is
+    analyse_stream_sharded (one all-gather); the merged measurements and intervals are identical on every rank, so every
+    rank runs the same deterministic detector and AdaptConfig and arrives at the same Pass-2 spec without further
+    communication.  The 17 band graphs read only the elected regions (<= 60 s of speech, <= 18 s of room tone
+    -- the reference re-decodes them 17 times, analyser_bands.go:106-167): each rank measures them itself from the
+    region's samples.  Returns (Measurements, [Interval], VoiceActivity, FilterConfig, AdaptDiagnostics, spec)."""
+    from . import adapt
+    m, iv = analyse_stream_sharded(ctx, pcm, rate, channels, device=device)
+    va, _, _ = adapt.detect_voice_activity(m, iv)
+    lo, hi = adapt.band_plan()
+    flat = pcm.reshape(-1)
+
+    def region_bands(start_ns, dur_ns, lo_hz, hi_hz):
+        # atrim=start=%f:duration=%f (analyser_bands.go:54-60): the same sample window jt_band_rms cuts from the whole stream
+        st, du = float("%f" % (start_ns / 1e9)), float("%f" % (dur_ns / 1e9))
+        s0 = (round(st * 1e6) * rate + 500000) // 1000000
+        n = (round(du * 1e6) * rate + 500000) // 1000000
+        a, b = min(max(s0, 0), flat.size // channels), min(flat.size // channels, s0 + n)
+        return ctx.band_rms(flat[a * channels: b * channels], rate, 0.0, du, lo_hz, hi_hz, channels=channels)
+
+    speech = noise = None
+    if va.has_speech_profile and va.speech_profile.region.duration_ns > 0:
+        r, f = region_bands(va.speech_profile.region.start_ns, va.speech_profile.region.duration_ns, lo[:2], hi[:2])
+        speech = (list(r), list(f))
+    if va.has_noise_profile and va.noise_profile.duration_ns > 0:
+        r, f = region_bands(va.noise_profile.start_ns, va.noise_profile.duration_ns, lo[2:], hi[2:])
+        noise = (list(r), list(f))
+    adapt.apply_band_rms(va, speech, noise)
+    cfg, diag = adapt.adapt_config(m, va, base)
+    return m, iv, va, cfg, diag, adapt.build_filter_spec(cfg)
+
+
+def process_stream_sharded_adaptive(ctx, comm, pcm, rate, channels=1, base=None, timings=None, device=None):
+    """ProcessAudio (processor.go:78-216) of ONE stream over the ranks of `comm` with the adaptive Pass-2 spec derived on
+    every rank from the sharded Pass 1 (adapt_stream_sharded)."""
+    import time
+    t0 = time.perf_counter()
+    m, iv, va, cfg, diag, spec = adapt_stream_sharded(ctx, pcm, rate, channels, base=base, device=device)
+    if timings is not None:
+        timings["pass1+adapt"] = time.perf_counter() - t0
+    out, info = process_stream_sharded(ctx, comm, pcm, rate, channels, pass2_spec=spec, target_i=cfg.loudnorm.target_i,
+                                       target_tp=cfg.loudnorm.target_tp, target_lra=cfg.loudnorm.target_lra, timings=timings)
+    info.update(input=m, intervals=iv, voice_activity=va, config=cfg, diagnostics=diag)
+    return out, info

@@ -11,7 +11,7 @@ import pytest
 import jt_oracle as O
 import oracle_graph as OG
 from jivetalking_b200 import adapt as A
-from jivetalking_b200 import gpudsp, synth
+from jivetalking_b200 import gpudsp, shard, synth
 
 pytestmark = pytest.mark.gpu
 RATE = 48000
@@ -185,3 +185,18 @@ def test_voice_activated_capture_drops_afftdn(ctx):
     # the adapted spec runs through Pass 2
     got = ctx.run_graph(an.pass2_spec.decode(), x * gate, RATE, want_meta=False)
     assert got["rate"] == 44100 and len(got["pcm"]) % 4096 == 0 and len(got["pcm"]) >= 60 * 44100
+
+
+def test_adaptive_chain_sharded_equals_single_gpu(ctx, podcast, analysis):
+    """configs[3] with the adaptive spec: Pass 1 (chunk + merge) -> detector / AdaptConfig on every rank -> Passes 2-4 in
+    chunks == jt_process_audio_adaptive on the whole stream."""
+    an, _ = analysis
+    pcm1, res1, _ = A.process_audio_adaptive(ctx, podcast, RATE)
+    pcm, r = shard.process_stream_sharded_adaptive(ctx, shard.LocalComm(4), podcast, RATE)
+    assert r["specs"][0] == an.pass2_spec.decode()
+    assert bytes(r["voice_activity"]) == bytes(an.voice_activity)
+    assert len(pcm) == len(pcm1) == res1.n_out
+    d = (pcm.astype(np.int32) - pcm1.astype(np.int32)) / 32768.0
+    assert float(np.sqrt(np.mean(d * d))) < 1e-4
+    assert abs(r["final"].input_i - res1.final.input_i) <= 0.01 and abs(r["final"].input_tp - res1.final.input_tp) <= 0.01
+    assert abs(r["final"].input_lra - res1.final.input_lra) <= 0.05

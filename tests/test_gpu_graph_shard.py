@@ -189,7 +189,15 @@ def _nccl_worker(rank, world, port, q):
             pcm1, res1 = c.process_audio(x, 48000)
             d = (pcm.astype(np.int32) - pcm1.astype(np.int32)) / 32768.0
             ok = len(pcm) == len(pcm1) and rms(d) < 1e-4 and abs(r["final"].input_i - res1.final.input_i) <= 0.01
-    q.put((rank, ok, len(pcm), int(np.abs(pcm.astype(np.int64)).sum()), r["final"].input_i, r["final"].input_tp))
+        # the adaptive spec derived on every rank from the chunked Pass 1 (shard.adapt_stream_sharded): identical on both
+        # ranks and equal to the single-GPU analysis
+        from jivetalking_b200 import adapt
+        y = synth.podcast_like(80.0, 48000, sibilance_db=-14.0)
+        _, _, va, _, _, spec = shard.adapt_stream_sharded(c, y, 48000, device=dev)
+        if rank == 0:
+            an, _ = adapt.analyse_adaptive(c, y, 48000)
+            ok = ok and spec == an.pass2_spec.decode() and bytes(va) == bytes(an.voice_activity)
+    q.put((rank, ok, len(pcm), int(np.abs(pcm.astype(np.int64)).sum()), r["final"].input_i, r["final"].input_tp, spec))
     dist.barrier()
     dist.destroy_process_group()
 
