@@ -137,3 +137,31 @@ def test_output_region_measure(ctx, speech, start, duration):
         assert abs(last[-1].r128_M - elast[-1]["M"]) < 0.0011 and abs(last[-1].r128_true_peak - elast[-1]["true_peak"]) < 0.0011
     ov = [m for m in got["meta"] if not math.isnan(m.astats_overall_RMS_level)]
     assert len(ov) == 1 and all(math.isnan(v) for v in ov[0].astats)         # measure_perchannel=0: Overall keys only
+
+
+def test_concurrent_contexts(ctx):
+    """SURVEY 8b threading contract: a jt_ctx is single-threaded, distinct contexts run concurrently from distinct threads
+    (one per worker goroutine, cmd/jivetalking/pool.go:122-153 / CloneForWorker filters.go:368-373).  Four workers, own
+    context and stream each, same file: every result equals the serial one bit for bit."""
+    import threading
+    xs = [synth.speech_like(20.0, 48000, seed=100 + i) for i in range(2)]
+    serial = [ctx.process_audio(x, 48000) for x in xs]
+    results, errors = {}, []
+
+    def worker(k):
+        try:
+            with gpudsp.Context(0) as c:
+                for rep in range(2):
+                    pcm, res = c.process_audio(xs[k % 2], 48000)
+                    results[(k, rep)] = (pcm, res.final.input_i, res.final.input_tp, res.n_out)
+        except Exception as e:          # noqa: BLE001
+            errors.append(repr(e))
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for (k, rep), (pcm, i, tp, n) in results.items():
+        spcm, sres = serial[k % 2]
+        assert np.array_equal(pcm, spcm) and i == sres.final.input_i and tp == sres.final.input_tp and n == sres.n_out
