@@ -51,6 +51,10 @@ struct JtError { int code; std::string msg; };
 #define JT_CUDA(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) \
     JT_THROW(JT_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #x, cudaGetErrorString(_e)); } while (0)
 
+// Opt a kernel in to `bytes` of dynamic shared memory.  The attribute belongs to the function, not to a context: it is only
+// ever RAISED (process-wide, per device, under a lock), so a launch that needs less is always legal and two worker
+// threads launching the same kernel with different sizes cannot lower it under each other (SURVEY 8b threading contract).
+void jt_smem_optin(const void *kernel, size_t bytes);
 void *jt_dalloc_bytes(jt_ctx *c, size_t bytes);
 template <class T> static inline T *jt_dalloc(jt_ctx *c, size_t n) { return (T *)jt_dalloc_bytes(c, (n ? n : 1) * sizeof(T)); }
 void jt_release_all(jt_ctx *c);

@@ -384,3 +384,17 @@ Sig jt_pad_zero(jt_ctx *c, const Sig &in, int64_t n_total)
     JT_CUDA(cudaMemsetAsync((char *)o.d + (size_t)in.n * b, 0, (size_t)(n_total - in.n) * b, c->stream));
     return o;
 }
+
+#include <mutex>
+void jt_smem_optin(const void *kernel, size_t bytes)
+{
+    static std::mutex mu;
+    static std::map<std::pair<int, const void *>, size_t> granted;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> g(mu);
+    size_t &have = granted[{dev, kernel}];
+    if (bytes <= have) return;
+    JT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    have = bytes;
+}

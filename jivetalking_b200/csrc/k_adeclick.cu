@@ -348,11 +348,11 @@ Sig jt_adeclick(jt_ctx *c, const Sig &in, double w_ms, double overlap_pct, doubl
     // the windows pass through except where clicks are repaired: out = in, then E overwrites
     JT_CUDA(cudaMemcpyAsync(o.d, in.d, sizeof(double) * (size_t)in.n, cudaMemcpyDeviceToDevice, c->stream));
     const size_t smemA = sizeof(double) * K.W, smemC = sizeof(double) * (K.W + K.bw);
-    JT_CUDA(cudaFuncSetAttribute(k_dc_autocorr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA));
-    JT_CUDA(cudaFuncSetAttribute(k_dc_detect, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC));
+    jt_smem_optin((const void *)k_dc_autocorr, (size_t)(smemA));
+    jt_smem_optin((const void *)k_dc_detect, (size_t)(smemC));
     const size_t per_warp = ((size_t)K.bw * K.bw + 3 * (size_t)K.bw + (size_t)((K.nwords + 1) / 2)) * sizeof(double);
     const size_t smemE = per_warp * DC_WARPS;
-    JT_CUDA(cudaFuncSetAttribute(k_dc_interp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemE));
+    jt_smem_optin((const void *)k_dc_interp, (size_t)(smemE));
     int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (227 * 1024) / (smemE + 4096 + 1024)));
     int gridE = (int)std::min<int64_t>((nw + DC_WARPS - 1) / DC_WARPS, (int64_t)c->num_sms * per_sm);
     if (gridE < 1) gridE = 1;

@@ -430,12 +430,12 @@ Sig jt_afftdn(jt_ctx *c, const Sig &in, const AfftdnParams &P, const AfftdnCarry
     float *d_frames = jt_dalloc<float>(c, (size_t)n_hops * K.W);
     double *d_cand = jt_dalloc<double>(c, (size_t)n_hops * 2), *d_pre = jt_dalloc<double>(c, n_hops), *d_post = jt_dalloc<double>(c, n_hops);
     const size_t smem_fft = sizeof(float2) * 3 * (size_t)K.FL;
-    JT_CUDA(cudaFuncSetAttribute(k_afftdn_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fft));
-    JT_CUDA(cudaFuncSetAttribute(k_afftdn_synth, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fft));
+    jt_smem_optin((const void *)k_afftdn_fwd, (size_t)(smem_fft));
+    jt_smem_optin((const void *)k_afftdn_synth, (size_t)(smem_fft));
     const int warm = 128;                             // 0.39^128, 0.78^128: both recursions have forgotten their start
     const int chunk_gain = 768, chunk_band = 256;
     const size_t smem_band = sizeof(double) * ((size_t)(chunk_band + warm) * nb + (size_t)nb * nb);
-    JT_CUDA(cudaFuncSetAttribute(k_afftdn_bandrec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_band));
+    jt_smem_optin((const void *)k_afftdn_bandrec, (size_t)(smem_band));
     const int64_t n_pairs = (n_hops + 1) / 2;
     const int fft_per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / (smem_fft + 1024)));
     const int grid_fft = (int)std::min<int64_t>(n_pairs, (int64_t)c->num_sms * fft_per_sm * 4);

@@ -163,7 +163,7 @@ Sig jt_alimiter(jt_ctx *c, const Sig &in, const LimiterParams &p)
     const int64_t lanes = (in.n + seg - 1) / seg;
     const double level = p.auto_level ? 1 / p.limit : 1;
     const size_t smem = 2 * (2 * LimIn::WARP_BYTES + LimOut::WARP_BYTES);
-    JT_CUDA(cudaFuncSetAttribute(k_alimiter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    jt_smem_optin((const void *)k_alimiter, (size_t)(smem));
     JtLaunch L(c, "alimiter");
     k_alimiter<<<(int)((lanes + 63) / 64), 64, smem, c->stream>>>((const double *)in.d, (double *)o.d, in.n, seg, warm, in.rate, bs,
                                                                     p.limit, release, p.level_in, p.level_out, level, p.asc);

@@ -182,7 +182,7 @@ Sig jt_anlmdn(jt_ctx *c, const Sig &in, double strength, double patch_s, double 
     const float smooth = fminf(m, (float)(1 << 20) / lut_scale);
     const int64_t n_hops = (in.n + H - 1) / H;
     const size_t smem = sizeof(float) * (N + 128);
-    JT_CUDA(cudaFuncSetAttribute(k_anlmdn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+    jt_smem_optin((const void *)k_anlmdn, (size_t)(std::max<size_t>(smem, 1024)));
     const int grid = jt_grid_for(n_hops, 1, c->num_sms, 64);
     JtLaunch L(c, "anlmdn");
     NlmK P; P.sw = sw; P.smooth = smooth; P.lut_scale = lut_scale; P.inv_lut_scale = 1.f / lut_scale;

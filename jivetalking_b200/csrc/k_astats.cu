@@ -381,8 +381,8 @@ static void astats_launch_t(jt_ctx *c, const Sig &in, int64_t n, AstatsPending &
         double *d_fin = jt_dalloc<double>(c, nb), *d_carry = jt_dalloc<double>(c, nb);
         JtLaunch L(c, "astats:rms_scan", 3);
         const size_t smemC = 2 * LaneStage<T, AsRow<T>::R, 2>::WARP_BYTES;
-        JT_CUDA(cudaFuncSetAttribute(k_astats_c1<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC));
-        JT_CUDA(cudaFuncSetAttribute(k_astats_c2<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC));
+        jt_smem_optin((const void *)k_astats_c1<T>, (size_t)(smemC));
+        jt_smem_optin((const void *)k_astats_c2<T>, (size_t)(smemC));
         k_astats_c1<T><<<(int)((nb + 63) / 64), 64, smemC, c->stream>>>(xc, nc, mult, d_fin);
         k_astats_carry<<<1, 1024, 0, c->stream>>>(d_fin, d_carry, nb, pow(mult, (double)BS));
         k_astats_c2<T><<<(int)((nb + 63) / 64), 64, smemC, c->stream>>>(xc, nc, mult, d_carry, track_from, d_mm);
@@ -396,7 +396,7 @@ static void astats_launch_t(jt_ctx *c, const Sig &in, int64_t n, AstatsPending &
         float *d_bmin = jt_dalloc<float>(c, nbt); unsigned *d_bcnt = jt_dalloc<unsigned>(c, nbt);
         const size_t smemD = sizeof(float) * (2 * (size_t)tc + 1);
         if (smemD > 200 * 1024) JT_THROW(JT_ERR_UNSUPPORTED, "astats at %d Hz (50 ms window of %d samples)", in.rate, tc);
-        JT_CUDA(cudaFuncSetAttribute(k_astats_nf<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemD));
+        jt_smem_optin((const void *)k_astats_nf<T>, (size_t)(smemD));
         JtLaunch L(c, "astats:noise_floor", 2);
         k_astats_nf<T><<<jt_grid_for(nbt, 1, c->num_sms, 32), AS_NF_THREADS, smemD, c->stream>>>(xn, nn, tc, d_bmin, d_bcnt);
         k_astats_nf_reduce<<<1, 1024, 0, c->stream>>>(d_bmin, d_bcnt, nbt, d_nf, d_counts + 4);

@@ -103,7 +103,7 @@ static double *run_envelope(jt_ctx *c, const Sig &in, double attack_ms, double r
     const int64_t lanes = (in.n + seg - 1) / seg;
     JtLaunch L(c, "envelope_follower");
     const size_t smem = (ENV_THREADS / 32) * (EnvIn::WARP_BYTES + EnvOut::WARP_BYTES);
-    JT_CUDA(cudaFuncSetAttribute(k_envelope, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    jt_smem_optin((const void *)k_envelope, (size_t)(smem));
     k_envelope<<<(int)((lanes + ENV_THREADS - 1) / ENV_THREADS), ENV_THREADS, smem, c->stream>>>((const double *)in.d, env, in.n, seg, (int)warm, ac, rc, rms);
     return env;
 }

@@ -159,7 +159,7 @@ static void run_ticks(jt_ctx *c, const Sig &in, int tick, int64_t n_ticks_total,
     JtLaunch L(c, in.rate >= 176400 ? "r128_kweight_ticks:192k" : "r128_kweight_ticks");
 #define R128_LAUNCH(T) do { \
         const size_t smem = 2 * LaneStage<T, 512 / (int)sizeof(T), 2>::WARP_BYTES; \
-        JT_CUDA(cudaFuncSetAttribute(k_r128_ticks<T, STRUCT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        jt_smem_optin((const void *)k_r128_ticks<T, STRUCT>, (size_t)(smem)); \
         k_r128_ticks<T, STRUCT><<<grid, 64, smem, c->stream>>>((const T *)in.d, in.n, tick, n_ticks_total, G, WU, kw, d_pow, d_peak); } while (0)
     if (in.fmt == JT_FMT_S16) R128_LAUNCH(int16_t);
     else if (in.fmt == JT_FMT_FLT) R128_LAUNCH(float);

@@ -224,7 +224,7 @@ void jt_aspectralstats_launch(jt_ctx *c, const Sig &in0, int win, const std::vec
     float *d_rows = jt_dalloc<float>(c, (size_t)n_items * JT_SP_COUNT);
     const int grid = jt_grid_for((n_items + 1) / 2, 1, c->num_sms, 8);
     const size_t smem_sp = sizeof(float2) * 3 * (size_t)win + sizeof(float) * (win / 2);
-    JT_CUDA(cudaFuncSetAttribute(k_spectral, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_sp));
+    jt_smem_optin((const void *)k_spectral, (size_t)(smem_sp));
     {
         JtLaunch L(c, "aspectralstats", 2);
         k_spectral<<<grid, SP_THREADS, smem_sp, c->stream>>>((const float *)in.d, in.n, win, in.rate, n_items, d_items, d_tw, d_lut, d_mags, d_rows);

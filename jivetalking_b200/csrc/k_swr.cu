@@ -513,7 +513,7 @@ static void launch_phase_f64(jt_ctx *c, const Sig &in, const SwrPlan &p, int64_t
     const size_t smem = sizeof(double) * ((size_t)span + (MODE == SWR_MODE_STORE ? 2 * (size_t)pc : 0)) + 16;
     const int grid = jt_grid_for((n_periods + qc - 1) / qc, 1, c->num_sms, 8);
 #define PHASE_LAUNCH(LV, NTV) do { auto kfn = k_swr_phase_f64<TIN, LV, MODE, NTV>; \
-        JT_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        jt_smem_optin((const void *)kfn, (size_t)(smem)); \
         kfn<<<grid, NTV, smem, c->stream>>>((const TIN *)in.d, in.n, n_periods, n_out, pc, div, qc, d_bank, out, tick_max, tick, n_ticks); } while (0)
     if (pc <= 160) { if (L == 32) PHASE_LAUNCH(32, 160); else if (L == 36) PHASE_LAUNCH(36, 160); else PHASE_LAUNCH(72, 160); }
     else { if (L == 32) PHASE_LAUNCH(32, 640); else if (L == 36) PHASE_LAUNCH(36, 640); else PHASE_LAUNCH(72, 640); }
@@ -554,7 +554,7 @@ static void launch_slot_f32(jt_ctx *c, const Sig &in, const SwrPlan &p, int64_t 
     const size_t smem = sizeof(float) * (((size_t)span + 3) / 4 * 4 + (size_t)QB * pc) + 16;
     const int grid = jt_grid_for((n_periods + qc - 1) / qc, 1, c->num_sms, 8);
 #define SLOT_LAUNCH(LV, RV) do { auto kfn = k_swr_slot_f32<TIN, TOUT, LV, RV, QB>; \
-        JT_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        jt_smem_optin((const void *)kfn, (size_t)(smem)); \
         kfn<<<grid, 160, smem, c->stream>>>((const TIN *)in.d, in.n, n_periods, n_out, pc, div, nslots, qc, d_bank, out); } while (0)
     if (up) SLOT_LAUNCH(32, 5);
     else if (L == 36) SLOT_LAUNCH(36, 1);
@@ -576,11 +576,11 @@ static void launch_qlane_f64(jt_ctx *c, const Sig &in, const SwrPlan &p, int64_t
     const int grid = jt_grid_for((n_periods + 63) / 64, 1, c->num_sms, 8);
     if (up) {
         auto kfn = k_swr_qlane_f64<TIN, MODE, 5>;
-        JT_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        jt_smem_optin((const void *)kfn, (size_t)(smem));
         kfn<<<grid, 256, smem, c->stream>>>((const TIN *)in.d, in.n, n_periods, n_out, pc, L, div, nslots, d_bank, out, tick_max, tick, n_ticks, span);
     } else {
         auto kfn = k_swr_qlane_f64<TIN, MODE, 1>;
-        JT_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        jt_smem_optin((const void *)kfn, (size_t)(smem));
         kfn<<<grid, 256, smem, c->stream>>>((const TIN *)in.d, in.n, n_periods, n_out, pc, L, div, nslots, d_bank, out, tick_max, tick, n_ticks, span);
     }
 }
@@ -614,7 +614,7 @@ static void launch_generic(jt_ctx *c, const Sig &in, const SwrPlan &p, int64_t n
     const int span = 32 * p.div + p.filter_length + p.div;
     const size_t smem = (size_t)(span + (span >> 5) + 2) * sizeof(TW);
     auto kfn = k_swr_generic<TIN, TW, MODE>;
-    JT_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    jt_smem_optin((const void *)kfn, (size_t)(smem));
     const int grid = jt_grid_for((n_periods + 31) / 32, 1, c->num_sms, 8);
     kfn<<<grid, 256, smem, c->stream>>>((const TIN *)in.d, in.n, n_periods, n_out, p.phase_count, p.filter_length, p.div,
                                           d_bank, out, tick_max, tick, n_ticks, span);
