@@ -33,6 +33,8 @@ def main():
     ap.add_argument("--channels", type=int, default=2)
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--check", action="store_true", help="rank 0 also runs the whole stream on one GPU and compares")
+    ap.add_argument("--adaptive", action="store_true",
+                    help="conversational input; every rank derives the Pass-2 spec from the sharded Pass 1 (detector + AdaptConfig)")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -41,7 +43,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
-    seg = synth.speech_like(600.0, a.rate, seed=12345)
+    seg = synth.podcast_like(600.0, a.rate, seed=12345) if a.adaptive else synth.speech_like(600.0, a.rate, seed=12345)
     n = int(a.hours * 3600 * a.rate)
     # the stream lives in PINNED host memory (what a decoder thread would fill): windows go to the GPU at PCIe rate
     pcm = torch.empty(n * a.channels, dtype=torch.float32, pin_memory=True).numpy()
@@ -59,9 +61,13 @@ def main():
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             phases = {}
-            m1, iv = shard.analyse_stream_sharded(ctx, pcm, a.rate, a.channels, device=dev)
-            phases["pass1"] = time.perf_counter() - t0
-            out, r = shard.process_stream_sharded(ctx, comm, pcm, a.rate, a.channels, timings=phases)
+            if a.adaptive:
+                out, r = shard.process_stream_sharded_adaptive(ctx, comm, pcm, a.rate, a.channels, timings=phases, device=dev)
+                m1, iv = r["input"], r["intervals"]
+            else:
+                m1, iv = shard.analyse_stream_sharded(ctx, pcm, a.rate, a.channels, device=dev)
+                phases["pass1"] = time.perf_counter() - t0
+                out, r = shard.process_stream_sharded(ctx, comm, pcm, a.rate, a.channels, timings=phases)
             torch.cuda.synchronize()
             if world > 1:
                 dist.barrier()
@@ -75,12 +81,18 @@ def main():
         if a.check and rank == 0:
             ctx.process_audio(pcm[: 10 * a.rate * a.channels], a.rate, a.channels)
             t0 = time.perf_counter()
-            pcm1, res1 = ctx.process_audio(pcm, a.rate, a.channels)
+            if a.adaptive:
+                from jivetalking_b200 import adapt
+                pcm1, res1, an1 = adapt.process_audio_adaptive(ctx, pcm, a.rate, a.channels)
+            else:
+                pcm1, res1 = ctx.process_audio(pcm, a.rate, a.channels)
             single = time.perf_counter() - t0
             d = (out.astype(np.int32) - pcm1.astype(np.int32)) / 32768.0
             check = {"pcm_rms_diff": float(np.sqrt(np.mean(d * d))), "n_out_equal": bool(len(out) == len(pcm1)),
                      "d_final_lufs": r["final"].input_i - res1.final.input_i, "d_final_dbtp": r["final"].input_tp - res1.final.input_tp,
                      "d_final_lra": r["final"].input_lra - res1.final.input_lra, "d_input_lufs": m1.input_i - res1.input.input_i, "single_gpu_jt_process_audio_seconds": single}
+            if a.adaptive:
+                check["spec_equal"] = bool(r["specs"][0] == an1.pass2_spec.decode())
     if rank == 0:
         best = min(times)
         print(json.dumps({
@@ -89,7 +101,8 @@ def main():
             "n_gpus": world, "seconds_per_stream": best, "rank0_phase_seconds_last_rep": {k: round(v, 4) for k, v in phases.items()}, "all_seconds": times,
             "realtime_x": a.hours * 3600 / best, "frames_per_s": n / best,
             "input_lufs": m1.input_i, "input_dbtp": m1.input_tp, "final_lufs": r["final"].input_i, "final_dbtp": r["final"].input_tp,
-            "final_lra": r["final"].input_lra, "n_out": int(len(out)), "pass3_input_i": r["pass3"].input_i, "check": check}))
+            "final_lra": r["final"].input_lra, "n_out": int(len(out)), "pass3_input_i": r["pass3"].input_i, "check": check,
+            "adaptive": bool(a.adaptive), "pass2_spec": r["specs"][0] if a.adaptive else "DefaultFilterConfig"}))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
