@@ -301,6 +301,26 @@ def main():
                     "pass2_spec": an_a.pass2_spec.decode(), "speech_profile": bool(va.has_speech_profile),
                     "noise_profile": bool(va.has_noise_profile), "voice_activated": bool(va.voice_activated),
                     "noise_floor": va.floor, "final_lufs": res_a.final.input_i, "final_dbtp": res_a.final.input_tp}
+    # ---- the result's container: FLAC stream of the s16 44.1 kHz output, device resident -------------------
+    flac = None
+    if rank == 0 and not args.no_adaptive:
+        res_f = step_dev()
+        n_out = int(res_f.n_out)
+        cap_b = int(gpudsp.lib().jt_flac_max_bytes(n_out, 4096))
+        d_flac = torch.empty(cap_b, dtype=torch.uint8, device="cuda")
+        ctx.flac_encode_ptr(d_out.data_ptr(), n_out, 44100, 4096, d_flac.data_ptr(), cap_b, True)
+        torch.cuda.synchronize()
+        ev0.record(lib_stream)
+        for _ in range(args.steps):
+            nbytes = ctx.flac_encode_ptr(d_out.data_ptr(), n_out, 44100, 4096, d_flac.data_ptr(), cap_b, True)
+        ev1.record(lib_stream)
+        torch.cuda.synchronize()
+        t_fl = ev0.elapsed_time(ev1) * 1e-3 / args.steps
+        flac = {"ms_per_step": 1e3 * t_fl, "realtime_x": (n_out / 44100) / t_fl, "samples_per_s": n_out / t_fl,
+                "bytes": int(nbytes), "ratio": nbytes / (2.0 * n_out),
+                "algorithmic_GBps": (2.0 * n_out + nbytes) / t_fl / 1e9,
+                "entry": "jt_flac_encode_dev (4096-sample frames, fixed predictors + partitioned Rice; encoder.go:92-101)"}
+        del d_flac
     barrier()
 
     if world > 1:
@@ -355,6 +375,8 @@ def main():
     }
     if adaptive is not None:
         line["adaptive"] = adaptive
+    if flac is not None:
+        line["flac_encode"] = flac
     if not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         sec = 150.0                           # ~20 s of scalar CPU work per core (the oracle chain runs ~8x realtime/core)

@@ -424,6 +424,18 @@ int jt_process_audio_adaptive_dev(jt_ctx *ctx, const void *d_pcm_in, int64_t n_f
                         const jt_filter_config *base, int16_t *d_pcm_out, int64_t pcm_out_cap,
                         jt_process_result *res, jt_analysis *analysis);
 
+/* ---- FLAC container of the chain's output ------------------------------------------------------------------
+ * The reference hands its s16 mono 44.1 kHz result to libavcodec's FLAC encoder in 4096-sample frames
+ * (internal/processor/encoder.go:92-101, processor.go:379-384).  jt_flac_encode writes a complete FLAC stream (RFC 9639:
+ * "fLaC", STREAMINFO, fixed-block-size frames with CONSTANT / FIXED-predictor + partitioned Rice / VERBATIM subframes,
+ * CRC-8 / CRC-16) of n mono s16 samples: bit-exact audio for any FLAC decoder, not the byte sequence libavcodec would emit
+ * (its LPC search is not reproduced).  block_size 16..4096 (the reference uses 4096); MD5 is left "unknown" (zero). */
+int64_t jt_flac_max_bytes(int64_t n_samples, int block_size);
+int jt_flac_encode(jt_ctx *ctx, const int16_t *pcm, int64_t n_samples, int sample_rate, int block_size,
+                   void *out, int64_t out_cap, int64_t *n_bytes);
+int jt_flac_encode_dev(jt_ctx *ctx, const int16_t *d_pcm, int64_t n_samples, int sample_rate, int block_size,
+                   void *d_out, int64_t out_cap, int64_t *n_bytes);
+
 /* the cudaStream_t (as void *) every kernel and copy of this context is issued on, so a caller can order its own
  * device work against it or bracket calls with CUDA events */
 void   *jt_cuda_stream(const jt_ctx *ctx);

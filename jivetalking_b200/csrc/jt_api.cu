@@ -1270,3 +1270,33 @@ extern "C" int jt_process_audio_adaptive_dev(jt_ctx *c, const void *d_in, int64_
         process_adaptive_device(c, d_in, n_frames, rate, channels, fmt, base, d_out, true, cap, res, analysis);
     });
 }
+
+// ---------------------------------------------------------------------------------------
+// FLAC container of the chain's output (Encoder: internal/processor/encoder.go:92-101)
+// ---------------------------------------------------------------------------------------
+extern "C" int64_t jt_flac_max_bytes(int64_t n_samples, int block_size)
+{
+    if (n_samples < 0 || block_size < 16) return JT_ERR_INVALID_ARG;
+    return jt_flac_bound(n_samples, block_size);
+}
+static int flac_common(jt_ctx *c, const int16_t *pcm, bool on_device, int64_t n, int rate, int block_size, void *out, int64_t cap, int64_t *n_bytes)
+{
+    return guarded(c, [&]() {
+        if ((!pcm && n > 0) || !out || n < 0) JT_THROW(JT_ERR_INVALID_ARG, "null argument");
+        const int16_t *d_in = on_device ? pcm : (const int16_t *)upload(c, pcm, (size_t)n * sizeof(int16_t));
+        int64_t total = 0;
+        void *d = jt_flac_encode_device(c, d_in, n, rate, block_size, &total);
+        if (n_bytes) *n_bytes = total;
+        if (total > cap) JT_THROW(JT_ERR_BUFFER, "out holds %lld bytes, the stream has %lld", (long long)cap, (long long)total);
+        if (on_device) JT_CUDA(cudaMemcpyAsync(out, d, (size_t)total, cudaMemcpyDeviceToDevice, c->stream));
+        else download(c, out, d, (size_t)total);
+    });
+}
+extern "C" int jt_flac_encode(jt_ctx *c, const int16_t *pcm, int64_t n, int rate, int block_size, void *out, int64_t cap, int64_t *n_bytes)
+{
+    return flac_common(c, pcm, false, n, rate, block_size, out, cap, n_bytes);
+}
+extern "C" int jt_flac_encode_dev(jt_ctx *c, const int16_t *d_pcm, int64_t n, int rate, int block_size, void *d_out, int64_t cap, int64_t *n_bytes)
+{
+    return flac_common(c, d_pcm, true, n, rate, block_size, d_out, cap, n_bytes);
+}

@@ -173,6 +173,10 @@ Sig  jt_biquad(jt_ctx *c, const Sig &in, const BiquadCoef &k, bool tdii, double 
 void jt_band_rms_batch(jt_ctx *c, const Sig &in, const double *lo, const double *hi, int n_bands,
                        double *rms_db, int32_t *found);
 
+// ---- k_flac.cu ------------------------------------------------------------------------------
+int64_t jt_flac_bound(int64_t n, int block_size);
+void *jt_flac_encode_device(jt_ctx *c, const int16_t *d_pcm, int64_t n, int rate, int block_size, int64_t *n_bytes);
+
 // ---- k_anlmdn.cu / k_afftdn.cu ------------------------------------------------------------
 Sig  jt_anlmdn(jt_ctx *c, const Sig &in_flt, double strength, double patch_s, double research_s, double smooth);
 struct AfftdnParams {

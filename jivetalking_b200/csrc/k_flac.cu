@@ -1,0 +1,338 @@
+// FLAC (RFC 9639) encoder for the chain's output: mono, 16 bit, fixed block size -- the container the reference writes its
+// result in (mono / 44.1 kHz / s16 / 4096-sample frames through libavcodec's encoder: internal/processor/encoder.go:92-101,
+// processor.go:379-384; SURVEY 8f-3: at > 10 000 x realtime the CPU encoder, a few hundred x realtime per core, is the next
+// bottleneck of a drop-in).
+//
+// Frames are independent, so ONE WARP encodes one frame: samples staged in shared memory (8 KB), the frame built in a
+// shared-memory byte buffer with word-wide atomicOr (lanes own disjoint bit ranges; only boundary words are shared), then
+// stored with coalesced word copies into a fixed-stride staging slot.  Decisions (identical, integer for integer, to the
+// sequential oracle oracle/orc_flac.c, so the two streams are compared byte for byte):
+//   CONSTANT subframe when all samples are equal; else the FIXED predictor order 0..4 with the smallest sum |residual|;
+//   Rice partition order 0..6 (block size a multiple of 64), each partition's parameter as libavcodec's flacenc picks it
+//   (k = log2((sum - n/2) / n), max 14), the order with the fewest exact bits; VERBATIM when that is not smaller.
+// CRC-16 of a frame is computed in parallel: every lane takes 1/32 of the (right-aligned) frame from a zero state, and the
+// partial CRCs are chained with the matrix of "append L zero bytes" (CRCs are linear over GF(2)).
+// A host scan of the frame sizes gives the offsets; a second kernel packs the frames behind the 42-byte stream header.
+// HBM traffic: 2 B/sample read + ~1 B/sample staged and re-read + ~1 B/sample written.
+#include "jt_internal.h"
+#include "jt_device.cuh"
+#include <cstdio>
+#include <cstring>
+
+namespace {
+constexpr int FL_WARPS = 4;                              // frames per CTA
+constexpr int FL_MAX_BS = 4096;
+constexpr int FL_FRAME_CAP = 16 + 2 * FL_MAX_BS + 2 + 2; // header + verbatim subframe + CRC-16, multiple of 4 (8212)
+constexpr int FL_FRAME_WORDS = FL_FRAME_CAP / 4;
+constexpr int FL_MAX_PORDER = 6;
+static_assert(FL_FRAME_CAP % 4 == 0, "frame slots are copied as words");
+
+struct FlWarp {                                          // per-warp shared memory
+    int16_t x[FL_MAX_BS];
+    uint32_t frame[FL_FRAME_WORDS];
+    uint32_t cell[64];                                   // sum of folded residuals per 1/64 of the block
+    uint16_t col[16];                                    // CRC-16 "append L zero bytes" operator, one column per state bit
+};
+
+__device__ __forceinline__ uint32_t fl_fold(int32_t r) { return ((uint32_t)r << 1) ^ (uint32_t)(r >> 31); }
+
+template <int ORDER> __device__ __forceinline__ int32_t fl_res(const int16_t *x, int i)
+{
+    if (ORDER == 0) return x[i];
+    if (ORDER == 1) return (int32_t)x[i] - x[i - 1];
+    if (ORDER == 2) return (int32_t)x[i] - 2 * x[i - 1] + x[i - 2];
+    if (ORDER == 3) return (int32_t)x[i] - 3 * x[i - 1] + 3 * x[i - 2] - x[i - 3];
+    return (int32_t)x[i] - 4 * x[i - 1] + 6 * x[i - 2] - 4 * x[i - 3] + x[i - 4];
+}
+__device__ __forceinline__ int32_t fl_res_o(const int16_t *x, int i, int order)
+{
+    switch (order) {
+    case 0: return fl_res<0>(x, i);
+    case 1: return fl_res<1>(x, i);
+    case 2: return fl_res<2>(x, i);
+    case 3: return fl_res<3>(x, i);
+    default: return fl_res<4>(x, i);
+    }
+}
+
+__device__ __forceinline__ int fl_optimal_param(unsigned long long sum, int n)      // flacenc.c find_optimal_param
+{
+    if (sum <= (unsigned long long)(n >> 1)) return 0;
+    unsigned long long q = (sum - (unsigned long long)(n >> 1)) / (unsigned long long)n;
+    if (q > 0x7fffffffull) q = 0x7fffffffull;
+    const int k = q ? 31 - __clz((unsigned)q) : 0;     // av_log2(0) == 0
+    return k > 14 ? 14 : k;
+}
+
+__device__ __forceinline__ unsigned long long fl_warp_sum_u64(unsigned long long v)
+{
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// OR `n` bits (n + (bit & 7) <= 32) of v, MSB first, at bit position `bit` of a byte stream held in little-endian words
+__device__ __forceinline__ void fl_put(uint32_t *buf, int bit, int n, uint32_t v)
+{
+    const int B = bit >> 3, o = bit & 7;
+    const uint32_t w = v << (32 - o - n);                // big-endian window over bytes B .. B+3
+    const uint32_t le = __byte_perm(w, 0, 0x0123);       // the same four bytes as a little-endian word
+    const int A = B >> 2, sh = (B & 3) * 8;
+    atomicOr(&buf[A], le << sh);
+    if (sh) { const uint32_t hi = le >> (32 - sh); if (hi) atomicOr(&buf[A + 1], hi); }
+}
+
+__device__ __forceinline__ uint16_t fl_crc16_byte(uint16_t c, uint32_t byte)
+{
+    c ^= (uint16_t)(byte << 8);
+#pragma unroll
+    for (int b = 0; b < 8; b++) c = (uint16_t)((c & 0x8000) ? (c << 1) ^ 0x8005 : (c << 1));
+    return c;
+}
+
+__device__ __forceinline__ int fl_rate_code(int rate)
+{
+    switch (rate) {
+    case 88200: return 1; case 176400: return 2; case 192000: return 3; case 8000: return 4; case 16000: return 5; case 22050: return 6;
+    case 24000: return 7; case 32000: return 8; case 44100: return 9; case 48000: return 10; case 96000: return 11;
+    }
+    return 0;
+}
+
+__global__ void __launch_bounds__(FL_WARPS * 32)
+k_flac_frames(const int16_t *__restrict__ pcm, int64_t n, int block_size, int rate, int64_t n_frames,
+              uint32_t *__restrict__ stage, uint32_t *__restrict__ sizes)
+{
+    extern __shared__ __align__(16) unsigned char fl_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    FlWarp &S = reinterpret_cast<FlWarp *>(fl_smem)[warp];
+    for (int64_t f = (int64_t)blockIdx.x * FL_WARPS + warp; f < n_frames; f += (int64_t)gridDim.x * FL_WARPS) {
+        const int64_t s0 = f * block_size;
+        const int bs = (int)min((int64_t)block_size, n - s0);
+        // ---- stage samples, clear the frame ----
+        for (int i = lane; i < bs; i += 32) S.x[i] = pcm[s0 + i];
+        for (int i = lane; i < FL_FRAME_WORDS; i += 32) S.frame[i] = 0;
+        __syncwarp();
+        const int16_t *x = S.x;
+        uint8_t *fb = reinterpret_cast<uint8_t *>(S.frame);
+        // ---- frame header (lane 0) ----
+        int hdr_bytes = 0;
+        if (lane == 0) {
+            const int bs_code = bs == 4096 ? 12 : 7;
+            fb[0] = 0xFF; fb[1] = 0xF8; fb[2] = (uint8_t)((bs_code << 4) | fl_rate_code(rate)); fb[3] = 0x08;    // mono, 16 bit
+            int p = 4; const unsigned long long v = (unsigned long long)f;
+            if (v < 0x80) fb[p++] = (uint8_t)v;
+            else {
+                const int nb = v < 0x800 ? 2 : v < 0x10000 ? 3 : v < 0x200000 ? 4 : v < 0x4000000 ? 5 : v < 0x80000000ull ? 6 : 7;
+                const uint8_t lead[8] = {0, 0, 0xC0, 0xE0, 0xF0, 0xF8, 0xFC, 0xFE};
+                unsigned long long t = v;
+                for (int i = nb - 1; i > 0; i--) { fb[p + i] = (uint8_t)(0x80 | (t & 0x3F)); t >>= 6; }
+                fb[p] = (uint8_t)(lead[nb] | t);
+                p += nb;
+            }
+            if (bs_code == 7) { fb[p++] = (uint8_t)((bs - 1) >> 8); fb[p++] = (uint8_t)(bs - 1); }
+            uint8_t c = 0;
+            for (int i = 0; i < p; i++) { c ^= fb[i]; for (int b = 0; b < 8; b++) c = (uint8_t)((c & 0x80) ? (c << 1) ^ 0x07 : (c << 1)); }
+            fb[p++] = c;
+            hdr_bytes = p;
+        }
+        hdr_bytes = __shfl_sync(0xffffffffu, hdr_bytes, 0);
+        __syncwarp();
+        const int sub0 = hdr_bytes * 8;                   // first bit of the subframe
+        // ---- lane ranges: [lo, mid) and [mid, hi) are the lane's two cells when the block divides into 64 ----
+        const bool cells = (bs % 64) == 0;
+        const int chunk = (bs + 31) / 32;
+        const int lo = min(bs, lane * chunk), hi = min(bs, lo + chunk);
+        const int mid = cells ? lo + chunk / 2 : hi;
+        // ---- constant? fixed-order errors ----
+        bool equal = true;
+        unsigned long long e0 = 0, e1 = 0, e2 = 0, e3 = 0, e4 = 0;
+        for (int i = lo; i < hi; i++) {
+            equal = equal && (x[i] == x[0]);
+            const int32_t r0 = fl_res<0>(x, i);
+            e0 += (unsigned)abs(r0);
+            if (i >= 1) e1 += (unsigned)abs(fl_res<1>(x, i));
+            if (i >= 2) e2 += (unsigned)abs(fl_res<2>(x, i));
+            if (i >= 3) e3 += (unsigned)abs(fl_res<3>(x, i));
+            if (i >= 4) e4 += (unsigned)abs(fl_res<4>(x, i));
+        }
+        const bool constant = __all_sync(0xffffffffu, equal);
+        int total_bits;                                   // bits of header + subframe before padding
+        if (constant) {
+            if (lane == 0) { fl_put(S.frame, sub0, 8, 0x00); fl_put(S.frame, sub0 + 8, 16, (uint16_t)x[0]); }
+            total_bits = sub0 + 24;
+        } else {
+            e0 = fl_warp_sum_u64(e0); e1 = fl_warp_sum_u64(e1); e2 = fl_warp_sum_u64(e2); e3 = fl_warp_sum_u64(e3); e4 = fl_warp_sum_u64(e4);
+            int order = 0; unsigned long long best_err = e0;
+            if (bs > 1 && e1 < best_err) { best_err = e1; order = 1; }
+            if (bs > 2 && e2 < best_err) { best_err = e2; order = 2; }
+            if (bs > 3 && e3 < best_err) { best_err = e3; order = 3; }
+            if (bs > 4 && e4 < best_err) { best_err = e4; order = 4; }
+            // ---- per-cell sums of the folded residual ----
+            const int a0 = max(lo, order), a1 = max(mid, order);          // residual samples of the two cells: [a0, mid), [a1, hi)
+            uint32_t c0 = 0, c1 = 0;
+            for (int i = a0; i < mid; i++) c0 += fl_fold(fl_res_o(x, i, order));
+            for (int i = a1; i < hi; i++) c1 += fl_fold(fl_res_o(x, i, order));
+            S.cell[2 * lane] = c0; S.cell[2 * lane + 1] = c1;
+            __syncwarp();
+            int pmax = 0;
+            if (cells) { pmax = FL_MAX_PORDER; while (pmax > 0 && (bs >> pmax) <= order) pmax--; }
+            int best_p = 0, bk0 = 0, bk1 = 0; unsigned long long best_bits = ~0ull;
+            for (int p = 0; p <= pmax; p++) {
+                const int per = 64 >> p;                                  // cells per partition
+                const int psz = bs >> p;
+                int k0, k1;
+                {
+                    const int j = (2 * lane) / per;
+                    unsigned long long s = 0;
+                    for (int g = j * per; g < (j + 1) * per; g++) s += S.cell[g];
+                    k0 = fl_optimal_param(s, psz - (j == 0 ? order : 0));
+                }
+                {
+                    const int j = (2 * lane + 1) / per;
+                    unsigned long long s = 0;
+                    for (int g = j * per; g < (j + 1) * per; g++) s += S.cell[g];
+                    k1 = fl_optimal_param(s, psz - (j == 0 ? order : 0));
+                }
+                unsigned long long bits = 0;
+                for (int i = a0; i < mid; i++) bits += (fl_fold(fl_res_o(x, i, order)) >> k0) + (unsigned)(k0 + 1);
+                for (int i = a1; i < hi; i++) bits += (fl_fold(fl_res_o(x, i, order)) >> k1) + (unsigned)(k1 + 1);
+                bits = fl_warp_sum_u64(bits) + 4ull * (unsigned long long)(1 << p);
+                if (bits < best_bits) { best_bits = bits; best_p = p; bk0 = k0; bk1 = k1; }
+            }
+            const unsigned long long fixed_bits = 8ull + 16ull * (unsigned)order + 6ull + best_bits, verbatim_bits = 8ull + 16ull * (unsigned)bs;
+            if (fixed_bits >= verbatim_bits) {
+                if (lane == 0) fl_put(S.frame, sub0, 8, 0x02);
+                for (int i = lo; i < hi; i++) fl_put(S.frame, sub0 + 8 + 16 * i, 16, (uint16_t)x[i]);
+                total_bits = sub0 + 8 + 16 * bs;
+            } else {
+                const int per = 64 >> best_p;
+                // a cell opens a partition (4-bit parameter in front of it) when it is the partition's first cell
+                const bool open0 = cells ? ((2 * lane) % per) == 0 : lane == 0;
+                const bool open1 = cells ? ((2 * lane + 1) % per) == 0 : false;
+                unsigned lane_bits = (open0 ? 4u : 0u) + (open1 ? 4u : 0u);
+                for (int i = a0; i < mid; i++) lane_bits += (fl_fold(fl_res_o(x, i, order)) >> bk0) + (unsigned)(bk0 + 1);
+                for (int i = a1; i < hi; i++) lane_bits += (fl_fold(fl_res_o(x, i, order)) >> bk1) + (unsigned)(bk1 + 1);
+                unsigned incl = lane_bits;
+                for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+                const int base = sub0 + 8 + 16 * order + 6;
+                int pos = base + (int)(incl - lane_bits);
+                total_bits = base + (int)__shfl_sync(0xffffffffu, incl, 31);
+                if (lane == 0) {
+                    fl_put(S.frame, sub0, 8, (uint32_t)((0x08 | order) << 1));
+                    for (int i = 0; i < order; i++) fl_put(S.frame, sub0 + 8 + 16 * i, 16, (uint16_t)x[i]);
+                    fl_put(S.frame, sub0 + 8 + 16 * order, 6, (uint32_t)best_p);       // method 00 + partition order
+                }
+                if (open0) { fl_put(S.frame, pos, 4, (uint32_t)bk0); pos += 4; }
+                for (int i = a0; i < mid; i++) {
+                    const uint32_t u = fl_fold(fl_res_o(x, i, order));
+                    pos += (int)(u >> bk0);
+                    fl_put(S.frame, pos, bk0 + 1, (1u << bk0) | (u & ((1u << bk0) - 1)));          // the unary stop bit and the k low bits
+                    pos += bk0 + 1;
+                }
+                if (open1) { fl_put(S.frame, pos, 4, (uint32_t)bk1); pos += 4; }
+                for (int i = a1; i < hi; i++) {
+                    const uint32_t u = fl_fold(fl_res_o(x, i, order));
+                    pos += (int)(u >> bk1);
+                    fl_put(S.frame, pos, bk1 + 1, (1u << bk1) | (u & ((1u << bk1) - 1)));
+                    pos += bk1 + 1;
+                }
+            }
+        }
+        __syncwarp();
+        // ---- CRC-16 over the padded frame: lanes take 1/32 each of the right-aligned bytes, then chain ----
+        const int nb = (total_bits + 7) >> 3;
+        const int L = (nb + 31) / 32, Z = 32 * L - nb;
+        uint16_t part = 0;
+        for (int v = lane * L; v < (lane + 1) * L; v++) { const int r = v - Z; if (r >= 0) part = fl_crc16_byte(part, fb[r]); }
+        if (lane < 16) { uint16_t c = (uint16_t)(1u << lane); for (int i = 0; i < L; i++) c = fl_crc16_byte(c, 0); S.col[lane] = c; }
+        __syncwarp();
+        uint16_t crc = 0;
+        for (int l = 0; l < 32; l++) {
+            const uint16_t pl = (uint16_t)__shfl_sync(0xffffffffu, (unsigned)part, l);
+            uint16_t m = 0;
+            for (int b = 0; b < 16; b++) if ((crc >> b) & 1) m ^= S.col[b];
+            crc = m ^ pl;
+        }
+        if (lane == 0) { fb[nb] = (uint8_t)(crc >> 8); fb[nb + 1] = (uint8_t)crc; sizes[f] = (uint32_t)(nb + 2); }
+        __syncwarp();
+        uint32_t *dst = stage + (size_t)f * FL_FRAME_WORDS;
+        const int words = (nb + 2 + 3) >> 2;
+        for (int i = lane; i < words; i += 32) dst[i] = S.frame[i];
+        __syncwarp();
+    }
+}
+
+// pack the frames behind the stream header: one warp per frame, bytes (destinations are not word aligned)
+__global__ void k_flac_pack(const uint8_t *__restrict__ stage, const uint32_t *__restrict__ sizes, const unsigned long long *__restrict__ offsets,
+                            int64_t n_frames, uint8_t *__restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t wpb = blockDim.x >> 5;
+    for (int64_t f = (int64_t)blockIdx.x * wpb + (threadIdx.x >> 5); f < n_frames; f += (int64_t)gridDim.x * wpb) {
+        const uint8_t *src = stage + (size_t)f * FL_FRAME_CAP;
+        uint8_t *dst = out + offsets[f];
+        const int sz = (int)sizes[f];
+        for (int i = lane; i < sz; i += 32) dst[i] = src[i];
+    }
+}
+}  // namespace
+
+int64_t jt_flac_bound(int64_t n, int block_size)
+{
+    const int64_t frames = (n + block_size - 1) / block_size;
+    return 42 + frames * (16 + 2 * (int64_t)block_size + 2) + 64;
+}
+
+// Encodes n mono s16 samples at d_pcm; returns a device buffer with the stream and its length.
+void *jt_flac_encode_device(jt_ctx *c, const int16_t *d_pcm, int64_t n, int rate, int block_size, int64_t *n_bytes)
+{
+    if (block_size < 16 || block_size > FL_MAX_BS) JT_THROW(JT_ERR_UNSUPPORTED, "FLAC block size %d (16..%d)", block_size, FL_MAX_BS);
+    if (rate <= 0 || rate >= (1 << 20)) JT_THROW(JT_ERR_INVALID_ARG, "FLAC sample rate %d", rate);
+    const int64_t frames = (n + block_size - 1) / block_size;
+    uint8_t hdr[42]; memset(hdr, 0, sizeof(hdr));
+    uint32_t min_fs = 0, max_fs = 0;
+    uint8_t *d_out = nullptr;
+    int64_t total = 42;
+    if (frames > 0) {
+        uint32_t *d_stage = (uint32_t *)jt_dalloc_bytes(c, (size_t)frames * FL_FRAME_CAP);
+        uint32_t *d_sizes = jt_dalloc<uint32_t>(c, (size_t)frames);
+        const size_t smem = sizeof(FlWarp) * FL_WARPS;
+        jt_smem_optin((const void *)k_flac_frames, smem);
+        const int grid = (int)std::min<int64_t>((frames + FL_WARPS - 1) / FL_WARPS, (int64_t)c->num_sms * 12);
+        {
+            JtLaunch L(c, "flac:frames");
+            k_flac_frames<<<grid, FL_WARPS * 32, smem, c->stream>>>(d_pcm, n, block_size, rate, frames, d_stage, d_sizes);
+        }
+        uint32_t *h_sizes = jt_pinned<uint32_t>(c, (size_t)frames);
+        JT_CUDA(cudaMemcpyAsync(h_sizes, d_sizes, sizeof(uint32_t) * frames, cudaMemcpyDeviceToHost, c->stream));
+        JT_CUDA(cudaStreamSynchronize(c->stream));
+        unsigned long long *h_off = jt_pinned<unsigned long long>(c, (size_t)frames);
+        min_fs = 0xFFFFFF;
+        for (int64_t f = 0; f < frames; f++) {
+            h_off[f] = (unsigned long long)total; total += h_sizes[f];
+            min_fs = std::min(min_fs, h_sizes[f]); max_fs = std::max(max_fs, h_sizes[f]);
+        }
+        unsigned long long *d_off = jt_dalloc<unsigned long long>(c, (size_t)frames);
+        JT_CUDA(cudaMemcpyAsync(d_off, h_off, sizeof(unsigned long long) * frames, cudaMemcpyHostToDevice, c->stream));
+        d_out = (uint8_t *)jt_dalloc_bytes(c, (size_t)total + 16);
+        {
+            JtLaunch L(c, "flac:pack");
+            const int pgrid = (int)std::min<int64_t>((frames + 7) / 8, (int64_t)c->num_sms * 8);
+            k_flac_pack<<<pgrid, 256, 0, c->stream>>>((const uint8_t *)d_stage, d_sizes, d_off, frames, d_out);
+        }
+    } else d_out = (uint8_t *)jt_dalloc_bytes(c, 64);
+    // "fLaC" + STREAMINFO (last metadata block): block sizes, frame sizes, rate / channels / bits, sample count, MD5 unknown
+    memcpy(hdr, "fLaC", 4);
+    hdr[4] = 0x80; hdr[7] = 34;
+    hdr[8] = (uint8_t)(block_size >> 8); hdr[9] = (uint8_t)block_size; hdr[10] = hdr[8]; hdr[11] = hdr[9];
+    hdr[12] = (uint8_t)(min_fs >> 16); hdr[13] = (uint8_t)(min_fs >> 8); hdr[14] = (uint8_t)min_fs;
+    hdr[15] = (uint8_t)(max_fs >> 16); hdr[16] = (uint8_t)(max_fs >> 8); hdr[17] = (uint8_t)max_fs;
+    // 20 bits rate | 3 bits channels-1 (0) | 5 bits bps-1 (15) | 36 bits total samples
+    const unsigned long long v = ((unsigned long long)rate << 44) | (0ull << 41) | (15ull << 36) | ((unsigned long long)n & 0xFFFFFFFFFull);
+    for (int i = 0; i < 8; i++) hdr[18 + i] = (uint8_t)(v >> (56 - 8 * i));
+    uint8_t *h_hdr = jt_pinned<uint8_t>(c, 64);
+    memcpy(h_hdr, hdr, 42);
+    JT_CUDA(cudaMemcpyAsync(d_out, h_hdr, 42, cudaMemcpyHostToDevice, c->stream));
+    if (n_bytes) *n_bytes = total;
+    return d_out;
+}

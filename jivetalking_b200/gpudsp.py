@@ -146,6 +146,11 @@ def lib():
     L.jt_default_pass2_spec.argtypes = [C.c_char_p, C.c_size_t]
     L.jt_pass1_spec.argtypes = [C.c_char_p, C.c_size_t]
     L.jt_loudnorm_stats_json.argtypes = [C.POINTER(LoudnormStats), C.c_char_p, C.c_size_t]
+    L.jt_flac_max_bytes.restype = _I64
+    L.jt_flac_max_bytes.argtypes = [_I64, _INT]
+    fl = [_P, _P, _I64, _INT, _INT, _P, _I64, C.POINTER(_I64)]
+    L.jt_flac_encode.argtypes = fl
+    L.jt_flac_encode_dev.argtypes = fl
     L.jt_cuda_stream.restype = _P
     L.jt_cuda_stream.argtypes = [_P]
     L.jt_launch_count.restype = _I64
@@ -346,6 +351,21 @@ class Context:
                                     C.byref(res))
         self._check(rc)
         return out[: res.n_out].copy(), res
+
+    def flac_encode(self, pcm_s16, rate=44100, block_size=4096):
+        """Complete FLAC stream (bytes) of mono s16 samples: the container of the chain's output (encoder.go:92-101)."""
+        pcm = np.ascontiguousarray(pcm_s16, dtype=np.int16)
+        cap = lib().jt_flac_max_bytes(len(pcm), block_size)
+        out = np.zeros(cap, dtype=np.uint8)
+        nb = _I64(0)
+        self._check(lib().jt_flac_encode(self._h, pcm.ctypes.data_as(_P), len(pcm), rate, block_size, out.ctypes.data_as(_P), cap, C.byref(nb)))
+        return out[: nb.value].tobytes()
+
+    def flac_encode_ptr(self, in_ptr, n, rate, block_size, out_ptr, out_cap, on_device):
+        nb = _I64(0)
+        fn = lib().jt_flac_encode_dev if on_device else lib().jt_flac_encode
+        self._check(fn(self._h, _P(in_ptr), n, rate, block_size, _P(out_ptr), out_cap, C.byref(nb)))
+        return nb.value
 
     # -- raw pointer variants for bench.py (torch owns the memory) ----------------------------
     def process_audio_ptr(self, in_ptr, n, rate, channels, fmt, out_ptr, out_cap, on_device, pass2_spec=None):

@@ -1,0 +1,284 @@
+/*
+ * ORACLE (test infrastructure only) -- FLAC (RFC 9639) for the chain's output format: mono, 16 bit, fixed block size
+ * (the reference writes its result through libavcodec's FLAC encoder: mono / 44.1 kHz / s16 / 4096-sample frames,
+ * internal/processor/encoder.go:92-101, processor.go:379-384).
+ *
+ *  orc_flac_encode_s16   sequential restatement of the encoder decisions the CUDA kernel (csrc/k_flac.cu) takes, so the two
+ *                        streams can be compared BYTE for byte: CONSTANT subframe when all samples are equal; otherwise the
+ *                        FIXED predictor order 0..4 with the smallest sum of |residual|; Rice partition order 0..6 (block
+ *                        size a multiple of 64) with the parameter of each partition chosen as libavcodec's flacenc does
+ *                        (find_optimal_param: k = log2((sum - n/2) / n)) and the order with the fewest exact bits; VERBATIM
+ *                        when that is not smaller than 16 bits per sample.  STREAMINFO carries min / max frame size, the
+ *                        sample count and an all-zero MD5 ("not known").
+ *  orc_flac_decode_s16   independent decoder of the subset above (plus LPC subframes, for streams of other encoders).
+ *
+ * Pinned: tests/test_oracle_flac.py decodes the encoder's streams with the REAL FFmpeg 8.0.1 libavcodec FLAC decoder found in
+ * this image (oracle/ref_flac.py) and requires the PCM back bit for bit; the decoder is pinned by decoding the same streams.
+ */
+#include "orc.h"
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ---- bit writer (MSB first) ---- */
+typedef struct { uint8_t *p; int64_t cap, bit; int overflow; } BW;
+static void bw_put(BW *w, int n, uint64_t v)
+{
+    for (int i = n - 1; i >= 0; i--) {
+        int64_t byte = w->bit >> 3;
+        if (byte >= w->cap) { w->overflow = 1; return; }
+        if ((v >> i) & 1) w->p[byte] |= (uint8_t)(0x80 >> (w->bit & 7));
+        w->bit++;
+    }
+}
+static void bw_unary(BW *w, uint32_t q) { w->bit += q; bw_put(w, 1, 1); }      /* q zeros then a one: the buffer is pre-zeroed */
+
+static uint8_t crc8(const uint8_t *p, int64_t n)
+{
+    uint8_t c = 0;
+    for (int64_t i = 0; i < n; i++) { c ^= p[i]; for (int b = 0; b < 8; b++) c = (uint8_t)((c & 0x80) ? (c << 1) ^ 0x07 : (c << 1)); }
+    return c;
+}
+static uint16_t crc16(const uint8_t *p, int64_t n)
+{
+    uint16_t c = 0;
+    for (int64_t i = 0; i < n; i++) { c ^= (uint16_t)(p[i] << 8); for (int b = 0; b < 8; b++) c = (uint16_t)((c & 0x8000) ? (c << 1) ^ 0x8005 : (c << 1)); }
+    return c;
+}
+
+static int rate_code(int rate)
+{
+    switch (rate) {
+    case 88200: return 1; case 176400: return 2; case 192000: return 3; case 8000: return 4; case 16000: return 5; case 22050: return 6;
+    case 24000: return 7; case 32000: return 8; case 44100: return 9; case 48000: return 10; case 96000: return 11;
+    }
+    return 0;                                   /* take it from STREAMINFO */
+}
+static int utf8_put(uint8_t *o, uint64_t v)    /* the "UTF-8" coded frame number, up to 36 bits */
+{
+    if (v < 0x80) { o[0] = (uint8_t)v; return 1; }
+    int n = v < 0x800 ? 2 : v < 0x10000 ? 3 : v < 0x200000 ? 4 : v < 0x4000000 ? 5 : v < 0x80000000ull ? 6 : 7;
+    static const uint8_t lead[8] = {0, 0, 0xC0, 0xE0, 0xF0, 0xF8, 0xFC, 0xFE};
+    for (int i = n - 1; i > 0; i--) { o[i] = (uint8_t)(0x80 | (v & 0x3F)); v >>= 6; }
+    o[0] = (uint8_t)(lead[n] | v);
+    return n;
+}
+
+static inline uint32_t fold(int32_t r) { return ((uint32_t)r << 1) ^ (uint32_t)(r >> 31); }
+static inline int ilog2_u32(uint32_t v) { int l = 0; while (v >>= 1) l++; return l; }
+static int optimal_param(uint64_t sum, int n)  /* flacenc.c find_optimal_param, max 14 */
+{
+    if (sum <= (uint64_t)(n >> 1)) return 0;
+    uint64_t q = (sum - (uint64_t)(n >> 1)) / (uint64_t)n;
+    if (q > 0x7fffffffull) q = 0x7fffffffull;
+    int k = ilog2_u32((uint32_t)q);
+    return k > 14 ? 14 : k;
+}
+
+/* residual of the fixed predictor of `order` at sample i (i >= order) */
+static inline int32_t fixed_res(const int16_t *x, int64_t i, int order)
+{
+    switch (order) {
+    case 0: return x[i];
+    case 1: return (int32_t)x[i] - x[i - 1];
+    case 2: return (int32_t)x[i] - 2 * x[i - 1] + x[i - 2];
+    case 3: return (int32_t)x[i] - 3 * x[i - 1] + 3 * x[i - 2] - x[i - 3];
+    default: return (int32_t)x[i] - 4 * x[i - 1] + 6 * x[i - 2] - 4 * x[i - 3] + x[i - 4];
+    }
+}
+
+#define ORC_FLAC_MAX_PORDER 6
+
+/* one frame; returns bytes written */
+static int64_t encode_frame(const int16_t *x, int bs, int nominal_bs, int rate, uint64_t frame_no, uint8_t *out, int64_t cap)
+{
+    memset(out, 0, (size_t)cap);
+    BW w = {out, cap, 0, 0};
+    /* frame header */
+    bw_put(&w, 14, 0x3FFE); bw_put(&w, 1, 0); bw_put(&w, 1, 0);                /* sync, reserved, fixed block size */
+    const int bs_code = bs == 4096 ? 12 : 7;                                   /* 1100 = 4096, 0111 = 16-bit (bs - 1) follows */
+    bw_put(&w, 4, (uint64_t)bs_code); bw_put(&w, 4, (uint64_t)rate_code(rate));
+    bw_put(&w, 4, 0); bw_put(&w, 3, 4); bw_put(&w, 1, 0);                      /* mono, 16 bit, reserved */
+    uint8_t u8[8]; int nu = utf8_put(u8, frame_no);
+    for (int i = 0; i < nu; i++) bw_put(&w, 8, u8[i]);
+    if (bs_code == 7) bw_put(&w, 16, (uint64_t)(bs - 1));
+    bw_put(&w, 8, crc8(out, w.bit >> 3));
+    (void)nominal_bs;
+    /* subframe decision */
+    int constant = 1;
+    for (int i = 1; i < bs; i++) if (x[i] != x[0]) { constant = 0; break; }
+    if (constant) {
+        bw_put(&w, 8, 0x00); bw_put(&w, 16, (uint16_t)x[0]);
+    } else {
+        int best_order = 0; uint64_t best_err = ~0ull;
+        for (int o = 0; o <= 4 && o < bs; o++) {
+            uint64_t e = 0;
+            for (int i = o; i < bs; i++) { int32_t r = fixed_res(x, i, o); e += (uint64_t)(r < 0 ? -(int64_t)r : r); }
+            if (e < best_err) { best_err = e; best_order = o; }
+        }
+        const int order = best_order;
+        int pmax = 0;
+        if (bs % 64 == 0) { pmax = ORC_FLAC_MAX_PORDER; while (pmax > 0 && (bs >> pmax) <= order) pmax--; }
+        int best_p = 0; uint64_t best_bits = ~0ull; int best_k[1 << ORC_FLAC_MAX_PORDER];
+        for (int p = 0; p <= pmax; p++) {
+            const int psz = bs >> p; uint64_t bits = 0; int ks[1 << ORC_FLAC_MAX_PORDER];
+            for (int j = 0; j < (1 << p); j++) {
+                const int a = j * psz < order ? order : j * psz, b = (j + 1) * psz, n = b - a;
+                uint64_t s = 0;
+                for (int i = a; i < b; i++) s += fold(fixed_res(x, i, order));
+                const int k = optimal_param(s, n);
+                uint64_t sh = 0;
+                for (int i = a; i < b; i++) sh += fold(fixed_res(x, i, order)) >> k;
+                bits += 4 + (uint64_t)n * (uint64_t)(k + 1) + sh;
+                ks[j] = k;
+            }
+            if (bits < best_bits) { best_bits = bits; best_p = p; memcpy(best_k, ks, sizeof(int) * (size_t)(1 << p)); }
+        }
+        const uint64_t fixed_bits = 8 + 16ull * (uint64_t)order + 6 + best_bits, verbatim_bits = 8 + 16ull * (uint64_t)bs;
+        if (fixed_bits >= verbatim_bits) {
+            bw_put(&w, 8, 0x02);
+            for (int i = 0; i < bs; i++) bw_put(&w, 16, (uint16_t)x[i]);
+        } else {
+            bw_put(&w, 8, (uint64_t)((0x08 | order) << 1));
+            for (int i = 0; i < order; i++) bw_put(&w, 16, (uint16_t)x[i]);
+            bw_put(&w, 2, 0); bw_put(&w, 4, (uint64_t)best_p);
+            const int psz = bs >> best_p;
+            for (int j = 0; j < (1 << best_p); j++) {
+                const int a = j * psz < order ? order : j * psz, b = (j + 1) * psz, k = best_k[j];
+                bw_put(&w, 4, (uint64_t)k);
+                for (int i = a; i < b; i++) { const uint32_t u = fold(fixed_res(x, i, order)); bw_unary(&w, u >> k); if (k) bw_put(&w, k, u & ((1u << k) - 1)); }
+            }
+        }
+    }
+    if (w.bit & 7) w.bit += 8 - (w.bit & 7);
+    if (w.overflow || (w.bit >> 3) + 2 > cap) return -1;
+    const uint16_t c = crc16(out, w.bit >> 3);
+    bw_put(&w, 16, c);
+    return w.bit >> 3;
+}
+
+int64_t orc_flac_max_bytes(int64_t n, int block_size)
+{
+    const int64_t frames = (n + block_size - 1) / block_size;
+    return 4 + 4 + 34 + frames * (16 + 2 * (int64_t)block_size + 2) + 64;
+}
+
+/* whole stream; returns bytes, or -1 when `cap` is short */
+int64_t orc_flac_encode_s16(const int16_t *x, int64_t n, int rate, int block_size, uint8_t *out, int64_t cap)
+{
+    if (block_size < 16 || block_size > 65535 || cap < 42) return -1;
+    const int64_t frames = (n + block_size - 1) / block_size;
+    int64_t pos = 42; uint32_t min_fs = 0xFFFFFF, max_fs = 0;
+    const int64_t fcap = 16 + 2 * (int64_t)block_size + 2;
+    uint8_t *tmp = (uint8_t *)malloc((size_t)fcap);
+    for (int64_t f = 0; f < frames; f++) {
+        const int bs = (int)((n - f * block_size) < block_size ? (n - f * block_size) : block_size);
+        const int64_t sz = encode_frame(x + f * block_size, bs, block_size, rate, (uint64_t)f, tmp, fcap);
+        if (sz < 0 || pos + sz > cap) { free(tmp); return -1; }
+        memcpy(out + pos, tmp, (size_t)sz); pos += sz;
+        if ((uint32_t)sz < min_fs) min_fs = (uint32_t)sz;
+        if ((uint32_t)sz > max_fs) max_fs = (uint32_t)sz;
+    }
+    free(tmp);
+    if (frames == 0) min_fs = 0;
+    memset(out, 0, 42);
+    memcpy(out, "fLaC", 4);
+    BW w = {out, 42, 32, 0};
+    bw_put(&w, 1, 1); bw_put(&w, 7, 0); bw_put(&w, 24, 34);                    /* last metadata block, STREAMINFO, 34 bytes */
+    bw_put(&w, 16, (uint64_t)block_size); bw_put(&w, 16, (uint64_t)block_size);
+    bw_put(&w, 24, min_fs); bw_put(&w, 24, max_fs);
+    bw_put(&w, 20, (uint64_t)rate); bw_put(&w, 3, 0); bw_put(&w, 5, 15); bw_put(&w, 36, (uint64_t)n);
+    return pos;                                                                 /* MD5 stays zero: "not known" */
+}
+
+/* ---- decoder ---- */
+typedef struct { const uint8_t *p; int64_t n, bit; int err; } BR;
+static uint64_t br_get(BR *r, int n)
+{
+    uint64_t v = 0;
+    for (int i = 0; i < n; i++) {
+        const int64_t byte = r->bit >> 3;
+        if (byte >= r->n) { r->err = 1; return 0; }
+        v = (v << 1) | ((r->p[byte] >> (7 - (r->bit & 7))) & 1);
+        r->bit++;
+    }
+    return v;
+}
+static int32_t br_sget(BR *r, int n) { uint64_t v = br_get(r, n); return (int32_t)((int64_t)(v << (64 - n)) >> (64 - n)); }
+static uint32_t br_unary(BR *r) { uint32_t q = 0; while (!r->err && br_get(r, 1) == 0) q++; return q; }
+
+/* returns samples decoded (mono, <= 16 bit), negative on a malformed stream: -2 CRC-8, -3 CRC-16, -4 syntax */
+int64_t orc_flac_decode_s16(const uint8_t *in, int64_t nbytes, int16_t *out, int64_t cap, int *rate_out)
+{
+    if (nbytes < 42 || memcmp(in, "fLaC", 4)) return -4;
+    BR r = {in, nbytes, 32, 0};
+    int last = 0, rate = 0, bps = 16; int64_t total = 0;
+    while (!last) {
+        last = (int)br_get(&r, 1); const int type = (int)br_get(&r, 7); const int len = (int)br_get(&r, 24);
+        if (type == 0) {
+            br_get(&r, 16); br_get(&r, 16); br_get(&r, 24); br_get(&r, 24);
+            rate = (int)br_get(&r, 20); const int ch = (int)br_get(&r, 3) + 1; bps = (int)br_get(&r, 5) + 1; total = (int64_t)br_get(&r, 36);
+            if (ch != 1 || bps > 16) return -4;
+            r.bit += 128;
+        } else r.bit += 8ll * len;
+        if (r.err) return -4;
+    }
+    if (rate_out) *rate_out = rate;
+    int64_t pos = 0; int32_t *buf = (int32_t *)malloc(sizeof(int32_t) * 65536);
+    while ((r.bit >> 3) < nbytes) {
+        const int64_t f0 = r.bit >> 3;
+        if (br_get(&r, 14) != 0x3FFE) { free(buf); return -4; }
+        br_get(&r, 2);
+        const int bsc = (int)br_get(&r, 4), src = (int)br_get(&r, 4), chc = (int)br_get(&r, 4), szc = (int)br_get(&r, 3);
+        br_get(&r, 1);
+        if (chc != 0 || (szc != 4 && szc != 0)) { free(buf); return -4; }
+        int b0 = (int)br_get(&r, 8), extra = 0;                               /* coded number */
+        if (b0 >= 0xC0) { int m = 0x20; extra = 1; while (b0 & m) { extra++; m >>= 1; } }
+        for (int i = 0; i < extra; i++) br_get(&r, 8);
+        int bs;
+        if (bsc == 6) bs = (int)br_get(&r, 8) + 1; else if (bsc == 7) bs = (int)br_get(&r, 16) + 1;
+        else if (bsc == 1) bs = 192; else if (bsc >= 2 && bsc <= 5) bs = 576 << (bsc - 2); else if (bsc >= 8) bs = 256 << (bsc - 8); else { free(buf); return -4; }
+        if (src == 12) br_get(&r, 8); else if (src == 13 || src == 14) br_get(&r, 16);
+        const uint8_t c8 = (uint8_t)br_get(&r, 8);
+        if (r.err || crc8(in + f0, (r.bit >> 3) - 1 - f0) != c8) { free(buf); return -2; }
+        /* subframe */
+        if (br_get(&r, 1)) { free(buf); return -4; }
+        const int type = (int)br_get(&r, 6); int wasted = 0;
+        if (br_get(&r, 1)) wasted = (int)br_unary(&r) + 1;
+        const int sb = bps - wasted;
+        if (type == 0) { const int32_t v = br_sget(&r, sb); for (int i = 0; i < bs; i++) buf[i] = v; }
+        else if (type == 1) { for (int i = 0; i < bs; i++) buf[i] = br_sget(&r, sb); }
+        else if ((type >= 8 && type <= 12) || type >= 32) {
+            const int lpc = type >= 32, order = lpc ? (type & 31) + 1 : type & 7;
+            int32_t coef[32]; int shift = 0;
+            for (int i = 0; i < order; i++) buf[i] = br_sget(&r, sb);
+            if (lpc) { const int prec = (int)br_get(&r, 4) + 1; shift = br_sget(&r, 5); for (int i = 0; i < order; i++) coef[i] = br_sget(&r, prec); }
+            const int method = (int)br_get(&r, 2), porder = (int)br_get(&r, 4), plen = method ? 5 : 4, esc = method ? 31 : 15;
+            if (method > 1) { free(buf); return -4; }
+            int i = order;
+            for (int j = 0; j < (1 << porder); j++) {
+                const int cnt = (bs >> porder) - (j == 0 ? order : 0), k = (int)br_get(&r, plen);
+                if (k == esc) { const int nb = (int)br_get(&r, 5); for (int t = 0; t < cnt; t++) buf[i++] = nb ? br_sget(&r, nb) : 0; }
+                else for (int t = 0; t < cnt; t++) { const uint32_t q = br_unary(&r); const uint32_t u = (q << k) | (uint32_t)br_get(&r, k); buf[i++] = (int32_t)(u >> 1) ^ -(int32_t)(u & 1); }
+                if (r.err) { free(buf); return -4; }
+            }
+            for (i = order; i < bs; i++) {
+                int64_t pred;
+                if (lpc) { pred = 0; for (int t = 0; t < order; t++) pred += (int64_t)coef[t] * buf[i - 1 - t]; pred >>= shift; }
+                else switch (order) {
+                    case 0: pred = 0; break; case 1: pred = buf[i - 1]; break; case 2: pred = 2ll * buf[i - 1] - buf[i - 2]; break;
+                    case 3: pred = 3ll * buf[i - 1] - 3ll * buf[i - 2] + buf[i - 3]; break;
+                    default: pred = 4ll * buf[i - 1] - 6ll * buf[i - 2] + 4ll * buf[i - 3] - buf[i - 4];
+                }
+                buf[i] = (int32_t)(buf[i] + pred);
+            }
+        } else { free(buf); return -4; }
+        if (r.bit & 7) r.bit += 8 - (r.bit & 7);
+        const int64_t f1 = r.bit >> 3;
+        const uint16_t c16 = (uint16_t)br_get(&r, 16);
+        if (r.err || crc16(in + f0, f1 - f0) != c16) { free(buf); return -3; }
+        for (int i = 0; i < bs; i++) { if (pos >= cap) { free(buf); return -1; } out[pos++] = (int16_t)(buf[i] * (1 << wasted)); }
+    }
+    free(buf);
+    return (total && pos != total) ? -4 : pos;
+}

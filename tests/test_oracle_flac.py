@@ -1,0 +1,71 @@
+"""The oracle's FLAC encoder / decoder (oracle/orc_flac.c) pinned on the REAL FFmpeg libavcodec FLAC decoder found in this
+image (oracle/ref_flac.py builds a probe against the reference's vendored headers): every stream the oracle encoder writes
+must come back bit for bit from libavcodec and from the oracle's own decoder.  CPU only."""
+import numpy as np
+import pytest
+
+import ref_flac
+from jivetalking_b200 import synth
+
+
+def s16(x):
+    return np.clip(np.round(x * 32768.0), -32768, 32767).astype(np.int16)
+
+
+def signals():
+    sp = s16(synth.speech_like(3.0, 44100, seed=5))
+    rng = np.random.default_rng(3)
+    out = {"speech": sp[: 4096 * 20], "ragged": sp[:50000], "one_frame": sp[:4096], "tiny": sp[:100],
+           "silence": np.zeros(4096 * 3, dtype=np.int16), "dc": np.full(9000, -1234, dtype=np.int16),
+           "white_full_scale": rng.integers(-32768, 32768, 4096 * 2).astype(np.int16),
+           "clipped": s16(np.clip(3.0 * synth.speech_like(1.0, 44100, seed=9), -1, 1)),
+           "extremes": np.tile(np.array([-32768, 32767], dtype=np.int16), 4096)}
+    mixed = sp[: 4096 * 6].copy()
+    mixed[4096:8192] = 0
+    mixed[3 * 4096: 3 * 4096 + 2000] = 321
+    out["mixed"] = mixed
+    return out
+
+
+SIG = signals()
+
+
+@pytest.mark.parametrize("name", sorted(SIG))
+@pytest.mark.parametrize("block_size", [4096, 1024, 100])
+def test_round_trip_oracle_and_real_libavcodec(name, block_size):
+    x = SIG[name]
+    stream = ref_flac.encode(x, 44100, block_size)
+    assert stream[:4] == b"fLaC" and stream[4] == 0x80 and stream[7] == 34
+    y, rate = ref_flac.decode(stream, len(x) + 16)
+    assert rate == 44100 and np.array_equal(x, y)
+    ref = ref_flac.ref_decode(stream)
+    if ref is None:
+        pytest.skip("FFmpeg libavcodec / reference headers not present: oracle decoder only")
+    pcm, rrate, ch = ref
+    assert (rrate, ch) == (44100, 1) and np.array_equal(pcm, x)
+
+
+def test_streaminfo_and_compression():
+    x = SIG["speech"]
+    stream = ref_flac.encode(x, 44100, 4096)
+    si = stream[8:42]
+    assert int.from_bytes(si[0:2], "big") == 4096 and int.from_bytes(si[2:4], "big") == 4096
+    min_fs, max_fs = int.from_bytes(si[4:7], "big"), int.from_bytes(si[7:10], "big")
+    assert 0 < min_fs <= max_fs < 8212
+    v = int.from_bytes(si[10:18], "big")
+    assert v >> 44 == 44100 and (v >> 41) & 7 == 0 and (v >> 36) & 31 == 15 and v & ((1 << 36) - 1) == len(x)
+    assert si[18:34] == bytes(16)                           # MD5 "not known"
+    assert len(stream) < 0.7 * 2 * len(x)                   # a speech-like signal compresses
+    assert len(ref_flac.encode(SIG["silence"], 44100, 4096)) == 42 + 3 * (6 + 3 + 2)     # CONSTANT subframes
+    assert len(ref_flac.encode(SIG["white_full_scale"], 44100, 4096)) == 42 + 2 * (6 + 1 + 8192 + 2)   # VERBATIM
+
+
+def test_decoder_rejects_corruption():
+    x = SIG["speech"][: 4096 * 3]
+    stream = bytearray(ref_flac.encode(x, 44100, 4096))
+    bad = bytearray(stream); bad[42 + 2] ^= 0x10            # frame header -> CRC-8
+    with pytest.raises(ValueError):
+        ref_flac.decode(bytes(bad), len(x) + 16)
+    bad = bytearray(stream); bad[42 + 500] ^= 0x01          # residual bits -> CRC-16 (or a syntax error on the way)
+    with pytest.raises(ValueError):
+        ref_flac.decode(bytes(bad), len(x) + 16)
