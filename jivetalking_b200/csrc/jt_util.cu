@@ -102,7 +102,11 @@ const void *jt_dev_table(jt_ctx *c, const char *tag, const void *host, size_t by
     if (it != c->dev_tables.end()) return it->second;
     void *d = nullptr;
     if (cudaMalloc(&d, bytes ? bytes : 16) != cudaSuccess) JT_THROW(JT_ERR_NOMEM, "cudaMalloc(%zu) for table %s", bytes, tag);
-    if (bytes && cudaMemcpy(d, host, bytes, cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(d); JT_THROW(JT_ERR_CUDA, "table upload %s", tag); }
+    // On the context's own stream and waited for: the stream is non-blocking, so a cudaMemcpy on the legacy stream is NOT
+    // ordered before the kernels that read the table (from pageable memory it may return while the DMA is still queued --
+    // harmless on an idle device, a stale table when other contexts keep the copy engine busy).  First use only: cached.
+    if (bytes && (cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
+                  cudaStreamSynchronize(c->stream) != cudaSuccess)) { cudaFree(d); JT_THROW(JT_ERR_CUDA, "table upload %s", tag); }
     c->dev_tables[key] = d;
     return d;
 }

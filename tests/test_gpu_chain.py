@@ -145,23 +145,24 @@ def test_concurrent_contexts(ctx):
     context and stream each, same file: every result equals the serial one bit for bit."""
     import threading
     xs = [synth.speech_like(20.0, 48000, seed=100 + i) for i in range(2)]
-    serial = [ctx.process_audio(x, 48000) for x in xs]
+    serial = [ctx.process_audio(x, 48000) for x in xs]      # (fresh contexts below: their first call also uploads every table)
     results, errors = {}, []
 
     def worker(k):
         try:
-            with gpudsp.Context(0) as c:
-                for rep in range(2):
-                    pcm, res = c.process_audio(xs[k % 2], 48000)
-                    results[(k, rep)] = (pcm, res.final.input_i, res.final.input_tp, res.n_out)
+            for rep in range(3):
+                with gpudsp.Context(0) as c:             # a fresh context each time: first-call table uploads under load
+                    pcm, res = c.process_audio(xs[(k + rep) % 2], 48000)
+                    results[(k, rep)] = ((k + rep) % 2, pcm, res.final.input_i, res.final.input_tp, res.n_out)
         except Exception as e:          # noqa: BLE001
             errors.append(repr(e))
-    threads = [threading.Thread(target=worker, args=(k,)) for k in range(4)]
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(6)]
     for t in threads:
         t.start()
     for t in threads:
         t.join()
     assert not errors, errors
-    for (k, rep), (pcm, i, tp, n) in results.items():
-        spcm, sres = serial[k % 2]
+    assert len(results) == 18
+    for (k, rep), (which, pcm, i, tp, n) in results.items():
+        spcm, sres = serial[which]
         assert np.array_equal(pcm, spcm) and i == sres.final.input_i and tp == sres.final.input_tp and n == sres.n_out
