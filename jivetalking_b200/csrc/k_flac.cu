@@ -28,7 +28,7 @@ constexpr int FL_MAX_PORDER = 6;
 static_assert(FL_FRAME_CAP % 4 == 0, "frame slots are copied as words");
 
 struct FlWarp {                                          // per-warp shared memory
-    int16_t x[FL_MAX_BS];
+    int16_t x[FL_MAX_BS + 64];                           // lane chunks skewed by one word each: see FL_X
     uint32_t frame[FL_FRAME_WORDS];
     uint32_t cell[64];                                   // sum of folded residuals per 1/64 of the block
     uint16_t col[16];                                    // CRC-16 "append L zero bytes" operator, one column per state bit
@@ -36,24 +36,28 @@ struct FlWarp {                                          // per-warp shared memo
 
 __device__ __forceinline__ uint32_t fl_fold(int32_t r) { return ((uint32_t)r << 1) ^ (uint32_t)(r >> 31); }
 
-template <int ORDER> __device__ __forceinline__ int32_t fl_res(const int16_t *x, int i)
-{
-    if (ORDER == 0) return x[i];
-    if (ORDER == 1) return (int32_t)x[i] - x[i - 1];
-    if (ORDER == 2) return (int32_t)x[i] - 2 * x[i - 1] + x[i - 2];
-    if (ORDER == 3) return (int32_t)x[i] - 3 * x[i - 1] + 3 * x[i - 2] - x[i - 3];
-    return (int32_t)x[i] - 4 * x[i - 1] + 6 * x[i - 2] - 4 * x[i - 3] + x[i - 4];
-}
-__device__ __forceinline__ int32_t fl_res_o(const int16_t *x, int i, int order)
-{
-    switch (order) {
-    case 0: return fl_res<0>(x, i);
-    case 1: return fl_res<1>(x, i);
-    case 2: return fl_res<2>(x, i);
-    case 3: return fl_res<3>(x, i);
-    default: return fl_res<4>(x, i);
-    }
-}
+// Sample i of the staged block.  A lane walks its own contiguous chunk, so with the plain layout all 32 lanes would hit one
+// bank (chunk = 128 int16 = 64 words: ncu showed 605 M conflicts in 636 M shared wavefronts); when the chunk is a power of two
+// every chunk is shifted by one more word (2 int16), which puts the lanes on 32 different banks.
+#define FL_X(i) (x[(i) + ((((i) >> xsh) << 1) & xpad)])
+
+// for (i in [a, b)) with r = residual of the fixed predictor `order` at i (a >= order): the previous four samples ride in
+// registers, one shared-memory read per sample
+#define FL_FOR_RES(a, b, BODY)                                                                                         \
+    do {                                                                                                               \
+        int i_ = (a);                                                                                                  \
+        if (i_ < (b)) {                                                                                                \
+            int32_t m1_ = i_ >= 1 ? FL_X(i_ - 1) : 0, m2_ = i_ >= 2 ? FL_X(i_ - 2) : 0, m3_ = i_ >= 3 ? FL_X(i_ - 3) : 0,    \
+                    m4_ = i_ >= 4 ? FL_X(i_ - 4) : 0;                                                                  \
+            for (; i_ < (b); i_++) {                                                                                   \
+                const int32_t x0_ = FL_X(i_);                                                                          \
+                const int32_t r = order == 0 ? x0_ : order == 1 ? x0_ - m1_ : order == 2 ? x0_ - 2 * m1_ + m2_         \
+                                : order == 3 ? x0_ - 3 * m1_ + 3 * m2_ - m3_ : x0_ - 4 * m1_ + 6 * m2_ - 4 * m3_ + m4_; \
+                BODY;                                                                                                  \
+                m4_ = m3_; m3_ = m2_; m2_ = m1_; m1_ = x0_;                                                            \
+            }                                                                                                          \
+        }                                                                                                              \
+    } while (0)
 
 __device__ __forceinline__ int fl_optimal_param(unsigned long long sum, int n)      // flacenc.c find_optimal_param
 {
@@ -109,10 +113,12 @@ k_flac_frames(const int16_t *__restrict__ pcm, int64_t n, int block_size, int ra
         const int64_t s0 = f * block_size;
         const int bs = (int)min((int64_t)block_size, n - s0);
         // ---- stage samples, clear the frame ----
-        for (int i = lane; i < bs; i += 32) S.x[i] = pcm[s0 + i];
+        const int chunk = (bs + 31) / 32;
+        const int xpad = (chunk >= 2 && (chunk & (chunk - 1)) == 0) ? -1 : 0, xsh = xpad ? 31 - __clz(chunk) : 0;
+        int16_t *x = S.x;
+        for (int i = lane; i < bs; i += 32) FL_X(i) = pcm[s0 + i];
         for (int i = lane; i < FL_FRAME_WORDS; i += 32) S.frame[i] = 0;
         __syncwarp();
-        const int16_t *x = S.x;
         uint8_t *fb = reinterpret_cast<uint8_t *>(S.frame);
         // ---- frame header (lane 0) ----
         int hdr_bytes = 0;
@@ -140,25 +146,29 @@ k_flac_frames(const int16_t *__restrict__ pcm, int64_t n, int block_size, int ra
         const int sub0 = hdr_bytes * 8;                   // first bit of the subframe
         // ---- lane ranges: [lo, mid) and [mid, hi) are the lane's two cells when the block divides into 64 ----
         const bool cells = (bs % 64) == 0;
-        const int chunk = (bs + 31) / 32;
         const int lo = min(bs, lane * chunk), hi = min(bs, lo + chunk);
         const int mid = cells ? lo + chunk / 2 : hi;
         // ---- constant? fixed-order errors ----
         bool equal = true;
         unsigned long long e0 = 0, e1 = 0, e2 = 0, e3 = 0, e4 = 0;
-        for (int i = lo; i < hi; i++) {
-            equal = equal && (x[i] == x[0]);
-            const int32_t r0 = fl_res<0>(x, i);
-            e0 += (unsigned)abs(r0);
-            if (i >= 1) e1 += (unsigned)abs(fl_res<1>(x, i));
-            if (i >= 2) e2 += (unsigned)abs(fl_res<2>(x, i));
-            if (i >= 3) e3 += (unsigned)abs(fl_res<3>(x, i));
-            if (i >= 4) e4 += (unsigned)abs(fl_res<4>(x, i));
+        {
+            const int32_t first = FL_X(0);
+            int32_t m1 = lo >= 1 ? FL_X(lo - 1) : 0, m2 = lo >= 2 ? FL_X(lo - 2) : 0, m3 = lo >= 3 ? FL_X(lo - 3) : 0, m4 = lo >= 4 ? FL_X(lo - 4) : 0;
+            for (int i = lo; i < hi; i++) {
+                const int32_t x0 = FL_X(i);
+                equal = equal && (x0 == first);
+                e0 += (unsigned)abs(x0);
+                if (i >= 1) e1 += (unsigned)abs(x0 - m1);
+                if (i >= 2) e2 += (unsigned)abs(x0 - 2 * m1 + m2);
+                if (i >= 3) e3 += (unsigned)abs(x0 - 3 * m1 + 3 * m2 - m3);
+                if (i >= 4) e4 += (unsigned)abs(x0 - 4 * m1 + 6 * m2 - 4 * m3 + m4);
+                m4 = m3; m3 = m2; m2 = m1; m1 = x0;
+            }
         }
         const bool constant = __all_sync(0xffffffffu, equal);
         int total_bits;                                   // bits of header + subframe before padding
         if (constant) {
-            if (lane == 0) { fl_put(S.frame, sub0, 8, 0x00); fl_put(S.frame, sub0 + 8, 16, (uint16_t)x[0]); }
+            if (lane == 0) { fl_put(S.frame, sub0, 8, 0x00); fl_put(S.frame, sub0 + 8, 16, (uint16_t)FL_X(0)); }
             total_bits = sub0 + 24;
         } else {
             e0 = fl_warp_sum_u64(e0); e1 = fl_warp_sum_u64(e1); e2 = fl_warp_sum_u64(e2); e3 = fl_warp_sum_u64(e3); e4 = fl_warp_sum_u64(e4);
@@ -170,8 +180,8 @@ k_flac_frames(const int16_t *__restrict__ pcm, int64_t n, int block_size, int ra
             // ---- per-cell sums of the folded residual ----
             const int a0 = max(lo, order), a1 = max(mid, order);          // residual samples of the two cells: [a0, mid), [a1, hi)
             uint32_t c0 = 0, c1 = 0;
-            for (int i = a0; i < mid; i++) c0 += fl_fold(fl_res_o(x, i, order));
-            for (int i = a1; i < hi; i++) c1 += fl_fold(fl_res_o(x, i, order));
+            FL_FOR_RES(a0, mid, c0 += fl_fold(r));
+            FL_FOR_RES(a1, hi, c1 += fl_fold(r));
             S.cell[2 * lane] = c0; S.cell[2 * lane + 1] = c1;
             __syncwarp();
             int pmax = 0;
@@ -194,15 +204,15 @@ k_flac_frames(const int16_t *__restrict__ pcm, int64_t n, int block_size, int ra
                     k1 = fl_optimal_param(s, psz - (j == 0 ? order : 0));
                 }
                 unsigned long long bits = 0;
-                for (int i = a0; i < mid; i++) bits += (fl_fold(fl_res_o(x, i, order)) >> k0) + (unsigned)(k0 + 1);
-                for (int i = a1; i < hi; i++) bits += (fl_fold(fl_res_o(x, i, order)) >> k1) + (unsigned)(k1 + 1);
+                FL_FOR_RES(a0, mid, bits += (fl_fold(r) >> k0) + (unsigned)(k0 + 1));
+                FL_FOR_RES(a1, hi, bits += (fl_fold(r) >> k1) + (unsigned)(k1 + 1));
                 bits = fl_warp_sum_u64(bits) + 4ull * (unsigned long long)(1 << p);
                 if (bits < best_bits) { best_bits = bits; best_p = p; bk0 = k0; bk1 = k1; }
             }
             const unsigned long long fixed_bits = 8ull + 16ull * (unsigned)order + 6ull + best_bits, verbatim_bits = 8ull + 16ull * (unsigned)bs;
             if (fixed_bits >= verbatim_bits) {
                 if (lane == 0) fl_put(S.frame, sub0, 8, 0x02);
-                for (int i = lo; i < hi; i++) fl_put(S.frame, sub0 + 8 + 16 * i, 16, (uint16_t)x[i]);
+                for (int i = lo; i < hi; i++) fl_put(S.frame, sub0 + 8 + 16 * i, 16, (uint16_t)FL_X(i));
                 total_bits = sub0 + 8 + 16 * bs;
             } else {
                 const int per = 64 >> best_p;
@@ -210,8 +220,8 @@ k_flac_frames(const int16_t *__restrict__ pcm, int64_t n, int block_size, int ra
                 const bool open0 = cells ? ((2 * lane) % per) == 0 : lane == 0;
                 const bool open1 = cells ? ((2 * lane + 1) % per) == 0 : false;
                 unsigned lane_bits = (open0 ? 4u : 0u) + (open1 ? 4u : 0u);
-                for (int i = a0; i < mid; i++) lane_bits += (fl_fold(fl_res_o(x, i, order)) >> bk0) + (unsigned)(bk0 + 1);
-                for (int i = a1; i < hi; i++) lane_bits += (fl_fold(fl_res_o(x, i, order)) >> bk1) + (unsigned)(bk1 + 1);
+                FL_FOR_RES(a0, mid, lane_bits += (fl_fold(r) >> bk0) + (unsigned)(bk0 + 1));
+                FL_FOR_RES(a1, hi, lane_bits += (fl_fold(r) >> bk1) + (unsigned)(bk1 + 1));
                 unsigned incl = lane_bits;
                 for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
                 const int base = sub0 + 8 + 16 * order + 6;
@@ -219,23 +229,23 @@ k_flac_frames(const int16_t *__restrict__ pcm, int64_t n, int block_size, int ra
                 total_bits = base + (int)__shfl_sync(0xffffffffu, incl, 31);
                 if (lane == 0) {
                     fl_put(S.frame, sub0, 8, (uint32_t)((0x08 | order) << 1));
-                    for (int i = 0; i < order; i++) fl_put(S.frame, sub0 + 8 + 16 * i, 16, (uint16_t)x[i]);
+                    for (int i = 0; i < order; i++) fl_put(S.frame, sub0 + 8 + 16 * i, 16, (uint16_t)FL_X(i));
                     fl_put(S.frame, sub0 + 8 + 16 * order, 6, (uint32_t)best_p);       // method 00 + partition order
                 }
                 if (open0) { fl_put(S.frame, pos, 4, (uint32_t)bk0); pos += 4; }
-                for (int i = a0; i < mid; i++) {
-                    const uint32_t u = fl_fold(fl_res_o(x, i, order));
+                FL_FOR_RES(a0, mid, {
+                    const uint32_t u = fl_fold(r);
                     pos += (int)(u >> bk0);
                     fl_put(S.frame, pos, bk0 + 1, (1u << bk0) | (u & ((1u << bk0) - 1)));          // the unary stop bit and the k low bits
                     pos += bk0 + 1;
-                }
+                });
                 if (open1) { fl_put(S.frame, pos, 4, (uint32_t)bk1); pos += 4; }
-                for (int i = a1; i < hi; i++) {
-                    const uint32_t u = fl_fold(fl_res_o(x, i, order));
+                FL_FOR_RES(a1, hi, {
+                    const uint32_t u = fl_fold(r);
                     pos += (int)(u >> bk1);
                     fl_put(S.frame, pos, bk1 + 1, (1u << bk1) | (u & ((1u << bk1) - 1)));
                     pos += bk1 + 1;
-                }
+                });
             }
         }
         __syncwarp();
