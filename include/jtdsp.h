@@ -424,6 +424,13 @@ int jt_process_audio_adaptive_dev(jt_ctx *ctx, const void *d_pcm_in, int64_t n_f
                         const jt_filter_config *base, int16_t *d_pcm_out, int64_t pcm_out_cap,
                         jt_process_result *res, jt_analysis *analysis);
 
+/* RIFF / WAVE input (the reference's fixtures are s16 WAVs, testutil_test.go:140-190; it decodes through libavformat,
+ * internal/audio/reader.go): locates the PCM of a file image in memory.  *sample_fmt is a JT_FMT_* value, the samples are
+ * interleaved at bytes + *data_offset.  JT_ERR_UNSUPPORTED for 8 / 24 bit or compressed data, and for 32-bit integer PCM
+ * (described in the outputs, but the chain has no s32 kernels yet).  Host-only, no jt_ctx. */
+int jt_wav_parse(const void *bytes, int64_t n_bytes, int *sample_fmt, int *sample_rate, int *channels,
+                 int64_t *data_offset, int64_t *n_frames);
+
 /* ---- FLAC container of the chain's output ------------------------------------------------------------------
  * The reference hands its s16 mono 44.1 kHz result to libavcodec's FLAC encoder in 4096-sample frames
  * (internal/processor/encoder.go:92-101, processor.go:379-384).  jt_flac_encode writes a complete FLAC stream (RFC 9639:

@@ -146,6 +146,7 @@ def lib():
     L.jt_default_pass2_spec.argtypes = [C.c_char_p, C.c_size_t]
     L.jt_pass1_spec.argtypes = [C.c_char_p, C.c_size_t]
     L.jt_loudnorm_stats_json.argtypes = [C.POINTER(LoudnormStats), C.c_char_p, C.c_size_t]
+    L.jt_wav_parse.argtypes = [_P, _I64, C.POINTER(_INT), C.POINTER(_INT), C.POINTER(_INT), C.POINTER(_I64), C.POINTER(_I64)]
     L.jt_flac_max_bytes.restype = _I64
     L.jt_flac_max_bytes.argtypes = [_I64, _INT]
     fl = [_P, _P, _I64, _INT, _INT, _P, _I64, C.POINTER(_I64)]
@@ -161,6 +162,18 @@ def lib():
     L.jt_kernel_timing.argtypes = [_P, _INT, C.POINTER(C.c_double), C.POINTER(_I64)]
     _lib = L
     return L
+
+
+def wav_parse(data):
+    """(numpy view of the interleaved samples, rate, channels) of a RIFF/WAVE file image (bytes); raises JtError."""
+    buf = np.frombuffer(data, dtype=np.uint8)
+    fmt, rate, ch, off, nfr = _INT(0), _INT(0), _INT(0), _I64(0), _I64(0)
+    rc = lib().jt_wav_parse(buf.ctypes.data_as(_P), len(buf), C.byref(fmt), C.byref(rate), C.byref(ch), C.byref(off), C.byref(nfr))
+    if rc != 0:
+        raise JtError(rc, "jt_wav_parse")
+    dt = _NP_OF_FMT[fmt.value]
+    n = nfr.value * ch.value
+    return np.frombuffer(data, dtype=dt, count=n, offset=off.value), rate.value, ch.value
 
 
 def pass1_spec():

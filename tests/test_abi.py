@@ -77,3 +77,35 @@ def test_pass34_spec_builders_match_reference_goldens():
             # the reference fixture passes offset=0.00 explicitly (its `offset` argument); ours derives
             # offset = effectiveTargetI - measured_I as ApplyNormalisation does (normalise.go:873)
             assert spec4.replace("offset=4.00", "offset=0.00") == want_p4.replace("offset=4.00", "offset=0.00")
+
+
+def test_wav_parse(tmp_path):
+    """jt_wav_parse on files written by Python's wave module (the reference's fixtures are s16 WAVs, testutil_test.go:140-190)"""
+    import io
+    import struct
+    import wave
+    import numpy as np
+    import pytest
+    from jivetalking_b200 import gpudsp
+    x = (np.arange(2000) % 257 - 128).astype(np.int16)
+    for ch in (1, 2):
+        bio = io.BytesIO()
+        with wave.open(bio, "wb") as w:
+            w.setnchannels(ch); w.setsampwidth(2); w.setframerate(48000); w.writeframes(x.tobytes())
+        pcm, rate, channels = gpudsp.wav_parse(bio.getvalue())
+        assert (rate, channels) == (48000, ch) and pcm.dtype == np.int16 and np.array_equal(pcm, x)
+    # float32 WAV with a LIST chunk in front of the data and an odd-sized chunk (padding byte)
+    f = np.linspace(-1, 1, 333, dtype=np.float32)
+    fmt = struct.pack("<HHIIHH", 3, 1, 44100, 44100 * 4, 4, 32)
+    body = b"WAVE" + b"fmt " + struct.pack("<I", 16) + fmt + b"LIST" + struct.pack("<I", 5) + b"abcde\0" + b"data" + struct.pack("<I", f.nbytes) + f.tobytes()
+    pcm, rate, channels = gpudsp.wav_parse(b"RIFF" + struct.pack("<I", len(body)) + body)
+    assert rate == 44100 and channels == 1 and pcm.dtype == np.float32 and np.array_equal(pcm, f)
+    # 24-bit PCM and garbage fail loudly
+    bio = io.BytesIO()
+    with wave.open(bio, "wb") as w:
+        w.setnchannels(1); w.setsampwidth(3); w.setframerate(48000); w.writeframes(b"\0" * 300)
+    with pytest.raises(gpudsp.JtError) as e:
+        gpudsp.wav_parse(bio.getvalue())
+    assert e.value.code == -5
+    with pytest.raises(gpudsp.JtError):
+        gpudsp.wav_parse(b"not a wav file at all")
