@@ -957,44 +957,3 @@ extern "C" double jt_adapt_gate_threshold(double vl, double sep, int *narrow) { 
 extern "C" double jt_adapt_gate_threshold_no_profile(double floor, double peak, double crest, double ratio, double gap) { return gate_threshold_no_profile(floor, peak, crest, ratio, gap); }
 extern "C" int jt_adapt_band_noise(const double *bands, int n, char *buf, size_t cap) { return copy_out(band_noise(bands, n), buf, cap); }
 
-// ---------------------------------------------------------------------------------------------------------------------
-// RIFF / WAVE header of an input file (the reference's tests and fixtures are s16 WAVs, testutil_test.go:140-190; the
-// reference itself decodes through libavformat, internal/audio/reader.go): where the PCM lies and what it is, so a caller
-// can hand the sample bytes of a memory-mapped file straight to jt_analyse / jt_process_audio*.  Host-only.
-// ---------------------------------------------------------------------------------------------------------------------
-static uint32_t rd_u32(const unsigned char *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
-static uint32_t rd_u16(const unsigned char *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
-
-extern "C" int jt_wav_parse(const void *bytes, int64_t n_bytes, int *sample_fmt, int *sample_rate, int *channels,
-                            int64_t *data_offset, int64_t *n_frames)
-{
-    const unsigned char *b = (const unsigned char *)bytes;
-    if (!b || n_bytes < 12 || memcmp(b, "RIFF", 4) || memcmp(b + 8, "WAVE", 4)) return JT_ERR_INVALID_ARG;
-    int64_t pos = 12; bool have_fmt = false; int tag = 0, ch = 0, rate = 0, bits = 0, align = 0;
-    while (pos + 8 <= n_bytes) {
-        const unsigned char *c = b + pos; const int64_t len = rd_u32(c + 4);
-        if (!memcmp(c, "fmt ", 4)) {
-            if (len < 16 || pos + 8 + 16 > n_bytes) return JT_ERR_INVALID_ARG;
-            tag = (int)rd_u16(c + 8); ch = (int)rd_u16(c + 10); rate = (int)rd_u32(c + 12); align = (int)rd_u16(c + 20); bits = (int)rd_u16(c + 22);
-            if (tag == 0xFFFE && len >= 40 && pos + 8 + 40 <= n_bytes) tag = (int)rd_u16(c + 8 + 24);      // WAVE_FORMAT_EXTENSIBLE: SubFormat
-            have_fmt = true;
-        } else if (!memcmp(c, "data", 4)) {
-            if (!have_fmt || ch <= 0 || rate <= 0) return JT_ERR_INVALID_ARG;
-            int fmt;
-            if (tag == 1 && bits == 16) fmt = JT_FMT_S16;
-            else if (tag == 1 && bits == 32) fmt = JT_FMT_S32;
-            else if (tag == 3 && bits == 32) fmt = JT_FMT_FLT;
-            else if (tag == 3 && bits == 64) fmt = JT_FMT_DBL;
-            else return JT_ERR_UNSUPPORTED;                                                                    // 8 / 24 bit, compressed
-            const int frame_bytes = ch * (bits / 8);
-            if (align && align != frame_bytes) return JT_ERR_INVALID_ARG;
-            int64_t avail = n_bytes - (pos + 8);
-            int64_t dl = (len == 0xFFFFFFFFll || len > avail) ? avail : len;                                 // streamed / truncated files
-            if (sample_fmt) *sample_fmt = fmt; if (sample_rate) *sample_rate = rate; if (channels) *channels = ch;
-            if (data_offset) *data_offset = pos + 8; if (n_frames) *n_frames = dl / frame_bytes;
-            return fmt == JT_FMT_S32 ? JT_ERR_UNSUPPORTED : JT_OK;                                            // described, but no s32 kernels yet
-        }
-        pos += 8 + len + (len & 1);
-    }
-    return JT_ERR_INVALID_ARG;
-}
