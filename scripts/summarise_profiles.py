@@ -21,7 +21,7 @@ if os.path.exists(src):
     for row in csv.DictReader(lines):
         if row.get("Metric Name") != "gpu__time_duration.sum":
             continue
-        name = re.sub(r"<.*", "", re.sub(r"\(.*", "", row["Kernel Name"])).replace("void ", "")
+        name = re.sub(r"<.*", "", re.sub(r"\(.*", "", row["Kernel Name"].replace("<unnamed>::", ""))).replace("void ", "")
         v = float(row["Metric Value"].replace(",", ""))
         u = row["Metric Unit"]
         ms = v / 1e6 if u.startswith("ns") else v / 1e3 if u.startswith("us") else v
