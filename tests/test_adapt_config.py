@@ -509,3 +509,32 @@ def test_apply_band_rms():                                 # analyser_bands.go:1
     assert va.noise_profile.bands_measured and va.noise_profile.n_band_noise == 15
     A.apply_band_rms(va, ([-30.0, 0.0], [1, 0]), ([math.nan] * 6 + noise[:9], [1] * 15))
     assert not va.speech_profile.bands_measured and not va.noise_profile.bands_measured     # 9 finite bands < afftdnMinFiniteBands
+
+
+def test_abi_argument_validation():
+    """whole-call failure with a negative code, never a partial result (SURVEY 8b error convention)"""
+    import ctypes as C
+    L = A._L()
+    m = A.new_measurements(input_i=-20.0)
+    va = A.VoiceActivity()
+    assert L.jt_detect_voice_activity(None, None, 0, C.byref(va), None, 0, None, 0) == -1
+    assert L.jt_detect_voice_activity(C.byref(m), None, 5, C.byref(va), None, 0, None, 0) == -1
+    assert L.jt_adapt_config(None, None, C.byref(va), C.byref(A.FilterConfig()), None) == -1
+    buf = C.create_string_buffer(16)
+    assert L.jt_build_filter_spec(C.byref(A.default_filter_config()), buf, 16) == -7          # JT_ERR_BUFFER
+    # a short regions buffer: JT_ERR_BUFFER, and nothing written to *out
+    # two speech runs separated by a loud interval the spectral veto rejects (the loud-gap guard, analyser_vad.go:531-536), then room tone
+    iv = [A.interval(i * A.HOP_NS, rms=-15.0, momentary=-15.0, centroid=9000.0 if i == 60 else 2000.0, entropy=0.4) for i in range(121)]
+    iv += [A.interval((121 + i) * A.HOP_NS, rms=-60.0, momentary=-60.0, centroid=2000.0, entropy=0.4) for i in range(60)]
+    arr = (A.Interval * len(iv))(*iv)
+    ok_va, runs, _ = A.detect_voice_activity(m, iv)
+    assert len(runs) >= 2
+    out = A.VoiceActivity()
+    one = (A.Region * 1)()
+    assert L.jt_detect_voice_activity(C.byref(m), arr, len(iv), C.byref(out), one, 1, None, 0) == -7
+    assert out.n_speech_regions == 0 and out.split == 0.0
+    # empty stream: the detector degrades to "unmeasured" (floor 0 -> AdaptConfig keeps the safe defaults, adaptive.go:151-155)
+    va0, runs0, cands0 = A.detect_voice_activity(m, [])
+    assert (va0.floor, va0.n_speech_regions, va0.has_noise_profile, va0.has_speech_profile) == (0.0, 0, 0, 0) and not runs0 and not cands0
+    cfg, _ = A.adapt_config(m, va0)
+    assert "afftdn=nr=12:nt=w:tn=1," in A.build_filter_spec(cfg)
