@@ -26,11 +26,11 @@ constexpr int FL_FRAME_CAP = 16 + 2 * FL_MAX_BS + 2 + 2; // header + verbatim su
 constexpr int FL_FRAME_WORDS = FL_FRAME_CAP / 4;
 constexpr int FL_MAX_PORDER = 6;
 static_assert(FL_FRAME_CAP % 4 == 0, "frame slots are copied as words");
+static_assert(FL_FRAME_WORDS >= 64 * 15, "the (u >> k) table borrows the frame buffer");
 
 struct FlWarp {                                          // per-warp shared memory
     int16_t x[FL_MAX_BS + 64];                           // lane chunks skewed by one word each: see FL_X
     uint32_t frame[FL_FRAME_WORDS];
-    uint32_t cell[64];                                   // sum of folded residuals per 1/64 of the block
     uint16_t col[16];                                    // CRC-16 "append L zero bytes" operator, one column per state bit
 };
 
@@ -112,37 +112,19 @@ k_flac_frames(const int16_t *__restrict__ pcm, int64_t n, int block_size, int ra
     for (int64_t f = (int64_t)blockIdx.x * FL_WARPS + warp; f < n_frames; f += (int64_t)gridDim.x * FL_WARPS) {
         const int64_t s0 = f * block_size;
         const int bs = (int)min((int64_t)block_size, n - s0);
-        // ---- stage samples, clear the frame ----
+        // ---- stage samples ----
         const int chunk = (bs + 31) / 32;
         const int xpad = (chunk >= 2 && (chunk & (chunk - 1)) == 0) ? -1 : 0, xsh = xpad ? 31 - __clz(chunk) : 0;
         int16_t *x = S.x;
         for (int i = lane; i < bs; i += 32) FL_X(i) = pcm[s0 + i];
-        for (int i = lane; i < FL_FRAME_WORDS; i += 32) S.frame[i] = 0;
         __syncwarp();
         uint8_t *fb = reinterpret_cast<uint8_t *>(S.frame);
-        // ---- frame header (lane 0) ----
-        int hdr_bytes = 0;
-        if (lane == 0) {
-            const int bs_code = bs == 4096 ? 12 : 7;
-            fb[0] = 0xFF; fb[1] = 0xF8; fb[2] = (uint8_t)((bs_code << 4) | fl_rate_code(rate)); fb[3] = 0x08;    // mono, 16 bit
-            int p = 4; const unsigned long long v = (unsigned long long)f;
-            if (v < 0x80) fb[p++] = (uint8_t)v;
-            else {
-                const int nb = v < 0x800 ? 2 : v < 0x10000 ? 3 : v < 0x200000 ? 4 : v < 0x4000000 ? 5 : v < 0x80000000ull ? 6 : 7;
-                const uint8_t lead[8] = {0, 0, 0xC0, 0xE0, 0xF0, 0xF8, 0xFC, 0xFE};
-                unsigned long long t = v;
-                for (int i = nb - 1; i > 0; i--) { fb[p + i] = (uint8_t)(0x80 | (t & 0x3F)); t >>= 6; }
-                fb[p] = (uint8_t)(lead[nb] | t);
-                p += nb;
-            }
-            if (bs_code == 7) { fb[p++] = (uint8_t)((bs - 1) >> 8); fb[p++] = (uint8_t)(bs - 1); }
-            uint8_t c = 0;
-            for (int i = 0; i < p; i++) { c ^= fb[i]; for (int b = 0; b < 8; b++) c = (uint8_t)((c & 0x80) ? (c << 1) ^ 0x07 : (c << 1)); }
-            fb[p++] = c;
-            hdr_bytes = p;
-        }
-        hdr_bytes = __shfl_sync(0xffffffffu, hdr_bytes, 0);
-        __syncwarp();
+        uint32_t *tab = S.frame;                          // until the frame is written its buffer holds the (u >> k) table: 64 cells x 15
+        // frame header length: sync + flags (4), coded frame number, 16-bit block size unless 4096, CRC-8
+        const unsigned long long fno = (unsigned long long)f;
+        const int ulen = fno < 0x80 ? 1 : fno < 0x800 ? 2 : fno < 0x10000 ? 3 : fno < 0x200000 ? 4 : fno < 0x4000000 ? 5 : fno < 0x80000000ull ? 6 : 7;
+        const int bs_code = bs == 4096 ? 12 : 7;
+        const int hdr_bytes = 4 + ulen + (bs_code == 7 ? 2 : 0) + 1;
         const int sub0 = hdr_bytes * 8;                   // first bit of the subframe
         // ---- lane ranges: [lo, mid) and [mid, hi) are the lane's two cells when the block divides into 64 ----
         const bool cells = (bs % 64) == 0;
@@ -166,27 +148,35 @@ k_flac_frames(const int16_t *__restrict__ pcm, int64_t n, int block_size, int ra
             }
         }
         const bool constant = __all_sync(0xffffffffu, equal);
-        int total_bits;                                   // bits of header + subframe before padding
-        if (constant) {
-            if (lane == 0) { fl_put(S.frame, sub0, 8, 0x00); fl_put(S.frame, sub0 + 8, 16, (uint16_t)FL_X(0)); }
-            total_bits = sub0 + 24;
-        } else {
+        // ---- decisions (no frame bytes yet) ----
+        int order = 0, best_p = 0, bk0 = 0, bk1 = 0, a0 = lo, a1 = mid;
+        bool verbatim = false, open0 = false, open1 = false;
+        unsigned lane_bits = 0;
+        if (!constant) {
             e0 = fl_warp_sum_u64(e0); e1 = fl_warp_sum_u64(e1); e2 = fl_warp_sum_u64(e2); e3 = fl_warp_sum_u64(e3); e4 = fl_warp_sum_u64(e4);
-            int order = 0; unsigned long long best_err = e0;
+            unsigned long long best_err = e0;
             if (bs > 1 && e1 < best_err) { best_err = e1; order = 1; }
             if (bs > 2 && e2 < best_err) { best_err = e2; order = 2; }
             if (bs > 3 && e3 < best_err) { best_err = e3; order = 3; }
             if (bs > 4 && e4 < best_err) { best_err = e4; order = 4; }
-            // ---- per-cell sums of the folded residual ----
-            const int a0 = max(lo, order), a1 = max(mid, order);          // residual samples of the two cells: [a0, mid), [a1, hi)
-            uint32_t c0 = 0, c1 = 0;
-            FL_FOR_RES(a0, mid, c0 += fl_fold(r));
-            FL_FOR_RES(a1, hi, c1 += fl_fold(r));
-            S.cell[2 * lane] = c0; S.cell[2 * lane + 1] = c1;
+            a0 = max(lo, order); a1 = max(mid, order);                    // residual samples of the two cells: [a0, mid), [a1, hi)
+            // one pass: per cell, the sum of (u >> k) for every Rice parameter k (k = 0 is the plain sum that picks the parameter)
+            {
+                uint32_t t0[15], t1[15];
+#pragma unroll
+                for (int k = 0; k < 15; k++) { t0[k] = 0; t1[k] = 0; }
+                FL_FOR_RES(a0, mid, { const uint32_t u = fl_fold(r);
+                    _Pragma("unroll") for (int k = 0; k < 15; k++) t0[k] += u >> k; });
+                FL_FOR_RES(a1, hi, { const uint32_t u = fl_fold(r);
+                    _Pragma("unroll") for (int k = 0; k < 15; k++) t1[k] += u >> k; });
+#pragma unroll
+                for (int k = 0; k < 15; k++) { tab[(2 * lane) * 15 + k] = t0[k]; tab[(2 * lane + 1) * 15 + k] = t1[k]; }
+            }
             __syncwarp();
+            const unsigned cnt0 = (unsigned)max(0, mid - a0), cnt1 = (unsigned)max(0, hi - a1);
             int pmax = 0;
             if (cells) { pmax = FL_MAX_PORDER; while (pmax > 0 && (bs >> pmax) <= order) pmax--; }
-            int best_p = 0, bk0 = 0, bk1 = 0; unsigned long long best_bits = ~0ull;
+            unsigned long long best_bits = ~0ull; unsigned best_lane = 0;
             for (int p = 0; p <= pmax; p++) {
                 const int per = 64 >> p;                                  // cells per partition
                 const int psz = bs >> p;
@@ -194,59 +184,82 @@ k_flac_frames(const int16_t *__restrict__ pcm, int64_t n, int block_size, int ra
                 {
                     const int j = (2 * lane) / per;
                     unsigned long long s = 0;
-                    for (int g = j * per; g < (j + 1) * per; g++) s += S.cell[g];
+                    for (int g = j * per; g < (j + 1) * per; g++) s += tab[g * 15];
                     k0 = fl_optimal_param(s, psz - (j == 0 ? order : 0));
                 }
                 {
                     const int j = (2 * lane + 1) / per;
                     unsigned long long s = 0;
-                    for (int g = j * per; g < (j + 1) * per; g++) s += S.cell[g];
+                    for (int g = j * per; g < (j + 1) * per; g++) s += tab[g * 15];
                     k1 = fl_optimal_param(s, psz - (j == 0 ? order : 0));
                 }
-                unsigned long long bits = 0;
-                FL_FOR_RES(a0, mid, bits += (fl_fold(r) >> k0) + (unsigned)(k0 + 1));
-                FL_FOR_RES(a1, hi, bits += (fl_fold(r) >> k1) + (unsigned)(k1 + 1));
-                bits = fl_warp_sum_u64(bits) + 4ull * (unsigned long long)(1 << p);
-                if (bits < best_bits) { best_bits = bits; best_p = p; bk0 = k0; bk1 = k1; }
+                const unsigned mine = cnt0 * (unsigned)(k0 + 1) + tab[(2 * lane) * 15 + k0] + cnt1 * (unsigned)(k1 + 1) + tab[(2 * lane + 1) * 15 + k1];
+                const unsigned long long bits = fl_warp_sum_u64((unsigned long long)mine) + 4ull * (unsigned long long)(1 << p);
+                if (bits < best_bits) { best_bits = bits; best_p = p; bk0 = k0; bk1 = k1; best_lane = mine; }
             }
             const unsigned long long fixed_bits = 8ull + 16ull * (unsigned)order + 6ull + best_bits, verbatim_bits = 8ull + 16ull * (unsigned)bs;
-            if (fixed_bits >= verbatim_bits) {
-                if (lane == 0) fl_put(S.frame, sub0, 8, 0x02);
-                for (int i = lo; i < hi; i++) fl_put(S.frame, sub0 + 8 + 16 * i, 16, (uint16_t)FL_X(i));
-                total_bits = sub0 + 8 + 16 * bs;
-            } else {
-                const int per = 64 >> best_p;
-                // a cell opens a partition (4-bit parameter in front of it) when it is the partition's first cell
-                const bool open0 = cells ? ((2 * lane) % per) == 0 : lane == 0;
-                const bool open1 = cells ? ((2 * lane + 1) % per) == 0 : false;
-                unsigned lane_bits = (open0 ? 4u : 0u) + (open1 ? 4u : 0u);
-                FL_FOR_RES(a0, mid, lane_bits += (fl_fold(r) >> bk0) + (unsigned)(bk0 + 1));
-                FL_FOR_RES(a1, hi, lane_bits += (fl_fold(r) >> bk1) + (unsigned)(bk1 + 1));
-                unsigned incl = lane_bits;
-                for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-                const int base = sub0 + 8 + 16 * order + 6;
-                int pos = base + (int)(incl - lane_bits);
-                total_bits = base + (int)__shfl_sync(0xffffffffu, incl, 31);
-                if (lane == 0) {
-                    fl_put(S.frame, sub0, 8, (uint32_t)((0x08 | order) << 1));
-                    for (int i = 0; i < order; i++) fl_put(S.frame, sub0 + 8 + 16 * i, 16, (uint16_t)FL_X(i));
-                    fl_put(S.frame, sub0 + 8 + 16 * order, 6, (uint32_t)best_p);       // method 00 + partition order
-                }
-                if (open0) { fl_put(S.frame, pos, 4, (uint32_t)bk0); pos += 4; }
-                FL_FOR_RES(a0, mid, {
-                    const uint32_t u = fl_fold(r);
-                    pos += (int)(u >> bk0);
-                    fl_put(S.frame, pos, bk0 + 1, (1u << bk0) | (u & ((1u << bk0) - 1)));          // the unary stop bit and the k low bits
-                    pos += bk0 + 1;
-                });
-                if (open1) { fl_put(S.frame, pos, 4, (uint32_t)bk1); pos += 4; }
-                FL_FOR_RES(a1, hi, {
-                    const uint32_t u = fl_fold(r);
-                    pos += (int)(u >> bk1);
-                    fl_put(S.frame, pos, bk1 + 1, (1u << bk1) | (u & ((1u << bk1) - 1)));
-                    pos += bk1 + 1;
-                });
+            verbatim = fixed_bits >= verbatim_bits;
+            const int per = 64 >> best_p;
+            // a cell opens a partition (4-bit parameter in front of it) when it is the partition's first cell
+            open0 = cells ? ((2 * lane) % per) == 0 : lane == 0;
+            open1 = cells ? ((2 * lane + 1) % per) == 0 : false;
+            lane_bits = best_lane + (open0 ? 4u : 0u) + (open1 ? 4u : 0u);
+        }
+        __syncwarp();                                     // the table has been read: the buffer becomes the frame
+        for (int i = lane; i < FL_FRAME_WORDS; i += 32) S.frame[i] = 0;
+        __syncwarp();
+        // ---- frame header (lane 0) ----
+        if (lane == 0) {
+            fb[0] = 0xFF; fb[1] = 0xF8; fb[2] = (uint8_t)((bs_code << 4) | fl_rate_code(rate)); fb[3] = 0x08;    // mono, 16 bit
+            int p = 4;
+            if (ulen == 1) fb[p++] = (uint8_t)fno;
+            else {
+                const uint8_t lead[8] = {0, 0, 0xC0, 0xE0, 0xF0, 0xF8, 0xFC, 0xFE};
+                unsigned long long t = fno;
+                for (int i = ulen - 1; i > 0; i--) { fb[p + i] = (uint8_t)(0x80 | (t & 0x3F)); t >>= 6; }
+                fb[p] = (uint8_t)(lead[ulen] | t);
+                p += ulen;
             }
+            if (bs_code == 7) { fb[p++] = (uint8_t)((bs - 1) >> 8); fb[p++] = (uint8_t)(bs - 1); }
+            uint8_t c = 0;
+            for (int i = 0; i < p; i++) { c ^= fb[i]; for (int b = 0; b < 8; b++) c = (uint8_t)((c & 0x80) ? (c << 1) ^ 0x07 : (c << 1)); }
+            fb[p] = c;
+        }
+        __syncwarp();
+        // ---- subframe ----
+        int total_bits;                                   // bits of header + subframe before padding
+        if (constant) {
+            if (lane == 0) { fl_put(S.frame, sub0, 8, 0x00); fl_put(S.frame, sub0 + 8, 16, (uint16_t)FL_X(0)); }
+            total_bits = sub0 + 24;
+        } else if (verbatim) {
+            if (lane == 0) fl_put(S.frame, sub0, 8, 0x02);
+            for (int i = lo; i < hi; i++) fl_put(S.frame, sub0 + 8 + 16 * i, 16, (uint16_t)FL_X(i));
+            total_bits = sub0 + 8 + 16 * bs;
+        } else {
+            unsigned incl = lane_bits;
+            for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+            const int base = sub0 + 8 + 16 * order + 6;
+            int pos = base + (int)(incl - lane_bits);
+            total_bits = base + (int)__shfl_sync(0xffffffffu, incl, 31);
+            if (lane == 0) {
+                fl_put(S.frame, sub0, 8, (uint32_t)((0x08 | order) << 1));
+                for (int i = 0; i < order; i++) fl_put(S.frame, sub0 + 8 + 16 * i, 16, (uint16_t)FL_X(i));
+                fl_put(S.frame, sub0 + 8 + 16 * order, 6, (uint32_t)best_p);       // method 00 + partition order
+            }
+            if (open0) { fl_put(S.frame, pos, 4, (uint32_t)bk0); pos += 4; }
+            FL_FOR_RES(a0, mid, {
+                const uint32_t u = fl_fold(r);
+                pos += (int)(u >> bk0);
+                fl_put(S.frame, pos, bk0 + 1, (1u << bk0) | (u & ((1u << bk0) - 1)));          // the unary stop bit and the k low bits
+                pos += bk0 + 1;
+            });
+            if (open1) { fl_put(S.frame, pos, 4, (uint32_t)bk1); pos += 4; }
+            FL_FOR_RES(a1, hi, {
+                const uint32_t u = fl_fold(r);
+                pos += (int)(u >> bk1);
+                fl_put(S.frame, pos, bk1 + 1, (1u << bk1) | (u & ((1u << bk1) - 1)));
+                pos += bk1 + 1;
+            });
         }
         __syncwarp();
         // ---- CRC-16 over the padded frame: lanes take 1/32 each of the right-aligned bytes, then chain ----
