@@ -74,6 +74,40 @@ def build_ref():
     return _REF_BIN
 
 
+_REF_ENC = os.path.join(_HERE, "_ref", "ref_flac_encode")
+
+
+def build_ref_encoder():
+    if os.path.exists(_REF_ENC):
+        return _REF_ENC
+    libs = [sorted(glob.glob(os.path.join(_LIBDIR, p))) for p in ("libavcodec-*", "libavutil-*", "libswresample-*")]
+    if not os.path.isdir(_REF_INC) or not all(libs):
+        return None
+    os.makedirs(os.path.dirname(_REF_ENC), exist_ok=True)
+    cmd = ["gcc", "-O1", "-o", _REF_ENC, os.path.join(_HERE, "ref_flac_enc_probe.c"), "-I" + _REF_INC] + [l[0] for l in libs] + \
+          ["-Wl,-rpath," + _LIBDIR, "-Wl,--allow-shlib-undefined", "-lm"]
+    try:
+        subprocess.check_call(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    except (subprocess.CalledProcessError, OSError):
+        return None
+    return _REF_ENC
+
+
+def ref_encode(pcm, rate=44100, level=5):
+    """REAL libavcodec FLAC encoder (LPC, 4096-sample frames) -> stream bytes, or None when the probe / libraries are absent"""
+    exe = build_ref_encoder()
+    if exe is None or not os.path.isdir(_LIBDIR):
+        return None
+    with tempfile.TemporaryDirectory() as d:
+        fi, fo = os.path.join(d, "a.raw"), os.path.join(d, "a.flac")
+        np.ascontiguousarray(pcm, dtype=np.int16).tofile(fi)
+        env = dict(os.environ, LD_LIBRARY_PATH=_LIBDIR + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+        r = subprocess.run([exe, fi, fo, str(rate), str(level)], capture_output=True, text=True, env=env)
+        if r.returncode != 0:
+            raise RuntimeError(f"ref_flac_encode rc={r.returncode}: {r.stdout} {r.stderr}")
+        return open(fo, "rb").read()
+
+
 def ref_decode(stream):
     """REAL libavcodec -> (int16 array, rate, channels) or None when the probe / libraries are absent"""
     exe = build_ref()

@@ -69,3 +69,16 @@ def test_decoder_rejects_corruption():
     bad = bytearray(stream); bad[42 + 500] ^= 0x01          # residual bits -> CRC-16 (or a syntax error on the way)
     with pytest.raises(ValueError):
         ref_flac.decode(bytes(bad), len(x) + 16)
+
+
+@pytest.mark.parametrize("name", ["speech", "ragged", "clipped", "mixed", "extremes", "silence", "white_full_scale"])
+@pytest.mark.parametrize("level", [0, 5, 8])
+def test_oracle_decoder_on_real_libavcodec_streams(name, level):
+    """the other direction: streams written by the REAL libavcodec encoder (LPC subframes at the reference's level 5) decode
+    bit for bit with the oracle's decoder -- the checker a GPU FLAC decoder of the input side will be held against"""
+    x = SIG[name]
+    stream = ref_flac.ref_encode(x, 44100, level)
+    if stream is None:
+        pytest.skip("FFmpeg libavcodec / reference headers not present")
+    y, rate = ref_flac.decode(stream, len(x) + 16)
+    assert rate == 44100 and np.array_equal(x, y)
