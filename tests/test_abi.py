@@ -109,3 +109,45 @@ def test_wav_parse(tmp_path):
     assert e.value.code == -5
     with pytest.raises(gpudsp.JtError):
         gpudsp.wav_parse(b"not a wav file at all")
+
+
+def test_limiter_planners_match_reference_tables():
+    """a9 planners through jt_build_pass3_spec / jt_build_pass4_spec against the reference's tables:
+    TestCalculateLimiterCeiling (normalise_test.go:1204-1388), TestCalculatePreGain (:1987-2044),
+    TestPreGainCeilingRederivation (:1764-1852), TestLoudnormInternalTargetTPCancellation (:1029-1062)."""
+    import pytest
+    from jivetalking_b200 import gpudsp
+    MIN = -24.0
+    table = [  # measuredI, measuredTP, targetI, targetTP, wantCeiling, wantNeeded, wantClamped
+        (-24.9, -5.0, -16.0, -2.0, -10.9, True, False), (-20.0, -3.0, -16.0, -2.0, -6.0, True, False),
+        (-20.0, -10.0, -16.0, -2.0, 0.0, False, False), (-12.0, -1.0, -16.0, -2.0, 0.0, False, False),
+        (-20.0, -6.0, -16.0, -2.0, 0.0, False, False), (-43.0, -20.0, -16.0, -2.0, MIN, True, True),
+        (-40.0, -15.0, -16.0, -2.0, MIN, True, True), (-33.5, -15.0, -16.0, -2.0, -19.5, True, False),
+        (-43.2, -18.6, -16.0, -2.0, MIN, True, True), (-36.6, -15.0, -16.0, -2.0, -22.6, True, False)]
+    for mi, mtp, ti, ttp, want, needed, clamped in table:
+        spec3, plan = gpudsp.build_pass3_spec(mi, mtp, ti, ttp)
+        assert bool(plan.limiter_needed) == needed and bool(plan.limiter_clamped) == clamped, (mi, mtp)
+        if needed:
+            # a clamped ceiling is re-derived after the pre-gain and lands on the minimum again (TestPreGainCeilingRederivation)
+            assert abs(plan.limiter_ceiling_db - want) < 0.01, (mi, mtp, plan.limiter_ceiling_db)
+            assert ("alimiter=limit=%.6f" % 10 ** (plan.limiter_ceiling_db / 20)) in spec3
+        else:
+            assert "alimiter" not in spec3 and "volume" not in spec3
+        ideal = ttp - (ti - mi)
+        assert abs(plan.limiter_pregain_db - (MIN - ideal if ideal < MIN else 0.0)) < 1e-9
+        assert (("volume=%.1fdB," % plan.limiter_pregain_db) in spec3) == (clamped and plan.limiter_pregain_db > 0)
+    # TestCalculatePreGain
+    for mi, want_gain, want_ceil in ((-43.2, 5.2, -24.0), (-24.9, 0.0, None), (-38.0, 0.0, None)):
+        _, plan = gpudsp.build_pass3_spec(mi, -10.0 if want_ceil is None else -18.6, -16.0, -2.0)
+        assert abs(plan.limiter_pregain_db - want_gain) < 0.01
+        if want_ceil is not None:
+            assert abs(plan.limiter_ceiling_db - want_ceil) < 0.01
+    # the internal TP target cancels out: linear mode always reaches the desired loudness, emitted TP clamped to [-9, 0]
+    for mi, mtp in ((-24.9, -5.0), (-36.5, -24.0), (-12.0, -1.0), (-30.0, -3.0)):
+        _, plan = gpudsp.build_pass3_spec(mi, mtp)
+        st = gpudsp.LoudnormStats()
+        st.input_i, st.input_tp, st.input_lra, st.input_thresh = mi, mtp, 6.0, mi - 10.0
+        spec4, eff, off = gpudsp.build_pass4_spec(plan, st)
+        assert eff == pytest.approx(-16.0) and off == pytest.approx(-16.0 - mi)
+        tp = float(spec4.split("loudnorm=")[1].split(":TP=")[1].split(":")[0])
+        assert -9.0 <= tp <= 0.0 and abs(tp - max(-9.0, min(0.0, mtp + (-16.0 - mi) + 0.3))) < 0.006
