@@ -151,3 +151,28 @@ def test_limiter_planners_match_reference_tables():
         assert eff == pytest.approx(-16.0) and off == pytest.approx(-16.0 - mi)
         tp = float(spec4.split("loudnorm=")[1].split(":TP=")[1].split(":")[0])
         assert -9.0 <= tp <= 0.0 and abs(tp - max(-9.0, min(0.0, mtp + (-16.0 - mi) + 0.3))) < 0.006
+
+
+def test_loudnorm_stats_json_has_the_reference_wire_shape():
+    """jt_loudnorm_stats_json renders what af_loudnorm writes to stats_file: the ten keys of LoudnormStats
+    (normalise.go:64-75) as decimal STRINGS ("%.2f"), which the reference parses with strconv.ParseFloat
+    (normalise.go:321-343; fixture shape: normalise_test.go:19)."""
+    import ctypes as C
+    import json
+    from jivetalking_b200 import gpudsp
+    L = gpudsp.lib()
+    st = gpudsp.LoudnormStats()
+    st.input_i, st.input_tp, st.input_lra, st.input_thresh = -23.004, -4.0, 5.0, -33.0
+    st.output_i, st.output_tp, st.output_lra, st.output_thresh = -16.0, -2.0, 5.0, -26.0
+    st.target_offset, st.normalization_type, st.valid = 0.0, 0, 1
+    buf = C.create_string_buffer(1024)
+    assert L.jt_loudnorm_stats_json(C.byref(st), buf, len(buf)) == 0
+    doc = json.loads(buf.value.decode())
+    assert sorted(doc) == sorted(["input_i", "input_tp", "input_lra", "input_thresh", "output_i", "output_tp", "output_lra",
+                                  "output_thresh", "normalization_type", "target_offset"])
+    assert all(isinstance(v, str) for v in doc.values())
+    assert doc["input_i"] == "-23.00" and doc["normalization_type"] == "linear" and float(doc["output_tp"]) == -2.0
+    st.normalization_type = 1
+    L.jt_loudnorm_stats_json(C.byref(st), buf, len(buf))
+    assert json.loads(buf.value.decode())["normalization_type"] == "dynamic"
+    assert L.jt_loudnorm_stats_json(C.byref(st), buf, 10) == -7
