@@ -75,7 +75,8 @@ int orc_astats(const void *xv, int fmt, int64_t n, int rate, orc_astats_out *o)
         {
             double a = fabs(nd); if (a > 1.0) a = 1.0;
             long idx = lrint(a * HISTOGRAM_MAX);
-            if (idx < 0) idx = 0; if (idx > HISTOGRAM_MAX) idx = HISTOGRAM_MAX;
+            if (idx < 0) idx = 0;
+            if (idx > HISTOGRAM_MAX) idx = HISTOGRAM_MAX;
             ehist[idx]++;
         }
         if (nb_samples >= (uint64_t)tc_samples) {
