@@ -108,6 +108,35 @@ def ref_encode(pcm, rate=44100, level=5):
         return open(fo, "rb").read()
 
 
+_REF_WAV = os.path.join(_HERE, "_ref", "ref_wav_read")
+
+
+def ref_wav_read(data):
+    """REAL libavformat + libavcodec read of a file image -> (interleaved numpy samples, rate, channels) or None"""
+    if not os.path.exists(_REF_WAV):
+        libs = [sorted(glob.glob(os.path.join(_LIBDIR, p))) for p in ("libavformat-*", "libavcodec-*", "libavutil-*", "libswresample-*")]
+        if not os.path.isdir(_REF_INC) or not all(libs):
+            return None
+        os.makedirs(os.path.dirname(_REF_WAV), exist_ok=True)
+        cmd = ["gcc", "-O1", "-o", _REF_WAV, os.path.join(_HERE, "ref_wav_probe.c"), "-I" + _REF_INC] + [l[0] for l in libs] + \
+              ["-Wl,-rpath," + _LIBDIR, "-Wl,--allow-shlib-undefined", "-lm"]
+        try:
+            subprocess.check_call(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        except (subprocess.CalledProcessError, OSError):
+            return None
+    with tempfile.TemporaryDirectory() as d:
+        fi, fo = os.path.join(d, "a.wav"), os.path.join(d, "a.raw")
+        with open(fi, "wb") as f:
+            f.write(data)
+        env = dict(os.environ, LD_LIBRARY_PATH=_LIBDIR + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+        r = subprocess.run([_REF_WAV, fi, fo], capture_output=True, text=True, env=env)
+        if r.returncode != 0:
+            raise RuntimeError(f"ref_wav_read rc={r.returncode}: {r.stdout} {r.stderr}")
+        info = dict(kv.split("=") for kv in r.stdout.split())
+        dt = {1: np.int16, 2: np.int32, 3: np.float32, 4: np.float64}[int(info["fmt"])]
+        return np.fromfile(fo, dtype=dt), int(info["rate"]), int(info["channels"])
+
+
 def ref_decode(stream):
     """REAL libavcodec -> (int16 array, rate, channels) or None when the probe / libraries are absent"""
     exe = build_ref()

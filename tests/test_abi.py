@@ -88,18 +88,29 @@ def test_wav_parse(tmp_path):
     import pytest
     from jivetalking_b200 import gpudsp
     x = (np.arange(2000) % 257 - 128).astype(np.int16)
+    wavs = []
     for ch in (1, 2):
         bio = io.BytesIO()
         with wave.open(bio, "wb") as w:
             w.setnchannels(ch); w.setsampwidth(2); w.setframerate(48000); w.writeframes(x.tobytes())
+        wavs.append(bio.getvalue())
         pcm, rate, channels = gpudsp.wav_parse(bio.getvalue())
         assert (rate, channels) == (48000, ch) and pcm.dtype == np.int16 and np.array_equal(pcm, x)
     # float32 WAV with a LIST chunk in front of the data and an odd-sized chunk (padding byte)
     f = np.linspace(-1, 1, 333, dtype=np.float32)
     fmt = struct.pack("<HHIIHH", 3, 1, 44100, 44100 * 4, 4, 32)
     body = b"WAVE" + b"fmt " + struct.pack("<I", 16) + fmt + b"LIST" + struct.pack("<I", 5) + b"abcde\0" + b"data" + struct.pack("<I", f.nbytes) + f.tobytes()
-    pcm, rate, channels = gpudsp.wav_parse(b"RIFF" + struct.pack("<I", len(body)) + body)
+    wavs.append(b"RIFF" + struct.pack("<I", len(body)) + body)
+    pcm, rate, channels = gpudsp.wav_parse(wavs[-1])
     assert rate == 44100 and channels == 1 and pcm.dtype == np.float32 and np.array_equal(pcm, f)
+    # ... and the reference's actual reader (libavformat demuxer + libavcodec PCM decoder, internal/audio/reader.go) sees
+    # the same samples in every case above, when the real FFmpeg libraries are in the image
+    import ref_flac
+    for data in wavs:
+        ref = ref_flac.ref_wav_read(data)
+        if ref is not None:
+            g, grate, gch = gpudsp.wav_parse(data)
+            assert (ref[1], ref[2]) == (grate, gch) and ref[0].dtype == g.dtype and np.array_equal(ref[0], g)
     # 24-bit PCM and garbage fail loudly
     bio = io.BytesIO()
     with wave.open(bio, "wb") as w:
