@@ -208,6 +208,7 @@ static int spec_out_rate(const char *spec, int rate)
         for (const FilterNode &f : jt_parse_spec(spec ? spec : "")) {
             if (f.name == "aformat") rate = (int)f.num("sample_rates", "r", rate);
             else if (f.name == "aresample") { if (const std::string *p = f.get("")) rate = atoi(p->c_str()); }
+            else if (f.name == "loudnorm" && !jt_loudnorm_linear_mode(f)) rate = 192000;
         }
     } catch (const JtError &) {}
     return rate;
@@ -595,12 +596,7 @@ static ChunkGeometry chunk_geometry(const char *spec, int rate)
             U = lcm64(U, unit_for(rate, r, hop));
         } else if (f.name == "ebur128") { if (r % 10) JT_THROW(JT_ERR_UNSUPPORTED, "ebur128 at %d Hz", r); U = lcm64(U, unit_for(rate, r, r / 10)); }
         else if (f.name == "loudnorm") {
-            const bool linear = f.flag("linear", "", true);
-            const double I = f.num("I", "i", -24), TP = f.num("TP", "tp", -2), LRA = f.num("LRA", "lra", 7);
-            const double mI = f.num("measured_I", "measured_i", 0), mTP = f.num("measured_TP", "measured_tp", 99);
-            const double mLRA = f.num("measured_LRA", "measured_lra", 0), mTh = f.num("measured_thresh", "", -70);
-            const bool lin_mode = linear && mTP != 99 && mTh != -70 && mLRA != 0 && mI != 0 && mTP + (I - mI) <= TP && mLRA <= LRA;
-            if (!lin_mode) nr = 192000;
+            if (!jt_loudnorm_linear_mode(f)) nr = 192000;
             U = lcm64(U, unit_for(rate, nr, (nr + 5) / 10));
         } else if (f.name == "atrim") JT_THROW(JT_ERR_UNSUPPORTED, "atrim in a chunked graph");
         if (nr != r) { if (nr <= 0) JT_THROW(JT_ERR_SPEC, "bad rate in %s", f.name.c_str()); U = lcm64(U, unit_for(rate, nr, 1)); r = nr; }
@@ -634,7 +630,7 @@ extern "C" int64_t jt_graph_chunk_bytes(const char *spec, int64_t owned, int rat
     (void)spec;
     if (rate <= 0 || owned < 0) return 0;
     // ticks on a link of at most 192 kHz (same count as on the input link), spectral rows: at most one per input tick
-    const int64_t nt = owned / std::max(rate / 10, 1) + 4;
+    const int64_t nt = owned / std::max(rate / 10, 1) + 4 + 32;       // + the re-metered flush frame of dynamic loudnorm (2.9 s)
     return (int64_t)sizeof(JtGraphChunkHdr) + nt * (3 * 8 + 2 * 8 + 2 * 8 + 8 + JT_SP_COUNT * 4) + (int64_t)jt_astats_host_bytes() + 256;
 }
 
@@ -739,9 +735,16 @@ extern "C" int jt_graph_chunk(jt_ctx *c, const char *spec, const void *pcm_local
             if (nticks < 0) nticks = 0;
             if (loc_tick0 + nticks > pd.nt) JT_THROW(JT_ERR_INVALID_ARG, "internal: local meter tick range");
         };
+        LoudnormPending ltail; int64_t ltail_first = 0, li_split = 0;     // dynamic mode: the flush frame is metered twice (last chunk)
         if (gd.has_ln && blob) {
             meter(gl.ln_in_sig, gd.ln_in_sig.n, li, li_loc, h.li_tick0, h.li_nticks);
             if (gd.ln_linear) meter(gl.ln_out_sig, gd.ln_out_sig.n, lo, lo_loc, h.lo_tick0, h.lo_nticks);
+            if (last && gd.ln_dynamic && gd.ln_in_extra) {
+                const int s100 = (gl.ln_in_sig.rate + 5) / 10;
+                jt_loudnorm_tail_launch(c, gl.ln_in_sig, gd.ln_in_sig.n, gd.ln_dual, ltail, &ltail_first);
+                li_split = gd.ln_in_sig.n / s100;                     // ticks from here on come from the tail run
+                h.li_nticks = ltail_first + ltail.nt - h.li_tick0;
+            }
         }
         // ---- the owned part of the sink audio ----
         {
@@ -786,7 +789,15 @@ extern "C" int jt_graph_chunk(jt_ctx *c, const char *spec, const void *pcm_local
         }
         if (ap.host && h.astats_n > 0) memcpy(w, ap.host, h.astats_bytes); else memset(w, 0, h.astats_bytes);
         w += h.astats_bytes;
-        if (h.li_nticks > 0) { memcpy(w, li.hp + li_loc, 8 * h.li_nticks); w += 8 * h.li_nticks; memcpy(w, li.hk + li_loc, 8 * h.li_nticks); w += 8 * h.li_nticks; }
+        if (h.li_nticks > 0) {
+            std::vector<double> tp(h.li_nticks), tk(h.li_nticks);
+            for (int64_t k = 0; k < h.li_nticks; k++) {
+                const int64_t gt = h.li_tick0 + k;
+                if (ltail.nt > 0 && gt >= li_split) { tp[k] = ltail.hp[gt - ltail_first]; tk[k] = ltail.hk[gt - ltail_first]; }
+                else { tp[k] = li.hp[li_loc + k]; tk[k] = li.hk[li_loc + k]; }
+            }
+            memcpy(w, tp.data(), 8 * h.li_nticks); w += 8 * h.li_nticks; memcpy(w, tk.data(), 8 * h.li_nticks); w += 8 * h.li_nticks;
+        }
         if (h.lo_nticks > 0) { memcpy(w, lo.hp + lo_loc, 8 * h.lo_nticks); w += 8 * h.lo_nticks; memcpy(w, lo.hk + lo_loc, 8 * h.lo_nticks); w += 8 * h.lo_nticks; }
         if (blob_bytes) *blob_bytes = need;
     });
@@ -819,7 +830,8 @@ extern "C" int jt_graph_merge(const char *spec, int64_t total, int rate, int cha
         const int hs_sp = gd.spec_win / 2;
         const int64_t n_hops = gd.has_spec ? (gd.spec_sig.n + hs_sp - 1) / hs_sp : 0;
         const int s_in = gd.has_ln ? (gd.ln_in_sig.rate + 5) / 10 : 1, s_out = gd.has_ln && gd.ln_linear ? (gd.ln_out_sig.rate + 5) / 10 : 1;
-        const int64_t li_nt = gd.has_ln ? (gd.ln_in_sig.n + s_in - 1) / s_in : 0, lo_nt = gd.has_ln && gd.ln_linear ? (gd.ln_out_sig.n + s_out - 1) / s_out : 0;
+        const int64_t li_n = gd.has_ln ? gd.ln_in_sig.n + gd.ln_in_extra : 0;      // dynamic mode meters the flush frame a second time
+        const int64_t li_nt = gd.has_ln ? (li_n + s_in - 1) / s_in : 0, lo_nt = gd.has_ln && gd.ln_linear ? (gd.ln_out_sig.n + s_out - 1) / s_out : 0;
         std::vector<double> hp(nt), hk(nt), ht(nt), lip(li_nt), lik(li_nt), lop(lo_nt), lok(lo_nt);
         std::vector<float> rows((size_t)n_hops * JT_SP_COUNT, 0.f);
         std::vector<char> as(jt_astats_host_bytes());
@@ -855,7 +867,7 @@ extern "C" int jt_graph_merge(const char *spec, int64_t total, int rate, int cha
         GraphResult res; memset(&res.ln, 0, sizeof(res.ln));
         if (gd.has_ln) {
             LoudnormMeter mi, mo;
-            jt_loudnorm_meter_host_finalize(lip.data(), lik.data(), li_nt, gd.ln_in_sig.n / s_in, s_in, gd.ln_dual, mi);
+            jt_loudnorm_meter_host_finalize(lip.data(), lik.data(), li_nt, li_n / s_in, s_in, gd.ln_dual, mi);
             res.ln.valid = 1;
             if (gd.ln_linear) {
                 jt_loudnorm_meter_host_finalize(lop.data(), lok.data(), lo_nt, gd.ln_out_sig.n / s_out, s_out, gd.ln_dual, mo);
@@ -863,7 +875,7 @@ extern "C" int jt_graph_merge(const char *spec, int64_t total, int rate, int cha
                 res.ln.output_i = mo.I; res.ln.output_tp = 20. * log10(mo.sample_peak); res.ln.output_lra = mo.LRA; res.ln.output_thresh = mo.thresh;
                 res.ln.target_offset = gd.ln_I - mo.I;
             } else {
-                res.ln.normalization_type = 1;
+                res.ln.normalization_type = gd.ln_type;
                 res.ln.output_i = res.ln.output_tp = res.ln.output_lra = res.ln.output_thresh = res.ln.target_offset = NAN;
             }
             res.ln.input_i = mi.I; res.ln.input_tp = 20. * log10(mi.sample_peak); res.ln.input_lra = mi.LRA; res.ln.input_thresh = mi.thresh;

@@ -84,6 +84,16 @@ std::vector<FilterNode> jt_parse_spec(const std::string &spec)
     return nodes;
 }
 
+bool jt_loudnorm_linear_mode(const FilterNode &f)
+{
+    if (!f.flag("linear", "", true)) return false;
+    const double I = f.num("I", "i", -24), TP = f.num("TP", "tp", -2), LRA = f.num("LRA", "lra", 7);
+    const double mI = f.num("measured_I", "measured_i", 0), mTP = f.num("measured_TP", "measured_tp", 99);
+    const double mLRA = f.num("measured_LRA", "measured_lra", 0), mTh = f.num("measured_thresh", "", -70);
+    const double off = I - mI, off_tp = mTP + off;
+    return mTP != 99 && mTh != -70 && mLRA != 0 && mI != 0 && off_tp <= TP && mLRA <= LRA;
+}
+
 static double wire_slow(const char *fmt, double v)
 {
     char b[512];          // "%f" of DBL_MAX (astats Min_difference on a 1-sample stream) is 316 characters
@@ -443,12 +453,9 @@ void jt_graph_build(jt_ctx *c, const std::string &spec, const void *d_in, int64_
             const double mI = f.num("measured_I", "measured_i", 0), mTP = f.num("measured_TP", "measured_tp", 99);
             const double mLRA = f.num("measured_LRA", "measured_lra", 0), mTh = f.num("measured_thresh", "", -70);
             double offset = f.num("offset", "", 0);
-            const bool linear = f.flag("linear", "", true), dual = f.flag("dual_mono", "", false);
-            bool lin_mode = false;
-            if (linear) {     // af_loudnorm.c init()
-                const double off = I - mI, off_tp = mTP + off;
-                if (mTP != 99 && mTh != -70 && mLRA != 0 && mI != 0 && off_tp <= TP && mLRA <= LRA) { lin_mode = true; offset = off; }
-            }
+            const bool dual = f.flag("dual_mono", "", false);
+            const bool lin_mode = jt_loudnorm_linear_mode(f);
+            if (lin_mode) offset = I - mI;
             g.has_ln = true; g.ln_linear = lin_mode; g.ln_I = I;
             g.ln_dual = dual;
             if (lin_mode) {
@@ -459,11 +466,45 @@ void jt_graph_build(jt_ctx *c, const std::string &spec, const void *d_in, int64_
                 g.ln_out_sig = E.cur;
                 if (mode == JT_GRAPH_NORMAL) jt_loudnorm_meter_launch(c, E.cur, dual, g.ln_out);
             } else {
-                // dynamic mode: af_loudnorm.c query_formats forces the input link to 192 kHz / dbl
-                if (want_pcm || !last) JT_THROW(JT_ERR_UNSUPPORTED, "loudnorm dynamic mode with audio output (linear-mode preconditions not met: measured_I=%g measured_TP=%g measured_LRA=%g measured_thresh=%g)", mI, mTP, mLRA, mTh);
+                // dynamic mode: af_loudnorm.c query_formats() forces BOTH links to 192 kHz / dbl
+                const bool audio = want_pcm || !last;
+                if (chunked && audio) JT_THROW(JT_ERR_UNSUPPORTED, "loudnorm dynamic mode with audio output in a chunked graph (linear-mode preconditions not met: measured_I=%g measured_TP=%g measured_LRA=%g measured_thresh=%g)", mI, mTP, mLRA, mTh);
                 do_resample(E, 192000, JT_FMT_DBL, true);
-                g.ln_in_sig = E.cur;
-                if (mode == JT_GRAPH_NORMAL) jt_loudnorm_meter_launch(c, E.cur, dual, g.ln_in);
+                g.ln_in_sig = E.cur; g.ln_dynamic = true;
+                const int64_t n192 = E.cur.n;
+                const int F100 = 19200, F3000 = 576000;
+                g.ln_type = n192 < F3000 ? 0 : 1;
+                g.ln_in_extra = n192 < F3000 ? 0 : F3000 - F100;
+                if (mode == JT_GRAPH_NORMAL) {
+                    jt_loudnorm_meter_launch(c, E.cur, dual, g.ln_in);
+                    if (g.ln_in_extra) jt_loudnorm_tail_launch(c, E.cur, n192, dual, g.ln_tail, &g.ln_tail_first);
+                }
+                if (audio) {
+                    jt_loudnorm_opts o; o.I = I; o.TP = TP; o.LRA = LRA; o.measured_I = mI; o.measured_TP = mTP; o.measured_LRA = mLRA;
+                    o.measured_thresh = mTh; o.offset = offset; o.dual_mono = dual;
+                    if (dry) E.cur.fmt = JT_FMT_DBL;
+                    else { int ty = 1; E.cur = jt_loudnorm_dynamic(c, E.cur, o, g.ln_in, &ty); }
+                    E.link_fmt = JT_FMT_DBL;
+                    g.ln_out_sig = E.cur; g.ln_has_out = true;
+                    if (mode == JT_GRAPH_NORMAL) jt_loudnorm_meter_launch(c, E.cur, dual, g.ln_out);
+                    if (n192 >= F3000) {
+                        // output frames: 100 ms once the 3 s first frame is in, one per consumed 100 ms frame (a short one at
+                        // EOF), then the 2.9 s flush frame
+                        std::vector<FrameRef> nf; size_t a = 0;
+                        auto ready_at = [&](int64_t consumed) {        // the link frame holding sample consumed - 1
+                            while (a + 1 < E.frames.size() && E.frames[a + 1].start <= consumed - 1) a++;
+                            return E.frames.empty() ? (int64_t)0 : E.frames[a].ready;
+                        };
+                        FrameRef fr; fr.start = 0; fr.nb = F100; fr.ready = ready_at(F3000); nf.push_back(fr);
+                        int64_t pos = F100, src = F3000;
+                        while (src < n192) {
+                            const int nb = (int)std::min<int64_t>(F100, n192 - src); src += nb;
+                            FrameRef o2; o2.start = pos; o2.nb = nb; o2.ready = nb == F100 ? ready_at(src) : INT64_MAX; nf.push_back(o2); pos += nb;
+                        }
+                        FrameRef fl; fl.start = pos; fl.nb = F3000 - F100; fl.ready = INT64_MAX; nf.push_back(fl);
+                        E.frames.swap(nf);
+                    }
+                }
             }
         } else if (f.name == "astats") {
             E.materialise();
@@ -566,15 +607,27 @@ void jt_graph_finish(jt_ctx *c, GraphRun &g, GraphResult &res)
     res.out = g.out;
     if (g.has_ln) {
         LoudnormMeter mi, mo;
-        jt_loudnorm_meter_finish(c, g.ln_in, mi);
+        if (g.ln_dynamic && g.ln_in_extra && g.ln_tail.nt > 0) {
+            // the stream's ticks, then -- from the tick holding the stream's end on -- those of the re-metered tail
+            JT_CUDA(cudaEventSynchronize(g.ln_in.ev)); JT_CUDA(cudaEventSynchronize(g.ln_tail.ev));
+            const int64_t split = g.ln_in_sig.n / g.ln_in.s100, t0 = g.ln_tail_first;
+            const int64_t nt = t0 + g.ln_tail.nt, nfull = t0 + g.ln_tail.nfull;
+            std::vector<double> hp(nt), hk(nt);
+            for (int64_t k = 0; k < nt; k++) {
+                if (k < split) { hp[k] = g.ln_in.hp[k]; hk[k] = g.ln_in.hk[k]; }
+                else { hp[k] = g.ln_tail.hp[k - t0]; hk[k] = g.ln_tail.hk[k - t0]; }
+            }
+            jt_loudnorm_meter_host_finalize(hp.data(), hk.data(), nt, nfull, g.ln_in.s100, g.ln_dual, mi);
+        } else jt_loudnorm_meter_finish(c, g.ln_in, mi);
         res.ln.valid = 1;
-        if (g.ln_linear) {
+        if (g.ln_linear || g.ln_has_out) {
             jt_loudnorm_meter_finish(c, g.ln_out, mo);
-            res.ln.normalization_type = 0;
+            res.ln.normalization_type = g.ln_linear ? 0 : g.ln_type;
             res.ln.output_i = mo.I; res.ln.output_tp = 20. * log10(mo.sample_peak); res.ln.output_lra = mo.LRA; res.ln.output_thresh = mo.thresh;
             res.ln.target_offset = g.ln_I - mo.I;
         } else {
-            res.ln.normalization_type = 1;
+            // measure-only call (Pass 3): the discarded output is not produced, its four values are not known
+            res.ln.normalization_type = g.ln_type;
             res.ln.output_i = res.ln.output_tp = res.ln.output_lra = res.ln.output_thresh = res.ln.target_offset = NAN;
         }
         res.ln.input_i = mi.I; res.ln.input_tp = 20. * log10(mi.sample_peak); res.ln.input_lra = mi.LRA; res.ln.input_thresh = mi.thresh;

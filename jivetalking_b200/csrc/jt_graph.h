@@ -15,6 +15,8 @@ struct FilterNode {
     bool flag(const char *k1, const char *k2, bool dflt) const;
 };
 std::vector<FilterNode> jt_parse_spec(const std::string &spec);
+// af_loudnorm.c init(): linear mode only when all four measured_* were given and the projected peak / LRA fit the targets
+bool jt_loudnorm_linear_mode(const FilterNode &f);
 
 // One frame on a link, with the metadata it inherited (indices into the producers' outputs).
 struct FrameRef {
@@ -48,7 +50,12 @@ struct GraphRun {
     R128Result r128; bool r128_done = false;
     // loudnorm
     bool has_ln = false, ln_linear = false, ln_dual = false; double ln_I = 0;
-    LoudnormPending ln_in, ln_out;
+    LoudnormPending ln_in, ln_out, ln_tail;
+    // dynamic mode (af_loudnorm.c outside its linear-mode preconditions): both links at 192 kHz; the flush frame --
+    // the stream's last 2.9 s -- is metered a second time on the input side (ln_in_extra samples; ln_tail holds
+    // their per-100 ms values from global tick ln_tail_first on); ln_type is what uninit() prints (0 "linear": a
+    // stream shorter than 3 s falls back to a single gain)
+    bool ln_dynamic = false, ln_has_out = false; int ln_type = 0; int64_t ln_in_extra = 0, ln_tail_first = 0;
     // the signals the measuring filters see (DRY: sizes / formats only; CHUNK: device signals of the local window)
     Sig r128_sig, ln_in_sig, ln_out_sig; bool r128_dual = false, r128_tp = false;
     int exchanges = 0;          // cross-chunk exchange steps the graph went through (CHUNK)

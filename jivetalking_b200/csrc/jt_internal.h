@@ -135,12 +135,27 @@ void jt_ebur128_finish(jt_ctx *c, R128Pending &pd, R128Result &out);
 void jt_ebur128_host_finalize(jt_ctx *c, const double *tick_pow, const double *tick_peak, const double *tick_tp_or_null,
                               int64_t n_ticks, int tick, bool dualmono, R128Result &out);
 struct LoudnormMeter { double I, LRA, thresh, sample_peak; };
+// the state of libavfilter/ebur128.c replayed over per-100 ms K-weighted energies hp[] (see k_r128.cu)
+struct LnMeterState {
+    int s100; double wgt;
+    std::vector<uint32_t> h400, h3000; double sum400 = 0; uint64_t cnt400 = 0;
+    LnMeterState(int s100, bool dual_mono);
+    void add_tick(const double *hp, int64_t k);                    // tick k (0-based) has completed
+    double shortterm_energy(const double *hp, int64_t k) const;    // 3 s ending with tick k (zeros before the stream)
+    double shortterm(const double *hp, int64_t k) const;
+    double relative_threshold() const, global() const, lra() const;
+};
 void jt_loudnorm_meter(jt_ctx *c, const Sig &in, bool dual_mono, LoudnormMeter &out);   // libavfilter/ebur128.c
 struct LoudnormPending { int64_t nt = 0, nfull = 0; int s100 = 0; bool dual_mono = false; double *hp = nullptr, *hk = nullptr; cudaEvent_t ev = nullptr; };
 void jt_loudnorm_meter_launch(jt_ctx *c, const Sig &in, bool dual_mono, LoudnormPending &pd);
 void jt_loudnorm_meter_finish(jt_ctx *c, LoudnormPending &pd, LoudnormMeter &out);
 // host part over per-100 ms values (K-weighted energy, sample peak): nt ticks, the first nfull of them complete
 void jt_loudnorm_meter_host_finalize(const double *hp, const double *hk, int64_t nt, int64_t nfull, int s100, bool dual_mono, LoudnormMeter &out);
+
+// ---- k_loudnorm.cu: af_loudnorm.c dynamic mode ------------------------------------------------
+struct jt_loudnorm_opts { double I, TP, LRA, measured_I, measured_TP, measured_LRA, measured_thresh, offset; int dual_mono; };
+Sig  jt_loudnorm_dynamic(jt_ctx *c, const Sig &x192, const jt_loudnorm_opts &o, LoudnormPending &pd_in, int *normalization_type);
+void jt_loudnorm_tail_launch(jt_ctx *c, const Sig &x_end, int64_t n_stream, bool dual_mono, LoudnormPending &tail, int64_t *first_tick);
 
 // ---- k_astats.cu --------------------------------------------------------------------------
 struct AstatsResult { double v[JT_AS_COUNT]; double overall_rms, overall_peak; double nb_samples; };

@@ -15,6 +15,7 @@
 #include "jt_lanes.cuh"
 #include <algorithm>
 #include <cstdio>
+#include <mutex>
 
 struct KWeight { double pb0, pb1, pb2, pa1, pa2, rb0, rb1, rb2, ra1, ra2; double b[5], a[5]; };
 
@@ -275,7 +276,7 @@ void jt_ebur128_host_finalize(jt_ctx *c, const double *hp, const double *hk, con
 }
 
 // ---------------------------------------------------------------------------------------
-// loudnorm's meter: libavfilter/ebur128.c (libebur128 port), block-list gating
+// loudnorm's meter: libavfilter/ebur128.c (FFmpeg's cut-down libebur128 port), histogram gating
 // ---------------------------------------------------------------------------------------
 void jt_loudnorm_meter_launch(jt_ctx *c, const Sig &in, bool dual_mono, LoudnormPending &pd)
 {
@@ -301,46 +302,103 @@ void jt_loudnorm_meter_finish(jt_ctx *c, LoudnormPending &pd, LoudnormMeter &out
     jt_loudnorm_meter_host_finalize(pd.hp, pd.hk, pd.nt, pd.nfull, pd.s100, pd.dual_mono, out);
 }
 
+// libavfilter/ebur128.c keeps its 400 ms gating blocks and its 3 s short-term blocks in two 1000-bin histograms of
+// 0.1 LU (the port dropped libebur128's block lists): integrated loudness, relative threshold and LRA are functions
+// of the histograms, i.e. quantised to bin centres.  LnMeterState replays that state machine over per-100 ms
+// K-weighted energies; af_loudnorm's dynamic mode queries it after every 100 ms frame (k_loudnorm.cu).
+static double g_hist_energy[1000], g_hist_bound[1001];
+static void hist_tables()
+{
+    static std::once_flag once;
+    std::call_once(once, []() {
+        g_hist_bound[0] = pow(10.0, (-70.0 + 0.691) / 10.0);
+        for (int i = 0; i < 1000; i++) g_hist_energy[i] = pow(10.0, ((double)i / 10.0 - 69.95 + 0.691) / 10.0);
+        for (int i = 1; i <= 1000; i++) g_hist_bound[i] = pow(10.0, ((double)i / 10.0 - 70.0 + 0.691) / 10.0);
+    });
+}
+static size_t hist_index(double energy)
+{
+    size_t lo = 0, hi = 1000, mid;
+    do { mid = (lo + hi) / 2; if (energy >= g_hist_bound[mid]) lo = mid; else hi = mid; } while (hi - lo != 1);
+    return lo;
+}
+static inline double energy_to_loudness(double e) { return 10.0 * (log(e) / log(10.0)) - 0.691; }
+
+LnMeterState::LnMeterState(int s100_, bool dual_mono) : s100(s100_), wgt(dual_mono ? 2.0 : 1.0), h400(1000, 0), h3000(1000, 0) { hist_tables(); }
+
+void LnMeterState::add_tick(const double *hp, int64_t k)
+{
+    // tick k has just completed: k + 1 ticks of audio have been seen
+    if (k >= 3) {
+        const double e = wgt * (hp[k - 3] + hp[k - 2] + hp[k - 1] + hp[k]) / (4.0 * s100);
+        if (e >= g_hist_bound[0]) { const size_t j = hist_index(e); h400[j]++; sum400 += g_hist_energy[j]; cnt400++; }
+    }
+    if (k >= 29 && (k - 29) % 10 == 0) {               // short_term_frame_counter: first at 3 s, then every 1 s
+        const double e = shortterm_energy(hp, k);
+        if (e >= g_hist_bound[0]) h3000[hist_index(e)]++;
+    }
+}
+double LnMeterState::shortterm_energy(const double *hp, int64_t k) const
+{
+    double s = 0; for (int64_t j = std::max<int64_t>(0, k - 29); j <= k; j++) s += hp[j];
+    return wgt * s / (30.0 * s100);
+}
+double LnMeterState::shortterm(const double *hp, int64_t k) const
+{
+    const double e = shortterm_energy(hp, k);
+    return e <= 0.0 ? -HUGE_VAL : energy_to_loudness(e);
+}
+// sums run in bin order like ebur128_calc_relative_threshold, so the values are those of the upstream loops bit for bit
+static double rel_threshold_energy(const std::vector<uint32_t> &h, uint64_t cnt)
+{
+    double sum = 0; for (size_t j = 0; j < 1000; j++) sum += h[j] * g_hist_energy[j];
+    return sum / (double)cnt * pow(10.0, -10.0 / 10.0);
+}
+double LnMeterState::relative_threshold() const
+{
+    if (!cnt400) return -70.0;
+    return energy_to_loudness(rel_threshold_energy(h400, cnt400));
+}
+double LnMeterState::global() const
+{
+    if (!cnt400) return -HUGE_VAL;
+    const double rel = rel_threshold_energy(h400, cnt400);
+    size_t start;
+    if (rel < g_hist_bound[0]) start = 0; else { start = hist_index(rel); if (rel > g_hist_energy[start]) ++start; }
+    double g = 0; uint64_t cnt = 0;
+    for (size_t j = start; j < 1000; j++) { g += h400[j] * g_hist_energy[j]; cnt += h400[j]; }
+    if (!cnt) return -HUGE_VAL;
+    return energy_to_loudness(g / (double)cnt);
+}
+double LnMeterState::lra() const
+{
+    uint64_t size = 0; double power = 0;
+    for (size_t j = 0; j < 1000; j++) { size += h3000[j]; power += h3000[j] * g_hist_energy[j]; }
+    if (!size) return 0.0;
+    power /= (double)size;
+    const double integ = pow(10.0, -20.0 / 10.0) * power;
+    size_t index;
+    if (integ < g_hist_bound[0]) index = 0; else { index = hist_index(integ); if (integ > g_hist_energy[index]) ++index; }
+    size = 0;
+    for (size_t j = index; j < 1000; j++) size += h3000[j];
+    if (!size) return 0.0;
+    const uint64_t plo = (uint64_t)((size - 1) * 0.1 + 0.5), phi = (uint64_t)((size - 1) * 0.95 + 0.5);
+    size = 0; size_t j = index;
+    while (size <= plo) size += h3000[j++];
+    const double l_en = g_hist_energy[j - 1];
+    while (size <= phi) size += h3000[j++];
+    const double h_en = g_hist_energy[j - 1];
+    return energy_to_loudness(h_en) - energy_to_loudness(l_en);
+}
+
 void jt_loudnorm_meter_host_finalize(const double *hp, const double *hk, int64_t nt, int64_t nfull, int s100, bool dual_mono, LoudnormMeter &out)
 {
     out.I = -HUGE_VAL; out.LRA = 0; out.thresh = -70.0; out.sample_peak = 0;
     if (nt <= 0) return;
     for (int64_t k = 0; k < nt; k++) out.sample_peak = std::max(out.sample_peak, hk[k]);
-
-    const double wgt = dual_mono ? 2.0 : 1.0;
-    const double abs_thr = pow(10.0, (-70.0 + 0.691) / 10.0);
-    // gating blocks: 400 ms every 100 ms
-    double sum = 0; uint64_t cnt = 0;
-    std::vector<double> blocks; blocks.reserve(nfull);
-    for (int64_t k = 3; k < nfull; k++) {
-        double e = wgt * (hp[k - 3] + hp[k - 2] + hp[k - 1] + hp[k]) / (4.0 * s100);
-        if (e >= abs_thr) { blocks.push_back(e); sum += e; cnt++; }
-    }
-    if (cnt) {
-        double rel = sum / cnt * 0.1;            // RELATIVE_GATE_FACTOR = 10^(-10/10)
-        out.thresh = 10 * log10(rel) - 0.691;
-        double g = 0; uint64_t gc = 0;
-        for (double e : blocks) if (e >= rel) { g += e; gc++; }
-        out.I = gc ? 10 * log10(g / gc) - 0.691 : -HUGE_VAL;
-    }
-    // short-term blocks: 3 s, first at 3 s then every 1 s (short_term_frame_counter 30 -> 20)
-    std::vector<double> st;
-    for (int64_t k = 29; k < nfull; k += 10) {
-        double s = 0; for (int j = 29; j >= 0; j--) s += hp[k - j];
-        double e = wgt * s / (30.0 * s100);
-        if (e >= abs_thr) st.push_back(e);
-    }
-    if (!st.empty()) {
-        std::sort(st.begin(), st.end());
-        double p = 0; for (double e : st) p += e; p /= st.size();
-        const double integ = 0.01 * p;              // -20 LU
-        size_t first = 0; while (first < st.size() && st[first] < integ) first++;
-        const size_t sz = st.size() - first;
-        if (sz) {
-            double h = st[first + (size_t)((sz - 1) * 0.95 + 0.5)], l = st[first + (size_t)((sz - 1) * 0.1 + 0.5)];
-            out.LRA = (10 * log10(h) - 0.691) - (10 * log10(l) - 0.691);
-        }
-    }
+    LnMeterState st(s100, dual_mono);
+    for (int64_t k = 0; k < nfull; k++) st.add_tick(hp, k);
+    out.I = st.global(); out.LRA = st.lra(); out.thresh = st.relative_threshold();
 }
 
 void jt_ebur128(jt_ctx *c, const Sig &in, bool dualmono, bool true_peak, R128Result &out)

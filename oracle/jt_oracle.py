@@ -205,6 +205,25 @@ def loudnorm_meter(x, rate, dual_mono=True):
     return dict(I=o[0], LRA=o[1], thresh=o[2], sample_peak=o[3])
 
 
+def loudnorm_is_linear(I, TP, LRA, mI, mTP, mLRA, mTh, linear=True):
+    opt = np.array([I, TP, LRA, mI, mTP, mLRA, mTh, 0.0])
+    return bool(_proto("orc_loudnorm_is_linear", C.c_int, [_P, C.c_int])(_ptr(opt), int(linear)))
+
+
+def loudnorm(x, rate, I=-24.0, TP=-2.0, LRA=7.0, mI=0.0, mTP=99.0, mLRA=0.0, mTh=-70.0, offset=0.0, linear=True, dual_mono=False):
+    """af_loudnorm.c over its input link x (f64; 192 kHz when the mode is dynamic).  Returns (y, stats dict)."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    opt = np.array([I, TP, LRA, mI, mTP, mLRA, mTh, offset])
+    y = np.zeros(len(x))
+    st = np.zeros(10)
+    n = _proto("orc_loudnorm", _I64, [_P, _I64, C.c_int, _P, C.c_int, C.c_int, _P, _P])(_ptr(x), len(x), rate, _ptr(opt), int(linear), int(dual_mono), _ptr(y), _ptr(st))
+    assert n == len(x), (n, len(x))
+    keys = ["input_i", "input_tp", "input_lra", "input_thresh", "output_i", "output_tp", "output_lra", "output_thresh"]
+    d = {k: float(st[i]) for i, k in enumerate(keys)}
+    d["normalization_type"] = int(st[8]); d["target_offset"] = float(st[9])
+    return y, d
+
+
 def afftdn(x, rate, nr=12.0, nf=-50.0, nt=0, bn=None, tn=False, ad=0.5, fo=1.0, bm=1.25):
     x = np.ascontiguousarray(x, dtype=np.float32)
     out = np.zeros_like(x)

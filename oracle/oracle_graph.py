@@ -383,20 +383,36 @@ def run_spec(spec, x, rate, channels=1, frame_size=4096, want_pcm=True):
             mI, mTP = float(_get(o, "measured_I", "measured_i", default=0)), float(_get(o, "measured_TP", "measured_tp", default=99))
             mLRA, mTh = float(_get(o, "measured_LRA", "measured_lra", default=0)), float(o.get("measured_thresh", -70))
             dual = o.get("dual_mono", "false") == "true"
-            lin = o.get("linear", "true") == "true" and mTP != 99 and mTh != -70 and mLRA != 0 and mI != 0 and mTP + (I - mI) <= TP and mLRA <= LRA
-            if lin:
-                cur = as_fmt(cur, np.float64)
-                mi = O.loudnorm_meter(cur, rate, dual)
-                cur = cur * 10 ** ((I - mI) / 20.0)
-                mo = O.loudnorm_meter(cur, rate, dual)
-                ln = dict(normalization_type=0, output_i=mo["I"], output_tp=20 * math.log10(mo["sample_peak"]) if mo["sample_peak"] > 0 else -math.inf,
-                          output_lra=mo["LRA"], output_thresh=mo["thresh"], target_offset=I - mo["I"])
-            else:
+            offs = float(o.get("offset", 0))
+            lin = O.loudnorm_is_linear(I, TP, LRA, mI, mTP, mLRA, mTh, o.get("linear", "true") == "true")
+            if not lin:
+                # query_formats(): outside linear mode both links of the filter run at 192 kHz / dbl
                 cur, frames = resample(cur, 192000, np.float64, frames)
-                mi = O.loudnorm_meter(cur, rate, dual)
-                ln = dict(normalization_type=1)
-            ln.update(input_i=mi["I"], input_tp=20 * math.log10(mi["sample_peak"]) if mi["sample_peak"] > 0 else -math.inf,
-                      input_lra=mi["LRA"], input_thresh=mi["thresh"])
+            cur = as_fmt(cur, np.float64)
+            if not lin and last and not want_pcm and len(cur) >= 576000:
+                # measure-only call (Pass 3): the four input_* values are those of the stream followed by its last 2.9 s
+                # again (filter_frame meters the flush frame a second time); the discarded output is not produced
+                mi = O.loudnorm_meter(np.concatenate([cur, cur[len(cur) - 556800:]]), rate, dual)
+                ln = dict(normalization_type=1, input_i=mi["I"], input_tp=20 * math.log10(mi["sample_peak"]) if mi["sample_peak"] > 0 else -math.inf,
+                          input_lra=mi["LRA"], input_thresh=mi["thresh"])
+            else:
+                n_in = len(cur)
+                cur, ln = O.loudnorm(cur, rate, I, TP, LRA, mI, mTP, mLRA, mTh, offs, o.get("linear", "true") == "true", dual)
+                if not lin:
+                    # output frames: 100 ms after the 3 s first frame, one per consumed 100 ms frame, then the 2.9 s flush frame
+                    if n_in < 576000:
+                        pass                      # single-gain fall-back: frames pass through
+                    else:
+                        nf, pos, src_pos = [], 0, 576000
+                        def ready_at(p):
+                            f = next((f for f in frames if f["start"] <= p - 1 < f["start"] + f["nb"]), frames[-1])
+                            return f["ready"]
+                        nf.append(dict(start=0, nb=19200, ready=ready_at(576000), astats_pos=-1, hop=-1, tick=-1)); pos = 19200
+                        while src_pos < n_in:
+                            nb = min(19200, n_in - src_pos); src_pos += nb
+                            nf.append(dict(start=pos, nb=nb, ready=ready_at(src_pos) if nb == 19200 else 1 << 62, astats_pos=-1, hop=-1, tick=-1)); pos += nb
+                        nf.append(dict(start=pos, nb=556800, ready=1 << 62, astats_pos=-1, hop=-1, tick=-1))
+                        frames = nf
         elif name == "astats":
             astats_sig, astats_rate = cur, rate
             for f in frames:

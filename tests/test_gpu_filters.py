@@ -157,7 +157,3 @@ def test_unsupported_and_bad_specs_fail_loudly(ctx):
     assert e.value.code == -4
     with pytest.raises(gpudsp.JtError):
         ctx.run_graph("highpass=f=80", np.zeros(9600, dtype=np.float32), 48000, channels=2)
-    # dynamic-mode loudnorm with audio requested is outside the built path and says so
-    with pytest.raises(gpudsp.JtError) as e:
-        ctx.run_graph("loudnorm=I=-16:TP=-1:LRA=20", x, 48000)
-    assert e.value.code == -5

@@ -47,7 +47,8 @@ def test_bs1770_known_answers():
     assert abs(r["I"] - (-23.0)) < 0.1 and r["LRA"] < 0.1
     assert abs(r["M"][-1] - (-23.0)) < 0.1 and abs(r["S"][-1] - (-23.0)) < 0.1
     m = O.loudnorm_meter(x, fs, dual_mono=True)
-    assert abs(m["I"] - (-23.0)) < 0.1 and abs(m["I"] - r["I"]) < 0.02
+    # loudnorm's meter (libavfilter/ebur128.c) keeps its gating blocks in 0.1 LU histogram bins: I is a bin centre
+    assert abs(m["I"] - (-23.0)) < 0.1 and abs(m["I"] - r["I"]) < 0.06
     # without dual-mono a mono signal reads 3.01 LU lower
     assert abs(O.ebur128(x, fs, dualmono=False)["I"] - (r["I"] - 3.0103)) < 0.011
     # true peak of a sine sampled off-peak: fs/4 with 45 degree phase -> sample peak -3.01 dB, true peak ~0 dB
