@@ -426,8 +426,9 @@ int jt_process_audio_adaptive_dev(jt_ctx *ctx, const void *d_pcm_in, int64_t n_f
 
 /* RIFF / WAVE input (the reference's fixtures are s16 WAVs, testutil_test.go:140-190; it decodes through libavformat,
  * internal/audio/reader.go): locates the PCM of a file image in memory.  *sample_fmt is a JT_FMT_* value, the samples are
- * interleaved at bytes + *data_offset.  JT_ERR_UNSUPPORTED for 8 / 24 bit or compressed data, and for 32-bit integer PCM
- * (described in the outputs, but the chain has no s32 kernels yet).  Host-only, no jt_ctx. */
+ * interleaved at bytes + *data_offset.  JT_ERR_UNSUPPORTED for 8 / 24 bit or compressed data and for RF64 / BW64 files.  A data
+ * chunk of declared size 0 or 0xFFFFFFFF (streamed files) runs to the end of the buffer, as libavformat reads it.
+ * Host-only, no jt_ctx. */
 int jt_wav_parse(const void *bytes, int64_t n_bytes, int *sample_fmt, int *sample_rate, int *channels,
                  int64_t *data_offset, int64_t *n_frames);
 

@@ -166,7 +166,7 @@ static int run_graph_common(jt_ctx *c, const char *spec, const void *pcm_in, boo
 {
     return guarded(c, [&]() {
         if (!spec || (!pcm_in && n_frames > 0)) JT_THROW(JT_ERR_INVALID_ARG, "null spec or input");
-        if (fmt != JT_FMT_S16 && fmt != JT_FMT_FLT && fmt != JT_FMT_DBL) JT_THROW(JT_ERR_UNSUPPORTED, "input sample format %d", fmt);
+        if (!jt_valid_fmt(fmt)) JT_THROW(JT_ERR_UNSUPPORTED, "input sample format %d", fmt);
         const size_t in_bytes = (size_t)n_frames * channels * jt_fmt_bytes(fmt);
         const void *d_in = in_on_device ? pcm_in : upload(c, pcm_in, in_bytes);
         GraphResult g;
@@ -380,7 +380,7 @@ extern "C" int jt_analyse(jt_ctx *c, const void *pcm_in, int64_t n_frames, int r
 {
     return guarded(c, [&]() {
         if (!pcm_in && n_frames > 0) JT_THROW(JT_ERR_INVALID_ARG, "null input");
-        if (fmt != JT_FMT_S16 && fmt != JT_FMT_FLT && fmt != JT_FMT_DBL) JT_THROW(JT_ERR_UNSUPPORTED, "input sample format %d", fmt);
+        if (!jt_valid_fmt(fmt)) JT_THROW(JT_ERR_UNSUPPORTED, "input sample format %d", fmt);
         const void *d_in = upload(c, pcm_in, (size_t)n_frames * channels * jt_fmt_bytes(fmt));
         analyse_device(c, d_in, n_frames, rate, channels, fmt, frame_size, out, iv, iv_cap, n_iv);
     });
@@ -430,7 +430,7 @@ extern "C" int jt_analyse_chunk(jt_ctx *c, const void *pcm_local, int64_t n_loca
         const int F = 4096;
         const int64_t U = jt_analyse_chunk_unit(rate);
         if (!pcm_local || !blob || U <= 0) JT_THROW(JT_ERR_INVALID_ARG, "null argument or unsupported rate");
-        if (fmt != JT_FMT_S16 && fmt != JT_FMT_FLT && fmt != JT_FMT_DBL) JT_THROW(JT_ERR_UNSUPPORTED, "input sample format %d", fmt);
+        if (!jt_valid_fmt(fmt)) JT_THROW(JT_ERR_UNSUPPORTED, "input sample format %d", fmt);
         if (own_first % U || local_first % U || local_first > own_first || own_first + owned > total_frames || owned <= 0 ||
             local_first + n_local < own_first + owned || local_first + n_local > total_frames)
             JT_THROW(JT_ERR_INVALID_ARG, "chunk [%lld,+%lld) / local [%lld,+%lld): boundaries must be multiples of jt_analyse_chunk_unit = %lld frames",
@@ -451,9 +451,13 @@ extern "C" int jt_analyse_chunk(jt_ctx *c, const void *pcm_local, int64_t n_loca
         JT_CUDA(cudaMemcpyAsync(h_pk, d_pk, sizeof(double) * nsrc, cudaMemcpyDeviceToHost, c->stream));
         // the Pass-1 filters on the local stream (aformat mono -> astats -> aspectralstats -> ebur128)
         Sig mono = jt_downmix(c, d_in, n_local, channels, fmt, rate);
+        // astats sees the link's own format; aspectralstats converts to flt and ebur128 reads THAT link (s16 / flt widen
+        // exactly, 32-bit integers are rounded to float first)
+        const Sig mono_as = mono;
+        if (mono.fmt == JT_FMT_S32) mono = jt_convert(c, mono, JT_FMT_FLT);
         const int64_t as_upto = pass1_astats_upto(total_frames, tick, F);
         const int64_t as_n = std::max<int64_t>(0, std::min(own_first + owned, as_upto) - own_first);
-        AstatsPending ap; jt_astats_chunk_launch(c, mono, off, as_n, own_first, ap);
+        AstatsPending ap; jt_astats_chunk_launch(c, mono_as, off, as_n, own_first, ap);
         // sink frames (100 ms, the last one possibly partial) whose first sample is owned, and the hop each shows
         const int64_t tick0 = own_first / tick;
         const int64_t n_sink = (owned + tick - 1) / tick, n_ticks = last ? (total_frames / tick - tick0) : owned / tick;
@@ -467,7 +471,7 @@ extern "C" int jt_analyse_chunk(jt_ctx *c, const void *pcm_local, int64_t n_loca
         JT_CUDA(cudaStreamSynchronize(c->stream));
         JtChunkHdr h; memset(&h, 0, sizeof(h));
         h.magic = JT_CHUNK_MAGIC; h.total_frames = total_frames; h.first = own_first; h.owned = owned;
-        h.rate = rate; h.channels = channels; h.fmt = fmt; h.frame_size = F; h.tick = tick; h.link_fmt = mono.fmt; h.tc = ap.tc;
+        h.rate = rate; h.channels = channels; h.fmt = fmt; h.frame_size = F; h.tick = tick; h.link_fmt = mono_as.fmt; h.tc = ap.tc;
         h.tick0 = tick0; h.n_ticks = std::max<int64_t>(n_ticks, 0); h.src0 = own_first / F; h.n_src = nsrc; h.n_rows = n_sink;
         h.astats_bytes = (int64_t)jt_astats_host_bytes(); h.astats_n = ap.host ? as_n : 0; h.astats_upto = as_upto;
         if (!h.tc) h.tc = (int)std::fmax(0.05 * rate + .5, 1);
@@ -641,7 +645,7 @@ extern "C" int jt_graph_chunk(jt_ctx *c, const char *spec, const void *pcm_local
 {
     return guarded(c, [&]() {
         if (!spec || !pcm_local) JT_THROW(JT_ERR_INVALID_ARG, "null spec or input");
-        if (fmt != JT_FMT_S16 && fmt != JT_FMT_FLT && fmt != JT_FMT_DBL) JT_THROW(JT_ERR_UNSUPPORTED, "input sample format %d", fmt);
+        if (!jt_valid_fmt(fmt)) JT_THROW(JT_ERR_UNSUPPORTED, "input sample format %d", fmt);
         if (frame_size <= 0) frame_size = 4096;
         const ChunkGeometry G = chunk_geometry(spec, rate);
         const int64_t U = G.unit;
@@ -1061,7 +1065,7 @@ extern "C" int jt_measure_output_region(jt_ctx *c, const void *pcm, int64_t n_fr
 {
     return guarded(c, [&]() {
         if (!pcm && n_frames > 0) JT_THROW(JT_ERR_INVALID_ARG, "null input");
-        if (fmt != JT_FMT_S16 && fmt != JT_FMT_FLT && fmt != JT_FMT_DBL) JT_THROW(JT_ERR_UNSUPPORTED, "input sample format %d", fmt);
+        if (!jt_valid_fmt(fmt)) JT_THROW(JT_ERR_UNSUPPORTED, "input sample format %d", fmt);
         const void *d_in = upload(c, pcm, (size_t)n_frames * channels * jt_fmt_bytes(fmt));
         region_measure_device(c, d_in, n_frames, rate, channels, fmt, start_ns, dur_ns, out, frames);
     });
@@ -1182,7 +1186,7 @@ extern "C" int jt_process_audio(jt_ctx *c, const void *pcm_in, int64_t n_frames,
 {
     return guarded(c, [&]() {
         if (!pcm_in && n_frames > 0) JT_THROW(JT_ERR_INVALID_ARG, "null input");
-        if (fmt != JT_FMT_S16 && fmt != JT_FMT_FLT && fmt != JT_FMT_DBL) JT_THROW(JT_ERR_UNSUPPORTED, "input sample format %d", fmt);
+        if (!jt_valid_fmt(fmt)) JT_THROW(JT_ERR_UNSUPPORTED, "input sample format %d", fmt);
         const void *d_in = upload(c, pcm_in, (size_t)n_frames * channels * jt_fmt_bytes(fmt));
         process_device(c, d_in, n_frames, rate, channels, fmt, pass2_spec, pcm_out, false, cap, res);
     });
@@ -1249,7 +1253,7 @@ extern "C" int jt_analyse_adaptive(jt_ctx *c, const void *pcm_in, int64_t n_fram
 {
     return guarded(c, [&]() {
         if (!pcm_in && n_frames > 0) JT_THROW(JT_ERR_INVALID_ARG, "null input");
-        if (fmt != JT_FMT_S16 && fmt != JT_FMT_FLT && fmt != JT_FMT_DBL) JT_THROW(JT_ERR_UNSUPPORTED, "input sample format %d", fmt);
+        if (!jt_valid_fmt(fmt)) JT_THROW(JT_ERR_UNSUPPORTED, "input sample format %d", fmt);
         const void *d_in = upload(c, pcm_in, (size_t)n_frames * channels * jt_fmt_bytes(fmt));
         analyse_adaptive_device(c, d_in, n_frames, rate, channels, fmt, frame_size, base, out, iv, iv_cap, n_iv);
     });
@@ -1269,7 +1273,7 @@ extern "C" int jt_process_audio_adaptive(jt_ctx *c, const void *pcm_in, int64_t 
 {
     return guarded(c, [&]() {
         if (!pcm_in && n_frames > 0) JT_THROW(JT_ERR_INVALID_ARG, "null input");
-        if (fmt != JT_FMT_S16 && fmt != JT_FMT_FLT && fmt != JT_FMT_DBL) JT_THROW(JT_ERR_UNSUPPORTED, "input sample format %d", fmt);
+        if (!jt_valid_fmt(fmt)) JT_THROW(JT_ERR_UNSUPPORTED, "input sample format %d", fmt);
         const void *d_in = upload(c, pcm_in, (size_t)n_frames * channels * jt_fmt_bytes(fmt));
         process_adaptive_device(c, d_in, n_frames, rate, channels, fmt, base, pcm_out, false, cap, res, analysis);
     });

@@ -26,14 +26,39 @@ template <> __device__ __forceinline__ int16_t jt_conv<double, int16_t>(double v
     return (int16_t)max(-32768, min(32767, r));
 }
 
+// 32-bit integer samples (24-bit FLAC / WAV decode to s32): audioconvert.c CONV_FUNC table, pinned on the real
+// libswresample (tests/golden/swr_golden.npz)
+template <> __device__ __forceinline__ float   jt_conv<int32_t, float>(int32_t v)  { return __fmul_rn((float)v, 1.0f / 2147483648.0f); }
+template <> __device__ __forceinline__ double  jt_conv<int32_t, double>(int32_t v) { return (double)v * (1.0 / 2147483648.0); }
+template <> __device__ __forceinline__ int16_t jt_conv<int32_t, int16_t>(int32_t v) { return (int16_t)(v >> 16); }
+template <> __device__ __forceinline__ int32_t jt_conv<int16_t, int32_t>(int16_t v) { return (int32_t)v * 65536; }
+template <> __device__ __forceinline__ int32_t jt_conv<int32_t, int32_t>(int32_t v) { return v; }
+template <> __device__ __forceinline__ int32_t jt_conv<float, int32_t>(float v)
+{   // av_clipl_int32(llrintf(v * (1U << 31)))
+    const float s = __fmul_rn(v, 2147483648.0f);
+    if (!(s < 2147483648.0f)) return 2147483647;
+    if (s < -2147483648.0f) return (int32_t)0x80000000;
+    return (int32_t)__float2ll_rn(s);
+}
+template <> __device__ __forceinline__ int32_t jt_conv<double, int32_t>(double v)
+{   // av_clipl_int32(llrint(v * (1U << 31)))
+    const double s = __dmul_rn(v, 2147483648.0);
+    if (!(s < 2147483647.5)) return 2147483647;
+    if (s < -2147483648.0) return (int32_t)0x80000000;
+    const long long r = __double2ll_rn(s);
+    return (int32_t)(r > 2147483647LL ? 2147483647LL : r);
+}
+
 // value normalised to [-1,1] the way the Go side does for raw frame statistics
 // (analyser_metrics.go:310-349: s16 / 32768.0, float/double as is)
 __device__ __forceinline__ double jt_norm_f64(int16_t v) { return (double)v / 32768.0; }
+__device__ __forceinline__ double jt_norm_f64(int32_t v) { return (double)v / 2147483648.0; }
 __device__ __forceinline__ double jt_norm_f64(float v)   { return (double)v; }
 __device__ __forceinline__ double jt_norm_f64(double v)  { return v; }
 
 // load any supported sample as the f64 a swr/aformat conversion to dbl would give
 __device__ __forceinline__ double jt_as_f64(int16_t v) { return (double)v * (1.0 / 32768.0); }
+__device__ __forceinline__ double jt_as_f64(int32_t v) { return (double)v * (1.0 / 2147483648.0); }
 __device__ __forceinline__ double jt_as_f64(float v)   { return (double)v; }
 __device__ __forceinline__ double jt_as_f64(double v)  { return v; }
 

@@ -311,7 +311,7 @@ void jt_graph_build(jt_ctx *c, const std::string &spec, const void *d_in, int64_
             int out_rate = (int)f.num("sample_rates", "r", E.cur.rate);
             std::string sf = f.str("sample_fmts", "f", "");
             int out_fmt = 0;
-            if (sf == "s16") out_fmt = JT_FMT_S16; else if (sf == "flt" || sf == "fltp") out_fmt = JT_FMT_FLT;
+            if (sf == "s16") out_fmt = JT_FMT_S16; else if (sf == "s32") out_fmt = JT_FMT_S32; else if (sf == "flt" || sf == "fltp") out_fmt = JT_FMT_FLT;
             else if (sf == "dbl" || sf == "dblp") out_fmt = JT_FMT_DBL; else if (!sf.empty()) JT_THROW(JT_ERR_UNSUPPORTED, "aformat sample_fmts=%s", sf.c_str());
             if (last && !want_pcm && out_rate != E.cur.rate) {
                 // measure-only call: the resampled audio would be discarded, keep the frame cadence only
@@ -354,7 +354,7 @@ void jt_graph_build(jt_ctx *c, const std::string &spec, const void *d_in, int64_
             // timestamps only
         } else if (f.name == "highpass" || f.name == "lowpass") {
             E.materialise();
-            if (E.link_fmt != JT_FMT_S16 && E.link_fmt != JT_FMT_FLT && E.link_fmt != JT_FMT_DBL) JT_THROW(JT_ERR_UNSUPPORTED, "biquad format");
+            if (!jt_valid_fmt(E.link_fmt)) JT_THROW(JT_ERR_UNSUPPORTED, "biquad format");
             const double freq = f.num("f", "frequency", 3000);
             const int poles = (int)f.num("p", "poles", 2);
             const std::string wt = f.str("t", "width_type", "q");

@@ -87,12 +87,13 @@ struct JtHost {
 
 // ---- device-resident mono signal --------------------------------------------------------
 struct Sig {
-    int fmt = 0;        // JT_FMT_S16 / FLT / DBL
+    int fmt = 0;        // JT_FMT_S16 / S32 / FLT / DBL
     int rate = 0;
     int64_t n = 0;      // samples (mono)
     void *d = nullptr;  // device pointer
 };
 static inline size_t jt_fmt_bytes(int fmt) { return fmt == JT_FMT_S16 ? 2 : fmt == JT_FMT_DBL ? 8 : 4; }
+static inline bool jt_valid_fmt(int fmt) { return fmt == JT_FMT_S16 || fmt == JT_FMT_S32 || fmt == JT_FMT_FLT || fmt == JT_FMT_DBL; }
 
 // ---- jt_util.cu ---------------------------------------------------------------------------
 Sig  jt_convert(jt_ctx *c, const Sig &in, int out_fmt);                   // audioconvert.c semantics

@@ -241,6 +241,12 @@ Sig jt_convert(jt_ctx *c, const Sig &in, int out_fmt)
     case JT_FMT_FLT * 16 + JT_FMT_S16: return convert_t<float, int16_t>(c, in, out_fmt);
     case JT_FMT_DBL * 16 + JT_FMT_FLT: return convert_t<double, float>(c, in, out_fmt);
     case JT_FMT_DBL * 16 + JT_FMT_S16: return convert_t<double, int16_t>(c, in, out_fmt);
+    case JT_FMT_S32 * 16 + JT_FMT_FLT: return convert_t<int32_t, float>(c, in, out_fmt);
+    case JT_FMT_S32 * 16 + JT_FMT_DBL: return convert_t<int32_t, double>(c, in, out_fmt);
+    case JT_FMT_S32 * 16 + JT_FMT_S16: return convert_t<int32_t, int16_t>(c, in, out_fmt);
+    case JT_FMT_S16 * 16 + JT_FMT_S32: return convert_t<int16_t, int32_t>(c, in, out_fmt);
+    case JT_FMT_FLT * 16 + JT_FMT_S32: return convert_t<float, int32_t>(c, in, out_fmt);
+    case JT_FMT_DBL * 16 + JT_FMT_S32: return convert_t<double, int32_t>(c, in, out_fmt);
     }
     JT_THROW(JT_ERR_UNSUPPORTED, "sample format conversion %d -> %d", in.fmt, out_fmt);
 }
@@ -267,10 +273,24 @@ __global__ void k_downmix2_s16(const short2 *__restrict__ in, int16_t *__restric
     }
 }
 
+// s32 stereo -> s32 mono: swr picks FLTP as its internal format (swresample.c swr_init: 32-bit integer input with a
+// rematrix), mixes with the normalised 0.5 / 0.5 matrix in float and converts back -- the low 8 bits of a 32-bit sample
+// do not survive (pinned on the real library: tests/golden/swr_golden.npz "stereo_s32_to_mono")
+__global__ void k_downmix2_s32(const int2 *__restrict__ in, int32_t *__restrict__ out, int64_t n)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const int2 v = in[i];
+        const float l = jt_conv<int32_t, float>(v.x), r = jt_conv<int32_t, float>(v.y);
+        out[i] = jt_conv<float, int32_t>(__fadd_rn(__fmul_rn(l, 0.5f), __fmul_rn(r, 0.5f)));
+    }
+}
+
 Sig jt_downmix(jt_ctx *c, const void *d_in, int64_t n, int channels, int fmt, int rate)
 {
     Sig o; o.fmt = fmt; o.rate = rate; o.n = n;
-    if (fmt != JT_FMT_S16 && fmt != JT_FMT_FLT && fmt != JT_FMT_DBL)
+    if (fmt != JT_FMT_S16 && fmt != JT_FMT_S32 && fmt != JT_FMT_FLT && fmt != JT_FMT_DBL)
         JT_THROW(JT_ERR_UNSUPPORTED, "input sample format %d", fmt);
     if (channels == 1) { o.d = const_cast<void *>(d_in); return o; }
     if (channels != 2) JT_THROW(JT_ERR_UNSUPPORTED, "downmix from %d channels", channels);
@@ -282,6 +302,10 @@ Sig jt_downmix(jt_ctx *c, const void *d_in, int64_t n, int channels, int fmt, in
         o.d = jt_dalloc<int16_t>(c, n);
         JtLaunch L(c, "downmix");
         k_downmix2_s16<<<jt_grid_for(n, 256, c->num_sms, 16), 256, 0, c->stream>>>((const short2 *)d_in, (int16_t *)o.d, n);
+    } else if (fmt == JT_FMT_S32) {
+        o.d = jt_dalloc<int32_t>(c, n);
+        JtLaunch L(c, "downmix");
+        k_downmix2_s32<<<jt_grid_for(n, 256, c->num_sms, 16), 256, 0, c->stream>>>((const int2 *)d_in, (int32_t *)o.d, n);
     } else JT_THROW(JT_ERR_UNSUPPORTED, "stereo f64 downmix");
     return o;
 }
@@ -324,6 +348,7 @@ void jt_raw_frame_stats(jt_ctx *c, const void *d_in, int64_t n_frames, int chann
     const int grid = jt_grid_for(n_src_frames, 8, c->num_sms, 32);
     JtLaunch L(c, "raw_frame_stats");
     if (fmt == JT_FMT_S16) k_raw_frame_stats<int16_t><<<grid, 256, 0, c->stream>>>((const int16_t *)d_in, n_total, per, d_sumsq, d_peak, n_src_frames);
+    else if (fmt == JT_FMT_S32) k_raw_frame_stats<int32_t><<<grid, 256, 0, c->stream>>>((const int32_t *)d_in, n_total, per, d_sumsq, d_peak, n_src_frames);
     else if (fmt == JT_FMT_FLT) k_raw_frame_stats<float><<<grid, 256, 0, c->stream>>>((const float *)d_in, n_total, per, d_sumsq, d_peak, n_src_frames);
     else k_raw_frame_stats<double><<<grid, 256, 0, c->stream>>>((const double *)d_in, n_total, per, d_sumsq, d_peak, n_src_frames);
 }

@@ -16,6 +16,7 @@ extern "C" int jt_wav_parse(const void *bytes, int64_t n_bytes, int *sample_fmt,
                             int64_t *data_offset, int64_t *n_frames)
 {
     const unsigned char *b = (const unsigned char *)bytes;
+    if (b && n_bytes >= 12 && (!memcmp(b, "RF64", 4) || !memcmp(b, "BW64", 4)) && !memcmp(b + 8, "WAVE", 4)) return JT_ERR_UNSUPPORTED;   // 64-bit sizes in a ds64 chunk
     if (!b || n_bytes < 12 || memcmp(b, "RIFF", 4) || memcmp(b + 8, "WAVE", 4)) return JT_ERR_INVALID_ARG;
     int64_t pos = 12; bool have_fmt = false; int tag = 0, ch = 0, rate = 0, bits = 0, align = 0;
     while (pos + 8 <= n_bytes) {
@@ -36,10 +37,12 @@ extern "C" int jt_wav_parse(const void *bytes, int64_t n_bytes, int *sample_fmt,
             const int frame_bytes = ch * (bits / 8);
             if (align && align != frame_bytes) return JT_ERR_INVALID_ARG;
             int64_t avail = n_bytes - (pos + 8);
-            int64_t dl = (len == 0xFFFFFFFFll || len > avail) ? avail : len;                                 // streamed / truncated files
+            // streamed files (an encoder writing to a pipe leaves 0 or 0xFFFFFFFF) and truncated ones: libavformat's wav
+            // demuxer reads such a data chunk to the end of the file
+            int64_t dl = (len == 0 || len == 0xFFFFFFFFll || len > avail) ? avail : len;
             if (sample_fmt) *sample_fmt = fmt; if (sample_rate) *sample_rate = rate; if (channels) *channels = ch;
             if (data_offset) *data_offset = pos + 8; if (n_frames) *n_frames = dl / frame_bytes;
-            return fmt == JT_FMT_S32 ? JT_ERR_UNSUPPORTED : JT_OK;                                            // described, but no s32 kernels yet
+            return JT_OK;
         }
         pos += 8 + len + (len & 1);
     }

@@ -27,6 +27,11 @@ template <> struct AsTraits<int16_t> {
     static __device__ __forceinline__ double nd(int16_t v) { return (double)v / 32767.0; }
     static __device__ __forceinline__ unsigned long long absi(int16_t v) { int i = v; return (unsigned long long)(i < 0 ? -i : i); }
 };
+template <> struct AsTraits<int32_t> {
+    static __device__ __forceinline__ double d(int32_t v) { return (double)v; }
+    static __device__ __forceinline__ double nd(int32_t v) { return (double)v / 2147483647.0; }
+    static __device__ __forceinline__ unsigned long long absi(int32_t v) { long long i = v; return (unsigned long long)(i < 0 ? -i : i); }
+};
 template <> struct AsTraits<float> {
     static __device__ __forceinline__ double d(float v) { return (double)v; }
     static __device__ __forceinline__ double nd(float v) { return (double)v; }
@@ -450,10 +455,10 @@ void jt_astats_host_finalize(const void *host, int64_t n, int fmt, int tc, Astat
     const AstatsHost *h = (const AstatsHost *)host;
     const AsPartA &r = h->total;
     const unsigned long long *hist = h->hist;
-    const int maxbits = fmt == JT_FMT_S16 ? 16 : fmt == JT_FMT_FLT ? 32 : 64;
+    const int maxbits = fmt == JT_FMT_S16 ? 16 : (fmt == JT_FMT_FLT || fmt == JT_FMT_S32) ? 32 : 64;
     const float h_nf = h->nf;
     const double N = (double)n;
-    const double scale = fmt == JT_FMT_S16 ? 32767.0 : 1.0;
+    const double scale = fmt == JT_FMT_S16 ? 32767.0 : fmt == JT_FMT_S32 ? 2147483647.0 : 1.0;
     const double nmin = r.mn / scale, nmax = r.mx / scale;
     double min_s2 = h->mm[0], max_s2 = h->mm[1];
     if (n <= tc) min_s2 = max_s2 = r.sumsq / N;      // af_astats.c: fewer samples than the window
@@ -495,6 +500,7 @@ void jt_astats_launch(jt_ctx *c, const Sig &in, int64_t n_upto, AstatsPending &p
     const int64_t n = std::min(n_upto, in.n);
     if (n <= 0) return;
     if (in.fmt == JT_FMT_S16) astats_launch_t<int16_t>(c, in, n, pd);
+    else if (in.fmt == JT_FMT_S32) astats_launch_t<int32_t>(c, in, n, pd);
     else if (in.fmt == JT_FMT_FLT) astats_launch_t<float>(c, in, n, pd);
     else astats_launch_t<double>(c, in, n, pd);
 }
@@ -509,6 +515,7 @@ void jt_astats_chunk_launch(jt_ctx *c, const Sig &in, int64_t own0, int64_t own_
     pd = AstatsPending();
     if (own_n <= 0 || own0 < 0 || own0 + own_n > in.n) return;
     if (in.fmt == JT_FMT_S16) astats_launch_t<int16_t>(c, in, own_n, pd, own0, global_first);
+    else if (in.fmt == JT_FMT_S32) astats_launch_t<int32_t>(c, in, own_n, pd, own0, global_first);
     else if (in.fmt == JT_FMT_FLT) astats_launch_t<float>(c, in, own_n, pd, own0, global_first);
     else astats_launch_t<double>(c, in, own_n, pd, own0, global_first);
 }

@@ -57,6 +57,10 @@ template <> struct BqIO<int16_t, float> {       // need_clipping path: clamp, th
     static __device__ __forceinline__ int16_t out(float v) { if (v < -32768.f) return -32768; if (v > 32767.f) return 32767; return (int16_t)(int)v; }
 };
 
+template <> struct BqIO<int32_t, double> {      // BIQUAD_FILTER(s32, int32_t, double, INT32_MIN, INT32_MAX, 1): clamp, then truncation
+    static __device__ __forceinline__ int32_t out(double v) { if (v < -2147483648.0) return (int32_t)0x80000000; if (v > 2147483647.0) return 2147483647; return (int32_t)v; }
+};
+
 template <class F> struct BqState { F s0 = 0, s1 = 0, s2 = 0, s3 = 0; };
 
 // one step; TDII: state (w1,w2).  DI: state (i1,i2,o1,o2).  Unfused mul/add = the C code
@@ -109,6 +113,7 @@ Sig jt_biquad(jt_ctx *c, const Sig &in, const BiquadCoef &k, bool tdii, double m
     if (in.fmt == JT_FMT_FLT) launch_biquad<float, float>(c, in, o, k, tdii, mix);
     else if (in.fmt == JT_FMT_DBL) launch_biquad<double, double>(c, in, o, k, tdii, mix);
     else if (in.fmt == JT_FMT_S16) launch_biquad<int16_t, float>(c, in, o, k, tdii, mix);
+    else if (in.fmt == JT_FMT_S32) launch_biquad<int32_t, double>(c, in, o, k, tdii, mix);
     else JT_THROW(JT_ERR_UNSUPPORTED, "biquad on sample format %d", in.fmt);
     return o;
 }
@@ -117,6 +122,9 @@ Sig jt_biquad(jt_ctx *c, const Sig &in, const BiquadCoef &k, bool tdii, double m
 // K20: all bands x all segments in one launch.  lane = (band, segment); highpass(lo) then
 // lowpass(hi), both direct form I in the link format, then astats' sum of squares.
 // ---------------------------------------------------------------------------------------
+template <class T> struct BandNorm { static __device__ __forceinline__ double nd(T v) { return (double)v; } };      // astats' normalised sample
+template <> struct BandNorm<int16_t> { static __device__ __forceinline__ double nd(int16_t v) { return (double)v / 32767.0; } };
+template <> struct BandNorm<int32_t> { static __device__ __forceinline__ double nd(int32_t v) { return (double)v / 2147483647.0; } };
 struct BandCoef { float hb0, hb1, hb2, hna1, hna2, lb0, lb1, lb2, lna1, lna2; double dh[5], dl[5]; };
 
 template <class T, class F>
@@ -138,7 +146,7 @@ k_band_rms(const T *__restrict__ x, int64_t n, int seg, int warm, int64_t segs_p
             const T h = BqIO<T, F>::out(bq_step<F, false>(sh, (F)x[i], hb0, hb1, hb2, hna1, hna2, (F)1, (F)0));
             const T l = BqIO<T, F>::out(bq_step<F, false>(sl, (F)h, lb0, lb1, lb2, lna1, lna2, (F)1, (F)0));
             if (i >= s0) {
-                const double nd = sizeof(T) == 2 ? (double)l / 32767.0 : (double)l;
+                const double nd = BandNorm<T>::nd(l);
                 acc = fma(nd, nd, acc);
             }
         }
@@ -174,6 +182,7 @@ void jt_band_rms_batch(jt_ctx *c, const Sig &in, const double *lo, const double 
         if (in.fmt == JT_FMT_FLT) k_band_rms<float, float><<<grid, 64, 0, c->stream>>>((const float *)in.d, in.n, seg, warm, spb, n_bands, d_coef, d_sum);
         else if (in.fmt == JT_FMT_DBL) k_band_rms<double, double><<<grid, 64, 0, c->stream>>>((const double *)in.d, in.n, seg, warm, spb, n_bands, d_coef, d_sum);
         else if (in.fmt == JT_FMT_S16) k_band_rms<int16_t, float><<<grid, 64, 0, c->stream>>>((const int16_t *)in.d, in.n, seg, warm, spb, n_bands, d_coef, d_sum);
+        else if (in.fmt == JT_FMT_S32) k_band_rms<int32_t, double><<<grid, 64, 0, c->stream>>>((const int32_t *)in.d, in.n, seg, warm, spb, n_bands, d_coef, d_sum);
         else JT_THROW(JT_ERR_UNSUPPORTED, "band rms on sample format %d", in.fmt);
     }
     std::vector<double> hs(n_bands);

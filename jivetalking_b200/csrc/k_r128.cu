@@ -146,10 +146,11 @@ k_r128_ticks(const TIN *__restrict__ x, int64_t n, int tick, int64_t n_ticks_tot
 }
 
 template <int STRUCT>
-static void run_ticks(jt_ctx *c, const Sig &in, int tick, int64_t n_ticks_total, const KWeight &kw,
+static void run_ticks(jt_ctx *c, const Sig &in0, int tick, int64_t n_ticks_total, const KWeight &kw,
                       double *d_pow, double *d_peak)
 {
     if (n_ticks_total <= 0) return;
+    const Sig in = in0.fmt == JT_FMT_S32 ? jt_convert(c, in0, JT_FMT_DBL) : in0;      // the filter's link is dbl: s32 widens exactly
     // 34 KB of staging per warp: 6 warps per SM.  Two ticks per lane (plus two of warm-up) unless that would
     // need a second wave of CTAs; then the lanes grow instead.
     const int WU = 2;
@@ -189,7 +190,7 @@ void jt_ebur128_launch(jt_ctx *c, const Sig &in, bool dualmono, bool true_peak, 
     run_ticks<0>(c, in, tick, nt, kw, d_pow, d_peak);
     if (true_peak) {
         if (in.rate == 192000) JT_CUDA(cudaMemcpyAsync(d_tp, d_peak, sizeof(double) * nt, cudaMemcpyDeviceToDevice, c->stream));
-        else { SwrPlan p = jt_swr_plan(in.rate, 192000); jt_swr_tick_absmax(c, in, p, tick, nt, d_tp); }
+        else { SwrPlan p = jt_swr_plan(in.rate, 192000); jt_swr_tick_absmax(c, in.fmt == JT_FMT_S32 ? jt_convert(c, in, JT_FMT_DBL) : in, p, tick, nt, d_tp); }
     }
     pd.hp = jt_pinned<double>(c, nt); pd.hk = jt_pinned<double>(c, nt); pd.ht = jt_pinned<double>(c, nt);
     JT_CUDA(cudaMemcpyAsync(pd.hp, d_pow, sizeof(double) * nt, cudaMemcpyDeviceToHost, c->stream));

@@ -622,9 +622,11 @@ static void launch_generic(jt_ctx *c, const Sig &in, const SwrPlan &p, int64_t n
 
 static bool small_path(const SwrPlan &p) { return p.div == 1 && p.filter_length == 32 && (p.phase_count == 2 || p.phase_count == 4 || p.phase_count == 6 || p.phase_count == 8); }
 
-Sig jt_swr_resample(jt_ctx *c, const Sig &in, const SwrPlan &p, int work_fmt, bool flush, int fuse_out_fmt)
+Sig jt_swr_resample(jt_ctx *c, const Sig &in0, const SwrPlan &p, int work_fmt, bool flush, int fuse_out_fmt)
 {
-    if (p.identity) return jt_convert(c, in, work_fmt);
+    if (p.identity) return jt_convert(c, in0, work_fmt);
+    // 32-bit integer input: swr converts to its internal format (flt for s32: swr_init's int_sample_fmt rule) before anything else
+    const Sig in = in0.fmt == JT_FMT_S32 ? jt_convert(c, in0, work_fmt) : in0;
     const int64_t n_out = flush ? p.out_count_flush(in.n) : p.out_count(in.n);
     // the f32 slot kernel converts on store: the 44.1 kHz / s16 output stage never materialises its float stream
     const bool fuse_s16 = work_fmt == JT_FMT_FLT && fuse_out_fmt == JT_FMT_S16 && slot_path_ok(p) && in.fmt != JT_FMT_DBL;
@@ -676,7 +678,7 @@ void jt_swr_tick_absmax(jt_ctx *c, const Sig &in, const SwrPlan &p, int tick, in
     if (n_ticks <= 0) return;
     // outputs swr has produced once n_ticks*tick inputs were fed (ebur128 never flushes)
     const int64_t fed = n_ticks * (int64_t)tick;
-    Sig v = in; v.n = std::min(in.n, fed);
+    Sig v = in.fmt == JT_FMT_S32 ? jt_convert(c, in, JT_FMT_DBL) : in; v.n = std::min(in.n, fed);
     const int64_t n_out = p.out_count(v.n);
     if (n_out <= 0) return;
     JtLaunch Lc(c, small_path(p) ? "truepeak_oversample:small_f64" : phase_path_ok(p) ? "truepeak_oversample:phase_f64" : qlane_path_ok(p) ? "truepeak_oversample:qlane_f64" : "truepeak_oversample:generic");

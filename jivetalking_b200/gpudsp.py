@@ -14,8 +14,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libjtdsp.so")
 
 FMT_S16, FMT_S32, FMT_FLT, FMT_DBL = 1, 2, 3, 4
-_NP_OF_FMT = {FMT_S16: np.int16, FMT_FLT: np.float32, FMT_DBL: np.float64}
-_FMT_OF_NP = {np.dtype(np.int16): FMT_S16, np.dtype(np.float32): FMT_FLT, np.dtype(np.float64): FMT_DBL}
+_NP_OF_FMT = {FMT_S16: np.int16, FMT_S32: np.int32, FMT_FLT: np.float32, FMT_DBL: np.float64}
+_FMT_OF_NP = {np.dtype(np.int16): FMT_S16, np.dtype(np.int32): FMT_S32, np.dtype(np.float32): FMT_FLT, np.dtype(np.float64): FMT_DBL}
 
 AS_NAMES = ["Dynamic_range", "RMS_level", "Peak_level", "RMS_trough", "RMS_peak", "DC_offset", "Flat_factor",
             "Crest_factor", "Zero_crossings_rate", "Zero_crossings", "Max_difference", "Min_difference",

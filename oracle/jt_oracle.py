@@ -15,7 +15,7 @@ _SO = os.path.join(_HERE, "_build", "libjtoracle.so")
 NSPEC = 13
 SPEC_NAMES = ["mean", "variance", "centroid", "spread", "skewness", "kurtosis", "entropy",
               "flatness", "crest", "flux", "slope", "decrease", "rolloff"]
-FMT_S16, FMT_FLT, FMT_DBL = 1, 3, 4
+FMT_S16, FMT_S32, FMT_FLT, FMT_DBL = 1, 2, 3, 4
 
 
 def build(force=False):
@@ -108,7 +108,7 @@ def ebur128(x, rate, dualmono=True, true_peak=True):
 
 def astats(x, rate):
     x = np.ascontiguousarray(x)
-    fmt = {np.dtype(np.int16): FMT_S16, np.dtype(np.float32): FMT_FLT, np.dtype(np.float64): FMT_DBL}[x.dtype]
+    fmt = {np.dtype(np.int16): FMT_S16, np.dtype(np.int32): FMT_S32, np.dtype(np.float32): FMT_FLT, np.dtype(np.float64): FMT_DBL}[x.dtype]
     o = AstatsOut()
     assert lib().orc_astats(_ptr(x), fmt, len(x), rate, C.byref(o)) == 0
     return {f: getattr(o, f) for f in ASTATS_FIELDS}
@@ -138,7 +138,8 @@ def biquad(x, rate, kind, freq, q=0.707, normalize=False, tdii=False, mix=1.0):
     x = np.ascontiguousarray(x)
     c = np.zeros(5)
     _proto("orc_biquad_design", None, [C.c_int, _D, _D, C.c_int, C.c_int, _P])(1 if kind == "highpass" else 0, freq, q, rate, int(normalize), _ptr(c))
-    name = {np.dtype(np.float32): "orc_biquad_f32", np.dtype(np.float64): "orc_biquad_f64", np.dtype(np.int16): "orc_biquad_s16"}[x.dtype]
+    name = {np.dtype(np.float32): "orc_biquad_f32", np.dtype(np.float64): "orc_biquad_f64", np.dtype(np.int16): "orc_biquad_s16",
+            np.dtype(np.int32): "orc_biquad_s32"}[x.dtype]
     out = np.zeros_like(x)
     _proto(name, None, [_P, _P, _I64, _P, C.c_int, _D])(_ptr(x), _ptr(out), len(x), _ptr(c), int(tdii), mix)
     return out

@@ -26,15 +26,33 @@ def downmix(x, channels):
         return x
     assert channels == 2
     n = x.size // 2
+    if x.dtype == np.int32:
+        # swr's internal format for a 32-bit integer rematrix is FLTP; the matrix is the normalised 0.5 / 0.5 (pinned on the
+        # real libswresample: tests/golden/swr_golden.npz)
+        L, R = to_f32(x[0::2]), to_f32(x[1::2])
+        mix = (L * np.float32(0.5) + R * np.float32(0.5)).astype(np.float32)
+        return f32_to_s32(mix)
     out = np.zeros(n, dtype=x.dtype)
     fn = {np.dtype(np.float32): O.lib().orc_downmix_stereo_f32, np.dtype(np.int16): O.lib().orc_downmix_stereo_s16}[x.dtype]
     fn(x.ctypes.data_as(O._P), n, out.ctypes.data_as(O._P))
     return out
 
 
+def f32_to_s32(v):
+    """audioconvert.c: av_clipl_int32(llrintf(v * (1U << 31)))"""
+    s = np.rint((v.astype(np.float32) * np.float32(2147483648.0)).astype(np.float64))
+    return np.clip(s, -2147483648.0, 2147483647.0).astype(np.int32)
+
+
+def f64_to_s32(v):
+    return np.clip(np.rint(v.astype(np.float64) * 2147483648.0), -2147483648.0, 2147483647.0).astype(np.int32)
+
+
 def to_f32(x):
     if x.dtype == np.float32:
         return x
+    if x.dtype == np.int32:
+        return (x.astype(np.float32) * np.float32(1.0 / 2147483648.0)).astype(np.float32)
     if x.dtype == np.int16:
         return (x.astype(np.float32) * np.float32(1.0 / 32768.0)).astype(np.float32)
     return x.astype(np.float32)
@@ -43,6 +61,8 @@ def to_f32(x):
 def to_f64(x):
     if x.dtype == np.int16:
         return x.astype(np.float64) * (1.0 / 32768.0)
+    if x.dtype == np.int32:
+        return x.astype(np.float64) * (1.0 / 2147483648.0)
     return x.astype(np.float64)
 
 
@@ -95,7 +115,8 @@ def pass1_meta(x, rate, channels=1, frame_size=4096):
     mono = downmix(x, channels)
     n = len(mono)
     ends = [min((f + 1) * frame_size, n) for f in range((n + frame_size - 1) // frame_size)]
-    return analysis_meta(mono, to_f32(mono), to_f64(mono), rate, ends)
+    # aspectralstats turns the link to flt; ebur128 widens THAT (exact for s16 / flt input, float-rounded for s32)
+    return analysis_meta(mono, to_f32(mono), to_f64(to_f32(mono)) if mono.dtype == np.int32 else to_f64(mono), rate, ends)
 
 
 def pass1_analyse(x, rate, channels=1, frame_size=4096):
@@ -107,6 +128,8 @@ def pass1_analyse(x, rate, channels=1, frame_size=4096):
     n = len(x) // channels
     if x.dtype == np.int16:
         xs = x.astype(np.float64) / 32768.0
+    elif x.dtype == np.int32:
+        xs = x.astype(np.float64) / 2147483648.0
     else:
         xs = x.astype(np.float64)
     xs = xs.reshape(n, channels) if channels > 1 else xs
@@ -272,7 +295,11 @@ def run_spec(spec, x, rate, channels=1, frame_size=4096, want_pcm=True):
         if dt == np.float64:
             return to_f64(sig)
         if dt == np.float32:
-            return to_f32(sig) if sig.dtype == np.int16 else sig.astype(np.float32)
+            return to_f32(sig) if sig.dtype in (np.int16, np.int32) else sig.astype(np.float32)
+        if dt == np.int32:
+            return f32_to_s32(sig) if sig.dtype == np.float32 else f64_to_s32(sig) if sig.dtype == np.float64 else sig.astype(np.int32) * 65536
+        if dt == np.int16 and sig.dtype == np.int32:
+            return (sig >> 16).astype(np.int16)
         if dt == np.int16:
             out = np.zeros(len(sig), dtype=np.int16)
             (O.lib().orc_conv_f64_to_s16 if sig.dtype == np.float64 else O.lib().orc_conv_f32_to_s16)(O._ptr(np.ascontiguousarray(sig)), len(sig), O._ptr(out))
@@ -303,7 +330,7 @@ def run_spec(spec, x, rate, channels=1, frame_size=4096, want_pcm=True):
         if name == "aformat":
             out_rate = int(_get(o, "sample_rates", "r", default=rate))
             sf = _get(o, "sample_fmts", "f", default="")
-            dt = {"s16": np.int16, "flt": np.float32, "dbl": np.float64, "": cur.dtype}[sf]
+            dt = {"s16": np.int16, "s32": np.int32, "flt": np.float32, "dbl": np.float64, "": cur.dtype}[sf]
             if last and not want_pcm and out_rate != rate:
                 tot = O.swr_out_count(len(cur), rate, out_rate, flush=True)
                 nf, done = [], 0

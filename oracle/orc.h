@@ -74,7 +74,7 @@ int orc_ebur128(const double *x, int64_t n, int rate, int dualmono, int want_tru
                 orc_r128_summary *sum);
 
 /* ---------------- astats (libavfilter/af_astats.c), one channel -------------------- */
-enum { ORC_FMT_S16 = 1, ORC_FMT_FLT = 3, ORC_FMT_DBL = 4 };   /* AVSampleFormat values */
+enum { ORC_FMT_S16 = 1, ORC_FMT_S32 = 2, ORC_FMT_FLT = 3, ORC_FMT_DBL = 4 };   /* AVSampleFormat values */
 typedef struct orc_astats_out {
     double nb_samples;
     double DC_offset, Min_level, Max_level, Min_difference, Max_difference, Mean_difference,

@@ -22,7 +22,7 @@ int orc_astats(const void *xv, int fmt, int64_t n, int rate, orc_astats_out *o)
     const double time_constant = 0.05;
     const int tc_samples = (int)fmax(time_constant * rate + .5, 1);
     const double mult = exp((-1 / time_constant / rate));
-    const int maxbitdepth = fmt == ORC_FMT_S16 ? 16 : fmt == ORC_FMT_FLT ? 32 : 64;
+    const int maxbitdepth = fmt == ORC_FMT_S16 ? 16 : (fmt == ORC_FMT_FLT || fmt == ORC_FMT_S32) ? 32 : 64;
 
     double min = DBL_MAX, max = -DBL_MAX, nmin = DBL_MAX, nmax = -DBL_MAX;
     double min_non_zero = DBL_MAX, min_diff = DBL_MAX, max_diff = 0;
@@ -42,6 +42,7 @@ int orc_astats(const void *xv, int fmt, int64_t n, int rate, orc_astats_out *o)
     for (int64_t k = 0; k < n; k++) {
         double d, nd; int64_t iv;
         if (fmt == ORC_FMT_S16) { int16_t s = ((const int16_t *)xv)[k]; d = s; nd = s / (double)INT16_MAX; iv = s; }
+        else if (fmt == ORC_FMT_S32) { int32_t s = ((const int32_t *)xv)[k]; d = s; nd = s / (double)INT32_MAX; iv = s; }
         else if (fmt == ORC_FMT_FLT) { float s = ((const float *)xv)[k]; d = s; nd = s; iv = llrint(s * (double)(UINT64_C(1) << 31)); }
         else { double s = ((const double *)xv)[k]; d = s; nd = s;
                double t = s * 9223372036854775808.0;

@@ -9,6 +9,7 @@
  */
 #include "orc.h"
 #include <math.h>
+#include <stdint.h>
 #include <string.h>
 
 void orc_biquad_design(int highpass, double freq, double q, int rate, int normalize, double *c /* b0 b1 b2 a1 a2 */)
@@ -28,7 +29,7 @@ void orc_biquad_design(int highpass, double freq, double q, int rate, int normal
     c[0] = b0; c[1] = b1; c[2] = b2; c[3] = a1; c[4] = a2;
 }
 
-#define GEN(NAME, T, F, CLIP)                                                              \
+#define GEN(NAME, T, F, CLIP, LO, HI)                                                              \
 void NAME(const T *in, T *out, int64_t n, const double *c, int tdii, double mix)           \
 {                                                                                          \
     F b0 = (F)c[0], b1 = (F)c[1], b2 = (F)c[2], a1 = (F)-c[3], a2 = (F)-c[4];              \
@@ -45,10 +46,11 @@ void NAME(const T *in, T *out, int64_t n, const double *c, int tdii, double mix)
             i2 = i1; i1 = x; o2 = o1; o1 = o;                                              \
         }                                                                                  \
         o = o * wet + x * dry;                                                             \
-        if (CLIP) { if (o < -32768.f) o = -32768.f; else if (o > 32767.f) o = 32767.f; }   \
+        if (CLIP) { if (o < (F)(LO)) o = (F)(LO); else if (o > (F)(HI)) o = (F)(HI); }     \
         out[i] = (T)o;                                                                     \
     }                                                                                      \
 }
-GEN(orc_biquad_f32, float, float, 0)
-GEN(orc_biquad_f64, double, double, 0)
-GEN(orc_biquad_s16, int16_t, float, 1)
+GEN(orc_biquad_f32, float, float, 0, 0, 0)
+GEN(orc_biquad_f64, double, double, 0, 0, 0)
+GEN(orc_biquad_s16, int16_t, float, 1, INT16_MIN, INT16_MAX)
+GEN(orc_biquad_s32, int32_t, double, 1, INT32_MIN, INT32_MAX)      /* BIQUAD_FILTER(s32, int32_t, double, INT32_MIN, INT32_MAX, 1) */

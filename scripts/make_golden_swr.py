@@ -38,5 +38,22 @@ out["stereo_f32_to_mono"] = ref_swr.convert(st, "flt", 48000, "flt", 48000, in_c
 st16 = np.clip(np.round(st * 32768), -32768, 32767).astype(np.int16)
 out["in_stereo_s16"] = st16
 out["stereo_s16_to_mono"] = ref_swr.convert(st16, "s16", 48000, "s16", 48000, in_ch=2, out_ch=1)
+# 32-bit integer samples (what 24-bit FLAC / WAV decode to): conversions, the flt-internal normalised downmix, and the
+# flt-internal resample swr picks for a 32-bit integer input (swr_init's int_sample_fmt rule)
+s32 = np.clip(np.round(noise * 0.9 * 2 ** 31), -2 ** 31, 2 ** 31 - 1).astype(np.int32)
+s32[:6] = [2 ** 31 - 1, -2 ** 31, 2 ** 31 - 129, 12345678, -1, 1]
+out["in_s32"] = s32
+out["s32_to_flt"] = ref_swr.convert(s32, "s32", 48000, "flt", 48000)
+out["s32_to_dbl"] = ref_swr.convert(s32, "s32", 48000, "dbl", 48000)
+out["s32_to_s16"] = ref_swr.convert(s32, "s32", 48000, "s16", 48000)
+out["flt_to_s32"] = ref_swr.convert((noise * 4.0).astype(np.float32), "flt", 48000, "s32", 48000)
+out["dbl_to_s32"] = ref_swr.convert(noise * 4.0, "dbl", 48000, "s32", 48000)
+st32 = np.empty(2 * 3000, dtype=np.int32); st32[0::2] = s32[:3000]; st32[1::2] = s32[3000:]
+out["in_stereo_s32"] = st32
+out["stereo_s32_to_mono"] = ref_swr.convert(st32, "s32", 48000, "s32", 48000, in_ch=2, out_ch=1)
+out["s32_to_dbl_48000_192000"] = ref_swr.convert(s32, "s32", 48000, "dbl", 192000, frame=4096, flush=True)
+# loudnorm's dynamic-mode output leaves at 192 kHz / dbl: the aresample barrier back to the source rate
+for (ir, orr) in ((192000, 44100), (192000, 48000)):
+    out[f"dbl_noise_{ir}_{orr}_1"] = ref_swr.convert(noise, "dbl", ir, "dbl", orr, frame=4096, flush=True)
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "swr_golden.npz"), **out)
 print("wrote", len(out), "arrays")

@@ -72,3 +72,29 @@ def test_live_against_library_when_present():
             ref = ref_swr.convert(x, "dbl", a, "dbl", b, frame=1000, flush=True)
             y = O.swr_resample(x, a, b, flush=True)
             assert len(y) == len(ref) and (len(y) == 0 or np.max(np.abs(y - ref)) < 2e-15)
+
+
+def test_s32_conversions_and_downmix_match_real_swr():
+    """32-bit integer samples (what 24-bit FLAC / WAV decode to; analyser_metrics.go:285,329 handles them): the oracle's
+    numpy restatements of audioconvert.c's s32 rows and of the flt-internal normalised rematrix, against the real library."""
+    import oracle_graph as OG
+    s32 = G["in_s32"]
+    assert np.array_equal(OG.to_f32(s32), G["s32_to_flt"])
+    assert np.array_equal(OG.to_f64(s32), G["s32_to_dbl"])
+    assert np.array_equal((s32 >> 16).astype(np.int16), G["s32_to_s16"])
+    x = G["in_noise"] * 4.0
+    assert np.array_equal(OG.f32_to_s32(x.astype(np.float32)), G["flt_to_s32"])
+    assert np.array_equal(OG.f64_to_s32(x), G["dbl_to_s32"])
+    assert np.array_equal(OG.downmix(G["in_stereo_s32"], 2), G["stereo_s32_to_mono"])
+    # a 32-bit integer input with a rate change runs swr's FLTP-internal resampler
+    y = O.swr_resample(OG.to_f32(s32), 48000, 192000, flush=True).astype(np.float64)
+    ref = G["s32_to_dbl_48000_192000"]
+    assert len(y) == len(ref) and np.max(np.abs(y - ref)) < 5e-7
+
+
+@pytest.mark.parametrize("rates", [(192000, 44100), (192000, 48000)])
+def test_downsample_from_192k_matches_real_swr(rates):
+    """the aresample barrier behind a dynamic-mode loudnorm (normalise.go:1294-1304)"""
+    ref = G[f"dbl_noise_{rates[0]}_{rates[1]}_1"]
+    y = O.swr_resample(G["in_noise"], rates[0], rates[1], flush=True)
+    assert len(y) == len(ref) and np.max(np.abs(y - ref)) < 2e-15
