@@ -143,8 +143,11 @@ def test_band_rms_17(ctx, speech48):
     for b in range(17):
         y = O.biquad(O.biquad(reg, 48000, "highpass", lo[b]), 48000, "lowpass", hi[b])
         exp = O.astats(y, 48000)["RMS_level"]
-        if np.isfinite(exp) and hi[b] < 23000:
+        # (the 24 kHz band's 29.4 kHz low-pass lies past Nyquist: af_biquads.c config_filter() puts it in bypass, so the
+        #  band measures the 19.6 kHz high-passed region -- both sides implement that, and the band is compared like the rest)
+        if np.isfinite(exp):
             assert found[b] == 1 and abs(got[b] - exp) < 2e-3, (b, got[b], exp)
+    assert np.isfinite(got[16])
 
 
 def test_unsupported_and_bad_specs_fail_loudly(ctx):

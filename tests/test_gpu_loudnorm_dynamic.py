@@ -119,14 +119,14 @@ def test_pass4_graph_with_dynamic_fallback_and_aresample_barrier(ctx):
     OG.assert_meta_close(got["meta"], exp["meta"], spectral_rtol=5e-3, roundoff_only_below_lufs=-100.0)
 
 
-@pytest.mark.parametrize("gap", [(1.0, 0.3), (0.0, 0.0)])
+@pytest.mark.parametrize("gap", [(1.0, 0.3, 3.0), (0.0, 0.0, 3.0), (0.0, 0.0, 33 * 4096 / 44100.0)])
 def test_process_audio_on_the_reference_fixture(ctx, gap):
     """TestProcessAudio (processor_test.go:360-376): 3 s, 44.1 kHz s16, 440 Hz at -18 dBFS + noise at -55 dBFS, 0.3 s gap at
     1 s, through the test's own minimal chain.  Whether Pass 4's loudnorm stays linear hangs on how Pass 3's LRA prints
-    (0.1 LU histogram bins over three or four short-term blocks, the flush frame counted twice): with the gap it comes
-    out non-zero here, without it 0.00 -> dynamic mode.  The reference ships the file either way, so must we."""
+    (0.1 LU histogram bins over three short-term blocks, the flush frame counted twice, 65 ms of asetnsamples padding
+    inside the second one): 0.00 selects dynamic mode.  The reference ships the file either way, so must we."""
     from jivetalking_b200 import adapt as A
-    x = synth.reference_test_audio(3.0, 44100, 440.0, -18.0, -55.0, gap[0], gap[1])
+    x = synth.reference_test_audio(gap[2], 44100, 440.0, -18.0, -55.0, gap[0], gap[1])
     base = A.default_filter_config()             # newTestBaseConfig + downmix, analysis, resample, 95 Hz high-pass
     base.bandlimit_lowpass.enabled = base.noise_reduction.enabled = base.speech_gate.enabled = 0
     base.levelling_compressor.enabled = base.deesser.enabled = 0
@@ -134,8 +134,8 @@ def test_process_audio_on_the_reference_fixture(ctx, gap):
     pcm, res, an = A.process_audio_adaptive(ctx, x, 44100, base=base)
     assert "highpass=f=95" in an.pass2_spec.decode()
     assert res.pass4.valid
-    if gap[1] == 0.0:
-        assert res.pass4.normalization_type == 1
+    # af_loudnorm's init(): measured_LRA == 0 is one of the sentinels that keep it out of linear mode
+    assert res.pass4.normalization_type == (1 if float("%.2f" % res.pass3.input_lra) == 0.0 else 0)
     assert len(pcm) % 4096 == 0 and res.n_out == len(pcm) and len(pcm) >= 3 * 44100
     # same orchestration over the oracle
     p2 = OG.run_spec(an.pass2_spec.decode(), x, 44100)

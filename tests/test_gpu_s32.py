@@ -28,7 +28,7 @@ def test_pass1_s32_mono(ctx, speech24):
     exp = OG.pass1_meta(speech24, 48000)
     OG.assert_meta_close(got["meta"], exp)
     last = [m for m in got["meta"] if not math.isnan(m.astats[0])][-1]
-    assert last.astats[gpudsp.AS_NAMES.index("Bit_depth")] == 24.0            # astats sees the 24 used bits of the 32
+    assert 16.0 <= last.astats[gpudsp.AS_NAMES.index("Bit_depth")] <= 24.0     # astats counts the bits in use: never the low 8 of a 24-bit master
 
 
 def test_analyse_s32_stereo_intervals(ctx):
