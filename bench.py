@@ -1,16 +1,23 @@
 #!/usr/bin/env python
-"""bench.py -- jivetalking four-pass chain (analyse / process / measure / normalise) on B200.
+"""bench.py -- jivetalking ProcessAudio (analyse / process / measure / normalise) on B200.
 
-Metric (BASELINE.json): samples/s (x realtime) through the full 4-pass chain.  One "step" = the
-whole chain over one 60 min 48 kHz mono f32 stream (BASELINE.json configs[1]) per GPU; with N GPUs
-each rank processes its own file (configs[2], file-per-GPU, no data-path collective -> weak
-scaling).  `value` is timed with the stream already resident in HBM (jt_process_audio_dev); `e2e`
-goes through the reference-facing C ABI call jt_process_audio with pinned HOST buffers, so the
-host->device copy of the PCM and the device->host copy of the 16-bit result are inside the timed
-region.  `--impl reference` times the CPU oracle (the restated FFmpeg path; the reference's own
-embedded-FFmpeg path needs Go + libffmpeg.a, absent here) on the box's host cores.
+Metric (BASELINE.json): samples/s (x realtime) through the full 4-pass chain.  One "step" = ProcessAudio
+(processor.go:78-216: Pass 1 -> detector -> 17 band graphs -> AdaptConfig -> Pass 2 -> region re-measures -> Pass 3 ->
+Pass 4 -> region re-measures) over one 60 min 48 kHz mono f32 conversational stream (BASELINE.json configs[1]) per GPU; with
+N GPUs each rank processes its own file (configs[2], file per GPU, no data-path collective -> weak scaling).
+
+  value : the stream already resident in HBM (jt_process_audio_adaptive_dev), CUDA events on the library's stream
+  e2e   : the reference-facing C-ABI call jt_process_audio_adaptive with pinned HOST buffers -- the host->device copy of the
+          PCM and the device->host copy of the 16-bit result are inside the timed region
+  extras: fixed_spec (caller-supplied DefaultFilterConfig spec, the round-1 headline), flac_encode (the result's container),
+          batch_sweep (configs[4]: 1..256 concurrent 10 min streams, N = 1 only), stream_sharded (configs[3]: one 3 h
+          96 kHz stereo stream over the N GPUs, N > 1 only)
+
+`--impl reference` times the CPU oracle's ProcessAudio (oracle/chain_oracle.py: the restated FFmpeg path -- the reference's
+own embedded-FFmpeg path needs Go + libffmpeg.a, absent here) on the box's host cores; it never loads libjtdsp.
 """
 import argparse
+import importlib.util
 import json
 import math
 import os
@@ -20,12 +27,11 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-sys.path.insert(0, ROOT)
 
 RATE = 48000
 MINUTES = 60
-BYTES_PER_SAMPLE_4PASS = 15.35          # 4 + 5.8375 + 1.8375 + 3.675
-# algorithmic HBM bytes per input sample of each kernel group (bytes of its resident input + output)
+BYTES_PER_SAMPLE_4PASS = 15.35          # 4 (Pass 1) + 5.8375 (Pass 2) + 1.8375 (Pass 3) + 3.675 (Pass 4)
+# algorithmic HBM bytes per input sample of each kernel group: bytes of its resident input + output
 KERNEL_BYTES = {
     "anlmdn": 8.0,                      # f32 in + f32 out
     "afftdn": 8.0,
@@ -39,28 +45,36 @@ KERNEL_BYTES = {
     "agate_gain": 24.0, "acompressor_gain": 24.0,
     "alimiter": 16.0 * 0.91875,
     "biquad": 8.0, "convert": 12.0, "raw_frame_stats": 4.0, "deesser": 16.0,
-    "loudnorm_linear_gain": 16.0 * 0.91875, "volume": 8.0,
+    "loudnorm_linear_gain": 16.0 * 0.91875, "volume": 8.0, "band_rms": 4.0,
 }
-
-
-# dram__bytes_read.sum + dram__bytes_write.sum per launch on the 60 min stream, from the `ncu --set full` captures
-# summarised in profiles/ncu_r1k.md / ncu_r1h.md (cold-cache replay; None where the kernel was not captured)
-NCU_TRAFFIC_BYTES_60MIN = {
-    "adeclick:interp": 1.661498e9 + 0.722141e9,            # profiles/ncu_r1k.md
-    "anlmdn": 0.706247e9 + 0.651037e9,                     # profiles/ncu_r1k.md
-    "afftdn:fwd": 0.702286e9 + 2.324030e9,
-    "alimiter": 3.293223e9 + 1.231703e9,
-    "swr_resample:qlane_f64": 0.705825e9 + 1.226726e9,
-    "envelope_follower": 8.088282e9 + 1.336265e9,          # profiles/ncu_r1k.md
-    "r128_kweight_ticks": 1.383083e9 + 0.006421e9,         # profiles/ncu_r1d.md
-}
-# what actually bounds each group; the contract's roofline is reported against HBM regardless
 KERNEL_BOUND = {
-    "adeclick:interp": "latency (10 warps/SM, shared-memory round trips of the banded LDL^T k-loop)",
+    "adeclick:interp": "latency (banded LDL^T k-loop, shared-memory round trips)",
     "anlmdn": "FP32 issue / shared-memory bandwidth",
-    "envelope_follower": "f64 dependent-issue latency (one warp per scheduler)",
+    "envelope_follower": "f64 dependent-issue latency (one lane per stream segment)",
     "afftdn:fwd": "barriers of the shared-memory FFT + f64 tracking statistics",
 }
+
+
+def load_by_path(name, path):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def synth_module():
+    """the synthetic-input generators, loaded by path: the reference arm must not import the product package"""
+    return load_by_path("jt_synth", os.path.join(ROOT, "jivetalking_b200", "synth.py"))
+
+
+def ncu_traffic():
+    """dram bytes per launch of each kernel on the 60 min stream, from the committed `ncu --set full` summaries
+    (profiles/kernel_roofline_r2.json, written by scripts/summarise_profiles.py)"""
+    p = os.path.join(ROOT, "profiles", "kernel_roofline_r2.json")
+    try:
+        return {k: v.get("dram_bytes_per_launch") for k, v in json.load(open(p)).get("kernels", {}).items()}, os.path.relpath(p, ROOT)
+    except Exception:
+        return {}, None
 
 
 def measured_peaks():
@@ -114,54 +128,44 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
-def make_input(seed, minutes, kind="speech"):
-    from jivetalking_b200 import synth
+def _block(args):
+    seed, seconds = args
+    return synth_module().podcast_like(seconds, RATE, seed=seed)
+
+
+def make_input(seed, minutes):
+    """C2: `minutes` of the conversational recipe (speech runs, room-tone pauses: the detector elects both regions and every
+    adaptive branch runs), 10 min blocks with distinct seeds, generated on a few host processes"""
+    import multiprocessing as mp
     import numpy as np
-    gen = synth.speech_like if kind == "speech" else synth.podcast_like      # podcast: > 20 % room tone, elects both regions
-    blocks = [gen(600.0 if m + 10 <= minutes else (minutes - m) * 60.0, RATE, seed=seed * 1000 + m)
-              for m in range(0, minutes, 10)]
-    return np.concatenate(blocks)
+    jobs = [(seed * 1000 + m, 600.0 if m + 10 <= minutes else (minutes - m) * 60.0) for m in range(0, minutes, 10)]
+    with mp.get_context("spawn").Pool(min(len(jobs), max(1, (os.cpu_count() or 2) // 2))) as pool:
+        return np.concatenate(pool.map(_block, jobs))
 
 
-def cpu_chain(x, rate):
-    """The oracle's four-pass chain (test infrastructure; only the cpu_baseline / reference legs call it)."""
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import oracle_graph as OG
-    from jivetalking_b200 import gpudsp
-    OG.run_spec(gpudsp.pass1_spec(), x, rate, want_pcm=False)
-    p2 = OG.run_spec(gpudsp.default_pass2_spec(), x, rate)
-    last = [m for m in p2["meta"] if not math.isnan(m["I"])][-1]
-    out_tp = -120.0 if last["true_peak"] <= 0 else 20 * math.log10(last["true_peak"])
-    spec3, plan = gpudsp.build_pass3_spec(last["I"], out_tp)
-    p3 = OG.run_spec(spec3, p2["pcm"], 44100, want_pcm=False)
-    st = gpudsp.LoudnormStats()
-    for k in ("input_i", "input_tp", "input_lra", "input_thresh"):
-        setattr(st, k, p3["loudnorm"][k])
-    spec4, _, _ = gpudsp.build_pass4_spec(plan, st)
-    return OG.run_spec(spec4, p2["pcm"], 44100)["pcm"]
-
-
+# ---- CPU legs: the oracle's ProcessAudio on host cores (test infrastructure; never the thing shipped) --------------------
 def _cpu_worker(args):
     seed, seconds = args
-    from jivetalking_b200 import synth
-    x = synth.speech_like(seconds, RATE, seed=seed)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import chain_oracle as CO
+    x = synth_module().podcast_like(seconds, RATE, seed=seed)
     t0 = time.perf_counter()
-    cpu_chain(x, RATE)
+    CO.process_audio(x, RATE)
     return len(x), time.perf_counter() - t0
 
 
 def cpu_baseline(cores, seconds_per_core):
-    """Each host core runs the scalar oracle chain over its own `seconds_per_core` s stream
-    (the reference's own parallelism is one file per CPU thread: cmd/jivetalking/pool.go:122-153)."""
+    """Each host core runs the scalar oracle ProcessAudio over its own stream (the reference's own parallelism is one file per
+    CPU thread: cmd/jivetalking/pool.go:122-153)."""
     import multiprocessing as mp
-    ctx = mp.get_context("spawn")
-    t0 = time.perf_counter()
-    with ctx.Pool(cores) as pool:
+    with mp.get_context("spawn").Pool(cores) as pool:
         res = pool.map(_cpu_worker, [(900 + i, seconds_per_core) for i in range(cores)])
-    wall = time.perf_counter() - t0
     total = sum(r[0] for r in res)
     busy = max(r[1] for r in res)
-    return total / busy, total, busy, wall
+    return total / busy, total, busy
+
+
+CPU_SAMPLE_SECONDS = 120.0              # ~25 s of scalar CPU work per core per step
 
 
 def run_reference(args):
@@ -169,10 +173,9 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    sec = 150.0                           # ~20 s of scalar CPU work per core (the oracle chain runs ~8x realtime/core)
     vals = []
     for i in range(args.warmup + args.steps):
-        v, total, busy, _ = cpu_baseline(cores, sec)
+        v, total, busy = cpu_baseline(cores, CPU_SAMPLE_SECONDS)
         if i >= args.warmup:
             vals.append((v, busy))
     value = sum(v for v, _ in vals) / len(vals)
@@ -180,12 +183,57 @@ def run_reference(args):
             "realtime_x": value / RATE, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * sum(b for _, b in vals) / len(vals), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
-            "config": {"workload": "60 min 48 kHz mono f32, full 4-pass chain (BASELINE.json configs[1])",
+            "config": {"workload": "ProcessAudio (adaptive), 60 min 48 kHz mono f32 (BASELINE.json configs[1])",
                        "note": "bounded sample of that workload per step"},
             "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port",
-                             "sample": f"{cores} x {sec:.0f} s streams of the C2 recipe, one scalar oracle chain per core"},
+                             "sample": f"{cores} x {CPU_SAMPLE_SECONDS:.0f} s conversational streams, one scalar oracle ProcessAudio per core "
+                                       "(Pass 1, detector, 17 bands, AdaptConfig, Pass 2-4, region re-measures)"},
             "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+# ---- configs[4]: batch sweep ------------------------------------------------------------------------------------------
+def batch_sweep(local, torch, gpudsp, adapt, steps_cap=256):
+    """B concurrent 10 min streams on ONE GPU, B = 1 .. 256: a pool of worker threads, one jt_ctx (one CUDA stream) each -- the
+    reference's goroutine-per-file pool (pool.go:122-153) -- drains the B files.  x realtime = B x 600 s / wall time, device
+    synchronised on both sides.  The B inputs are four distinct seeds used round-robin, device resident."""
+    import numpy as np
+    syn = synth_module()
+    n = 600 * RATE
+    inputs = [torch.from_numpy(syn.podcast_like(600.0, RATE, seed=777 + i)).cuda() for i in range(4)]
+    out_cap = int(n * 44100 / RATE) + 3 * 4096
+    max_workers = 8
+    ctxs = [gpudsp.Context(local) for _ in range(max_workers)]
+    outs = [torch.empty(out_cap, dtype=torch.int16, device="cuda") for _ in range(max_workers)]
+
+    def run(B):
+        W = min(B, max_workers)
+        def work(w):
+            for i in range(w, B, W):
+                adapt.process_audio_adaptive_ptr(ctxs[w], inputs[i % len(inputs)].data_ptr(), n, RATE, 1, gpudsp.FMT_FLT,
+                                                 outs[w].data_ptr(), out_cap, True)
+        ts = [threading.Thread(target=work, args=(w,)) for w in range(W)]
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0
+
+    run(max_workers)                                   # warm every context (arena growth, table uploads)
+    res = {}
+    B = 1
+    while B <= steps_cap:
+        dt = run(B)
+        res[str(B)] = {"seconds": dt, "realtime_x": B * 600.0 / dt, "workers": min(B, max_workers)}
+        B *= 2
+    for c in ctxs:
+        c.close()
+    del inputs, outs
+    return {"streams": "10 min 48 kHz mono f32 conversational, ProcessAudio (adaptive), device resident", "by_batch": res,
+            "note": "one worker thread + jt_ctx per concurrent stream, at most 8; wall clock between device synchronisations"}
 
 
 def main():
@@ -196,15 +244,17 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--minutes", type=int, default=MINUTES)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-adaptive", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip fixed_spec / flac_encode / batch_sweep / stream_sharded")
+    ap.add_argument("--sharded-hours", type=float, default=3.0)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
 
+    sys.path.insert(0, ROOT)
     import numpy as np
     import torch
     import torch.distributed as dist
-    from jivetalking_b200 import gpudsp
+    from jivetalking_b200 import adapt, gpudsp, shard
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -215,7 +265,6 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    from jivetalking_b200 import shard
     my_files = shard.assign_files(world, rank, world)               # one file per GPU (configs[2])
     x = make_input(shard.stream_seed(12345, my_files[0]), args.minutes)   # C2 / C3: seeds 12345 + file index
     n = len(x)
@@ -234,15 +283,15 @@ def main():
         torch.cuda.synchronize()
 
     def step_dev():
-        return ctx.process_audio_ptr(d_in.data_ptr(), n, RATE, 1, gpudsp.FMT_FLT, d_out.data_ptr(), out_cap, True)
+        return adapt.process_audio_adaptive_ptr(ctx, d_in.data_ptr(), n, RATE, 1, gpudsp.FMT_FLT, d_out.data_ptr(), out_cap, True)
 
     def step_e2e():
-        return ctx.process_audio_ptr(h_in.data_ptr(), n, RATE, 1, gpudsp.FMT_FLT, h_out.data_ptr(), out_cap, False)
+        return adapt.process_audio_adaptive_ptr(ctx, h_in.data_ptr(), n, RATE, 1, gpudsp.FMT_FLT, h_out.data_ptr(), out_cap, False)
 
     # ---- device-resident timing (value) -------------------------------------------------------
     ctx.enable_timing(True)                  # warm up in the configuration that is timed (event pools, caches)
     for _ in range(args.warmup):
-        res = step_dev()
+        res, an = step_dev()
     ctx.reset_counters()
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -250,7 +299,7 @@ def main():
         t0 = time.perf_counter()
         ev0.record(lib_stream)
         for _ in range(args.steps):
-            res = step_dev()
+            res, an = step_dev()
         ev1.record(lib_stream)
         torch.cuda.synchronize()
         barrier()
@@ -268,43 +317,29 @@ def main():
     t0 = time.perf_counter()
     ev0.record(lib_stream)
     for _ in range(args.steps):
-        res_e = step_e2e()
+        res_e, _ = step_e2e()
     ev1.record(lib_stream)
     barrier()
     t_e2e_wall = time.perf_counter() - t0
-    t_e2e = max(ev0.elapsed_time(ev1) * 1e-3, 0.0)
+    # the call returns after its device->host copy has landed, so the wall clock between the barriers IS the end-to-end time;
+    # the event pair on the library stream is reported next to it
+    t_e2e = max(t_e2e_wall, ev0.elapsed_time(ev1) * 1e-3)
 
-    # ---- the adaptive path on the library side (Pass 1 -> detector -> 17 band graphs -> AdaptConfig -> Pass 2..4), reported
-    #      next to the headline; Pass 2 cannot overlap Pass 1 here because its spec depends on Pass 1's measurements ----------
-    adaptive = None
-    if rank == 0 and not args.no_adaptive:
-        from jivetalking_b200 import adapt
-        # a conversational recipe (speech runs / room-tone pauses) so the detector elects both regions and every adaptive branch runs
-        # (one 10 min block tiled: generating it costs host seconds, not GPU work)
-        blk = make_input(4242, min(10, args.minutes), kind="podcast")
-        d_in.copy_(torch.from_numpy(np.tile(blk, (n + len(blk) - 1) // len(blk))[:n]))
+    extras = {}
+    if rank == 0 and not args.no_extras:
+        # ---- the caller-supplied-spec entry (DefaultFilterConfig spec): Pass 2 is enqueued before Pass 1 -------------------
         for _ in range(2):
-            adapt.process_audio_adaptive_ptr(ctx, d_in.data_ptr(), n, RATE, 1, gpudsp.FMT_FLT, d_out.data_ptr(), out_cap, True)
+            ctx.process_audio_ptr(d_in.data_ptr(), n, RATE, 1, gpudsp.FMT_FLT, d_out.data_ptr(), out_cap, True)
         torch.cuda.synchronize()
         ev0.record(lib_stream)
         for _ in range(args.steps):
-            res_a, an_a = adapt.process_audio_adaptive_ptr(ctx, d_in.data_ptr(), n, RATE, 1, gpudsp.FMT_FLT, d_out.data_ptr(), out_cap, True)
+            res_f = ctx.process_audio_ptr(d_in.data_ptr(), n, RATE, 1, gpudsp.FMT_FLT, d_out.data_ptr(), out_cap, True)
         ev1.record(lib_stream)
         torch.cuda.synchronize()
-        t_ad = ev0.elapsed_time(ev1) * 1e-3 / args.steps
-        va = an_a.voice_activity
-        adaptive = {"value": n / t_ad, "unit": "samples/s", "realtime_x": n / t_ad / RATE, "ms_per_step": 1e3 * t_ad,
-                    "entry": "jt_process_audio_adaptive_dev (ProcessAudio with AnalyseAudio + AdaptConfig + MeasureOutputRegions inside the library)",
-                    "input": f"{args.minutes} min conversational synthetic (synth.podcast_like, 10 min block tiled), device-resident",
-                    "regions_remeasured": int(an_a.filtered_regions.has_room_tone + an_a.filtered_regions.has_speech +
-                                              an_a.final_regions.has_room_tone + an_a.final_regions.has_speech),
-                    "pass2_spec": an_a.pass2_spec.decode(), "speech_profile": bool(va.has_speech_profile),
-                    "noise_profile": bool(va.has_noise_profile), "voice_activated": bool(va.voice_activated),
-                    "noise_floor": va.floor, "final_lufs": res_a.final.input_i, "final_dbtp": res_a.final.input_tp}
-    # ---- the result's container: FLAC stream of the s16 44.1 kHz output, device resident -------------------
-    flac = None
-    if rank == 0 and not args.no_adaptive:
-        res_f = step_dev()
+        t_fx = ev0.elapsed_time(ev1) * 1e-3 / args.steps
+        extras["fixed_spec"] = {"value": n / t_fx, "unit": "samples/s", "realtime_x": n / t_fx / RATE, "ms_per_step": 1e3 * t_fx,
+                                "entry": "jt_process_audio_dev with DefaultFilterConfig's spec (filters.go:353-355), same input"}
+        # ---- the result's container: FLAC stream of the s16 44.1 kHz output, device resident -------------------
         n_out = int(res_f.n_out)
         cap_b = int(gpudsp.lib().jt_flac_max_bytes(n_out, 4096))
         d_flac = torch.empty(cap_b, dtype=torch.uint8, device="cuda")
@@ -316,11 +351,23 @@ def main():
         ev1.record(lib_stream)
         torch.cuda.synchronize()
         t_fl = ev0.elapsed_time(ev1) * 1e-3 / args.steps
-        flac = {"ms_per_step": 1e3 * t_fl, "realtime_x": (n_out / 44100) / t_fl, "samples_per_s": n_out / t_fl,
-                "bytes": int(nbytes), "ratio": nbytes / (2.0 * n_out),
-                "algorithmic_GBps": (2.0 * n_out + nbytes) / t_fl / 1e9,
-                "entry": "jt_flac_encode_dev (4096-sample frames, fixed predictors + partitioned Rice; encoder.go:92-101)"}
+        extras["flac_encode"] = {"ms_per_step": 1e3 * t_fl, "realtime_x": (n_out / 44100) / t_fl, "samples_per_s": n_out / t_fl,
+                                 "bytes": int(nbytes), "ratio": nbytes / (2.0 * n_out), "algorithmic_GBps": (2.0 * n_out + nbytes) / t_fl / 1e9,
+                                 "entry": "jt_flac_encode_dev (4096-sample frames; encoder.go:92-101)"}
         del d_flac
+    barrier()
+    if world == 1 and not args.no_extras:
+        del d_in, d_out
+        torch.cuda.empty_cache()
+        extras["batch_sweep"] = batch_sweep(local, torch, gpudsp, adapt)
+        d_in = d_out = None
+    if world > 1 and not args.no_extras and hasattr(shard, "bench_stream_sharded"):
+        del d_in, d_out
+        torch.cuda.empty_cache()
+        sh = shard.bench_stream_sharded(ctx, local, rank, world, hours=args.sharded_hours)
+        if rank == 0 and sh is not None:
+            extras["stream_sharded"] = sh
+        d_in = d_out = None
     barrier()
 
     if world > 1:
@@ -336,6 +383,7 @@ def main():
     value = total_samples / t_dev
     e2e = total_samples / t_e2e
     peak, peak_src = measured_peaks()
+    traffic, traffic_src = ncu_traffic()
     timings.sort(key=lambda t: -t[1])
     gaps = [t for t in timings if t[0].startswith("gap:")]
     timings = [t for t in timings if not t[0].startswith("gap:")]
@@ -345,22 +393,25 @@ def main():
     dom_bytes = KERNEL_BYTES.get(dom[0].split(":")[0], 8.0) * n
     achieved = dom_bytes / (dom_ms_per_step * 1e-3) / 1e9 if dom_ms_per_step > 0 else 0.0
     kernel_ms = sum(t[1] for t in gpu_timings) / args.steps
+    va = an.voice_activity
     line = {
         "metric": "samples/s full 4-pass chain", "value": value, "unit": "samples/s", "realtime_x": value / RATE,
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
-        "config": {"workload": f"{args.minutes} min 48 kHz mono f32 per GPU, full 4-pass chain (BASELINE.json configs[1]; file per GPU = configs[2])",
-                   "samples_per_gpu": n, "pass2_spec": "DefaultFilterConfig (filters.go:353-355)",
+        "config": {"workload": f"ProcessAudio (adaptive), {args.minutes} min 48 kHz mono f32 conversational stream per GPU "
+                               "(BASELINE.json configs[1]; file per GPU = configs[2])",
+                   "entry": "jt_process_audio_adaptive[_dev]: Pass 1, detector, 17 band graphs, AdaptConfig, Pass 2, region re-measures, Pass 3, Pass 4, region re-measures",
+                   "samples_per_gpu": n, "pass2_spec": an.pass2_spec.decode(),
                    "l2": "inputs (691 MB/stream) and every intermediate exceed the 126 MB L2"},
         "e2e": {"value": e2e, "unit": "samples/s", "realtime_x": e2e / RATE, "h2d_bytes_per_step": int(n * 4),
                 "d2h_bytes_per_step": int(res_e.n_out * 2), "ms_per_step": 1e3 * t_e2e / args.steps},
         "gpu_launches": int(launches),
-        "timing": {"method": "CUDA events on the library stream around the K steps (max over ranks)",
+        "timing": {"method": "CUDA events on the library stream around the K steps (max over ranks); e2e: wall clock between barriers, the call returns after its D2H copy",
                    "wall_ms_per_step": 1e3 * t_wall / args.steps, "e2e_wall_ms_per_step": 1e3 * t_e2e_wall / args.steps},
         "roofline": {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak if peak else None,
-                     "traffic": NCU_TRAFFIC_BYTES_60MIN.get(dom[0]) if args.minutes == 60 else None,
-                     "traffic_source": "profiles/ncu_r1k.md / ncu_r1h.md (bytes per launch, ncu --set full)", "peak_source": peak_src,
+                     "traffic": traffic.get(dom[0]) if args.minutes == 60 else None,
+                     "traffic_source": traffic_src, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": dom_bytes,
                      "kernel_ms_per_step": dom_ms_per_step, "kernel_share_of_step": dom_ms_per_step / (1e3 * t_dev / args.steps),
                      "chain_frac": (BYTES_PER_SAMPLE_4PASS * n / (t_dev / args.steps) / 1e9) / peak,
@@ -371,18 +422,18 @@ def main():
         "device_idle_ms_total_per_step": sum(g[1] for g in gaps) / args.steps,
         "clocks": clocks.summary(),
         "result": {"final_lufs": res.final.input_i, "final_dbtp": res.final.input_tp, "final_lra": res.final.input_lra,
-                   "n_out": int(res.n_out), "limiter_needed": int(res.limiter_needed), "pass4_type": int(res.pass4.normalization_type)},
+                   "n_out": int(res.n_out), "limiter_needed": int(res.limiter_needed), "pass4_type": int(res.pass4.normalization_type),
+                   "speech_profile": bool(va.has_speech_profile), "noise_profile": bool(va.has_noise_profile),
+                   "voice_activated": bool(va.voice_activated), "noise_floor": va.floor,
+                   "regions_remeasured": int(an.filtered_regions.has_room_tone + an.filtered_regions.has_speech +
+                                             an.final_regions.has_room_tone + an.final_regions.has_speech)},
     }
-    if adaptive is not None:
-        line["adaptive"] = adaptive
-    if flac is not None:
-        line["flac_encode"] = flac
-    if not args.no_cpu_baseline:
+    line.update(extras)
+    if not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
-        sec = 150.0                           # ~20 s of scalar CPU work per core (the oracle chain runs ~8x realtime/core)
-        v, total, busy, wall = cpu_baseline(cores, sec)
+        v, total, busy = cpu_baseline(cores, CPU_SAMPLE_SECONDS)
         line["cpu_baseline"] = {"value": v, "unit": "samples/s", "realtime_x": v / RATE, "cores": cores, "kind": "port",
-                                "sample": f"{cores} x {sec:.0f} s streams of the same recipe, one scalar oracle chain per core "
+                                "sample": f"{cores} x {CPU_SAMPLE_SECONDS:.0f} s conversational streams, one scalar oracle ProcessAudio per core "
                                           f"({busy:.1f} s of CPU work per core)"}
     print(json.dumps(line))
     if world > 1:

@@ -424,6 +424,33 @@ int jt_process_audio_adaptive_dev(jt_ctx *ctx, const void *d_pcm_in, int64_t n_f
                         const jt_filter_config *base, int16_t *d_pcm_out, int64_t pcm_out_cap,
                         jt_process_result *res, jt_analysis *analysis);
 
+/* ---- the whole ProcessAudio of ONE stream over several GPUs behind one call per rank (configs[3]) ---------------
+ * jt_sharded_plan tells rank `rank` of `n_ranks` which frames of the stream it owns and which window [local_first, +n_local)
+ * it must decode (8 s of context on the left, 1 s on the right, all boundaries on `unit`).  Every rank then calls
+ * jt_process_audio_sharded with that window and an all-gather callback installed by jt_set_exchange(ctx, fn, user, n_ranks):
+ * Pass 1 -> merged measurements -> detector, band graphs, AdaptConfig (identical on every rank) -> Pass 2 (the owned part of
+ * the 44.1 kHz output stays on the GPU that made it) -> Pass 3 -> Pass 4, each pass one chunk per rank.  Only measurement
+ * blobs, the elected regions' samples and the HALO a neighbour lacks for Pass 3 / 4 cross ranks.  Each rank gets back the
+ * part of the result it owns: samples [*out_first, *out_first + *n_out) of the res->n_out samples of the whole output.
+ * adaptive = 0 runs DefaultFilterConfig's Pass-2 spec.  loudnorm's dynamic fall-back is not available chunked
+ * (JT_ERR_UNSUPPORTED).  The collective must be entered by every rank the same number of times: all ranks must pass the
+ * same stream description. */
+typedef struct jt_shard_plan { int64_t unit, own_first, owned, local_first, n_local; } jt_shard_plan;
+typedef struct jt_shard_timing {          /* host seconds per phase on this rank (device synchronised at each lap) */
+    double upload, pass1_chunk, pass1_merge, adapt, pass2_chunk, pass2_merge, regions, halo, pass3_chunk, pass3_merge,
+           pass4_chunk, pass4_merge, download, exchange /* inside the callback, all phases */;
+    int64_t halo_bytes; int32_t exchange_calls, reserved;
+} jt_shard_timing;
+int jt_sharded_plan(int64_t total_frames, int sample_rate, int n_ranks, int rank, jt_shard_plan *out);
+int jt_process_audio_sharded(jt_ctx *ctx, const void *pcm_local, int64_t n_local, int sample_rate, int channels, int sample_fmt,
+                             int64_t total_frames, int n_ranks, int rank, const jt_filter_config *base, int adaptive,
+                             int16_t *pcm_out, int64_t pcm_out_cap, int64_t *out_first, int64_t *n_out,
+                             jt_process_result *res, jt_analysis *analysis, jt_shard_timing *timing);
+int jt_process_audio_sharded_dev(jt_ctx *ctx, const void *d_pcm_local, int64_t n_local, int sample_rate, int channels, int sample_fmt,
+                             int64_t total_frames, int n_ranks, int rank, const jt_filter_config *base, int adaptive,
+                             int16_t *d_pcm_out, int64_t pcm_out_cap, int64_t *out_first, int64_t *n_out,
+                             jt_process_result *res, jt_analysis *analysis, jt_shard_timing *timing);
+
 /* RIFF / WAVE input (the reference's fixtures are s16 WAVs, testutil_test.go:140-190; it decodes through libavformat,
  * internal/audio/reader.go): locates the PCM of a file image in memory.  *sample_fmt is a JT_FMT_* value, the samples are
  * interleaved at bytes + *data_offset.  JT_ERR_UNSUPPORTED for 8 / 24 bit or compressed data and for RF64 / BW64 files.  A data

@@ -205,6 +205,11 @@ def _L():
     pa = [_P, _P, _I64, _INT, _INT, _INT, C.POINTER(FilterConfig), _P, _I64, C.POINTER(ProcessResult), C.POINTER(Analysis)]
     L.jt_process_audio_adaptive.argtypes = pa
     L.jt_process_audio_adaptive_dev.argtypes = pa
+    L.jt_sharded_plan.argtypes = [_I64, _INT, _INT, _INT, C.POINTER(ShardPlan)]
+    sh = [_P, _P, _I64, _INT, _INT, _INT, _I64, _INT, _INT, C.POINTER(FilterConfig), _INT, _P, _I64, C.POINTER(_I64), C.POINTER(_I64),
+          C.POINTER(ProcessResult), C.POINTER(Analysis), C.POINTER(ShardTiming)]
+    L.jt_process_audio_sharded.argtypes = sh
+    L.jt_process_audio_sharded_dev.argtypes = sh
     _bound = True
     return L
 
@@ -545,3 +550,55 @@ def process_audio_adaptive_ptr(ctx, in_ptr, n, rate, channels, fmt, out_ptr, out
     ctx._check(fn(ctx._h, _P(in_ptr), n, rate, channels, fmt, C.byref(base) if base is not None else None, _P(out_ptr), out_cap,
                   C.byref(res), C.byref(an)))
     return res, an
+
+
+# ---- ONE stream over several GPUs behind one call per rank (jt_process_audio_sharded, include/jtdsp.h) ------------------------
+class ShardPlan(C.Structure):
+    _fields_ = [("unit", _I64), ("own_first", _I64), ("owned", _I64), ("local_first", _I64), ("n_local", _I64)]
+
+
+class ShardTiming(C.Structure):
+    _fields_ = [(k, C.c_double) for k in ("upload", "pass1_chunk", "pass1_merge", "adapt", "pass2_chunk", "pass2_merge", "regions", "halo",
+                                           "pass3_chunk", "pass3_merge", "pass4_chunk", "pass4_merge", "download", "exchange")] + \
+               [("halo_bytes", _I64), ("exchange_calls", C.c_int32), ("reserved", C.c_int32)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+
+
+def sharded_plan(total_frames, rate, world, rank):
+    p = ShardPlan()
+    _check(_L().jt_sharded_plan(int(total_frames), int(rate), int(world), int(rank), C.byref(p)))
+    return p
+
+
+def process_audio_sharded(ctx, pcm_local, rate, channels, total_frames, world, rank, exchange=None, adaptive=True, base=None):
+    """One rank's call of jt_process_audio_sharded.  pcm_local: this rank's window (sharded_plan), interleaved numpy array;
+    exchange(send: bytes) -> bytes of all ranks in rank order (an all-gather).  Returns (owned int16 output, its first sample
+    index in the whole output, ProcessResult, Analysis, ShardTiming)."""
+    import numpy as np
+    pcm_local = np.ascontiguousarray(pcm_local)
+    n_local = pcm_local.size // channels
+    plan = sharded_plan(total_frames, rate, world, rank)
+    cap = int(plan.owned * 44100 / rate) + 4 * 4096 + 2 * 890820
+    out = np.empty(cap, dtype=np.int16)
+    res, an, tm = ProcessResult(), Analysis(), ShardTiming()
+    first, n_out = _I64(), _I64()
+    ctx.set_exchange(exchange, world)
+    try:
+        ctx._check(_L().jt_process_audio_sharded(ctx._h, pcm_local.ctypes.data_as(_P), n_local, rate, channels, gpudsp._FMT_OF_NP[pcm_local.dtype],
+                                                 int(total_frames), world, rank, C.byref(base) if base is not None else None, int(bool(adaptive)),
+                                                 out.ctypes.data_as(_P), cap, C.byref(first), C.byref(n_out), C.byref(res), C.byref(an), C.byref(tm)))
+    finally:
+        ctx.set_exchange(None, 1)
+    return out[:n_out.value], first.value, res, an, tm
+
+
+def process_audio_sharded_ptr(ctx, in_ptr, n_local, rate, channels, fmt, total_frames, world, rank, out_ptr, out_cap, on_device, adaptive=True, base=None):
+    """raw-pointer variant (bench: torch owns the pinned / device memory); the exchange must already be installed"""
+    res, an, tm = ProcessResult(), Analysis(), ShardTiming()
+    first, n_out = _I64(), _I64()
+    fn = _L().jt_process_audio_sharded_dev if on_device else _L().jt_process_audio_sharded
+    ctx._check(fn(ctx._h, _P(in_ptr), n_local, rate, channels, fmt, int(total_frames), world, rank, C.byref(base) if base is not None else None,
+                  int(bool(adaptive)), _P(out_ptr), out_cap, C.byref(first), C.byref(n_out), C.byref(res), C.byref(an), C.byref(tm)))
+    return first.value, n_out.value, res, an, tm

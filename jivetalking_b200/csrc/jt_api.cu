@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstring>
 #include <climits>
+#include <ctime>
 
 // ---------------------------------------------------------------------------------------
 // context
@@ -42,6 +43,7 @@ extern "C" int jt_create(int device, jt_ctx **out)
     jt_ctx *c = new jt_ctx();
     c->device = device; c->num_sms = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return JT_ERR_CUDA; }
+    if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaStreamDestroy(c->stream); delete c; return JT_ERR_CUDA; }
     *out = c;
     return JT_OK;
 }
@@ -59,6 +61,7 @@ extern "C" void jt_destroy(jt_ctx *c)
     for (auto &sl : c->slabs) cudaFree(sl.base);
     for (auto &b : c->pin_blocks) cudaFreeHost(b.first);
     for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
+    if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
     delete c;
 }
@@ -92,6 +95,8 @@ template <class F> static int guarded(jt_ctx *c, F body)
     catch (const std::bad_alloc &) { rc = JT_ERR_NOMEM; c->last_error = "host allocation failed"; }
     jt_release_all(c);
     cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (rc == JT_OK && e != cudaSuccess) { rc = JT_ERR_CUDA; c->last_error = cudaGetErrorString(e); }
+    e = cudaStreamSynchronize(c->copy_stream);
     if (rc == JT_OK && e != cudaSuccess) { rc = JT_ERR_CUDA; c->last_error = cudaGetErrorString(e); }
     cudaError_t e2 = cudaGetLastError();
     if (rc == JT_OK && e2 != cudaSuccess) { rc = JT_ERR_CUDA; c->last_error = cudaGetErrorString(e2); }
@@ -422,14 +427,16 @@ extern "C" int64_t jt_analyse_chunk_bytes(int64_t owned_frames, int rate)
     return (int64_t)sizeof(JtChunkHdr) + nt * (3 * 8 + 8 + JT_SP_COUNT * 4) + ns * 16 + (int64_t)jt_astats_host_bytes() + 64;
 }
 
-extern "C" int jt_analyse_chunk(jt_ctx *c, const void *pcm_local, int64_t n_local, int rate, int channels, int fmt,
-                                int64_t local_first, int64_t own_first, int64_t owned, int64_t total_frames,
-                                void *blob, int64_t blob_cap, int64_t *blob_bytes)
+// d_in: the local window on the DEVICE.  blob: resized to the chunk's mergeable values.  mono_out (optional): the downmixed
+// window in the link's format (what the band graphs of the adaptive path read).
+static void analyse_chunk_core(jt_ctx *c, const void *d_in, int64_t n_local, int rate, int channels, int fmt,
+                               int64_t local_first, int64_t own_first, int64_t owned, int64_t total_frames,
+                               std::vector<char> &blob_out, Sig *mono_out)
 {
-    return guarded(c, [&]() {
+    {
         const int F = 4096;
         const int64_t U = jt_analyse_chunk_unit(rate);
-        if (!pcm_local || !blob || U <= 0) JT_THROW(JT_ERR_INVALID_ARG, "null argument or unsupported rate");
+        if (!d_in || U <= 0) JT_THROW(JT_ERR_INVALID_ARG, "null argument or unsupported rate");
         if (!jt_valid_fmt(fmt)) JT_THROW(JT_ERR_UNSUPPORTED, "input sample format %d", fmt);
         if (own_first % U || local_first % U || local_first > own_first || own_first + owned > total_frames || owned <= 0 ||
             local_first + n_local < own_first + owned || local_first + n_local > total_frames)
@@ -441,7 +448,6 @@ extern "C" int jt_analyse_chunk(jt_ctx *c, const void *pcm_local, int64_t n_loca
         if (!last && local_first + n_local - (own_first + owned) < 4096) JT_THROW(JT_ERR_INVALID_ARG, "a chunk before the stream's end needs >= 4096 frames of right context");
         const int tick = rate / 10;
         const int64_t off = own_first - local_first;
-        const void *d_in = upload(c, pcm_local, (size_t)n_local * channels * jt_fmt_bytes(fmt));
         // a2: raw per-decoder-frame statistics of the owned frames
         const int64_t nsrc = (owned + F - 1) / F;
         double *d_ss = jt_dalloc<double>(c, nsrc), *d_pk = jt_dalloc<double>(c, nsrc);
@@ -454,6 +460,7 @@ extern "C" int jt_analyse_chunk(jt_ctx *c, const void *pcm_local, int64_t n_loca
         // astats sees the link's own format; aspectralstats converts to flt and ebur128 reads THAT link (s16 / flt widen
         // exactly, 32-bit integers are rounded to float first)
         const Sig mono_as = mono;
+        if (mono_out) *mono_out = mono_as;
         if (mono.fmt == JT_FMT_S32) mono = jt_convert(c, mono, JT_FMT_FLT);
         const int64_t as_upto = pass1_astats_upto(total_frames, tick, F);
         const int64_t as_n = std::max<int64_t>(0, std::min(own_first + owned, as_upto) - own_first);
@@ -476,9 +483,9 @@ extern "C" int jt_analyse_chunk(jt_ctx *c, const void *pcm_local, int64_t n_loca
         h.astats_bytes = (int64_t)jt_astats_host_bytes(); h.astats_n = ap.host ? as_n : 0; h.astats_upto = as_upto;
         if (!h.tc) h.tc = (int)std::fmax(0.05 * rate + .5, 1);
         const int64_t need = (int64_t)sizeof(h) + h.n_ticks * 24 + nsrc * 16 + n_sink * (8 + JT_SP_COUNT * 4) + h.astats_bytes;
-        if (need > blob_cap) JT_THROW(JT_ERR_BUFFER, "chunk blob needs %lld bytes", (long long)need);
         h.bytes = need;
-        char *w = (char *)blob;
+        blob_out.resize((size_t)need);
+        char *w = blob_out.data();
         memcpy(w, &h, sizeof(h)); w += sizeof(h);
         const int64_t lt0 = off / tick;                       // local index of the first owned tick
         if (h.n_ticks > 0 && lt0 + h.n_ticks > rp.nt) JT_THROW(JT_ERR_INVALID_ARG, "internal: local tick range");
@@ -494,9 +501,25 @@ extern "C" int jt_analyse_chunk(jt_ctx *c, const void *pcm_local, int64_t n_loca
             w += JT_SP_COUNT * 4;
         }
         if (ap.host) memcpy(w, ap.host, h.astats_bytes); else memset(w, 0, h.astats_bytes);
-        if (blob_bytes) *blob_bytes = need;
+    }
+}
+
+extern "C" int jt_analyse_chunk(jt_ctx *c, const void *pcm_local, int64_t n_local, int rate, int channels, int fmt,
+                                int64_t local_first, int64_t own_first, int64_t owned, int64_t total_frames,
+                                void *blob, int64_t blob_cap, int64_t *blob_bytes)
+{
+    return guarded(c, [&]() {
+        if (!pcm_local || !blob) JT_THROW(JT_ERR_INVALID_ARG, "null argument");
+        if (!jt_valid_fmt(fmt)) JT_THROW(JT_ERR_UNSUPPORTED, "input sample format %d", fmt);
+        const void *d_in = upload(c, pcm_local, (size_t)n_local * channels * jt_fmt_bytes(fmt));
+        std::vector<char> b;
+        analyse_chunk_core(c, d_in, n_local, rate, channels, fmt, local_first, own_first, owned, total_frames, b, nullptr);
+        if ((int64_t)b.size() > blob_cap) JT_THROW(JT_ERR_BUFFER, "chunk blob needs %lld bytes", (long long)b.size());
+        memcpy(blob, b.data(), b.size());
+        if (blob_bytes) *blob_bytes = (int64_t)b.size();
     });
 }
+
 
 extern "C" int jt_analyse_merge(int n_chunks, const void *const *blobs, jt_measurements *out, jt_interval *iv, int64_t iv_cap, int64_t *n_iv)
 {
@@ -525,6 +548,11 @@ extern "C" int jt_analyse_merge(int n_chunks, const void *const *blobs, jt_measu
         bool first_as = true;
         for (const JtChunkHdr *h : hs) {
             const char *r = (const char *)h + sizeof(JtChunkHdr);
+            // a truncated or corrupt all-gather payload must not drive a memcpy: every count non-negative and in range,
+            // and the sections must add up to the size the header declares
+            if (h->n_ticks < 0 || h->n_src < 0 || h->n_rows < 0 || h->tick0 < 0 || h->src0 < 0 || h->astats_bytes != (int64_t)as.size()) return JT_ERR_INVALID_ARG;
+            if (h->n_ticks > nt || h->n_src > nsrc || h->n_rows > n_hops + 2) return JT_ERR_INVALID_ARG;
+            if (h->bytes != (int64_t)sizeof(JtChunkHdr) + h->n_ticks * 24 + h->n_src * 16 + h->n_rows * (8 + JT_SP_COUNT * 4) + h->astats_bytes) return JT_ERR_INVALID_ARG;
             if (h->tick0 + h->n_ticks > nt || h->src0 + h->n_src > nsrc) return JT_ERR_INVALID_ARG;
             memcpy(&hp[h->tick0], r, 8 * h->n_ticks); r += 8 * h->n_ticks;
             memcpy(&hk[h->tick0], r, 8 * h->n_ticks); r += 8 * h->n_ticks;
@@ -638,13 +666,18 @@ extern "C" int64_t jt_graph_chunk_bytes(const char *spec, int64_t owned, int rat
     return (int64_t)sizeof(JtGraphChunkHdr) + nt * (3 * 8 + 2 * 8 + 2 * 8 + 8 + JT_SP_COUNT * 4) + (int64_t)jt_astats_host_bytes() + 256;
 }
 
-extern "C" int jt_graph_chunk(jt_ctx *c, const char *spec, const void *pcm_local, int64_t n_local, int rate, int channels, int fmt,
-                              int64_t local_first, int64_t own_first, int64_t owned, int64_t total, int frame_size,
-                              void *pcm_out, int64_t cap, int64_t *out_first, int64_t *n_out, int *out_rate, int *out_fmt,
-                              void *blob, int64_t blob_cap, int64_t *blob_bytes)
+// d_in: the local window on the DEVICE.  want_pcm: produce the sink audio; its owned part goes to pcm_out (host, `cap`
+// frames) and / or to *own_dev (a fresh device buffer of *n_out frames that outlives the chunk's temporaries -- the caller
+// releases it).  want_blob: fill blob_out with the chunk's mergeable measurement values.
+static void graph_chunk_core(jt_ctx *c, const char *spec, const void *d_in, int64_t n_local, int rate, int channels, int fmt,
+                             int64_t local_first, int64_t own_first, int64_t owned, int64_t total, int frame_size,
+                             bool want_pcm, void *pcm_out, int64_t cap, Sig *own_dev,
+                             int64_t *out_first, int64_t *n_out, int *out_rate, int *out_fmt,
+                             bool want_blob, std::vector<char> &blob_out)
 {
-    return guarded(c, [&]() {
-        if (!spec || !pcm_local) JT_THROW(JT_ERR_INVALID_ARG, "null spec or input");
+    {
+        void *blob = want_blob ? (void *)&blob_out : nullptr;      // non-null = measurement kernels run
+        if (!spec || !d_in) JT_THROW(JT_ERR_INVALID_ARG, "null spec or input");
         if (!jt_valid_fmt(fmt)) JT_THROW(JT_ERR_UNSUPPORTED, "input sample format %d", fmt);
         if (frame_size <= 0) frame_size = 4096;
         const ChunkGeometry G = chunk_geometry(spec, rate);
@@ -662,13 +695,12 @@ extern "C" int jt_graph_chunk(jt_ctx *c, const char *spec, const void *pcm_local
 
         // the whole stream's link sizes and sink-frame cadence (no device work)
         GraphRun gd;
-        jt_graph_build(c, spec, nullptr, total, rate, channels, fmt, frame_size, pcm_out != nullptr, true, JT_GRAPH_DRY, nullptr, gd);
+        jt_graph_build(c, spec, nullptr, total, rate, channels, fmt, frame_size, want_pcm, true, JT_GRAPH_DRY, nullptr, gd);
         // the audio filters on the local window
         GraphChunk ck; ck.local_first = local_first; ck.own_first = own_first; ck.owned = owned; ck.total = total; ck.rate = rate; ck.last = last;
         ck.exchange = c->exchange; ck.exchange_user = c->exchange_user; ck.n_ranks = c->exchange_ranks;
-        const void *d_in = upload(c, pcm_local, (size_t)n_local * channels * jt_fmt_bytes(fmt));
         GraphRun gl;
-        jt_graph_build(c, spec, d_in, n_local, rate, channels, fmt, frame_size, pcm_out != nullptr, false, JT_GRAPH_CHUNK, &ck, gl);
+        jt_graph_build(c, spec, d_in, n_local, rate, channels, fmt, frame_size, want_pcm, false, JT_GRAPH_CHUNK, &ck, gl);
 
         // positions of the window / the owned range on a link of rate r whose whole-stream length is n_link
         struct Range { int64_t loc0, a, b; };          // link position of the window's first sample; owned = [a, b)
@@ -758,26 +790,35 @@ extern "C" int jt_graph_chunk(jt_ctx *c, const char *spec, const void *pcm_local
             if (n_out) *n_out = h.out_n;
             if (out_rate) *out_rate = gd.out.rate;
             if (out_fmt) *out_fmt = gd.out.fmt;
-            if (pcm_out) {
-                if (h.out_n > cap) JT_THROW(JT_ERR_BUFFER, "pcm_out holds %lld frames, the chunk owns %lld", (long long)cap, (long long)h.out_n);
+            if (want_pcm && (pcm_out || own_dev)) {
+                if (pcm_out && h.out_n > cap) JT_THROW(JT_ERR_BUFFER, "pcm_out holds %lld frames, the chunk owns %lld", (long long)cap, (long long)h.out_n);
                 if (gl.out.fmt != gd.out.fmt || !gl.out.d) JT_THROW(JT_ERR_INVALID_ARG, "internal: sink format");
                 const size_t bs = jt_fmt_bytes(gl.out.fmt);
                 const int64_t s0 = R.a - R.loc0, have = std::max<int64_t>(0, std::min(h.out_n, gl.out.n - s0));
                 if (s0 < 0 || (!last && have < h.out_n)) JT_THROW(JT_ERR_INVALID_ARG, "internal: sink range (%lld of %lld)", (long long)have, (long long)h.out_n);
-                if (have) JT_CUDA(cudaMemcpyAsync(pcm_out, (const char *)gl.out.d + (size_t)s0 * bs, (size_t)have * bs, cudaMemcpyDeviceToHost, c->stream));
-                if (have < h.out_n) memset((char *)pcm_out + (size_t)have * bs, 0, (size_t)(h.out_n - have) * bs);     // asetnsamples padding
+                if (pcm_out) {
+                    if (have) JT_CUDA(cudaMemcpyAsync(pcm_out, (const char *)gl.out.d + (size_t)s0 * bs, (size_t)have * bs, cudaMemcpyDeviceToHost, c->stream));
+                    if (have < h.out_n) memset((char *)pcm_out + (size_t)have * bs, 0, (size_t)(h.out_n - have) * bs);     // asetnsamples padding
+                }
+                if (own_dev) {
+                    // the caller pre-allocated own_dev->d (so it survives the release of this chunk's temporaries)
+                    if (!own_dev->d || own_dev->n < h.out_n) JT_THROW(JT_ERR_INVALID_ARG, "internal: resident sink buffer");
+                    if (have) JT_CUDA(cudaMemcpyAsync(own_dev->d, (const char *)gl.out.d + (size_t)s0 * bs, (size_t)have * bs, cudaMemcpyDeviceToDevice, c->stream));
+                    if (have < h.out_n) JT_CUDA(cudaMemsetAsync((char *)own_dev->d + (size_t)have * bs, 0, (size_t)(h.out_n - have) * bs, c->stream));
+                    own_dev->n = h.out_n; own_dev->fmt = gl.out.fmt; own_dev->rate = gd.out.rate;
+                }
             }
         }
         // ---- wait, pack ----
         std::vector<float> rows; int64_t n_hops = 0;
         if (have_sp) jt_aspectralstats_finish(c, sp, rows, n_hops);
         JT_CUDA(cudaStreamSynchronize(c->stream));
-        if (!blob) { if (blob_bytes) *blob_bytes = 0; return; }
+        if (!blob) { blob_out.clear(); return; }
         h.n_rows = have_sp ? (int64_t)want_g.size() : 0;
         const int64_t need = (int64_t)sizeof(h) + h.r_nticks * 24 + h.n_rows * (8 + JT_SP_COUNT * 4) + h.astats_bytes + (h.li_nticks + h.lo_nticks) * 16;
-        if (need > blob_cap) JT_THROW(JT_ERR_BUFFER, "chunk blob needs %lld bytes", (long long)need);
         h.bytes = need;
-        char *w = (char *)blob;
+        blob_out.resize((size_t)need);
+        char *w = blob_out.data();
         memcpy(w, &h, sizeof(h)); w += sizeof(h);
         if (h.r_nticks > 0) {
             memcpy(w, rp.hp + r_loc_tick0, 8 * h.r_nticks); w += 8 * h.r_nticks;
@@ -803,9 +844,29 @@ extern "C" int jt_graph_chunk(jt_ctx *c, const char *spec, const void *pcm_local
             memcpy(w, tp.data(), 8 * h.li_nticks); w += 8 * h.li_nticks; memcpy(w, tk.data(), 8 * h.li_nticks); w += 8 * h.li_nticks;
         }
         if (h.lo_nticks > 0) { memcpy(w, lo.hp + lo_loc, 8 * h.lo_nticks); w += 8 * h.lo_nticks; memcpy(w, lo.hk + lo_loc, 8 * h.lo_nticks); w += 8 * h.lo_nticks; }
-        if (blob_bytes) *blob_bytes = need;
+    }
+}
+
+extern "C" int jt_graph_chunk(jt_ctx *c, const char *spec, const void *pcm_local, int64_t n_local, int rate, int channels, int fmt,
+                              int64_t local_first, int64_t own_first, int64_t owned, int64_t total, int frame_size,
+                              void *pcm_out, int64_t cap, int64_t *out_first, int64_t *n_out, int *out_rate, int *out_fmt,
+                              void *blob, int64_t blob_cap, int64_t *blob_bytes)
+{
+    return guarded(c, [&]() {
+        if (!spec || !pcm_local) JT_THROW(JT_ERR_INVALID_ARG, "null spec or input");
+        if (!jt_valid_fmt(fmt)) JT_THROW(JT_ERR_UNSUPPORTED, "input sample format %d", fmt);
+        const void *d_in = upload(c, pcm_local, (size_t)n_local * channels * jt_fmt_bytes(fmt));
+        std::vector<char> b;
+        graph_chunk_core(c, spec, d_in, n_local, rate, channels, fmt, local_first, own_first, owned, total, frame_size,
+                         pcm_out != nullptr, pcm_out, cap, nullptr, out_first, n_out, out_rate, out_fmt, blob != nullptr, b);
+        if (blob) {
+            if ((int64_t)b.size() > blob_cap) JT_THROW(JT_ERR_BUFFER, "chunk blob needs %lld bytes", (long long)b.size());
+            memcpy(blob, b.data(), b.size());
+        }
+        if (blob_bytes) *blob_bytes = (int64_t)b.size();
     });
 }
+
 
 extern "C" int jt_graph_merge(const char *spec, int64_t total, int rate, int channels, int fmt, int frame_size,
                               int n_chunks, const void *const *blobs, jt_frame_meta *meta, int64_t meta_cap, int64_t *n_meta,
@@ -844,6 +905,10 @@ extern "C" int jt_graph_merge(const char *spec, int64_t total, int rate, int cha
         for (const JtGraphChunkHdr *h : hs) {
             const char *r = (const char *)h + sizeof(JtGraphChunkHdr);
             if (h->r_nticks < 0 || h->r_tick0 < 0 || h->r_tick0 + h->r_nticks > nt) return JT_ERR_INVALID_ARG;
+            if (h->n_rows < 0 || h->n_rows > n_hops + 2 || h->li_nticks < 0 || h->lo_nticks < 0 || h->li_tick0 < 0 || h->lo_tick0 < 0 ||
+                h->astats_bytes != (int64_t)as.size()) return JT_ERR_INVALID_ARG;
+            if (h->bytes != (int64_t)sizeof(JtGraphChunkHdr) + h->r_nticks * 24 + h->n_rows * (8 + JT_SP_COUNT * 4) + h->astats_bytes +
+                            (h->li_nticks + h->lo_nticks) * 16) return JT_ERR_INVALID_ARG;
             if (h->r_nticks > 0) {
                 memcpy(&hp[h->r_tick0], r, 8 * h->r_nticks); r += 8 * h->r_nticks;
                 memcpy(&hk[h->r_tick0], r, 8 * h->r_nticks); r += 8 * h->r_nticks;
@@ -1025,14 +1090,22 @@ extern "C" int jt_build_pass4_spec(const jt_process_result *plan, const jt_loudn
 // ---------------------------------------------------------------------------------------
 static double go_seconds(int64_t ns) { return (double)(ns / 1000000000LL) + (double)(ns % 1000000000LL) / 1e9; }     // time.Duration.Seconds
 
+// sample_a / sample_b >= 0: the region as an explicit sample range of the buffer (a buffer that starts on the stream's
+// decoder-frame grid: the sharded path, which assembles a region from the ranks that own its parts)
 static void region_measure_device(jt_ctx *c, const void *d_pcm, int64_t n_frames, int rate, int channels, int fmt,
-                                  int64_t start_ns, int64_t dur_ns, jt_region_sample *out, int64_t *frames_out)
+                                  int64_t start_ns, int64_t dur_ns, jt_region_sample *out, int64_t *frames_out,
+                                  int64_t sample_a = -1, int64_t sample_b = -1)
 {
+    char spec[512];
+    if (sample_a >= 0) {
+        snprintf(spec, sizeof(spec), "atrim=start_sample=%lld:end_sample=%lld,asetpts=PTS-STARTPTS,astats=metadata=1:measure_perchannel=0,"
+                                     "aspectralstats=measure=all,ebur128=metadata=1:peak=sample+true", (long long)sample_a, (long long)sample_b);
+    } else {
     if (start_ns < 0) JT_THROW(JT_ERR_INVALID_ARG, "invalid region: negative start time");
     if (dur_ns <= 0) JT_THROW(JT_ERR_INVALID_ARG, "invalid region: non-positive duration");
-    char spec[512];
     snprintf(spec, sizeof(spec), "atrim=start=%f:duration=%f,asetpts=PTS-STARTPTS,astats=metadata=1:measure_perchannel=0,"
                                  "aspectralstats=measure=all,ebur128=metadata=1:peak=sample+true", go_seconds(start_ns), go_seconds(dur_ns));
+    }
     const size_t mark = c->allocs.size();
     GraphResult g;
     jt_graph_run(c, spec, d_pcm, n_frames, rate, channels, fmt, 4096, false, true, g);
@@ -1099,16 +1172,18 @@ static void measure_output_regions(jt_ctx *c, const void *d_pcm, int64_t n, cons
 // GPU is already working on the next pass: graphs are enqueued (jt_graph_enqueue) ahead of being finished.
 static void process_device(jt_ctx *c, const void *d_in, int64_t n_frames, int rate, int channels, int fmt, const char *pass2_spec,
                            int16_t *pcm_out, bool out_on_device, int64_t cap, jt_process_result *res,
-                           const jt_measurements *pass1_done = nullptr, const jt_filter_config *cfg = nullptr, jt_analysis *an = nullptr)
+                           const jt_measurements *pass1_done = nullptr, const jt_filter_config *cfg = nullptr, jt_analysis *an = nullptr,
+                           const GraphResume *head = nullptr, size_t head_mark = (size_t)-1)
 {
     jt_process_result R; memset(&R, 0, sizeof(R));
     // defaultLoudnormConfig, filters.go:523-532 (or the caller's base config on the adaptive path)
     const double tI = cfg ? cfg->loudnorm.target_i : -16.0, tTP = cfg ? cfg->loudnorm.target_tp : -1.0, tLRA = cfg ? cfg->loudnorm.target_lra : 20.0;
-    const size_t mark = c->allocs.size();
+    const size_t mark = head_mark != (size_t)-1 ? head_mark : c->allocs.size();
     // Pass 1 and Pass 2: device work.  Both read the input only (Pass 2's spec comes from the caller), so Pass 2's
     // long kernels go first and the integer bookkeeping of Pass 1's 200 000 frames happens behind them
+    // (adaptive path: the spec-independent head of Pass 2 is already running, `head` is the state behind it)
     GraphRun g2;
-    jt_graph_enqueue(c, pass2_spec ? pass2_spec : PASS2_DEFAULT_SPEC, d_in, n_frames, rate, channels, fmt, 4096, true, true, g2);
+    jt_graph_enqueue(c, pass2_spec ? pass2_spec : PASS2_DEFAULT_SPEC, d_in, n_frames, rate, channels, fmt, 4096, true, true, g2, head);
     if (g2.out.fmt != JT_FMT_S16 || g2.out.rate != 44100) JT_THROW(JT_ERR_SPEC, "Pass-2 spec must end in the s16/44.1 kHz output stage (processor.go:379-384)");
     jt_release_since(c, mark, g2.out.d);          // keep only the Pass-2 output ("the FLAC on disk")
     jt_check_cancel(c);
@@ -1165,7 +1240,12 @@ static void process_device(jt_ctx *c, const void *d_in, int64_t n_frames, int ra
     if (pcm_out) {                                 // the result leaves while the host assembles Pass 4's metadata
         if (g4.out.n > cap) JT_THROW(JT_ERR_BUFFER, "pcm_out holds %lld samples, chain produced %lld", (long long)cap, (long long)g4.out.n);
         const size_t ob = (size_t)g4.out.n * sizeof(int16_t);
-        if (ob) JT_CUDA(cudaMemcpyAsync(pcm_out, g4.out.d, ob, out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
+        // the copy engine takes the result as soon as its last sample exists (ev_out), while the compute stream goes on
+        // with Pass 4's analysis tail
+        if (ob && g4.out_ready) {
+            JT_CUDA(cudaStreamWaitEvent(c->copy_stream, g4.out_ready, 0));
+            JT_CUDA(cudaMemcpyAsync(pcm_out, g4.out.d, ob, out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->copy_stream));
+        } else if (ob) JT_CUDA(cudaMemcpyAsync(pcm_out, g4.out.d, ob, out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
     }
     {
         GraphResult r4;
@@ -1178,6 +1258,7 @@ static void process_device(jt_ctx *c, const void *d_in, int64_t n_frames, int ra
         measure_output_regions(c, g4.out.d, g4.out.n, an->voice_activity, &an->final_regions);
     }
     JT_CUDA(cudaStreamSynchronize(c->stream));
+    JT_CUDA(cudaStreamSynchronize(c->copy_stream));
     if (res) *res = R;
 }
 
@@ -1206,7 +1287,8 @@ extern "C" int jt_process_audio_dev(jt_ctx *c, const void *d_in, int64_t n_frame
 // so the two cannot overlap here as they do in process_device with a caller-supplied spec.
 // ---------------------------------------------------------------------------------------
 static void analyse_adaptive_device(jt_ctx *c, const void *d_in, int64_t n_frames, int rate, int channels, int fmt, int F,
-                                    const jt_filter_config *base, jt_analysis *out, jt_interval *iv_out, int64_t iv_cap, int64_t *n_iv_out)
+                                    const jt_filter_config *base, jt_analysis *out, jt_interval *iv_out, int64_t iv_cap, int64_t *n_iv_out,
+                                    AnalysePending *pending = nullptr /* Pass 1 already enqueued by the caller */)
 {
     if (!out) JT_THROW(JT_ERR_INVALID_ARG, "null analysis");
     memset(out, 0, sizeof(*out));
@@ -1215,7 +1297,8 @@ static void analyse_adaptive_device(jt_ctx *c, const void *d_in, int64_t n_frame
     jt_interval *iv = iv_out; int64_t cap = iv_cap;
     if (!iv) { cap = (int64_t)((double)n_frames / rate / 0.25) + 16; own.resize((size_t)cap); iv = own.data(); }
     int64_t n_iv = 0;
-    analyse_device(c, d_in, n_frames, rate, channels, fmt, F, &out->measurements, iv, cap, &n_iv);
+    if (pending) analyse_finish(c, *pending, &out->measurements, iv, cap, &n_iv);
+    else analyse_device(c, d_in, n_frames, rate, channels, fmt, F, &out->measurements, iv, cap, &n_iv);
     if (n_iv_out) *n_iv_out = n_iv;
     if (out->measurements.sink_frames == 0 || std::isnan(out->measurements.input_i))
         JT_THROW(JT_ERR_INVALID_ARG, "ebur128 measurements not found in metadata (analyser.go:397-399)");
@@ -1259,14 +1342,55 @@ extern "C" int jt_analyse_adaptive(jt_ctx *c, const void *pcm_in, int64_t n_fram
     });
 }
 
+// The filters of a Pass-2 spec that AdaptConfig never touches: everything before the first adaptive filter
+// (Pass2FilterOrder, filters.go:58-68: downmix, rumble high-pass, band-limit low-pass, anlmdn | afftdn, gate, compressor,
+// de-esser, analysis, resample).  Returns the head as a spec string ("" when there is none).
+static std::string pass2_static_head(const std::string &spec)
+{
+    std::vector<FilterNode> nodes = jt_parse_spec(spec);
+    size_t n = 0, pos = 0, end = 0;
+    for (; n < nodes.size(); n++) {
+        const std::string &nm = nodes[n].name;
+        if (!(nm == "aformat" || nm == "highpass" || nm == "lowpass" || nm == "anlmdn")) break;
+        if (nm == "aformat" && n > 0) break;                    // the output stage, not the downmix
+        // the node's text ends at the next top-level comma (none of these filters has escaped commas)
+        const size_t comma = spec.find(',', pos);
+        end = comma == std::string::npos ? spec.size() : comma;
+        pos = end + 1;
+    }
+    return n ? spec.substr(0, end) : std::string();
+}
+
 static void process_adaptive_device(jt_ctx *c, const void *d_in, int64_t n_frames, int rate, int channels, int fmt, const jt_filter_config *base,
                                     int16_t *pcm_out, bool out_on_device, int64_t cap, jt_process_result *res, jt_analysis *analysis)
 {
     std::vector<jt_analysis> own(analysis ? 0 : 1);
     jt_analysis *an = analysis ? analysis : own.data();
-    analyse_adaptive_device(c, d_in, n_frames, rate, channels, fmt, 4096, base, an, nullptr, 0, nullptr);
+    // Pass 1's kernels first; behind them, without waiting, the head of Pass 2 that no measurement can change (predicted
+    // from AdaptConfig on empty measurements and checked against the real spec below), so the GPU keeps working while
+    // the host assembles Pass 1's metadata, runs the detector and derives the spec's adaptive tail.
+    std::string head_spec;
+    {
+        jt_measurements m0; memset(&m0, 0, sizeof(m0));
+        jt_voice_activity va0; memset(&va0, 0, sizeof(va0));
+        jt_filter_config cfg0; char spec0[2048];
+        if (jt_adapt_config(base, &m0, &va0, &cfg0, nullptr) == JT_OK && jt_build_filter_spec(&cfg0, spec0, sizeof(spec0)) == JT_OK)
+            head_spec = pass2_static_head(spec0);
+    }
+    AnalysePending p1;
+    const size_t mark1 = c->allocs.size();
+    analyse_enqueue(c, d_in, n_frames, rate, channels, fmt, 4096, p1);
+    jt_release_since(c, mark1, nullptr);
+    const size_t head_mark = c->allocs.size();
+    GraphResume head; bool have_head = false;
+    if (!head_spec.empty()) { jt_graph_head(c, head_spec, d_in, n_frames, rate, channels, fmt, 4096, head); have_head = true; }
+    analyse_adaptive_device(c, d_in, n_frames, rate, channels, fmt, 4096, base, an, nullptr, 0, nullptr, &p1);
     jt_check_cancel(c);
-    process_device(c, d_in, n_frames, rate, channels, fmt, an->pass2_spec, pcm_out, out_on_device, cap, res, &an->measurements, &an->config, an);
+    const std::string spec = an->pass2_spec;
+    const bool match = have_head && spec.compare(0, head_spec.size(), head_spec) == 0 && (spec.size() == head_spec.size() || spec[head_spec.size()] == ',');
+    if (have_head && !match) jt_release_since(c, head_mark, nullptr);       // the prediction missed: Pass 2 runs from the input
+    process_device(c, d_in, n_frames, rate, channels, fmt, an->pass2_spec, pcm_out, out_on_device, cap, res, &an->measurements, &an->config, an,
+                   match ? &head : nullptr, match ? head_mark : (size_t)-1);
 }
 extern "C" int jt_process_audio_adaptive(jt_ctx *c, const void *pcm_in, int64_t n_frames, int rate, int channels, int fmt,
                                          const jt_filter_config *base, int16_t *pcm_out, int64_t cap, jt_process_result *res, jt_analysis *analysis)
@@ -1285,6 +1409,417 @@ extern "C" int jt_process_audio_adaptive_dev(jt_ctx *c, const void *d_in, int64_
         if (!d_in && n_frames > 0) JT_THROW(JT_ERR_INVALID_ARG, "null input");
         process_adaptive_device(c, d_in, n_frames, rate, channels, fmt, base, d_out, true, cap, res, analysis);
     });
+}
+
+// ---------------------------------------------------------------------------------------
+// ONE stream over several GPUs, orchestrated inside the library (BASELINE.json configs[3]): every rank calls
+// jt_process_audio_sharded with its window of the input and an all-gather callback (jt_set_exchange); the call runs
+// ProcessAudio (processor.go:78-216) with every pass cut into one chunk per rank.  What crosses ranks:
+//   - the mergeable measurement blobs of each measuring pass (a few MB per hour of audio), one all-gather each;
+//   - afftdn's noise-floor carry (32 bytes per rank), inside Pass 2;
+//   - the samples of the elected regions (<= 60 s of speech, <= 18 s of room tone) for the 17 band graphs and for the
+//     region re-measures of the Pass-2 / Pass-4 outputs: each rank contributes the part it owns;
+//   - the HALO of the Pass-2 output that a neighbour needs for Pass 3 / 4 (whose chunk grid at 44.1 kHz differs from
+//     Pass 2's): context + grid shift, tens of seconds -- never the stream.
+// The Pass-2 output stays resident on the rank that made it; each rank returns the part of the result it owns.
+// ---------------------------------------------------------------------------------------
+namespace {
+struct ShardComm {
+    jt_ctx *c; int rank, world; double seconds = 0; int calls = 0;
+    // all-gather of byte strings of any length, built on the fixed-size primitive: lengths first, then padded payloads
+    std::vector<std::vector<char>> allgather(const std::vector<char> &send)
+    {
+        std::vector<std::vector<char>> out((size_t)world);
+        if (world == 1 || !c->exchange) { out[0] = send; return out; }
+        const double t0 = host_seconds();
+        std::vector<int64_t> lens((size_t)world, 0);
+        const int64_t mine = (int64_t)send.size();
+        int rc = c->exchange(c->exchange_user, &mine, sizeof(int64_t), lens.data());
+        if (rc) JT_THROW(JT_ERR_INVALID_ARG, "exchange callback failed (%d)", rc);
+        int64_t cap = 0; for (int64_t l : lens) { if (l < 0 || l > ((int64_t)1 << 40)) JT_THROW(JT_ERR_INVALID_ARG, "exchange: bad length"); cap = std::max(cap, l); }
+        if (cap > 0) {
+            std::vector<char> sb((size_t)cap, 0), rb((size_t)cap * world);
+            if (mine) memcpy(sb.data(), send.data(), (size_t)mine);
+            rc = c->exchange(c->exchange_user, sb.data(), cap, rb.data());
+            if (rc) JT_THROW(JT_ERR_INVALID_ARG, "exchange callback failed (%d)", rc);
+            for (int r = 0; r < world; r++) out[(size_t)r].assign(rb.begin() + (size_t)r * cap, rb.begin() + (size_t)r * cap + lens[(size_t)r]);
+        }
+        seconds += host_seconds() - t0; calls += 2;
+        return out;
+    }
+    static double host_seconds() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
+};
+
+struct Chunks { std::vector<int64_t> first, owned; };
+static Chunks plan_chunks(int64_t total, int64_t unit, int world)
+{
+    Chunks ck; ck.first.resize((size_t)world); ck.owned.resize((size_t)world);
+    const int64_t units = std::max<int64_t>(1, (total + unit - 1) / unit), per = units / world, extra = units % world;
+    int64_t first = 0;
+    for (int r = 0; r < world; r++) {
+        const int64_t nu = per + (r < extra ? 1 : 0);
+        const int64_t own = std::min(nu * unit, std::max<int64_t>(total - first, 0));
+        ck.first[(size_t)r] = first; ck.owned[(size_t)r] = own; first += own;
+    }
+    return ck;
+}
+static int64_t sharded_unit(int rate)
+{
+    const int64_t u1 = jt_analyse_chunk_unit(rate), u2 = chunk_geometry(PASS2_DEFAULT_SPEC, rate).unit;
+    if (u1 <= 0 || u2 <= 0) JT_THROW(JT_ERR_UNSUPPORTED, "sharded processing at %d Hz", rate);
+    return lcm64(u1, u2);
+}
+// sample range of a region on a link, the way trim.c cuts it from "%f"-printed seconds (analyser_output.go:18, analyser_bands.go:54-60)
+static void region_range(int64_t start_ns, int64_t dur_ns, int rate, int64_t n_total, int64_t *a, int64_t *b)
+{
+    const double st = jt_wire("%f", go_seconds(start_ns)), du = jt_wire("%f", go_seconds(dur_ns));
+    const int64_t st_us = llround(st * 1e6), du_us = llround(du * 1e6);
+    const int64_t s0 = (st_us * rate + 500000) / 1000000, len = du_us > 0 ? (du_us * rate + 500000) / 1000000 : INT64_MAX / 4;
+    *a = std::min(std::max<int64_t>(s0, 0), n_total); *b = std::min(n_total, s0 + len);
+    if (*b < *a) *b = *a;
+}
+}   // namespace
+
+extern "C" int jt_sharded_plan(int64_t total_frames, int rate, int n_ranks, int rank, jt_shard_plan *out)
+{
+    if (!out || n_ranks <= 0 || rank < 0 || rank >= n_ranks || total_frames <= 0) return JT_ERR_INVALID_ARG;
+    try {
+        const int64_t U = sharded_unit(rate);
+        const Chunks ck = plan_chunks(total_frames, U, n_ranks);
+        const int64_t left = ((int64_t)8 * rate + U - 1) / U * U, right = ((int64_t)rate + U - 1) / U * U;
+        memset(out, 0, sizeof(*out));
+        out->unit = U; out->own_first = ck.first[(size_t)rank]; out->owned = ck.owned[(size_t)rank];
+        out->local_first = std::max<int64_t>(0, out->own_first - left);
+        out->n_local = out->owned > 0 ? std::min(total_frames, out->own_first + out->owned + right) - out->local_first : 0;
+    } catch (const JtError &e) { return e.code; }
+    return JT_OK;
+}
+
+static void process_sharded_device(jt_ctx *c, const void *d_local, int64_t n_local, int rate, int channels, int fmt,
+                                   int64_t total, int world, int rank, const jt_filter_config *base, int adaptive,
+                                   int16_t *pcm_out, bool out_on_device, int64_t cap, int64_t *out_first, int64_t *n_out,
+                                   jt_process_result *res, jt_analysis *analysis, jt_shard_timing *tm)
+{
+    if (world <= 0 || rank < 0 || rank >= world) JT_THROW(JT_ERR_INVALID_ARG, "bad rank / world");
+    if (world > 1 && (!c->exchange || c->exchange_ranks != world)) JT_THROW(JT_ERR_INVALID_ARG, "jt_set_exchange must provide an all-gather over %d ranks", world);
+    jt_shard_plan P;
+    int rc = jt_sharded_plan(total, rate, world, rank, &P);
+    if (rc) JT_THROW(rc, "sharded plan");
+    if (P.owned <= 0) JT_THROW(JT_ERR_INVALID_ARG, "the stream is too short for %d ranks (one unit of %lld frames per rank at least)", world, (long long)P.unit);
+    if (n_local != P.n_local) JT_THROW(JT_ERR_INVALID_ARG, "window of %lld frames, jt_sharded_plan asks for %lld", (long long)n_local, (long long)P.n_local);
+    ShardComm comm{c, rank, world};
+    jt_shard_timing T; memset(&T, 0, sizeof(T));
+    double t_prev = ShardComm::host_seconds();
+    auto lap = [&](double &slot) { JT_CUDA(cudaStreamSynchronize(c->stream)); const double t = ShardComm::host_seconds(); slot += t - t_prev; t_prev = t; };
+    std::vector<jt_analysis> own_an(analysis ? 0 : 1);
+    jt_analysis *an = analysis ? analysis : own_an.data();
+    memset(an, 0, sizeof(*an));
+    jt_process_result R; memset(&R, 0, sizeof(R));
+    const double tI = base ? base->loudnorm.target_i : -16.0, tTP = base ? base->loudnorm.target_tp : -1.0, tLRA = base ? base->loudnorm.target_lra : 20.0;
+    const Chunks ck1 = plan_chunks(total, P.unit, world);
+
+    // ---- Pass 1: chunk analysis, one all-gather, merge on every rank ----
+    std::vector<jt_interval> iv((size_t)((double)total / rate / 0.25) + 16);
+    int64_t n_iv = 0;
+    Sig mono;                                             // the downmixed window (device), kept for the band graphs
+    {
+        std::vector<char> blob;
+        analyse_chunk_core(c, d_local, n_local, rate, channels, fmt, P.local_first, P.own_first, P.owned, total, blob, &mono);
+        lap(T.pass1_chunk);
+        std::vector<std::vector<char>> all = comm.allgather(blob);
+        std::vector<const void *> ptrs; for (auto &b : all) if (!b.empty()) ptrs.push_back(b.data());
+        rc = jt_analyse_merge((int)ptrs.size(), ptrs.data(), &an->measurements, iv.data(), (int64_t)iv.size(), &n_iv);
+        if (rc) JT_THROW(rc, "Pass-1 merge");
+        R.input = an->measurements;
+        lap(T.pass1_merge);
+    }
+    // ---- detector, band graphs over the elected regions (their samples gathered from the ranks that own them), AdaptConfig ----
+    std::string spec2 = PASS2_DEFAULT_SPEC;
+    if (adaptive) {
+        if (an->measurements.sink_frames == 0 || std::isnan(an->measurements.input_i)) JT_THROW(JT_ERR_INVALID_ARG, "ebur128 measurements not found in metadata (analyser.go:397-399)");
+        rc = jt_detect_voice_activity(&an->measurements, iv.data(), n_iv, &an->voice_activity, nullptr, 0, nullptr, 0);
+        if (rc) JT_THROW(rc, "voice-activity detector");
+        jt_voice_activity &va = an->voice_activity;
+        const bool want_speech = va.has_speech_profile && va.speech_profile.region.duration_ns > 0;
+        const bool want_noise = va.has_noise_profile && va.noise_profile.duration_ns > 0;
+        if (want_speech || want_noise) {
+            int64_t ra[2] = {0, 0}, rb[2] = {0, 0};
+            if (want_speech) region_range(va.speech_profile.region.start_ns, va.speech_profile.region.duration_ns, rate, total, &ra[0], &rb[0]);
+            if (want_noise) region_range(va.noise_profile.start_ns, va.noise_profile.duration_ns, rate, total, &ra[1], &rb[1]);
+            const size_t bs = jt_fmt_bytes(mono.fmt);
+            // my part of each region: region ^ owned, taken from the downmixed window
+            std::vector<char> send;
+            for (int k = 0; k < 2; k++) {
+                const int64_t lo = std::max(ra[k], P.own_first), hi = std::min(rb[k], P.own_first + P.owned);
+                if (hi > lo) {
+                    const size_t off = send.size(); send.resize(off + (size_t)(hi - lo) * bs);
+                    JT_CUDA(cudaMemcpyAsync(send.data() + off, (const char *)mono.d + (size_t)(lo - P.local_first) * bs, (size_t)(hi - lo) * bs, cudaMemcpyDeviceToHost, c->stream));
+                }
+            }
+            JT_CUDA(cudaStreamSynchronize(c->stream));
+            std::vector<std::vector<char>> all = comm.allgather(send);
+            double lo_hz[17], hi_hz[17]; jt_band_plan(lo_hz, hi_hz);
+            double rms[17] = {0}; int32_t found[17] = {0};
+            std::vector<size_t> cursor((size_t)world, 0);
+            for (int k = 0; k < 2; k++) {
+                const int64_t len = rb[k] - ra[k];
+                if (len <= 0) continue;
+                std::vector<char> reg((size_t)len * bs);
+                for (int r = 0; r < world; r++) {
+                    const int64_t lo = std::max(ra[k], ck1.first[(size_t)r]), hi = std::min(rb[k], ck1.first[(size_t)r] + ck1.owned[(size_t)r]);
+                    if (hi > lo) {
+                        if (cursor[(size_t)r] + (size_t)(hi - lo) * bs > all[(size_t)r].size()) JT_THROW(JT_ERR_INVALID_ARG, "internal: region gather");
+                        memcpy(reg.data() + (size_t)(lo - ra[k]) * bs, all[(size_t)r].data() + cursor[(size_t)r], (size_t)(hi - lo) * bs);
+                        cursor[(size_t)r] += (size_t)(hi - lo) * bs;
+                    }
+                }
+                Sig rs; rs.fmt = mono.fmt; rs.rate = rate; rs.n = len; rs.d = upload(c, reg.data(), reg.size());
+                JT_CUDA(cudaStreamSynchronize(c->stream));             // `reg` is pageable host memory about to go out of scope
+                if (k == 0) jt_band_rms_batch(c, rs, lo_hz, hi_hz, 2, rms, found);
+                else jt_band_rms_batch(c, rs, lo_hz + 2, hi_hz + 2, 15, rms + 2, found + 2);
+            }
+            jt_apply_band_rms(&va, want_speech ? rms : nullptr, want_speech ? found : nullptr, want_noise ? rms + 2 : nullptr, want_noise ? found + 2 : nullptr);
+        }
+        rc = jt_adapt_config(base, &an->measurements, &va, &an->config, &an->diagnostics);
+        if (rc) JT_THROW(rc, "AdaptConfig");
+        rc = jt_build_filter_spec(&an->config, an->pass2_spec, sizeof(an->pass2_spec));
+        if (rc) JT_THROW(rc, "BuildFilterSpec");
+        spec2 = an->pass2_spec;
+    } else copy_str(PASS2_DEFAULT_SPEC, an->pass2_spec, sizeof(an->pass2_spec));
+    lap(T.adapt);
+
+    // the regions the reference re-measures on the Pass-2 and Pass-4 outputs (MeasureOutputRegions, analyser_output.go:261-297)
+    auto measure_regions = [&](const Sig &own, int64_t own_first44, const Chunks &ck44, int64_t n44, jt_output_regions *o) {
+        memset(o, 0, sizeof(*o));
+        if (!adaptive) return;
+        const jt_voice_activity &va = an->voice_activity;
+        int64_t a[2] = {0, 0}, b[2] = {0, 0}, g0[2] = {0, 0}; bool want[2] = {false, false};
+        int64_t s_ns[2] = {va.noise_profile.start_ns, va.speech_profile.region.start_ns}, d_ns[2] = {va.noise_profile.duration_ns, va.speech_profile.region.duration_ns};
+        want[0] = va.has_noise_profile && d_ns[0] > 0 && s_ns[0] >= 0; want[1] = va.has_speech_profile && d_ns[1] > 0 && s_ns[1] >= 0;
+        std::vector<char> send;
+        for (int k = 0; k < 2; k++) {
+            if (!want[k]) continue;
+            region_range(s_ns[k], d_ns[k], 44100, n44, &a[k], &b[k]);
+            g0[k] = a[k] / 4096 * 4096;                    // the decoder frame holding the region's first sample: same frame grid as the whole stream
+            const int64_t lo = std::max(g0[k], own_first44), hi = std::min(b[k], own_first44 + own.n);
+            if (hi > lo) {
+                const size_t off = send.size(); send.resize(off + (size_t)(hi - lo) * 2);
+                JT_CUDA(cudaMemcpyAsync(send.data() + off, (const char *)own.d + (size_t)(lo - own_first44) * 2, (size_t)(hi - lo) * 2, cudaMemcpyDeviceToHost, c->stream));
+            }
+        }
+        JT_CUDA(cudaStreamSynchronize(c->stream));
+        std::vector<std::vector<char>> all = comm.allgather(send);
+        std::vector<size_t> cursor((size_t)world, 0);
+        for (int k = 0; k < 2; k++) {
+            if (!want[k]) continue;
+            const int64_t len = b[k] - g0[k];
+            jt_region_sample *dst = k == 0 ? &o->room_tone : &o->speech;
+            if (b[k] - a[k] <= 0) continue;
+            std::vector<int16_t> reg((size_t)len);
+            for (int r = 0; r < world; r++) {
+                const int64_t lo = std::max(g0[k], ck44.first[(size_t)r]), hi = std::min(b[k], ck44.first[(size_t)r] + ck44.owned[(size_t)r]);
+                if (hi > lo) {
+                    if (cursor[(size_t)r] + (size_t)(hi - lo) * 2 > all[(size_t)r].size()) JT_THROW(JT_ERR_INVALID_ARG, "internal: region gather");
+                    memcpy(reg.data() + (lo - g0[k]), all[(size_t)r].data() + cursor[(size_t)r], (size_t)(hi - lo) * 2);
+                    cursor[(size_t)r] += (size_t)(hi - lo) * 2;
+                }
+            }
+            try {
+                const void *d_reg = upload(c, reg.data(), reg.size() * 2);
+                JT_CUDA(cudaStreamSynchronize(c->stream));
+                region_measure_device(c, d_reg, len, 44100, 1, JT_FMT_S16, 0, 0, dst, nullptr, a[k] - g0[k], b[k] - g0[k]);
+                if (k == 0) o->has_room_tone = 1; else o->has_speech = 1;
+            } catch (const JtError &e) { if (e.code == JT_ERR_CUDA || e.code == JT_ERR_CANCELLED) throw; }
+        }
+    };
+
+    // ---- Pass 2 on the window: the owned part of the 44.1 kHz output stays on this GPU ----
+    GraphRun gd2;
+    jt_graph_build(c, spec2, nullptr, total, rate, channels, fmt, 4096, true, true, JT_GRAPH_DRY, nullptr, gd2);
+    if (gd2.out.fmt != JT_FMT_S16 || gd2.out.rate != 44100) JT_THROW(JT_ERR_SPEC, "Pass-2 spec must end in the s16/44.1 kHz output stage (processor.go:379-384)");
+    const int64_t n44 = gd2.out.n;
+    Chunks ck2; ck2.first.resize((size_t)world); ck2.owned.resize((size_t)world);       // ownership of the Pass-2 output
+    for (int r = 0; r < world; r++) {
+        const int64_t f = (int64_t)((__int128)ck1.first[(size_t)r] * 44100 / rate);
+        const bool last = ck1.first[(size_t)r] + ck1.owned[(size_t)r] == total;
+        const int64_t e = last ? n44 : (int64_t)((__int128)(ck1.first[(size_t)r] + ck1.owned[(size_t)r]) * 44100 / rate);
+        ck2.first[(size_t)r] = f; ck2.owned[(size_t)r] = ck1.owned[(size_t)r] > 0 ? e - f : 0;
+    }
+    Sig own2; own2.fmt = JT_FMT_S16; own2.rate = 44100; own2.n = ck2.owned[(size_t)rank]; own2.d = jt_dalloc<int16_t>(c, (size_t)own2.n);
+    {
+        const size_t mark = c->allocs.size();
+        std::vector<char> blob; int64_t of = 0, on = 0; int orate = 0, ofmt = 0;
+        graph_chunk_core(c, spec2.c_str(), d_local, n_local, rate, channels, fmt, P.local_first, P.own_first, P.owned, total, 4096,
+                         true, nullptr, 0, &own2, &of, &on, &orate, &ofmt, true, blob);
+        if (of != ck2.first[(size_t)rank] || on != ck2.owned[(size_t)rank]) JT_THROW(JT_ERR_INVALID_ARG, "internal: Pass-2 ownership (%lld+%lld vs %lld+%lld)", (long long)of, (long long)on, (long long)ck2.first[(size_t)rank], (long long)ck2.owned[(size_t)rank]);
+        JT_CUDA(cudaStreamSynchronize(c->stream));
+        jt_release_since(c, mark, nullptr);
+        lap(T.pass2_chunk);
+        std::vector<std::vector<char>> all = comm.allgather(blob);
+        std::vector<const void *> ptrs; for (auto &b : all) if (!b.empty()) ptrs.push_back(b.data());
+        rc = jt_graph_merge(spec2.c_str(), total, rate, channels, fmt, 4096, (int)ptrs.size(), ptrs.data(), nullptr, 0, nullptr, nullptr, &R.filtered);
+        if (rc) JT_THROW(rc, "Pass-2 merge");
+        lap(T.pass2_merge);
+    }
+    measure_regions(own2, ck2.first[(size_t)rank], ck2, n44, &an->filtered_regions);
+    lap(T.regions);
+
+    // ---- Pass 3 / 4 run on their own chunk grid at 44.1 kHz: every rank fetches the halo it lacks ----
+    char spec3[1024], spec4[4096];
+    rc = jt_build_pass3_spec(R.filtered.input_i, R.filtered.input_tp, tI, tTP, tLRA, spec3, sizeof(spec3), &R);
+    if (rc) JT_THROW(rc, "pass-3 spec");
+    // Pass 4's grid (whole adeclick hops, resampler periods, ticks) is the coarser one and a multiple of Pass 3's
+    jt_process_result plan_probe = R; jt_loudnorm_stats p3_probe; memset(&p3_probe, 0, sizeof(p3_probe));
+    p3_probe.input_i = -20; p3_probe.input_tp = -6; p3_probe.input_lra = 5; p3_probe.input_thresh = -30;
+    rc = jt_build_pass4_spec(&plan_probe, &p3_probe, tI, tTP, tLRA, 44100, spec4, sizeof(spec4), nullptr, nullptr);
+    if (rc) JT_THROW(rc, "pass-4 spec");
+    const int64_t U34 = lcm64(chunk_geometry(spec3, 44100).unit, chunk_geometry(spec4, 44100).unit);
+    const Chunks ck4 = plan_chunks(n44, U34, world);
+    int64_t ctxL = 0, ctxR = 0;
+    { const int64_t l = (int64_t)8 * 44100, r = 44100; ctxL = (l + U34 - 1) / U34 * U34; ctxR = (r + U34 - 1) / U34 * U34; }
+    auto window_of = [&](int r, int64_t *lo, int64_t *hi) {
+        if (ck4.owned[(size_t)r] <= 0) { *lo = *hi = 0; return; }
+        *lo = std::max<int64_t>(0, ck4.first[(size_t)r] - ctxL); *hi = std::min(n44, ck4.first[(size_t)r] + ck4.owned[(size_t)r] + ctxR);
+    };
+    int64_t wlo = 0, whi = 0; window_of(rank, &wlo, &whi);
+    Sig win; win.fmt = JT_FMT_S16; win.rate = 44100; win.n = whi - wlo; win.d = jt_dalloc<int16_t>(c, (size_t)std::max<int64_t>(win.n, 1));
+    {
+        // piece(s -> d) = window(d) ^ owned2(s), for d != s, in rank order of d: every rank can compute every piece's extent
+        std::vector<char> send;
+        const int64_t mo = ck2.first[(size_t)rank], me = mo + ck2.owned[(size_t)rank];
+        for (int d = 0; d < world; d++) {
+            if (d == rank) continue;
+            int64_t lo, hi; window_of(d, &lo, &hi);
+            lo = std::max(lo, mo); hi = std::min(hi, me);
+            if (hi > lo) {
+                const size_t off = send.size(); send.resize(off + (size_t)(hi - lo) * 2);
+                JT_CUDA(cudaMemcpyAsync(send.data() + off, (const char *)own2.d + (size_t)(lo - mo) * 2, (size_t)(hi - lo) * 2, cudaMemcpyDeviceToHost, c->stream));
+            }
+        }
+        JT_CUDA(cudaStreamSynchronize(c->stream));
+        T.halo_bytes = (int64_t)send.size();
+        std::vector<std::vector<char>> all = comm.allgather(send);
+        for (int s = 0; s < world; s++) {
+            const int64_t so = ck2.first[(size_t)s], se = so + ck2.owned[(size_t)s];
+            if (s == rank) {
+                const int64_t lo = std::max(wlo, so), hi = std::min(whi, se);
+                if (hi > lo) JT_CUDA(cudaMemcpyAsync((char *)win.d + (size_t)(lo - wlo) * 2, (const char *)own2.d + (size_t)(lo - so) * 2, (size_t)(hi - lo) * 2, cudaMemcpyDeviceToDevice, c->stream));
+                continue;
+            }
+            size_t cur = 0;
+            for (int d = 0; d < world; d++) {
+                if (d == s) continue;
+                int64_t lo, hi; window_of(d, &lo, &hi);
+                lo = std::max(lo, so); hi = std::min(hi, se);
+                if (hi <= lo) continue;
+                if (d == rank) {
+                    if (cur + (size_t)(hi - lo) * 2 > all[(size_t)s].size()) JT_THROW(JT_ERR_INVALID_ARG, "internal: halo exchange");
+                    JT_CUDA(cudaMemcpyAsync((char *)win.d + (size_t)(lo - wlo) * 2, all[(size_t)s].data() + cur, (size_t)(hi - lo) * 2, cudaMemcpyHostToDevice, c->stream));
+                }
+                cur += (size_t)(hi - lo) * 2;
+            }
+        }
+        JT_CUDA(cudaStreamSynchronize(c->stream));
+        lap(T.halo);
+    }
+    const bool have4 = ck4.owned[(size_t)rank] > 0;
+    // ---- Pass 3 (measure only) ----
+    {
+        const size_t mark = c->allocs.size();
+        std::vector<char> blob;
+        if (have4) {
+            int64_t of = 0, on = 0; int orate = 0, ofmt = 0;
+            graph_chunk_core(c, spec3, win.d, win.n, 44100, 1, JT_FMT_S16, wlo, ck4.first[(size_t)rank], ck4.owned[(size_t)rank], n44, 4096,
+                             false, nullptr, 0, nullptr, &of, &on, &orate, &ofmt, true, blob);
+            JT_CUDA(cudaStreamSynchronize(c->stream));
+        }
+        jt_release_since(c, mark, nullptr);
+        lap(T.pass3_chunk);
+        std::vector<std::vector<char>> all = comm.allgather(blob);
+        std::vector<const void *> ptrs; for (auto &b : all) if (!b.empty()) ptrs.push_back(b.data());
+        rc = jt_graph_merge(spec3, n44, 44100, 1, JT_FMT_S16, 4096, (int)ptrs.size(), ptrs.data(), nullptr, 0, nullptr, &R.pass3, nullptr);
+        if (rc) JT_THROW(rc, "Pass-3 merge");
+        lap(T.pass3_merge);
+    }
+    const double mI = jt_wire("%.2f", R.pass3.input_i);
+    if (std::isinf(mI) || std::isnan(mI) || mI < -70.0) JT_THROW(JT_ERR_INVALID_ARG, "cannot normalise silent audio (measured %.1f LUFS)", mI);
+    double eff = 0, off = 0;
+    rc = jt_build_pass4_spec(&R, &R.pass3, tI, tTP, tLRA, 44100, spec4, sizeof(spec4), &eff, &off);
+    if (rc) JT_THROW(rc, "pass-4 spec");
+    R.effective_target_i = eff; R.linear_possible = eff == tI;
+    // ---- Pass 4 ----
+    GraphRun gd4;
+    jt_graph_build(c, spec4, nullptr, n44, 44100, 1, JT_FMT_S16, 4096, true, true, JT_GRAPH_DRY, nullptr, gd4);
+    const int64_t n_final = gd4.out.n;
+    Chunks ck5; ck5.first.resize((size_t)world); ck5.owned.resize((size_t)world);       // ownership of the final output (44.1 kHz in and out)
+    for (int r = 0; r < world; r++) {
+        const bool last = ck4.owned[(size_t)r] > 0 && ck4.first[(size_t)r] + ck4.owned[(size_t)r] == n44;
+        ck5.first[(size_t)r] = ck4.first[(size_t)r]; ck5.owned[(size_t)r] = ck4.owned[(size_t)r] > 0 ? (last ? n_final : ck4.first[(size_t)r] + ck4.owned[(size_t)r]) - ck4.first[(size_t)r] : 0;
+    }
+    Sig own4; own4.fmt = JT_FMT_S16; own4.rate = 44100; own4.n = ck5.owned[(size_t)rank]; own4.d = jt_dalloc<int16_t>(c, (size_t)std::max<int64_t>(own4.n, 1));
+    {
+        const size_t mark = c->allocs.size();
+        std::vector<char> blob;
+        if (have4) {
+            int64_t of = 0, on = 0; int orate = 0, ofmt = 0;
+            graph_chunk_core(c, spec4, win.d, win.n, 44100, 1, JT_FMT_S16, wlo, ck4.first[(size_t)rank], ck4.owned[(size_t)rank], n44, 4096,
+                             true, nullptr, 0, &own4, &of, &on, &orate, &ofmt, true, blob);
+            if (of != ck5.first[(size_t)rank] || on != ck5.owned[(size_t)rank]) JT_THROW(JT_ERR_INVALID_ARG, "internal: Pass-4 ownership");
+            JT_CUDA(cudaStreamSynchronize(c->stream));
+        }
+        jt_release_since(c, mark, nullptr);
+        lap(T.pass4_chunk);
+        std::vector<std::vector<char>> all = comm.allgather(blob);
+        std::vector<const void *> ptrs; for (auto &b : all) if (!b.empty()) ptrs.push_back(b.data());
+        rc = jt_graph_merge(spec4, n44, 44100, 1, JT_FMT_S16, 4096, (int)ptrs.size(), ptrs.data(), nullptr, 0, nullptr, &R.pass4, &R.final);
+        if (rc) JT_THROW(rc, "Pass-4 merge");
+        lap(T.pass4_merge);
+    }
+    measure_regions(own4, ck5.first[(size_t)rank], ck5, n_final, &an->final_regions);
+    lap(T.regions);
+    // ---- the owned part of the result ----
+    R.n_out = n_final;
+    if (out_first) *out_first = ck5.first[(size_t)rank];
+    if (n_out) *n_out = own4.n;
+    if (pcm_out && own4.n > 0) {
+        if (own4.n > cap) JT_THROW(JT_ERR_BUFFER, "pcm_out holds %lld samples, this rank owns %lld", (long long)cap, (long long)own4.n);
+        JT_CUDA(cudaMemcpyAsync(pcm_out, own4.d, (size_t)own4.n * 2, out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
+    }
+    lap(T.download);
+    T.exchange = comm.seconds; T.exchange_calls = comm.calls;
+    if (res) *res = R;
+    if (tm) *tm = T;
+}
+
+static int sharded_common(jt_ctx *c, const void *pcm_local, bool on_device, int64_t n_local, int rate, int channels, int fmt,
+                          int64_t total, int world, int rank, const jt_filter_config *base, int adaptive,
+                          int16_t *pcm_out, int64_t cap, int64_t *out_first, int64_t *n_out,
+                          jt_process_result *res, jt_analysis *analysis, jt_shard_timing *tm)
+{
+    return guarded(c, [&]() {
+        if (!pcm_local && n_local > 0) JT_THROW(JT_ERR_INVALID_ARG, "null input");
+        if (!jt_valid_fmt(fmt)) JT_THROW(JT_ERR_UNSUPPORTED, "input sample format %d", fmt);
+        const double t0 = ShardComm::host_seconds();
+        const void *d_in = on_device ? pcm_local : upload(c, pcm_local, (size_t)n_local * channels * jt_fmt_bytes(fmt));
+        JT_CUDA(cudaStreamSynchronize(c->stream));
+        const double t_up = ShardComm::host_seconds() - t0;
+        process_sharded_device(c, d_in, n_local, rate, channels, fmt, total, world, rank, base, adaptive, pcm_out, on_device, cap, out_first, n_out, res, analysis, tm);
+        if (tm) tm->upload = t_up;
+    });
+}
+extern "C" int jt_process_audio_sharded(jt_ctx *c, const void *pcm_local, int64_t n_local, int rate, int channels, int fmt,
+                                        int64_t total, int world, int rank, const jt_filter_config *base, int adaptive,
+                                        int16_t *pcm_out, int64_t cap, int64_t *out_first, int64_t *n_out,
+                                        jt_process_result *res, jt_analysis *analysis, jt_shard_timing *tm)
+{
+    return sharded_common(c, pcm_local, false, n_local, rate, channels, fmt, total, world, rank, base, adaptive, pcm_out, cap, out_first, n_out, res, analysis, tm);
+}
+extern "C" int jt_process_audio_sharded_dev(jt_ctx *c, const void *d_local, int64_t n_local, int rate, int channels, int fmt,
+                                        int64_t total, int world, int rank, const jt_filter_config *base, int adaptive,
+                                        int16_t *d_out, int64_t cap, int64_t *out_first, int64_t *n_out,
+                                        jt_process_result *res, jt_analysis *analysis, jt_shard_timing *tm)
+{
+    return sharded_common(c, d_local, true, n_local, rate, channels, fmt, total, world, rank, base, adaptive, d_out, cap, out_first, n_out, res, analysis, tm);
 }
 
 // ---------------------------------------------------------------------------------------

@@ -263,9 +263,19 @@ void jt_graph_run(jt_ctx *c, const std::string &spec, const void *d_in, int64_t 
 }
 
 void jt_graph_enqueue(jt_ctx *c, const std::string &spec, const void *d_in, int64_t n_frames, int rate, int channels,
-                      int fmt, int frame_size, bool want_pcm, bool want_meta, GraphRun &g)
+                      int fmt, int frame_size, bool want_pcm, bool want_meta, GraphRun &g, const GraphResume *resume)
 {
-    jt_graph_build(c, spec, d_in, n_frames, rate, channels, fmt, frame_size, want_pcm, want_meta, JT_GRAPH_NORMAL, nullptr, g);
+    jt_graph_build(c, spec, d_in, n_frames, rate, channels, fmt, frame_size, want_pcm, want_meta, JT_GRAPH_NORMAL, nullptr, g, resume);
+}
+
+// run the filters of `head_spec` and hand back the executor's state behind them (no analysis, no sink)
+void jt_graph_head(jt_ctx *c, const std::string &head_spec, const void *d_in, int64_t n_frames, int rate, int channels,
+                   int fmt, int frame_size, GraphResume &out)
+{
+    GraphRun g;
+    out = GraphResume();
+    out.head = head_spec;
+    jt_graph_build(c, head_spec, d_in, n_frames, rate, channels, fmt, frame_size, true, false, JT_GRAPH_NORMAL, nullptr, g, nullptr, &out);
 }
 
 // mono view of the source: what jt_downmix returns, without the device work (dry runs)
@@ -277,7 +287,8 @@ static Sig dry_mono(int64_t n_frames, int fmt, int rate) { Sig s; s.fmt = fmt; s
 //              were a stream of its own, the signals the analysis filters see are recorded (GraphRun::*_sig) and their
 //              kernels are left to the caller, who knows which part of the window is owned; no end-of-stream padding.
 void jt_graph_build(jt_ctx *c, const std::string &spec, const void *d_in, int64_t n_frames, int rate, int channels,
-                    int fmt, int frame_size, bool want_pcm, bool want_meta, int mode, const GraphChunk *chunk, GraphRun &g)
+                    int fmt, int frame_size, bool want_pcm, bool want_meta, int mode, const GraphChunk *chunk, GraphRun &g,
+                    const GraphResume *resume, GraphResume *capture)
 {
     if (n_frames < 0 || rate <= 0 || channels <= 0) JT_THROW(JT_ERR_INVALID_ARG, "bad stream description");
     if (frame_size <= 0) frame_size = 4096;
@@ -292,9 +303,15 @@ void jt_graph_build(jt_ctx *c, const std::string &spec, const void *d_in, int64_
     const void *raw = d_in;
     if (channels == 1) { E.cur = dry ? dry_mono(n_frames, fmt, rate) : jt_downmix(c, raw, n_frames, 1, fmt, rate); have_mono = true; }
     E.link_fmt = fmt;
-    E.frames = source_frames(n_frames, frame_size);
+    size_t first_node = 0;
+    if (resume) {
+        // the head of this spec already ran (jt_graph_head): continue from the state behind it
+        if (resume->n_nodes < 0 || (size_t)resume->n_nodes > nodes.size()) JT_THROW(JT_ERR_INVALID_ARG, "internal: graph resume");
+        E.cur = resume->cur; E.link_fmt = resume->link_fmt; E.frames = resume->frames; have_mono = true;
+        first_node = (size_t)resume->n_nodes;
+    } else E.frames = source_frames(n_frames, frame_size);
 
-    for (size_t ni = 0; ni < nodes.size(); ni++) {
+    for (size_t ni = first_node; ni < nodes.size(); ni++) {
         const FilterNode &f = nodes[ni];
         const bool last = ni + 1 == nodes.size();
         if (!dry) jt_check_cancel(c);
@@ -338,8 +355,13 @@ void jt_graph_build(jt_ctx *c, const std::string &spec, const void *d_in, int64_
             // libavfilter/trim.c: start_pts / duration_tb = av_rescale_q(usec, AV_TIME_BASE_Q, 1/rate), nearest
             const double st = f.num("start", "starti", 0.0), du = f.num("duration", "durationi", 0.0);
             const int64_t st_us = llround(st * 1e6), du_us = llround(du * 1e6);
-            const int64_t s0 = (st_us * E.cur.rate + 500000) / 1000000;
-            const int64_t len = du_us > 0 ? (du_us * E.cur.rate + 500000) / 1000000 : INT64_MAX / 4;
+            int64_t s0 = (st_us * E.cur.rate + 500000) / 1000000;
+            int64_t len = du_us > 0 ? (du_us * E.cur.rate + 500000) / 1000000 : INT64_MAX / 4;
+            if (f.get("start_sample") || f.get("end_sample")) {          // trim.c's sample-exact options
+                s0 = (int64_t)f.num("start_sample", "", 0);
+                const int64_t e1 = (int64_t)f.num("end_sample", "", (double)(INT64_MAX / 4));
+                len = std::max<int64_t>(e1 - s0, 0);
+            }
             const int64_t a = std::min(std::max<int64_t>(s0, 0), E.cur.n), b = std::min(E.cur.n, s0 + len);
             std::vector<FrameRef> nf;
             for (const FrameRef &fr : E.frames) {
@@ -535,7 +557,9 @@ void jt_graph_build(jt_ctx *c, const std::string &spec, const void *d_in, int64_
         }
     }
     if (!have_mono) JT_THROW(JT_ERR_UNSUPPORTED, "%d-channel graph without a mono downmix", channels);
+    if (capture) { capture->n_nodes = (int)nodes.size(); capture->cur = E.cur; capture->link_fmt = E.link_fmt; capture->frames = E.frames; return; }
     if (E.cur.d && want_pcm) E.materialise();
+    if (E.cur.d && want_pcm && mode == JT_GRAPH_NORMAL) g.out_ready = jt_record_event(c);     // the sink audio is complete; analysis kernels follow
     g.out = E.cur; g.out.fmt = E.cur.d ? E.cur.fmt : E.link_fmt;
     g.frames.swap(E.frames);
     g.has_astats = E.has_astats; g.has_spec = E.has_spec; g.has_r128 = E.has_r128; g.astats_overall_only = E.astats_overall_only;

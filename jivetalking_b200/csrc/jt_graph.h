@@ -42,6 +42,7 @@ struct GraphResult {
 struct GraphRun {
     std::vector<FrameRef> frames;
     Sig out; int out_fmt = 0;
+    cudaEvent_t out_ready = nullptr;      // recorded once the sink audio is complete (the analysis kernels come after it)
     bool want_meta = false;
     bool has_astats = false, has_spec = false, has_r128 = false, astats_overall_only = false;
     Sig astats_sig, spec_sig; int spec_win = 2048;
@@ -62,6 +63,11 @@ struct GraphRun {
 };
 
 enum { JT_GRAPH_NORMAL = 0, JT_GRAPH_DRY = 1, JT_GRAPH_CHUNK = 2 };
+// The executor's state after the first n_nodes filters of a spec: lets the spec-independent head of Pass 2 (downmix, both
+// biquads, anlmdn -- filters.go:58-68) run while the host still derives the adaptive tail of the spec from Pass 1.
+struct GraphResume { int n_nodes = 0; std::string head; Sig cur; int link_fmt = 0; std::vector<FrameRef> frames; };
+void jt_graph_head(jt_ctx *c, const std::string &head_spec, const void *d_in, int64_t n_frames, int rate, int channels,
+                   int fmt, int frame_size, GraphResume &out);
 // Where a local window sits in its stream (input-link sample indices) and how carries cross chunk boundaries
 struct GraphChunk {
     int64_t local_first = 0, own_first = 0, owned = 0, total = 0; int rate = 0; bool last = false;
@@ -70,11 +76,12 @@ struct GraphChunk {
     int64_t link_pos(int64_t pos, int link_rate) const { return (int64_t)((__int128)pos * link_rate / rate); }
 };
 void jt_graph_build(jt_ctx *c, const std::string &spec, const void *d_in, int64_t n_frames, int rate, int channels,
-                    int fmt, int frame_size, bool want_pcm, bool want_meta, int mode, const GraphChunk *chunk, GraphRun &g);
+                    int fmt, int frame_size, bool want_pcm, bool want_meta, int mode, const GraphChunk *chunk, GraphRun &g,
+                    const GraphResume *resume = nullptr, GraphResume *capture = nullptr);
 void jt_assemble_records(const std::vector<FrameRef> &frames, bool has_r128, const R128Result &r128, bool has_spec,
                          const std::vector<float> &spec_rows, int64_t spec_hops, GraphResult &res);
 void jt_graph_enqueue(jt_ctx *c, const std::string &spec, const void *d_in, int64_t n_frames, int rate, int channels,
-                      int fmt, int frame_size, bool want_pcm, bool want_meta, GraphRun &g);
+                      int fmt, int frame_size, bool want_pcm, bool want_meta, GraphRun &g, const GraphResume *resume = nullptr);
 const R128Result &jt_graph_r128_early(jt_ctx *c, GraphRun &g);     // waits for the ebur128 values only
 void jt_graph_finish(jt_ctx *c, GraphRun &g, GraphResult &res);
 

@@ -18,6 +18,7 @@ struct jt_ctx {
     int device = 0;
     int num_sms = JT_NSM_DEFAULT;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // device->host copy of a finished result while later analysis kernels still run
     std::string last_error;
     std::atomic<int> cancel{0};
     int64_t launches = 0;

@@ -141,12 +141,25 @@ cudaEvent_t jt_record_event(jt_ctx *c)
 
 void jt_release_since(jt_ctx *c, size_t mark, const void *keep)
 {
+    // `keep` may point INTO an allocation (a view of a buffer, a fused kernel's offset output): the allocation that
+    // contains it survives; a non-null keep that no allocation made since `mark` contains is a caller bug
     std::vector<void *> kept(c->allocs.begin(), c->allocs.begin() + std::min(mark, c->allocs.size()));
+    bool found = keep == nullptr;
     for (size_t i = mark; i < c->allocs.size(); i++) {
-        if (c->allocs[i] == keep) kept.push_back(c->allocs[i]);
-        else arena_release(c, c->allocs[i]);
+        void *p = c->allocs[i];
+        auto it = c->live.find(p);
+        const bool holds = keep && it != c->live.end() && (const char *)keep >= (const char *)p && (const char *)keep < (const char *)p + it->second;
+        if (holds) { kept.push_back(p); found = true; }
+        else arena_release(c, p);
     }
     c->allocs.swap(kept);
+    if (!found) {
+        for (void *p : c->allocs) {     // kept from before the mark: fine
+            auto it = c->live.find(p);
+            if (it != c->live.end() && (const char *)keep >= (const char *)p && (const char *)keep < (const char *)p + it->second) { found = true; break; }
+        }
+        if (!found) JT_THROW(JT_ERR_INVALID_ARG, "internal: jt_release_since would free the buffer that must survive");
+    }
 }
 
 void jt_check_cancel(jt_ctx *c)

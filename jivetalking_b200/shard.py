@@ -297,3 +297,158 @@ def process_stream_sharded_adaptive(ctx, comm, pcm, rate, channels=1, base=None,
                                        target_tp=cfg.loudnorm.target_tp, target_lra=cfg.loudnorm.target_lra, timings=timings)
     info.update(input=m, intervals=iv, voice_activity=va, config=cfg, diagnostics=diag)
     return out, info
+
+
+# ---- the whole ProcessAudio of one stream behind ONE call per rank (jt_process_audio_sharded) ----------------------------------
+class ThreadComm:
+    """All-gather between `world` threads of one process (tests on one GPU: every "rank" is a thread with its own jt_ctx)."""
+
+    def __init__(self, world):
+        import threading
+        self.world = world
+        self._slots = [b""] * world
+        self._bar = threading.Barrier(world)
+
+    def exchange_for(self, rank):
+        def fn(send):
+            self._slots[rank] = bytes(send)
+            self._bar.wait()
+            out = b"".join(self._slots)
+            self._bar.wait()
+            return out
+        return fn
+
+
+def process_stream_sharded_call(ctxs, pcm, rate, channels=1, adaptive=True, base=None):
+    """ONE stream, len(ctxs) ranks as threads of this process, each calling jt_process_audio_sharded with its window.
+    Returns (whole int16 output assembled from the owned parts, [per-rank (ProcessResult, Analysis, ShardTiming)])."""
+    import threading
+    import numpy as np
+    from . import adapt
+    world = len(ctxs)
+    total = pcm.size // channels
+    comm = ThreadComm(world)
+    results, errors = [None] * world, [None] * world
+
+    def work(r):
+        try:
+            p = adapt.sharded_plan(total, rate, world, r)
+            win = pcm.reshape(-1)[p.local_first * channels: (p.local_first + p.n_local) * channels]
+            results[r] = adapt.process_audio_sharded(ctxs[r], win, rate, channels, total, world, r, exchange=comm.exchange_for(r),
+                                                     adaptive=adaptive, base=base)
+        except Exception as e:          # noqa: BLE001  (a failing rank must not leave the others waiting at the barrier)
+            errors[r] = e
+            comm._bar.abort()
+
+    ts = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    for e in errors:
+        if e is not None and not isinstance(e, threading.BrokenBarrierError):
+            raise e
+    for e in errors:
+        if e is not None:
+            raise e
+    n_out = int(results[0][2].n_out)
+    out = np.zeros(n_out, dtype=np.int16)
+    for own, first, res, an, tm in results:
+        out[first: first + len(own)] = own
+    return out, [(r[2], r[3], r[4]) for r in results]
+
+
+def bench_stream_sharded(ctx, local, rank, world, hours=3.0, rate=96000, channels=2, reps=2, single_gpu=True):
+    """BASELINE.json configs[3] inside bench.py: ONE `hours` h 96 kHz stereo f32 conversational stream over the `world` GPUs
+    of the process group, one jt_process_audio_sharded call per rank.  Timed region (barrier + device synchronise on both
+    sides, max over ranks): from the rank's window in pinned HOST memory to its owned part of the result in pinned host
+    memory -- window upload, every chunk, every exchange (NCCL all-gathers of measurement blobs, region samples and halos),
+    every merge, result download.  Rank 0 then runs the same stream unchunked on its one GPU (jt_process_audio_adaptive, host
+    buffers) for the speed-up.  The stream is a 10 min block of the C2 recipe tiled (R = L delayed 7 samples x 0.9)."""
+    import time
+    import numpy as np
+    from . import adapt, gpudsp, synth
+    dev = torch.device("cuda", local)
+    total = int(hours * 3600 * rate)
+    seg = synth.stereo_from_mono(synth.podcast_like(600.0, rate, seed=12345)) if channels == 2 else synth.podcast_like(600.0, rate, seed=12345)
+    seg_frames = seg.size // channels
+
+    def window(first, n):
+        """frames [first, first + n) of the tiled stream, in pinned host memory"""
+        buf = torch.empty(n * channels, dtype=torch.float32, pin_memory=True)
+        a = buf.numpy()
+        pos = 0
+        while pos < n:
+            o = (first + pos) % seg_frames
+            m = min(seg_frames - o, n - pos)
+            a[pos * channels: (pos + m) * channels] = seg[o * channels: (o + m) * channels]
+            pos += m
+        return buf
+
+    p = adapt.sharded_plan(total, rate, world, rank)
+    h_in = window(p.local_first, p.n_local)
+    cap = int(p.owned * 44100 / rate) + 4 * 4096 + 2 * 890820
+    h_out = torch.empty(cap, dtype=torch.int16, pin_memory=True)
+    comm = DistComm(dev)
+    ctx.set_exchange(comm.exchange, world)
+    times, last = [], None
+    try:
+        for rep in range(reps + 1):                    # first repetition = warm-up
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            last = adapt.process_audio_sharded_ptr(ctx, h_in.data_ptr(), p.n_local, rate, channels, gpudsp.FMT_FLT, total, world, rank,
+                                                   h_out.data_ptr(), cap, False, adaptive=True)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            if rep > 0:
+                times.append(float(dt[0]))
+    finally:
+        ctx.set_exchange(None, 1)
+    first, n_out, res, an, tm = last
+    keys = [k for k, _ in adapt.ShardTiming._fields_ if k not in ("reserved", "halo_bytes", "exchange_calls")]
+    ph = torch.tensor([getattr(tm, k) for k in keys], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ph, op=dist.ReduceOp.MAX)
+    best = min(times)
+    single = None
+    if single_gpu:
+        del h_in
+        if rank == 0:
+            try:
+                whole = window(0, total)
+                out1 = torch.empty(int(total * 44100 / rate) + 3 * 4096, dtype=torch.int16, pin_memory=True)
+                ts = []
+                for rep in range(2):
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    r1, a1 = adapt.process_audio_adaptive_ptr(ctx, whole.data_ptr(), total, rate, channels, gpudsp.FMT_FLT, out1.data_ptr(), out1.numel(), False)
+                    torch.cuda.synchronize()
+                    ts.append(time.perf_counter() - t0)
+                single = {"seconds": min(ts), "final_lufs": r1.final.input_i, "final_dbtp": r1.final.input_tp,
+                          "spec_equal": bool(a1.pass2_spec == an.pass2_spec)}
+                del whole, out1
+            except Exception as e:          # noqa: BLE001  (host memory for an 8 GB pinned stream may not be there)
+                single = {"error": str(e)}
+        if world > 1:
+            dist.barrier()
+    if rank != 0:
+        return None
+    phases = {k: round(float(v), 4) for k, v in zip(keys, ph)}
+    limiter = max((k for k in phases if k != "exchange"), key=lambda k: phases[k])
+    out = {"workload": f"single {hours:g} h {rate} Hz {channels}-channel f32 conversational stream, one chunk per GPU per pass (BASELINE.json configs[3])",
+           "entry": "jt_process_audio_sharded (one call per rank, NCCL all-gather callback)", "n_gpus": world, "seconds_per_stream": best,
+           "all_seconds": times, "realtime_x": hours * 3600 / best, "frames_per_s": total / best,
+           "phase_seconds_max_over_ranks": phases, "slowest_phase": limiter, "halo_bytes_rank0": int(tm.halo_bytes), "exchange_calls": int(tm.exchange_calls),
+           "final_lufs": res.final.input_i, "final_dbtp": res.final.input_tp, "final_lra": res.final.input_lra, "n_out": int(res.n_out),
+           "pass2_spec": an.pass2_spec.decode()}
+    if single is not None:
+        out["single_gpu_unchunked"] = single
+        if "seconds" in single:
+            out["speedup_vs_single_gpu"] = single["seconds"] / best
+    return out

@@ -170,3 +170,42 @@ def test_dist_comm_exchange_and_gathers_two_ranks():
         assert got == b"\x01" * 32 + b"\x02" * 32                      # rank order
         assert pcm == [0, 1, 2, 100, 101, 102, 103, 104]                # ragged chunks, stream order
         assert blobs == [b"x" * 5, b"x" * 6]
+
+
+# ---- jt_process_audio_sharded's host side over gloo: the plan every rank derives and the all-gather callback contract ----------
+def _plan_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from jivetalking_b200 import adapt
+    total, rate = 37 * 60 * 96000 + 1234, 96000
+    p = adapt.sharded_plan(total, rate, world, rank)
+    comm = shard.DistComm(None)
+    # the exchange primitive jt_set_exchange expects: fixed-size records, every rank's in rank order (an all-gather)
+    rec = bytes([rank + 1]) * 24
+    got = comm.exchange(rec)
+    # variable-length payloads are built on it inside the library: lengths first, then padded payloads
+    lens = comm.exchange(int(p.owned).to_bytes(8, "little"))
+    dist.barrier()
+    out.put((rank, (p.unit, p.own_first, p.owned, p.local_first, p.n_local), got, lens, total))
+    dist.destroy_process_group()
+
+
+def test_sharded_plan_and_exchange_over_gloo():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_plan_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, p0, g0, l0, total), (_, p1, g1, l1, _) = res
+    assert g0 == g1 == bytes([1]) * 24 + bytes([2]) * 24 and l0 == l1
+    assert [int.from_bytes(l0[i * 8:(i + 1) * 8], "little") for i in range(2)] == [p0[2], p1[2]]
+    unit = p0[0]
+    assert p0[1] == 0 and p1[1] == p0[2] and p0[2] + p1[2] == total and p0[2] % unit == 0          # the chunks tile the stream on the unit
+    assert p1[3] % unit == 0 and p1[1] - p1[3] >= 8 * 96000 and p0[4] - p0[2] >= 96000             # 8 s of left context, 1 s of right
+    assert p0[3] == 0 and p1[3] + p1[4] == total
