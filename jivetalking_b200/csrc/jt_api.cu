@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstring>
 #include <climits>
+#include <memory>
 #include <ctime>
 
 // ---------------------------------------------------------------------------------------
@@ -44,6 +45,7 @@ extern "C" int jt_create(int device, jt_ctx **out)
     c->device = device; c->num_sms = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return JT_ERR_CUDA; }
     if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaStreamDestroy(c->stream); delete c; return JT_ERR_CUDA; }
+    if (cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaStreamDestroy(c->copy_stream); cudaStreamDestroy(c->stream); delete c; return JT_ERR_CUDA; }
     *out = c;
     return JT_OK;
 }
@@ -62,6 +64,7 @@ extern "C" void jt_destroy(jt_ctx *c)
     for (auto &b : c->pin_blocks) cudaFreeHost(b.first);
     for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    if (c->side_stream) { cudaStreamSynchronize(c->side_stream); cudaStreamDestroy(c->side_stream); }
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
     delete c;
 }
@@ -1288,7 +1291,8 @@ extern "C" int jt_process_audio_dev(jt_ctx *c, const void *d_in, int64_t n_frame
 // ---------------------------------------------------------------------------------------
 static void analyse_adaptive_device(jt_ctx *c, const void *d_in, int64_t n_frames, int rate, int channels, int fmt, int F,
                                     const jt_filter_config *base, jt_analysis *out, jt_interval *iv_out, int64_t iv_cap, int64_t *n_iv_out,
-                                    AnalysePending *pending = nullptr /* Pass 1 already enqueued by the caller */)
+                                    AnalysePending *pending = nullptr /* Pass 1 already enqueued by the caller */,
+                                    cudaEvent_t input_ready = nullptr /* with it: the band graphs run on the side stream */)
 {
     if (!out) JT_THROW(JT_ERR_INVALID_ARG, "null analysis");
     memset(out, 0, sizeof(*out));
@@ -1310,6 +1314,18 @@ static void analyse_adaptive_device(jt_ctx *c, const void *d_in, int64_t n_frame
     const bool want_speech = va.has_speech_profile && va.speech_profile.region.duration_ns > 0;
     const bool want_noise = va.has_noise_profile && va.noise_profile.duration_ns > 0;
     if (want_speech || want_noise) {
+        // The band graphs read the input only.  When Pass 2's head is already queued on the main stream they go to the side
+        // stream (ordered behind the input's upload by `input_ready`), so their result does not wait for anlmdn.
+        struct StreamSwap {
+            jt_ctx *c; cudaStream_t main;
+            StreamSwap(jt_ctx *ctx, cudaStream_t to) : c(ctx), main(ctx->stream) { c->stream = to; }
+            ~StreamSwap() { cudaStreamSynchronize(c->stream); c->stream = main; }      // everything issued on it is done before its buffers are released
+        };
+        std::unique_ptr<StreamSwap> swap;
+        if (input_ready && c->side_stream) {
+            JT_CUDA(cudaStreamWaitEvent(c->side_stream, input_ready, 0));
+            swap.reset(new StreamSwap(c, c->side_stream));
+        }
         Sig mono = jt_downmix(c, d_in, n_frames, channels, fmt, rate);
         auto region = [&](int64_t start_ns, int64_t dur_ns) {
             // atrim=start=%f:duration=%f (analyser_bands.go:54-60): seconds printed with six decimals
@@ -1322,6 +1338,7 @@ static void analyse_adaptive_device(jt_ctx *c, const void *d_in, int64_t n_frame
         double rms[17] = {0}; int32_t found[17] = {0};
         if (want_speech) { Sig r = region(va.speech_profile.region.start_ns, va.speech_profile.region.duration_ns); jt_band_rms_batch(c, r, lo, hi, 2, rms, found); }
         if (want_noise) { Sig r = region(va.noise_profile.start_ns, va.noise_profile.duration_ns); jt_band_rms_batch(c, r, lo + 2, hi + 2, 15, rms + 2, found + 2); }
+        swap.reset();
         jt_apply_band_rms(&va, want_speech ? rms : nullptr, want_speech ? found : nullptr, want_noise ? rms + 2 : nullptr, want_noise ? found + 2 : nullptr);
     }
     rc = jt_adapt_config(base, &out->measurements, &va, &out->config, &out->diagnostics);
@@ -1381,10 +1398,13 @@ static void process_adaptive_device(jt_ctx *c, const void *d_in, int64_t n_frame
     const size_t mark1 = c->allocs.size();
     analyse_enqueue(c, d_in, n_frames, rate, channels, fmt, 4096, p1);
     jt_release_since(c, mark1, nullptr);
+    // the side stream starts behind Pass 1's kernels: the input is in HBM by then, and every arena block Pass 1 has already
+    // given back (the arena hands blocks out again at once, relying on stream order) is no longer in use
+    cudaEvent_t input_ready = jt_record_event(c);
     const size_t head_mark = c->allocs.size();
     GraphResume head; bool have_head = false;
     if (!head_spec.empty()) { jt_graph_head(c, head_spec, d_in, n_frames, rate, channels, fmt, 4096, head); have_head = true; }
-    analyse_adaptive_device(c, d_in, n_frames, rate, channels, fmt, 4096, base, an, nullptr, 0, nullptr, &p1);
+    analyse_adaptive_device(c, d_in, n_frames, rate, channels, fmt, 4096, base, an, nullptr, 0, nullptr, &p1, have_head ? input_ready : nullptr);
     jt_check_cancel(c);
     const std::string spec = an->pass2_spec;
     const bool match = have_head && spec.compare(0, head_spec.size(), head_spec) == 0 && (spec.size() == head_spec.size() || spec[head_spec.size()] == ',');

@@ -19,6 +19,7 @@ struct jt_ctx {
     int num_sms = JT_NSM_DEFAULT;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;   // device->host copy of a finished result while later analysis kernels still run
+    cudaStream_t side_stream = nullptr;   // small input-only work (the 17 band graphs) that must not queue behind Pass 2's head
     std::string last_error;
     std::atomic<int> cancel{0};
     int64_t launches = 0;

@@ -35,19 +35,42 @@ __device__ __forceinline__ double dc_sample(const double *__restrict__ x, int64_
 }
 
 // ---- A: autocorrelation -------------------------------------------------------------------
+// r[l] = (1/W) sum_{j=l}^{W-1} s[j] s[j-l], j ascending (the scalar loop's order), for l = 0 .. order.  A thread owns FOUR
+// consecutive lags and walks j once: the operand s[j-l] of lag l at step j is the operand of lag l-1 at step j-1, so it
+// moves through a four-deep register window and every step costs two shared-memory loads (s[j], s[j-l0]) for four
+// multiply-adds -- the one-lag-per-thread version was bound by shared-memory bandwidth (two loads per multiply-add).
+// Leading products with a not-yet-valid operand are +-0.0 added to a sum that is still +0.0: bit-identical.
+#define DC_AC_G 4            // windows per CTA
+#define DC_AC_LT 4           // lags per thread
 __global__ void __launch_bounds__(64)
 k_dc_autocorr(const double *__restrict__ x, int64_t n, int64_t n_windows, DcConst K, double *__restrict__ r_out)
 {
-    extern __shared__ double s_in[];
-    for (int64_t w = blockIdx.x; w < n_windows; w += gridDim.x) {
+    extern __shared__ double s_in[];                    // DC_AC_G windows of W samples
+    const int tpw = (K.order + DC_AC_LT) / DC_AC_LT;      // threads per window: ceil((order + 1) / 4)
+    const int64_t groups = (n_windows + DC_AC_G - 1) / DC_AC_G;
+    for (int64_t grp = blockIdx.x; grp < groups; grp += gridDim.x) {
         __syncthreads();
-        for (int j = threadIdx.x; j < K.W; j += blockDim.x) s_in[j] = dc_sample(x, n, w, j, K);
+        for (int g = 0; g < DC_AC_G; g++) {
+            const int64_t w = grp * DC_AC_G + g;
+            if (w < n_windows) for (int j = threadIdx.x; j < K.W; j += blockDim.x) s_in[g * K.W + j] = dc_sample(x, n, w, j, K);
+        }
         __syncthreads();
-        const int l = threadIdx.x;
-        if (l <= K.order) {
-            double v = 0.0;
-            for (int j = l; j < K.W; j++) v = jdadd(v, jdmul(s_in[j], s_in[j - l]));
-            r_out[w * K.bw + l] = jdmul(v, 1. / K.W);
+        const int g = threadIdx.x / tpw, l0 = (threadIdx.x - g * tpw) * DC_AC_LT;
+        const int64_t w = grp * DC_AC_G + g;
+        if (g < DC_AC_G && w < n_windows) {
+            const double *sw = s_in + g * K.W;
+            double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+            double w1 = 0.0, w2 = 0.0, w3 = 0.0;         // s[j-l0-1], s[j-l0-2], s[j-l0-3] (zero before the window)
+            for (int j = l0; j < K.W; j++) {
+                const double sj = sw[j], w0 = sw[j - l0];
+                v0 = jdadd(v0, jdmul(sj, w0)); v1 = jdadd(v1, jdmul(sj, w1)); v2 = jdadd(v2, jdmul(sj, w2)); v3 = jdadd(v3, jdmul(sj, w3));
+                w3 = w2; w2 = w1; w1 = w0;
+            }
+            const double inv = 1. / K.W;
+            if (l0 + 0 <= K.order) r_out[w * K.bw + l0 + 0] = jdmul(v0, inv);
+            if (l0 + 1 <= K.order) r_out[w * K.bw + l0 + 1] = jdmul(v1, inv);
+            if (l0 + 2 <= K.order) r_out[w * K.bw + l0 + 2] = jdmul(v2, inv);
+            if (l0 + 3 <= K.order) r_out[w * K.bw + l0 + 3] = jdmul(v3, inv);
         }
     }
 }
@@ -82,13 +105,20 @@ k_dc_levinson(const double *__restrict__ r_in, int64_t n_windows, DcConst K, dou
 }
 
 // ---- C: detector, burst fusion, edge clearing -> click bitmap + count ------------------------
+// The interpolation's linear system is banded in click order; its band width is the largest number of later clicks within
+// `order` samples of any click.  Windows are binned by that width so that k_dc_interp can run each bin with a ring just
+// large enough (DC_CLASS_R): the narrow bins -- almost all windows -- fit three times as many warps on an SM.
+#define DC_NCLASS 4
+__host__ __device__ inline int dc_class_ring(int cl, int bw) { return cl == 0 ? 16 : cl == 1 ? 24 : cl == 2 ? 32 : bw; }
+
 __global__ void __launch_bounds__(256)
 k_dc_detect(const double *__restrict__ x, int64_t n, int64_t n_windows, DcConst K, const double *__restrict__ acoef,
-            const double *__restrict__ sigmae, unsigned *__restrict__ bits_out, int *__restrict__ count_out)
+            const double *__restrict__ sigmae, unsigned *__restrict__ bits_out, int *__restrict__ count_out,
+            int *__restrict__ class_count /* DC_NCLASS */, int *__restrict__ class_list /* DC_NCLASS x n_windows */)
 {
     extern __shared__ double s_in[];                 // W samples, then order+1 coefficients
     __shared__ unsigned s_bits[160], s_fill[160];
-    __shared__ int s_cnt;
+    __shared__ int s_cnt, s_maxc;
     double *kc = s_in + K.W;
     for (int64_t w = blockIdx.x; w < n_windows; w += gridDim.x) {
         __syncthreads();
@@ -100,18 +130,37 @@ k_dc_detect(const double *__restrict__ x, int64_t n, int64_t n_windows, DcConst 
         }
         for (int j = threadIdx.x; j < K.W; j += blockDim.x) s_in[j] = dc_sample(x, n, w, j, K);
         for (int j = threadIdx.x; j <= K.order; j += blockDim.x) kc[j] = acoef[w * K.bw + j];
-        if (threadIdx.x == 0) s_cnt = 0;
+        if (threadIdx.x == 0) { s_cnt = 0; s_maxc = 0; }
         __syncthreads();
         const double thr = jdmul(sigmae[2 * w], K.threshold);
-        for (int i0 = 0; i0 < K.nwords * 32; i0 += blockDim.x) {
-            const int i = i0 + threadIdx.x; bool cflag = false;
-            if (i < K.W) {
-                double d = 0.0;
-                if (i >= K.order) for (int j = 0; j <= K.order; j++) d = jdadd(d, jdmul(kc[j], s_in[i - j]));
-                cflag = fabs(d) > thr;
+        // prediction error d_i = sum_{j=0}^{order} k[j] s[i-j], j ascending.  A thread owns four consecutive samples: the
+        // operand s[i-j] moves through a four-deep register window, two shared-memory loads per four multiply-adds
+        for (int i0 = 0; i0 < K.nwords * 32; i0 += blockDim.x * 4) {
+            const int ib = i0 + threadIdx.x * 4;             // samples ib .. ib + 3
+            double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+            if (ib < K.W) {
+                auto S = [&](int q) { return (q >= 0 && q < K.W) ? s_in[q] : 0.0; };
+                double a1 = S(ib + 1), a2 = S(ib + 2), a3 = S(ib + 3);     // s[ib+1-j], s[ib+2-j], s[ib+3-j] at j = 0
+                for (int j = 0; j <= K.order; j++) {
+                    const double kj = kc[j], a0 = S(ib - j);
+                    d0 = jdadd(d0, jdmul(kj, a0)); d1 = jdadd(d1, jdmul(kj, a1)); d2 = jdadd(d2, jdmul(kj, a2)); d3 = jdadd(d3, jdmul(kj, a3));
+                    a3 = a2; a2 = a1; a1 = a0;
+                }
             }
-            const unsigned m = __ballot_sync(0xffffffffu, cflag);
-            if ((threadIdx.x & 31) == 0 && (i >> 5) < K.nwords) s_bits[i >> 5] = m;
+            unsigned nib = 0;
+            if (ib + 0 < K.W && ib + 0 >= K.order && fabs(d0) > thr) nib |= 1u;
+            if (ib + 1 < K.W && ib + 1 >= K.order && fabs(d1) > thr) nib |= 2u;
+            if (ib + 2 < K.W && ib + 2 >= K.order && fabs(d2) > thr) nib |= 4u;
+            if (ib + 3 < K.W && ib + 3 >= K.order && fabs(d3) > thr) nib |= 8u;
+            // a warp covers 128 samples = 4 words: lane q < 4 assembles word q from the nibbles of lanes 8q .. 8q + 7
+            unsigned word = 0;
+            const int lane = threadIdx.x & 31;
+            for (int m = 0; m < 8; m++) {
+                const unsigned nb = __shfl_sync(0xffffffffu, nib, ((lane & 3) << 3) + m);
+                word |= nb << (4 * m);
+            }
+            const int wd = ((i0 + (threadIdx.x & ~31) * 4) >> 5) + lane;
+            if (lane < 4 && wd < K.nwords) s_bits[wd] = word;
         }
         __syncthreads();
         // burst fusion: a gap between two consecutive original clicks at most `burst` apart is filled
@@ -133,23 +182,51 @@ k_dc_detect(const double *__restrict__ x, int64_t n, int64_t n_windows, DcConst 
             unsigned m = s_bits[wd] | s_fill[wd];
             for (int b = 0; b < 32; b++) { const int i = wd * 32 + b; if (i < K.order || i >= K.W - K.order) m &= ~(1u << b); }
             bits_out[w * K.nwords + wd] = m;
+            s_bits[wd] = m;                          // (each thread rewrites only the words it read above)
             if (m) atomicAdd(&s_cnt, __popc(m));
         }
         __syncthreads();
-        if (threadIdx.x == 0) count_out[w] = s_cnt;
+        // band width: for every click, the later clicks at most `order` samples away (order <= 63: three words at most)
+        for (int wd = threadIdx.x; wd < K.nwords; wd += blockDim.x) {
+            unsigned m = s_bits[wd]; int best = 0;
+            while (m) {
+                const int b = __ffs(m) - 1; m &= m - 1;
+                const int p0 = wd * 32 + b + 1, p1 = min(wd * 32 + b + K.order, K.W - 1);      // bits p0 .. p1
+                int cnt = 0;
+                for (int q = p0 >> 5; q <= (p1 >> 5) && q < K.nwords; q++) {
+                    unsigned v = s_bits[q];
+                    if (q == (p0 >> 5)) v &= 0xffffffffu << (p0 & 31);
+                    if (q == (p1 >> 5)) v &= 0xffffffffu >> (31 - (p1 & 31));
+                    cnt += __popc(v);
+                }
+                best = max(best, cnt);
+            }
+            if (best) atomicMax(&s_maxc, best);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            count_out[w] = s_cnt;
+            if (s_cnt > 0) {
+                int cl = 0;
+                while (cl < DC_NCLASS - 1 && s_maxc + 1 > dc_class_ring(cl, K.bw)) cl++;
+                class_list[(size_t)cl * n_windows + atomicAdd(&class_count[cl], 1)] = (int)w;
+            }
+        }
     }
 }
 
 // ---- E: interpolation ----------------------------------------------------------------------
-#define DC_WARPS 5          // 20.7 KB of ring per warp: two 5-warp CTAs fill an SM's 227 KB
+#define DC_WARPS 4          // warps per CTA; the ring of a warp is R x R doubles (R = the bin's band width + 1)
 __global__ void __launch_bounds__(DC_WARPS * 32)
-k_dc_interp(const double *__restrict__ x, double *__restrict__ y, int64_t n, int64_t n_windows, DcConst K,
+k_dc_interp(const double *__restrict__ x, double *__restrict__ y, int64_t n, int64_t n_windows, DcConst K, int R,
             const double *__restrict__ acoef, const unsigned *__restrict__ bits_in, const int *__restrict__ count_in,
+            const int *__restrict__ list, const int *__restrict__ list_count,
             double *__restrict__ scratch, size_t scratch_per_warp, int *__restrict__ next_window)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int order = K.order, bw = K.bw;                    // ring is bw x bw
+    const int order = K.order, bw = K.bw;                    // ring is R x R, R <= bw: rows k .. k + R - 1 of the band
+    const int n_list = *list_count;
     __shared__ unsigned char s_pa[2048], s_pb[2048];   // pair table (a, b), b <= a <= 63, ordered by a then b
     const int npairs_full = order * (order + 1) / 2;
     for (int p = threadIdx.x; p < npairs_full; p += blockDim.x) {
@@ -157,23 +234,24 @@ k_dc_interp(const double *__restrict__ x, double *__restrict__ y, int64_t n, int
         s_pa[p] = (unsigned char)a; s_pb[p] = (unsigned char)(p - a * (a - 1) / 2 + 1);
     }
     __syncthreads();
-    const size_t per_warp = ((size_t)bw * bw + 3 * (size_t)bw + (size_t)((K.nwords + 1) / 2)) * sizeof(double);
+    const size_t per_warp = ((size_t)R * R + 2 * (size_t)bw + (size_t)R + (size_t)((K.nwords + 1) / 2)) * sizeof(double);
     double *ring = (double *)(smem_raw + (size_t)warp * per_warp);
-    double *kc = ring + (size_t)bw * bw, *aux = kc + bw, *vring = aux + bw;     // vring: right-hand side / forward-substituted values of rows k .. k+order
-    unsigned *sbits = (unsigned *)(vring + bw);                                  // the window's click bitmap
+    double *kc = ring + (size_t)R * R, *aux = kc + bw, *vring = aux + bw;       // vring: right-hand side / forward-substituted values of rows k .. k+R-1
+    unsigned *sbits = (unsigned *)(vring + R);                                   // the window's click bitmap
     const int64_t gw = (int64_t)blockIdx.x * DC_WARPS + warp;
     double *S = scratch + (size_t)gw * scratch_per_warp;
-    // scratch layout: Lg[nmax][order], Dg[nmax], vec[nmax], outv[nmax], idx (as int)[nmax]
+    // scratch layout: Lg[nmax][R-1], Dg[nmax], vec[nmax], outv[nmax], idx (as int)[nmax]
     const size_t nmax = (size_t)K.W;
-    double *Lg = S, *yd = Lg + nmax * order, *vec = yd + nmax, *outv = vec + nmax;      // yd[i] = y_i / D_i
+    const int Ls = R - 1;                                                               // a column of the factor has at most R-1 entries
+    double *Lg = S, *yd = Lg + nmax * Ls, *vec = yd + nmax, *outv = vec + nmax;         // yd[i] = y_i / D_i
     int *idx = (int *)(outv + nmax), *am = idx + 2 * ((nmax + 1) / 2);
     // ring slot of matrix index k + a given rk = k % bw (a <= order < bw): no integer division in the inner loops
-#define WRAP(v) ((v) >= bw ? (v) - bw : (v))
-#define RINGS(r, cidx) ring[(size_t)(r) * bw + (cidx)]
+#define WRAP(v) ((v) >= R ? (v) - R : (v))
+#define RINGS(r, cidx) ring[(size_t)(r) * R + (cidx)]
 
     for (;;) {
         int64_t w = 0;
-        if (lane == 0) w = atomicAdd(next_window, 1);
+        if (lane == 0) { const int t = atomicAdd(next_window, 1); w = t < n_list ? list[t] : n_windows; }
         w = __shfl_sync(0xffffffffu, w, 0);
         if (w >= n_windows) break;
         const int nclk = count_in[w];
@@ -230,15 +308,15 @@ k_dc_interp(const double *__restrict__ x, double *__restrict__ y, int64_t n, int
         auto load_row = [&](int j, int rj) {
             if (j >= nclk) return;
             const int ij = idx[j];
-            for (int t0 = 0; t0 < bw; t0 += 32) {
+            for (int t0 = 0; t0 < R; t0 += 32) {
                 const int t = t0 + lane, i = j - t;
-                const int d = (t < bw && i >= 0) ? ij - idx[i] : order + 1;
-                if (d <= order) RINGS(rj, WRAP(rj + bw - t)) = aux[d];
+                const int d = (t < R && i >= 0) ? ij - idx[i] : order + 1;
+                if (d <= order) RINGS(rj, WRAP(rj + R - t)) = aux[d];
                 if (!__ballot_sync(0xffffffffu, d <= order && lane == 31)) break;      // sorted: nothing further couples
             }
         };
-        for (int j = 0; j <= order; j++) load_row(j, j);
-        for (int j = lane; j <= order && j < nclk; j += 32) vring[j] = vec[j];
+        for (int j = 0; j < R; j++) load_row(j, j);
+        for (int j = lane; j < R && j < nclk; j += 32) vring[j] = vec[j];
         __syncwarp();
         bool ok = true;
         int rk = 0;
@@ -255,13 +333,13 @@ k_dc_interp(const double *__restrict__ x, double *__restrict__ y, int64_t n, int
                 amax = __popc(__ballot_sync(0xffffffffu, c0)) + __popc(__ballot_sync(0xffffffffu, c1));
             }
             const double yk = vring[rk];
-            const double v_in = (lane == 0 && k + bw < nclk) ? vec[k + bw] : 0.0;      // right-hand side of the row entering below: fetched early
+            const double v_in = (lane == 0 && k + R < nclk) ? vec[k + R] : 0.0;        // right-hand side of the row entering below: fetched early
             // column k: L(j,k) = A'(j,k) / D_k ; forward substitution v_j -= L(j,k) * y_k
             for (int a = lane + 1; a <= amax; a += 32) {
                 const int ra = WRAP(rk + a);
                 const double L = RINGS(ra, rk) / Dk;
                 RINGS(ra, rk) = L;
-                Lg[(size_t)k * order + (a - 1)] = L;
+                Lg[(size_t)k * Ls + (a - 1)] = L;
                 vring[ra] = jdsub(vring[ra], jdmul(L, yk));
             }
             if (lane == 0) { yd[k] = yk; outv[k] = Dk; am[k] = amax; }      // y_k / D_k is formed after the loop, off the critical path
@@ -273,10 +351,10 @@ k_dc_interp(const double *__restrict__ x, double *__restrict__ y, int64_t n, int
                 const double Lb = RINGS(rb, rk), La = RINGS(ra, rk);
                 RINGS(ra, rb) = jdsub(RINGS(ra, rb), jdmul(jdmul(Dk, Lb), La));
             }
-            load_row(k + bw, rk);           // row k+order+1 takes the slot row k leaves (no trailing update touches it)
-            if (lane == 0 && k + bw < nclk) vring[rk] = v_in;
+            load_row(k + R, rk);            // row k+R takes the slot row k leaves (no trailing update touches it)
+            if (lane == 0 && k + R < nclk) vring[rk] = v_in;
             __syncwarp();
-            rk = rk + 1 == bw ? 0 : rk + 1;
+            rk = rk + 1 == R ? 0 : rk + 1;
         }
         if (!ok) continue;                  // factorisation hit a zero pivot: af_adeclick.c leaves the window as is
         __syncwarp();
@@ -288,15 +366,15 @@ k_dc_interp(const double *__restrict__ x, double *__restrict__ y, int64_t n, int
             double win0 = 0.0, win1 = 0.0;
             int amax = am[nclk - 1];
             double o_y = yd[nclk - 1];
-            double L0 = lane < amax ? Lg[(size_t)(nclk - 1) * order + lane] : 0.0;
-            double L1 = lane + 32 < amax ? Lg[(size_t)(nclk - 1) * order + lane + 32] : 0.0;
+            double L0 = lane < amax ? Lg[(size_t)(nclk - 1) * Ls + lane] : 0.0;
+            double L1 = lane + 32 < amax ? Lg[(size_t)(nclk - 1) * Ls + lane + 32] : 0.0;
             for (int i = nclk - 1; i >= 0; i--) {
                 // next row's operands are fetched before this row's dependent chain starts
                 int amax_n = 0; double oy_n = 0.0, L0n = 0.0, L1n = 0.0;
                 if (i > 0) {
                     amax_n = am[i - 1]; oy_n = yd[i - 1];
-                    if (lane < amax_n) L0n = Lg[(size_t)(i - 1) * order + lane];
-                    if (lane + 32 < amax_n) L1n = Lg[(size_t)(i - 1) * order + lane + 32];
+                    if (lane < amax_n) L0n = Lg[(size_t)(i - 1) * Ls + lane];
+                    if (lane + 32 < amax_n) L1n = Lg[(size_t)(i - 1) * Ls + lane + 32];
                 }
                 const double prod0 = jdmul(L0, win0), prod1 = jdmul(L1, win1);
                 double o = o_y;
@@ -342,31 +420,40 @@ Sig jt_adeclick(jt_ctx *c, const Sig &in, double w_ms, double overlap_pct, doubl
     const int64_t nw = (in.n + K.hop - 1) / K.hop;
     double *d_r = jt_dalloc<double>(c, (size_t)nw * K.bw), *d_a = jt_dalloc<double>(c, (size_t)nw * K.bw), *d_sig = jt_dalloc<double>(c, (size_t)nw * 2);
     unsigned *d_bits = jt_dalloc<unsigned>(c, (size_t)nw * K.nwords);
-    int *d_cnt = jt_dalloc<int>(c, nw + 1);
-    int *d_next = d_cnt + nw;
-    JT_CUDA(cudaMemsetAsync(d_next, 0, sizeof(int), c->stream));
+    int *d_cnt = jt_dalloc<int>(c, nw + 2 * DC_NCLASS);
+    int *d_class_count = d_cnt + nw, *d_next = d_class_count + DC_NCLASS;
+    int *d_class_list = jt_dalloc<int>(c, (size_t)DC_NCLASS * nw);
+    JT_CUDA(cudaMemsetAsync(d_class_count, 0, 2 * DC_NCLASS * sizeof(int), c->stream));
     // the windows pass through except where clicks are repaired: out = in, then E overwrites
     JT_CUDA(cudaMemcpyAsync(o.d, in.d, sizeof(double) * (size_t)in.n, cudaMemcpyDeviceToDevice, c->stream));
-    const size_t smemA = sizeof(double) * K.W, smemC = sizeof(double) * (K.W + K.bw);
+    const size_t smemA = sizeof(double) * K.W * DC_AC_G, smemC = sizeof(double) * (K.W + K.bw);
+    if (DC_AC_G * ((K.order + DC_AC_LT) / DC_AC_LT) > 64) JT_THROW(JT_ERR_UNSUPPORTED, "adeclick AR order %d", K.order);
     jt_smem_optin((const void *)k_dc_autocorr, (size_t)(smemA));
     jt_smem_optin((const void *)k_dc_detect, (size_t)(smemC));
-    const size_t per_warp = ((size_t)K.bw * K.bw + 3 * (size_t)K.bw + (size_t)((K.nwords + 1) / 2)) * sizeof(double);
-    const size_t smemE = per_warp * DC_WARPS;
-    jt_smem_optin((const void *)k_dc_interp, (size_t)(smemE));
-    int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (227 * 1024) / (smemE + 4096 + 1024)));
-    int gridE = (int)std::min<int64_t>((nw + DC_WARPS - 1) / DC_WARPS, (int64_t)c->num_sms * per_sm);
-    if (gridE < 1) gridE = 1;
-    const size_t nmax = (size_t)K.W;
-    const size_t scratch_per_warp = nmax * K.order + 3 * nmax + 2 * ((nmax + 1) / 2) + 8;
-    double *scratch = jt_dalloc<double>(c, scratch_per_warp * (size_t)gridE * DC_WARPS);
     { JtLaunch L(c, "adeclick:autocorr");
-    k_dc_autocorr<<<jt_grid_for(nw, 1, c->num_sms, 64), 64, smemA, c->stream>>>((const double *)in.d, in.n, nw, K, d_r); }
+    k_dc_autocorr<<<jt_grid_for((nw + DC_AC_G - 1) / DC_AC_G, 1, c->num_sms, 16), 64, smemA, c->stream>>>((const double *)in.d, in.n, nw, K, d_r); }
     { JtLaunch L(c, "adeclick:levinson");
     k_dc_levinson<<<(int)((nw + 127) / 128), 128, 0, c->stream>>>(d_r, nw, K, d_a, d_sig); }
     { JtLaunch L(c, "adeclick:detect");
-    k_dc_detect<<<jt_grid_for(nw, 1, c->num_sms, 32), 256, smemC, c->stream>>>((const double *)in.d, in.n, nw, K, d_a, d_sig, d_bits, d_cnt); }
-    JtLaunch L(c, "adeclick:interp");
-    k_dc_interp<<<gridE, DC_WARPS * 32, smemE, c->stream>>>((const double *)in.d, (double *)o.d, in.n, nw, K, d_a, d_bits, d_cnt,
-                                                            scratch, scratch_per_warp, d_next);
+    k_dc_detect<<<jt_grid_for(nw, 1, c->num_sms, 32), 256, smemC, c->stream>>>((const double *)in.d, in.n, nw, K, d_a, d_sig, d_bits, d_cnt, d_class_count, d_class_list); }
+    // one launch per band-width bin, widest first; a bin's grid fills the SMs as far as its ring allows (64 registers per
+    // thread: 32 warps per SM at most)
+    const size_t nmax = (size_t)K.W;
+    JtLaunch L(c, "adeclick:interp", DC_NCLASS);
+    for (int cl = DC_NCLASS - 1; cl >= 0; cl--) {
+        const int R = std::min(dc_class_ring(cl, K.bw), K.bw);
+        if (cl < DC_NCLASS - 1 && dc_class_ring(cl, K.bw) >= K.bw) continue;          // this bin is empty by construction: the last one covers it
+        const size_t per_warp = ((size_t)R * R + 2 * (size_t)K.bw + (size_t)R + (size_t)((K.nwords + 1) / 2)) * sizeof(double);
+        const size_t smemE = per_warp * DC_WARPS;
+        jt_smem_optin((const void *)k_dc_interp, (size_t)(smemE));
+        const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(32 / DC_WARPS, (227 * 1024) / (smemE + 4096 + 1024)));
+        int gridE = (int)std::min<int64_t>((nw + DC_WARPS - 1) / DC_WARPS, (int64_t)c->num_sms * per_sm);
+        if (gridE < 1) gridE = 1;
+        const size_t scratch_per_warp = nmax * (size_t)(R - 1) + 3 * nmax + 2 * ((nmax + 1) / 2) + 8;
+        double *scratch = jt_dalloc<double>(c, scratch_per_warp * (size_t)gridE * DC_WARPS);
+        k_dc_interp<<<gridE, DC_WARPS * 32, smemE, c->stream>>>((const double *)in.d, (double *)o.d, in.n, nw, K, R, d_a, d_bits, d_cnt,
+                                                                d_class_list + (size_t)cl * nw, d_class_count + cl,
+                                                                scratch, scratch_per_warp, d_next + cl);
+    }
     return o;
 }

@@ -51,23 +51,30 @@ static KWeight kweight_design(int rate)
     return k;
 }
 
-// One lane = G consecutive ticks (plus WU warm-up ticks).  STRUCT 0: cascade of two direct
-// form I biquads (f_ebur128.c FILTER macro); STRUCT 1: 4th-order direct form II (ebur128.c).
+// One lane = G consecutive UNITS plus a warm-up of `warm` samples (1.5 ticks: 36 time constants of the RLB high-pass, whose
+// state is forgotten to 2e-16 by then).  A unit is a whole 100 ms tick (S = 1: long streams, where there are more ticks than
+// lanes to fill the machine) or one of S equal parts of a tick (short streams -- a 60 s region, a 10 min file -- where whole-
+// tick lanes would leave most SMs idle and the launch would cost a fixed (warm + G ticks) walk whatever the length).
+// STRUCT 0: cascade of two direct form I biquads (f_ebur128.c FILTER macro); STRUCT 1: 4th-order direct form II (ebur128.c).
+__device__ __forceinline__ int64_t r128_unit_start(int64_t u, int S, int L, int tick) { const int64_t k = u / S; return k * tick + (u - k * S) * (int64_t)L; }
+__device__ __forceinline__ int64_t r128_unit_end(int64_t u, int S, int L, int tick) { const int64_t k = u / S; return k * tick + min((u - k * S + 1) * (int64_t)L, (int64_t)tick); }
+
 template <class TIN, int STRUCT>
 __global__ void __launch_bounds__(64)
-k_r128_ticks(const TIN *__restrict__ x, int64_t n, int tick, int64_t n_ticks_total, int G, int WU,
-             const __grid_constant__ KWeight kw, double *__restrict__ tick_pow, double *__restrict__ tick_peak)
+k_r128_ticks(const TIN *__restrict__ x, int64_t n, int tick, int64_t n_units_total, int G, int warm, int S, int L,
+             const __grid_constant__ KWeight kw, double *__restrict__ unit_pow, double *__restrict__ unit_peak)
 {
     constexpr int R = 512 / (int)sizeof(TIN);                    // 512-byte rows, double-buffered
     extern __shared__ __align__(16) unsigned char smem[];
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = t * G < n_ticks_total;
-    const int64_t k0 = min(t * G, n_ticks_total);
-    const int64_t k1 = min(k0 + (int64_t)G, n_ticks_total);
-    const int64_t begin = max((int64_t)0, (k0 - WU) * (int64_t)tick);
-    const int64_t end = live ? min(k1 * (int64_t)tick, n) : begin;
+    const bool live = t * G < n_units_total;
+    const int64_t k0 = min(t * G, n_units_total);
+    const int64_t k1 = min(k0 + (int64_t)G, n_units_total);
+    const int64_t warm_end = min(r128_unit_start(k0, S, L, tick), n);
+    const int64_t begin = max((int64_t)0, warm_end - warm);
+    const int64_t end = live ? min(r128_unit_end(k1 - 1, S, L, tick), n) : begin;
     LaneStage<TIN, R, 2> in;
-    in.init(smem + (size_t)(threadIdx.x >> 5) * LaneStage<TIN, R, 2>::WARP_BYTES, x + begin, end - begin);
+    in.init(smem + (size_t)(threadIdx.x >> 5) * LaneStage<TIN, R, 2>::WARP_BYTES, x + begin, max(end - begin, (int64_t)0));
     double x1 = 0, x2 = 0, y1 = 0, y2 = 0, z1 = 0, z2 = 0;      // STRUCT 0
     double v1 = 0, v2 = 0, v3 = 0, v4 = 0;                        // STRUCT 1
     // One warp per scheduler: the walk is bound by the dependent-issue latency of f64 (8 cycles), so the
@@ -93,8 +100,7 @@ k_r128_ticks(const TIN *__restrict__ x, int64_t n, int tick, int64_t n_ticks_tot
     // patterns; f64 min / max issue at a third of the add rate, profiles/ubench_r1.txt)
     unsigned long long pkb = 0ull;
     auto peak_in = [&](double v) { const unsigned long long b = (unsigned long long)__double_as_longlong(v) & 0x7fffffffffffffffull; pkb = b > pkb ? b : pkb; };
-    const int64_t warm_end = k0 * (int64_t)tick;
-    int64_t k = k0, tick_end = min((k0 + 1) * (int64_t)tick, n);
+    int64_t k = k0, unit_end = min(r128_unit_end(k0, S, L, tick), n);
     double acc = 0.0;
     in.prime();
     for (int tile = 0; tile < in.ntiles; tile++) {
@@ -103,7 +109,7 @@ k_r128_ticks(const TIN *__restrict__ x, int64_t n, int tick, int64_t n_ticks_tot
         const int nv = in.valid(tile);
         int64_t i = begin + (int64_t)tile * R;
         int q = 0;
-        // branch-free runs: [warm-up run] then runs that end at a tick boundary
+        // branch-free runs: [warm-up run] then runs that end at a unit boundary
         while (q < nv) {
             if (i < warm_end) {
                 const int run = (int)min((int64_t)(nv - q), warm_end - i);
@@ -118,7 +124,7 @@ k_r128_ticks(const TIN *__restrict__ x, int64_t n, int tick, int64_t n_ticks_tot
                 for (; r < run; r++) (void)step(jt_as_f64(row[q + r]));
                 q += run; i += run;
             } else {
-                const int run = (int)min((int64_t)(nv - q), tick_end - i);
+                const int run = (int)min((int64_t)(nv - q), unit_end - i);
                 int r = 0;
                 for (; r + 8 <= run; r += 8) {
                     double v[8];
@@ -134,15 +140,27 @@ k_r128_ticks(const TIN *__restrict__ x, int64_t n, int tick, int64_t n_ticks_tot
                     peak_in(x0);
                 }
                 q += run; i += run;
-                if (i == tick_end) {
-                    tick_pow[k] = acc; tick_peak[k] = __longlong_as_double((long long)pkb);
+                if (i == unit_end) {
+                    unit_pow[k] = acc; unit_peak[k] = __longlong_as_double((long long)pkb);
                     acc = 0.0; pkb = 0ull; k++;
-                    tick_end = min((k + 1) * (int64_t)tick, n);
+                    // (units past the stream's end stay at the zeros the buffers were cleared to)
+                    unit_end = k < k1 ? min(r128_unit_end(k, S, L, tick), n) : n + 1;
                 }
             }
         }
         in.release();
     }
+}
+
+// per-tick values from the S parts of each tick, summed in part order (deterministic)
+__global__ void k_r128_fold(const double *__restrict__ unit_pow, const double *__restrict__ unit_peak, int64_t n_ticks, int S,
+                            double *__restrict__ tick_pow, double *__restrict__ tick_peak)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_ticks) return;
+    double p = 0.0, m = 0.0;
+    for (int j = 0; j < S; j++) { p += unit_pow[k * S + j]; m = fmax(m, unit_peak[k * S + j]); }
+    tick_pow[k] = p; tick_peak[k] = m;
 }
 
 template <int STRUCT>
@@ -151,22 +169,34 @@ static void run_ticks(jt_ctx *c, const Sig &in0, int tick, int64_t n_ticks_total
 {
     if (n_ticks_total <= 0) return;
     const Sig in = in0.fmt == JT_FMT_S32 ? jt_convert(c, in0, JT_FMT_DBL) : in0;      // the filter's link is dbl: s32 widens exactly
-    // 34 KB of staging per warp: 6 warps per SM.  Two ticks per lane (plus two of warm-up) unless that would
-    // need a second wave of CTAs; then the lanes grow instead.
-    const int WU = 2;
+    // 34 KB of staging per warp: 6 warps per SM
     const int64_t slots = (int64_t)c->num_sms * 6 * 32;
-    const int G = (int)std::max<int64_t>(2, (n_ticks_total + slots - 1) / slots);
-    const int64_t lanes = (n_ticks_total + G - 1) / G;
+    const int warm = tick + tick / 2;
+    int S = 1, G;
+    if (n_ticks_total * 4 < slots) {
+        // a short stream: cut every tick into S parts so the lanes fill the machine (parts of at least 256 samples)
+        S = (int)std::min<int64_t>(std::min<int64_t>(16, slots / (2 * n_ticks_total)), std::max(1, tick / 256));
+        if (S < 1) S = 1;
+        G = 1;
+    } else G = (int)std::max<int64_t>(2, (n_ticks_total + slots - 1) / slots);      // ticks per lane; grows instead of a second wave of CTAs
+    const int L = (tick + S - 1) / S;
+    const int64_t n_units = n_ticks_total * S;
+    const int64_t lanes = (n_units + G - 1) / G;
     const int grid = (int)((lanes + 63) / 64);
-    JtLaunch L(c, in.rate >= 176400 ? "r128_kweight_ticks:192k" : "r128_kweight_ticks");
+    double *u_pow = d_pow, *u_peak = d_peak;
+    if (S > 1) { u_pow = jt_dalloc<double>(c, (size_t)n_units); u_peak = jt_dalloc<double>(c, (size_t)n_units); }
+    JT_CUDA(cudaMemsetAsync(u_pow, 0, sizeof(double) * (size_t)n_units, c->stream));
+    JT_CUDA(cudaMemsetAsync(u_peak, 0, sizeof(double) * (size_t)n_units, c->stream));
+    JtLaunch Lc(c, in.rate >= 176400 ? "r128_kweight_ticks:192k" : "r128_kweight_ticks", S > 1 ? 2 : 1);
 #define R128_LAUNCH(T) do { \
         const size_t smem = 2 * LaneStage<T, 512 / (int)sizeof(T), 2>::WARP_BYTES; \
         jt_smem_optin((const void *)k_r128_ticks<T, STRUCT>, (size_t)(smem)); \
-        k_r128_ticks<T, STRUCT><<<grid, 64, smem, c->stream>>>((const T *)in.d, in.n, tick, n_ticks_total, G, WU, kw, d_pow, d_peak); } while (0)
+        k_r128_ticks<T, STRUCT><<<grid, 64, smem, c->stream>>>((const T *)in.d, in.n, tick, n_units, G, warm, S, L, kw, u_pow, u_peak); } while (0)
     if (in.fmt == JT_FMT_S16) R128_LAUNCH(int16_t);
     else if (in.fmt == JT_FMT_FLT) R128_LAUNCH(float);
     else R128_LAUNCH(double);
 #undef R128_LAUNCH
+    if (S > 1) k_r128_fold<<<(int)((n_ticks_total + 255) / 256), 256, 0, c->stream>>>(u_pow, u_peak, n_ticks_total, S, d_pow, d_peak);
 }
 
 // ---------------------------------------------------------------------------------------
