@@ -42,35 +42,75 @@ __device__ __forceinline__ double dc_sample(const double *__restrict__ x, int64_
 // Leading products with a not-yet-valid operand are +-0.0 added to a sum that is still +0.0: bit-identical.
 #define DC_AC_G 4            // windows per CTA
 #define DC_AC_LT 4           // lags per thread
-__global__ void __launch_bounds__(64)
-k_dc_autocorr(const double *__restrict__ x, int64_t n, int64_t n_windows, DcConst K, double *__restrict__ r_out)
+__device__ __forceinline__ void dc_ac_lags(const double *__restrict__ sw, int PL, int l0, int W, double *v)
 {
-    extern __shared__ double s_in[];                    // DC_AC_G windows of W samples
+    // window sample i at plane i & 3, slot i >> 2 of sw.  j and l0 are multiples of 4 at the top of every trip, so a trip reads
+    // slot q of each plane for s[j .. j+3] and slot q - l0/4 for s[j-l0 .. j-l0+3]
+    double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
+    double c1 = 0.0, c2 = 0.0, c3 = 0.0;                 // s[j-l0-1], s[j-l0-2], s[j-l0-3] (zero before the window)
+    const double *pb = sw + (l0 >> 2), *pa = sw;
+    int j = l0;
+    // four steps per trip: the eight loads and sixteen products of a trip are independent of the four running sums,
+    // whose additions stay in j order
+    for (; j + 4 <= W; j += 4, pb++, pa++) {
+        const double b0 = pb[0], b1 = pb[PL], b2 = pb[2 * PL], b3 = pb[3 * PL];
+        const double a0 = pa[0], a1 = pa[PL], a2 = pa[2 * PL], a3 = pa[3 * PL];
+        const double p00 = jdmul(b0, a0), p01 = jdmul(b0, c1), p02 = jdmul(b0, c2), p03 = jdmul(b0, c3);
+        const double p10 = jdmul(b1, a1), p11 = jdmul(b1, a0), p12 = jdmul(b1, c1), p13 = jdmul(b1, c2);
+        const double p20 = jdmul(b2, a2), p21 = jdmul(b2, a1), p22 = jdmul(b2, a0), p23 = jdmul(b2, c1);
+        const double p30 = jdmul(b3, a3), p31 = jdmul(b3, a2), p32 = jdmul(b3, a1), p33 = jdmul(b3, a0);
+        v0 = jdadd(jdadd(jdadd(jdadd(v0, p00), p10), p20), p30);
+        v1 = jdadd(jdadd(jdadd(jdadd(v1, p01), p11), p21), p31);
+        v2 = jdadd(jdadd(jdadd(jdadd(v2, p02), p12), p22), p32);
+        v3 = jdadd(jdadd(jdadd(jdadd(v3, p03), p13), p23), p33);
+        c1 = a3; c2 = a2; c3 = a1;
+    }
+    for (; j < W; j++) {
+        const double sj = sw[(j & 3) * PL + (j >> 2)], a0 = sw[((j - l0) & 3) * PL + ((j - l0) >> 2)];
+        v0 = jdadd(v0, jdmul(sj, a0)); v1 = jdadd(v1, jdmul(sj, c1)); v2 = jdadd(v2, jdmul(sj, c2)); v3 = jdadd(v3, jdmul(sj, c3));
+        c3 = c2; c2 = c1; c1 = a0;
+    }
+    v[0] = v0; v[1] = v1; v[2] = v2; v[3] = v3;
+}
+
+__global__ void __launch_bounds__(64)
+k_dc_autocorr(const double *__restrict__ x, int64_t n, int64_t n_windows, DcConst K, int PL, double *__restrict__ r_out)
+{
+    // The DC_AC_G consecutive windows of a CTA overlap (hop < W): they are staged ONCE as the contiguous span they cover, in four
+    // planes (sample 4k+p of the span at plane p, slot k).  Threads of a window read addresses 4 samples apart -- s[j - l0],
+    // l0 = 4 * thread -- which in planes are consecutive slots; the s[j] every thread of a window needs is one broadcast.
+    extern __shared__ double s_in[];
     const int tpw = (K.order + DC_AC_LT) / DC_AC_LT;      // threads per window: ceil((order + 1) / 4)
     const int64_t groups = (n_windows + DC_AC_G - 1) / DC_AC_G;
+    const int g = threadIdx.x / tpw, l0 = (threadIdx.x - g * tpw) * DC_AC_LT;
+    const double inv = 1. / K.W;
     for (int64_t grp = blockIdx.x; grp < groups; grp += gridDim.x) {
-        __syncthreads();
-        for (int g = 0; g < DC_AC_G; g++) {
-            const int64_t w = grp * DC_AC_G + g;
-            if (w < n_windows) for (int j = threadIdx.x; j < K.W; j += blockDim.x) s_in[g * K.W + j] = dc_sample(x, n, w, j, K);
-        }
-        __syncthreads();
-        const int g = threadIdx.x / tpw, l0 = (threadIdx.x - g * tpw) * DC_AC_LT;
-        const int64_t w = grp * DC_AC_G + g;
-        if (g < DC_AC_G && w < n_windows) {
-            const double *sw = s_in + g * K.W;
-            double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
-            double w1 = 0.0, w2 = 0.0, w3 = 0.0;         // s[j-l0-1], s[j-l0-2], s[j-l0-3] (zero before the window)
-            for (int j = l0; j < K.W; j++) {
-                const double sj = sw[j], w0 = sw[j - l0];
-                v0 = jdadd(v0, jdmul(sj, w0)); v1 = jdadd(v1, jdmul(sj, w1)); v2 = jdadd(v2, jdmul(sj, w2)); v3 = jdadd(v3, jdmul(sj, w3));
-                w3 = w2; w2 = w1; w1 = w0;
+        const int64_t w0 = grp * DC_AC_G;
+        const int nwin = (int)min((int64_t)DC_AC_G, n_windows - w0);
+        const int64_t s_base = w0 * (int64_t)K.hop - K.skip;
+        const int span = K.W + (nwin - 1) * K.hop;
+        const bool shared_span = (K.hop & 3) == 0 && s_base >= 0 && s_base + span <= n;     // no fifo edge rule inside the group
+        double v[4];
+        if (shared_span) {
+            __syncthreads();
+#pragma unroll 8
+            for (int i = threadIdx.x; i < span; i += 64) s_in[(i & 3) * PL + (i >> 2)] = x[s_base + i];
+            __syncthreads();
+            if (g < nwin) {
+                dc_ac_lags(s_in + g * (K.hop >> 2), PL, l0, K.W, v);
+                const int64_t w = w0 + g;
+                for (int t = 0; t < 4; t++) if (l0 + t <= K.order) r_out[w * K.bw + l0 + t] = jdmul(v[t], inv);
             }
-            const double inv = 1. / K.W;
-            if (l0 + 0 <= K.order) r_out[w * K.bw + l0 + 0] = jdmul(v0, inv);
-            if (l0 + 1 <= K.order) r_out[w * K.bw + l0 + 1] = jdmul(v1, inv);
-            if (l0 + 2 <= K.order) r_out[w * K.bw + l0 + 2] = jdmul(v2, inv);
-            if (l0 + 3 <= K.order) r_out[w * K.bw + l0 + 3] = jdmul(v3, inv);
+        } else {
+            for (int gg = 0; gg < nwin; gg++) {           // stream edges: one window at a time through the fifo's rules
+                __syncthreads();
+                for (int j = threadIdx.x; j < K.W; j += 64) s_in[(j & 3) * PL + (j >> 2)] = dc_sample(x, n, w0 + gg, j, K);
+                __syncthreads();
+                if (g == gg) {
+                    dc_ac_lags(s_in, PL, l0, K.W, v);
+                    for (int t = 0; t < 4; t++) if (l0 + t <= K.order) r_out[(w0 + gg) * K.bw + l0 + t] = jdmul(v[t], inv);
+                }
+            }
         }
     }
 }
@@ -116,10 +156,14 @@ k_dc_detect(const double *__restrict__ x, int64_t n, int64_t n_windows, DcConst 
             const double *__restrict__ sigmae, unsigned *__restrict__ bits_out, int *__restrict__ count_out,
             int *__restrict__ class_count /* DC_NCLASS */, int *__restrict__ class_list /* DC_NCLASS x n_windows */)
 {
-    extern __shared__ double s_in[];                 // W samples, then order+1 coefficients
+    extern __shared__ double s_raw[];                // the window (zero-padded: OP samples before, 4 after) in four planes, then the coefficients
     __shared__ unsigned s_bits[160], s_fill[160];
     __shared__ int s_cnt, s_maxc;
-    double *kc = s_in + K.W;
+    // sample i (-OP <= i < W + 4) lives at plane (i + OP) & 3, slot (i + OP) >> 2: a thread's four samples are 4 apart from its
+    // neighbour's, which in planes is the next slot -- no bank conflicts -- and the zero padding removes every bounds check
+    const int OP = (K.order + 3) & ~3, PL = (OP + K.W + 4 + 3) / 4 + 1;
+    double *kc = s_raw + 4 * PL;
+#define SI(i) s_raw[(((i) + OP) & 3) * PL + (((i) + OP) >> 2)]
     for (int64_t w = blockIdx.x; w < n_windows; w += gridDim.x) {
         __syncthreads();
         const bool finite = sigmae[2 * w + 1] != 0.0;
@@ -128,8 +172,10 @@ k_dc_detect(const double *__restrict__ x, int64_t n, int64_t n_windows, DcConst 
             if (threadIdx.x == 0) count_out[w] = 0;
             continue;
         }
-        for (int j = threadIdx.x; j < K.W; j += blockDim.x) s_in[j] = dc_sample(x, n, w, j, K);
-        for (int j = threadIdx.x; j <= K.order; j += blockDim.x) kc[j] = acoef[w * K.bw + j];
+        for (int j = threadIdx.x; j < K.W; j += blockDim.x) SI(j) = dc_sample(x, n, w, j, K);
+        for (int j = threadIdx.x; j < OP; j += blockDim.x) SI(j - OP) = 0.0;
+        for (int j = threadIdx.x; j < 4; j += blockDim.x) SI(K.W + j) = 0.0;
+        for (int j = threadIdx.x; j <= K.order + 3; j += blockDim.x) kc[j] = j <= K.order ? acoef[w * K.bw + j] : 0.0;
         if (threadIdx.x == 0) { s_cnt = 0; s_maxc = 0; }
         __syncthreads();
         const double thr = jdmul(sigmae[2 * w], K.threshold);
@@ -139,10 +185,23 @@ k_dc_detect(const double *__restrict__ x, int64_t n, int64_t n_windows, DcConst 
             const int ib = i0 + threadIdx.x * 4;             // samples ib .. ib + 3
             double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
             if (ib < K.W) {
-                auto S = [&](int q) { return (q >= 0 && q < K.W) ? s_in[q] : 0.0; };
-                double a1 = S(ib + 1), a2 = S(ib + 2), a3 = S(ib + 3);     // s[ib+1-j], s[ib+2-j], s[ib+3-j] at j = 0
-                for (int j = 0; j <= K.order; j++) {
-                    const double kj = kc[j], a0 = S(ib - j);
+                // s_in[ib + t - j], t = 0 .. 3: three carried values and four new ones per four steps of j; the products of a
+                // trip are formed first, the four running sums take them in j order.  (Past `order` the coefficients are
+                // zero-padded and the last trip's extra products are skipped.)
+                double a1 = SI(ib + 1), a2 = SI(ib + 2), a3 = SI(ib + 3);
+                int j = 0;
+                for (; j + 4 <= K.order + 1; j += 4) {
+                    const double k0 = kc[j], k1 = kc[j + 1], k2 = kc[j + 2], k3 = kc[j + 3];
+                    const double n0 = SI(ib - j), n1 = SI(ib - j - 1), n2 = SI(ib - j - 2), n3 = SI(ib - j - 3);
+                    // step j: (n0, a1, a2, a3); j+1: (n1, n0, a1, a2); j+2: (n2, n1, n0, a1); j+3: (n3, n2, n1, n0)
+                    d0 = jdadd(jdadd(jdadd(jdadd(d0, jdmul(k0, n0)), jdmul(k1, n1)), jdmul(k2, n2)), jdmul(k3, n3));
+                    d1 = jdadd(jdadd(jdadd(jdadd(d1, jdmul(k0, a1)), jdmul(k1, n0)), jdmul(k2, n1)), jdmul(k3, n2));
+                    d2 = jdadd(jdadd(jdadd(jdadd(d2, jdmul(k0, a2)), jdmul(k1, a1)), jdmul(k2, n0)), jdmul(k3, n1));
+                    d3 = jdadd(jdadd(jdadd(jdadd(d3, jdmul(k0, a3)), jdmul(k1, a2)), jdmul(k2, a1)), jdmul(k3, n0));
+                    a1 = n3; a2 = n2; a3 = n1;
+                }
+                for (; j <= K.order; j++) {
+                    const double kj = kc[j], a0 = SI(ib - j);
                     d0 = jdadd(d0, jdmul(kj, a0)); d1 = jdadd(d1, jdmul(kj, a1)); d2 = jdadd(d2, jdmul(kj, a2)); d3 = jdadd(d3, jdmul(kj, a3));
                     a3 = a2; a2 = a1; a1 = a0;
                 }
@@ -426,12 +485,16 @@ Sig jt_adeclick(jt_ctx *c, const Sig &in, double w_ms, double overlap_pct, doubl
     JT_CUDA(cudaMemsetAsync(d_class_count, 0, 2 * DC_NCLASS * sizeof(int), c->stream));
     // the windows pass through except where clicks are repaired: out = in, then E overwrites
     JT_CUDA(cudaMemcpyAsync(o.d, in.d, sizeof(double) * (size_t)in.n, cudaMemcpyDeviceToDevice, c->stream));
-    const size_t smemA = sizeof(double) * K.W * DC_AC_G, smemC = sizeof(double) * (K.W + K.bw);
+    // plane length of the span of DC_AC_G overlapping windows; = 8 mod 16 so that the four planes start 8 "double banks" apart
+    int PLa = (K.W + (DC_AC_G - 1) * std::min(K.hop, K.W) + 3) / 4 + 1;
+    PLa = (PLa + 7) / 16 * 16 + 8;
+    const size_t smemA = sizeof(double) * 4 * (size_t)PLa;
+    const size_t smemC = sizeof(double) * (4 * ((((K.order + 3) & ~3) + K.W + 4 + 3) / 4 + 1) + K.bw + 4);
     if (DC_AC_G * ((K.order + DC_AC_LT) / DC_AC_LT) > 64) JT_THROW(JT_ERR_UNSUPPORTED, "adeclick AR order %d", K.order);
     jt_smem_optin((const void *)k_dc_autocorr, (size_t)(smemA));
     jt_smem_optin((const void *)k_dc_detect, (size_t)(smemC));
     { JtLaunch L(c, "adeclick:autocorr");
-    k_dc_autocorr<<<jt_grid_for((nw + DC_AC_G - 1) / DC_AC_G, 1, c->num_sms, 16), 64, smemA, c->stream>>>((const double *)in.d, in.n, nw, K, d_r); }
+    k_dc_autocorr<<<jt_grid_for((nw + DC_AC_G - 1) / DC_AC_G, 1, c->num_sms, 16), 64, smemA, c->stream>>>((const double *)in.d, in.n, nw, K, PLa, d_r); }
     { JtLaunch L(c, "adeclick:levinson");
     k_dc_levinson<<<(int)((nw + 127) / 128), 128, 0, c->stream>>>(d_r, nw, K, d_a, d_sig); }
     { JtLaunch L(c, "adeclick:detect");

@@ -32,84 +32,30 @@ __device__ __forceinline__ double env_step(double e, double d, double attack_coe
     return d > e ? ea : er;
 }
 
-// Warm-up by SANDWICH.  The step map e -> e + (d - e) * (d > e ? a : r) is increasing in e, so a lane that starts `warm`
-// samples early with TWO states -- 0 and an upper bound of the true state -- keeps the true state between them; when the two
-// have met (to 1e-12 of their value) the lane knows its entry state without walking the 37 release time constants a start
-// from 0 alone would need to be sure.  They meet fast wherever the detector value keeps crossing the envelope (speech, room
-// tone: the attack coefficient is 40x the release), slowly only while the upper state coasts down in pure release.  The
-// upper bound: e_t <= max(d over the last L samples) + G * (1 - r)^L with G the stream's maximum of d (induction on the step
-// map), from per-1024-sample block maxima.  A lane whose states have NOT met by the end of the short warm-up writes nothing
-// and raises its flag; a second launch walks the flagged lanes with the full warm-up.
-#define ENV_BLK 1024
-__global__ void __launch_bounds__(256)
-k_env_blockmax(const double *__restrict__ x, int64_t n, int rms, double *__restrict__ bmax, double *__restrict__ gmax)
-{
-    __shared__ double red[8];
-    const int64_t nb = (n + ENV_BLK - 1) / ENV_BLK;
-    for (int64_t b = blockIdx.x; b < nb; b += gridDim.x) {
-        double m = 0.0;
-        for (int64_t i = b * ENV_BLK + threadIdx.x; i < min((b + 1) * (int64_t)ENV_BLK, n); i += 256) { const double v = x[i]; m = fmax(m, rms ? v * v : fabs(v)); }
-        m = jt_warp_max(m);
-        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
-        __syncthreads();
-        if (threadIdx.x == 0) { for (int i = 1; i < 8; i++) m = fmax(m, red[i]); bmax[b] = m; jt_atomic_max_nonneg(gmax, m); }
-        __syncthreads();
-    }
-}
-
 __global__ void __launch_bounds__(ENV_THREADS)
 k_envelope(const double *__restrict__ x, double *__restrict__ env, int64_t n, int seg, int warm,
-           double attack_coeff, double release_coeff, int rms,
-           const double *__restrict__ bmax, const double *__restrict__ gmax, int hist_blocks, double hist_decay,
-           int *__restrict__ redo, int only_redo)
+           double attack_coeff, double release_coeff, int rms)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int warp = threadIdx.x >> 5;
     unsigned char *wsm = smem + (size_t)warp * (EnvIn::WARP_BYTES + EnvOut::WARP_BYTES);
     const int64_t lane = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool live = lane * seg < n;
-    if (only_redo && live && !redo[lane]) live = false;
     const int64_t s0 = min(lane * seg, n), s1 = min(s0 + (int64_t)seg, n);
     const int64_t begin = max((int64_t)0, s0 - warm);
     EnvIn in; EnvOut out;
-    in.init(wsm, x + begin, live ? s1 - begin : 0);
+    in.init(wsm, x + begin, lane * seg < n ? s1 - begin : 0);
     out.init(wsm + EnvIn::WARP_BYTES, env + s0);
     // warm and seg are multiples of ENV_R, so a tile is either all warm-up or all output: the inner
     // loops are branch-free, which lets ptxas hoist the shared-memory loads and overlap everything
     // except the carried chain
-    double e = 0.0, eh = 0.0;
-    const bool sandwich = bmax != nullptr && !only_redo && begin > 0;
-    if (sandwich && live) {
-        const int64_t b1 = (begin + ENV_BLK - 1) / ENV_BLK, b0 = max((int64_t)0, begin / ENV_BLK - hist_blocks);
-        double m = 0.0;
-        for (int64_t bb = b0; bb < b1; bb++) m = fmax(m, bmax[bb]);
-        eh = m + *gmax * hist_decay;
-    }
-    bool ok = true, checked = !sandwich;
+    double e = 0.0;
     in.prime();
     for (int tile = 0; tile < in.ntiles; tile++) {
         in.prefetch();
         const double *row = in.wait(tile);
         const int nv = in.valid(tile);
         const int64_t i0 = begin + (int64_t)tile * ENV_R;
-        bool emit = i0 >= s0;
-        if (emit && !checked) {
-            // the two states have met: the true entry state is pinned to 1e-12 of its value (take the lower one; it is the
-            // state a walk from the stream's start would have, up to that)
-            ok = (eh - e) <= 1e-12 * eh;
-            if (!ok && nv > 0) redo[lane] = 1;
-            checked = true;
-        }
-        emit = emit && ok;
-        if (!emit && !checked) {
-            for (int k = 0; k < nv; k++) {
-                const double v = row[k], dd = rms ? v * v : fabs(v);
-                e = env_step(e, dd, attack_coeff, release_coeff);
-                eh = env_step(eh, dd, attack_coeff, release_coeff);
-            }
-            in.release();
-            continue;
-        }
+        const bool emit = i0 >= s0;
         for (int k0 = 0; k0 < nv; k0 += ENV_RO) {
             const int nb = min(ENV_RO, nv - k0);
             double *orow = out.row();
@@ -143,42 +89,22 @@ static double *run_envelope(jt_ctx *c, const Sig &in, double attack_ms, double r
     const double ac = std::fmin(1., 1. / (attack_ms * in.rate / 4000.)), rc = std::fmin(1., 1. / (release_ms * in.rate / 4000.));
     double *env = jt_dalloc<double>(c, in.n);
     const double cmin = std::fmin(ac, rc);
-    const double tau = cmin >= 1.0 ? 1.0 : 1.0 / -std::log1p(-cmin);           // samples per time constant of the slower branch
-    int64_t warm = cmin >= 1.0 ? 1 : (int64_t)std::ceil(37.0 * tau) + 16;
+    int64_t warm = cmin >= 1.0 ? 1 : (int64_t)std::ceil(37.0 / -std::log1p(-cmin)) + 16;
     if (warm > (1 << 22)) warm = 1 << 22;
     warm = (warm + ENV_R - 1) / ENV_R * ENV_R;                 // tile-aligned (see the kernel)
-    // short warm-up of the sandwich: ~14 time constants (the upper state coasts down from a loud passage to room tone in
-    // ~11 of them, the two states then meet within a few attack time constants)
-    int64_t warm_s = (int64_t)std::ceil(14.0 * tau);
-    warm_s = (warm_s + ENV_R - 1) / ENV_R * ENV_R;
-    const bool sandwich = rc <= ac && warm_s * 2 <= warm;      // the bound's induction needs release <= attack
-    // 84 KB of staging per warp lets 2 warps share an SM: the segment is sized so that all lanes run in one wave,
-    // never below 16384 samples
+    // Every lane re-reads `warm` samples before its segment (37 release time constants, ~89k samples at
+    // 200 ms / 48 kHz), so short segments multiply the HBM traffic while long ones leave the GPU to a handful
+    // of lanes.  84 KB of staging per warp lets 2 warps share an SM: the segment is sized so that all lanes
+    // run in one wave (20480 samples at one hour of audio: 5.3x re-read), never below 16384.
     const int64_t slots = (int64_t)c->num_sms * 2 * ENV_THREADS;
     int64_t seg64 = std::max<int64_t>(16384, (in.n + slots - 1) / slots);
     seg64 = std::min<int64_t>((seg64 + ENV_R - 1) / ENV_R * ENV_R, 1 << 20);
     const int seg = (int)seg64;
     const int64_t lanes = (in.n + seg - 1) / seg;
+    JtLaunch L(c, "envelope_follower");
     const size_t smem = (ENV_THREADS / 32) * (EnvIn::WARP_BYTES + EnvOut::WARP_BYTES);
     jt_smem_optin((const void *)k_envelope, (size_t)(smem));
-    const int grid = (int)((lanes + ENV_THREADS - 1) / ENV_THREADS);
-    if (!sandwich) {
-        JtLaunch L(c, "envelope_follower");
-        k_envelope<<<grid, ENV_THREADS, smem, c->stream>>>((const double *)in.d, env, in.n, seg, (int)warm, ac, rc, rms, nullptr, nullptr, 0, 0.0, nullptr, 0);
-        return env;
-    }
-    const int64_t nb = (in.n + ENV_BLK - 1) / ENV_BLK;
-    double *d_bmax = jt_dalloc<double>(c, (size_t)nb + 1), *d_gmax = d_bmax + nb;
-    int *d_redo = jt_dalloc<int>(c, (size_t)lanes);
-    JT_CUDA(cudaMemsetAsync(d_gmax, 0, sizeof(double), c->stream));
-    JT_CUDA(cudaMemsetAsync(d_redo, 0, sizeof(int) * (size_t)lanes, c->stream));
-    const int hist_blocks = (int)((warm + ENV_BLK - 1) / ENV_BLK);
-    const double hist_decay = std::pow(1.0 - rc, (double)hist_blocks * ENV_BLK - ENV_BLK);
-    JtLaunch L(c, "envelope_follower", 3);
-    k_env_blockmax<<<jt_grid_for(nb, 1, c->num_sms, 16), 256, 0, c->stream>>>((const double *)in.d, in.n, rms, d_bmax, d_gmax);
-    k_envelope<<<grid, ENV_THREADS, smem, c->stream>>>((const double *)in.d, env, in.n, seg, (int)warm_s, ac, rc, rms, d_bmax, d_gmax, hist_blocks, hist_decay, d_redo, 0);
-    // lanes whose states had not met: the full warm-up (every other lane leaves at once)
-    k_envelope<<<grid, ENV_THREADS, smem, c->stream>>>((const double *)in.d, env, in.n, seg, (int)warm, ac, rc, rms, nullptr, nullptr, 0, 0.0, d_redo, 1);
+    k_envelope<<<(int)((lanes + ENV_THREADS - 1) / ENV_THREADS), ENV_THREADS, smem, c->stream>>>((const double *)in.d, env, in.n, seg, (int)warm, ac, rc, rms);
     return env;
 }
 
