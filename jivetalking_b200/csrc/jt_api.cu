@@ -955,6 +955,19 @@ extern "C" int jt_graph_merge(const char *spec, int64_t total, int rate, int cha
         if (ln) *ln = res.ln;
         R128Result r128;
         if (gd.has_r128) jt_ebur128_host_finalize(nullptr, hp.data(), hk.data(), gd.r128_tp ? ht.data() : nullptr, nt, gd.r128_sig.rate / 10, gd.r128_dual, r128);
+        if (!meta && !n_meta) {
+            // accumulated measurements only: no records are built
+            if (accumulated) {
+                jt_accumulate_frames(gd.frames, gd.has_r128, r128, gd.has_spec, rows, n_hops, accumulated);
+                if (gd.has_astats && gd.last_astats_frame >= 0 && !first_as) {
+                    AstatsResult a;
+                    jt_astats_host_finalize(as.data(), gd.frames[gd.last_astats_frame].astats_pos, as_fmt, as_tc, a);
+                    if (!gd.astats_overall_only) for (int k = 0; k < JT_AS_COUNT; k++) accumulated->astats[k] = std::isnan(a.v[k]) ? NAN : jt_wire("%f", a.v[k]);
+                }
+                accumulated->duration_s = gd.out.rate > 0 ? (double)gd.out.n / gd.out.rate : 0.0;
+            }
+            return JT_OK;
+        }
         jt_assemble_records(gd.frames, gd.has_r128, r128, gd.has_spec, rows, n_hops, res);
         if (gd.has_astats && gd.last_astats_frame >= 0 && !first_as) {
             AstatsResult a;
@@ -1235,11 +1248,7 @@ static void process_device(jt_ctx *c, const void *d_in, int64_t n_frames, int ra
     jt_graph_enqueue(c, spec4, g2.out.d, g2.out.n, 44100, 1, JT_FMT_S16, 4096, true, true, g4);
     R.n_out = g4.out.n;
     // Pass 2: host part (sink-frame records, accumulators), while the GPU runs Pass 4
-    {
-        GraphResult r2;
-        jt_graph_finish(c, g2, r2);
-        MeasAcc a; for (auto &m : r2.meta) a.add(m); a.finish((double)g2.out.n / g2.out.rate); R.filtered = a.m;
-    }
+    jt_graph_finish_acc(c, g2, &R.filtered, nullptr);
     if (pcm_out) {                                 // the result leaves while the host assembles Pass 4's metadata
         if (g4.out.n > cap) JT_THROW(JT_ERR_BUFFER, "pcm_out holds %lld samples, chain produced %lld", (long long)cap, (long long)g4.out.n);
         const size_t ob = (size_t)g4.out.n * sizeof(int16_t);
@@ -1250,12 +1259,7 @@ static void process_device(jt_ctx *c, const void *d_in, int64_t n_frames, int ra
             JT_CUDA(cudaMemcpyAsync(pcm_out, g4.out.d, ob, out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->copy_stream));
         } else if (ob) JT_CUDA(cudaMemcpyAsync(pcm_out, g4.out.d, ob, out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
     }
-    {
-        GraphResult r4;
-        jt_graph_finish(c, g4, r4);
-        MeasAcc a; for (auto &m : r4.meta) a.add(m); a.finish((double)g4.out.n / g4.out.rate); R.final = a.m;
-        R.pass4 = r4.ln;
-    }
+    jt_graph_finish_acc(c, g4, &R.final, &R.pass4);
     if (an) {                                      // processor.go:150-160 and normalise.go's Pass-4 re-measure of the same regions
         measure_output_regions(c, g2.out.d, g2.out.n, an->voice_activity, &an->filtered_regions);
         measure_output_regions(c, g4.out.d, g4.out.n, an->voice_activity, &an->final_regions);
@@ -1566,37 +1570,29 @@ static void process_sharded_device(jt_ctx *c, const void *d_local, int64_t n_loc
             int64_t ra[2] = {0, 0}, rb[2] = {0, 0};
             if (want_speech) region_range(va.speech_profile.region.start_ns, va.speech_profile.region.duration_ns, rate, total, &ra[0], &rb[0]);
             if (want_noise) region_range(va.noise_profile.start_ns, va.noise_profile.duration_ns, rate, total, &ra[1], &rb[1]);
-            const size_t bs = jt_fmt_bytes(mono.fmt);
-            // my part of each region: region ^ owned, taken from the downmixed window
-            std::vector<char> send;
+            // every rank band-filters the part of each region it owns (the filters warm up on the samples before it: the
+            // region's own when they are in reach, so a part that starts the region starts from rest as the reference's
+            // graph does) and contributes 17 sums of squares
+            double lo_hz[17], hi_hz[17]; jt_band_plan(lo_hz, hi_hz);
+            std::vector<char> send(17 * sizeof(double), 0);
+            double *mine = (double *)send.data();
             for (int k = 0; k < 2; k++) {
                 const int64_t lo = std::max(ra[k], P.own_first), hi = std::min(rb[k], P.own_first + P.owned);
-                if (hi > lo) {
-                    const size_t off = send.size(); send.resize(off + (size_t)(hi - lo) * bs);
-                    JT_CUDA(cudaMemcpyAsync(send.data() + off, (const char *)mono.d + (size_t)(lo - P.local_first) * bs, (size_t)(hi - lo) * bs, cudaMemcpyDeviceToHost, c->stream));
-                }
+                if (hi <= lo) continue;
+                const int64_t cs = std::max(std::max(ra[k], lo - JT_BAND_WARM_MAX), P.local_first);
+                Sig part = jt_slice(mono, cs - P.local_first, hi - cs);
+                if (k == 0) jt_band_sumsq(c, part, lo - cs, lo_hz, hi_hz, 2, mine);
+                else jt_band_sumsq(c, part, lo - cs, lo_hz + 2, hi_hz + 2, 15, mine + 2);
             }
-            JT_CUDA(cudaStreamSynchronize(c->stream));
             std::vector<std::vector<char>> all = comm.allgather(send);
-            double lo_hz[17], hi_hz[17]; jt_band_plan(lo_hz, hi_hz);
             double rms[17] = {0}; int32_t found[17] = {0};
-            std::vector<size_t> cursor((size_t)world, 0);
-            for (int k = 0; k < 2; k++) {
+            for (int b = 0; b < 17; b++) {
+                const int k = b < 2 ? 0 : 1;
                 const int64_t len = rb[k] - ra[k];
-                if (len <= 0) continue;
-                std::vector<char> reg((size_t)len * bs);
-                for (int r = 0; r < world; r++) {
-                    const int64_t lo = std::max(ra[k], ck1.first[(size_t)r]), hi = std::min(rb[k], ck1.first[(size_t)r] + ck1.owned[(size_t)r]);
-                    if (hi > lo) {
-                        if (cursor[(size_t)r] + (size_t)(hi - lo) * bs > all[(size_t)r].size()) JT_THROW(JT_ERR_INVALID_ARG, "internal: region gather");
-                        memcpy(reg.data() + (size_t)(lo - ra[k]) * bs, all[(size_t)r].data() + cursor[(size_t)r], (size_t)(hi - lo) * bs);
-                        cursor[(size_t)r] += (size_t)(hi - lo) * bs;
-                    }
-                }
-                Sig rs; rs.fmt = mono.fmt; rs.rate = rate; rs.n = len; rs.d = upload(c, reg.data(), reg.size());
-                JT_CUDA(cudaStreamSynchronize(c->stream));             // `reg` is pageable host memory about to go out of scope
-                if (k == 0) jt_band_rms_batch(c, rs, lo_hz, hi_hz, 2, rms, found);
-                else jt_band_rms_batch(c, rs, lo_hz + 2, hi_hz + 2, 15, rms + 2, found + 2);
+                if (len <= 0 || !(k == 0 ? want_speech : want_noise)) continue;
+                double sum = 0;
+                for (int r = 0; r < world; r++) if (all[(size_t)r].size() == 17 * sizeof(double)) sum += ((const double *)all[(size_t)r].data())[b];
+                rms[b] = jt_wire("%f", log10(sqrt(sum / (double)len)) * 20); found[b] = 1;
             }
             jt_apply_band_rms(&va, want_speech ? rms : nullptr, want_speech ? found : nullptr, want_noise ? rms + 2 : nullptr, want_noise ? found + 2 : nullptr);
         }

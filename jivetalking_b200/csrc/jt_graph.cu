@@ -8,6 +8,7 @@
 // pushed input frame it becomes pullable).
 #include "jt_graph.h"
 #include <algorithm>
+#include <array>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -678,6 +679,85 @@ void jt_graph_finish(jt_ctx *c, GraphRun &g, GraphResult &res)
         m.astats_overall_RMS_level = jt_wire("%f", a.overall_rms);
         m.astats_overall_Peak_level = jt_wire("%f", a.overall_peak);
     }
+}
+
+// What the Go side accumulates from a pass's sink-frame records (latest-wins loudness values, mean of the spectral rows over
+// the frames that carry them: analyser_metrics.go:898-942) WITHOUT materialising the records: the per-frame work is the
+// "%g" rounding of 13 spectral values, spread over host threads.  Equal to feeding jt_assemble_records' output to the
+// accumulator, up to the order in which the spectral sums are added.
+void jt_accumulate_frames(const std::vector<FrameRef> &frames, bool has_r128, const R128Result &r128, bool has_spec,
+                          const std::vector<float> &spec_rows, int64_t spec_hops, jt_measurements *out)
+{
+    memset(out, 0, sizeof(*out));
+    for (double &a : out->astats) a = NAN;
+    const size_t nf = frames.size();
+    out->sink_frames = (int64_t)nf;
+    int64_t last_tick = -1; long last_tick_frame = -1;
+    for (size_t i = 0; i < nf; i++) if (frames[i].tick >= 0 && frames[i].tick < r128.n_ticks && (int64_t)frames[i].tick >= last_tick) { last_tick = frames[i].tick; last_tick_frame = (long)i; }
+    if (has_r128) {
+        // latest wins: the last frame that carries a tick gives M / S / peaks; I and LRA ride on the stream's last tick
+        for (long i = (long)nf - 1; i >= 0; i--) {
+            const FrameRef &fr = frames[(size_t)i];
+            if (fr.tick >= 0 && fr.tick < r128.n_ticks) {
+                const int64_t k = fr.tick;
+                out->last_m = jt_wire("%.3f", r128.M[k]); out->last_s = jt_wire("%.3f", r128.S[k]);
+                const double sp = jt_wire("%.3f", r128.sp_cum[k]), tp = jt_wire("%.3f", r128.tp_cum[k]);
+                out->input_sp = sp <= 0 ? -120.0 : 20 * log10(sp); out->input_tp = tp <= 0 ? -120.0 : 20 * log10(tp);
+                break;
+            }
+        }
+        if (last_tick_frame >= 0) { out->input_i = jt_wire("%.3f", r128.I); out->input_lra = jt_wire("%.3f", r128.LRA); }
+    }
+    if (has_spec && nf) {
+        const unsigned hw = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+        const unsigned nth = nf < 8192 ? 1u : hw;
+        std::vector<std::array<double, JT_SP_COUNT + 1>> part(nth);
+        auto work = [&](unsigned t) {
+            std::array<double, JT_SP_COUNT + 1> acc{}; 
+            const size_t per = (nf + nth - 1) / nth, a = t * per, b = std::min(nf, a + per);
+            for (size_t i = a; i < b; i++) {
+                const FrameRef &fr = frames[i];
+                if (fr.hop < 0 || fr.hop >= spec_hops) continue;
+                double v[JT_SP_COUNT]; bool any = false;
+                for (int k = 0; k < JT_SP_COUNT; k++) { v[k] = jt_wire("%g", (double)spec_rows[(size_t)fr.hop * JT_SP_COUNT + k]); any = any || !std::isnan(v[k]); }
+                if (!any) continue;
+                for (int k = 0; k < JT_SP_COUNT; k++) acc[k] += std::isnan(v[k]) ? 0.0 : v[k];
+                acc[JT_SP_COUNT] += 1.0;
+            }
+            part[t] = acc;
+        };
+        std::vector<std::thread> pool;
+        for (unsigned t = 1; t < nth; t++) pool.emplace_back(work, t);
+        work(0);
+        for (auto &t : pool) t.join();
+        double sum[JT_SP_COUNT] = {0}; double cnt = 0;
+        for (unsigned t = 0; t < nth; t++) { for (int k = 0; k < JT_SP_COUNT; k++) sum[k] += part[t][k]; cnt += part[t][JT_SP_COUNT]; }
+        out->spectral_frames = (int64_t)cnt;
+        for (int k = 0; k < JT_SP_COUNT; k++) out->spectral_mean[k] = cnt > 0 ? sum[k] / cnt : 0.0;
+    }
+}
+
+// jt_graph_finish for a caller that wants the accumulated measurements only (Pass 2 / Pass 4 inside the four-pass drivers)
+void jt_graph_finish_acc(jt_ctx *c, GraphRun &g, jt_measurements *acc, jt_loudnorm_stats *ln)
+{
+    const bool want = g.want_meta;
+    g.want_meta = false;
+    GraphResult res;
+    jt_graph_finish(c, g, res);                  // loudnorm statistics; no records
+    g.want_meta = want;
+    if (ln) *ln = res.ln;
+    if (!acc) return;
+    const R128Result &r128 = jt_graph_r128_early(c, g);
+    std::vector<float> spec_rows; int64_t spec_hops = 0;
+    if (g.has_spec) jt_aspectralstats_finish(c, g.specp, spec_rows, spec_hops);
+    JtHost hmeta(c, "meta_assembly");
+    jt_accumulate_frames(g.frames, g.has_r128, r128, g.has_spec, spec_rows, spec_hops, acc);
+    if (g.has_astats && g.last_astats_frame >= 0) {
+        AstatsResult a;
+        jt_astats_finish(c, g.astp, a);
+        if (!g.astats_overall_only) for (int k = 0; k < JT_AS_COUNT; k++) acc->astats[k] = std::isnan(a.v[k]) ? NAN : jt_wire("%f", a.v[k]);
+    }
+    acc->duration_s = g.out.rate > 0 ? (double)g.out.n / g.out.rate : 0.0;
 }
 
 void jt_assemble_records(const std::vector<FrameRef> &frames, bool has_r128, const R128Result &r128, bool has_spec,

@@ -84,6 +84,9 @@ void jt_graph_enqueue(jt_ctx *c, const std::string &spec, const void *d_in, int6
                       int fmt, int frame_size, bool want_pcm, bool want_meta, GraphRun &g, const GraphResume *resume = nullptr);
 const R128Result &jt_graph_r128_early(jt_ctx *c, GraphRun &g);     // waits for the ebur128 values only
 void jt_graph_finish(jt_ctx *c, GraphRun &g, GraphResult &res);
+void jt_graph_finish_acc(jt_ctx *c, GraphRun &g, jt_measurements *acc, jt_loudnorm_stats *ln);
+void jt_accumulate_frames(const std::vector<FrameRef> &frames, bool has_r128, const R128Result &r128, bool has_spec,
+                          const std::vector<float> &spec_rows, int64_t spec_hops, jt_measurements *out);
 
 void jt_pass1_records(jt_ctx *c, int64_t n_frames, int rate, int frame_size, const R128Result &r128,
                       const std::vector<float> &spec_rows, int64_t spec_hops, const AstatsResult *astats, GraphResult &res);

@@ -190,6 +190,8 @@ Sig  jt_biquad(jt_ctx *c, const Sig &in, const BiquadCoef &k, bool tdii, double 
 // 17-band batch (K20): per band highpass(lo) -> lowpass(hi) (direct form I) -> sum of squares / peak
 void jt_band_rms_batch(jt_ctx *c, const Sig &in, const double *lo, const double *hi, int n_bands,
                        double *rms_db, int32_t *found);
+#define JT_BAND_WARM_MAX (1 << 16)      // samples a band filter lane runs ahead of its segment at most
+void jt_band_sumsq(jt_ctx *c, const Sig &in, int64_t acc_from, const double *lo, const double *hi, int n_bands, double *sumsq_host);
 
 // ---- k_flac.cu ------------------------------------------------------------------------------
 int64_t jt_flac_bound(int64_t n, int block_size);

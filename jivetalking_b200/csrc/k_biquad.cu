@@ -130,7 +130,7 @@ struct BandCoef { float hb0, hb1, hb2, hna1, hna2, lb0, lb1, lb2, lna1, lna2; do
 template <class T, class F>
 __global__ void __launch_bounds__(64)
 k_band_rms(const T *__restrict__ x, int64_t n, int seg, int warm, int64_t segs_per_band, int n_bands,
-           const BandCoef *__restrict__ coef, double *__restrict__ sumsq /* n_bands */)
+           const BandCoef *__restrict__ coef, double *__restrict__ sumsq /* n_bands */, int64_t acc_from)
 {
     const int64_t lane = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     double acc = 0;
@@ -145,7 +145,7 @@ k_band_rms(const T *__restrict__ x, int64_t n, int seg, int warm, int64_t segs_p
         for (int64_t i = max((int64_t)0, s0 - warm); i < s1; i++) {
             const T h = BqIO<T, F>::out(bq_step<F, false>(sh, (F)x[i], hb0, hb1, hb2, hna1, hna2, (F)1, (F)0));
             const T l = BqIO<T, F>::out(bq_step<F, false>(sl, (F)h, lb0, lb1, lb2, lna1, lna2, (F)1, (F)0));
-            if (i >= s0) {
+            if (i >= s0 && i >= acc_from) {
                 const double nd = BandNorm<T>::nd(l);
                 acc = fma(nd, nd, acc);
             }
@@ -155,10 +155,13 @@ k_band_rms(const T *__restrict__ x, int64_t n, int seg, int warm, int64_t segs_p
     if (band < n_bands && acc != 0) atomicAdd(&sumsq[band], acc);
 }
 
-void jt_band_rms_batch(jt_ctx *c, const Sig &in, const double *lo, const double *hi, int n_bands, double *rms_db, int32_t *found)
+// sums of squares of the band-filtered signal over samples [acc_from, in.n) of `in`; the samples before acc_from only warm the
+// filters up (a rank of a sharded stream measuring its part of a region: jt_process_audio_sharded).  acc_from = 0 with `in`
+// starting at the region's first sample is the whole measurement.
+void jt_band_sumsq(jt_ctx *c, const Sig &in, int64_t acc_from, const double *lo, const double *hi, int n_bands, double *sumsq_host)
 {
-    for (int b = 0; b < n_bands; b++) { rms_db[b] = 0; found[b] = 0; }
-    if (in.n <= 0) return;
+    for (int b = 0; b < n_bands; b++) sumsq_host[b] = 0;
+    if (in.n <= 0 || acc_from >= in.n) return;
     std::vector<BandCoef> hc(n_bands);
     int warm = 1024;
     for (int b = 0; b < n_bands; b++) {
@@ -168,7 +171,7 @@ void jt_band_rms_batch(jt_ctx *c, const Sig &in, const double *lo, const double 
         k.lb0 = (float)l.b0; k.lb1 = (float)l.b1; k.lb2 = (float)l.b2; k.lna1 = (float)-l.a1; k.lna2 = (float)-l.a2;
         k.dh[0] = h.b0; k.dh[1] = h.b1; k.dh[2] = h.b2; k.dh[3] = -h.a1; k.dh[4] = -h.a2;
         k.dl[0] = l.b0; k.dl[1] = l.b1; k.dl[2] = l.b2; k.dl[3] = -l.a1; k.dl[4] = -l.a2;
-        warm = std::max(warm, std::min(std::max(biquad_warmup(h), biquad_warmup(l)), 1 << 16));
+        warm = std::max(warm, std::min(std::max(biquad_warmup(h), biquad_warmup(l)), JT_BAND_WARM_MAX));
     }
     BandCoef *d_coef = jt_dalloc<BandCoef>(c, n_bands);
     double *d_sum = jt_dalloc<double>(c, n_bands);
@@ -179,14 +182,21 @@ void jt_band_rms_batch(jt_ctx *c, const Sig &in, const double *lo, const double 
     const int grid = (int)((lanes + 63) / 64);
     {
         JtLaunch L(c, "band_rms");
-        if (in.fmt == JT_FMT_FLT) k_band_rms<float, float><<<grid, 64, 0, c->stream>>>((const float *)in.d, in.n, seg, warm, spb, n_bands, d_coef, d_sum);
-        else if (in.fmt == JT_FMT_DBL) k_band_rms<double, double><<<grid, 64, 0, c->stream>>>((const double *)in.d, in.n, seg, warm, spb, n_bands, d_coef, d_sum);
-        else if (in.fmt == JT_FMT_S16) k_band_rms<int16_t, float><<<grid, 64, 0, c->stream>>>((const int16_t *)in.d, in.n, seg, warm, spb, n_bands, d_coef, d_sum);
-        else if (in.fmt == JT_FMT_S32) k_band_rms<int32_t, double><<<grid, 64, 0, c->stream>>>((const int32_t *)in.d, in.n, seg, warm, spb, n_bands, d_coef, d_sum);
+        if (in.fmt == JT_FMT_FLT) k_band_rms<float, float><<<grid, 64, 0, c->stream>>>((const float *)in.d, in.n, seg, warm, spb, n_bands, d_coef, d_sum, acc_from);
+        else if (in.fmt == JT_FMT_DBL) k_band_rms<double, double><<<grid, 64, 0, c->stream>>>((const double *)in.d, in.n, seg, warm, spb, n_bands, d_coef, d_sum, acc_from);
+        else if (in.fmt == JT_FMT_S16) k_band_rms<int16_t, float><<<grid, 64, 0, c->stream>>>((const int16_t *)in.d, in.n, seg, warm, spb, n_bands, d_coef, d_sum, acc_from);
+        else if (in.fmt == JT_FMT_S32) k_band_rms<int32_t, double><<<grid, 64, 0, c->stream>>>((const int32_t *)in.d, in.n, seg, warm, spb, n_bands, d_coef, d_sum, acc_from);
         else JT_THROW(JT_ERR_UNSUPPORTED, "band rms on sample format %d", in.fmt);
     }
-    std::vector<double> hs(n_bands);
-    JT_CUDA(cudaMemcpyAsync(hs.data(), d_sum, sizeof(double) * n_bands, cudaMemcpyDeviceToHost, c->stream));
+    JT_CUDA(cudaMemcpyAsync(sumsq_host, d_sum, sizeof(double) * n_bands, cudaMemcpyDeviceToHost, c->stream));
     JT_CUDA(cudaStreamSynchronize(c->stream));
+}
+
+void jt_band_rms_batch(jt_ctx *c, const Sig &in, const double *lo, const double *hi, int n_bands, double *rms_db, int32_t *found)
+{
+    for (int b = 0; b < n_bands; b++) { rms_db[b] = 0; found[b] = 0; }
+    if (in.n <= 0) return;
+    std::vector<double> hs(n_bands);
+    jt_band_sumsq(c, in, 0, lo, hi, n_bands, hs.data());
     for (int b = 0; b < n_bands; b++) { rms_db[b] = jt_wire("%f", log10(sqrt(hs[b] / (double)in.n)) * 20); found[b] = 1; }
 }

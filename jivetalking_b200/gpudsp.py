@@ -278,12 +278,25 @@ class Context:
         self._check(rc)
         return buf.raw[: n.value]
 
-    def set_exchange(self, fn, n_ranks):
+    def set_exchange(self, fn, n_ranks, raw=False):
         """fn(send: bytes) -> bytes of n_ranks records in rank order (an all-gather); None removes it.  The carries
-        of a sharded stream (afftdn's tracked noise floor) cross chunk boundaries through it (jt_set_exchange)."""
+        of a sharded stream (afftdn's tracked noise floor) cross chunk boundaries through it (jt_set_exchange).
+        raw=True: fn(send_addr, nbytes, recv_addr) -> None works on the library's buffers in place (no Python copies)."""
         if fn is None:
             self._xfn = None
             lib().jt_set_exchange(self._h, None, None, 1)
+            return
+        if raw:
+            def _cbr(user, send, nbytes, recv):
+                try:
+                    fn(send, nbytes, recv)
+                    return 0
+                except Exception:          # an exception must not unwind through the C frames
+                    import traceback
+                    traceback.print_exc()
+                    return -1
+            self._xfn = EXCHANGE_FN(_cbr)
+            lib().jt_set_exchange(self._h, C.cast(self._xfn, _P), None, n_ranks)
             return
 
         def _cb(user, send, nbytes, recv):

@@ -186,6 +186,12 @@ def _plan_worker(rank, world, port, out):
     got = comm.exchange(rec)
     # variable-length payloads are built on it inside the library: lengths first, then padded payloads
     lens = comm.exchange(int(p.owned).to_bytes(8, "little"))
+    # the in-place variant bench.py installs (jt_set_exchange with raw=True) gives the same bytes
+    import ctypes as C
+    sb = (C.c_ubyte * 24).from_buffer_copy(rec)
+    rb = (C.c_ubyte * (24 * world))()
+    comm.exchange_raw(C.addressof(sb), 24, C.addressof(rb))
+    assert bytes(rb) == got
     dist.barrier()
     out.put((rank, (p.unit, p.own_first, p.owned, p.local_first, p.n_local), got, lens, total))
     dist.destroy_process_group()
