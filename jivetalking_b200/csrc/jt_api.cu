@@ -676,7 +676,7 @@ static void graph_chunk_core(jt_ctx *c, const char *spec, const void *d_in, int6
                              int64_t local_first, int64_t own_first, int64_t owned, int64_t total, int frame_size,
                              bool want_pcm, void *pcm_out, int64_t cap, Sig *own_dev,
                              int64_t *out_first, int64_t *n_out, int *out_rate, int *out_fmt,
-                             bool want_blob, std::vector<char> &blob_out)
+                             bool want_blob, std::vector<char> &blob_out, const GraphResume *head = nullptr)
 {
     {
         void *blob = want_blob ? (void *)&blob_out : nullptr;      // non-null = measurement kernels run
@@ -703,7 +703,7 @@ static void graph_chunk_core(jt_ctx *c, const char *spec, const void *d_in, int6
         GraphChunk ck; ck.local_first = local_first; ck.own_first = own_first; ck.owned = owned; ck.total = total; ck.rate = rate; ck.last = last;
         ck.exchange = c->exchange; ck.exchange_user = c->exchange_user; ck.n_ranks = c->exchange_ranks;
         GraphRun gl;
-        jt_graph_build(c, spec, d_in, n_local, rate, channels, fmt, frame_size, want_pcm, false, JT_GRAPH_CHUNK, &ck, gl);
+        jt_graph_build(c, spec, d_in, n_local, rate, channels, fmt, frame_size, want_pcm, false, JT_GRAPH_CHUNK, &ck, gl, head);
 
         // positions of the window / the owned range on a link of rate r whose whole-stream length is n_link
         struct Range { int64_t loc0, a, b; };          // link position of the window's first sample; owned = [a, b)
@@ -1293,6 +1293,14 @@ extern "C" int jt_process_audio_dev(jt_ctx *c, const void *d_in, int64_t n_frame
 // ProcessAudio with the adapted Pass-2 spec (processor.go:78-216).  Pass 2 depends on Pass 1 through the detector,
 // so the two cannot overlap here as they do in process_device with a caller-supplied spec.
 // ---------------------------------------------------------------------------------------
+// issue the enclosed work on another stream of the context; on leaving, everything issued there is done (so its buffers can be
+// released) and the context is back on its own stream
+struct StreamSwap {
+    jt_ctx *c; cudaStream_t main;
+    StreamSwap(jt_ctx *ctx, cudaStream_t to) : c(ctx), main(ctx->stream) { c->stream = to; }
+    ~StreamSwap() { cudaStreamSynchronize(c->stream); c->stream = main; }
+};
+
 static void analyse_adaptive_device(jt_ctx *c, const void *d_in, int64_t n_frames, int rate, int channels, int fmt, int F,
                                     const jt_filter_config *base, jt_analysis *out, jt_interval *iv_out, int64_t iv_cap, int64_t *n_iv_out,
                                     AnalysePending *pending = nullptr /* Pass 1 already enqueued by the caller */,
@@ -1320,11 +1328,6 @@ static void analyse_adaptive_device(jt_ctx *c, const void *d_in, int64_t n_frame
     if (want_speech || want_noise) {
         // The band graphs read the input only.  When Pass 2's head is already queued on the main stream they go to the side
         // stream (ordered behind the input's upload by `input_ready`), so their result does not wait for anlmdn.
-        struct StreamSwap {
-            jt_ctx *c; cudaStream_t main;
-            StreamSwap(jt_ctx *ctx, cudaStream_t to) : c(ctx), main(ctx->stream) { c->stream = to; }
-            ~StreamSwap() { cudaStreamSynchronize(c->stream); c->stream = main; }      // everything issued on it is done before its buffers are released
-        };
         std::unique_ptr<StreamSwap> swap;
         if (input_ready && c->side_stream) {
             JT_CUDA(cudaStreamWaitEvent(c->side_stream, input_ready, 0));
@@ -1534,7 +1537,10 @@ static void process_sharded_device(jt_ctx *c, const void *d_local, int64_t n_loc
     ShardComm comm{c, rank, world};
     jt_shard_timing T; memset(&T, 0, sizeof(T));
     double t_prev = ShardComm::host_seconds();
-    auto lap = [&](double &slot) { JT_CUDA(cudaStreamSynchronize(c->stream)); const double t = ShardComm::host_seconds(); slot += t - t_prev; t_prev = t; };
+    auto lap = [&](double &slot, bool sync = true) {
+        if (sync) JT_CUDA(cudaStreamSynchronize(c->stream));
+        const double t = ShardComm::host_seconds(); slot += t - t_prev; t_prev = t;
+    };
     std::vector<jt_analysis> own_an(analysis ? 0 : 1);
     jt_analysis *an = analysis ? analysis : own_an.data();
     memset(an, 0, sizeof(*an));
@@ -1546,16 +1552,28 @@ static void process_sharded_device(jt_ctx *c, const void *d_local, int64_t n_loc
     std::vector<jt_interval> iv((size_t)((double)total / rate / 0.25) + 16);
     int64_t n_iv = 0;
     Sig mono;                                             // the downmixed window (device), kept for the band graphs
+    GraphResume head2; bool have_head2 = false;
     {
         std::vector<char> blob;
         analyse_chunk_core(c, d_local, n_local, rate, channels, fmt, P.local_first, P.own_first, P.owned, total, blob, &mono);
         lap(T.pass1_chunk);
+        // the head of Pass 2 that no measurement can change (downmix, both biquads, anlmdn -- the heaviest kernel of the pass)
+        // runs on the window while the host exchanges and merges Pass 1 and derives the spec's adaptive tail
+        {
+            jt_measurements m0; memset(&m0, 0, sizeof(m0));
+            jt_voice_activity va0; memset(&va0, 0, sizeof(va0));
+            jt_filter_config cfg0; char spec0[2048];
+            std::string hs;
+            if (!adaptive) hs = pass2_static_head(PASS2_DEFAULT_SPEC);
+            else if (jt_adapt_config(base, &m0, &va0, &cfg0, nullptr) == JT_OK && jt_build_filter_spec(&cfg0, spec0, sizeof(spec0)) == JT_OK) hs = pass2_static_head(spec0);
+            if (!hs.empty()) { jt_graph_head(c, hs, d_local, n_local, rate, channels, fmt, 4096, head2); have_head2 = true; }
+        }
         std::vector<std::vector<char>> all = comm.allgather(blob);
         std::vector<const void *> ptrs; for (auto &b : all) if (!b.empty()) ptrs.push_back(b.data());
         rc = jt_analyse_merge((int)ptrs.size(), ptrs.data(), &an->measurements, iv.data(), (int64_t)iv.size(), &n_iv);
         if (rc) JT_THROW(rc, "Pass-1 merge");
         R.input = an->measurements;
-        lap(T.pass1_merge);
+        lap(T.pass1_merge, false);                        // (no device sync: Pass 2's head is running)
     }
     // ---- detector, band graphs over the elected regions (their samples gathered from the ranks that own them), AdaptConfig ----
     std::string spec2 = PASS2_DEFAULT_SPEC;
@@ -1576,6 +1594,10 @@ static void process_sharded_device(jt_ctx *c, const void *d_local, int64_t n_loc
             double lo_hz[17], hi_hz[17]; jt_band_plan(lo_hz, hi_hz);
             std::vector<char> send(17 * sizeof(double), 0);
             double *mine = (double *)send.data();
+            // (on the side stream: Pass 2's head occupies the main one; Pass 1's kernels, whose released blocks the arena may
+            //  hand out here, finished before the last lap)
+            std::unique_ptr<StreamSwap> swap;
+            if (have_head2 && c->side_stream) swap.reset(new StreamSwap(c, c->side_stream));
             for (int k = 0; k < 2; k++) {
                 const int64_t lo = std::max(ra[k], P.own_first), hi = std::min(rb[k], P.own_first + P.owned);
                 if (hi <= lo) continue;
@@ -1584,6 +1606,7 @@ static void process_sharded_device(jt_ctx *c, const void *d_local, int64_t n_loc
                 if (k == 0) jt_band_sumsq(c, part, lo - cs, lo_hz, hi_hz, 2, mine);
                 else jt_band_sumsq(c, part, lo - cs, lo_hz + 2, hi_hz + 2, 15, mine + 2);
             }
+            swap.reset();
             std::vector<std::vector<char>> all = comm.allgather(send);
             double rms[17] = {0}; int32_t found[17] = {0};
             for (int b = 0; b < 17; b++) {
@@ -1602,7 +1625,7 @@ static void process_sharded_device(jt_ctx *c, const void *d_local, int64_t n_loc
         if (rc) JT_THROW(rc, "BuildFilterSpec");
         spec2 = an->pass2_spec;
     } else copy_str(PASS2_DEFAULT_SPEC, an->pass2_spec, sizeof(an->pass2_spec));
-    lap(T.adapt);
+    lap(T.adapt, false);
 
     // the regions the reference re-measures on the Pass-2 and Pass-4 outputs (MeasureOutputRegions, analyser_output.go:261-297)
     auto measure_regions = [&](const Sig &own, int64_t own_first44, const Chunks &ck44, int64_t n44, jt_output_regions *o) {
@@ -1665,8 +1688,10 @@ static void process_sharded_device(jt_ctx *c, const void *d_local, int64_t n_loc
     {
         const size_t mark = c->allocs.size();
         std::vector<char> blob; int64_t of = 0, on = 0; int orate = 0, ofmt = 0;
+        const bool head_ok = have_head2 && spec2.compare(0, head2.head.size(), head2.head) == 0 &&
+                             (spec2.size() == head2.head.size() || spec2[head2.head.size()] == ',');
         graph_chunk_core(c, spec2.c_str(), d_local, n_local, rate, channels, fmt, P.local_first, P.own_first, P.owned, total, 4096,
-                         true, nullptr, 0, &own2, &of, &on, &orate, &ofmt, true, blob);
+                         true, nullptr, 0, &own2, &of, &on, &orate, &ofmt, true, blob, head_ok ? &head2 : nullptr);
         if (of != ck2.first[(size_t)rank] || on != ck2.owned[(size_t)rank]) JT_THROW(JT_ERR_INVALID_ARG, "internal: Pass-2 ownership (%lld+%lld vs %lld+%lld)", (long long)of, (long long)on, (long long)ck2.first[(size_t)rank], (long long)ck2.owned[(size_t)rank]);
         JT_CUDA(cudaStreamSynchronize(c->stream));
         jt_release_since(c, mark, nullptr);
