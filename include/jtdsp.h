@@ -451,6 +451,24 @@ int jt_process_audio_sharded_dev(jt_ctx *ctx, const void *d_pcm_local, int64_t n
                              int16_t *d_pcm_out, int64_t pcm_out_cap, int64_t *out_first, int64_t *n_out,
                              jt_process_result *res, jt_analysis *analysis, jt_shard_timing *timing);
 
+/* ---- the numbers of the per-file run record ---------------------------------------------------------------------
+ * The `schema_version`, `run`, `loudness`, `dynamics`, `spectral` and `noise` blocks of the reference's RunRecord
+ * (internal/processor/runrecord.go:24-100; tags analyser.go:140-199, 262-264, analyser_metrics.go:696-710) as the JSON text
+ * MarshalRunRecord writes (runrecord.go:425-433): keys sorted within every object, two-space indent, encoding/json float form,
+ * non-finite values as null -- so loudness.stages.{input,filtered,final}.{integrated_lufs,true_peak_dbtp,lra_lu} can be
+ * compared byte for byte with the reference's `.json`.  res = NULL renders an analysis-only record (input stages only, from
+ * analysis->measurements); analysis = NULL drops `noise`; run = NULL drops `run`.  `regions`, `filters`, `normalisation` and
+ * `interval_summary` serialise Go structs the caller already holds (jt_analysis / jt_process_result carry their values) and
+ * stay with the Go side.  *needed (may be NULL) receives the size the text takes, terminator included; JT_ERR_BUFFER when
+ * cap is short.  Host-only. */
+typedef struct jt_run_info {                 /* RunProvenance runrecord.go:53-61 */
+    const char *input_file, *version, *executable, *processed_at;
+    double duration_s; int32_t sample_rate_hz, channels;
+} jt_run_info;
+int jt_run_record_json(const jt_process_result *res, const jt_analysis *analysis, const jt_run_info *run, double target_i,
+                       char *buf, size_t cap, size_t *needed);
+int jt_go_json_float(double v, char *buf, size_t cap);        /* encoding/json's rendering of a float64 */
+
 /* RIFF / WAVE input (the reference's fixtures are s16 WAVs, testutil_test.go:140-190; it decodes through libavformat,
  * internal/audio/reader.go): locates the PCM of a file image in memory.  *sample_fmt is a JT_FMT_* value, the samples are
  * interleaved at bytes + *data_offset.  JT_ERR_UNSUPPORTED for 8 / 24 bit or compressed data and for RF64 / BW64 files.  A data
