@@ -489,6 +489,28 @@ int jt_flac_encode(jt_ctx *ctx, const int16_t *pcm, int64_t n_samples, int sampl
 int jt_flac_encode_dev(jt_ctx *ctx, const int16_t *d_pcm, int64_t n_samples, int sample_rate, int block_size,
                    void *d_out, int64_t out_cap, int64_t *n_bytes);
 
+/* ---- input-side containers: what the reference's audio.Reader (internal/audio/reader.go:29-188: libavformat demux +
+ * libavcodec decode) hands the passes, from a FILE IMAGE in memory ------------------------------------------------------------
+ * FLAC: interleaved s16 for streams of <= 16 bits per sample, interleaved s32 with the samples shifted up to fill 32 bits above
+ * (libavcodec flacdec.c); 4..24 bits, 1..8 channels, fixed or variable block size, every subframe type of RFC 9639 (CONSTANT,
+ * VERBATIM, FIXED, LPC up to order 32, 4 / 5 bit Rice parameters, escape partitions, wasted bits, left/side, side/right, mid/side).
+ * Frames are found by a parallel header scan and verified by their CRC-16 before they are decoded; a stream whose frames do
+ * not chain from the first one to the end of the buffer (truncated file, trailing tag) is JT_ERR_INVALID_ARG.
+ * jt_flac_stream_info is host-only (STREAMINFO: *n_frames is 0 when the encoder did not know the length; *sample_fmt as above).
+ * The decode entries write up to cap_frames frames to pcm_out (JT_ERR_BUFFER when the stream has more; *n_frames says how many). */
+int jt_flac_stream_info(const void *bytes, int64_t n_bytes, int *sample_fmt, int *sample_rate, int *channels, int *bits_per_sample,
+                        int64_t *n_frames, int64_t *audio_offset);
+int jt_flac_decode(jt_ctx *ctx, const void *bytes, int64_t n_bytes, void *pcm_out, int64_t cap_frames, int64_t *n_frames,
+                   int *sample_fmt, int *sample_rate, int *channels);
+int jt_flac_decode_dev(jt_ctx *ctx, const void *d_bytes, int64_t n_bytes, void *d_pcm_out, int64_t cap_frames, int64_t *n_frames,
+                   int *sample_fmt, int *sample_rate, int *channels);
+/* WAV (RIFF / WAVE, PCM 16 / 24 / 32 bit, IEEE float 32 / 64 bit): the samples as libavcodec's pcm_* decoders give them -- s16, s32
+ * (24-bit samples shifted up by 8), flt, dbl -- interleaved.  Same header rules as jt_wav_parse. */
+int jt_wav_decode(jt_ctx *ctx, const void *bytes, int64_t n_bytes, void *pcm_out, int64_t cap_frames, int64_t *n_frames,
+                  int *sample_fmt, int *sample_rate, int *channels);
+int jt_wav_decode_dev(jt_ctx *ctx, const void *d_bytes, int64_t n_bytes, void *d_pcm_out, int64_t cap_frames, int64_t *n_frames,
+                  int *sample_fmt, int *sample_rate, int *channels);
+
 /* the cudaStream_t (as void *) every kernel and copy of this context is issued on, so a caller can order its own
  * device work against it or bracket calls with CUDA events */
 void   *jt_cuda_stream(const jt_ctx *ctx);

@@ -1108,9 +1108,11 @@ static double go_seconds(int64_t ns) { return (double)(ns / 1000000000LL) + (dou
 
 // sample_a / sample_b >= 0: the region as an explicit sample range of the buffer (a buffer that starts on the stream's
 // decoder-frame grid: the sharded path, which assembles a region from the ranks that own its parts)
-static void region_measure_device(jt_ctx *c, const void *d_pcm, int64_t n_frames, int rate, int channels, int fmt,
-                                  int64_t start_ns, int64_t dur_ns, jt_region_sample *out, int64_t *frames_out,
-                                  int64_t sample_a = -1, int64_t sample_b = -1)
+// a region re-measure whose kernels are queued but whose host part has not run: lets ProcessAudio put all four of them behind
+// Pass 4 without the GPU waiting for the host in between
+struct RegionPending { GraphRun g; bool queued = false; };
+static void region_measure_enqueue(jt_ctx *c, const void *d_pcm, int64_t n_frames, int rate, int channels, int fmt,
+                                   int64_t start_ns, int64_t dur_ns, RegionPending &p, int64_t sample_a = -1, int64_t sample_b = -1)
 {
     char spec[512];
     if (sample_a >= 0) {
@@ -1123,9 +1125,14 @@ static void region_measure_device(jt_ctx *c, const void *d_pcm, int64_t n_frames
                                  "aspectralstats=measure=all,ebur128=metadata=1:peak=sample+true", go_seconds(start_ns), go_seconds(dur_ns));
     }
     const size_t mark = c->allocs.size();
-    GraphResult g;
-    jt_graph_run(c, spec, d_pcm, n_frames, rate, channels, fmt, 4096, false, true, g);
+    jt_graph_enqueue(c, spec, d_pcm, n_frames, rate, channels, fmt, 4096, false, true, p.g);
     jt_release_since(c, mark, nullptr);
+    p.queued = true;
+}
+static void region_measure_finish(jt_ctx *c, RegionPending &p, jt_region_sample *out, int64_t *frames_out)
+{
+    GraphResult g;
+    jt_graph_finish(c, p.g, g);
     double rms = 0, peak = 0, M = 0, S = 0, tp = 0, sp = 0, spec_sum[JT_SP_COUNT] = {0}; bool rms_found = false; int64_t spec_n = 0;
     for (const jt_frame_meta &f : g.meta) {
         if (!std::isnan(f.astats_overall_RMS_level)) { rms = f.astats_overall_RMS_level; rms_found = true; }
@@ -1148,6 +1155,14 @@ static void region_measure_device(jt_ctx *c, const void *d_pcm, int64_t n_frames
     r.momentary_lufs = M; r.short_term_lufs = S; r.true_peak = ratio_db(tp); r.sample_peak = ratio_db(sp);
     if (out) *out = r;
 }
+static void region_measure_device(jt_ctx *c, const void *d_pcm, int64_t n_frames, int rate, int channels, int fmt,
+                                  int64_t start_ns, int64_t dur_ns, jt_region_sample *out, int64_t *frames_out,
+                                  int64_t sample_a = -1, int64_t sample_b = -1)
+{
+    RegionPending p;
+    region_measure_enqueue(c, d_pcm, n_frames, rate, channels, fmt, start_ns, dur_ns, p, sample_a, sample_b);
+    region_measure_finish(c, p, out, frames_out);
+}
 
 extern "C" int jt_measure_output_region(jt_ctx *c, const void *pcm, int64_t n_frames, int rate, int channels, int fmt,
                                         int64_t start_ns, int64_t dur_ns, jt_region_sample *out, int64_t *frames)
@@ -1167,17 +1182,35 @@ extern "C" int jt_measure_output_region_dev(jt_ctx *c, const void *d_pcm, int64_
 
 // MeasureOutputRegions (analyser_output.go:261-297): the elected room-tone and speech regions of Pass 1 re-measured on a
 // pass's s16 output; a failing region is a warning, not an error (its sample stays absent)
-static void measure_output_regions(jt_ctx *c, const void *d_pcm, int64_t n, const jt_voice_activity &va, jt_output_regions *o)
+struct OutputRegionsPending { RegionPending room, speech; };
+static void measure_output_regions_enqueue(jt_ctx *c, const void *d_pcm, int64_t n, const jt_voice_activity &va, OutputRegionsPending &p)
 {
-    memset(o, 0, sizeof(*o));
     if (va.has_noise_profile) {
-        try { region_measure_device(c, d_pcm, n, 44100, 1, JT_FMT_S16, va.noise_profile.start_ns, va.noise_profile.duration_ns, &o->room_tone, nullptr); o->has_room_tone = 1; }
-        catch (const JtError &e) { if (e.code == JT_ERR_CUDA || e.code == JT_ERR_CANCELLED) throw; }
+        try { region_measure_enqueue(c, d_pcm, n, 44100, 1, JT_FMT_S16, va.noise_profile.start_ns, va.noise_profile.duration_ns, p.room); }
+        catch (const JtError &e) { p.room.queued = false; if (e.code == JT_ERR_CUDA || e.code == JT_ERR_CANCELLED) throw; }
     }
     if (va.has_speech_profile) {
-        try { region_measure_device(c, d_pcm, n, 44100, 1, JT_FMT_S16, va.speech_profile.region.start_ns, va.speech_profile.region.duration_ns, &o->speech, nullptr); o->has_speech = 1; }
+        try { region_measure_enqueue(c, d_pcm, n, 44100, 1, JT_FMT_S16, va.speech_profile.region.start_ns, va.speech_profile.region.duration_ns, p.speech); }
+        catch (const JtError &e) { p.speech.queued = false; if (e.code == JT_ERR_CUDA || e.code == JT_ERR_CANCELLED) throw; }
+    }
+}
+static void measure_output_regions_finish(jt_ctx *c, OutputRegionsPending &p, jt_output_regions *o)
+{
+    memset(o, 0, sizeof(*o));
+    if (p.room.queued) {
+        try { region_measure_finish(c, p.room, &o->room_tone, nullptr); o->has_room_tone = 1; }
         catch (const JtError &e) { if (e.code == JT_ERR_CUDA || e.code == JT_ERR_CANCELLED) throw; }
     }
+    if (p.speech.queued) {
+        try { region_measure_finish(c, p.speech, &o->speech, nullptr); o->has_speech = 1; }
+        catch (const JtError &e) { if (e.code == JT_ERR_CUDA || e.code == JT_ERR_CANCELLED) throw; }
+    }
+}
+static void measure_output_regions(jt_ctx *c, const void *d_pcm, int64_t n, const jt_voice_activity &va, jt_output_regions *o)
+{
+    OutputRegionsPending p;
+    measure_output_regions_enqueue(c, d_pcm, n, va, p);
+    measure_output_regions_finish(c, p, o);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1247,10 +1280,17 @@ static void process_device(jt_ctx *c, const void *d_in, int64_t n_frames, int ra
     GraphRun g4;
     jt_graph_enqueue(c, spec4, g2.out.d, g2.out.n, 44100, 1, JT_FMT_S16, 4096, true, true, g4);
     R.n_out = g4.out.n;
+    if (pcm_out && g4.out.n > cap) JT_THROW(JT_ERR_BUFFER, "pcm_out holds %lld samples, chain produced %lld", (long long)cap, (long long)g4.out.n);
+    // processor.go:150-160 and normalise.go's Pass-4 re-measure of the same regions: queued behind Pass 4 now, so the GPU goes
+    // straight on with them while the host is still assembling Pass 2's and Pass 4's metadata
+    OutputRegionsPending reg2, reg4;
+    if (an) {
+        measure_output_regions_enqueue(c, g2.out.d, g2.out.n, an->voice_activity, reg2);
+        measure_output_regions_enqueue(c, g4.out.d, g4.out.n, an->voice_activity, reg4);
+    }
     // Pass 2: host part (sink-frame records, accumulators), while the GPU runs Pass 4
     jt_graph_finish_acc(c, g2, &R.filtered, nullptr);
     if (pcm_out) {                                 // the result leaves while the host assembles Pass 4's metadata
-        if (g4.out.n > cap) JT_THROW(JT_ERR_BUFFER, "pcm_out holds %lld samples, chain produced %lld", (long long)cap, (long long)g4.out.n);
         const size_t ob = (size_t)g4.out.n * sizeof(int16_t);
         // the copy engine takes the result as soon as its last sample exists (ev_out), while the compute stream goes on
         // with Pass 4's analysis tail
@@ -1260,9 +1300,9 @@ static void process_device(jt_ctx *c, const void *d_in, int64_t n_frames, int ra
         } else if (ob) JT_CUDA(cudaMemcpyAsync(pcm_out, g4.out.d, ob, out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
     }
     jt_graph_finish_acc(c, g4, &R.final, &R.pass4);
-    if (an) {                                      // processor.go:150-160 and normalise.go's Pass-4 re-measure of the same regions
-        measure_output_regions(c, g2.out.d, g2.out.n, an->voice_activity, &an->filtered_regions);
-        measure_output_regions(c, g4.out.d, g4.out.n, an->voice_activity, &an->final_regions);
+    if (an) {
+        measure_output_regions_finish(c, reg2, &an->filtered_regions);
+        measure_output_regions_finish(c, reg4, &an->final_regions);
     }
     JT_CUDA(cudaStreamSynchronize(c->stream));
     JT_CUDA(cudaStreamSynchronize(c->copy_stream));
@@ -1891,4 +1931,86 @@ extern "C" int jt_flac_encode(jt_ctx *c, const int16_t *pcm, int64_t n, int rate
 extern "C" int jt_flac_encode_dev(jt_ctx *c, const int16_t *d_pcm, int64_t n, int rate, int block_size, void *d_out, int64_t cap, int64_t *n_bytes)
 {
     return flac_common(c, d_pcm, true, n, rate, block_size, d_out, cap, n_bytes);
+}
+
+// ---------------------------------------------------------------------------------------
+// Input-side containers (audio.Reader: internal/audio/reader.go:29-188): FLAC and WAV file images -> interleaved PCM
+// ---------------------------------------------------------------------------------------
+extern "C" int jt_flac_stream_info(const void *bytes, int64_t n_bytes, int *sample_fmt, int *sample_rate, int *channels, int *bits_per_sample,
+                                   int64_t *n_frames, int64_t *audio_offset)
+{
+    if (!bytes || n_bytes < 0) return JT_ERR_INVALID_ARG;
+    try { jt_flac_info_host(bytes, n_bytes, sample_fmt, sample_rate, channels, bits_per_sample, n_frames, audio_offset); }
+    catch (const JtError &e) { return e.code; }
+    return JT_OK;
+}
+static int flac_decode_common(jt_ctx *c, const void *bytes, bool on_device, int64_t n_bytes, void *out, int64_t cap_frames, int64_t *n_frames,
+                              int *sample_fmt, int *sample_rate, int *channels)
+{
+    return guarded(c, [&]() {
+        if (!bytes || !out || n_bytes < 0 || cap_frames < 0) JT_THROW(JT_ERR_INVALID_ARG, "null argument");
+        const uint8_t *d_in = on_device ? (const uint8_t *)bytes : (const uint8_t *)upload(c, bytes, (size_t)n_bytes);
+        int fmt = 0, rate = 0, ch = 0; int64_t frames = 0;
+        void *d = jt_flac_decode_device(c, d_in, n_bytes, &fmt, &rate, &ch, &frames);
+        if (n_frames) *n_frames = frames; if (sample_fmt) *sample_fmt = fmt; if (sample_rate) *sample_rate = rate; if (channels) *channels = ch;
+        if (frames > cap_frames) JT_THROW(JT_ERR_BUFFER, "out holds %lld frames, the stream has %lld", (long long)cap_frames, (long long)frames);
+        const size_t bytes_out = (size_t)frames * ch * jt_fmt_bytes(fmt);
+        if (on_device) JT_CUDA(cudaMemcpyAsync(out, d, bytes_out, cudaMemcpyDeviceToDevice, c->stream));
+        else download(c, out, d, bytes_out);
+    });
+}
+extern "C" int jt_flac_decode(jt_ctx *c, const void *bytes, int64_t n_bytes, void *pcm_out, int64_t cap_frames, int64_t *n_frames,
+                              int *sample_fmt, int *sample_rate, int *channels)
+{
+    return flac_decode_common(c, bytes, false, n_bytes, pcm_out, cap_frames, n_frames, sample_fmt, sample_rate, channels);
+}
+extern "C" int jt_flac_decode_dev(jt_ctx *c, const void *d_bytes, int64_t n_bytes, void *d_pcm_out, int64_t cap_frames, int64_t *n_frames,
+                                  int *sample_fmt, int *sample_rate, int *channels)
+{
+    return flac_decode_common(c, d_bytes, true, n_bytes, d_pcm_out, cap_frames, n_frames, sample_fmt, sample_rate, channels);
+}
+
+// WAV: what libavformat's wav demuxer + libavcodec's pcm_* decoders hand the reference: s16 / s32 (24-bit samples shifted up by 8) /
+// flt / dbl, interleaved.  The header is walked on the host (jt_wav_walk), the samples are copied / unpacked on the device.
+int jt_wav_walk(const void *bytes, int64_t n_readable, int64_t n_total, int *sample_fmt, int *sample_rate, int *channels, int *bits_per_sample,
+                int64_t *data_offset, int64_t *n_frames);                       // jt_wav.cu
+static int wav_decode_common(jt_ctx *c, const void *bytes, bool on_device, int64_t n_bytes, void *out, bool out_on_device, int64_t cap_frames,
+                             int64_t *n_frames, int *sample_fmt, int *sample_rate, int *channels)
+{
+    return guarded(c, [&]() {
+        if (!bytes || !out || n_bytes < 0 || cap_frames < 0) JT_THROW(JT_ERR_INVALID_ARG, "null argument");
+        // the header chunks sit in the first bytes of the file; 1 MB covers any LIST / bext / iXML block in front of "data"
+        std::vector<uint8_t> head;
+        const uint8_t *h = (const uint8_t *)bytes;
+        int64_t n_head = n_bytes;
+        if (on_device) {
+            n_head = std::min<int64_t>(n_bytes, 1 << 20);
+            head.resize((size_t)n_head);
+            JT_CUDA(cudaMemcpyAsync(head.data(), bytes, (size_t)n_head, cudaMemcpyDeviceToHost, c->stream));
+            JT_CUDA(cudaStreamSynchronize(c->stream));
+            h = head.data();
+        }
+        int fmt = 0, rate = 0, ch = 0, bits = 0; int64_t off = 0, frames = 0;
+        const int rc = jt_wav_walk(h, n_head, n_bytes, &fmt, &rate, &ch, &bits, &off, &frames);
+        if (rc != JT_OK) JT_THROW(rc, "WAV header not understood (%s)", rc == JT_ERR_UNSUPPORTED ? "unsupported sample format, RF64, or no data chunk in the first MB" : "malformed");
+        if (n_frames) *n_frames = frames; if (sample_fmt) *sample_fmt = fmt; if (sample_rate) *sample_rate = rate; if (channels) *channels = ch;
+        if (frames > cap_frames) JT_THROW(JT_ERR_BUFFER, "out holds %lld frames, the file has %lld", (long long)cap_frames, (long long)frames);
+        const int64_t n_samples = frames * ch;
+        const size_t in_bytes = (size_t)n_samples * (bits / 8), out_bytes = (size_t)n_samples * jt_fmt_bytes(fmt);
+        const uint8_t *d_in = on_device ? (const uint8_t *)bytes + off : (const uint8_t *)upload(c, (const uint8_t *)bytes + off, in_bytes);
+        void *d_res = out_on_device ? out : jt_dalloc_bytes(c, out_bytes + 16);
+        if (bits == 24) jt_unpack_s24(c, d_in, n_samples, (int32_t *)d_res);
+        else JT_CUDA(cudaMemcpyAsync(d_res, d_in, out_bytes, cudaMemcpyDeviceToDevice, c->stream));
+        if (!out_on_device) download(c, out, d_res, out_bytes);
+    });
+}
+extern "C" int jt_wav_decode(jt_ctx *c, const void *bytes, int64_t n_bytes, void *pcm_out, int64_t cap_frames, int64_t *n_frames,
+                             int *sample_fmt, int *sample_rate, int *channels)
+{
+    return wav_decode_common(c, bytes, false, n_bytes, pcm_out, false, cap_frames, n_frames, sample_fmt, sample_rate, channels);
+}
+extern "C" int jt_wav_decode_dev(jt_ctx *c, const void *d_bytes, int64_t n_bytes, void *d_pcm_out, int64_t cap_frames, int64_t *n_frames,
+                                 int *sample_fmt, int *sample_rate, int *channels)
+{
+    return wav_decode_common(c, d_bytes, true, n_bytes, d_pcm_out, true, cap_frames, n_frames, sample_fmt, sample_rate, channels);
 }

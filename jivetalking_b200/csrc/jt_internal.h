@@ -196,6 +196,11 @@ void jt_band_sumsq(jt_ctx *c, const Sig &in, int64_t acc_from, const double *lo,
 // ---- k_flac.cu ------------------------------------------------------------------------------
 int64_t jt_flac_bound(int64_t n, int block_size);
 void *jt_flac_encode_device(jt_ctx *c, const int16_t *d_pcm, int64_t n, int rate, int block_size, int64_t *n_bytes);
+// ---- k_flac_dec.cu: the input side (audio.Reader) ---------------------------------------------
+void jt_flac_info_host(const void *bytes, int64_t n_bytes, int *fmt, int *rate, int *channels, int *bps, int64_t *total, int64_t *audio_off);
+void *jt_flac_decode_device(jt_ctx *c, const uint8_t *d_bytes, int64_t n_bytes, int *fmt, int *rate, int *channels, int64_t *n_frames);
+// packed little-endian 24-bit PCM -> s32 (<< 8), as libavcodec's pcm_s24le decoder
+void jt_unpack_s24(jt_ctx *c, const uint8_t *d_bytes, int64_t n_samples, int32_t *d_out);
 
 // ---- k_anlmdn.cu / k_afftdn.cu ------------------------------------------------------------
 Sig  jt_anlmdn(jt_ctx *c, const Sig &in_flt, double strength, double patch_s, double research_s, double smooth);

@@ -367,6 +367,38 @@ void jt_raw_frame_stats(jt_ctx *c, const void *d_in, int64_t n_frames, int chann
 }
 
 // ---------------------------------------------------------------------------------------
+// packed little-endian 24-bit PCM -> s32 with the sample in the top 24 bits (libavcodec pcm.c, pcm_s24le).  Four samples
+// (12 bytes, three aligned words when the source is 4-byte aligned) per thread.
+// ---------------------------------------------------------------------------------------
+__global__ void k_unpack_s24(const uint8_t *__restrict__ in, int64_t n, int32_t *__restrict__ out)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const bool aligned = (((uintptr_t)in) & 3) == 0;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q * 4 < n; q += stride) {
+        const int64_t i = q * 4;
+        if (aligned && i + 4 <= n) {
+            const uint32_t *w = (const uint32_t *)(in + i * 3);
+            const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+            out[i] = (int32_t)(w0 << 8);
+            out[i + 1] = (int32_t)((w0 >> 24) << 8 | (w1 << 16));
+            out[i + 2] = (int32_t)((w1 >> 16) << 8 | (w2 << 24));
+            out[i + 3] = (int32_t)(w2 & 0xFFFFFF00u);
+        } else {
+            for (int64_t k = i; k < n && k < i + 4; k++) {
+                const uint8_t *p = in + k * 3;
+                out[k] = (int32_t)(((uint32_t)p[0] << 8) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 24));
+            }
+        }
+    }
+}
+void jt_unpack_s24(jt_ctx *c, const uint8_t *d_bytes, int64_t n_samples, int32_t *d_out)
+{
+    if (n_samples <= 0) return;
+    JtLaunch L(c, "wav_decode:s24");
+    k_unpack_s24<<<jt_grid_for((n_samples + 3) / 4, 256, c->num_sms, 16), 256, 0, c->stream>>>(d_bytes, n_samples, d_out);
+}
+
+// ---------------------------------------------------------------------------------------
 // volume (af_volume.c, precision=float: fltp * (float)volume) and loudnorm's linear gain
 // ---------------------------------------------------------------------------------------
 __global__ void k_scale_f32(const float *__restrict__ in, float *__restrict__ out, int64_t n, float g)
@@ -439,4 +471,39 @@ void jt_smem_optin(const void *kernel, size_t bytes)
     if (bytes <= have) return;
     JT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     have = bytes;
+}
+
+// ---------------------------------------------------------------------------------------
+// tensor map of a stream seen as rows of `seg` elements (jt_tiles.cuh).  cuTensorMapEncodeTiled is a driver entry point;
+// it is looked up through the runtime so the library keeps linking against cudart only.
+// ---------------------------------------------------------------------------------------
+#include "jt_tiles.cuh"
+#include <mutex>
+typedef CUresult (*jt_encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                       const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                       CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static jt_encode_tiled_fn jt_encode_tiled()
+{
+    static jt_encode_tiled_fn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *p = nullptr; cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = (jt_encode_tiled_fn)p;
+        cudaGetLastError();
+    });
+    return fn;
+}
+bool jt_lane_tensor_map(CUtensorMap *map, const void *base, int elem_bytes, int64_t n, int64_t seg, int lines_per_tile)
+{
+    jt_encode_tiled_fn enc = jt_encode_tiled();
+    const int64_t rows = seg > 0 ? n / seg : 0;
+    const int epl = 128 / elem_bytes;
+    if (!enc || rows < 1 || rows > 0x7FFFFFFFll || (((uintptr_t)base) & 15) || seg % epl || (seg * elem_bytes) % 16 || lines_per_tile < 1 || lines_per_tile > 256) return false;
+    const CUtensorMapDataType dt = elem_bytes == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_UINT16;
+    const cuuint64_t dims[3] = {(cuuint64_t)epl, (cuuint64_t)rows, (cuuint64_t)(seg / epl)};
+    const cuuint64_t strides[2] = {(cuuint64_t)seg * elem_bytes, 128};
+    const cuuint32_t box[3] = {(cuuint32_t)epl, 32, (cuuint32_t)lines_per_tile};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return enc(map, dt, 3, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }

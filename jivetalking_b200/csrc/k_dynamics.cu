@@ -12,6 +12,8 @@
 #include "jt_internal.h"
 #include "jt_device.cuh"
 #include "jt_lanes.cuh"
+#include "jt_tiles.cuh"
+#include <cstdlib>
 
 #define FAKE_INFINITY (65536.0 * 65536.0)
 
@@ -84,6 +86,110 @@ k_envelope(const double *__restrict__ x, double *__restrict__ env, int64_t n, in
     out.finish();
 }
 
+// ---- the same follower on tensor-map tiles (jt_tiles.cuh) ------------------------------------------------------------------
+// One warp per CTA, 32 samples per lane per tile (two 128-byte lines), a 4-deep ring in, two tiles out: 49 KB per warp, four
+// warps per SM -- one per scheduler, which is what the FP64 pipe can feed (5 DP instructions per sample, 2 issue cycles each).
+// The update runs in the form  e' = fma(e, 1 - c, c * d)  with both branches evaluated: the products c * d do not depend on
+// the state, so the carried chain is ONE fma plus the select, and the branch condition d > e is taken on the bit patterns
+// (both are non-negative, so they order like integers) on the integer pipe, in the shadow of the fma.  Against the scalar
+// C form  e + (d - e) * c  the result differs in the last place per step; the follower is a contraction, so the differences
+// do not accumulate beyond ~1e-16 / min(c) relative (2.6e-13 at 200 ms release), far inside the 1e-12 the gain stages are
+// tested to.
+#ifndef ENVT_CH
+#define ENVT_CH 4
+#endif
+#ifndef ENVT_NS
+#define ENVT_NS 3
+#endif
+typedef LaneTileIn<double, ENVT_CH, ENVT_NS> EnvTIn;
+typedef LaneTileOut<double, ENVT_CH> EnvTOut;
+#define ENVT_SMEM (EnvTIn::WARP_BYTES + EnvTOut::WARP_BYTES + 128 + 1024)      // tiles in, tiles out, barriers, alignment slack
+
+template <int RMS, bool EMIT>
+__device__ __forceinline__ double envt_tile(const unsigned char *t, unsigned char *ot, int lane, double e, double ca, double cr, double ka, double kr)
+{
+#pragma unroll
+    for (int line = 0; line < ENVT_CH; line++) {
+        double2 v[8];
+#pragma unroll
+        for (int ch = 0; ch < 8; ch++) v[ch] = *(const double2 *)(t + jt_tile_off(line, lane, ch));
+#pragma unroll
+        for (int ch = 0; ch < 8; ch++) {
+            const double d0 = RMS ? v[ch].x * v[ch].x : fabs(v[ch].x), d1 = RMS ? v[ch].y * v[ch].y : fabs(v[ch].y);
+            const double ad0 = ca * d0, rd0 = cr * d0, ad1 = ca * d1, rd1 = cr * d1;
+            const double ea0 = fma(e, ka, ad0), er0 = fma(e, kr, rd0);
+            e = __double_as_longlong(d0) > __double_as_longlong(e) ? ea0 : er0;
+            v[ch].x = e;
+            const double ea1 = fma(e, ka, ad1), er1 = fma(e, kr, rd1);
+            e = __double_as_longlong(d1) > __double_as_longlong(e) ? ea1 : er1;
+            v[ch].y = e;
+        }
+        if (EMIT) {
+#pragma unroll
+            for (int ch = 0; ch < 8; ch++) *(double2 *)(ot + jt_tile_off(line, lane, ch)) = v[ch];
+        }
+    }
+    return e;
+}
+
+template <int RMS>
+__global__ void __launch_bounds__(32)
+k_envelope_tiles(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map, const double *__restrict__ x,
+                 double *__restrict__ env, int64_t n, int64_t seg, int64_t warm, int64_t rows_full, double attack_coeff, double release_coeff)
+{
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int lane = threadIdx.x & 31;
+    const int64_t row0 = (int64_t)blockIdx.x * 32;
+    EnvTIn in; EnvTOut out;
+    in.init(smem, (uint64_t *)(smem + EnvTIn::WARP_BYTES + EnvTOut::WARP_BYTES), &in_map, x, n, seg, warm, row0, rows_full);
+    out.init(smem + EnvTIn::WARP_BYTES, &out_map, env, n, seg, row0, rows_full);
+    const double ka = 1.0 - attack_coeff, kr = 1.0 - release_coeff;
+    double e = 0.0;
+    in.prime();
+    int tile = 0;
+    for (; tile < in.own_tile0; tile++) {                                   // warm-up: nothing is stored
+        in.prefetch();
+        const unsigned char *t = in.wait(tile);
+        e = envt_tile<RMS, false>(t, nullptr, lane, e, attack_coeff, release_coeff, ka, kr);
+        in.release();
+    }
+    for (; tile < in.ntiles; tile++) {
+        in.prefetch();
+        const unsigned char *t = in.wait(tile);
+        e = envt_tile<RMS, true>(t, out.tile(), lane, e, attack_coeff, release_coeff, ka, kr);
+        in.release();
+        out.commit();
+    }
+    out.finish();
+}
+
+static bool run_envelope_tiles(jt_ctx *c, const Sig &in, double *env, double ac, double rc, int64_t warm, int rms)
+{
+    static const char *off = getenv("JT_NO_TILES");
+    if (off && *off == '1') return false;
+    const int R = EnvTIn::R;
+    warm = (warm + R - 1) / R * R;                          // tiles are all warm-up or all output
+    // segment: long enough that the warm-up re-read (warm / seg) does not make the pass HBM bound, short enough to fill the SMs
+    static const char *seg_env = getenv("JT_ENV_SEG");
+    const int64_t slots = (int64_t)c->num_sms * (int64_t)((227 * 1024) / (ENVT_SMEM + 1024)) * 32;      // lanes of one wave
+    int64_t seg = std::max<int64_t>(seg_env ? atoll(seg_env) : 16384, (in.n + slots - 1) / slots);
+    seg = std::min<int64_t>((seg + 127) / 128 * 128, 1 << 22);
+    if (in.n < 2 * seg || seg % R) return false;
+    CUtensorMap mi, mo;
+    if (!jt_lane_tensor_map(&mi, in.d, 8, in.n, seg, ENVT_CH) || !jt_lane_tensor_map(&mo, env, 8, in.n, seg, ENVT_CH)) return false;
+    const int64_t lanes = (in.n + seg - 1) / seg;
+    JtLaunch L(c, "envelope_follower");
+    if (rms) {
+        jt_smem_optin((const void *)k_envelope_tiles<1>, ENVT_SMEM);
+        k_envelope_tiles<1><<<(int)((lanes + 31) / 32), 32, ENVT_SMEM, c->stream>>>(mi, mo, (const double *)in.d, env, in.n, seg, warm, in.n / seg, ac, rc);
+    } else {
+        jt_smem_optin((const void *)k_envelope_tiles<0>, ENVT_SMEM);
+        k_envelope_tiles<0><<<(int)((lanes + 31) / 32), 32, ENVT_SMEM, c->stream>>>(mi, mo, (const double *)in.d, env, in.n, seg, warm, in.n / seg, ac, rc);
+    }
+    return true;
+}
+
 static double *run_envelope(jt_ctx *c, const Sig &in, double attack_ms, double release_ms, int rms)
 {
     const double ac = std::fmin(1., 1. / (attack_ms * in.rate / 4000.)), rc = std::fmin(1., 1. / (release_ms * in.rate / 4000.));
@@ -91,6 +197,7 @@ static double *run_envelope(jt_ctx *c, const Sig &in, double attack_ms, double r
     const double cmin = std::fmin(ac, rc);
     int64_t warm = cmin >= 1.0 ? 1 : (int64_t)std::ceil(37.0 / -std::log1p(-cmin)) + 16;
     if (warm > (1 << 22)) warm = 1 << 22;
+    if (run_envelope_tiles(c, in, env, ac, rc, warm, rms)) return env;
     warm = (warm + ENV_R - 1) / ENV_R * ENV_R;                 // tile-aligned (see the kernel)
     // Every lane re-reads `warm` samples before its segment (37 release time constants, ~89k samples at
     // 200 ms / 48 kHz), so short segments multiply the HBM traffic while long ones leave the GPU to a handful

@@ -152,6 +152,10 @@ def lib():
     fl = [_P, _P, _I64, _INT, _INT, _P, _I64, C.POINTER(_I64)]
     L.jt_flac_encode.argtypes = fl
     L.jt_flac_encode_dev.argtypes = fl
+    L.jt_flac_stream_info.argtypes = [_P, _I64, C.POINTER(_INT), C.POINTER(_INT), C.POINTER(_INT), C.POINTER(_INT), C.POINTER(_I64), C.POINTER(_I64)]
+    dec = [_P, _P, _I64, _P, _I64, C.POINTER(_I64), C.POINTER(_INT), C.POINTER(_INT), C.POINTER(_INT)]
+    for name in ("jt_flac_decode", "jt_flac_decode_dev", "jt_wav_decode", "jt_wav_decode_dev"):
+        getattr(L, name).argtypes = dec
     L.jt_cuda_stream.restype = _P
     L.jt_cuda_stream.argtypes = [_P]
     L.jt_launch_count.restype = _I64
@@ -174,6 +178,16 @@ def wav_parse(data):
     dt = _NP_OF_FMT[fmt.value]
     n = nfr.value * ch.value
     return np.frombuffer(data, dtype=dt, count=n, offset=off.value), rate.value, ch.value
+
+
+def flac_stream_info(data):
+    """STREAMINFO of a FLAC file image: dict(fmt, rate, channels, bits, n_frames, audio_offset); host only."""
+    buf = np.frombuffer(data, dtype=np.uint8)
+    fmt, rate, ch, bits, nfr, off = _INT(0), _INT(0), _INT(0), _INT(0), _I64(0), _I64(0)
+    rc = lib().jt_flac_stream_info(buf.ctypes.data_as(_P), len(buf), C.byref(fmt), C.byref(rate), C.byref(ch), C.byref(bits), C.byref(nfr), C.byref(off))
+    if rc != 0:
+        raise JtError(rc, "jt_flac_stream_info")
+    return dict(fmt=fmt.value, rate=rate.value, channels=ch.value, bits=bits.value, n_frames=nfr.value, audio_offset=off.value)
 
 
 def pass1_spec():
@@ -386,6 +400,32 @@ class Context:
         nb = _I64(0)
         self._check(lib().jt_flac_encode(self._h, pcm.ctypes.data_as(_P), len(pcm), rate, block_size, out.ctypes.data_as(_P), cap, C.byref(nb)))
         return out[: nb.value].tobytes()
+
+    def _decode(self, fn, data, cap_frames, max_channels=8):
+        buf = np.frombuffer(data, dtype=np.uint8)
+        out = np.zeros(max(1, cap_frames * max_channels), dtype=np.int64)          # room for any format
+        nfr, fmt, rate, ch = _I64(0), _INT(0), _INT(0), _INT(0)
+        self._check(fn(self._h, buf.ctypes.data_as(_P), len(buf), out.ctypes.data_as(_P), cap_frames, C.byref(nfr), C.byref(fmt), C.byref(rate), C.byref(ch)))
+        pcm = np.frombuffer(out.tobytes(), dtype=_NP_OF_FMT[fmt.value], count=nfr.value * ch.value).copy()
+        return pcm, fmt.value, rate.value, ch.value
+
+    def flac_decode(self, data, cap_frames=None):
+        """FLAC file image (bytes) -> (interleaved samples as libavcodec gives them, JT_FMT_*, rate, channels); reader.go:29-188."""
+        if cap_frames is None:
+            info = flac_stream_info(data)
+            cap_frames = info["n_frames"] if info["n_frames"] else len(data) * 8
+            return self._decode(lib().jt_flac_decode, data, cap_frames, info["channels"])
+        return self._decode(lib().jt_flac_decode, data, cap_frames)
+
+    def wav_decode(self, data):
+        """RIFF/WAVE file image -> (interleaved samples, JT_FMT_*, rate, channels), 24-bit PCM included (as s32 << 8)."""
+        return self._decode(lib().jt_wav_decode, data, len(data), 1)
+
+    def decode_ptr(self, kind, in_ptr, n_bytes, out_ptr, cap_frames, on_device):
+        fn = getattr(lib(), "jt_%s_decode%s" % (kind, "_dev" if on_device else ""))
+        nfr, fmt, rate, ch = _I64(0), _INT(0), _INT(0), _INT(0)
+        self._check(fn(self._h, _P(in_ptr), n_bytes, _P(out_ptr), cap_frames, C.byref(nfr), C.byref(fmt), C.byref(rate), C.byref(ch)))
+        return nfr.value, fmt.value, rate.value, ch.value
 
     def flac_encode_ptr(self, in_ptr, n, rate, block_size, out_ptr, out_cap, on_device):
         nb = _I64(0)

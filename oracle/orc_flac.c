@@ -11,6 +11,11 @@
  *                        when that is not smaller than 16 bits per sample.  STREAMINFO carries min / max frame size, the
  *                        sample count and an all-zero MD5 ("not known").
  *  orc_flac_decode_s16   independent decoder of the subset above (plus LPC subframes, for streams of other encoders).
+ *  orc_flac_decode_pcm   the INPUT side (internal/audio/reader.go:29-188: libavformat flac demuxer + libavcodec flacdec.c): any
+ *                        stream of RFC 9639 with 1..8 channels and 4..24 bits -- stereo decorrelation, wasted bits, variable
+ *                        block size -- as interleaved int32 in the decoder's output scale (s16 streams: value << (16 - bps);
+ *                        wider: value << (32 - bps), flacdec.c's sample_shift).  Checker of csrc/k_flac_dec.cu; pinned on the real
+ *                        libavformat + libavcodec reader (oracle/ref_wav_probe.c) in tests/test_oracle_flac.py.
  *
  * Pinned: tests/test_oracle_flac.py decodes the encoder's streams with the REAL FFmpeg 8.0.1 libavcodec FLAC decoder found in
  * this image (oracle/ref_flac.py) and requires the PCM back bit for bit; the decoder is pinned by decoding the same streams.
@@ -278,6 +283,116 @@ int64_t orc_flac_decode_s16(const uint8_t *in, int64_t nbytes, int16_t *out, int
         const uint16_t c16 = (uint16_t)br_get(&r, 16);
         if (r.err || crc16(in + f0, f1 - f0) != c16) { free(buf); return -3; }
         for (int i = 0; i < bs; i++) { if (pos >= cap) { free(buf); return -1; } out[pos++] = (int16_t)(buf[i] * (1 << wasted)); }
+    }
+    free(buf);
+    return (total && pos != total) ? -4 : pos;
+}
+
+/* ---- general decoder (input side) ---- */
+static int dec_subframe(BR *r, int32_t *buf, int bs, int bps_sub)
+{
+    if (br_get(r, 1)) return -4;
+    const int type = (int)br_get(r, 6); int wasted = 0;
+    if (br_get(r, 1)) wasted = (int)br_unary(r) + 1;
+    const int sb = bps_sub - wasted;
+    if (sb < 1 || sb > 32) return -4;
+    if (type == 0) { const int32_t v = br_sget(r, sb); for (int i = 0; i < bs; i++) buf[i] = v; }
+    else if (type == 1) { for (int i = 0; i < bs; i++) buf[i] = br_sget(r, sb); }
+    else if ((type >= 8 && type <= 12) || type >= 32) {
+        const int lpc = type >= 32, order = lpc ? (type & 31) + 1 : type & 7;
+        int32_t coef[32]; int shift = 0;
+        if (order > bs) return -4;
+        for (int i = 0; i < order; i++) buf[i] = br_sget(r, sb);
+        if (lpc) {
+            const int prec = (int)br_get(r, 4) + 1; if (prec == 16) return -4;
+            shift = br_sget(r, 5); if (shift < 0) return -4;
+            for (int i = 0; i < order; i++) coef[i] = br_sget(r, prec);
+        }
+        const int method = (int)br_get(r, 2), porder = (int)br_get(r, 4), plen = method ? 5 : 4, esc = method ? 31 : 15;
+        if (method > 1 || (bs >> porder) < order || ((bs >> porder) << porder) != bs) return -4;
+        int i = order;
+        for (int j = 0; j < (1 << porder); j++) {
+            const int cnt = (bs >> porder) - (j == 0 ? order : 0), k = (int)br_get(r, plen);
+            if (k == esc) { const int nb = (int)br_get(r, 5); for (int t = 0; t < cnt; t++) buf[i++] = nb ? br_sget(r, nb) : 0; }
+            else for (int t = 0; t < cnt; t++) { const uint32_t q = br_unary(r); const uint32_t u = (q << k) | (uint32_t)br_get(r, k); buf[i++] = (int32_t)(u >> 1) ^ -(int32_t)(u & 1); }
+            if (r->err) return -4;
+        }
+        for (i = order; i < bs; i++) {
+            int64_t pred;
+            if (lpc) { pred = 0; for (int t = 0; t < order; t++) pred += (int64_t)coef[t] * buf[i - 1 - t]; pred >>= shift; }
+            else switch (order) {
+                case 0: pred = 0; break; case 1: pred = buf[i - 1]; break; case 2: pred = 2ll * buf[i - 1] - buf[i - 2]; break;
+                case 3: pred = 3ll * buf[i - 1] - 3ll * buf[i - 2] + buf[i - 3]; break;
+                default: pred = 4ll * buf[i - 1] - 6ll * buf[i - 2] + 4ll * buf[i - 3] - buf[i - 4];
+            }
+            buf[i] = (int32_t)(buf[i] + pred);
+        }
+    } else return -4;
+    if (wasted) for (int i = 0; i < bs; i++) buf[i] = (int32_t)((uint32_t)buf[i] << wasted);
+    return r->err ? -4 : 0;
+}
+
+/* returns FRAMES decoded (out: interleaved int32, cap frames), negative on a malformed stream: -2 CRC-8, -3 CRC-16, -4 syntax, -1 cap */
+int64_t orc_flac_decode_pcm(const uint8_t *in, int64_t nbytes, int32_t *out, int64_t cap, int *rate_out, int *channels_out, int *bps_out)
+{
+    int64_t start = 0;
+    if (nbytes >= 10 && !memcmp(in, "ID3", 3)) start = 10 + (((int64_t)(in[6] & 0x7F) << 21) | ((in[7] & 0x7F) << 14) | ((in[8] & 0x7F) << 7) | (in[9] & 0x7F));
+    if (nbytes < start + 42 || memcmp(in + start, "fLaC", 4)) return -4;
+    BR r = {in, nbytes, (start + 4) * 8, 0};
+    int last = 0, rate = 0, bps = 16, ch = 1; int64_t total = 0;
+    while (!last) {
+        last = (int)br_get(&r, 1); const int type = (int)br_get(&r, 7); const int len = (int)br_get(&r, 24);
+        if (type == 0) {
+            br_get(&r, 16); br_get(&r, 16); br_get(&r, 24); br_get(&r, 24);
+            rate = (int)br_get(&r, 20); ch = (int)br_get(&r, 3) + 1; bps = (int)br_get(&r, 5) + 1; total = (int64_t)br_get(&r, 36);
+            r.bit += 128;
+        } else r.bit += 8ll * len;
+        if (r.err) return -4;
+    }
+    if (bps > 24 || bps < 4) return -4;
+    if (rate_out) *rate_out = rate;
+    if (channels_out) *channels_out = ch;
+    if (bps_out) *bps_out = bps;
+    const int out_shift = (bps <= 16 ? 16 : 32) - bps;
+    int64_t pos = 0; int32_t *buf = (int32_t *)malloc(sizeof(int32_t) * 65536 * 8);
+    while ((r.bit >> 3) < nbytes) {
+        const int64_t f0 = r.bit >> 3;
+        if (br_get(&r, 14) != 0x3FFE) { free(buf); return -4; }
+        br_get(&r, 2);
+        const int bsc = (int)br_get(&r, 4), src = (int)br_get(&r, 4), chc = (int)br_get(&r, 4), szc = (int)br_get(&r, 3);
+        br_get(&r, 1);
+        if (chc >= 11 || (chc < 8 ? chc + 1 : 2) != ch) { free(buf); return -4; }
+        (void)szc;
+        int b0 = (int)br_get(&r, 8), extra = 0;
+        if (b0 >= 0xC0) { int m = 0x20; extra = 1; while (b0 & m) { extra++; m >>= 1; } }
+        for (int i = 0; i < extra; i++) br_get(&r, 8);
+        int bs;
+        if (bsc == 6) bs = (int)br_get(&r, 8) + 1; else if (bsc == 7) bs = (int)br_get(&r, 16) + 1;
+        else if (bsc == 1) bs = 192; else if (bsc >= 2 && bsc <= 5) bs = 576 << (bsc - 2); else if (bsc >= 8) bs = 256 << (bsc - 8); else { free(buf); return -4; }
+        if (src == 12) br_get(&r, 8); else if (src == 13 || src == 14) br_get(&r, 16);
+        const uint8_t c8 = (uint8_t)br_get(&r, 8);
+        if (r.err || crc8(in + f0, (r.bit >> 3) - 1 - f0) != c8) { free(buf); return -2; }
+        for (int c = 0; c < ch; c++) {
+            const int side = (chc == 8 && c == 1) || (chc == 9 && c == 0) || (chc == 10 && c == 1);
+            const int rc = dec_subframe(&r, buf + (size_t)c * 65536, bs, bps + side);
+            if (rc) { free(buf); return rc; }
+        }
+        if (r.bit & 7) r.bit += 8 - (r.bit & 7);
+        const int64_t f1 = r.bit >> 3;
+        const uint16_t c16 = (uint16_t)br_get(&r, 16);
+        if (r.err || crc16(in + f0, f1 - f0) != c16) { free(buf); return -3; }
+        if (pos + bs > cap) { free(buf); return -1; }
+        for (int i = 0; i < bs; i++) {
+            if (ch == 2) {
+                int32_t a = buf[i], s = buf[65536 + i], l, rr;
+                if (chc == 8) { l = a; rr = a - s; }
+                else if (chc == 9) { l = a + s; rr = s; }
+                else if (chc == 10) { const int32_t m = (int32_t)(((uint32_t)a << 1) | ((uint32_t)s & 1u)); l = (m + s) >> 1; rr = (m - s) >> 1; }
+                else { l = a; rr = s; }
+                out[2 * (pos + i)] = (int32_t)((uint32_t)l << out_shift); out[2 * (pos + i) + 1] = (int32_t)((uint32_t)rr << out_shift);
+            } else for (int c = 0; c < ch; c++) out[(size_t)ch * (pos + i) + c] = (int32_t)((uint32_t)buf[(size_t)c * 65536 + i] << out_shift);
+        }
+        pos += bs;
     }
     free(buf);
     return (total && pos != total) ? -4 : pos;

@@ -31,6 +31,8 @@ def _lib():
         L.orc_flac_encode_s16.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_int64]
         L.orc_flac_decode_s16.restype = C.c_int64
         L.orc_flac_decode_s16.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(C.c_int)]
+        L.orc_flac_decode_pcm.restype = C.c_int64
+        L.orc_flac_decode_pcm.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         _bound = True
     return L
 
@@ -55,6 +57,20 @@ def decode(stream, max_samples):
     if n < 0:
         raise ValueError(f"orc_flac_decode_s16: {n}")
     return out[:n], rate.value
+
+
+def decode_pcm(stream, max_frames):
+    """oracle input-side decoder -> (interleaved samples as libavcodec hands them out: int16 for <= 16 bit streams, int32 above,
+    rate, channels, bits per sample); raises on a malformed stream"""
+    buf = np.frombuffer(stream, dtype=np.uint8)
+    rate, ch, bps = C.c_int(0), C.c_int(0), C.c_int(0)
+    out = np.zeros(max(1, max_frames) * 8, dtype=np.int32)
+    n = _lib().orc_flac_decode_pcm(buf.ctypes.data_as(C.c_void_p), len(buf), out.ctypes.data_as(C.c_void_p), max_frames,
+                                   C.byref(rate), C.byref(ch), C.byref(bps))
+    if n < 0:
+        raise ValueError(f"orc_flac_decode_pcm: {n}")
+    pcm = out[: n * ch.value]
+    return (pcm.astype(np.int16) if bps.value <= 16 else pcm.copy()), rate.value, ch.value, bps.value
 
 
 def build_ref():
@@ -93,16 +109,17 @@ def build_ref_encoder():
     return _REF_ENC
 
 
-def ref_encode(pcm, rate=44100, level=5):
-    """REAL libavcodec FLAC encoder (LPC, 4096-sample frames) -> stream bytes, or None when the probe / libraries are absent"""
+def ref_encode(pcm, rate=44100, level=5, channels=1, bits=16):
+    """REAL libavcodec FLAC encoder (LPC, 4096-sample frames) -> stream bytes, or None when the probe / libraries are absent.
+    pcm: interleaved; bits 24 takes int32 samples with the value in the top 24 bits"""
     exe = build_ref_encoder()
     if exe is None or not os.path.isdir(_LIBDIR):
         return None
     with tempfile.TemporaryDirectory() as d:
         fi, fo = os.path.join(d, "a.raw"), os.path.join(d, "a.flac")
-        np.ascontiguousarray(pcm, dtype=np.int16).tofile(fi)
+        np.ascontiguousarray(pcm, dtype=np.int16 if bits <= 16 else np.int32).tofile(fi)
         env = dict(os.environ, LD_LIBRARY_PATH=_LIBDIR + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
-        r = subprocess.run([exe, fi, fo, str(rate), str(level)], capture_output=True, text=True, env=env)
+        r = subprocess.run([exe, fi, fo, str(rate), str(level), str(channels), str(bits)], capture_output=True, text=True, env=env)
         if r.returncode != 0:
             raise RuntimeError(f"ref_flac_encode rc={r.returncode}: {r.stdout} {r.stderr}")
         return open(fo, "rb").read()
@@ -112,7 +129,8 @@ _REF_WAV = os.path.join(_HERE, "_ref", "ref_wav_read")
 
 
 def ref_wav_read(data):
-    """REAL libavformat + libavcodec read of a file image -> (interleaved numpy samples, rate, channels) or None"""
+    """REAL libavformat + libavcodec read of a file image (WAV, FLAC, ...: the demuxer is probed from the content, as the
+    reference's audio.Reader does) -> (interleaved numpy samples, rate, channels) or None"""
     if not os.path.exists(_REF_WAV):
         libs = [sorted(glob.glob(os.path.join(_LIBDIR, p))) for p in ("libavformat-*", "libavcodec-*", "libavutil-*", "libswresample-*")]
         if not os.path.isdir(_REF_INC) or not all(libs):

@@ -1,6 +1,8 @@
 """The oracle's FLAC encoder / decoder (oracle/orc_flac.c) pinned on the REAL FFmpeg libavcodec FLAC decoder found in this
 image (oracle/ref_flac.py builds a probe against the reference's vendored headers): every stream the oracle encoder writes
 must come back bit for bit from libavcodec and from the oracle's own decoder.  CPU only."""
+import os
+
 import numpy as np
 import pytest
 
@@ -82,3 +84,43 @@ def test_oracle_decoder_on_real_libavcodec_streams(name, level):
         pytest.skip("FFmpeg libavcodec / reference headers not present")
     y, rate = ref_flac.decode(stream, len(x) + 16)
     assert rate == 44100 and np.array_equal(x, y)
+
+
+# ---- the INPUT side: orc_flac_decode_pcm (checker of csrc/k_flac_dec.cu) ---------------------------------------------------
+import flac_synth  # noqa: E402
+
+GOLDEN_DEC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "flac_dec_golden.npz")
+
+
+def test_input_decoder_on_the_golden_streams():
+    """streams of the REAL libavcodec encoder (levels 0 / 5 / 8, mono / stereo, 16 / 24 bit) and of the stream generator, with the
+    samples the REAL libavformat + libavcodec reader decoded from them (scripts/make_golden_flac.py)"""
+    g = np.load(GOLDEN_DEC)
+    names = sorted(k[:-7] for k in g.files if k.endswith("_stream"))
+    assert len(names) >= 13
+    for name in names:
+        stream, want = g[name + "_stream"].tobytes(), g[name + "_pcm"]
+        pcm, rate, ch, bps = ref_flac.decode_pcm(stream, len(want))
+        assert pcm.dtype == want.dtype and np.array_equal(pcm, want), name
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_input_decoder_equals_the_real_reader_on_generated_streams(seed):
+    """every subframe type, LPC orders up to 32, wasted bits, escape partitions, variable block sizes, all channel assignments,
+    8..24 bits: oracle == the reference's reader (libavformat flac demuxer + libavcodec flacdec), where the probe exists"""
+    ch, bps = ((1, 16), (2, 16), (2, 24), (2, 8), (3, 12), (8, 20))[seed]
+    s = flac_synth.make_stream(seed, n_frames=5, channels=ch, bps=bps, rate=(44100, 48000, 37800)[seed % 3], variable=bool(seed & 1),
+                               metadata_pad=(seed % 3) * 64)
+    pcm, rate, c, b = ref_flac.decode_pcm(s, 40000)
+    assert (c, b) == (ch, bps)
+    ref = ref_flac.ref_wav_read(s)
+    if ref is None:
+        pytest.skip("no libavformat / libavcodec probe on this box")
+    assert ref[1:] == (rate, ch) and np.array_equal(ref[0], pcm)
+
+
+def test_input_decoder_rejects_corruption():
+    s = bytearray(flac_synth.make_stream(3, n_frames=3, channels=2, bps=16))
+    s[len(s) // 2] ^= 0x10
+    with pytest.raises(ValueError):
+        ref_flac.decode_pcm(bytes(s), 40000)
