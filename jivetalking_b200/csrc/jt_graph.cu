@@ -300,7 +300,7 @@ void jt_graph_build(jt_ctx *c, const std::string &spec, const void *d_in, int64_
     if (chunked) want_meta = false;              // the caller launches the analysis kernels on the owned part
 
     Exec E; E.c = c; E.dry = dry;
-    bool have_mono = false;
+    bool have_mono = false, r128_prelaunched = false;
     const void *raw = d_in;
     if (channels == 1) { E.cur = dry ? dry_mono(n_frames, fmt, rate) : jt_downmix(c, raw, n_frames, 1, fmt, rate); have_mono = true; }
     E.link_fmt = fmt;
@@ -531,6 +531,19 @@ void jt_graph_build(jt_ctx *c, const std::string &spec, const void *d_in, int64_
             }
         } else if (f.name == "astats") {
             E.materialise();
+            // An analysis tail astats -> aspectralstats -> ebur128 on float storage (Pass 1 of a float file): the meter sees the very same
+            // samples whichever of them runs first (only a dbl link is narrowed by aspectralstats' fltp negotiation), so its
+            // kernels are queued now and the GPU works through them while the host does the frame bookkeeping of the three
+            // nodes (3.5 ms per hour of audio -- at the head of Pass 1 the GPU had nothing else queued).
+            if (want_meta && mode == JT_GRAPH_NORMAL && !r128_prelaunched && E.cur.fmt == JT_FMT_FLT) {
+                size_t j = ni + 1;
+                while (j < nodes.size() && (nodes[j].name == "astats" || nodes[j].name == "aspectralstats")) j++;
+                if (j < nodes.size() && nodes[j].name == "ebur128") {
+                    const FilterNode &e = nodes[j];
+                    jt_ebur128_launch(c, E.cur, e.flag("dualmono", "", false), e.str("peak", "", "none").find("true") != std::string::npos, g.r128p);
+                    r128_prelaunched = true;
+                }
+            }
             E.has_astats = true; E.astats_sig = E.cur;
             { const std::string mp = f.str("measure_perchannel", "", "all"); E.astats_overall_only = (mp == "0" || mp == "none"); }
             for (FrameRef &fr : E.frames) fr.astats_pos = fr.start + fr.nb;
@@ -547,7 +560,8 @@ void jt_graph_build(jt_ctx *c, const std::string &spec, const void *d_in, int64_
             const bool tp = peak.find("true") != std::string::npos;
             const bool dual = f.flag("dualmono", "", false);
             // input link is dbl; s16/flt storage widens exactly on load
-            if (want_meta && mode == JT_GRAPH_NORMAL) jt_ebur128_launch(c, E.cur, dual, tp, g.r128p);
+            if (want_meta && mode == JT_GRAPH_NORMAL && !r128_prelaunched) jt_ebur128_launch(c, E.cur, dual, tp, g.r128p);
+            r128_prelaunched = false;
             g.r128_sig = E.cur; g.r128_dual = dual; g.r128_tp = tp;
             E.has_r128 = true; E.link_fmt = JT_FMT_DBL;
             const int tick = E.cur.rate / 10;
