@@ -285,6 +285,20 @@ def main():
     def step_dev():
         return adapt.process_audio_adaptive_ptr(ctx, d_in.data_ptr(), n, RATE, 1, gpudsp.FMT_FLT, d_out.data_ptr(), out_cap, True)
 
+    # e2e: a worker that goes through file after file double-buffers its input (jt_prefetch_input): while step k computes, the
+    # pinned host PCM of step k + 1 is on its way.  Every step still uploads its 691 MB and downloads its 318 MB inside the timed
+    # region; two pinned host buffers alternate so that consecutive steps hand the library different "files".
+    h_ins = [h_in, torch.from_numpy(x).pin_memory()]
+
+    def run_e2e(k_steps):
+        ctx.prefetch_input_ptr(h_ins[0].data_ptr(), n, 1, gpudsp.FMT_FLT)
+        r = None
+        for k in range(k_steps):
+            if k + 1 < k_steps:
+                ctx.prefetch_input_ptr(h_ins[(k + 1) & 1].data_ptr(), n, 1, gpudsp.FMT_FLT)
+            r = adapt.process_audio_adaptive_ptr(ctx, h_ins[k & 1].data_ptr(), n, RATE, 1, gpudsp.FMT_FLT, h_out.data_ptr(), out_cap, False)
+        return r
+
     def step_e2e():
         return adapt.process_audio_adaptive_ptr(ctx, h_in.data_ptr(), n, RATE, 1, gpudsp.FMT_FLT, h_out.data_ptr(), out_cap, False)
 
@@ -321,16 +335,21 @@ def main():
     ctx.enable_timing(False)
 
     # ---- end to end through the C ABI with host buffers (e2e) ----------------------------------
-    for _ in range(max(1, args.warmup // 2)):
-        step_e2e()
+    run_e2e(max(2, args.warmup // 2))
     barrier()
     t0 = time.perf_counter()
     ev0.record(lib_stream)
-    for _ in range(args.steps):
-        res_e, _ = step_e2e()
+    res_e, _ = run_e2e(args.steps)
     ev1.record(lib_stream)
     barrier()
     t_e2e_wall = time.perf_counter() - t0
+    # the same K steps as single blocking calls (upload, compute and download of one file strictly one after the other)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    t_e2e_single = time.perf_counter() - t0
     # the call returns after its device->host copy has landed, so the wall clock between the barriers IS the end-to-end time;
     # the event pair on the library stream is reported next to it
     t_e2e = max(t_e2e_wall, ev0.elapsed_time(ev1) * 1e-3)
@@ -414,7 +433,9 @@ def main():
                    "samples_per_gpu": n, "pass2_spec": an.pass2_spec.decode(),
                    "l2": "inputs (691 MB/stream) and every intermediate exceed the 126 MB L2"},
         "e2e": {"value": e2e, "unit": "samples/s", "realtime_x": e2e / RATE, "h2d_bytes_per_step": int(n * 4),
-                "d2h_bytes_per_step": int(res_e.n_out * 2), "ms_per_step": 1e3 * t_e2e / args.steps},
+                "d2h_bytes_per_step": int(res_e.n_out * 2), "ms_per_step": 1e3 * t_e2e / args.steps,
+                "mode": "jt_prefetch_input(file k+1) + jt_process_audio_adaptive(file k), pinned host buffers: each step's upload overlaps the previous step's kernels; the first upload of the timed region is exposed",
+                "single_call_ms_per_step": 1e3 * t_e2e_single / args.steps, "single_call_value": total_samples / t_e2e_single},
         "gpu_launches": int(launches),
         "timing": {"method": "CUDA events on the library stream around the K steps (max over ranks); e2e: wall clock between barriers, the call returns after its D2H copy",
                    "wall_ms_per_step": 1e3 * t_wall / args.steps, "e2e_wall_ms_per_step": 1e3 * t_e2e_wall / args.steps,

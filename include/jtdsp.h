@@ -511,6 +511,14 @@ int jt_wav_decode(jt_ctx *ctx, const void *bytes, int64_t n_bytes, void *pcm_out
 int jt_wav_decode_dev(jt_ctx *ctx, const void *d_bytes, int64_t n_bytes, void *d_pcm_out, int64_t cap_frames, int64_t *n_frames,
                   int *sample_fmt, int *sample_rate, int *channels);
 
+/* Double-buffered input for a worker that processes file after file: starts the host -> device copy of a LATER call's input on a
+ * separate stream and returns at once.  The next host-buffer entry of this context that is handed the same pointer and the same
+ * size (jt_analyse*, jt_run_graph, jt_process_audio*) uses the resident copy instead of uploading.  Issue it right before the call
+ * that processes the current file, so the copy runs under that call's kernels: prefetch(file k+1); process(file k); ...
+ * The host buffer must stay unchanged until the call that consumes it has returned, and should be pinned (cudaHostAlloc /
+ * cudaHostRegister): pageable memory is legal but copies synchronously.  Two copies may be outstanding per context. */
+int jt_prefetch_input(jt_ctx *ctx, const void *pcm, int64_t n_frames, int channels, int sample_fmt);
+
 /* the cudaStream_t (as void *) every kernel and copy of this context is issued on, so a caller can order its own
  * device work against it or bracket calls with CUDA events */
 void   *jt_cuda_stream(const jt_ctx *ctx);

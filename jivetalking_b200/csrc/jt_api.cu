@@ -58,6 +58,8 @@ extern "C" void jt_destroy(jt_ctx *c)
     jt_flush_timing(c);
     if (c->pin_in) cudaFreeHost(c->pin_in);
     if (c->pin_out) cudaFreeHost(c->pin_out);
+    if (c->upload_stream) { cudaStreamSynchronize(c->upload_stream); cudaStreamDestroy(c->upload_stream); }
+    for (auto &p : c->prefetch) { if (p.dev) cudaFree(p.dev); if (p.ev) cudaEventDestroy(p.ev); }
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (auto &kv : c->dev_tables) cudaFree(kv.second);
     for (auto &sl : c->slabs) cudaFree(sl.base);
@@ -67,6 +69,45 @@ extern "C" void jt_destroy(jt_ctx *c)
     if (c->side_stream) { cudaStreamSynchronize(c->side_stream); cudaStreamDestroy(c->side_stream); }
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
     delete c;
+}
+
+// A long transfer owns its copy engine for its whole duration, and the small copies of the compute stream (per-tick values,
+// statistics rows) that land on the same engine queue behind it: a 691 MB upload in one piece delayed the concurrent call by 8 ms
+// (scripts/debug/e2e_parts.py).  In pieces of 4 MB (~75 us each) the engine interleaves the other streams' copies between them.
+static cudaError_t copy_in_pieces(void *dst, const void *src, size_t bytes, cudaMemcpyKind kind, cudaStream_t stream)
+{
+    const size_t piece = 4u << 20;
+    for (size_t off = 0; off < bytes; off += piece) {
+        const cudaError_t e = cudaMemcpyAsync((char *)dst + off, (const char *)src + off, std::min(piece, bytes - off), kind, stream);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+// Double-buffered input: starts the host -> device copy of the input of a LATER call on the context's upload stream and returns
+// at once; the next host-buffer entry (jt_analyse*, jt_run_graph, jt_process_audio*) that is handed the same pointer and size finds
+// its input resident instead of copying it.  Call it right before processing the current file: the copy then runs under that
+// call's kernels (pinned host memory; pageable memory is copied synchronously here, which is legal but hides nothing).
+extern "C" int jt_prefetch_input(jt_ctx *c, const void *pcm, int64_t n_frames, int channels, int fmt)
+{
+    if (!c || !pcm || n_frames <= 0 || channels <= 0 || !jt_valid_fmt(fmt)) return JT_ERR_INVALID_ARG;
+    cudaSetDevice(c->device);
+    const size_t bytes = (size_t)n_frames * channels * jt_fmt_bytes(fmt);
+    if (!c->upload_stream && cudaStreamCreateWithFlags(&c->upload_stream, cudaStreamNonBlocking) != cudaSuccess) { c->last_error = "cudaStreamCreate (upload)"; return JT_ERR_CUDA; }
+    jt_ctx::Prefetch &p = c->prefetch[c->prefetch_next];
+    c->prefetch_next ^= 1;
+    p.valid = false;
+    if (p.cap < bytes) {
+        if (p.dev) { cudaStreamSynchronize(c->upload_stream); cudaFree(p.dev); p.dev = nullptr; p.cap = 0; }
+        if (cudaMalloc(&p.dev, bytes + 256) != cudaSuccess) { cudaGetLastError(); c->last_error = "cudaMalloc (prefetch)"; return JT_ERR_NOMEM; }
+        p.cap = bytes;
+    }
+    if (!p.ev && cudaEventCreateWithFlags(&p.ev, cudaEventDisableTiming) != cudaSuccess) { c->last_error = "cudaEventCreate"; return JT_ERR_CUDA; }
+    if (copy_in_pieces(p.dev, pcm, bytes, cudaMemcpyHostToDevice, c->upload_stream) != cudaSuccess || cudaEventRecord(p.ev, c->upload_stream) != cudaSuccess) {
+        c->last_error = cudaGetErrorString(cudaGetLastError()); return JT_ERR_CUDA;
+    }
+    p.host = pcm; p.bytes = bytes; p.valid = true;
+    return JT_OK;
 }
 
 extern "C" const char *jt_last_error(const jt_ctx *c) { return c ? c->last_error.c_str() : ""; }
@@ -121,6 +162,13 @@ static void *pinned(jt_ctx *c, void **slot, size_t *cap, size_t bytes)
 // ctx-owned pinned buffer in chunks so the copy engine runs at full PCIe rate.
 static void *upload(jt_ctx *c, const void *h, size_t bytes)
 {
+    // already on its way (jt_prefetch_input with this very buffer): order the compute stream behind the copy and use it in place
+    for (auto &p : c->prefetch)
+        if (p.valid && p.host == h && p.bytes == bytes && bytes) {
+            p.valid = false;
+            JT_CUDA(cudaStreamWaitEvent(c->stream, p.ev, 0));
+            return p.dev;
+        }
     void *d = jt_dalloc_bytes(c, bytes);
     if (!bytes) return d;
     cudaPointerAttributes at;
@@ -301,8 +349,8 @@ static void analyse_enqueue(jt_ctx *c, const void *d_in, int64_t n_frames, int r
     jt_raw_frame_stats(c, d_in, n_frames, channels, fmt, F, d_ss, d_pk, nsrc);
     ap.h_ss = jt_pinned<double>(c, nsrc); ap.h_pk = jt_pinned<double>(c, nsrc);
     if (nsrc) {
-        JT_CUDA(cudaMemcpyAsync(ap.h_ss, d_ss, sizeof(double) * nsrc, cudaMemcpyDeviceToHost, c->stream));
-        JT_CUDA(cudaMemcpyAsync(ap.h_pk, d_pk, sizeof(double) * nsrc, cudaMemcpyDeviceToHost, c->stream));
+        jt_copy_small(c, ap.h_ss, d_ss, sizeof(double) * nsrc);
+        jt_copy_small(c, ap.h_pk, d_pk, sizeof(double) * nsrc);
     }
     ap.ev = jt_record_event(c);
     jt_graph_enqueue(c, PASS1_SPEC, d_in, n_frames, rate, channels, fmt, F, false, true, ap.g);
@@ -1296,7 +1344,8 @@ static void process_device(jt_ctx *c, const void *d_in, int64_t n_frames, int ra
         // with Pass 4's analysis tail
         if (ob && g4.out_ready) {
             JT_CUDA(cudaStreamWaitEvent(c->copy_stream, g4.out_ready, 0));
-            JT_CUDA(cudaMemcpyAsync(pcm_out, g4.out.d, ob, out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->copy_stream));
+            if (out_on_device) JT_CUDA(cudaMemcpyAsync(pcm_out, g4.out.d, ob, cudaMemcpyDeviceToDevice, c->copy_stream));
+            else JT_CUDA(copy_in_pieces(pcm_out, g4.out.d, ob, cudaMemcpyDeviceToHost, c->copy_stream));
         } else if (ob) JT_CUDA(cudaMemcpyAsync(pcm_out, g4.out.d, ob, out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
     }
     jt_graph_finish_acc(c, g4, &R.final, &R.pass4);

@@ -43,6 +43,10 @@ struct jt_ctx {
     // pinned host arena for small device->host results (tick energies, statistics rows); reset per API call
     std::vector<std::pair<char *, size_t>> pin_blocks; size_t pin_block = 0, pin_used = 0;
     std::vector<cudaEvent_t> event_pool; size_t events_used = 0;
+    // jt_prefetch_input: the NEXT call's input on its way to the device while the current call computes (two slots, ping-pong)
+    struct Prefetch { void *dev = nullptr; size_t cap = 0; const void *host = nullptr; size_t bytes = 0; cudaEvent_t ev = nullptr; bool valid = false; };
+    Prefetch prefetch[2]; int prefetch_next = 0;
+    cudaStream_t upload_stream = nullptr;
     // cross-chunk carries of a stream sharded over several contexts / GPUs (jt_set_exchange)
     jt_exchange_fn exchange = nullptr; void *exchange_user = nullptr; int exchange_ranks = 1;
 };
@@ -66,6 +70,11 @@ template <class T> static inline const T *jt_dev_table(jt_ctx *c, const char *ta
 // pinned host scratch valid until the end of the current API call
 void *jt_pinned_bytes(jt_ctx *c, size_t bytes);
 template <class T> static inline T *jt_pinned(jt_ctx *c, size_t n) { return (T *)jt_pinned_bytes(c, (n ? n : 1) * sizeof(T)); }
+// Small transfers between device memory and PINNED host memory (jt_pinned) as a copy kernel on the context's stream instead of
+// the copy engines: a copy engine is held by one transfer at a time, so the per-tick values / statistics rows of the compute
+// stream queued behind a file-sized upload (jt_prefetch_input) or the download of the result for up to 12 ms.  Either pointer may
+// be the pinned one (cudaHostAlloc memory is device-accessible under unified addressing).
+void jt_copy_small(jt_ctx *c, void *dst, const void *src, size_t bytes);
 // an event (timing disabled) recorded on the context's stream now; owned by the context, recycled per API call
 cudaEvent_t jt_record_event(jt_ctx *c);
 void jt_release_since(jt_ctx *c, size_t mark, const void *keep);   // free allocations made after `mark`, except the one holding `keep`

@@ -127,6 +127,24 @@ void *jt_pinned_bytes(jt_ctx *c, size_t bytes)
     return p;
 }
 
+__global__ void k_copy_small(unsigned char *__restrict__ dst, const unsigned char *__restrict__ src, size_t bytes, int wide)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x, t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (wide) {
+        const size_t n16 = bytes >> 4;
+        for (size_t i = t; i < n16; i += stride) ((uint4 *)dst)[i] = ((const uint4 *)src)[i];
+        for (size_t i = (n16 << 4) + t; i < bytes; i += stride) dst[i] = src[i];
+    } else for (size_t i = t; i < bytes; i += stride) dst[i] = src[i];
+}
+void jt_copy_small(jt_ctx *c, void *dst, const void *src, size_t bytes)
+{
+    if (!bytes) return;
+    const int wide = ((((uintptr_t)dst) | ((uintptr_t)src)) & 15) == 0;
+    const size_t items = wide ? (bytes >> 4) + 16 : bytes;
+    c->launches++;
+    k_copy_small<<<(int)std::min<size_t>((items + 255) / 256, (size_t)c->num_sms * 2), 256, 0, c->stream>>>((unsigned char *)dst, (const unsigned char *)src, bytes, wide);
+}
+
 cudaEvent_t jt_record_event(jt_ctx *c)
 {
     if (c->events_used == c->event_pool.size()) {

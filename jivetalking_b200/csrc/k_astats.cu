@@ -408,10 +408,10 @@ static void astats_launch_t(jt_ctx *c, const Sig &in, int64_t n, AstatsPending &
     }
     AstatsHost *h = (AstatsHost *)jt_pinned_bytes(c, sizeof(AstatsHost));
     pd.host = h;
-    JT_CUDA(cudaMemcpyAsync(&h->total, d_total, sizeof(AsPartA), cudaMemcpyDeviceToHost, c->stream));
-    JT_CUDA(cudaMemcpyAsync(h->hist, d_hist, sizeof(unsigned long long) * (AS_HIST + 8), cudaMemcpyDeviceToHost, c->stream));
-    JT_CUDA(cudaMemcpyAsync(h->mm, d_mm, sizeof(double) * 2, cudaMemcpyDeviceToHost, c->stream));
-    JT_CUDA(cudaMemcpyAsync(&h->nf, d_nf, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    jt_copy_small(c, &h->total, d_total, sizeof(AsPartA));
+    jt_copy_small(c, h->hist, d_hist, sizeof(unsigned long long) * (AS_HIST + 8));
+    jt_copy_small(c, h->mm, d_mm, sizeof(double) * 2);
+    jt_copy_small(c, &h->nf, d_nf, sizeof(float));
     pd.ev = jt_record_event(c);
 }
 

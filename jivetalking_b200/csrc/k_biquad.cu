@@ -9,6 +9,7 @@
 #include "jt_internal.h"
 #include "jt_device.cuh"
 #include <cstdio>
+#include <cstring>
 
 BiquadCoef jt_biquad_design(bool highpass, double freq, double q, int rate, bool normalize)
 {
@@ -175,7 +176,9 @@ void jt_band_sumsq(jt_ctx *c, const Sig &in, int64_t acc_from, const double *lo,
     }
     BandCoef *d_coef = jt_dalloc<BandCoef>(c, n_bands);
     double *d_sum = jt_dalloc<double>(c, n_bands);
-    JT_CUDA(cudaMemcpyAsync(d_coef, hc.data(), sizeof(BandCoef) * n_bands, cudaMemcpyHostToDevice, c->stream));
+    BandCoef *h_coef = jt_pinned<BandCoef>(c, (size_t)n_bands);
+    memcpy(h_coef, hc.data(), sizeof(BandCoef) * n_bands);
+    jt_copy_small(c, d_coef, h_coef, sizeof(BandCoef) * n_bands);
     JT_CUDA(cudaMemsetAsync(d_sum, 0, sizeof(double) * n_bands, c->stream));
     const int seg = 4096;
     const int64_t spb = (in.n + seg - 1) / seg, lanes = spb * n_bands;
@@ -188,8 +191,10 @@ void jt_band_sumsq(jt_ctx *c, const Sig &in, int64_t acc_from, const double *lo,
         else if (in.fmt == JT_FMT_S32) k_band_rms<int32_t, double><<<grid, 64, 0, c->stream>>>((const int32_t *)in.d, in.n, seg, warm, spb, n_bands, d_coef, d_sum, acc_from);
         else JT_THROW(JT_ERR_UNSUPPORTED, "band rms on sample format %d", in.fmt);
     }
-    JT_CUDA(cudaMemcpyAsync(sumsq_host, d_sum, sizeof(double) * n_bands, cudaMemcpyDeviceToHost, c->stream));
+    double *h_sum = jt_pinned<double>(c, (size_t)n_bands);
+    jt_copy_small(c, h_sum, d_sum, sizeof(double) * n_bands);
     JT_CUDA(cudaStreamSynchronize(c->stream));
+    memcpy(sumsq_host, h_sum, sizeof(double) * n_bands);
 }
 
 void jt_band_rms_batch(jt_ctx *c, const Sig &in, const double *lo, const double *hi, int n_bands, double *rms_db, int32_t *found)

@@ -223,9 +223,9 @@ void jt_ebur128_launch(jt_ctx *c, const Sig &in, bool dualmono, bool true_peak, 
         else { SwrPlan p = jt_swr_plan(in.rate, 192000); jt_swr_tick_absmax(c, in.fmt == JT_FMT_S32 ? jt_convert(c, in, JT_FMT_DBL) : in, p, tick, nt, d_tp); }
     }
     pd.hp = jt_pinned<double>(c, nt); pd.hk = jt_pinned<double>(c, nt); pd.ht = jt_pinned<double>(c, nt);
-    JT_CUDA(cudaMemcpyAsync(pd.hp, d_pow, sizeof(double) * nt, cudaMemcpyDeviceToHost, c->stream));
-    JT_CUDA(cudaMemcpyAsync(pd.hk, d_peak, sizeof(double) * nt, cudaMemcpyDeviceToHost, c->stream));
-    if (true_peak) JT_CUDA(cudaMemcpyAsync(pd.ht, d_tp, sizeof(double) * nt, cudaMemcpyDeviceToHost, c->stream));
+    jt_copy_small(c, pd.hp, d_pow, sizeof(double) * nt);
+    jt_copy_small(c, pd.hk, d_peak, sizeof(double) * nt);
+    if (true_peak) jt_copy_small(c, pd.ht, d_tp, sizeof(double) * nt);
     pd.ev = jt_record_event(c);
 }
 
@@ -320,8 +320,8 @@ void jt_loudnorm_meter_launch(jt_ctx *c, const Sig &in, bool dual_mono, Loudnorm
     KWeight kw = kweight_design(in.rate);
     run_ticks<1>(c, in, pd.s100, pd.nt, kw, d_pow, d_peak);
     pd.hp = jt_pinned<double>(c, pd.nt); pd.hk = jt_pinned<double>(c, pd.nt);
-    JT_CUDA(cudaMemcpyAsync(pd.hp, d_pow, sizeof(double) * pd.nt, cudaMemcpyDeviceToHost, c->stream));
-    JT_CUDA(cudaMemcpyAsync(pd.hk, d_peak, sizeof(double) * pd.nt, cudaMemcpyDeviceToHost, c->stream));
+    jt_copy_small(c, pd.hp, d_pow, sizeof(double) * pd.nt);
+    jt_copy_small(c, pd.hk, d_peak, sizeof(double) * pd.nt);
     pd.ev = jt_record_event(c);
 }
 

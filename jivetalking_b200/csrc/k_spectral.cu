@@ -218,7 +218,7 @@ void jt_aspectralstats_launch(jt_ctx *c, const Sig &in0, int win, const std::vec
         memcpy(h_idx, pd.items.data(), sizeof(int64_t) * n_items);
         memcpy(h_idx + n_items, prev.data(), sizeof(int64_t) * n_items);
         d_items = jt_dalloc<int64_t>(c, 2 * (size_t)n_items); d_prev = d_items + n_items;
-        JT_CUDA(cudaMemcpyAsync(d_items, h_idx, sizeof(int64_t) * 2 * n_items, cudaMemcpyHostToDevice, c->stream));
+        jt_copy_small(c, d_items, h_idx, sizeof(int64_t) * 2 * n_items);
     }
     float *d_mags = jt_dalloc<float>(c, (size_t)n_items * (win / 2));
     float *d_rows = jt_dalloc<float>(c, (size_t)n_items * JT_SP_COUNT);
@@ -231,7 +231,7 @@ void jt_aspectralstats_launch(jt_ctx *c, const Sig &in0, int win, const std::vec
         k_spectral_flux<<<grid, 256, 0, c->stream>>>(d_mags, win / 2, n_items, d_prev, d_rows);
     }
     pd.h_rows = jt_pinned<float>(c, (size_t)n_items * JT_SP_COUNT);
-    JT_CUDA(cudaMemcpyAsync(pd.h_rows, d_rows, sizeof(float) * (size_t)n_items * JT_SP_COUNT, cudaMemcpyDeviceToHost, c->stream));
+    jt_copy_small(c, pd.h_rows, d_rows, sizeof(float) * (size_t)n_items * JT_SP_COUNT);
     pd.ev = jt_record_event(c);
 }
 

@@ -156,6 +156,7 @@ def lib():
     dec = [_P, _P, _I64, _P, _I64, C.POINTER(_I64), C.POINTER(_INT), C.POINTER(_INT), C.POINTER(_INT)]
     for name in ("jt_flac_decode", "jt_flac_decode_dev", "jt_wav_decode", "jt_wav_decode_dev"):
         getattr(L, name).argtypes = dec
+    L.jt_prefetch_input.argtypes = [_P, _P, _I64, _INT, _INT]
     L.jt_cuda_stream.restype = _P
     L.jt_cuda_stream.argtypes = [_P]
     L.jt_launch_count.restype = _I64
@@ -448,6 +449,10 @@ class Context:
 
     def launch_count(self):
         return lib().jt_launch_count(self._h)
+
+    def prefetch_input_ptr(self, in_ptr, n_frames, channels, fmt):
+        """start the upload of a LATER call's (pinned) host input; the call that gets the same pointer finds it resident"""
+        self._check(lib().jt_prefetch_input(self._h, _P(in_ptr), n_frames, channels, fmt))
 
     def reset_counters(self):
         lib().jt_reset_launch_count(self._h)
