@@ -140,21 +140,33 @@ k_astats_b(const T *__restrict__ x, int64_t n, const AsPartA *__restrict__ total
     }
 }
 
-// combine the per-CTA partials of pass A (fixed order: deterministic) and initialise the min / max cells of C and D
+// combine the per-CTA partials of pass A and initialise the min / max cells of C and D.  Fixed order, so deterministic: lane l
+// folds parts l, l + 32, ... in sequence, then the 32 lane results fold in a fixed butterfly (one thread walking all ~1200
+// partials took 0.35 ms per launch, 2.4 ms per step over the seven astats runs of ProcessAudio)
+__device__ __forceinline__ void as_fold(AsPartA &r, const AsPartA &b)
+{
+    r.sum += b.sum; r.sumsq += b.sumsq; r.diff_sum += b.diff_sum; r.diff_sumsq += b.diff_sumsq;
+    r.mn = fmin(r.mn, b.mn); r.mx = fmax(r.mx, b.mx); r.min_nz = fmin(r.min_nz, b.min_nz);
+    r.min_diff = fmin(r.min_diff, b.min_diff); r.max_diff = fmax(r.max_diff, b.max_diff);
+    r.zero_runs += b.zero_runs; r.mask |= b.mask;
+}
 __global__ void __launch_bounds__(32)
 k_astats_reduce(const AsPartA *__restrict__ parts, int nparts, AsPartA *__restrict__ total, double *__restrict__ mm, float *__restrict__ nf)
 {
-    if (threadIdx.x) return;
-    AsPartA r = parts[0];
-    for (int i = 1; i < nparts; i++) {
-        const AsPartA b = parts[i];
-        r.sum += b.sum; r.sumsq += b.sumsq; r.diff_sum += b.diff_sum; r.diff_sumsq += b.diff_sumsq;
-        r.mn = fmin(r.mn, b.mn); r.mx = fmax(r.mx, b.mx); r.min_nz = fmin(r.min_nz, b.min_nz);
-        r.min_diff = fmin(r.min_diff, b.min_diff); r.max_diff = fmax(r.max_diff, b.max_diff);
-        r.zero_runs += b.zero_runs; r.mask |= b.mask;
+    __shared__ AsPartA sh[32];
+    const int lane = threadIdx.x;
+    if (lane < nparts) {
+        AsPartA r = parts[lane];
+        for (int i = lane + 32; i < nparts; i += 32) as_fold(r, parts[i]);
+        sh[lane] = r;
     }
-    *total = r;
-    mm[0] = DBL_MAX; mm[1] = 0.0; *nf = FLT_MAX;
+    __syncwarp();
+    const int live = min(nparts, 32);
+    for (int o = 16; o; o >>= 1) {
+        if (lane < o && lane + o < live) { AsPartA r = sh[lane]; as_fold(r, sh[lane + o]); sh[lane] = r; }
+        __syncwarp();
+    }
+    if (lane == 0) { *total = sh[0]; mm[0] = DBL_MAX; mm[1] = 0.0; *nf = FLT_MAX; }
 }
 
 // C1: per block of BS samples, zero-state end value of avg = avg*mult + (1-mult)*nd^2.

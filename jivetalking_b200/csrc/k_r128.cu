@@ -15,6 +15,7 @@
 #include "jt_lanes.cuh"
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 
 struct KWeight { double pb0, pb1, pb2, pa1, pa2, rb0, rb1, rb2, ra1, ra2; double b[5], a[5]; };
@@ -163,12 +164,230 @@ __global__ void k_r128_fold(const double *__restrict__ unit_pow, const double *_
     tick_pow[k] = p; tick_peak[k] = m;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// The same per-tick values WITHOUT lanes and warm-up walks: K-weighting is linear, so the filter state at any sample is
+//   (end state of a zero-state run over the block before it)  +  Phi * (state at that block's start)
+// with Phi the 4 x 4 state transition over one block.  Three passes over blocks of B samples (B divides the tick, ~96):
+//   k_kw_blocks<.., 0>  thread per block: zero-state run -> the block's forced end state e_b            (9 DP per sample)
+//   k_kw_scan           thread per tick : s_{b+1} = Phi s_b + e_b, started two ticks (48 RLB time constants) early from
+//                       rest -> the true state at the start of each of the tick's blocks                (20 DP per block)
+//   k_kw_blocks<.., 1>  thread per block: the filter from that state -> energy and sample peak           (10 DP per sample)
+// and k_kw_fold sums a tick's block energies in block order.  A block's samples are walked by ONE thread with exactly the
+// recurrence of the sequential filter, so given its start state the result is the sequential one; the start state itself
+// differs from the sequential state by rounding only (1e-16 relative).  Every block is independent: 1.8 million threads for an
+// hour of audio, 5000 for a 10 s region -- the lane kernel above spent the same (warm-up + two ticks) walk whatever the length
+// and, at 6 warps per SM, 112 cycles per sample.  The CTA stages its 128 blocks in shared memory with coalesced row loads
+// (pitch B + 1: the per-thread walks are conflict free).
+struct KwPhi { double m[16]; };
+
+template <int STRUCT>
+__host__ __device__ __forceinline__ double kw_step(const KWeight &kw, double x0, double &x1, double &x2, double &s0, double &s1, double &s2, double &s3)
+{
+    if (STRUCT == 0) {                          // state: y1, y2, z1, z2 (+ the input history x1, x2)
+        const double t = fma(x2, kw.pb2, fma(x1, kw.pb1, x0 * kw.pb0));
+        const double y0 = fma(-s0, kw.pa1, fma(-s1, kw.pa2, t));
+        x2 = x1; x1 = x0;
+        const double u = fma(s1, kw.rb2, fma(s0, kw.rb1, y0 * kw.rb0));
+        const double z0 = fma(-s2, kw.ra1, fma(-s3, kw.ra2, u));
+        s1 = s0; s0 = y0; s3 = s2; s2 = z0;
+        return z0;
+    } else {                                    // state: v1 .. v4
+        const double v0 = fma(-kw.a[1], s0, fma(-kw.a[2], s1, fma(-kw.a[3], s2, fma(-kw.a[4], s3, x0))));
+        const double o = fma(kw.b[0], v0, fma(kw.b[1], s0, fma(kw.b[2], s1, fma(kw.b[3], s2, kw.b[4] * s3))));
+        s3 = s2; s2 = s1; s1 = s0; s0 = v0;
+        return o;
+    }
+}
+
+// THREADS * B contiguous samples -> tile rows of pitch B + 1, as vectors of VW elements (a vector never straddles two rows: VW | B)
+template <class TIN, int VW, int THREADS>
+__device__ __forceinline__ void kw_stage_vec(const TIN *__restrict__ src, TIN *__restrict__ tile, int B, int pitch, int tid)
+{
+    struct alignas(sizeof(TIN) * VW) Vec { TIN v[VW]; };
+    const Vec *xv = (const Vec *)src;
+    const int total = THREADS * B, step = THREADS * VW, dq = step / B, dr = step % B;
+    int idx = tid * VW, r = idx / B, col = idx % B;
+    while (idx < total) {
+        Vec v[4]; int off[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            off[j] = -1;
+            if (idx < total) {
+                v[j] = xv[idx / VW]; off[j] = r * pitch + col;
+                idx += step; r += dq; col += dr; if (col >= B) { col -= B; r++; }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) if (off[j] >= 0) {
+#pragma unroll
+            for (int e = 0; e < VW; e++) tile[off[j] + e] = v[j].v[e];
+        }
+    }
+}
+
+template <class TIN, int STRUCT, int PHASE, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+k_kw_blocks(const TIN *__restrict__ x, int64_t n, int B, int64_t n_blocks, const __grid_constant__ KWeight kw,
+            const double *__restrict__ s_in, double *__restrict__ s_out, double *__restrict__ e_out, double *__restrict__ pk_out)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    TIN *tile = (TIN *)smem;
+    const int pitch = B + 1, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t b0 = (int64_t)blockIdx.x * THREADS, g0 = b0 * B;
+    {   // the CTA's THREADS * B samples are contiguous: flat coalesced loads, several in flight per thread, (row, col) tracked
+        // incrementally (a load-store-load chain per row left the kernel waiting on DRAM latency: ncu r2q).  CTAs that lie
+        // inside the stream and start on a 16-byte boundary (all but the last, for the usual block sizes) load 16-byte vectors.
+        constexpr int VMAX = 16 / (int)sizeof(TIN);
+        const int total = THREADS * B;
+        const bool inside = g0 + total <= n;
+        const uintptr_t addr = (uintptr_t)(x + g0);
+        if (inside && B % VMAX == 0 && (addr & 15) == 0) kw_stage_vec<TIN, VMAX, THREADS>(x + g0, tile, B, pitch, tid);
+        else if (VMAX >= 4 && inside && B % (VMAX / 2) == 0 && (addr & 7) == 0) kw_stage_vec<TIN, (VMAX >= 4 ? VMAX / 2 : 1), THREADS>(x + g0, tile, B, pitch, tid);
+        else {
+            const int dq = THREADS / B, dr = THREADS % B;
+            int idx = tid, r = tid / B, col = tid % B;
+            while (idx < total) {
+                TIN v[8]; int off[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    off[j] = -1;
+                    if (idx < total) {
+                        const int64_t g = g0 + idx;
+                        v[j] = g < n ? x[g] : (TIN)0; off[j] = r * pitch + col;
+                        idx += THREADS; r += dq; col += dr; if (col >= B) { col -= B; r++; }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 8; j++) if (off[j] >= 0) tile[off[j]] = v[j];
+            }
+        }
+    }
+    (void)lane; (void)warp;
+    __syncthreads();
+    const int64_t b = b0 + tid;
+    if (b >= n_blocks) return;
+    const TIN *row = tile + tid * pitch;
+    double x1 = 0, x2 = 0;
+    if (STRUCT == 0) {
+        const int64_t t0 = b * B;
+        if (tid > 0) { x1 = jt_as_f64(row[-pitch + B - 1]); x2 = B >= 2 ? jt_as_f64(row[-pitch + B - 2]) : 0.0; }
+        else { if (t0 >= 1 && t0 - 1 < n) x1 = jt_as_f64(x[t0 - 1]); if (t0 >= 2 && t0 - 2 < n) x2 = jt_as_f64(x[t0 - 2]); }
+    }
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    if (PHASE == 1) { s0 = s_in[4 * b]; s1 = s_in[4 * b + 1]; s2 = s_in[4 * b + 2]; s3 = s_in[4 * b + 3]; }
+    double acc = 0.0; unsigned long long pkb = 0ull;
+    int k = 0;
+    for (; k + 8 <= B; k += 8) {
+        double v[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = jt_as_f64(row[k + j]);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const double z = kw_step<STRUCT>(kw, v[j], x1, x2, s0, s1, s2, s3);
+            if (PHASE == 1) {
+                acc = fma(z, z, acc);
+                const unsigned long long bits = (unsigned long long)__double_as_longlong(v[j]) & 0x7fffffffffffffffull; pkb = bits > pkb ? bits : pkb;
+            }
+        }
+    }
+    for (; k < B; k++) {
+        const double v = jt_as_f64(row[k]);
+        const double z = kw_step<STRUCT>(kw, v, x1, x2, s0, s1, s2, s3);
+        if (PHASE == 1) { acc = fma(z, z, acc); const unsigned long long bits = (unsigned long long)__double_as_longlong(v) & 0x7fffffffffffffffull; pkb = bits > pkb ? bits : pkb; }
+    }
+    if (PHASE == 0) { s_out[4 * b] = s0; s_out[4 * b + 1] = s1; s_out[4 * b + 2] = s2; s_out[4 * b + 3] = s3; }
+    else { e_out[b] = acc; pk_out[b] = __longlong_as_double((long long)pkb); }
+}
+
+// thread per tick: the state at the start of each of its P blocks (in place: e[] holds forced end states on entry of a block's
+// turn and is only read; the states go to s[])
+__global__ void __launch_bounds__(128)
+k_kw_scan(const double *__restrict__ e, int64_t n_blocks, int P, int64_t n_ticks, int warm_blocks, const __grid_constant__ KwPhi phi, double *__restrict__ s)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_ticks) return;
+    const int64_t b0 = k * P, b1 = min(b0 + (int64_t)P, n_blocks);
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    for (int64_t b = max((int64_t)0, b0 - warm_blocks); b < b1; b++) {
+        if (b >= b0) { s[4 * b] = s0; s[4 * b + 1] = s1; s[4 * b + 2] = s2; s[4 * b + 3] = s3; }
+        const double n0 = fma(phi.m[0], s0, fma(phi.m[1], s1, fma(phi.m[2], s2, fma(phi.m[3], s3, e[4 * b]))));
+        const double n1 = fma(phi.m[4], s0, fma(phi.m[5], s1, fma(phi.m[6], s2, fma(phi.m[7], s3, e[4 * b + 1]))));
+        const double n2 = fma(phi.m[8], s0, fma(phi.m[9], s1, fma(phi.m[10], s2, fma(phi.m[11], s3, e[4 * b + 2]))));
+        const double n3 = fma(phi.m[12], s0, fma(phi.m[13], s1, fma(phi.m[14], s2, fma(phi.m[15], s3, e[4 * b + 3]))));
+        s0 = n0; s1 = n1; s2 = n2; s3 = n3;
+    }
+}
+
+__global__ void k_kw_fold(const double *__restrict__ e_blk, const double *__restrict__ pk_blk, int64_t n_blocks, int P, int64_t n_ticks,
+                          double *__restrict__ tick_pow, double *__restrict__ tick_peak)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_ticks) return;
+    double p = 0.0, m = 0.0;
+    for (int64_t b = k * P; b < min((k + 1) * (int64_t)P, n_blocks); b++) { p += e_blk[b]; m = fmax(m, pk_blk[b]); }
+    tick_pow[k] = p; tick_peak[k] = m;
+}
+
+static int kw_block_size(int tick)
+{
+    int best = 0;
+    for (int d = 64; d <= 160; d++) if (tick % d == 0 && (!best || std::abs(d - 96) < std::abs(best - 96))) best = d;
+    return best;
+}
+
+template <int STRUCT>
+static KwPhi kw_transition(const KWeight &kw, int B)
+{
+    KwPhi phi;
+    for (int col = 0; col < 4; col++) {
+        double st[4] = {0, 0, 0, 0}; st[col] = 1.0;
+        double x1 = 0, x2 = 0;
+        for (int i = 0; i < B; i++) (void)kw_step<STRUCT>(kw, 0.0, x1, x2, st[0], st[1], st[2], st[3]);
+        for (int r = 0; r < 4; r++) phi.m[4 * r + col] = st[r];
+    }
+    return phi;
+}
+
+template <class TIN, int STRUCT>
+static void run_ticks_blocks_t(jt_ctx *c, const Sig &in, int tick, int64_t n_ticks, int B, const KWeight &kw, double *d_pow, double *d_peak)
+{
+    constexpr int THREADS = sizeof(TIN) == 8 ? 64 : 128;
+    const int P = tick / B;
+    const int64_t n_blocks = n_ticks * P;
+    double *d_e = jt_dalloc<double>(c, (size_t)n_blocks * 4), *d_s = jt_dalloc<double>(c, (size_t)n_blocks * 4);
+    double *d_eb = jt_dalloc<double>(c, (size_t)n_blocks), *d_pk = jt_dalloc<double>(c, (size_t)n_blocks);
+    const size_t smem = (size_t)THREADS * (B + 1) * sizeof(TIN);
+    const int grid = (int)((n_blocks + THREADS - 1) / THREADS);
+    const KwPhi phi = kw_transition<STRUCT>(kw, B);
+    jt_smem_optin((const void *)k_kw_blocks<TIN, STRUCT, 0, THREADS>, smem);
+    jt_smem_optin((const void *)k_kw_blocks<TIN, STRUCT, 1, THREADS>, smem);
+    k_kw_blocks<TIN, STRUCT, 0, THREADS><<<grid, THREADS, smem, c->stream>>>((const TIN *)in.d, in.n, B, n_blocks, kw, nullptr, d_e, nullptr, nullptr);
+    k_kw_scan<<<(int)((n_ticks + 127) / 128), 128, 0, c->stream>>>(d_e, n_blocks, P, n_ticks, 2 * P, phi, d_s);
+    k_kw_blocks<TIN, STRUCT, 1, THREADS><<<grid, THREADS, smem, c->stream>>>((const TIN *)in.d, in.n, B, n_blocks, kw, d_s, nullptr, d_eb, d_pk);
+    k_kw_fold<<<(int)((n_ticks + 255) / 256), 256, 0, c->stream>>>(d_eb, d_pk, n_blocks, P, n_ticks, d_pow, d_peak);
+}
+
 template <int STRUCT>
 static void run_ticks(jt_ctx *c, const Sig &in0, int tick, int64_t n_ticks_total, const KWeight &kw,
                       double *d_pow, double *d_peak)
 {
     if (n_ticks_total <= 0) return;
     const Sig in = in0.fmt == JT_FMT_S32 ? jt_convert(c, in0, JT_FMT_DBL) : in0;      // the filter's link is dbl: s32 widens exactly
+    {
+        static const char *lanes_only = getenv("JT_R128_LANES");
+        const int B = kw_block_size(tick);
+        // (the 4th-order direct form II of loudnorm's meter, STRUCT 1, keeps the lanes: its internal state is ~tau^2 = 6e5 times
+        //  the signal and the output a second difference of it, so a state re-derived to 1e-16 relative moves the output by
+        //  1e-8 -- the sequential rounding trajectory af_loudnorm's dynamic gains are tested against to 2e-9 is only reproduced by
+        //  walking it; the cascade of direct form I biquads of f_ebur128.c carries states of the signal's own size)
+        if (B && STRUCT == 0 && !(lanes_only && *lanes_only == '1')) {
+            JtLaunch Lb(c, in.rate >= 176400 ? "r128_kweight_ticks:192k" : "r128_kweight_ticks", 4);
+            if (in.fmt == JT_FMT_S16) run_ticks_blocks_t<int16_t, STRUCT>(c, in, tick, n_ticks_total, B, kw, d_pow, d_peak);
+            else if (in.fmt == JT_FMT_FLT) run_ticks_blocks_t<float, STRUCT>(c, in, tick, n_ticks_total, B, kw, d_pow, d_peak);
+            else run_ticks_blocks_t<double, STRUCT>(c, in, tick, n_ticks_total, B, kw, d_pow, d_peak);
+            return;
+        }
+    }
     // 34 KB of staging per warp: 6 warps per SM
     const int64_t slots = (int64_t)c->num_sms * 6 * 32;
     const int warm = tick + tick / 2;
