@@ -480,14 +480,22 @@ int jt_wav_parse(const void *bytes, int64_t n_bytes, int *sample_fmt, int *sampl
 /* ---- FLAC container of the chain's output ------------------------------------------------------------------
  * The reference hands its s16 mono 44.1 kHz result to libavcodec's FLAC encoder in 4096-sample frames
  * (internal/processor/encoder.go:92-101, processor.go:379-384).  jt_flac_encode writes a complete FLAC stream (RFC 9639:
- * "fLaC", STREAMINFO, fixed-block-size frames with CONSTANT / FIXED-predictor + partitioned Rice / VERBATIM subframes,
- * CRC-8 / CRC-16) of n mono s16 samples: bit-exact audio for any FLAC decoder, not the byte sequence libavcodec would emit
- * (its LPC search is not reproduced).  block_size 16..4096 (the reference uses 4096); MD5 is left "unknown" (zero). */
+ * "fLaC", STREAMINFO, fixed-block-size frames with CONSTANT / FIXED-predictor / LPC (orders 1..8, 12-bit coefficients, Welch
+ * window) + partitioned Rice / VERBATIM subframes, CRC-8 / CRC-16) of n mono s16 samples: bit-exact audio for any FLAC decoder,
+ * not the byte sequence libavcodec would emit (its order estimate is replaced by the measured residual of every order; streams
+ * come out 0.1 % smaller than its compression_level 5 on the synthetic recipes).  block_size 16..4096 (the reference uses 4096);
+ * MD5 is left "unknown" (zero): jt_flac_set_md5. */
 int64_t jt_flac_max_bytes(int64_t n_samples, int block_size);
 int jt_flac_encode(jt_ctx *ctx, const int16_t *pcm, int64_t n_samples, int sample_rate, int block_size,
                    void *out, int64_t out_cap, int64_t *n_bytes);
 int jt_flac_encode_dev(jt_ctx *ctx, const int16_t *d_pcm, int64_t n_samples, int sample_rate, int block_size,
                    void *d_out, int64_t out_cap, int64_t *n_bytes);
+
+/* STREAMINFO's MD5 of the unencoded samples (libavcodec's encoder fills it, encoder.go:92-101).  MD5 is a serial chain -- host
+ * work, ~0.5 s per hour of audio on one core -- so it is separate from the encode: jt_flac_encode leaves the field zero ("not
+ * known", legal), jt_flac_set_md5 fills it from the samples the stream was made of.  Host-only, no jt_ctx. */
+int jt_md5(const void *data, int64_t n_bytes, unsigned char out[16]);
+int jt_flac_set_md5(void *stream, int64_t n_bytes, const int16_t *pcm, int64_t n_samples);
 
 /* ---- input-side containers: what the reference's audio.Reader (internal/audio/reader.go:29-188: libavformat demux +
  * libavcodec decode) hands the passes, from a FILE IMAGE in memory ------------------------------------------------------------

@@ -18,6 +18,7 @@
 #include "jt_device.cuh"
 #include <cstdio>
 #include <cstring>
+#include <vector>
 
 namespace {
 constexpr int FL_WARPS = 4;                              // frames per CTA
@@ -25,6 +26,8 @@ constexpr int FL_MAX_BS = 4096;
 constexpr int FL_FRAME_CAP = 16 + 2 * FL_MAX_BS + 2 + 2; // header + verbatim subframe + CRC-16, multiple of 4 (8212)
 constexpr int FL_FRAME_WORDS = FL_FRAME_CAP / 4;
 constexpr int FL_MAX_PORDER = 6;
+constexpr int FL_LPC_MAX = 8;                            // LPC orders 1..8 (the reference's compression_level 5), 12-bit coefficients
+constexpr int FL_LPC_PREC = 12;
 static_assert(FL_FRAME_CAP % 4 == 0, "frame slots are copied as words");
 static_assert(FL_FRAME_WORDS >= 64 * 15, "the (u >> k) table borrows the frame buffer");
 
@@ -32,6 +35,9 @@ struct FlWarp {                                          // per-warp shared memo
     int16_t x[FL_MAX_BS + 64];                           // lane chunks skewed by one word each: see FL_X
     uint32_t frame[FL_FRAME_WORDS];
     uint16_t col[16];                                    // CRC-16 "append L zero bytes" operator, one column per state bit
+    int32_t lq[FL_LPC_MAX + 1][FL_LPC_MAX];              // quantised LPC coefficients of every order (lane 0 writes, all read)
+    int32_t lsh[FL_LPC_MAX + 1];
+    int32_t n_lpc;
 };
 
 __device__ __forceinline__ uint32_t fl_fold(int32_t r) { return ((uint32_t)r << 1) ^ (uint32_t)(r >> 31); }
@@ -41,23 +47,34 @@ __device__ __forceinline__ uint32_t fl_fold(int32_t r) { return ((uint32_t)r << 
 // every chunk is shifted by one more word (2 int16), which puts the lanes on 32 different banks.
 #define FL_X(i) (x[(i) + ((((i) >> xsh) << 1) & xpad)])
 
-// for (i in [a, b)) with r = residual of the fixed predictor `order` at i (a >= order): the previous four samples ride in
-// registers, one shared-memory read per sample
+// for (i in [a, b)) with r = residual at i of the predictor (c1 .. c8 on the previous eight samples, >> sh; a >= order): the
+// previous samples ride in registers, one shared-memory read per sample.  The fixed predictors are this with binomial
+// coefficients and sh = 0; unused taps are zero.
 #define FL_FOR_RES(a, b, BODY)                                                                                         \
     do {                                                                                                               \
         int i_ = (a);                                                                                                  \
         if (i_ < (b)) {                                                                                                \
             int32_t m1_ = i_ >= 1 ? FL_X(i_ - 1) : 0, m2_ = i_ >= 2 ? FL_X(i_ - 2) : 0, m3_ = i_ >= 3 ? FL_X(i_ - 3) : 0,    \
-                    m4_ = i_ >= 4 ? FL_X(i_ - 4) : 0;                                                                  \
+                    m4_ = i_ >= 4 ? FL_X(i_ - 4) : 0, m5_ = i_ >= 5 ? FL_X(i_ - 5) : 0, m6_ = i_ >= 6 ? FL_X(i_ - 6) : 0,    \
+                    m7_ = i_ >= 7 ? FL_X(i_ - 7) : 0, m8_ = i_ >= 8 ? FL_X(i_ - 8) : 0;                                \
             for (; i_ < (b); i_++) {                                                                                   \
                 const int32_t x0_ = FL_X(i_);                                                                          \
-                const int32_t r = order == 0 ? x0_ : order == 1 ? x0_ - m1_ : order == 2 ? x0_ - 2 * m1_ + m2_         \
-                                : order == 3 ? x0_ - 3 * m1_ + 3 * m2_ - m3_ : x0_ - 4 * m1_ + 6 * m2_ - 4 * m3_ + m4_; \
+                const int32_t r = x0_ - ((pc1 * m1_ + pc2 * m2_ + pc3 * m3_ + pc4 * m4_ + pc5 * m5_ + pc6 * m6_ + pc7 * m7_ + pc8 * m8_) >> psh); \
                 BODY;                                                                                                  \
-                m4_ = m3_; m3_ = m2_; m2_ = m1_; m1_ = x0_;                                                            \
+                m8_ = m7_; m7_ = m6_; m6_ = m5_; m5_ = m4_; m4_ = m3_; m3_ = m2_; m2_ = m1_; m1_ = x0_;                \
             }                                                                                                          \
         }                                                                                                              \
     } while (0)
+
+// Welch window in Q15 by an integer formula (the oracle's welch_q15)
+__host__ __device__ inline int32_t fl_welch_q15(int i, int n)
+{
+    const long long t = 2 * (long long)i - (n - 1), d = (long long)(n + 1) * (n + 1);
+    const long long w = 32767 - (t * t * 32767) / d;
+    return (int32_t)(w < 0 ? 0 : w);
+}
+
+__device__ __forceinline__ unsigned long long fl_est_bits(unsigned long long sum_abs, int n, unsigned long long overhead);
 
 __device__ __forceinline__ int fl_optimal_param(unsigned long long sum, int n)      // flacenc.c find_optimal_param
 {
@@ -66,6 +83,13 @@ __device__ __forceinline__ int fl_optimal_param(unsigned long long sum, int n)  
     if (q > 0x7fffffffull) q = 0x7fffffffull;
     const int k = q ? 31 - __clz((unsigned)q) : 0;     // av_log2(0) == 0
     return k > 14 ? 14 : k;
+}
+
+__device__ __forceinline__ unsigned long long fl_est_bits(unsigned long long sum_abs, int n, unsigned long long overhead)
+{
+    const unsigned long long S = 2 * sum_abs;
+    const int k = fl_optimal_param(S, n);
+    return overhead + (unsigned long long)n * (unsigned long long)(k + 1) + (S >> k);
 }
 
 __device__ __forceinline__ unsigned long long fl_warp_sum_u64(unsigned long long v)
@@ -104,6 +128,7 @@ __device__ __forceinline__ int fl_rate_code(int rate)
 
 __global__ void __launch_bounds__(FL_WARPS * 32)
 k_flac_frames(const int16_t *__restrict__ pcm, int64_t n, int block_size, int rate, int64_t n_frames,
+              const int16_t *__restrict__ win_full, const int16_t *__restrict__ win_last,
               uint32_t *__restrict__ stage, uint32_t *__restrict__ sizes)
 {
     extern __shared__ __align__(16) unsigned char fl_smem[];
@@ -149,16 +174,101 @@ k_flac_frames(const int16_t *__restrict__ pcm, int64_t n, int block_size, int ra
         }
         const bool constant = __all_sync(0xffffffffu, equal);
         // ---- decisions (no frame bytes yet) ----
-        int order = 0, best_p = 0, bk0 = 0, bk1 = 0, a0 = lo, a1 = mid;
-        bool verbatim = false, open0 = false, open1 = false;
+        int order = 0, best_p = 0, bk0 = 0, bk1 = 0, a0 = lo, a1 = mid, psh = 0;
+        int32_t pc1 = 0, pc2 = 0, pc3 = 0, pc4 = 0, pc5 = 0, pc6 = 0, pc7 = 0, pc8 = 0;
+        bool verbatim = false, open0 = false, open1 = false, is_lpc = false;
         unsigned lane_bits = 0;
         if (!constant) {
             e0 = fl_warp_sum_u64(e0); e1 = fl_warp_sum_u64(e1); e2 = fl_warp_sum_u64(e2); e3 = fl_warp_sum_u64(e3); e4 = fl_warp_sum_u64(e4);
-            unsigned long long best_err = e0;
-            if (bs > 1 && e1 < best_err) { best_err = e1; order = 1; }
-            if (bs > 2 && e2 < best_err) { best_err = e2; order = 2; }
-            if (bs > 3 && e3 < best_err) { best_err = e3; order = 3; }
-            if (bs > 4 && e4 < best_err) { best_err = e4; order = 4; }
+            // ---- LPC analysis: windowed autocorrelation (integer, exact), Levinson-Durbin + quantisation on lane 0 ----
+            int n_lpc = 0;
+            if (bs > FL_LPC_MAX + 1) {
+                const int16_t *win = bs == block_size ? win_full : win_last;      // nullptr: the ragged last block computes its window
+                long long R0 = 0, R1 = 0, R2 = 0, R3 = 0, R4 = 0, R5 = 0, R6 = 0, R7 = 0, R8 = 0;
+                {
+                    int32_t h1 = 0, h2 = 0, h3 = 0, h4 = 0, h5 = 0, h6 = 0, h7 = 0, h8 = 0;
+#define FL_XW(i) ((int32_t)(((int32_t)FL_X(i) * (win ? (int32_t)win[i] : fl_welch_q15((i), bs))) >> 8))
+                    if (lo >= 1 && lo < hi) h1 = FL_XW(lo - 1); if (lo >= 2 && lo < hi) h2 = FL_XW(lo - 2); if (lo >= 3 && lo < hi) h3 = FL_XW(lo - 3);
+                    if (lo >= 4 && lo < hi) h4 = FL_XW(lo - 4); if (lo >= 5 && lo < hi) h5 = FL_XW(lo - 5); if (lo >= 6 && lo < hi) h6 = FL_XW(lo - 6);
+                    if (lo >= 7 && lo < hi) h7 = FL_XW(lo - 7); if (lo >= 8 && lo < hi) h8 = FL_XW(lo - 8);
+                    for (int i = lo; i < hi; i++) {
+                        const int32_t v = FL_XW(i);
+                        R0 += (long long)v * v; R1 += (long long)v * h1; R2 += (long long)v * h2; R3 += (long long)v * h3; R4 += (long long)v * h4;
+                        R5 += (long long)v * h5; R6 += (long long)v * h6; R7 += (long long)v * h7; R8 += (long long)v * h8;
+                        h8 = h7; h7 = h6; h6 = h5; h5 = h4; h4 = h3; h3 = h2; h2 = h1; h1 = v;
+                    }
+#undef FL_XW
+                }
+                long long R[FL_LPC_MAX + 1] = {R0, R1, R2, R3, R4, R5, R6, R7, R8};
+#pragma unroll
+                for (int k = 0; k <= FL_LPC_MAX; k++) R[k] = (long long)fl_warp_sum_u64((unsigned long long)R[k]);
+                if (lane == 0) {
+                    int usable = 0;
+                    if (R[0] > 0) {
+                        double err = (double)R[0], lpc[FL_LPC_MAX], tmp[FL_LPC_MAX];
+                        for (int i = 0; i < FL_LPC_MAX; i++) {
+                            double acc = (double)R[i + 1];
+                            for (int j = 0; j < i; j++) acc = __dsub_rn(acc, __dmul_rn(lpc[j], (double)R[i - j]));
+                            const double k = __ddiv_rn(acc, err);
+                            for (int j = 0; j < i; j++) tmp[j] = __dsub_rn(lpc[j], __dmul_rn(k, lpc[i - 1 - j]));
+                            for (int j = 0; j < i; j++) lpc[j] = tmp[j];
+                            lpc[i] = k;
+                            err = __dmul_rn(err, __dsub_rn(1.0, __dmul_rn(k, k)));
+                            if (!(err > 0.0)) break;
+                            const int o = i + 1, qmax = (1 << (FL_LPC_PREC - 1)) - 1;
+                            double cmax = 0.0;
+                            for (int j = 0; j < o; j++) { const double a = lpc[j] < 0 ? -lpc[j] : lpc[j]; if (a > cmax) cmax = a; }
+                            int sh = 14;
+                            while (sh > 0 && __dmul_rn(cmax, (double)(1 << sh)) > (double)qmax) sh--;
+                            double e = 0.0;
+                            for (int j = 0; j < o; j++) {
+                                e = __dadd_rn(e, __dmul_rn(lpc[j], (double)(1 << sh)));
+                                long long v = __double2ll_rn(e);
+                                if (v > qmax) v = qmax;
+                                if (v < -qmax) v = -qmax;
+                                S.lq[o][j] = (int32_t)v;
+                                e = __dsub_rn(e, (double)v);
+                            }
+                            for (int j = o; j < FL_LPC_MAX; j++) S.lq[o][j] = 0;
+                            S.lsh[o] = sh;
+                            usable = o;
+                        }
+                    }
+                    S.n_lpc = usable;
+                }
+                __syncwarp();
+                n_lpc = S.n_lpc;
+            }
+            // ---- candidates: FIXED 0..4, then LPC 1..n_lpc, scored by the Rice-cost estimate of sum |residual| + header; first minimum wins ----
+            unsigned long long best_est = ~0ull;
+            {
+                const unsigned long long ef[5] = {e0, e1, e2, e3, e4};
+                const int32_t fc[5][4] = {{0, 0, 0, 0}, {1, 0, 0, 0}, {2, -1, 0, 0}, {3, -3, 1, 0}, {4, -6, 4, -1}};
+                for (int o = 0; o <= 4 && o < bs; o++) {
+                    const unsigned long long b = fl_est_bits(ef[o], bs - o, 16ull * (unsigned)o);
+                    if (b < best_est) { best_est = b; order = o; pc1 = fc[o][0]; pc2 = fc[o][1]; pc3 = fc[o][2]; pc4 = fc[o][3]; }
+                }
+            }
+            for (int o = 1; o <= n_lpc; o++) {
+                const int32_t c1 = S.lq[o][0], c2 = S.lq[o][1], c3 = S.lq[o][2], c4 = S.lq[o][3], c5 = S.lq[o][4], c6 = S.lq[o][5], c7 = S.lq[o][6], c8 = S.lq[o][7];
+                const int sh = S.lsh[o];
+                unsigned long long e = 0;
+                {
+                    int i = max(lo, o);
+                    if (i < hi) {
+                        int32_t m1 = FL_X(i - 1), m2 = i >= 2 ? FL_X(i - 2) : 0, m3 = i >= 3 ? FL_X(i - 3) : 0, m4 = i >= 4 ? FL_X(i - 4) : 0,
+                                m5 = i >= 5 ? FL_X(i - 5) : 0, m6 = i >= 6 ? FL_X(i - 6) : 0, m7 = i >= 7 ? FL_X(i - 7) : 0, m8 = i >= 8 ? FL_X(i - 8) : 0;
+                        for (; i < hi; i++) {
+                            const int32_t x0 = FL_X(i);
+                            e += (unsigned)abs(x0 - ((c1 * m1 + c2 * m2 + c3 * m3 + c4 * m4 + c5 * m5 + c6 * m6 + c7 * m7 + c8 * m8) >> sh));
+                            m8 = m7; m7 = m6; m6 = m5; m5 = m4; m4 = m3; m3 = m2; m2 = m1; m1 = x0;
+                        }
+                    }
+                }
+                e = fl_warp_sum_u64(e);
+                const unsigned long long b = fl_est_bits(e, bs - o, 16ull * (unsigned)o + 9ull + (unsigned long long)FL_LPC_PREC * (unsigned)o);
+                if (b < best_est) { best_est = b; order = o; is_lpc = true; psh = sh; pc1 = c1; pc2 = c2; pc3 = c3; pc4 = c4; pc5 = c5; pc6 = c6; pc7 = c7; pc8 = c8; }
+            }
             a0 = max(lo, order); a1 = max(mid, order);                    // residual samples of the two cells: [a0, mid), [a1, hi)
             // one pass: per cell, the sum of (u >> k) for every Rice parameter k (k = 0 is the plain sum that picks the parameter)
             {
@@ -197,8 +307,9 @@ k_flac_frames(const int16_t *__restrict__ pcm, int64_t n, int block_size, int ra
                 const unsigned long long bits = fl_warp_sum_u64((unsigned long long)mine) + 4ull * (unsigned long long)(1 << p);
                 if (bits < best_bits) { best_bits = bits; best_p = p; bk0 = k0; bk1 = k1; best_lane = mine; }
             }
-            const unsigned long long fixed_bits = 8ull + 16ull * (unsigned)order + 6ull + best_bits, verbatim_bits = 8ull + 16ull * (unsigned)bs;
-            verbatim = fixed_bits >= verbatim_bits;
+            const unsigned long long coded_bits = 8ull + 16ull * (unsigned)order + (is_lpc ? 9ull + (unsigned long long)FL_LPC_PREC * (unsigned)order : 0ull) + 6ull + best_bits,
+                                     verbatim_bits = 8ull + 16ull * (unsigned)bs;
+            verbatim = coded_bits >= verbatim_bits;
             const int per = 64 >> best_p;
             // a cell opens a partition (4-bit parameter in front of it) when it is the partition's first cell
             open0 = cells ? ((2 * lane) % per) == 0 : lane == 0;
@@ -238,13 +349,20 @@ k_flac_frames(const int16_t *__restrict__ pcm, int64_t n, int block_size, int ra
         } else {
             unsigned incl = lane_bits;
             for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-            const int base = sub0 + 8 + 16 * order + 6;
+            const int lpc_bits = is_lpc ? 9 + FL_LPC_PREC * order : 0;
+            const int base = sub0 + 8 + 16 * order + lpc_bits + 6;
             int pos = base + (int)(incl - lane_bits);
             total_bits = base + (int)__shfl_sync(0xffffffffu, incl, 31);
             if (lane == 0) {
-                fl_put(S.frame, sub0, 8, (uint32_t)((0x08 | order) << 1));
+                fl_put(S.frame, sub0, 8, (uint32_t)((is_lpc ? (0x20 | (order - 1)) : (0x08 | order)) << 1));
                 for (int i = 0; i < order; i++) fl_put(S.frame, sub0 + 8 + 16 * i, 16, (uint16_t)FL_X(i));
-                fl_put(S.frame, sub0 + 8 + 16 * order, 6, (uint32_t)best_p);       // method 00 + partition order
+                if (is_lpc) {
+                    int q = sub0 + 8 + 16 * order;
+                    fl_put(S.frame, q, 4, (uint32_t)(FL_LPC_PREC - 1)); fl_put(S.frame, q + 4, 5, (uint32_t)psh); q += 9;
+                    const int32_t cc[8] = {pc1, pc2, pc3, pc4, pc5, pc6, pc7, pc8};
+                    for (int j = 0; j < order; j++) fl_put(S.frame, q + FL_LPC_PREC * j, FL_LPC_PREC, (uint32_t)cc[j] & ((1u << FL_LPC_PREC) - 1));
+                }
+                fl_put(S.frame, sub0 + 8 + 16 * order + lpc_bits, 6, (uint32_t)best_p);       // method 00 + partition order
             }
             if (open0) { fl_put(S.frame, pos, 4, (uint32_t)bk0); pos += 4; }
             FL_FOR_RES(a0, mid, {
@@ -322,9 +440,13 @@ void *jt_flac_encode_device(jt_ctx *c, const int16_t *d_pcm, int64_t n, int rate
         const size_t smem = sizeof(FlWarp) * FL_WARPS;
         jt_smem_optin((const void *)k_flac_frames, smem);
         const int grid = (int)std::min<int64_t>((frames + FL_WARPS - 1) / FL_WARPS, (int64_t)c->num_sms * 12);
+        // Welch window (Q15, integer formula) of the nominal block; a ragged last block computes its own in the kernel
+        std::vector<int16_t> wf((size_t)block_size);
+        for (int i = 0; i < block_size; i++) wf[i] = (int16_t)fl_welch_q15(i, block_size);
+        const int16_t *d_wf = jt_dev_table(c, "flac_welch", wf), *d_wl = nullptr;
         {
             JtLaunch L(c, "flac:frames");
-            k_flac_frames<<<grid, FL_WARPS * 32, smem, c->stream>>>(d_pcm, n, block_size, rate, frames, d_stage, d_sizes);
+            k_flac_frames<<<grid, FL_WARPS * 32, smem, c->stream>>>(d_pcm, n, block_size, rate, frames, d_wf, d_wl, d_stage, d_sizes);
         }
         uint32_t *h_sizes = jt_pinned<uint32_t>(c, (size_t)frames);
         JT_CUDA(cudaMemcpyAsync(h_sizes, d_sizes, sizeof(uint32_t) * frames, cudaMemcpyDeviceToHost, c->stream));

@@ -157,6 +157,8 @@ def lib():
     for name in ("jt_flac_decode", "jt_flac_decode_dev", "jt_wav_decode", "jt_wav_decode_dev"):
         getattr(L, name).argtypes = dec
     L.jt_prefetch_input.argtypes = [_P, _P, _I64, _INT, _INT]
+    L.jt_md5.argtypes = [_P, _I64, _P]
+    L.jt_flac_set_md5.argtypes = [_P, _I64, _P, _I64]
     L.jt_cuda_stream.restype = _P
     L.jt_cuda_stream.argtypes = [_P]
     L.jt_launch_count.restype = _I64
@@ -189,6 +191,16 @@ def flac_stream_info(data):
     if rc != 0:
         raise JtError(rc, "jt_flac_stream_info")
     return dict(fmt=fmt.value, rate=rate.value, channels=ch.value, bits=bits.value, n_frames=nfr.value, audio_offset=off.value)
+
+
+def flac_set_md5(stream, pcm_s16):
+    """stream bytes with STREAMINFO's MD5 filled in from the mono s16 samples it encodes (host only)"""
+    buf = bytearray(stream)
+    pcm = np.ascontiguousarray(pcm_s16, dtype=np.int16)
+    rc = lib().jt_flac_set_md5((C.c_char * len(buf)).from_buffer(buf), len(buf), pcm.ctypes.data_as(_P), len(pcm))
+    if rc != 0:
+        raise JtError(rc, "jt_flac_set_md5")
+    return bytes(buf)
 
 
 def pass1_spec():

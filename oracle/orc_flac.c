@@ -24,6 +24,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <math.h>
 
 /* ---- bit writer (MSB first) ---- */
 typedef struct { uint8_t *p; int64_t cap, bit; int overflow; } BW;
@@ -94,6 +95,75 @@ static inline int32_t fixed_res(const int16_t *x, int64_t i, int order)
 
 #define ORC_FLAC_MAX_PORDER 6
 
+/* ---- LPC subframes (RFC 9639 section 9.2.6): the analysis is integer up to the autocorrelation, so the CUDA encoder and this one
+ * take the same decisions bit for bit.  Window: Welch, Q15, integer formula; windowed samples cut to 23 bits so that the 9 lags
+ * of a 4096-sample block sum exactly in int64; Levinson-Durbin in double with every operation rounded on its own (no fused
+ * multiply-add on either side); 12-bit coefficients with the shift and error feedback of flacenc.c's quantize_lpc_coefs, so the
+ * prediction of 16-bit samples up to order 8 fits 32-bit arithmetic. ---- */
+#define ORC_LPC_MAX 8
+#define ORC_LPC_PREC 12
+static int32_t welch_q15(int i, int n)
+{
+    const int64_t t = 2 * (int64_t)i - (n - 1), d = (int64_t)(n + 1) * (n + 1);
+    const int64_t w = 32767 - (t * t * 32767) / d;
+    return (int32_t)(w < 0 ? 0 : w);
+}
+/* coefficients (quantised) and shift of every order 1..maxo; returns the number of usable orders (0: no LPC for this block) */
+static int lpc_analyse(const int16_t *x, int bs, int maxo, int32_t q[ORC_LPC_MAX + 1][ORC_LPC_MAX], int shift[ORC_LPC_MAX + 1])
+{
+    int64_t R[ORC_LPC_MAX + 1];
+    int32_t *xw = (int32_t *)malloc(sizeof(int32_t) * (size_t)bs);
+    for (int i = 0; i < bs; i++) xw[i] = ((int32_t)x[i] * welch_q15(i, bs)) >> 8;
+    for (int k = 0; k <= maxo; k++) { int64_t a = 0; for (int i = k; i < bs; i++) a += (int64_t)xw[i] * xw[i - k]; R[k] = a; }
+    free(xw);
+    if (R[0] <= 0) return 0;
+    volatile double err = (double)R[0];
+    double lpc[ORC_LPC_MAX], tmp[ORC_LPC_MAX];
+    int usable = 0;
+    for (int i = 0; i < maxo; i++) {
+        volatile double acc = (double)R[i + 1];
+        for (int j = 0; j < i; j++) { volatile double m = lpc[j] * (double)R[i - j]; acc = acc - m; }
+        const double k = acc / err;
+        for (int j = 0; j < i; j++) { volatile double m = k * lpc[i - 1 - j]; tmp[j] = lpc[j] - m; }
+        for (int j = 0; j < i; j++) lpc[j] = tmp[j];
+        lpc[i] = k;
+        { volatile double kk = k * k; volatile double om = 1.0 - kk; err = err * om; }
+        if (!(err > 0.0)) break;
+        /* quantise order i + 1 */
+        const int o = i + 1, qmax = (1 << (ORC_LPC_PREC - 1)) - 1;
+        double cmax = 0.0;
+        for (int j = 0; j < o; j++) { const double a = lpc[j] < 0 ? -lpc[j] : lpc[j]; if (a > cmax) cmax = a; }
+        int sh = 14;
+        while (sh > 0 && cmax * (double)(1 << sh) > (double)qmax) sh--;
+        volatile double e = 0.0;
+        for (int j = 0; j < o; j++) {
+            volatile double m = lpc[j] * (double)(1 << sh);
+            e = e + m;
+            long long v = llrint(e);
+            if (v > qmax) v = qmax;
+            if (v < -qmax) v = -qmax;
+            q[o][j] = (int32_t)v;
+            e = e - (double)v;
+        }
+        shift[o] = sh;
+        usable = o;
+    }
+    return usable;
+}
+/* residual of the predictor (coefficients c[0..order-1] on x[i-1], x[i-2], ..., result >> sh) at sample i >= order */
+static inline int32_t pred_res(const int16_t *x, int64_t i, int order, const int32_t *c, int sh)
+{
+    int32_t a = 0;
+    for (int j = 0; j < order; j++) a += c[j] * (int32_t)x[i - 1 - j];
+    return (int32_t)x[i] - (a >> sh);
+}
+static uint64_t est_bits(uint64_t sum_abs, int n, uint64_t overhead)
+{
+    const uint64_t S = 2 * sum_abs;
+    const int k = optimal_param(S, n);
+    return overhead + (uint64_t)n * (uint64_t)(k + 1) + (S >> k);
+}
+
 /* one frame; returns bytes written */
 static int64_t encode_frame(const int16_t *x, int bs, int nominal_bs, int rate, uint64_t frame_no, uint8_t *out, int64_t cap)
 {
@@ -115,13 +185,24 @@ static int64_t encode_frame(const int16_t *x, int bs, int nominal_bs, int rate, 
     if (constant) {
         bw_put(&w, 8, 0x00); bw_put(&w, 16, (uint16_t)x[0]);
     } else {
-        int best_order = 0; uint64_t best_err = ~0ull;
+        /* candidates: FIXED orders 0..4, then LPC orders 1..8; each scored by the Rice-cost estimate of its sum |residual|
+         * plus its header; the first minimum wins */
+        static const int32_t fixed_c[5][4] = {{0, 0, 0, 0}, {1, 0, 0, 0}, {2, -1, 0, 0}, {3, -3, 1, 0}, {4, -6, 4, -1}};
+        int32_t lq[ORC_LPC_MAX + 1][ORC_LPC_MAX]; int lsh[ORC_LPC_MAX + 1];
+        const int n_lpc = bs > ORC_LPC_MAX + 1 ? lpc_analyse(x, bs, ORC_LPC_MAX, lq, lsh) : 0;
+        int order = 0, is_lpc = 0, sh = 0; int32_t coef[ORC_LPC_MAX] = {0}; uint64_t best_est = ~0ull;
         for (int o = 0; o <= 4 && o < bs; o++) {
             uint64_t e = 0;
-            for (int i = o; i < bs; i++) { int32_t r = fixed_res(x, i, o); e += (uint64_t)(r < 0 ? -(int64_t)r : r); }
-            if (e < best_err) { best_err = e; best_order = o; }
+            for (int i = o; i < bs; i++) { int32_t r = pred_res(x, i, o, fixed_c[o], 0); e += (uint64_t)(r < 0 ? -(int64_t)r : r); }
+            const uint64_t b = est_bits(e, bs - o, 16ull * (uint64_t)o);
+            if (b < best_est) { best_est = b; order = o; is_lpc = 0; sh = 0; memset(coef, 0, sizeof(coef)); memcpy(coef, fixed_c[o], sizeof(int32_t) * 4); }
         }
-        const int order = best_order;
+        for (int o = 1; o <= n_lpc; o++) {
+            uint64_t e = 0;
+            for (int i = o; i < bs; i++) { int32_t r = pred_res(x, i, o, lq[o], lsh[o]); e += (uint64_t)(r < 0 ? -(int64_t)r : r); }
+            const uint64_t b = est_bits(e, bs - o, 16ull * (uint64_t)o + 9 + (uint64_t)ORC_LPC_PREC * (uint64_t)o);
+            if (b < best_est) { best_est = b; order = o; is_lpc = 1; sh = lsh[o]; memset(coef, 0, sizeof(coef)); memcpy(coef, lq[o], sizeof(int32_t) * (size_t)o); }
+        }
         int pmax = 0;
         if (bs % 64 == 0) { pmax = ORC_FLAC_MAX_PORDER; while (pmax > 0 && (bs >> pmax) <= order) pmax--; }
         int best_p = 0; uint64_t best_bits = ~0ull; int best_k[1 << ORC_FLAC_MAX_PORDER];
@@ -129,29 +210,34 @@ static int64_t encode_frame(const int16_t *x, int bs, int nominal_bs, int rate, 
             const int psz = bs >> p; uint64_t bits = 0; int ks[1 << ORC_FLAC_MAX_PORDER];
             for (int j = 0; j < (1 << p); j++) {
                 const int a = j * psz < order ? order : j * psz, b = (j + 1) * psz, n = b - a;
-                uint64_t s = 0;
-                for (int i = a; i < b; i++) s += fold(fixed_res(x, i, order));
-                const int k = optimal_param(s, n);
-                uint64_t sh = 0;
-                for (int i = a; i < b; i++) sh += fold(fixed_res(x, i, order)) >> k;
-                bits += 4 + (uint64_t)n * (uint64_t)(k + 1) + sh;
+                uint64_t sum = 0;
+                for (int i = a; i < b; i++) sum += fold(pred_res(x, i, order, coef, sh));
+                const int k = optimal_param(sum, n);
+                uint64_t shs = 0;
+                for (int i = a; i < b; i++) shs += fold(pred_res(x, i, order, coef, sh)) >> k;
+                bits += 4 + (uint64_t)n * (uint64_t)(k + 1) + shs;
                 ks[j] = k;
             }
             if (bits < best_bits) { best_bits = bits; best_p = p; memcpy(best_k, ks, sizeof(int) * (size_t)(1 << p)); }
         }
-        const uint64_t fixed_bits = 8 + 16ull * (uint64_t)order + 6 + best_bits, verbatim_bits = 8 + 16ull * (uint64_t)bs;
-        if (fixed_bits >= verbatim_bits) {
+        const uint64_t head_bits = 8 + 16ull * (uint64_t)order + (is_lpc ? 9 + (uint64_t)ORC_LPC_PREC * (uint64_t)order : 0) + 6;
+        const uint64_t coded_bits = head_bits + best_bits, verbatim_bits = 8 + 16ull * (uint64_t)bs;
+        if (coded_bits >= verbatim_bits) {
             bw_put(&w, 8, 0x02);
             for (int i = 0; i < bs; i++) bw_put(&w, 16, (uint16_t)x[i]);
         } else {
-            bw_put(&w, 8, (uint64_t)((0x08 | order) << 1));
+            bw_put(&w, 8, (uint64_t)((is_lpc ? (0x20 | (order - 1)) : (0x08 | order)) << 1));
             for (int i = 0; i < order; i++) bw_put(&w, 16, (uint16_t)x[i]);
+            if (is_lpc) {
+                bw_put(&w, 4, ORC_LPC_PREC - 1); bw_put(&w, 5, (uint64_t)sh);
+                for (int j = 0; j < order; j++) bw_put(&w, ORC_LPC_PREC, (uint64_t)(uint32_t)coef[j] & ((1u << ORC_LPC_PREC) - 1));
+            }
             bw_put(&w, 2, 0); bw_put(&w, 4, (uint64_t)best_p);
             const int psz = bs >> best_p;
             for (int j = 0; j < (1 << best_p); j++) {
                 const int a = j * psz < order ? order : j * psz, b = (j + 1) * psz, k = best_k[j];
                 bw_put(&w, 4, (uint64_t)k);
-                for (int i = a; i < b; i++) { const uint32_t u = fold(fixed_res(x, i, order)); bw_unary(&w, u >> k); if (k) bw_put(&w, k, u & ((1u << k) - 1)); }
+                for (int i = a; i < b; i++) { const uint32_t u = fold(pred_res(x, i, order, coef, sh)); bw_unary(&w, u >> k); if (k) bw_put(&w, k, u & ((1u << k) - 1)); }
             }
         }
     }

@@ -124,3 +124,34 @@ def test_input_decoder_rejects_corruption():
     s[len(s) // 2] ^= 0x10
     with pytest.raises(ValueError):
         ref_flac.decode_pcm(bytes(s), 40000)
+
+
+# ---- LPC subframes and the MD5 field ------------------------------------------------------------------------------------------
+def test_lpc_streams_are_no_larger_than_libavcodec_level_5():
+    """the encoder's LPC subframes (orders 1..8 scored by their measured residual) against the REAL libavcodec encoder at the
+    reference's compression_level 5 (encoder.go:92-101), on the synthetic recipes: ours must not be larger"""
+    for name, x in (("speech", synth.speech_like(20.0, 44100, seed=3)), ("podcast", synth.podcast_like(20.0, 44100, seed=4))):
+        pcm = s16(x)
+        ours = ref_flac.encode(pcm, 44100, 4096)
+        y, _ = ref_flac.decode(ours, len(pcm) + 16)
+        assert np.array_equal(y, pcm)
+        lav = ref_flac.ref_encode(pcm, 44100, 5)
+        if lav is None:
+            pytest.skip("no libavcodec encoder probe on this box")
+        assert len(ours) <= len(lav), (name, len(ours), len(lav))
+        assert len(ours) < 0.96 * len(ref_flac.ref_encode(pcm, 44100, 0))          # level 0 = fixed predictors only
+        ref = ref_flac.ref_decode(ours)
+        assert ref is not None and np.array_equal(ref[0], pcm)
+
+
+def test_md5_field():
+    import hashlib
+    from jivetalking_b200 import gpudsp
+    rng = np.random.default_rng(2)
+    for n in (0, 1, 27, 28, 55, 56, 63, 64, 65, 4096, 44100):
+        pcm = rng.integers(-32768, 32767, size=n).astype(np.int16)
+        st = ref_flac.encode(pcm, 44100, 4096)
+        out = gpudsp.flac_set_md5(st, pcm)
+        assert out[26:42] == hashlib.md5(pcm.tobytes()).digest() and out[:26] == st[:26] and out[42:] == st[42:]
+    y, _ = ref_flac.decode(out, 44100 + 16)
+    assert np.array_equal(y, pcm)
