@@ -527,6 +527,11 @@ int jt_wav_decode_dev(jt_ctx *ctx, const void *d_bytes, int64_t n_bytes, void *d
  * cudaHostRegister): pageable memory is legal but copies synchronously.  Two copies may be outstanding per context. */
 int jt_prefetch_input(jt_ctx *ctx, const void *pcm, int64_t n_frames, int channels, int sample_fmt);
 
+/* Host threads one call may use for its per-frame metadata work (default: up to 8; 0 restores the default).  Process-wide.  A
+ * process that shares its node with other workers -- the ranks of jt_process_audio_sharded do this themselves -- should divide the
+ * cores among them.  Also settable as JT_HOST_THREADS. */
+void jt_set_host_threads(int n);
+
 /* the cudaStream_t (as void *) every kernel and copy of this context is issued on, so a caller can order its own
  * device work against it or bracket calls with CUDA events */
 void   *jt_cuda_stream(const jt_ctx *ctx);

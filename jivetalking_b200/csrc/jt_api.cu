@@ -3,6 +3,7 @@
 // extractFrameMetadata / extractOutputFrameMetadata analyser_metrics.go:784-924,
 // ApplyNormalisation normalise.go:722-905) restated in C++ above the kernels.
 #include "jt_graph.h"
+#include <thread>
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
@@ -1929,6 +1930,9 @@ static int sharded_common(jt_ctx *c, const void *pcm_local, bool on_device, int6
     return guarded(c, [&]() {
         if (!pcm_local && n_local > 0) JT_THROW(JT_ERR_INVALID_ARG, "null input");
         if (!jt_valid_fmt(fmt)) JT_THROW(JT_ERR_UNSUPPORTED, "input sample format %d", fmt);
+        // the ranks of a sharded stream usually share a node: split its cores among them for the host-side merges (unless the
+        // caller has set a number)
+        { static bool once = false; if (!once && world > 1 && !getenv("JT_HOST_THREADS")) { jt_set_host_threads((int)std::max(1u, std::thread::hardware_concurrency() / (unsigned)world)); once = true; } }
         const double t0 = ShardComm::host_seconds();
         const void *d_in = on_device ? pcm_local : upload(c, pcm_local, (size_t)n_local * channels * jt_fmt_bytes(fmt));
         JT_CUDA(cudaStreamSynchronize(c->stream));

@@ -7,6 +7,8 @@
 // (which sink frame inherits which astats / aspectralstats / ebur128 stamp, and after which
 // pushed input frame it becomes pullable).
 #include "jt_graph.h"
+#include <atomic>
+#include <cstdlib>
 #include <algorithm>
 #include <array>
 #include <cstdio>
@@ -135,6 +137,20 @@ static bool wire_g6(double v, double *out)
         return true;
     }
     return false;
+}
+
+// Host threads one call may use for its per-frame metadata work (the "%g" rounding of ~13 values per sink frame).  Default: up to 8;
+// a process that shares its node with other ranks of a sharded stream divides the cores among them (jt_set_host_threads, or
+// JT_HOST_THREADS) -- eight ranks x eight threads on sixteen cores was most of pass1_merge in profiles/bench_r2i_n8.json.
+static std::atomic<int> g_host_threads{0};
+extern "C" void jt_set_host_threads(int n) { g_host_threads.store(n < 0 ? 0 : n); }
+unsigned jt_host_threads()
+{
+    int n = g_host_threads.load();
+    if (n <= 0) { static const char *e = getenv("JT_HOST_THREADS"); if (e) n = atoi(e); }
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    if (n <= 0) n = 8;
+    return std::max(1u, std::min((unsigned)n, hw));
 }
 
 double jt_wire(const char *fmt, double v)
@@ -631,7 +647,7 @@ static void assemble_records(const std::vector<FrameRef> &frames, bool has_r128,
                 for (int k = 0; k < JT_SP_COUNT; k++) m.spectral[k] = jt_wire("%g", (double)spec_rows[(size_t)fr.hop * JT_SP_COUNT + k]);
         }
     };
-    const unsigned hw = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+    const unsigned hw = jt_host_threads();
     if (nf < 8192 || hw == 1) fill(0, nf);
     else {
         const size_t per = (nf + hw - 1) / hw;
@@ -723,7 +739,7 @@ void jt_accumulate_frames(const std::vector<FrameRef> &frames, bool has_r128, co
         if (last_tick_frame >= 0) { out->input_i = jt_wire("%.3f", r128.I); out->input_lra = jt_wire("%.3f", r128.LRA); }
     }
     if (has_spec && nf) {
-        const unsigned hw = std::max(1u, std::min(8u, std::thread::hardware_concurrency()));
+        const unsigned hw = jt_host_threads();
         const unsigned nth = nf < 8192 ? 1u : hw;
         std::vector<std::array<double, JT_SP_COUNT + 1>> part(nth);
         auto work = [&](unsigned t) {

@@ -97,3 +97,4 @@ void jt_graph_run(jt_ctx *c, const std::string &spec, const void *d_in, int64_t 
                   int fmt, int frame_size, bool want_pcm, bool want_meta, GraphResult &res);
 
 double jt_wire(const char *fmt, double v);    // value as the Go side parses it back from FFmpeg's printf
+unsigned jt_host_threads();                   // host threads a call may use for per-frame metadata work (jt_set_host_threads)
