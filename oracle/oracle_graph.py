@@ -515,6 +515,12 @@ def assert_meta_close(got, exp, spectral_rtol=2e-3, spectral_atol=1e-9, astats_a
     # signed statistics (skewness, slope, decrease) cancel towards 0: scale their absolute tolerance
     # by the column's magnitude over the stream
     col_scale = [max([abs(e["spectral"][k]) for e in exp if math.isfinite(e["spectral"][k])] + [0.0]) for k in range(13)]
+    # the rolloff (column 12) is the frequency of the BIN where the cumulative energy crosses 85 %: quantised to rate / win_size,
+    # so round-off that moves the crossing by a hair moves the value by a whole bin.  Behind f32 stages whose noise floor depends
+    # on where a lane starts, one bin either way is accepted in at most 1 % of the frames.
+    rolls = sorted({e["spectral"][12] for e in exp if math.isfinite(e["spectral"][12])})
+    roll_step = min([b - a for a, b in zip(rolls, rolls[1:]) if b - a > 1e-9] + [0.0])
+    roll_flips = 0
     for i, (g, e) in enumerate(zip(got, exp)):
         assert g.first_sample == e["first_sample"] and g.nb_samples == e["nb_samples"], (i, g.first_sample, e)
         for name, gv, ev in (("M", g.r128_M, e["M"]), ("S", g.r128_S, e["S"]), ("I", g.r128_I, e["I"]),
@@ -529,7 +535,11 @@ def assert_meta_close(got, exp, spectral_rtol=2e-3, spectral_atol=1e-9, astats_a
             if roundoff_only:
                 assert math.isnan(g.spectral[k]) == math.isnan(e["spectral"][k]), (i, "spectral", k)
                 continue
-            assert _close(g.spectral[k], e["spectral"][k], spectral_atol + 2e-4 * col_scale[k] + (2e-4 if k in (4, 5) else 0.0), spectral_rtol), (i, "spectral", k, g.spectral[k], e["spectral"][k])
+            ok = _close(g.spectral[k], e["spectral"][k], spectral_atol + 2e-4 * col_scale[k] + (2e-4 if k in (4, 5) else 0.0), spectral_rtol)
+            if not ok and k == 12 and roll_step > 0 and abs(g.spectral[k] - e["spectral"][k]) <= roll_step * 1.001:
+                roll_flips += 1
+                ok = roll_flips <= max(1, len(exp) // 100)
+            assert ok, (i, "spectral", k, g.spectral[k], e["spectral"][k])
         if e["astats"] is None:
             assert all(math.isnan(g.astats[k]) for k in range(len(AS_NAMES))), (i, "unexpected astats")
         else:

@@ -198,5 +198,7 @@ def test_adaptive_chain_sharded_equals_single_gpu(ctx, podcast, analysis):
     assert len(pcm) == len(pcm1) == res1.n_out
     d = (pcm.astype(np.int32) - pcm1.astype(np.int32)) / 32768.0
     assert float(np.sqrt(np.mean(d * d))) < 1e-4
-    assert abs(r["final"].input_i - res1.final.input_i) <= 0.01 and abs(r["final"].input_tp - res1.final.input_tp) <= 0.01
+    # the true peak reaches the host as a linear value printed with three decimals ("%.3f" of ~0.56: one step is 0.0154 dB), and
+    # a chunk boundary moves the f32 biquads' rounding noise, so the last decimal may differ by one
+    assert abs(r["final"].input_i - res1.final.input_i) <= 0.01 and abs(r["final"].input_tp - res1.final.input_tp) <= 0.02
     assert abs(r["final"].input_lra - res1.final.input_lra) <= 0.05
