@@ -1408,7 +1408,8 @@ static void analyse_adaptive_device(jt_ctx *c, const void *d_in, int64_t n_frame
     if (n_iv_out) *n_iv_out = n_iv;
     if (out->measurements.sink_frames == 0 || std::isnan(out->measurements.input_i))
         JT_THROW(JT_ERR_INVALID_ARG, "ebur128 measurements not found in metadata (analyser.go:397-399)");
-    int rc = jt_detect_voice_activity(&out->measurements, iv, n_iv, &out->voice_activity, nullptr, 0, nullptr, 0);
+    int rc;
+    { JtHost hdet(c, "voice_activity_detector"); rc = jt_detect_voice_activity(&out->measurements, iv, n_iv, &out->voice_activity, nullptr, 0, nullptr, 0); }
     if (rc) JT_THROW(rc, "voice-activity detector");
     jt_voice_activity &va = out->voice_activity;
     // measureSpeechBands + measureNoiseBands: the 2 + 15 band graphs of analyser_bands.go:33 over the elected regions
@@ -1438,7 +1439,7 @@ static void analyse_adaptive_device(jt_ctx *c, const void *d_in, int64_t n_frame
         swap.reset();
         jt_apply_band_rms(&va, want_speech ? rms : nullptr, want_speech ? found : nullptr, want_noise ? rms + 2 : nullptr, want_noise ? found + 2 : nullptr);
     }
-    rc = jt_adapt_config(base, &out->measurements, &va, &out->config, &out->diagnostics);
+    { JtHost hcfg(c, "adapt_config"); rc = jt_adapt_config(base, &out->measurements, &va, &out->config, &out->diagnostics); }
     if (rc) JT_THROW(rc, "AdaptConfig");
     rc = jt_build_filter_spec(&out->config, out->pass2_spec, sizeof(out->pass2_spec));
     if (rc) JT_THROW(rc, "BuildFilterSpec");

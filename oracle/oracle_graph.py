@@ -519,7 +519,8 @@ def assert_meta_close(got, exp, spectral_rtol=2e-3, spectral_atol=1e-9, astats_a
     # so round-off that moves the crossing by a hair moves the value by a whole bin.  Behind f32 stages whose noise floor depends
     # on where a lane starts, one bin either way is accepted in at most 1 % of the frames.
     rolls = sorted({e["spectral"][12] for e in exp if math.isfinite(e["spectral"][12])})
-    roll_step = min([b - a for a, b in zip(rolls, rolls[1:]) if b - a > 1e-9] + [0.0])
+    roll_gaps = [b - a for a, b in zip(rolls, rolls[1:]) if b - a > 1e-9]
+    roll_step = min(roll_gaps) if roll_gaps else 0.0
     roll_flips = 0
     for i, (g, e) in enumerate(zip(got, exp)):
         assert g.first_sample == e["first_sample"] and g.nb_samples == e["nb_samples"], (i, g.first_sample, e)
@@ -536,10 +537,10 @@ def assert_meta_close(got, exp, spectral_rtol=2e-3, spectral_atol=1e-9, astats_a
                 assert math.isnan(g.spectral[k]) == math.isnan(e["spectral"][k]), (i, "spectral", k)
                 continue
             ok = _close(g.spectral[k], e["spectral"][k], spectral_atol + 2e-4 * col_scale[k] + (2e-4 if k in (4, 5) else 0.0), spectral_rtol)
-            if not ok and k == 12 and roll_step > 0 and abs(g.spectral[k] - e["spectral"][k]) <= roll_step * 1.001:
+            if not ok and k == 12 and roll_step > 0 and abs(g.spectral[k] - e["spectral"][k]) <= roll_step * 1.01:       # ("%g" keeps six digits: the printed steps vary in the last one)
                 roll_flips += 1
                 ok = roll_flips <= max(1, len(exp) // 100)
-            assert ok, (i, "spectral", k, g.spectral[k], e["spectral"][k])
+            assert ok, (i, "spectral", k, g.spectral[k], e["spectral"][k], "rolloff step / flips", roll_step, roll_flips)
         if e["astats"] is None:
             assert all(math.isnan(g.astats[k]) for k in range(len(AS_NAMES))), (i, "unexpected astats")
         else:
