@@ -1484,13 +1484,15 @@ static void process_adaptive_device(jt_ctx *c, const void *d_in, int64_t n_frame
     // Pass 1's kernels first; behind them, without waiting, the head of Pass 2 that no measurement can change (predicted
     // from AdaptConfig on empty measurements and checked against the real spec below), so the GPU keeps working while
     // the host assembles Pass 1's metadata, runs the detector and derives the spec's adaptive tail.
-    std::string head_spec;
+    std::string head_spec, predicted_spec;
     {
         jt_measurements m0; memset(&m0, 0, sizeof(m0));
         jt_voice_activity va0; memset(&va0, 0, sizeof(va0));
         jt_filter_config cfg0; char spec0[2048];
-        if (jt_adapt_config(base, &m0, &va0, &cfg0, nullptr) == JT_OK && jt_build_filter_spec(&cfg0, spec0, sizeof(spec0)) == JT_OK)
+        if (jt_adapt_config(base, &m0, &va0, &cfg0, nullptr) == JT_OK && jt_build_filter_spec(&cfg0, spec0, sizeof(spec0)) == JT_OK) {
             head_spec = pass2_static_head(spec0);
+            predicted_spec = spec0;             // afftdn's forward transforms (independent of its adaptive parameters) join the head
+        }
     }
     AnalysePending p1;
     const size_t mark1 = c->allocs.size();
@@ -1501,7 +1503,7 @@ static void process_adaptive_device(jt_ctx *c, const void *d_in, int64_t n_frame
     cudaEvent_t input_ready = jt_record_event(c);
     const size_t head_mark = c->allocs.size();
     GraphResume head; bool have_head = false;
-    if (!head_spec.empty()) { jt_graph_head(c, head_spec, d_in, n_frames, rate, channels, fmt, 4096, head); have_head = true; }
+    if (!head_spec.empty()) { jt_graph_head(c, head_spec, d_in, n_frames, rate, channels, fmt, 4096, head, &predicted_spec); have_head = true; }
     analyse_adaptive_device(c, d_in, n_frames, rate, channels, fmt, 4096, base, an, nullptr, 0, nullptr, &p1, have_head ? input_ready : nullptr);
     jt_check_cancel(c);
     const std::string spec = an->pass2_spec;

@@ -286,13 +286,43 @@ void jt_graph_enqueue(jt_ctx *c, const std::string &spec, const void *d_in, int6
 }
 
 // run the filters of `head_spec` and hand back the executor's state behind them (no analysis, no sink)
+static AfftdnParams parse_afftdn(const FilterNode &f)
+{
+    AfftdnParams p;
+    p.nr = f.num("nr", "noise_reduction", 12); p.nf = f.num("nf", "noise_floor", -50); p.rf = f.num("rf", "residual_floor", -38);
+    p.ad = f.num("ad", "adaptivity", 0.5); p.fo = f.num("fo", "floor_offset", 1.0); p.bm = f.num("bm", "band_multiplier", 1.25);
+    p.gs = (int)f.num("gs", "gain_smooth", 0);
+    p.tn = f.flag("tn", "track_noise", false);
+    if (f.flag("tr", "track_residual", false)) JT_THROW(JT_ERR_UNSUPPORTED, "afftdn track_residual");
+    const std::string nt = f.str("nt", "noise_type", "w");
+    if (nt == "w" || nt == "white") p.nt = 0; else if (nt == "v" || nt == "vinyl") p.nt = 1; else if (nt == "s" || nt == "shellac") p.nt = 2;
+    else if (nt == "c" || nt == "custom") p.nt = 3; else JT_THROW(JT_ERR_SPEC, "afftdn nt=%s", nt.c_str());
+    if (const std::string *bn = f.get("bn", "band_noise")) {
+        std::vector<double> v = parse_bn(*bn); p.has_bn = true;
+        for (size_t i = 0; i < 15 && i < v.size(); i++) p.bn[i] = v[i];
+    }
+    const std::string om = f.str("om", "output_mode", "o");
+    if (om != "o" && om != "output") JT_THROW(JT_ERR_UNSUPPORTED, "afftdn output mode %s", om.c_str());
+    return p;
+}
+
 void jt_graph_head(jt_ctx *c, const std::string &head_spec, const void *d_in, int64_t n_frames, int rate, int channels,
-                   int fmt, int frame_size, GraphResume &out)
+                   int fmt, int frame_size, GraphResume &out, const std::string *predicted_spec)
 {
     GraphRun g;
     out = GraphResume();
     out.head = head_spec;
     jt_graph_build(c, head_spec, d_in, n_frames, rate, channels, fmt, frame_size, true, false, JT_GRAPH_NORMAL, nullptr, g, nullptr, &out);
+    if (predicted_spec && out.cur.d && out.cur.fmt == JT_FMT_FLT && out.link_fmt == JT_FMT_FLT) {
+        const std::vector<FilterNode> nodes = jt_parse_spec(*predicted_spec);
+        if ((size_t)out.n_nodes < nodes.size() && nodes[(size_t)out.n_nodes].name == "afftdn") {
+            // without the floor candidates of track_noise: whether the real spec tracks is one of the things the host is still
+            // deciding (a spec that does runs its own forward pass, as before)
+            AfftdnParams p = parse_afftdn(nodes[(size_t)out.n_nodes]);
+            p.tn = 0;
+            jt_afftdn_forward(c, out.cur, p, out.fwd);
+        }
+    }
 }
 
 // mono view of the source: what jt_downmix returns, without the device work (dry runs)
@@ -415,21 +445,7 @@ void jt_graph_build(jt_ctx *c, const std::string &spec, const void *d_in, int64_
             E.frames = reframe(E.frames, E.cur.n, 2 * K + 1);
         } else if (f.name == "afftdn") {
             E.materialise(); E.storage(JT_FMT_FLT);
-            AfftdnParams p;
-            p.nr = f.num("nr", "noise_reduction", 12); p.nf = f.num("nf", "noise_floor", -50); p.rf = f.num("rf", "residual_floor", -38);
-            p.ad = f.num("ad", "adaptivity", 0.5); p.fo = f.num("fo", "floor_offset", 1.0); p.bm = f.num("bm", "band_multiplier", 1.25);
-            p.gs = (int)f.num("gs", "gain_smooth", 0);
-            p.tn = f.flag("tn", "track_noise", false);
-            if (f.flag("tr", "track_residual", false)) JT_THROW(JT_ERR_UNSUPPORTED, "afftdn track_residual");
-            const std::string nt = f.str("nt", "noise_type", "w");
-            if (nt == "w" || nt == "white") p.nt = 0; else if (nt == "v" || nt == "vinyl") p.nt = 1; else if (nt == "s" || nt == "shellac") p.nt = 2;
-            else if (nt == "c" || nt == "custom") p.nt = 3; else JT_THROW(JT_ERR_SPEC, "afftdn nt=%s", nt.c_str());
-            if (const std::string *bn = f.get("bn", "band_noise")) {
-                std::vector<double> v = parse_bn(*bn); p.has_bn = true;
-                for (size_t i = 0; i < 15 && i < v.size(); i++) p.bn[i] = v[i];
-            }
-            const std::string om = f.str("om", "output_mode", "o");
-            if (om != "o" && om != "output") JT_THROW(JT_ERR_UNSUPPORTED, "afftdn output mode %s", om.c_str());
+            const AfftdnParams p = parse_afftdn(f);
             if (chunked && p.tn) {
                 // the tracked noise floor is the one state of the chain with unbounded memory: its carry crosses chunks
                 const int64_t A = E.cur.rate / 80;
@@ -440,7 +456,7 @@ void jt_graph_build(jt_ctx *c, const std::string &spec, const void *d_in, int64_
                 cy.key = chunk->own_first; cy.fn = chunk->exchange; cy.user = chunk->exchange_user; cy.n_ranks = chunk->n_ranks;
                 E.cur = jt_afftdn(c, E.cur, p, &cy);
                 g.exchanges++;
-            } else if (!dry) E.cur = jt_afftdn(c, E.cur, p);
+            } else if (!dry) E.cur = jt_afftdn(c, E.cur, p, nullptr, (resume && ni == first_node) ? &resume->fwd : nullptr);
             E.frames = reframe(E.frames, E.cur.n, E.cur.rate / 80);
         } else if (f.name == "agate") {
             E.materialise(); E.storage(JT_FMT_DBL);

@@ -65,9 +65,11 @@ struct GraphRun {
 enum { JT_GRAPH_NORMAL = 0, JT_GRAPH_DRY = 1, JT_GRAPH_CHUNK = 2 };
 // The executor's state after the first n_nodes filters of a spec: lets the spec-independent head of Pass 2 (downmix, both
 // biquads, anlmdn -- filters.go:58-68) run while the host still derives the adaptive tail of the spec from Pass 1.
-struct GraphResume { int n_nodes = 0; std::string head; Sig cur; int link_fmt = 0; std::vector<FrameRef> frames; };
+struct GraphResume { int n_nodes = 0; std::string head; Sig cur; int link_fmt = 0; std::vector<FrameRef> frames; AfftdnFwd fwd; };
+// predicted_spec: the whole spec the head was cut from; when afftdn follows the head, its parameter-independent forward transforms
+// run here too (jt_afftdn_forward) and ride along in `out`
 void jt_graph_head(jt_ctx *c, const std::string &head_spec, const void *d_in, int64_t n_frames, int rate, int channels,
-                   int fmt, int frame_size, GraphResume &out);
+                   int fmt, int frame_size, GraphResume &out, const std::string *predicted_spec = nullptr);
 // Where a local window sits in its stream (input-link sample indices) and how carries cross chunk boundaries
 struct GraphChunk {
     int64_t local_first = 0, own_first = 0, owned = 0, total = 0; int rate = 0; bool last = false;

@@ -221,7 +221,12 @@ struct AfftdnParams {
 // hop0 is obtained by composing the affine carries of the chunks before this one (key = stream position), exchanged
 // through `fn` (an all-gather of fixed-size records; NULL = this chunk starts the stream / single chunk)
 struct AfftdnCarry { int64_t hop0 = 0, hop1 = 0, key = 0; jt_exchange_fn fn = nullptr; void *user = nullptr; int n_ranks = 1; };
-Sig  jt_afftdn(jt_ctx *c, const Sig &in_flt, const AfftdnParams &p, const AfftdnCarry *carry = nullptr);
+// The forward transforms of afftdn do not depend on its noise parameters (only on the rate, and on tn / fo for the floor
+// candidates): jt_afftdn_forward runs them ahead, while the host still derives those parameters, and jt_afftdn takes them over
+// when the stash was made from the very signal it is given.
+struct AfftdnFwd { void *d_spec = nullptr; double *d_cand = nullptr; const void *src = nullptr; int64_t n = 0, n_hops = 0; int rate = 0, tn = 0; double fo = 0; };
+void jt_afftdn_forward(jt_ctx *c, const Sig &in_flt, const AfftdnParams &p, AfftdnFwd &out);
+Sig  jt_afftdn(jt_ctx *c, const Sig &in_flt, const AfftdnParams &p, const AfftdnCarry *carry = nullptr, const AfftdnFwd *fwd = nullptr);
 
 // ---- k_dynamics.cu ------------------------------------------------------------------------
 struct GateParams { double threshold, ratio, attack, release, range, knee, makeup; int detection_rms; };

@@ -349,21 +349,55 @@ static void floor_affine(const double *cand, int64_t h0, int64_t h1, double &A, 
 }
 struct FloorCarryRec { int64_t key; double A, B; int64_t valid; };
 
-Sig jt_afftdn(jt_ctx *c, const Sig &in, const AfftdnParams &P, const AfftdnCarry *carry)
+// transform geometry, window and floor constant: functions of the rate (and of ad / fo, which ride along in K)
+static void afftdn_geometry(int rate, const AfftdnParams &P, AfConst &K, std::vector<double> &window, std::vector<float2> &tw)
+{
+    const double sample_rate = (float)rate;
+    K.A = (int)(sample_rate / 80); K.W = 3 * K.A;
+    K.FL = 1; while (K.FL <= K.W) K.FL <<= 1;
+    K.FL2 = K.FL / 2; K.bins = K.FL2 + 1;
+    if (K.FL < 512 || K.bins > AF_MAXOWN * AF_THREADS || K.FL > 8192) JT_THROW(JT_ERR_UNSUPPORTED, "afftdn at %d Hz (transform length %d)", rate, K.FL);
+    K.ratio = P.ad; K.floor_offset = P.fo; K.nbands = 0; K.gain_scale = K.max_gain = 0;
+    window.resize(K.W); double sum = 0;
+    { const double wscale = sqrt(8.0 / (9.0 * K.FL)); for (int i = 0; i < K.W; i++) { double d = sin(i * M_PI / K.W); d *= wscale * d; window[i] = d; sum += d * d; } }
+    K.floor_ = (double)(1LL << 48) * exp(-23.025558369790467) * (0.5 * sum);
+    tw.resize(K.FL);                                // full circle: the radix-4 passes use w, w^2, w^3
+    for (int k = 0; k < K.FL; k++) { const double a = -2.0 * M_PI * k / K.FL; tw[k] = make_float2((float)cos(a), (float)sin(a)); }
+}
+static int afftdn_fft_grid(jt_ctx *c, const AfConst &K, int64_t n_hops, size_t &smem_fft)
+{
+    smem_fft = sizeof(float2) * 3 * (size_t)K.FL;
+    const int64_t n_pairs = (n_hops + 1) / 2;
+    const int fft_per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / (smem_fft + 1024)));
+    return (int)std::min<int64_t>(n_pairs, (int64_t)c->num_sms * fft_per_sm * 4);
+}
+
+void jt_afftdn_forward(jt_ctx *c, const Sig &in, const AfftdnParams &P, AfftdnFwd &out)
+{
+    out = AfftdnFwd();
+    if (in.fmt != JT_FMT_FLT || in.n <= 0) return;
+    AfConst K; std::vector<double> window; std::vector<float2> tw;
+    afftdn_geometry(in.rate, P, K, window, tw);
+    const int64_t n_hops = (in.n + K.A - 1) / K.A;
+    const double *d_window = jt_dev_table(c, "afftdn_window", window);
+    const float2 *d_tw = jt_dev_table(c, "afftdn_tw", tw);
+    float2 *d_spec = jt_dalloc<float2>(c, (size_t)n_hops * K.bins);
+    double *d_cand = jt_dalloc<double>(c, (size_t)n_hops * 2);
+    size_t smem_fft; const int grid_fft = afftdn_fft_grid(c, K, n_hops, smem_fft);
+    jt_smem_optin((const void *)k_afftdn_fwd, smem_fft);
+    { JtLaunch L(c, "afftdn:fwd");
+      k_afftdn_fwd<<<grid_fft, AF_THREADS, smem_fft, c->stream>>>((const float *)in.d, in.n, n_hops, K, d_window, d_tw, d_spec, P.tn, d_cand); }
+    out.d_spec = d_spec; out.d_cand = d_cand; out.src = in.d; out.n = in.n; out.n_hops = n_hops; out.rate = in.rate; out.tn = P.tn; out.fo = P.fo;
+}
+
+Sig jt_afftdn(jt_ctx *c, const Sig &in, const AfftdnParams &P, const AfftdnCarry *carry, const AfftdnFwd *fwd)
 {
     if (in.fmt != JT_FMT_FLT) JT_THROW(JT_ERR_INVALID_ARG, "afftdn expects float input");
     Sig o = in; o.d = jt_dalloc<float>(c, in.n);
     if (in.n <= 0) return o;
-    AfConst K;
+    AfConst K; std::vector<double> window; std::vector<float2> tw;
+    afftdn_geometry(in.rate, P, K, window, tw);
     const double sample_rate = (float)in.rate;
-    K.A = (int)(sample_rate / 80); K.W = 3 * K.A;
-    K.FL = 1; while (K.FL <= K.W) K.FL <<= 1;
-    K.FL2 = K.FL / 2; K.bins = K.FL2 + 1;
-    if (K.FL < 512 || K.bins > AF_MAXOWN * AF_THREADS || K.FL > 8192) JT_THROW(JT_ERR_UNSUPPORTED, "afftdn at %d Hz (transform length %d)", in.rate, K.FL);
-    K.ratio = P.ad; K.floor_offset = P.fo;
-    std::vector<double> window(K.W); double sum = 0;
-    { const double wscale = sqrt(8.0 / (9.0 * K.FL)); for (int i = 0; i < K.W; i++) { double d = sin(i * M_PI / K.W); d *= wscale * d; window[i] = d; sum += d * d; } }
-    K.floor_ = (double)(1LL << 48) * exp(-23.025558369790467) * (0.5 * sum);
     std::vector<int> bin2band(K.bins);
     for (int i = 0; i < K.bins; i++) bin2band[i] = (int)lrint(P.bm * freq2bark((0.5 * i * sample_rate) / K.FL2));
     K.nbands = bin2band[K.bins - 1] + 1;
@@ -413,8 +447,6 @@ Sig jt_afftdn(jt_ctx *c, const Sig &in, const AfftdnParams &P, const AfftdnCarry
           rel_var[m] = exp((d5 * d3 + band_noise * d4) * AF_C);
       } }
     K.max_gain = exp(P.nr * (0.5 * AF_C)); K.gain_scale = 1.0 / (K.max_gain * K.max_gain);
-    std::vector<float2> tw(K.FL);                   // full circle: the radix-4 passes use w, w^2, w^3
-    for (int k = 0; k < K.FL; k++) { const double a = -2.0 * M_PI * k / K.FL; tw[k] = make_float2((float)cos(a), (float)sin(a)); }
 
     const int64_t n_hops = (in.n + K.A - 1) / K.A;
     const double *d_window = jt_dev_table(c, "afftdn_window", window);
@@ -424,23 +456,22 @@ Sig jt_afftdn(jt_ctx *c, const Sig &in, const AfftdnParams &P, const AfftdnCarry
     const int *d_b2b = jt_dev_table(c, "afftdn_bin2band", bin2band);
     const double *d_alpha = jt_dev_table(c, "afftdn_alpha", alpha), *d_beta = jt_dev_table(c, "afftdn_beta", beta);
     const double *d_spread = jt_dev_table(c, "afftdn_spread", spread);
-    float2 *d_spec = jt_dalloc<float2>(c, (size_t)n_hops * K.bins);
+    // forward transforms already made from this very signal (jt_afftdn_forward)?
+    const bool have_fwd = fwd && fwd->d_spec && fwd->src == in.d && fwd->n == in.n && fwd->n_hops == n_hops && fwd->rate == in.rate && fwd->tn == P.tn && fwd->fo == P.fo;
+    float2 *d_spec = have_fwd ? (float2 *)fwd->d_spec : jt_dalloc<float2>(c, (size_t)n_hops * K.bins);
     double *d_gain = jt_dalloc<double>(c, (size_t)n_hops * K.bins), *d_clean = jt_dalloc<double>(c, (size_t)n_hops * K.bins);
     double *d_raw = jt_dalloc<double>(c, (size_t)n_hops * nb), *d_amt = jt_dalloc<double>(c, (size_t)n_hops * nb);
     float *d_frames = jt_dalloc<float>(c, (size_t)n_hops * K.W);
-    double *d_cand = jt_dalloc<double>(c, (size_t)n_hops * 2), *d_pre = jt_dalloc<double>(c, n_hops), *d_post = jt_dalloc<double>(c, n_hops);
-    const size_t smem_fft = sizeof(float2) * 3 * (size_t)K.FL;
+    double *d_cand = have_fwd ? fwd->d_cand : jt_dalloc<double>(c, (size_t)n_hops * 2), *d_pre = jt_dalloc<double>(c, n_hops), *d_post = jt_dalloc<double>(c, n_hops);
+    size_t smem_fft; const int grid_fft = afftdn_fft_grid(c, K, n_hops, smem_fft);
     jt_smem_optin((const void *)k_afftdn_fwd, (size_t)(smem_fft));
     jt_smem_optin((const void *)k_afftdn_synth, (size_t)(smem_fft));
     const int warm = 128;                             // 0.39^128, 0.78^128: both recursions have forgotten their start
     const int chunk_gain = 768, chunk_band = 256;
     const size_t smem_band = sizeof(double) * ((size_t)(chunk_band + warm) * nb + (size_t)nb * nb);
     jt_smem_optin((const void *)k_afftdn_bandrec, (size_t)(smem_band));
-    const int64_t n_pairs = (n_hops + 1) / 2;
-    const int fft_per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / (smem_fft + 1024)));
-    const int grid_fft = (int)std::min<int64_t>(n_pairs, (int64_t)c->num_sms * fft_per_sm * 4);
     {
-        { JtLaunch L(c, "afftdn:fwd");
+        if (!have_fwd) { JtLaunch L(c, "afftdn:fwd");
           k_afftdn_fwd<<<grid_fft, AF_THREADS, smem_fft, c->stream>>>((const float *)in.d, in.n, n_hops, K, d_window, d_tw, d_spec, P.tn, d_cand); }
         double nf_start = P.nf;
         if (carry && P.tn) {
