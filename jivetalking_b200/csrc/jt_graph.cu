@@ -347,6 +347,7 @@ void jt_graph_build(jt_ctx *c, const std::string &spec, const void *d_in, int64_
 
     Exec E; E.c = c; E.dry = dry;
     bool have_mono = false, r128_prelaunched = false;
+    int64_t astats_prelaunched_upto = -1; const void *astats_prelaunched_sig = nullptr;
     const void *raw = d_in;
     if (channels == 1) { E.cur = dry ? dry_mono(n_frames, fmt, rate) : jt_downmix(c, raw, n_frames, 1, fmt, rate); have_mono = true; }
     E.link_fmt = fmt;
@@ -574,6 +575,11 @@ void jt_graph_build(jt_ctx *c, const std::string &spec, const void *d_in, int64_
                     const FilterNode &e = nodes[j];
                     jt_ebur128_launch(c, E.cur, e.flag("dualmono", "", false), e.str("peak", "", "none").find("true") != std::string::npos, g.r128p);
                     r128_prelaunched = true;
+                    // the same for astats itself when nothing but analysis nodes follow to the end of the spec: the sink's last
+                    // frame then carries the statistics of the whole signal (checked against the final cadence below)
+                    size_t e2 = j + 1;
+                    while (e2 < nodes.size() && (nodes[e2].name == "astats" || nodes[e2].name == "aspectralstats" || nodes[e2].name == "ebur128")) e2++;
+                    if (e2 == nodes.size() && E.cur.n > 0) { jt_astats_launch(c, E.cur, E.cur.n, g.astp); astats_prelaunched_upto = E.cur.n; astats_prelaunched_sig = E.cur.d; }
                 }
             }
             E.has_astats = true; E.astats_sig = E.cur;
@@ -622,7 +628,9 @@ void jt_graph_build(jt_ctx *c, const std::string &spec, const void *d_in, int64_
         for (size_t i = 0; i < nf; i++) if (g.frames[i].hop >= 0) wanted.push_back(g.frames[i].hop);
         jt_aspectralstats_launch(c, g.spec_sig, g.spec_win, &wanted, g.specp);
     }
-    if (g.has_astats && g.last_astats_frame >= 0) jt_astats_launch(c, g.astats_sig, g.frames[g.last_astats_frame].astats_pos, g.astp);
+    if (g.has_astats && g.last_astats_frame >= 0 &&
+        !(astats_prelaunched_upto == g.frames[g.last_astats_frame].astats_pos && astats_prelaunched_sig == g.astats_sig.d))
+        jt_astats_launch(c, g.astats_sig, g.frames[g.last_astats_frame].astats_pos, g.astp);
 }
 
 const R128Result &jt_graph_r128_early(jt_ctx *c, GraphRun &g)

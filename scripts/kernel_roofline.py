@@ -39,8 +39,22 @@ ALG = {
     "k_spectral": ("aspectralstats", 4 * N, "f32 in (13 statistics per shown hop out)"),
     "k_spectral_flux": ("aspectralstats", 0, "magnitude rows of the shown hops"),
     "k_r128_ticks<float, 0>": ("r128_kweight_ticks", 4 * N, "f32 in (per-tick energies out)"),
+    "k_kw_blocks<float, 0, 0, 128>": ("r128_kweight_ticks", 4 * N, "f32 in (forced end state per 96-sample block out)"),
+    "k_kw_blocks<float, 0, 1, 128>": ("r128_kweight_ticks", 4 * N, "f32 in (block energies / peaks out)"),
+    "k_kw_blocks<double, 0, 0, 64>": ("r128_kweight_ticks", 8 * M, "f64 in at 44.1 kHz"),
+    "k_kw_blocks<double, 0, 1, 64>": ("r128_kweight_ticks", 8 * M, "f64 in at 44.1 kHz"),
+    "k_kw_blocks<short, 0, 0, 128>": ("r128_kweight_ticks", 0, "regions only"),
+    "k_kw_blocks<short, 0, 1, 128>": ("r128_kweight_ticks", 0, "regions only"),
+    "k_kw_scan": ("r128_kweight_ticks", 0, "4 doubles per block"), "k_kw_fold": ("r128_kweight_ticks", 0, "2 doubles per block"),
+    "k_envelope_tiles<1>": ("envelope_follower", 16 * N, "f64 in + f64 envelope out"),
+    "k_envelope_tiles<0>": ("envelope_follower", 16 * N, "f64 in + f64 envelope out"),
+    "k_biquad_tiles<true>": ("biquad", 8 * N, "f32 in + f32 out"), "k_biquad_tiles<false>": ("biquad", 8 * N, "f32 in + f32 out"),
+    "k_copy_small": ("copy_small", 0, "per-tick values / statistics rows to pinned host memory"),
+    "k_fd_scan<false>": ("flac_decode:scan", 0.86 * M, "FLAC stream in (~0.86 B / sample)"), "k_fd_scan<true>": ("flac_decode:scan", 0.86 * M, "FLAC stream in"),
+    "k_fd_link": ("flac_decode:link", 0.86 * M, "FLAC stream in (CRC-16)"), "k_fd_frames": ("flac_decode:frames", 0.86 * M + 4 * M, "stream in + planar int32 out"),
+    "k_fd_output<short>": ("flac_decode:output", 6 * M, "planar int32 in + s16 out"),
     "k_r128_ticks<float, 1>": ("r128_kweight_ticks:192k", 4 * 4 * M, "f32 in at 192 kHz"),
-    "k_r128_ticks<double, 1>": ("r128_kweight_ticks:192k", 8 * 4 * M, "f64 in at 192 kHz"),
+    "k_r128_ticks<double, 1>": ("r128_kweight_ticks:192k", 8 * M, "f64 in at 44.1 kHz (loudnorm's output meter)"),
     "k_swr_small<float, 4, 1>": ("truepeak_oversample:small_f64", 4 * N, "f32 in at 48 kHz (per-tick maxima out)"),
     "k_swr_phase_f64<float, 32, 1, 640>": ("truepeak_oversample:phase_f64", 4 * M, "f32 in at 44.1 kHz (per-tick maxima out)"),
     "k_swr_phase_f64<float, 36, 0, 160>": ("swr_resample:phase_f64", 4 * N + 8 * M, "f32 in at 48 kHz + f64 out at 44.1 kHz"),

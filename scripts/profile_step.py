@@ -28,7 +28,9 @@ def main():
         if a.flac:
             cap_b = int(gpudsp.lib().jt_flac_max_bytes(int(res.n_out), 4096))
             d_flac = torch.empty(cap_b, dtype=torch.uint8, device="cuda")
-            ctx.flac_encode_ptr(d_out.data_ptr(), int(res.n_out), 44100, 4096, d_flac.data_ptr(), cap_b, True)
+            nb = ctx.flac_encode_ptr(d_out.data_ptr(), int(res.n_out), 44100, 4096, d_flac.data_ptr(), cap_b, True)
+            d_back = torch.empty(int(res.n_out) + 4096, dtype=torch.int16, device="cuda")
+            ctx.decode_ptr("flac", d_flac.data_ptr(), nb, d_back.data_ptr(), int(res.n_out) + 4096, True)
         torch.cuda.synchronize()
     print("profile_step: n_out", int(res.n_out), "I", res.final.input_i)
 
