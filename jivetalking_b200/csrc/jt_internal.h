@@ -119,7 +119,12 @@ Sig  jt_pad_zero(jt_ctx *c, const Sig &in, int64_t n_total);              // ase
 // ---- k_swr.cu -----------------------------------------------------------------------------
 struct SwrPlan {
     int in_rate = 0, out_rate = 0, phase_count = 0, filter_length = 0, div = 0;
-    std::vector<double> bank;   // phase_count x filter_length
+    // index advance per output in 1/phase_count input samples = inc_num / inc_den (swr's dst_incr / src_incr, reduced).  Exact
+    // ratios (reduced phase count <= 1024): inc_den == 1, inc_num == div.  Otherwise 1024 phases, a fractional advance and
+    // swr's linear interpolation between neighbouring phases (linear_interp defaults to on): `linear`, bank has phase_count + 1 rows
+    int64_t inc_num = 0, inc_den = 1;
+    bool linear = false;
+    std::vector<double> bank;   // phase_count (+ 1 when linear) x filter_length
     bool identity = false;
     int64_t out_count(int64_t n_in) const;        // outputs produced after n_in inputs, no flush
     int64_t out_count_flush(int64_t n_in) const;  // total with end reflection

@@ -42,7 +42,8 @@ __device__ __forceinline__ bool nlm_weight(float c, float xs, const NlmK &k, flo
 // over four samples loads 6 values per edge stream instead of 12, and a stride of three floats between lanes is
 // conflict-free.  With S = 96 one warp covers all 192 lags of a hop.
 __global__ void __launch_bounds__(128)
-k_anlmdn(const float *__restrict__ x, float *__restrict__ y, int64_t n, int K, int S, NlmK P, int64_t n_hops)
+k_anlmdn(const float *__restrict__ x, float *__restrict__ y, int64_t n, int K, int S, NlmK P, int64_t n_hops,
+         const int *__restrict__ hop_list, const int *__restrict__ hop_count)
 {
     extern __shared__ float win[];                       // N floats (+ slack)
     __shared__ float part[2][NLM_CHUNK][4][2];
@@ -53,7 +54,10 @@ k_anlmdn(const float *__restrict__ x, float *__restrict__ y, int64_t n, int K, i
     bool live[NLM_V];                                    // lags past S-1 read the zeroed slack behind the window and never contribute
 #pragma unroll
     for (int m = 0; m < NLM_V; m++) live[m] = v0 + m < S;
-    for (int64_t h = blockIdx.x; h < n_hops; h += gridDim.x) {
+    // with a hop list (k_nlm_screen) only the listed hops are walked; every other hop is already the delayed input
+    const int64_t n_work = hop_list ? (int64_t)*hop_count : n_hops;
+    for (int64_t hi = blockIdx.x; hi < n_work; hi += gridDim.x) {
+        const int64_t h = hop_list ? (int64_t)hop_list[hi] : hi;
         const int64_t pos = h * (int64_t)H;
         const int nb = (int)min((int64_t)H, n - pos);
         __syncthreads();
@@ -163,6 +167,104 @@ k_anlmdn(const float *__restrict__ x, float *__restrict__ y, int64_t n, int K, i
     }
 }
 
+
+// ---- screening pass ------------------------------------------------------------------------------------------------
+// A lag only enters a sample's average when its patch distance d = sum_{k=-K..K} (f[i+k] - f[j+k])^2 falls below
+// smooth / sw (with the reference's s = 0.00001 that is a mean squared difference at -65 dBFS); when no lag does, the
+// output is the (delayed) input, bit for bit: P / Q = (0 + f[i]) / (0 + 1).  On programme material almost every hop is of
+// that kind, and the exact kernel above spends its time proving it with 192 running distances per sample.  The screen proves
+// it for a whole group of hops with an eighth of the instructions, from a LOWER BOUND of every distance the exact kernel
+// can see there:
+//   * g_v[n] = (f[n] - f[n+v])^2, v = 1..S, covers both signs of the lag (the pair i, i-v is the pair i-v, (i-v)+v);
+//   * every patch (H = 2K+1 consecutive n) contains R = floor((H - BS + 1) / BS) whole blocks of BS samples of a grid anchored
+//     at the group's first patch start, so d >= the sum of R consecutive block sums G_v[b]; and it lies inside R + 3 blocks,
+//     which bounds d -- and with it the rounding the exact kernel's float accumulator can have picked up since the hop's
+//     seed (3 H ulp of its largest value; 5 H is allowed for) -- from above;
+//   * a group is passed through when, for every lag, min_b LB_v[b] >= 1.01 smooth / sw + crel * max_b UB_v[b], crel covering
+//     that rounding and the rounding of the block prefix sums the two bounds are read from.
+// Anything else (digital silence, room tone under the cut-off, a decay of more than ~33 dB inside a group) goes to the exact
+// kernel through the hop list.  Outputs are identical to running the exact kernel on every hop.
+struct NlmScreen { int K, S, H, BS, R, HC, SP, wlen; float thr, crel; };
+
+template <int LPT>
+__global__ void __launch_bounds__(256)
+k_nlm_screen(const float *__restrict__ x, float *__restrict__ y, int64_t n, NlmScreen Q, int64_t n_hops,
+             int *__restrict__ hop_list, int *__restrict__ hop_count)
+{
+    extern __shared__ __align__(16) float nlm_sm[];
+    float *xs = nlm_sm;                 // the group's samples from its first patch start on, zero outside the stream
+    float *Gs = nlm_sm + Q.wlen;        // [block][lag] block sums, then their prefix sums in place
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int H = Q.H, BS = Q.BS, SP = Q.SP, R = Q.R;
+    const int64_t n_groups = (n_hops + Q.HC - 1) / Q.HC;
+    for (int64_t hg = blockIdx.x; hg < n_groups; hg += gridDim.x) {
+        const int64_t h0 = hg * Q.HC;
+        const int hn = (int)min((int64_t)Q.HC, n_hops - h0);
+        const int64_t pos0 = h0 * (int64_t)H, ps_min = pos0 - 2 * (Q.K + Q.S);
+        const int span = (hn - 1) * H + Q.S + H - 1;              // patch starts of the group: ps_min .. ps_min + span
+        const int nrs = (span + BS - 1) / BS + 1, nblk = nrs + R + 2;
+        const int wl = nblk * BS + SP + 8;
+        __syncthreads();
+        for (int j = threadIdx.x; j < wl; j += blockDim.x) {
+            const int64_t s = ps_min + j;
+            xs[j] = (s >= 0 && s < n) ? x[s] : 0.f;
+        }
+        __syncthreads();
+        // block sums: a warp per block, lane l owns the lags 1 + LPT l .. LPT (l + 1)
+        for (int b = warp; b < nblk; b += nwarp) {
+            const float *pa = xs + b * BS, *pw = pa + 1 + LPT * lane;
+            float acc[LPT];
+#pragma unroll
+            for (int m = 0; m < LPT; m++) acc[m] = 0.f;
+            for (int i = 0; i < BS; i += 8) {
+                const float4 a0 = *(const float4 *)(pa + i), a1 = *(const float4 *)(pa + i + 4);
+                const float a[8] = { a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w };
+                float w[8 + LPT - 1];
+#pragma unroll
+                for (int j = 0; j < 8 + LPT - 1; j++) w[j] = pw[i + j];
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+#pragma unroll
+                    for (int m = 0; m < LPT; m++) { const float t = a[j] - w[j + m]; acc[m] = fmaf(t, t, acc[m]); }
+            }
+#pragma unroll
+            for (int m = 0; m < LPT; m++) Gs[b * SP + LPT * lane + m] = acc[m];
+        }
+        __syncthreads();
+        // per lag: prefix sums over the blocks, then the two bounds of every run start
+        int flag = 0;
+        for (int v = threadIdx.x; v < Q.S; v += blockDim.x) {
+            float *col = Gs + v;
+            float p = 0.f;
+            for (int b = 0; b < nblk; b++) { const float g = col[b * SP]; col[b * SP] = p; p += g; }
+            col[nblk * SP] = p;
+            float lo = 3.0e38f, hi = 0.f;
+            for (int b = 0; b < nrs; b++) {
+                const float p0 = col[b * SP];
+                lo = fminf(lo, col[(b + R) * SP] - p0);
+                hi = fmaxf(hi, col[(b + R + 3) * SP] - p0);
+            }
+            flag |= !(lo >= 1.01f * Q.thr + Q.crel * hi);
+        }
+        flag = __syncthreads_or(flag);
+        // the pass-through value of every sample of the group (the exact kernel overwrites the listed hops afterwards)
+        const int cnt = (int)min((int64_t)hn * H, n - pos0);
+        for (int t = threadIdx.x; t < cnt; t += blockDim.x) y[pos0 + t] = __fadd_rn(0.f, xs[t + Q.K + Q.S]);
+        if (flag && threadIdx.x == 0) {
+            const int base = atomicAdd(hop_count, hn);
+            for (int i = 0; i < hn; i++) hop_list[base + i] = (int)(h0 + i);
+        }
+    }
+}
+
+template <int LPT>
+static void nlm_screen_launch(jt_ctx *c, const float *x, float *y, int64_t n, const NlmScreen &Q, int64_t n_hops, size_t smem, int *list, int *count)
+{
+    jt_smem_optin((const void *)k_nlm_screen<LPT>, smem);
+    const int64_t n_groups = (n_hops + Q.HC - 1) / Q.HC;
+    k_nlm_screen<LPT><<<jt_grid_for(n_groups, 1, c->num_sms, 64), 256, smem, c->stream>>>(x, y, n, Q, n_hops, list, count);
+}
+
 static int64_t rescale_near(int64_t a, int64_t b, int64_t c) { return (a * b + c / 2) / c; }
 
 Sig jt_anlmdn(jt_ctx *c, const Sig &in, double strength, double patch_s, double research_s, double smooth_m)
@@ -184,9 +286,47 @@ Sig jt_anlmdn(jt_ctx *c, const Sig &in, double strength, double patch_s, double 
     const size_t smem = sizeof(float) * (N + 128);
     jt_smem_optin((const void *)k_anlmdn, (size_t)(std::max<size_t>(smem, 1024)));
     const int grid = jt_grid_for(n_hops, 1, c->num_sms, 64);
-    JtLaunch L(c, "anlmdn");
     NlmK P; P.sw = sw; P.smooth = smooth; P.lut_scale = lut_scale; P.inv_lut_scale = 1.f / lut_scale;
     P.maybe = (smooth / sw) * 1.0001f;
-    k_anlmdn<<<grid, threads, smem, c->stream>>>((const float *)in.d, (float *)o.d, in.n, K, S, P, n_hops);
+    // screening pass (see k_nlm_screen): block size ~ H / 18 so that a patch holds R ~ 17 whole blocks, hops grouped so that a
+    // group's block sums fit ~70 KB of shared memory (three groups per SM)
+    int *d_list = nullptr, *d_count = nullptr;
+    const bool no_screen = getenv("JT_ANLMDN_NO_SCREEN") != nullptr;     // tests: every hop through the exact kernel
+    NlmScreen Q{};
+    Q.K = K; Q.S = S; Q.H = H; Q.BS = 32 * std::max(1, (H + 288) / 577); Q.R = (H - Q.BS + 1) / Q.BS;
+    const int lpt_need = (S + 31) / 32;
+    const int lpt = lpt_need <= 4 ? lpt_need : lpt_need <= 6 ? 6 : lpt_need <= 8 ? 8 : 12;
+    Q.SP = 32 * lpt;
+    size_t smem_screen = 0;
+    if (!no_screen && Q.R >= 4 && n_hops < (int64_t)1 << 31) {
+        for (Q.HC = 8; Q.HC >= 1; Q.HC--) {
+            const int span = (Q.HC - 1) * H + S + H - 1;
+            const int nrs = (span + Q.BS - 1) / Q.BS + 1, nblk = nrs + Q.R + 2;
+            Q.wlen = ((nblk * Q.BS + Q.SP + 8) + 3) & ~3;
+            smem_screen = sizeof(float) * ((size_t)Q.wlen + (size_t)(nblk + 1) * Q.SP);
+            const double u = 1.0 / 16777216.0;
+            Q.crel = (float)(1.5 * (5.0 * H * u + 2.0 * nblk * u * ((double)nblk / (Q.R + 3) + 1.0)));
+            if (smem_screen <= 72 * 1024 || Q.HC == 1) break;
+        }
+        if (smem_screen > 200 * 1024) smem_screen = 0;
+    }
+    if (smem_screen) {
+        Q.thr = smooth / sw;
+        d_list = jt_dalloc<int>(c, (size_t)n_hops + 1);
+        d_count = d_list + n_hops;
+        JT_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int), c->stream));
+        JtLaunch L(c, "anlmdn:screen");
+        switch (lpt) {
+        case 1: nlm_screen_launch<1>(c, (const float *)in.d, (float *)o.d, in.n, Q, n_hops, smem_screen, d_list, d_count); break;
+        case 2: nlm_screen_launch<2>(c, (const float *)in.d, (float *)o.d, in.n, Q, n_hops, smem_screen, d_list, d_count); break;
+        case 3: nlm_screen_launch<3>(c, (const float *)in.d, (float *)o.d, in.n, Q, n_hops, smem_screen, d_list, d_count); break;
+        case 4: nlm_screen_launch<4>(c, (const float *)in.d, (float *)o.d, in.n, Q, n_hops, smem_screen, d_list, d_count); break;
+        case 6: nlm_screen_launch<6>(c, (const float *)in.d, (float *)o.d, in.n, Q, n_hops, smem_screen, d_list, d_count); break;
+        case 8: nlm_screen_launch<8>(c, (const float *)in.d, (float *)o.d, in.n, Q, n_hops, smem_screen, d_list, d_count); break;
+        default: nlm_screen_launch<12>(c, (const float *)in.d, (float *)o.d, in.n, Q, n_hops, smem_screen, d_list, d_count); break;
+        }
+    }
+    JtLaunch L(c, "anlmdn");
+    k_anlmdn<<<grid, threads, smem, c->stream>>>((const float *)in.d, (float *)o.d, in.n, K, S, P, n_hops, d_list, d_count);
     return o;
 }

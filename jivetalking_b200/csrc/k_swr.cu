@@ -52,12 +52,17 @@ static SwrPlan swr_plan_design(int in_rate, int out_rate)
     double factor = std::fmin((double)out_rate * cutoff / in_rate, 1.0);
     int64_t g = gcd_i64(out_rate, in_rate);
     int64_t pc = out_rate / g;
-    if (pc > (1 << phase_shift))
-        JT_THROW(JT_ERR_UNSUPPORTED, "resample %d -> %d needs swr's linear-interpolated path (phase count %lld > 1024)",
-                 in_rate, out_rate, (long long)pc);
+    // exact_rational: the reduced phase count when it fits 1 << phase_shift; otherwise all 1024 phases, a fractional index
+    // advance and (linear_interp is on by default) resample_linear -- e.g. 22.05 kHz or 11.025 kHz sources into ebur128's
+    // 192 kHz true-peak oversampler.  Pinned on the real library: tests/test_oracle_swr.py
+    if (pc > (1 << phase_shift)) { pc = 1 << phase_shift; p.linear = true; }
     p.phase_count = (int)pc;
     p.filter_length = std::max((int)std::ceil(filter_size / factor), 1);
-    p.div = (int)(((int64_t)in_rate * pc) / out_rate);
+    {
+        const int64_t num = (int64_t)in_rate * pc, den = out_rate, gg = gcd_i64(num, den);
+        p.inc_num = num / gg; p.inc_den = den / gg;
+    }
+    p.div = (int)(p.inc_num / p.inc_den);
     const int L = p.filter_length, center = (L - 1) / 2;
     const int ph_nb = pc % 2 ? (int)pc : (int)pc / 2 + 1;
     p.bank.assign((size_t)(pc + 1) * L, 0.0);
@@ -80,6 +85,15 @@ static SwrPlan swr_plan_design(int in_rate, int out_rate)
             for (int i = 0; i < L; i++) p.bank[(size_t)(pc - ph) * L + L - 1 - i] = p.bank[(size_t)ph * L + i];
     }
     p.bank.resize((size_t)pc * L);
+    if (p.linear) {
+        // row phase_count = phase 0 one sample later (swri_resample_init: row 0 shifted by one tap inside its allocation of
+        // FFALIGN(L, 8) slots, the first tap taken from row 0's last allocated slot)
+        const int alloc = (L + 7) & ~7;
+        p.bank.resize((size_t)(pc + 1) * L, 0.0);
+        double *row = p.bank.data() + (size_t)pc * L;
+        row[0] = alloc > L ? 0.0 : p.bank[L - 1];
+        for (int i = 1; i < L; i++) row[i] = p.bank[i - 1];
+    }
     return p;
 }
 
@@ -88,12 +102,12 @@ static int64_t avail_outputs(const SwrPlan &p, int64_t n_avail)
     const int64_t pc = p.phase_count, L = p.filter_length, c = (L - 1) / 2;
     int64_t span = (1 + n_avail - L) * pc + pc * c;
     if (span <= 0) return 0;
-    return (span + p.div - 1) / p.div;
+    return (span * p.inc_den + p.inc_num - 1) / p.inc_num;          // outputs m with floor(m inc_num / inc_den) < span
 }
 int64_t SwrPlan::first_tap(int64_t m) const
 {
     const int64_t pc = phase_count, c = (filter_length - 1) / 2;
-    return jt_floordiv(-pc * c + m * (int64_t)div, pc);
+    return jt_floordiv(-pc * c + jt_floordiv(m * inc_num, inc_den), pc);
 }
 int64_t SwrPlan::out_count(int64_t n_in) const
 {
@@ -245,6 +259,51 @@ k_swr_generic(const TIN *__restrict__ x, int64_t n, int64_t n_periods, int64_t n
                     }
                     cur_max = fmax(cur_max, fabs((double)v));
                 }
+            }
+        }
+        if (MODE == SWR_MODE_TICKMAX && cur_k >= 0 && cur_k < n_ticks) jt_atomic_max_nonneg(&tick_max[cur_k], cur_max);
+    }
+}
+
+
+// Inexact ratios (SwrPlan::linear; resample_template.c resample_linear): output m reads from phase index
+// -pc c + floor(m num / den), interpolating between that phase's row and the next by frac / den.  Thread per output over a
+// staged tile; coefficient rows come through the L1 (1025 rows: the bank does not fit registers or a CTA's shared memory
+// at f64).  A rare path (22.05 / 11.025 kHz sources, odd rates): written for clarity, not for the last cycle.
+template <class TIN, class TW, int MODE>
+__global__ void __launch_bounds__(256)
+k_swr_linear(const TIN *__restrict__ x, int64_t n, int64_t n_out, int pc, int L, int64_t num, int64_t den,
+             const TW *__restrict__ bank, TW *__restrict__ out, double *__restrict__ tick_max, int tick, int64_t n_ticks,
+             int span, int tb)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TW *sx = (TW *)smem_raw;
+    const int c = (L - 1) / 2;
+    const int64_t tiles = (n_out + tb - 1) / tb;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int64_t m0 = tile * tb, m1 = min(m0 + tb, n_out);
+        const int64_t base = jt_floordiv(-(int64_t)pc * c + (m0 * num) / den, (int64_t)pc);
+        __syncthreads();
+        for (int i = threadIdx.x; i < span; i += blockDim.x) sx[i] = swr_load<TIN, TW>(x, base + i, n);
+        __syncthreads();
+        double cur_max = 0.0; int64_t cur_k = -1;
+        for (int64_t m = m0 + threadIdx.x; m < m1; m += blockDim.x) {
+            const int64_t t = m * num, q = t / den, frac = t - q * den;
+            const int64_t pos = -(int64_t)pc * c + q, sidx = jt_floordiv(pos, (int64_t)pc);
+            const int ph = (int)(pos - sidx * pc);
+            const TW *f = bank + (size_t)ph * L, *w = sx + (sidx - base);
+            TW val = 0, v2 = 0;
+            for (int i = 0; i < L; i++) { const TW s = w[i]; val = fma(s, __ldg(f + i), val); v2 = fma(s, __ldg(f + L + i), v2); }
+            val += (v2 - val) * (TW)frac / (TW)den;
+            if (MODE == SWR_MODE_STORE) out[m] = val;
+            else {
+                int64_t need = sidx + L; if (need < L + 1) need = L + 1;
+                const int64_t k = (need + tick - 1) / tick - 1;
+                if (k != cur_k) {
+                    if (cur_k >= 0 && cur_k < n_ticks) jt_atomic_max_nonneg(&tick_max[cur_k], cur_max);
+                    cur_k = k; cur_max = 0.0;
+                }
+                cur_max = fmax(cur_max, fabs((double)val));
             }
         }
         if (MODE == SWR_MODE_TICKMAX && cur_k >= 0 && cur_k < n_ticks) jt_atomic_max_nonneg(&tick_max[cur_k], cur_max);
@@ -496,6 +555,7 @@ k_swr_phase_f64(const TIN *__restrict__ x, int64_t n, int64_t n_periods, int64_t
 
 static bool phase_path_ok(const SwrPlan &p)
 {
+    if (p.linear) return false;
     const int L = p.filter_length;
     if (!(L == 32 || L == 36 || L == 72)) return false;
     return p.phase_count >= 32 && p.phase_count <= 640 && p.div >= 2;
@@ -524,7 +584,7 @@ static void launch_phase_f64(jt_ctx *c, const Sig &in, const SwrPlan &p, int64_t
 template <class TW>
 static const TW *device_bank(jt_ctx *c, const SwrPlan &p)
 {
-    const size_t nb = (size_t)p.phase_count * p.filter_length;
+    const size_t nb = p.bank.size();                    // phase_count (+ 1 when linear) rows
     std::vector<TW> hb(nb);
     for (size_t i = 0; i < nb; i++) hb[i] = (TW)p.bank[i];
     return jt_dev_table(c, sizeof(TW) == 4 ? "swr_bank_f32" : "swr_bank_f64", hb);
@@ -532,6 +592,7 @@ static const TW *device_bank(jt_ctx *c, const SwrPlan &p)
 
 static bool slot_path_ok(const SwrPlan &p)
 {
+    if (p.linear) return false;
     const int L = p.filter_length;
     const bool up = p.phase_count > p.div;
     const int nslots = up ? p.div : p.phase_count;
@@ -586,6 +647,7 @@ static void launch_qlane_f64(jt_ctx *c, const Sig &in, const SwrPlan &p, int64_t
 }
 static bool qlane_path_ok(const SwrPlan &p)
 {
+    if (p.linear) return false;
     const bool up = p.phase_count > p.div;
     if (p.filter_length % 2) return false;
     if (up && (p.phase_count + p.div - 1) / p.div > 5) return false;
@@ -620,7 +682,23 @@ static void launch_generic(jt_ctx *c, const Sig &in, const SwrPlan &p, int64_t n
                                           d_bank, out, tick_max, tick, n_ticks, span);
 }
 
-static bool small_path(const SwrPlan &p) { return p.div == 1 && p.filter_length == 32 && (p.phase_count == 2 || p.phase_count == 4 || p.phase_count == 6 || p.phase_count == 8); }
+template <class TIN, class TW, int MODE>
+static void launch_linear(jt_ctx *c, const Sig &in, const SwrPlan &p, int64_t n_out, TW *out,
+                          double *tick_max, int tick, int64_t n_ticks)
+{
+    const TW *d_bank = device_bank<TW>(c, p);
+    const int tb = 2048;
+    const int span = (int)(((int64_t)tb * p.inc_num / p.inc_den) / p.phase_count) + p.filter_length + 4;
+    const size_t smem = (size_t)span * sizeof(TW) + 16;
+    if (smem > 200 * 1024) JT_THROW(JT_ERR_UNSUPPORTED, "resample %d -> %d: tile of %d inputs", p.in_rate, p.out_rate, span);
+    auto kfn = k_swr_linear<TIN, TW, MODE>;
+    jt_smem_optin((const void *)kfn, smem);
+    const int grid = jt_grid_for((n_out + tb - 1) / tb, 1, c->num_sms, 8);
+    kfn<<<grid, 256, smem, c->stream>>>((const TIN *)in.d, in.n, n_out, p.phase_count, p.filter_length, p.inc_num, p.inc_den,
+                                          d_bank, out, tick_max, tick, n_ticks, span, tb);
+}
+
+static bool small_path(const SwrPlan &p) { return !p.linear && p.div == 1 && p.filter_length == 32 && (p.phase_count == 2 || p.phase_count == 4 || p.phase_count == 6 || p.phase_count == 8); }
 
 Sig jt_swr_resample(jt_ctx *c, const Sig &in0, const SwrPlan &p, int work_fmt, bool flush, int fuse_out_fmt)
 {
@@ -635,7 +713,19 @@ Sig jt_swr_resample(jt_ctx *c, const Sig &in0, const SwrPlan &p, int work_fmt, b
     if (n_out <= 0) return o;
     const char *kind = work_fmt == JT_FMT_DBL ? (small_path(p) ? "swr_resample:small_f64" : phase_path_ok(p) ? "swr_resample:phase_f64" : qlane_path_ok(p) ? "swr_resample:qlane_f64" : "swr_resample:generic")
                                               : (slot_path_ok(p) ? (p.phase_count > p.div ? "swr_resample:slot_f32_up" : "swr_resample:slot_f32_down") : "swr_resample:generic");
-    JtLaunch Lc(c, kind);
+    JtLaunch Lc(c, p.linear ? "swr_resample:linear" : kind);
+    if (p.linear) {
+        if (work_fmt == JT_FMT_DBL) {
+            if (in.fmt == JT_FMT_S16) launch_linear<int16_t, double, SWR_MODE_STORE>(c, in, p, n_out, (double *)o.d, nullptr, 1, 0);
+            else if (in.fmt == JT_FMT_FLT) launch_linear<float, double, SWR_MODE_STORE>(c, in, p, n_out, (double *)o.d, nullptr, 1, 0);
+            else launch_linear<double, double, SWR_MODE_STORE>(c, in, p, n_out, (double *)o.d, nullptr, 1, 0);
+        } else if (work_fmt == JT_FMT_FLT) {
+            if (in.fmt == JT_FMT_DBL) JT_THROW(JT_ERR_UNSUPPORTED, "f64 -> f32-internal resample");
+            if (in.fmt == JT_FMT_S16) launch_linear<int16_t, float, SWR_MODE_STORE>(c, in, p, n_out, (float *)o.d, nullptr, 1, 0);
+            else launch_linear<float, float, SWR_MODE_STORE>(c, in, p, n_out, (float *)o.d, nullptr, 1, 0);
+        } else JT_THROW(JT_ERR_UNSUPPORTED, "swr work format %d", work_fmt);
+        return o;
+    }
     if (work_fmt == JT_FMT_DBL) {
         if (small_path(p)) {
             if (in.fmt == JT_FMT_S16) launch_small<int16_t, SWR_MODE_STORE>(c, in, p, n_out, (double *)o.d, nullptr, 1, 0);
@@ -681,8 +771,12 @@ void jt_swr_tick_absmax(jt_ctx *c, const Sig &in, const SwrPlan &p, int tick, in
     Sig v = in.fmt == JT_FMT_S32 ? jt_convert(c, in, JT_FMT_DBL) : in; v.n = std::min(in.n, fed);
     const int64_t n_out = p.out_count(v.n);
     if (n_out <= 0) return;
-    JtLaunch Lc(c, small_path(p) ? "truepeak_oversample:small_f64" : phase_path_ok(p) ? "truepeak_oversample:phase_f64" : qlane_path_ok(p) ? "truepeak_oversample:qlane_f64" : "truepeak_oversample:generic");
-    if (small_path(p)) {
+    JtLaunch Lc(c, p.linear ? "truepeak_oversample:linear" : small_path(p) ? "truepeak_oversample:small_f64" : phase_path_ok(p) ? "truepeak_oversample:phase_f64" : qlane_path_ok(p) ? "truepeak_oversample:qlane_f64" : "truepeak_oversample:generic");
+    if (p.linear) {
+        if (v.fmt == JT_FMT_S16) launch_linear<int16_t, double, SWR_MODE_TICKMAX>(c, v, p, n_out, (double *)nullptr, d_tick_tp, tick, n_ticks);
+        else if (v.fmt == JT_FMT_FLT) launch_linear<float, double, SWR_MODE_TICKMAX>(c, v, p, n_out, (double *)nullptr, d_tick_tp, tick, n_ticks);
+        else launch_linear<double, double, SWR_MODE_TICKMAX>(c, v, p, n_out, (double *)nullptr, d_tick_tp, tick, n_ticks);
+    } else if (small_path(p)) {
         if (v.fmt == JT_FMT_S16) launch_small<int16_t, SWR_MODE_TICKMAX>(c, v, p, n_out, nullptr, d_tick_tp, tick, n_ticks);
         else if (v.fmt == JT_FMT_FLT) launch_small<float, SWR_MODE_TICKMAX>(c, v, p, n_out, nullptr, d_tick_tp, tick, n_ticks);
         else launch_small<double, SWR_MODE_TICKMAX>(c, v, p, n_out, nullptr, d_tick_tp, tick, n_ticks);

@@ -35,7 +35,8 @@ static int64_t gcd64(int64_t a, int64_t b) { while (b) { int64_t t = a % b; a = 
 
 typedef struct {
     int phase_count, filter_length, filter_alloc;
-    int dst_incr_div;      /* index advance per output sample, in 1/phase_count input samples */
+    int64_t inc_num, inc_den; /* index advance per output sample = inc_num / inc_den, in 1/phase_count input samples
+                              * (swr's dst_incr / src_incr, reduced): output m reads from index0 + floor(m inc_num / inc_den) */
     double *bank;          /* phase_count x filter_alloc */
     int in_rate, out_rate;
 } swr_plan;
@@ -48,15 +49,23 @@ static int plan_init2(swr_plan *p, int in_rate, int out_rate, int build_bank)
     int phase_count = 1 << phase_shift;
     int64_t g = gcd64(out_rate, in_rate);
     int64_t pc_exact = out_rate / g;
-    if (pc_exact > phase_count) return -1;          /* non-exact ratios: linear-interp path, not restated */
-    phase_count = (int)pc_exact;
+    /* exact_rational (default on): the reduced phase count when it fits, else the full 1 << phase_shift phases
+     * with a fractional index advance (index += dst_incr_div; frac += dst_incr_mod; carry at src_incr) and -- swr's
+     * linear_interp option defaults to on, and swri_resample() picks resample_linear whenever frac or dst_incr_mod is
+     * non-zero -- a linear interpolation between the two neighbouring phases by frac / src_incr
+     * (resample_template.c resample_linear; checked live against the real library, tests/test_oracle_swr.py) */
+    if (pc_exact <= phase_count) phase_count = (int)pc_exact;
     p->phase_count = phase_count;
     p->filter_length = (int)ceil(filter_size / factor);
     if (p->filter_length < 1) p->filter_length = 1;
     p->filter_alloc = (p->filter_length + 7) & ~7;
     p->in_rate = in_rate; p->out_rate = out_rate;
-    /* dst_incr/src_incr = in_rate*phase_count/out_rate exactly (exact_rational) */
-    p->dst_incr_div = (int)(((int64_t)in_rate * phase_count) / out_rate);
+    /* dst_incr / src_incr = in_rate * phase_count / out_rate (av_reduce; the power-of-two scaling that follows in
+     * swri_resample_init changes neither quotient nor carries) */
+    {
+        int64_t num = (int64_t)in_rate * phase_count, den = out_rate, gg = gcd64(num, den);
+        p->inc_num = num / gg; p->inc_den = den / gg;
+    }
     p->bank = NULL;
     if (!build_bank) return 0;
     p->bank = (double *)calloc((size_t)(phase_count + 1) * p->filter_alloc, sizeof(double));
@@ -94,6 +103,10 @@ static int plan_init2(swr_plan *p, int in_rate, int out_rate, int build_bank)
                 p->bank[(phase_count - ph) * alloc + tap_count - 1 - i] = p->bank[ph * alloc + i];
     }
     free(tab); free(sin_lut);
+    /* row phase_count, the upper neighbour of the last phase = phase 0 one sample later (swri_resample_init:
+     * memcpy of row 0 shifted by one tap, its first tap taken from row 0's last allocated slot) */
+    for (int i = 0; i + 1 < alloc; i++) p->bank[phase_count * alloc + i + 1] = p->bank[i];
+    p->bank[phase_count * alloc] = p->bank[alloc - 1];
     return 0;
 }
 
@@ -110,7 +123,8 @@ static int64_t outputs_available(const swr_plan *p, int64_t n_avail)
     int64_t index0 = -pc * c;
     int64_t span = end_index - index0;
     if (span <= 0) return 0;
-    return (span + p->dst_incr_div - 1) / p->dst_incr_div;
+    /* outputs m with floor(m inc_num / inc_den) < span */
+    return (span * p->inc_den + p->inc_num - 1) / p->inc_num;
 }
 
 /* swr holds back output until filter_length+1 input samples have arrived
@@ -125,7 +139,7 @@ static int64_t reflection_len(const swr_plan *p, int64_t n_in, int64_t m_done)
 {
     /* in_buffer_count at flush time = samples from the next output's first tap to the end */
     const int64_t pc = p->phase_count, L = p->filter_length, c = (L - 1) / 2;
-    int64_t pos = -pc * c + m_done * (int64_t)p->dst_incr_div;
+    int64_t pos = -pc * c + (m_done * p->inc_num) / p->inc_den;
     int64_t sidx = pos >= 0 ? pos / pc : -((-pos + pc - 1) / pc);
     int64_t cnt = n_in - sidx;
     if (cnt > L) cnt = L;
@@ -190,16 +204,28 @@ int64_t NAME(const T *in, int64_t n, int in_rate, int out_rate, int flush, T *ou
     }                                                                                        \
     if (total > cap) total = cap;                                                            \
     /* the bank in the working precision */                                                  \
-    T *bank = (T *)malloc(sizeof(T) * (size_t)pc * L);                                       \
-    for (int64_t ph = 0; ph < pc; ph++)                                                      \
+    T *bank = (T *)malloc(sizeof(T) * (size_t)(pc + 1) * L);                                 \
+    for (int64_t ph = 0; ph <= pc; ph++)                                                     \
         for (int64_t i = 0; i < L; i++) bank[ph * L + i] = (T)p.bank[ph * p.filter_alloc + i]; \
     for (int64_t m = 0; m < total; m++) {                                                    \
-        int64_t pos = -pc * c + m * (int64_t)p.dst_incr_div;                                 \
+        int64_t pos = -pc * c + (m * p.inc_num) / p.inc_den;                                 \
         int64_t sidx = pos >= 0 ? pos / pc : -((-pos + pc - 1) / pc);                        \
         int64_t ph = pos - sidx * pc;                                                        \
         const T *f = bank + ph * L;                                                          \
         ACC val = 0, val2 = 0;                                                               \
         int64_t i;                                                                           \
+        if (p.inc_den > 1) {                      /* resample_linear */                      \
+            const int64_t frac = (m * p.inc_num) % p.inc_den;                                \
+            for (i = 0; i < L; i++) {                                                        \
+                int64_t a = sidx + i;                                                        \
+                if (a < 0) a = -a; else if (a >= n) a = 2 * n - 1 - a;                       \
+                val  += in[a] * (ACC)f[i];                                                   \
+                val2 += in[a] * (ACC)f[i + L];                                               \
+            }                                                                                \
+            val += (val2 - val) * (ACC)frac / (ACC)p.inc_den;                                \
+            out[m] = (T)val;                                                                 \
+            continue;                                                                        \
+        }                                                                                    \
         for (i = 0; i + 1 < L; i += 2) {                                                     \
             int64_t a = sidx + i, b = sidx + i + 1;                                          \
             if (a < 0) a = -a; else if (a >= n) a = 2 * n - 1 - a;                           \

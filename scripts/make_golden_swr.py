@@ -55,5 +55,10 @@ out["s32_to_dbl_48000_192000"] = ref_swr.convert(s32, "s32", 48000, "dbl", 19200
 # loudnorm's dynamic-mode output leaves at 192 kHz / dbl: the aresample barrier back to the source rate
 for (ir, orr) in ((192000, 44100), (192000, 48000)):
     out[f"dbl_noise_{ir}_{orr}_1"] = ref_swr.convert(noise, "dbl", ir, "dbl", orr, frame=4096, flush=True)
+# inexact ratios (reduced phase count > 1024): 1024 phases, fractional index advance, resample_linear
+for (ir, orr) in ((22050, 192000), (11025, 192000), (47999, 44100)):
+    for flush in (0, 1):
+        out[f"dbl_noise_{ir}_{orr}_{flush}"] = ref_swr.convert(noise[:2000], "dbl", ir, "dbl", orr, frame=700, flush=bool(flush))
+out["flt_22050_192000"] = ref_swr.convert(noise[:2000].astype(np.float32), "flt", 22050, "flt", 192000, frame=700, flush=True)
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "swr_golden.npz"), **out)
 print("wrote", len(out), "arrays")

@@ -69,6 +69,43 @@ def test_anlmdn_44k_and_ragged(ctx):
     assert np.max(np.abs(g - e)) < 2e-6
 
 
+def _nlm_mixed(rate, seed):
+    """bursts that decay into room tone of -58 .. -90 dBFS, digital silence, a tone fading out: hops on both sides of the
+    screening decision (k_nlm_screen) and groups that mix them"""
+    rng = np.random.default_rng(seed)
+    parts = []
+    for k, floor_db in enumerate((-58.0, -70.0, -90.0, None, -66.0)):
+        n = int(rate * (0.35 + 0.11 * k))
+        t = np.arange(n) / rate
+        burst = synth.speech_like(n / rate + 0.1, rate, seed=seed + k)[:n] * np.exp(-t * (25.0 + 10 * k))
+        tone = 0.2 * np.sin(2 * np.pi * (140 + 60 * k) * t) * np.exp(-t * 40.0)
+        noise = 0.0 if floor_db is None else rng.standard_normal(n) * 10 ** (floor_db / 20)
+        parts.append(burst + tone + noise)
+        if floor_db is None:
+            parts.append(np.zeros(int(rate * 0.05)))
+    return np.concatenate(parts).astype(np.float32)
+
+
+@pytest.mark.parametrize("rate,spec", [(48000, "anlmdn=s=0.00001:p=0.0060:r=0.0020:m=3"), (96000, "anlmdn=s=0.00001:p=0.0060:r=0.0020:m=3"),
+                                       (44100, "anlmdn=s=0.00001:p=0.0060:r=0.0058:m=11"), (48000, "anlmdn=s=0.0001:p=0.0004:r=0.0010:m=5"),
+                                       (192000, "anlmdn=s=0.00001:p=0.0030:r=0.0020:m=3")])
+def test_anlmdn_screen_is_exact(ctx, monkeypatch, rate, spec):
+    """the screening pass only skips hops whose output is the delayed input: bit-identical to walking every hop"""
+    x = _nlm_mixed(rate, 31)[:-13]
+    monkeypatch.setenv("JT_ANLMDN_NO_SCREEN", "1")
+    full = ctx.run_graph(spec, x, rate, want_meta=False)["pcm"]
+    monkeypatch.delenv("JT_ANLMDN_NO_SCREEN")
+    got = ctx.run_graph(spec, x, rate, want_meta=False)["pcm"]
+    assert np.array_equal(got.view(np.uint32), full.view(np.uint32))
+    exp = OG.run_spec(spec, x, rate)["pcm"]
+    assert np.max(np.abs(got - exp)) < 2e-6
+    # both kinds of hop are present: samples the denoiser changed and samples it passed through
+    K = int(round(float(spec.split("p=")[1].split(":")[0]) * rate)); S = int(round(float(spec.split("r=")[1].split(":")[0]) * rate))
+    d = K + S
+    same = exp[d:] == x[:len(x) - d]
+    assert 0.02 < np.mean(same) < 0.98
+
+
 @pytest.mark.parametrize("spec", ["afftdn=nr=12:nt=w:tn=1", "afftdn=nr=12:nt=w:tn=0:nf=-58",
                                   "afftdn=nr=12:nt=custom:bn=2.5|1.0|0.5|0.0|-0.5|-1.0|-1.5|-2.0|-2.0|-1.0|0.0|1.0|2.0|3.0|4.0:tn=0:nf=-62"])
 def test_afftdn(ctx, speech48, spec):

@@ -20,6 +20,33 @@ def test_aresample_f64_vs_real_swr_golden(ctx, rates):
     assert np.max(np.abs(got["pcm"] - ref)) < 1e-14
 
 
+@pytest.mark.parametrize("rates", [(22050, 192000), (11025, 192000), (47999, 44100)])
+def test_aresample_inexact_ratio_vs_real_swr_golden(ctx, rates):
+    """swr's linear-interpolated path (k_swr_linear) against outputs of the real library"""
+    x = G["in_noise"][:2000]
+    ref = G[f"dbl_noise_{rates[0]}_{rates[1]}_1"]
+    got = ctx.run_graph(f"aresample={rates[1]}", x, rates[0], want_meta=False)
+    assert got["rate"] == rates[1] and len(got["pcm"]) == len(ref)
+    assert np.max(np.abs(got["pcm"] - ref)) < 1e-14
+    if rates[0] == 22050:
+        gf = ctx.run_graph("aresample=192000", x.astype(np.float32), 22050, want_meta=False)
+        assert gf["fmt"] == gpudsp.FMT_FLT and len(gf["pcm"]) == len(G["flt_22050_192000"])
+        assert np.max(np.abs(gf["pcm"] - G["flt_22050_192000"])) < 5e-7
+
+
+@pytest.mark.parametrize("rate", [22050, 11025])
+def test_true_peak_of_a_22k_source(ctx, rate):
+    """ebur128 peak=true on a source whose ratio to 192 kHz is inexact: per-frame and whole-stream true peaks vs the oracle"""
+    import oracle_graph as OG
+    from jivetalking_b200 import synth
+    x = synth.speech_like(7.3, rate, seed=5)
+    spec = "ebur128=metadata=1:peak=sample+true:dualmono=true:target=-16"
+    got = ctx.run_graph(spec, x, rate, want_pcm=False)
+    exp = OG.run_spec(spec, x, rate)
+    OG.assert_meta_close(got["meta"], exp["meta"])
+    assert got["meta"][-1].r128_true_peak > 0.01
+
+
 def test_output_stage_48k_to_s16_44k(ctx):
     rng = np.random.default_rng(11)
     x = (rng.standard_normal(100003) * 0.25)

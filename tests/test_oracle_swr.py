@@ -21,6 +21,24 @@ def test_resample_f64_matches_real_swr(name, rates, flush):
     assert np.max(np.abs(y - ref)) < 2e-15          # taps summed in a different order than the SIMD asm
 
 
+INEXACT = [(22050, 192000), (11025, 192000), (47999, 44100)]
+
+
+@pytest.mark.parametrize("rates", INEXACT)
+@pytest.mark.parametrize("flush", [0, 1])
+def test_inexact_ratio_linear_interpolated_path_matches_real_swr(rates, flush):
+    """reduced phase count > 1024 (a 22.05 kHz source into ebur128's 192 kHz true-peak oversampler): 1024 phases, fractional
+    index advance, linear interpolation between neighbouring phases (resample_template.c resample_linear)"""
+    x = G["in_noise"][:2000]
+    ref = G[f"dbl_noise_{rates[0]}_{rates[1]}_{flush}"]
+    y = O.swr_resample(x, rates[0], rates[1], flush=bool(flush))
+    assert len(y) == len(ref)
+    assert np.max(np.abs(y - ref)) < 2e-15
+    if rates == (22050, 192000) and flush:
+        yf = O.swr_resample(x.astype(np.float32), 22050, 192000, flush=True)
+        assert len(yf) == len(G["flt_22050_192000"]) and np.max(np.abs(yf - G["flt_22050_192000"])) < 5e-7
+
+
 def test_resample_f32_internal_path():
     x = G["in_noise"].astype(np.float32)
     ref = G["flt_44100_192000"]
@@ -68,7 +86,7 @@ def test_live_against_library_when_present():
     rng = np.random.default_rng(3)
     for n in (150, 4097, 30011):      # streams shorter than the filter (n <= filter_length) take a swr corner path not restated
         x = rng.standard_normal(n) * 0.1
-        for (a, b) in RATES + [(44100, 48000)]:
+        for (a, b) in RATES + [(44100, 48000)] + INEXACT + [(44100, 47999), (37800, 192000)]:
             ref = ref_swr.convert(x, "dbl", a, "dbl", b, frame=1000, flush=True)
             y = O.swr_resample(x, a, b, flush=True)
             assert len(y) == len(ref) and (len(y) == 0 or np.max(np.abs(y - ref)) < 2e-15)
