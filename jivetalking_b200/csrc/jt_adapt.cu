@@ -17,6 +17,8 @@
 #include <string>
 #include <vector>
 
+extern "C" void jt_vad_assign_astats(const jt_measurements *m, jt_voice_activity *va);
+
 namespace {
 
 typedef int64_t ns_t;
@@ -56,6 +58,15 @@ inline int    go_cmp(double x, double y) {                                      
     return x < y ? -1 : (x > y ? 1 : 0);
 }
 inline void   go_sort(std::vector<double> &v) { std::sort(v.begin(), v.end(), go_less); }
+// element k of the slice as slices.Sort would leave it, without sorting the rest (the detector only ever reads single order
+// statistics of its 14 400-per-hour level lists: six full sorts were half of its run time)
+inline double go_kth(std::vector<double> &v, int64_t k) { std::nth_element(v.begin(), v.begin() + k, v.end(), go_less); return v[(size_t)k]; }
+inline double go_pct(std::vector<double> &v, double pct)           // pct_sorted of the sorted slice
+{
+    if (v.empty()) return 0;
+    pct = pct < 0 ? 0 : (pct > 100 ? 100 : pct);
+    return go_kth(v, (int64_t)(pct / 100 * (double)(v.size() - 1)));
+}
 inline double dur_seconds(ns_t d) { return (double)(d / kSec) + (double)(d % kSec) / 1e9; }              // Duration.Seconds
 inline bool   is_finite(double v) { return !std::isnan(v) && !std::isinf(v); }
 inline double db_to_linear(double db) { return pow(10.0, db / 20.0); }                                    // filters.go:591-593
@@ -409,8 +420,7 @@ void gate_statistics(const View &v, double split, int axis, const jt_region *spe
         const Span r = in_range(v, speech->start_ns, speech->end_ns);
         for (int64_t i = r.lo; i < r.hi; i++) if (is_speech(v.iv[i], split, axis)) voiced.push_back(level_of(v.iv[i], axis));
     }
-    go_sort(voiced); go_sort(noise);
-    voiced_low = pct_sorted(voiced, kGateVoicedLowPct); noise_high = pct_sorted(noise, kGateNoiseHighPct); sep = voiced_low - noise_high;
+    voiced_low = go_pct(voiced, kGateVoicedLowPct); noise_high = go_pct(noise, kGateNoiseHighPct); sep = voiced_low - noise_high;
 }
 
 double floored_fraction(const View &v, int axis)                                  // analyser_vad.go:683-697
@@ -427,8 +437,7 @@ bool estimate_noise_floor(const View &v, double &floor, double &thr)
     if (v.n < kSilenceMinIntervals) return false;
     std::vector<double> lv((size_t)v.n), fx((size_t)v.n);
     for (int64_t i = 0; i < v.n; i++) { lv[i] = v.iv[i].momentary_lufs; fx[i] = v.iv[i].spectral[JT_SP_flux]; }
-    go_sort(lv); go_sort(fx);
-    const double l50 = lv[v.n / 2], f50 = fx[v.n / 2];
+    const double l50 = go_kth(lv, v.n / 2), f50 = go_kth(fx, v.n / 2);
     struct Scored { int64_t idx; double level, score; };
     std::vector<Scored> sc((size_t)v.n);
     for (int64_t i = 0; i < v.n; i++) {
@@ -439,12 +448,15 @@ bool estimate_noise_floor(const View &v, double &floor, double &thr)
         if (f50 > 0 && x.spectral[JT_SP_flux] > f50) { const double ratio = x.spectral[JT_SP_flux] / f50; if (ratio > 1) flx = 1.0 / ratio; }
         sc[i] = Scored{i, x.momentary_lufs, kRoomAmpW * amp + kRoomFluxW * flx};
     }
-    std::sort(sc.begin(), sc.end(), [](const Scored &a, const Scored &b) {
+    int64_t cnt = v.n / kSeedTopDiv; cnt = std::max<int64_t>(cnt, kSeedMinCount); cnt = std::min<int64_t>(cnt, v.n);
+    // the order is total (index breaks ties), so the first cnt elements of the sorted slice are a well-defined SET, and only
+    // their maximum level is read: a selection instead of the sort
+    auto before = [](const Scored &a, const Scored &b) {
         int c = go_cmp(b.score, a.score); if (c) return c < 0;
         c = go_cmp(a.level, b.level); if (c) return c < 0;
         return a.idx < b.idx;
-    });
-    int64_t cnt = v.n / kSeedTopDiv; cnt = std::max<int64_t>(cnt, kSeedMinCount); cnt = std::min<int64_t>(cnt, v.n);
+    };
+    if (cnt < v.n) std::nth_element(sc.begin(), sc.begin() + cnt, sc.end(), before);
     double mx = -120.0; bool seen = false;
     for (int64_t i = 0; i < cnt; i++) { const double l = sc[i].level; if (is_floored(l)) continue; if (!seen || l > mx) { mx = l; seen = true; } }
     if (!seen) return false;
@@ -744,10 +756,11 @@ static void detect(const View &v, double seed, jt_voice_activity &va, std::vecto
 {
     const int axis = 0; const ns_t hop = kIntervalHop;
     const Hist h = build_hist(v, axis, 1.0);
-    const std::vector<double> levels = vad_levels(v, axis);
-    const double p75 = pct_sorted(levels, 75);
+    std::vector<double> levels; levels.reserve((size_t)v.n);           // vad_levels without the sort: two order statistics are read
+    for (int64_t i = 0; i < v.n; i++) { const double l = level_of(v.iv[i], axis); if (!is_floored(l)) levels.push_back(l); }
+    const double p75 = go_pct(levels, 75);
     const double split = clamp_split(otsu(h), seed, p75);
-    const double floor = percentile_floor(levels.data(), (int64_t)levels.size(), seed);
+    const double floor = gomax(go_pct(levels, kNoiseFloorPct), seed + kNoiseMarginDB);        // percentile_floor
     std::vector<uint8_t> flags((size_t)v.n);
     for (int64_t i = 0; i < v.n; i++) flags[i] = is_speech(v.iv[i], split, axis);
     const double margin = hysteresis_margin(h, split);
@@ -806,15 +819,23 @@ extern "C" int jt_detect_voice_activity(const jt_measurements *m, const jt_inter
     double seed, thr;
     if (!estimate_noise_floor(v, seed, thr)) { seed = kLevelFloorDB; thr = adaptive_silence_threshold(kLevelFloorDB); }
     va.floor_prescan = seed; va.room_tone_detect_level = thr;
-    const Meas g = go_meas(m);
-    const bool astats_found = !std::isnan(m->astats[JT_AS_Dynamic_range]);
-    va.floor_astats = astats_found && !std::isnan(m->astats[JT_AS_Noise_floor]) ? m->astats[JT_AS_Noise_floor] : 0.0;
     std::vector<jt_region> runs; std::vector<jt_speech_candidate> cands;
     detect(v, seed, va, runs, cands);
-    // assignInputMeasurementSuggestions (analyser.go:515-531)
-    if (g.rms_level != 0 && va.floor != 0) va.reduction_headroom = gomax(0, gomin(60, g.rms_level - va.floor));
-    else va.reduction_headroom = m->input_i > -20.0 ? 40.0 : (m->input_i > -30.0 ? 25.0 : 15.0);
+    jt_vad_assign_astats(m, &va);
     return emit(va, runs, cands, out, regions_out, regions_cap, cands_out, cands_cap);
+}
+
+// The two values of jt_detect_voice_activity that read astats' whole-file statistics (nothing in the detector itself does): the
+// adaptive driver runs the detector while Pass 1's astats is still on the GPU and calls this once its values are in `m`.
+extern "C" void jt_vad_assign_astats(const jt_measurements *m, jt_voice_activity *va)
+{
+    if (!m || !va) return;
+    const Meas g = go_meas(m);
+    const bool astats_found = !std::isnan(m->astats[JT_AS_Dynamic_range]);
+    va->floor_astats = astats_found && !std::isnan(m->astats[JT_AS_Noise_floor]) ? m->astats[JT_AS_Noise_floor] : 0.0;
+    // assignInputMeasurementSuggestions (analyser.go:515-531)
+    if (g.rms_level != 0 && va->floor != 0) va->reduction_headroom = gomax(0, gomin(60, g.rms_level - va->floor));
+    else va->reduction_headroom = m->input_i > -20.0 ? 40.0 : (m->input_i > -30.0 ? 25.0 : 15.0);
 }
 
 extern "C" void jt_band_plan(double lo[17], double hi[17])

@@ -44,9 +44,14 @@ extern "C" int jt_create(int device, jt_ctx **out)
     if (prop.major < 10) return JT_ERR_CUDA;                                           // built for sm_100a only
     jt_ctx *c = new jt_ctx();
     c->device = device; c->num_sms = prop.multiProcessorCount;
-    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return JT_ERR_CUDA; }
+    // three priority levels: the side stream (band graphs the host is waiting for) above the main stream above the low stream
+    int pr_least = 0, pr_greatest = 0;
+    if (cudaDeviceGetStreamPriorityRange(&pr_least, &pr_greatest) != cudaSuccess) { pr_least = pr_greatest = 0; }
+    const int pr_main = pr_greatest < pr_least ? std::min(pr_greatest + 1, pr_least) : pr_least;
+    if (cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, pr_main) != cudaSuccess) { delete c; return JT_ERR_CUDA; }
     if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaStreamDestroy(c->stream); delete c; return JT_ERR_CUDA; }
-    if (cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaStreamDestroy(c->copy_stream); cudaStreamDestroy(c->stream); delete c; return JT_ERR_CUDA; }
+    if (cudaStreamCreateWithPriority(&c->side_stream, cudaStreamNonBlocking, pr_greatest) != cudaSuccess) { cudaStreamDestroy(c->copy_stream); cudaStreamDestroy(c->stream); delete c; return JT_ERR_CUDA; }
+    if (pr_main < pr_least && cudaStreamCreateWithPriority(&c->low_stream, cudaStreamNonBlocking, pr_least) != cudaSuccess) c->low_stream = nullptr;
     *out = c;
     return JT_OK;
 }
@@ -68,6 +73,7 @@ extern "C" void jt_destroy(jt_ctx *c)
     for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     if (c->side_stream) { cudaStreamSynchronize(c->side_stream); cudaStreamDestroy(c->side_stream); }
+    if (c->low_stream) { cudaStreamSynchronize(c->low_stream); cudaStreamDestroy(c->low_stream); }
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
     delete c;
 }
@@ -138,9 +144,11 @@ template <class F> static int guarded(jt_ctx *c, F body)
     try { body(); }
     catch (const JtError &e) { rc = e.code; c->last_error = e.msg; }
     catch (const std::bad_alloc &) { rc = JT_ERR_NOMEM; c->last_error = "host allocation failed"; }
+    if (c->low_stream) cudaStreamSynchronize(c->low_stream);      // (idle unless the call failed half-way)
     jt_release_all(c);
     cudaError_t e = cudaStreamSynchronize(c->stream);
     if (rc == JT_OK && e != cudaSuccess) { rc = JT_ERR_CUDA; c->last_error = cudaGetErrorString(e); }
+    jt_trace_dump(c);
     e = cudaStreamSynchronize(c->copy_stream);
     if (rc == JT_OK && e != cudaSuccess) { rc = JT_ERR_CUDA; c->last_error = cudaGetErrorString(e); }
     cudaError_t e2 = cudaGetLastError();
@@ -420,6 +428,7 @@ static void analyse_finish(jt_ctx *c, AnalysePending &ap, jt_measurements *out, 
 {
     GraphResult g;
     jt_graph_finish(c, ap.g, g);
+    jt_trace(c, "pass1 records done");
     JT_CUDA(cudaEventSynchronize(ap.ev));
     analyse_accumulate(c, g, ap.h_ss, ap.h_pk, ap.nsrc, ap.n_frames, ap.rate, ap.channels, ap.F, out, iv, iv_cap, n_iv);
 }
@@ -1057,6 +1066,28 @@ extern "C" int jt_debug_graph_plan(const char *spec, int64_t n, int rate, int ch
     return JT_OK;
 }
 
+// test hook (tests/test_frame_cadence.py): the sink-frame list of the device-free plan, six int64 per frame
+// (start, nb, ready, astats_pos, hop, tick); returns the number of sink frames (or a negative error code)
+extern "C" int64_t jt_debug_graph_frames(const char *spec, int64_t n, int rate, int channels, int fmt, int frame_size, int want_pcm, int64_t *out, int64_t cap_frames)
+{
+    if (!spec) return JT_ERR_INVALID_ARG;
+    try {
+        GraphRun gd;
+        jt_graph_build(nullptr, spec, nullptr, n, rate, channels, fmt, frame_size, want_pcm != 0, true, JT_GRAPH_DRY, nullptr, gd);
+        const int64_t nf = (int64_t)gd.frames.size();
+        if (out) {
+            if (nf > cap_frames) return JT_ERR_BUFFER;
+            for (int64_t i = 0; i < nf; i++) {
+                const FrameRef &f = gd.frames[(size_t)i];
+                int64_t *o = out + 6 * i;
+                o[0] = f.start; o[1] = f.nb; o[2] = f.ready; o[3] = f.astats_pos; o[4] = f.hop; o[5] = f.tick;
+            }
+        }
+        return nf;
+    } catch (const JtError &e) { return e.code; }
+    catch (const std::bad_alloc &) { return JT_ERR_NOMEM; }
+}
+
 // ---------------------------------------------------------------------------------------
 // K20: band RMS batch (measureSpeechBandRMS, analyser_bands.go:33-104)
 // ---------------------------------------------------------------------------------------
@@ -1284,6 +1315,7 @@ static void process_device(jt_ctx *c, const void *d_in, int64_t n_frames, int ra
     jt_graph_enqueue(c, pass2_spec ? pass2_spec : PASS2_DEFAULT_SPEC, d_in, n_frames, rate, channels, fmt, 4096, true, true, g2, head);
     if (g2.out.fmt != JT_FMT_S16 || g2.out.rate != 44100) JT_THROW(JT_ERR_SPEC, "Pass-2 spec must end in the s16/44.1 kHz output stage (processor.go:379-384)");
     jt_release_since(c, mark, g2.out.d);          // keep only the Pass-2 output ("the FLAC on disk")
+    jt_trace(c, "pass2 enqueued");
     jt_check_cancel(c);
     const size_t mark1 = c->allocs.size();
     AnalysePending p1;
@@ -1306,8 +1338,10 @@ static void process_device(jt_ctx *c, const void *d_in, int64_t n_frames, int ra
     // Pass 3: the Pass-2 output is re-read as the s16 FLAC the reference wrote (processor.go:126-146)
     const size_t mark3 = c->allocs.size();
     GraphRun g3;
+    jt_trace(c, "pass3 planned");
     jt_graph_enqueue(c, spec3, g2.out.d, g2.out.n, 44100, 1, JT_FMT_S16, 4096, false, false, g3);
     jt_release_since(c, mark3, nullptr);
+    jt_trace(c, "pass3 enqueued");
     // Pass 1: host part, while the GPU runs Pass 1 and Pass 3
     if (pass1_done) R.input = *pass1_done; else analyse_finish(c, p1, &R.input, nullptr, 0, nullptr);
     jt_check_cancel(c);
@@ -1318,6 +1352,7 @@ static void process_device(jt_ctx *c, const void *d_in, int64_t n_frames, int ra
         jt_graph_finish(c, g3, r3);
         R.pass3 = r3.ln;
     }
+    jt_trace(c, "pass3 finished");
     const double mI = jt_wire("%.2f", R.pass3.input_i);
     if (std::isinf(mI) || std::isnan(mI) || mI < -70.0) JT_THROW(JT_ERR_INVALID_ARG, "cannot normalise silent audio (measured %.1f LUFS)", mI);
     jt_check_cancel(c);
@@ -1328,6 +1363,7 @@ static void process_device(jt_ctx *c, const void *d_in, int64_t n_frames, int ra
     R.effective_target_i = eff; R.linear_possible = eff == tI;
     GraphRun g4;
     jt_graph_enqueue(c, spec4, g2.out.d, g2.out.n, 44100, 1, JT_FMT_S16, 4096, true, true, g4);
+    jt_trace(c, "pass4 enqueued");
     R.n_out = g4.out.n;
     if (pcm_out && g4.out.n > cap) JT_THROW(JT_ERR_BUFFER, "pcm_out holds %lld samples, chain produced %lld", (long long)cap, (long long)g4.out.n);
     // processor.go:150-160 and normalise.go's Pass-4 re-measure of the same regions: queued behind Pass 4 now, so the GPU goes
@@ -1337,8 +1373,10 @@ static void process_device(jt_ctx *c, const void *d_in, int64_t n_frames, int ra
         measure_output_regions_enqueue(c, g2.out.d, g2.out.n, an->voice_activity, reg2);
         measure_output_regions_enqueue(c, g4.out.d, g4.out.n, an->voice_activity, reg4);
     }
+    jt_trace(c, "regions enqueued");
     // Pass 2: host part (sink-frame records, accumulators), while the GPU runs Pass 4
     jt_graph_finish_acc(c, g2, &R.filtered, nullptr);
+    jt_trace(c, "pass2 accumulated");
     if (pcm_out) {                                 // the result leaves while the host assembles Pass 4's metadata
         const size_t ob = (size_t)g4.out.n * sizeof(int16_t);
         // the copy engine takes the result as soon as its last sample exists (ev_out), while the compute stream goes on
@@ -1350,12 +1388,15 @@ static void process_device(jt_ctx *c, const void *d_in, int64_t n_frames, int ra
         } else if (ob) JT_CUDA(cudaMemcpyAsync(pcm_out, g4.out.d, ob, out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
     }
     jt_graph_finish_acc(c, g4, &R.final, &R.pass4);
+    jt_trace(c, "pass4 accumulated");
     if (an) {
         measure_output_regions_finish(c, reg2, &an->filtered_regions);
         measure_output_regions_finish(c, reg4, &an->final_regions);
     }
+    jt_trace(c, "regions finished");
     JT_CUDA(cudaStreamSynchronize(c->stream));
     JT_CUDA(cudaStreamSynchronize(c->copy_stream));
+    jt_trace(c, "end");
     if (res) *res = R;
 }
 
@@ -1403,14 +1444,19 @@ static void analyse_adaptive_device(jt_ctx *c, const void *d_in, int64_t n_frame
     jt_interval *iv = iv_out; int64_t cap = iv_cap;
     if (!iv) { cap = (int64_t)((double)n_frames / rate / 0.25) + 16; own.resize((size_t)cap); iv = own.data(); }
     int64_t n_iv = 0;
+    // astats_later: Pass 1's astats runs on the low-priority stream (process_adaptive_device); the intervals, the detector and
+    // the band graphs do not read it, so its values are collected after them
+    const bool astats_later = pending && pending->g.astats_later;
     if (pending) analyse_finish(c, *pending, &out->measurements, iv, cap, &n_iv);
     else analyse_device(c, d_in, n_frames, rate, channels, fmt, F, &out->measurements, iv, cap, &n_iv);
+    jt_trace(c, "pass1 intervals done");
     if (n_iv_out) *n_iv_out = n_iv;
     if (out->measurements.sink_frames == 0 || std::isnan(out->measurements.input_i))
         JT_THROW(JT_ERR_INVALID_ARG, "ebur128 measurements not found in metadata (analyser.go:397-399)");
     int rc;
     { JtHost hdet(c, "voice_activity_detector"); rc = jt_detect_voice_activity(&out->measurements, iv, n_iv, &out->voice_activity, nullptr, 0, nullptr, 0); }
     if (rc) JT_THROW(rc, "voice-activity detector");
+    jt_trace(c, "detector done");
     jt_voice_activity &va = out->voice_activity;
     // measureSpeechBands + measureNoiseBands: the 2 + 15 band graphs of analyser_bands.go:33 over the elected regions
     double lo[17], hi[17]; jt_band_plan(lo, hi);
@@ -1437,12 +1483,22 @@ static void analyse_adaptive_device(jt_ctx *c, const void *d_in, int64_t n_frame
         if (want_speech) { Sig r = region(va.speech_profile.region.start_ns, va.speech_profile.region.duration_ns); jt_band_rms_batch(c, r, lo, hi, 2, rms, found); }
         if (want_noise) { Sig r = region(va.noise_profile.start_ns, va.noise_profile.duration_ns); jt_band_rms_batch(c, r, lo + 2, hi + 2, 15, rms + 2, found + 2); }
         swap.reset();
+        jt_trace(c, "band graphs done");
         jt_apply_band_rms(&va, want_speech ? rms : nullptr, want_speech ? found : nullptr, want_noise ? rms + 2 : nullptr, want_noise ? found + 2 : nullptr);
+    }
+    if (astats_later && pending->g.has_astats && pending->g.last_astats_frame >= 0) {
+        AstatsResult a;
+        jt_astats_finish(c, pending->g.astp, a);
+        // what MeasAcc::add takes from the record of the last astats frame (latest wins, absent keys stay NaN)
+        if (!pending->g.astats_overall_only)
+            for (int k = 0; k < JT_AS_COUNT; k++) { const double w = std::isnan(a.v[k]) ? NAN : jt_wire("%f", a.v[k]); if (!std::isnan(w)) out->measurements.astats[k] = w; }
+        jt_vad_assign_astats(&out->measurements, &va);
     }
     { JtHost hcfg(c, "adapt_config"); rc = jt_adapt_config(base, &out->measurements, &va, &out->config, &out->diagnostics); }
     if (rc) JT_THROW(rc, "AdaptConfig");
     rc = jt_build_filter_spec(&out->config, out->pass2_spec, sizeof(out->pass2_spec));
     if (rc) JT_THROW(rc, "BuildFilterSpec");
+    jt_trace(c, "spec built");
     jt_release_since(c, mark, nullptr);
 }
 
@@ -1496,21 +1552,45 @@ static void process_adaptive_device(jt_ctx *c, const void *d_in, int64_t n_frame
     }
     AnalysePending p1;
     const size_t mark1 = c->allocs.size();
-    analyse_enqueue(c, d_in, n_frames, rate, channels, fmt, 4096, p1);
-    jt_release_since(c, mark1, nullptr);
+    jt_trace(c, "start");
+    // Pass 1's astats is the one product of Pass 1 the host needs LAST (whole-file values for AdaptConfig; the intervals and the
+    // detector run on the meter's and aspectralstats' rows): it goes to the low-priority stream, where it fills the SMs the
+    // meter / spectral / head kernels leave free and the gap in which the main stream waits for the detector.  Its buffers --
+    // and everything else Pass 1 allocated -- are therefore released only after the host has seen Pass 1's last event.
+    const bool defer = c->low_stream != nullptr && !getenv("JT_NO_DEFER_ASTATS");
+    c->defer_astats = defer;
+    try { analyse_enqueue(c, d_in, n_frames, rate, channels, fmt, 4096, p1); } catch (...) { c->defer_astats = false; throw; }
+    c->defer_astats = false;
+    p1.g.astats_later = defer && p1.g.astats_on_low;
+    if (!defer) jt_release_since(c, mark1, nullptr);
+    const size_t mark1_end = c->allocs.size();
     // the side stream starts behind Pass 1's kernels: the input is in HBM by then, and every arena block Pass 1 has already
     // given back (the arena hands blocks out again at once, relying on stream order) is no longer in use
     cudaEvent_t input_ready = jt_record_event(c);
+    jt_trace(c, "pass1 enqueued");
     const size_t head_mark = c->allocs.size();
     GraphResume head; bool have_head = false;
     if (!head_spec.empty()) { jt_graph_head(c, head_spec, d_in, n_frames, rate, channels, fmt, 4096, head, &predicted_spec); have_head = true; }
-    analyse_adaptive_device(c, d_in, n_frames, rate, channels, fmt, 4096, base, an, nullptr, 0, nullptr, &p1, have_head ? input_ready : nullptr);
+    jt_trace(c, "head enqueued");
+    size_t head_mark_now = head_mark;
+    try {
+        analyse_adaptive_device(c, d_in, n_frames, rate, channels, fmt, 4096, base, an, nullptr, 0, nullptr, &p1, have_head ? input_ready : nullptr);
+    } catch (...) {
+        if (defer) cudaStreamSynchronize(c->low_stream);
+        throw;
+    }
+    if (defer) {
+        // analyse_finish has waited for every event of Pass 1 (astats' included): its blocks can go back to the arena
+        JT_CUDA(cudaStreamSynchronize(c->low_stream));
+        jt_release_range(c, mark1, mark1_end);
+        head_mark_now = head_mark - (mark1_end - mark1);
+    }
     jt_check_cancel(c);
     const std::string spec = an->pass2_spec;
     const bool match = have_head && spec.compare(0, head_spec.size(), head_spec) == 0 && (spec.size() == head_spec.size() || spec[head_spec.size()] == ',');
-    if (have_head && !match) jt_release_since(c, head_mark, nullptr);       // the prediction missed: Pass 2 runs from the input
+    if (have_head && !match) jt_release_since(c, head_mark_now, nullptr);       // the prediction missed: Pass 2 runs from the input
     process_device(c, d_in, n_frames, rate, channels, fmt, an->pass2_spec, pcm_out, out_on_device, cap, res, &an->measurements, &an->config, an,
-                   match ? &head : nullptr, match ? head_mark : (size_t)-1);
+                   match ? &head : nullptr, match ? head_mark_now : (size_t)-1);
 }
 extern "C" int jt_process_audio_adaptive(jt_ctx *c, const void *pcm_in, int64_t n_frames, int rate, int channels, int fmt,
                                          const jt_filter_config *base, int16_t *pcm_out, int64_t cap, jt_process_result *res, jt_analysis *analysis)
@@ -1875,6 +1955,7 @@ static void process_sharded_device(jt_ctx *c, const void *d_local, int64_t n_loc
         if (rc) JT_THROW(rc, "Pass-3 merge");
         lap(T.pass3_merge);
     }
+    jt_trace(c, "pass3 finished");
     const double mI = jt_wire("%.2f", R.pass3.input_i);
     if (std::isinf(mI) || std::isnan(mI) || mI < -70.0) JT_THROW(JT_ERR_INVALID_ARG, "cannot normalise silent audio (measured %.1f LUFS)", mI);
     double eff = 0, off = 0;

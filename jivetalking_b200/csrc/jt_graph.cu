@@ -203,12 +203,64 @@ static std::vector<FrameRef> reframe(const std::vector<FrameRef> &old, int64_t n
     return v;
 }
 
+// `chain` applied to `base`, level by level, without the intermediate lists: frame k of the last level starts at k F; walking
+// the levels downwards, the frame holding a frame's FIRST sample hands down its stamps (the stamp of the latest level wins, as
+// each reframe copies and each filter then overwrites), the frame holding its LAST sample decides when it can be built.
+// Equal to reframe() applied once per level followed by the filters' loops over the new frames.
+static std::vector<FrameRef> frames_collapse(const std::vector<FrameRef> &base, const std::vector<FrameLvl> &chain)
+{
+    if (chain.empty()) return base;
+    const FrameLvl &top = chain.back();
+    std::vector<FrameRef> v;
+    const int64_t cnt = top.F > 0 ? (top.n + top.F - 1) / top.F : 0;
+    v.resize((size_t)std::max<int64_t>(cnt, 0));
+    const int L = (int)chain.size();
+    std::vector<int64_t> lvl_cnt((size_t)L);
+    for (int i = 0; i < L; i++) lvl_cnt[i] = (chain[i].n + chain[i].F - 1) / chain[i].F;
+    size_t a = 0, b = 0;
+    for (int64_t k = 0; k < cnt; k++) {
+        FrameRef f; f.start = k * top.F; f.nb = (int32_t)std::min<int64_t>(top.F, top.n - f.start);
+        int64_t first = f.start, last = f.start + f.nb - 1;
+        bool have_as = false, have_hop = false, have_tick = false, dead = false;
+        for (int i = L - 1; i >= 0; i--) {
+            const FrameLvl &lv = chain[i];
+            if (lvl_cnt[i] <= 0) { dead = true; break; }               // an empty list below: nothing to inherit (reframe: old.empty())
+            const int64_t ia = std::min(first / lv.F, lvl_cnt[i] - 1), ib = std::min(last / lv.F, lvl_cnt[i] - 1);
+            const int64_t sa = ia * lv.F, na = std::min<int64_t>(lv.F, lv.n - sa);
+            if ((lv.tag & JT_LVL_ASTATS) && !have_as) { f.astats_pos = sa + na; have_as = true; }
+            if ((lv.tag & JT_LVL_HOP) && !have_hop) { f.hop = (int32_t)ia; have_hop = true; }
+            if ((lv.tag & JT_LVL_TICK) && !have_tick && na == lv.F) { f.tick = (int32_t)ia; have_tick = true; }
+            first = sa; last = std::min((ib + 1) * lv.F, lv.n) - 1;
+        }
+        if (!dead && !base.empty()) {
+            while (a + 1 < base.size() && base[a + 1].start <= first) a++;
+            if (b < a) b = a;
+            while (b + 1 < base.size() && base[b + 1].start <= last) b++;
+            if (!have_as) f.astats_pos = base[a].astats_pos;
+            if (!have_hop) f.hop = base[a].hop;
+            if (!have_tick) f.tick = base[a].tick;
+            f.ready = base[b].ready;
+        }
+        v[(size_t)k] = f;
+    }
+    return v;
+}
+
 // ---------------------------------------------------------------------------------------
 // executor
 // ---------------------------------------------------------------------------------------
 namespace {
 struct Exec {
     jt_ctx *c; Sig cur; int link_fmt; std::vector<FrameRef> frames;
+    std::vector<FrameLvl> chain;          // pending uniform re-framings of `frames` (collapsed by flush())
+    void ureframe(int64_t F) { FrameLvl l; l.F = std::max<int64_t>(F, 1); l.n = cur.n; chain.push_back(l); }
+    void stamp(unsigned tag)              // the filter's loop over the frames it has just asked for
+    {
+        if (!chain.empty()) { chain.back().tag |= tag; return; }
+        if (tag & JT_LVL_ASTATS) for (FrameRef &fr : frames) fr.astats_pos = fr.start + fr.nb;
+        if (tag & JT_LVL_HOP) for (size_t j = 0; j < frames.size(); j++) frames[j].hop = (int32_t)j;
+    }
+    void flush() { if (!chain.empty()) { std::vector<FrameRef> v = frames_collapse(frames, chain); frames.swap(v); chain.clear(); } }
     // analysis products
     bool has_astats = false, has_spec = false, has_r128 = false, astats_overall_only = false;
     Sig astats_sig, spec_sig; int spec_win = 2048;
@@ -246,6 +298,7 @@ static void do_resample(Exec &E, int out_rate, int out_fmt /* 0 = keep link form
     if (E.dry) { r = src; r.d = nullptr; r.rate = out_rate; r.n = p.out_count_flush(src.n); r.fmt = (work == JT_FMT_FLT && out_fmt == JT_FMT_S16) ? JT_FMT_S16 : work; }
     else r = jt_swr_resample(c, src, p, work, true, out_fmt);
     // frames: one output frame per input frame (aresample filter_frame), then the EOF flush frame
+    E.flush();
     std::vector<FrameRef> nf; int64_t done = 0;
     for (const FrameRef &f : E.frames) {
         const int64_t cnt = std::min<int64_t>(p.out_count(f.start + f.nb), r.n);
@@ -313,6 +366,7 @@ void jt_graph_head(jt_ctx *c, const std::string &head_spec, const void *d_in, in
     out = GraphResume();
     out.head = head_spec;
     jt_graph_build(c, head_spec, d_in, n_frames, rate, channels, fmt, frame_size, true, false, JT_GRAPH_NORMAL, nullptr, g, nullptr, &out);
+    jt_trace(c, "     head built");
     if (predicted_spec && out.cur.d && out.cur.fmt == JT_FMT_FLT && out.link_fmt == JT_FMT_FLT) {
         const std::vector<FilterNode> nodes = jt_parse_spec(*predicted_spec);
         if ((size_t)out.n_nodes < nodes.size() && nodes[(size_t)out.n_nodes].name == "afftdn") {
@@ -355,7 +409,7 @@ void jt_graph_build(jt_ctx *c, const std::string &spec, const void *d_in, int64_
     if (resume) {
         // the head of this spec already ran (jt_graph_head): continue from the state behind it
         if (resume->n_nodes < 0 || (size_t)resume->n_nodes > nodes.size()) JT_THROW(JT_ERR_INVALID_ARG, "internal: graph resume");
-        E.cur = resume->cur; E.link_fmt = resume->link_fmt; E.frames = resume->frames; have_mono = true;
+        E.cur = resume->cur; E.link_fmt = resume->link_fmt; E.frames = resume->frames; E.chain = resume->chain; have_mono = true;
         first_node = (size_t)resume->n_nodes;
     } else E.frames = source_frames(n_frames, frame_size);
 
@@ -363,6 +417,7 @@ void jt_graph_build(jt_ctx *c, const std::string &spec, const void *d_in, int64_
         const FilterNode &f = nodes[ni];
         const bool last = ni + 1 == nodes.size();
         if (!dry) jt_check_cancel(c);
+        if (!dry && c->trace) jt_trace(c, ("   node " + f.name).c_str());
         if (!have_mono) {
             // the only multi-channel-aware filter of the path is the leading downmix
             if (f.name == "aformat" && f.str("channel_layouts", "cl", "") == "mono") {
@@ -381,6 +436,7 @@ void jt_graph_build(jt_ctx *c, const std::string &spec, const void *d_in, int64_
             if (last && !want_pcm && out_rate != E.cur.rate) {
                 // measure-only call: the resampled audio would be discarded, keep the frame cadence only
                 SwrPlan p = jt_swr_plan(E.cur.rate, out_rate);
+                E.flush();
                 std::vector<FrameRef> nf; int64_t done = 0; const int64_t tot = p.out_count_flush(E.cur.n);
                 for (const FrameRef &fr : E.frames) { int64_t cnt = std::min(p.out_count(fr.start + fr.nb), tot); if (cnt > done) { FrameRef o = fr; o.start = done; o.nb = (int32_t)(cnt - done); nf.push_back(o); done = cnt; } }
                 if (tot > done) { FrameRef o; o.start = done; o.nb = (int32_t)(tot - done); o.ready = INT64_MAX; nf.push_back(o); }
@@ -393,7 +449,7 @@ void jt_graph_build(jt_ctx *c, const std::string &spec, const void *d_in, int64_
         } else if (f.name == "asetnsamples") {
             const int n = (int)f.num("n", "nb_out_samples", 1024);
             const bool pad = f.flag("p", "pad", true);
-            E.frames = reframe(E.frames, E.cur.n, n);
+            E.ureframe(n); E.flush();
             if (pad && !chunked && !E.frames.empty() && E.frames.back().nb < n) {
                 const int64_t tot = E.frames.back().start + n;
                 E.frames.back().nb = n;
@@ -411,6 +467,7 @@ void jt_graph_build(jt_ctx *c, const std::string &spec, const void *d_in, int64_
                 len = std::max<int64_t>(e1 - s0, 0);
             }
             const int64_t a = std::min(std::max<int64_t>(s0, 0), E.cur.n), b = std::min(E.cur.n, s0 + len);
+            E.flush();
             std::vector<FrameRef> nf;
             for (const FrameRef &fr : E.frames) {
                 const int64_t lo = std::max(fr.start, a), hi = std::min(fr.start + fr.nb, b);
@@ -443,7 +500,7 @@ void jt_graph_build(jt_ctx *c, const std::string &spec, const void *d_in, int64_
             const double s = f.num("s", "strength", 0.00001), p = f.num("p", "patch", 0.002), r = f.num("r", "research", 0.006), m = f.num("m", "smooth", 11.0);
             if (!dry) E.cur = jt_anlmdn(c, E.cur, s, p, r, m);
             const int K = (int)llround(p * E.cur.rate);      // frames of H = 2K+1 samples
-            E.frames = reframe(E.frames, E.cur.n, 2 * K + 1);
+            E.ureframe(2 * K + 1);
         } else if (f.name == "afftdn") {
             E.materialise(); E.storage(JT_FMT_FLT);
             const AfftdnParams p = parse_afftdn(f);
@@ -458,7 +515,7 @@ void jt_graph_build(jt_ctx *c, const std::string &spec, const void *d_in, int64_
                 E.cur = jt_afftdn(c, E.cur, p, &cy);
                 g.exchanges++;
             } else if (!dry) E.cur = jt_afftdn(c, E.cur, p, nullptr, (resume && ni == first_node) ? &resume->fwd : nullptr);
-            E.frames = reframe(E.frames, E.cur.n, E.cur.rate / 80);
+            E.ureframe(E.cur.rate / 80);
         } else if (f.name == "agate") {
             E.materialise(); E.storage(JT_FMT_DBL);
             GateParams p;
@@ -503,7 +560,7 @@ void jt_graph_build(jt_ctx *c, const std::string &spec, const void *d_in, int64_
             const double w = f.num("w", "window", 55), o = f.num("o", "overlap", 75);
             if (!dry) E.cur = jt_adeclick(c, E.cur, w, o, f.num("a", "arorder", 2), f.num("t", "threshold", 2), f.num("b", "burst", 2), save);
             const int ws = (int)(E.cur.rate * w / 1000.), hop = (int)(ws * (1. - o / 100.));
-            E.frames = reframe(E.frames, E.cur.n, std::max(hop, 1));
+            E.ureframe(std::max(hop, 1));
         } else if (f.name == "loudnorm") {
             const double I = f.num("I", "i", -24), TP = f.num("TP", "tp", -2), LRA = f.num("LRA", "lra", 7);
             const double mI = f.num("measured_I", "measured_i", 0), mTP = f.num("measured_TP", "measured_tp", 99);
@@ -546,6 +603,7 @@ void jt_graph_build(jt_ctx *c, const std::string &spec, const void *d_in, int64_
                     if (n192 >= F3000) {
                         // output frames: 100 ms once the 3 s first frame is in, one per consumed 100 ms frame (a short one at
                         // EOF), then the 2.9 s flush frame
+                        E.flush();
                         std::vector<FrameRef> nf; size_t a = 0;
                         auto ready_at = [&](int64_t consumed) {        // the link frame holding sample consumed - 1
                             while (a + 1 < E.frames.size() && E.frames[a + 1].start <= consumed - 1) a++;
@@ -579,20 +637,34 @@ void jt_graph_build(jt_ctx *c, const std::string &spec, const void *d_in, int64_
                     // frame then carries the statistics of the whole signal (checked against the final cadence below)
                     size_t e2 = j + 1;
                     while (e2 < nodes.size() && (nodes[e2].name == "astats" || nodes[e2].name == "aspectralstats" || nodes[e2].name == "ebur128")) e2++;
-                    if (e2 == nodes.size() && E.cur.n > 0) { jt_astats_launch(c, E.cur, E.cur.n, g.astp); astats_prelaunched_upto = E.cur.n; astats_prelaunched_sig = E.cur.d; }
+                    if (e2 == nodes.size() && E.cur.n > 0) {
+                        if (c->defer_astats && c->low_stream) {
+                            // behind everything queued so far on the main stream (the signal exists, every block the arena
+                            // handed out again is free), then on its own: the caller keeps the pass's buffers until it has
+                            // waited for astats' event
+                            cudaEvent_t fork = jt_record_event(c);
+                            JT_CUDA(cudaStreamWaitEvent(c->low_stream, fork, 0));
+                            cudaStream_t main_stream = c->stream;
+                            c->stream = c->low_stream;
+                            try { jt_astats_launch(c, E.cur, E.cur.n, g.astp); } catch (...) { c->stream = main_stream; throw; }
+                            c->stream = main_stream;
+                            g.astats_on_low = true;
+                        } else jt_astats_launch(c, E.cur, E.cur.n, g.astp);
+                        astats_prelaunched_upto = E.cur.n; astats_prelaunched_sig = E.cur.d;
+                    }
                 }
             }
             E.has_astats = true; E.astats_sig = E.cur;
             { const std::string mp = f.str("measure_perchannel", "", "all"); E.astats_overall_only = (mp == "0" || mp == "none"); }
-            for (FrameRef &fr : E.frames) fr.astats_pos = fr.start + fr.nb;
+            E.stamp(JT_LVL_ASTATS);
         } else if (f.name == "aspectralstats") {
             E.materialise(); E.storage(JT_FMT_FLT);
             const int win = (int)f.num("win_size", "", 2048);
             if (f.str("win_func", "", "hann") != "hann" && f.str("win_func", "", "hann") != "hanning") JT_THROW(JT_ERR_UNSUPPORTED, "aspectralstats win_func");
             if (f.num("overlap", "", 0.5) != 0.5) JT_THROW(JT_ERR_UNSUPPORTED, "aspectralstats overlap");
             E.has_spec = true; E.spec_sig = E.cur; E.spec_win = win;    // computed once the sink cadence is known
-            E.frames = reframe(E.frames, E.cur.n, win / 2);
-            for (size_t j = 0; j < E.frames.size(); j++) E.frames[j].hop = (int32_t)j;
+            E.ureframe(win / 2);
+            E.stamp(JT_LVL_HOP);
         } else if (f.name == "ebur128") {
             const std::string peak = f.str("peak", "", "none");
             const bool tp = peak.find("true") != std::string::npos;
@@ -603,14 +675,15 @@ void jt_graph_build(jt_ctx *c, const std::string &spec, const void *d_in, int64_
             g.r128_sig = E.cur; g.r128_dual = dual; g.r128_tp = tp;
             E.has_r128 = true; E.link_fmt = JT_FMT_DBL;
             const int tick = E.cur.rate / 10;
-            E.frames = reframe(E.frames, E.cur.n, tick);
-            for (size_t k = 0; k < E.frames.size(); k++) if (E.frames[k].nb == tick) E.frames[k].tick = (int32_t)k;
+            E.ureframe(tick);
+            E.stamp(JT_LVL_TICK);
         } else {
             JT_THROW(JT_ERR_UNSUPPORTED, "filter '%s' is not part of the jivetalking hot path", f.name.c_str());
         }
     }
     if (!have_mono) JT_THROW(JT_ERR_UNSUPPORTED, "%d-channel graph without a mono downmix", channels);
-    if (capture) { capture->n_nodes = (int)nodes.size(); capture->cur = E.cur; capture->link_fmt = E.link_fmt; capture->frames = E.frames; return; }
+    if (capture) { jt_trace(c, "     capture"); capture->n_nodes = (int)nodes.size(); capture->cur = E.cur; capture->link_fmt = E.link_fmt; capture->frames = E.frames; capture->chain = E.chain; jt_trace(c, "     captured"); return; }
+    E.flush();
     if (E.cur.d && want_pcm) E.materialise();
     if (E.cur.d && want_pcm && mode == JT_GRAPH_NORMAL) g.out_ready = jt_record_event(c);     // the sink audio is complete; analysis kernels follow
     g.out = E.cur; g.out.fmt = E.cur.d ? E.cur.fmt : E.link_fmt;
@@ -619,6 +692,7 @@ void jt_graph_build(jt_ctx *c, const std::string &spec, const void *d_in, int64_
     g.astats_sig = E.astats_sig; g.spec_sig = E.spec_sig; g.spec_win = E.spec_win;
     for (size_t i = 0; i < g.frames.size(); i++) if (g.frames[i].astats_pos >= 0) g.last_astats_frame = (long)i;
     if (!want_meta || mode != JT_GRAPH_NORMAL) return;
+    if (c->trace) jt_trace(c, "   graph tail");
     // ---- analysis kernels whose input cadence depends on the final sink framing -------------
     const size_t nf = g.frames.size();
     if (g.has_spec) {
@@ -629,8 +703,10 @@ void jt_graph_build(jt_ctx *c, const std::string &spec, const void *d_in, int64_
         jt_aspectralstats_launch(c, g.spec_sig, g.spec_win, &wanted, g.specp);
     }
     if (g.has_astats && g.last_astats_frame >= 0 &&
-        !(astats_prelaunched_upto == g.frames[g.last_astats_frame].astats_pos && astats_prelaunched_sig == g.astats_sig.d))
+        !(astats_prelaunched_upto == g.frames[g.last_astats_frame].astats_pos && astats_prelaunched_sig == g.astats_sig.d)) {
+        g.astats_on_low = false;                  // (a pre-launch that missed the final cadence is simply not read)
         jt_astats_launch(c, g.astats_sig, g.frames[g.last_astats_frame].astats_pos, g.astp);
+    }
 }
 
 const R128Result &jt_graph_r128_early(jt_ctx *c, GraphRun &g)
@@ -713,15 +789,17 @@ void jt_graph_finish(jt_ctx *c, GraphRun &g, GraphResult &res)
     }
     if (!g.want_meta) return;
     const R128Result &r128 = jt_graph_r128_early(c, g);
+    jt_trace(c, " finish: meter values");
     std::vector<float> spec_rows; int64_t spec_hops = 0;
     if (g.has_spec) jt_aspectralstats_finish(c, g.specp, spec_rows, spec_hops);
+    jt_trace(c, " finish: spectral rows");
     const std::vector<FrameRef> &frames = g.frames;
     JtHost hmeta(c, "meta_assembly");
     const long last_astats_frame = g.last_astats_frame;
     std::vector<std::thread> pool;
     assemble_records(frames, g.has_r128, r128, g.has_spec, spec_rows, spec_hops, res, pool);
     AstatsResult a; bool have_a = false; JtError aerr{0, ""};
-    if (g.has_astats && last_astats_frame >= 0) {
+    if (g.has_astats && last_astats_frame >= 0 && !g.astats_later) {
         try { jt_astats_finish(c, g.astp, a); have_a = true; }
         catch (const JtError &e) { aerr = e; }
     }

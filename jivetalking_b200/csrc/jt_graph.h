@@ -28,6 +28,13 @@ struct FrameRef {
     int32_t tick = -1;       // ebur128 100 ms tick index
 };
 
+// A pending uniform re-framing of a link (ff_inlink_consume_samples with min = max = F on a stream of n samples) and what the
+// filter that asked for it stamps on the new frames.  Consecutive levels are collapsed in ONE pass over the final frames
+// (frames_collapse): a Pass-2 graph goes source 4096 -> anlmdn 577 -> afftdn 600 -> aspectralstats 1024 -> ebur128 4800, and
+// materialising the 300 000 + 288 000 + 169 000 intermediate frames of an hour of audio was 10 ms of host time per pass.
+enum { JT_LVL_ASTATS = 1, JT_LVL_HOP = 2, JT_LVL_TICK = 4 };
+struct FrameLvl { int64_t F = 1, n = 0; unsigned tag = 0; };
+
 struct GraphResult {
     Sig out;                                  // sink signal (device)
     std::vector<jt_frame_meta> meta;          // one per sink frame
@@ -48,6 +55,8 @@ struct GraphRun {
     Sig astats_sig, spec_sig; int spec_win = 2048;
     R128Pending r128p; SpectralPending specp; AstatsPending astp;
     long last_astats_frame = -1;
+    bool astats_on_low = false;           // the executor put astats on the context's low-priority stream (jt_ctx::defer_astats)
+    bool astats_later = false;            // jt_graph_finish leaves astats' values out: the caller collects them (jt_astats_finish on astp) when it needs them
     R128Result r128; bool r128_done = false;
     // loudnorm
     bool has_ln = false, ln_linear = false, ln_dual = false; double ln_I = 0;
@@ -65,7 +74,7 @@ struct GraphRun {
 enum { JT_GRAPH_NORMAL = 0, JT_GRAPH_DRY = 1, JT_GRAPH_CHUNK = 2 };
 // The executor's state after the first n_nodes filters of a spec: lets the spec-independent head of Pass 2 (downmix, both
 // biquads, anlmdn -- filters.go:58-68) run while the host still derives the adaptive tail of the spec from Pass 1.
-struct GraphResume { int n_nodes = 0; std::string head; Sig cur; int link_fmt = 0; std::vector<FrameRef> frames; AfftdnFwd fwd; };
+struct GraphResume { int n_nodes = 0; std::string head; Sig cur; int link_fmt = 0; std::vector<FrameRef> frames; std::vector<FrameLvl> chain; AfftdnFwd fwd; };
 // predicted_spec: the whole spec the head was cut from; when afftdn follows the head, its parameter-independent forward transforms
 // run here too (jt_afftdn_forward) and ride along in `out`
 void jt_graph_head(jt_ctx *c, const std::string &head_spec, const void *d_in, int64_t n_frames, int rate, int channels,

@@ -19,7 +19,13 @@ struct jt_ctx {
     int num_sms = JT_NSM_DEFAULT;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;   // device->host copy of a finished result while later analysis kernels still run
-    cudaStream_t side_stream = nullptr;   // small input-only work (the 17 band graphs) that must not queue behind Pass 2's head
+    cudaStream_t side_stream = nullptr;   // small input-only work (the 17 band graphs) that must not queue behind Pass 2's head (highest priority)
+    cudaStream_t low_stream = nullptr;    // lowest priority: work whose result is needed late (Pass 1's astats on the adaptive path) fills the
+                                          // SMs the main stream leaves free and the gaps in which the main stream waits for the host
+    // JT_TRACE=1: host timestamps (and an event on the main stream) at the driver's milestones, printed when the call returns
+    struct TracePt { std::string label; double host; cudaEvent_t ev; };
+    std::vector<TracePt> trace_pts; int trace = -1;
+    bool defer_astats = false;            // set by the adaptive driver around Pass 1's enqueue: a pre-launched astats goes to low_stream
     std::string last_error;
     std::atomic<int> cancel{0};
     int64_t launches = 0;
@@ -78,7 +84,11 @@ void jt_copy_small(jt_ctx *c, void *dst, const void *src, size_t bytes);
 // an event (timing disabled) recorded on the context's stream now; owned by the context, recycled per API call
 cudaEvent_t jt_record_event(jt_ctx *c);
 void jt_release_since(jt_ctx *c, size_t mark, const void *keep);   // free allocations made after `mark`, except the one holding `keep`
+void jt_release_range(jt_ctx *c, size_t from, size_t to);          // free allocations [from, to) of the call's list, keep the rest
 void jt_check_cancel(jt_ctx *c);
+void jt_trace(jt_ctx *c, const char *label);     // no-op unless JT_TRACE is set
+void jt_trace_dump(jt_ctx *c);
+extern "C" void jt_vad_assign_astats(const jt_measurements *m, jt_voice_activity *va);   // jt_adapt.cu
 void jt_flush_timing(jt_ctx *c);
 
 // RAII launch bookkeeping: counts one launch of `name`, optionally brackets it with events.

@@ -180,6 +180,37 @@ void jt_release_since(jt_ctx *c, size_t mark, const void *keep)
     }
 }
 
+void jt_release_range(jt_ctx *c, size_t from, size_t to)
+{
+    to = std::min(to, c->allocs.size());
+    if (from >= to) return;
+    for (size_t i = from; i < to; i++) arena_release(c, c->allocs[i]);
+    c->allocs.erase(c->allocs.begin() + (long)from, c->allocs.begin() + (long)to);
+}
+
+void jt_trace(jt_ctx *c, const char *label)
+{
+    if (c->trace < 0) c->trace = getenv("JT_TRACE") ? 1 : 0;
+    if (!c->trace) return;
+    struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
+    jt_ctx::TracePt p{label, ts.tv_sec + 1e-9 * ts.tv_nsec, nullptr};
+    cudaEventCreate(&p.ev); cudaEventRecord(p.ev, c->stream);
+    c->trace_pts.push_back(p);
+}
+void jt_trace_dump(jt_ctx *c)
+{
+    if (c->trace_pts.empty()) return;
+    cudaDeviceSynchronize();
+    const jt_ctx::TracePt &p0 = c->trace_pts[0];
+    fprintf(stderr, "[jt_trace] %-28s %9s %9s   (ms since the first point: host reached it / main stream reached it)\n", "milestone", "host", "gpu");
+    for (const jt_ctx::TracePt &p : c->trace_pts) {
+        float g = 0; cudaEventElapsedTime(&g, p0.ev, p.ev);
+        fprintf(stderr, "[jt_trace] %-28s %9.3f %9.3f\n", p.label.c_str(), (p.host - p0.host) * 1e3, g);
+    }
+    for (jt_ctx::TracePt &p : c->trace_pts) cudaEventDestroy(p.ev);
+    c->trace_pts.clear();
+}
+
 void jt_check_cancel(jt_ctx *c)
 {
     if (c->cancel.load(std::memory_order_relaxed)) JT_THROW(JT_ERR_CANCELLED, "cancelled");
