@@ -145,6 +145,7 @@ template <class F> static int guarded(jt_ctx *c, F body)
     catch (const JtError &e) { rc = e.code; c->last_error = e.msg; }
     catch (const std::bad_alloc &) { rc = JT_ERR_NOMEM; c->last_error = "host allocation failed"; }
     if (c->low_stream) cudaStreamSynchronize(c->low_stream);      // (idle unless the call failed half-way)
+    if (c->side_stream) cudaStreamSynchronize(c->side_stream);
     jt_release_all(c);
     cudaError_t e = cudaStreamSynchronize(c->stream);
     if (rc == JT_OK && e != cudaSuccess) { rc = JT_ERR_CUDA; c->last_error = cudaGetErrorString(e); }
@@ -1192,7 +1193,8 @@ static double go_seconds(int64_t ns) { return (double)(ns / 1000000000LL) + (dou
 // Pass 4 without the GPU waiting for the host in between
 struct RegionPending { GraphRun g; bool queued = false; };
 static void region_measure_enqueue(jt_ctx *c, const void *d_pcm, int64_t n_frames, int rate, int channels, int fmt,
-                                   int64_t start_ns, int64_t dur_ns, RegionPending &p, int64_t sample_a = -1, int64_t sample_b = -1)
+                                   int64_t start_ns, int64_t dur_ns, RegionPending &p, int64_t sample_a = -1, int64_t sample_b = -1,
+                                   bool keep_buffers = false /* graphs on the side stream: the arena must not hand their blocks to the main stream */)
 {
     char spec[512];
     if (sample_a >= 0) {
@@ -1206,7 +1208,7 @@ static void region_measure_enqueue(jt_ctx *c, const void *d_pcm, int64_t n_frame
     }
     const size_t mark = c->allocs.size();
     jt_graph_enqueue(c, spec, d_pcm, n_frames, rate, channels, fmt, 4096, false, true, p.g);
-    jt_release_since(c, mark, nullptr);
+    if (!keep_buffers) jt_release_since(c, mark, nullptr);
     p.queued = true;
 }
 static void region_measure_finish(jt_ctx *c, RegionPending &p, jt_region_sample *out, int64_t *frames_out)
@@ -1263,16 +1265,31 @@ extern "C" int jt_measure_output_region_dev(jt_ctx *c, const void *d_pcm, int64_
 // MeasureOutputRegions (analyser_output.go:261-297): the elected room-tone and speech regions of Pass 1 re-measured on a
 // pass's s16 output; a failing region is a warning, not an error (its sample stays absent)
 struct OutputRegionsPending { RegionPending room, speech; };
-static void measure_output_regions_enqueue(jt_ctx *c, const void *d_pcm, int64_t n, const jt_voice_activity &va, OutputRegionsPending &p)
+// which: 1 = room tone, 2 = speech, 3 = both.  on_side: the graphs go to the context's side stream, ordered behind everything
+// queued on the main stream so far (their buffers come from the arena, which hands blocks out again relying on stream order).
+// A region graph is a dozen tiny launches over <= 60 s of audio: on the main stream the four of a call were 3.4 ms of a GPU
+// that sat mostly empty; on the side stream they run under the next pass's kernels.
+static void measure_output_regions_enqueue(jt_ctx *c, const void *d_pcm, int64_t n, const jt_voice_activity &va, OutputRegionsPending &p,
+                                           int which = 3, bool on_side = false)
 {
-    if (va.has_noise_profile) {
-        try { region_measure_enqueue(c, d_pcm, n, 44100, 1, JT_FMT_S16, va.noise_profile.start_ns, va.noise_profile.duration_ns, p.room); }
-        catch (const JtError &e) { p.room.queued = false; if (e.code == JT_ERR_CUDA || e.code == JT_ERR_CANCELLED) throw; }
+    cudaStream_t main_stream = c->stream;
+    if (on_side && c->side_stream) {
+        cudaEvent_t behind = jt_record_event(c);
+        JT_CUDA(cudaStreamWaitEvent(c->side_stream, behind, 0));
+        c->stream = c->side_stream;
     }
-    if (va.has_speech_profile) {
-        try { region_measure_enqueue(c, d_pcm, n, 44100, 1, JT_FMT_S16, va.speech_profile.region.start_ns, va.speech_profile.region.duration_ns, p.speech); }
-        catch (const JtError &e) { p.speech.queued = false; if (e.code == JT_ERR_CUDA || e.code == JT_ERR_CANCELLED) throw; }
-    }
+    const bool keep = c->stream != main_stream;
+    try {
+        if ((which & 1) && va.has_noise_profile) {
+            try { region_measure_enqueue(c, d_pcm, n, 44100, 1, JT_FMT_S16, va.noise_profile.start_ns, va.noise_profile.duration_ns, p.room, -1, -1, keep); }
+            catch (const JtError &e) { p.room.queued = false; if (e.code == JT_ERR_CUDA || e.code == JT_ERR_CANCELLED) throw; }
+        }
+        if ((which & 2) && va.has_speech_profile) {
+            try { region_measure_enqueue(c, d_pcm, n, 44100, 1, JT_FMT_S16, va.speech_profile.region.start_ns, va.speech_profile.region.duration_ns, p.speech, -1, -1, keep); }
+            catch (const JtError &e) { p.speech.queued = false; if (e.code == JT_ERR_CUDA || e.code == JT_ERR_CANCELLED) throw; }
+        }
+    } catch (...) { c->stream = main_stream; throw; }
+    c->stream = main_stream;
 }
 static void measure_output_regions_finish(jt_ctx *c, OutputRegionsPending &p, jt_output_regions *o)
 {
@@ -1317,6 +1334,12 @@ static void process_device(jt_ctx *c, const void *d_in, int64_t n_frames, int ra
     jt_release_since(c, mark, g2.out.d);          // keep only the Pass-2 output ("the FLAC on disk")
     jt_trace(c, "pass2 enqueued");
     jt_check_cancel(c);
+    // processor.go:150-160: the elected regions re-measured on Pass 2's output.  On the side stream, behind Pass 2's last kernel:
+    // they run under Pass 3 / Pass 4.  (Enqueued here, before Pass 3 takes and returns its buffers, so that nothing they hold was
+    // handed back while a main-stream kernel could still be using it.)
+    OutputRegionsPending reg2, reg4;
+    const bool regions_on_side = an && c->side_stream && !getenv("JT_REGIONS_MAIN");
+    if (an && regions_on_side) measure_output_regions_enqueue(c, g2.out.d, g2.out.n, an->voice_activity, reg2, 3, true);
     const size_t mark1 = c->allocs.size();
     AnalysePending p1;
     if (!pass1_done) {
@@ -1368,10 +1391,13 @@ static void process_device(jt_ctx *c, const void *d_in, int64_t n_frames, int ra
     if (pcm_out && g4.out.n > cap) JT_THROW(JT_ERR_BUFFER, "pcm_out holds %lld samples, chain produced %lld", (long long)cap, (long long)g4.out.n);
     // processor.go:150-160 and normalise.go's Pass-4 re-measure of the same regions: queued behind Pass 4 now, so the GPU goes
     // straight on with them while the host is still assembling Pass 2's and Pass 4's metadata
-    OutputRegionsPending reg2, reg4;
-    if (an) {
+    if (an && !regions_on_side) {
         measure_output_regions_enqueue(c, g2.out.d, g2.out.n, an->voice_activity, reg2);
         measure_output_regions_enqueue(c, g4.out.d, g4.out.n, an->voice_activity, reg4);
+    } else if (an) {
+        // normalise.go's re-measure of the same regions on Pass 4's output: one on each stream
+        measure_output_regions_enqueue(c, g4.out.d, g4.out.n, an->voice_activity, reg4, 2, true);
+        measure_output_regions_enqueue(c, g4.out.d, g4.out.n, an->voice_activity, reg4, 1, false);
     }
     jt_trace(c, "regions enqueued");
     // Pass 2: host part (sink-frame records, accumulators), while the GPU runs Pass 4
@@ -1395,6 +1421,7 @@ static void process_device(jt_ctx *c, const void *d_in, int64_t n_frames, int ra
     }
     jt_trace(c, "regions finished");
     JT_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->side_stream) JT_CUDA(cudaStreamSynchronize(c->side_stream));
     JT_CUDA(cudaStreamSynchronize(c->copy_stream));
     jt_trace(c, "end");
     if (res) *res = R;

@@ -369,7 +369,9 @@ static int afftdn_fft_grid(jt_ctx *c, const AfConst &K, int64_t n_hops, size_t &
     smem_fft = sizeof(float2) * 3 * (size_t)K.FL;
     const int64_t n_pairs = (n_hops + 1) / 2;
     const int fft_per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / (smem_fft + 1024)));
-    return (int)std::min<int64_t>(n_pairs, (int64_t)c->num_sms * fft_per_sm * 4);
+    // CTAs that live for ~8 transform pairs, not for a sixteenth of the stream: the block scheduler can only hand SM slots to a
+    // higher-priority stream (the band graphs the host is waiting for while this kernel runs in Pass 2's head) when CTAs retire
+    return (int)std::min<int64_t>(n_pairs, (int64_t)c->num_sms * fft_per_sm * 32);
 }
 
 void jt_afftdn_forward(jt_ctx *c, const Sig &in, const AfftdnParams &P, AfftdnFwd &out)
