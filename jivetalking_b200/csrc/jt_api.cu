@@ -1338,7 +1338,7 @@ static void process_device(jt_ctx *c, const void *d_in, int64_t n_frames, int ra
     // they run under Pass 3 / Pass 4.  (Enqueued here, before Pass 3 takes and returns its buffers, so that nothing they hold was
     // handed back while a main-stream kernel could still be using it.)
     OutputRegionsPending reg2, reg4;
-    const bool regions_on_side = an && c->side_stream && !getenv("JT_REGIONS_MAIN");
+    const bool regions_on_side = an && c->side_stream && !c->timing && !getenv("JT_REGIONS_MAIN");
     if (an && regions_on_side) measure_output_regions_enqueue(c, g2.out.d, g2.out.n, an->voice_activity, reg2, 3, true);
     const size_t mark1 = c->allocs.size();
     AnalysePending p1;
@@ -1493,7 +1493,7 @@ static void analyse_adaptive_device(jt_ctx *c, const void *d_in, int64_t n_frame
         // The band graphs read the input only.  When Pass 2's head is already queued on the main stream they go to the side
         // stream (ordered behind the input's upload by `input_ready`), so their result does not wait for anlmdn.
         std::unique_ptr<StreamSwap> swap;
-        if (input_ready && c->side_stream) {
+        if (input_ready && c->side_stream && !c->timing) {
             JT_CUDA(cudaStreamWaitEvent(c->side_stream, input_ready, 0));
             swap.reset(new StreamSwap(c, c->side_stream));
         }
@@ -1584,7 +1584,9 @@ static void process_adaptive_device(jt_ctx *c, const void *d_in, int64_t n_frame
     // detector run on the meter's and aspectralstats' rows): it goes to the low-priority stream, where it fills the SMs the
     // meter / spectral / head kernels leave free and the gap in which the main stream waits for the detector.  Its buffers --
     // and everything else Pass 1 allocated -- are therefore released only after the host has seen Pass 1's last event.
-    const bool defer = c->low_stream != nullptr && !getenv("JT_NO_DEFER_ASTATS");
+    // (with per-kernel timing on, everything stays on the main stream: an event pair around a kernel that shares the GPU with
+    // another stream's kernels measures the sharing, not the kernel)
+    const bool defer = c->low_stream != nullptr && !c->timing && !getenv("JT_NO_DEFER_ASTATS");
     c->defer_astats = defer;
     try { analyse_enqueue(c, d_in, n_frames, rate, channels, fmt, 4096, p1); } catch (...) { c->defer_astats = false; throw; }
     c->defer_astats = false;

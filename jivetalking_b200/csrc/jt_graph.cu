@@ -401,6 +401,7 @@ void jt_graph_build(jt_ctx *c, const std::string &spec, const void *d_in, int64_
 
     Exec E; E.c = c; E.dry = dry;
     bool have_mono = false, r128_prelaunched = false;
+    cudaEvent_t tail_fork = nullptr;      // see the ebur128 node
     int64_t astats_prelaunched_upto = -1; const void *astats_prelaunched_sig = nullptr;
     const void *raw = d_in;
     if (channels == 1) { E.cur = dry ? dry_mono(n_frames, fmt, rate) : jt_downmix(c, raw, n_frames, 1, fmt, rate); have_mono = true; }
@@ -670,7 +671,18 @@ void jt_graph_build(jt_ctx *c, const std::string &spec, const void *d_in, int64_
             const bool tp = peak.find("true") != std::string::npos;
             const bool dual = f.flag("dualmono", "", false);
             // input link is dbl; s16/flt storage widens exactly on load
-            if (want_meta && mode == JT_GRAPH_NORMAL && !r128_prelaunched) jt_ebur128_launch(c, E.cur, dual, tp, g.r128p);
+            if (want_meta && mode == JT_GRAPH_NORMAL && !r128_prelaunched) {
+                // The meter's kernels (the true-peak oversampler above all: 2 - 7 ms at one CTA of 640 threads per SM) leave most of
+                // an SM's warp slots empty, and the graph tail below queues aspectralstats and astats of the very signals that exist
+                // by now.  Mark this point of the main stream: the tail forks from here onto the low-priority stream and runs
+                // under the meter and the output stage instead of behind them.  (Only when no astats / aspectralstats node follows,
+                // i.e. their input -- and its format conversion -- is already queued; small region graphs are not worth two events.)
+                bool later_analysis = false;
+                for (size_t j = ni + 1; j < nodes.size(); j++) if (nodes[j].name == "astats" || nodes[j].name == "aspectralstats") later_analysis = true;
+                static const bool no_fork = getenv("JT_NO_TAIL_FORK") != nullptr;
+                if (!no_fork && !c->timing && !later_analysis && c->low_stream && (E.has_astats || E.has_spec) && E.cur.n >= (1 << 22)) tail_fork = jt_record_event(c);
+                jt_ebur128_launch(c, E.cur, dual, tp, g.r128p);
+            }
             r128_prelaunched = false;
             g.r128_sig = E.cur; g.r128_dual = dual; g.r128_tp = tp;
             E.has_r128 = true; E.link_fmt = JT_FMT_DBL;
@@ -695,6 +707,12 @@ void jt_graph_build(jt_ctx *c, const std::string &spec, const void *d_in, int64_
     if (c->trace) jt_trace(c, "   graph tail");
     // ---- analysis kernels whose input cadence depends on the final sink framing -------------
     const size_t nf = g.frames.size();
+    cudaStream_t main_stream = c->stream;
+    if (tail_fork) {
+        JT_CUDA(cudaStreamWaitEvent(c->low_stream, tail_fork, 0));
+        c->stream = c->low_stream;
+    }
+    try {
     if (g.has_spec) {
         // aspectralstats emits one row per 1024-sample hop, but a sink frame only ever shows the row of the
         // hop holding its first sample: compute just those (plus predecessors for the flux term)
@@ -706,6 +724,13 @@ void jt_graph_build(jt_ctx *c, const std::string &spec, const void *d_in, int64_
         !(astats_prelaunched_upto == g.frames[g.last_astats_frame].astats_pos && astats_prelaunched_sig == g.astats_sig.d)) {
         g.astats_on_low = false;                  // (a pre-launch that missed the final cadence is simply not read)
         jt_astats_launch(c, g.astats_sig, g.frames[g.last_astats_frame].astats_pos, g.astp);
+    }
+    } catch (...) { c->stream = main_stream; throw; }
+    if (tail_fork) {
+        // join: whatever the caller queues next on the main stream (or hands back to the arena) comes after the forked kernels
+        cudaEvent_t done = jt_record_event(c);
+        c->stream = main_stream;
+        JT_CUDA(cudaStreamWaitEvent(main_stream, done, 0));
     }
 }
 
