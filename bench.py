@@ -50,6 +50,7 @@ KERNEL_BYTES = {
 KERNEL_BOUND = {
     "adeclick:interp": "latency (banded LDL^T k-loop, shared-memory round trips)",
     "anlmdn": "FP32 issue / shared-memory bandwidth",
+    "anlmdn:screen": "FP32 issue (a subtract and an FMA per sample and lag; the exact kernel walks only the listed hops)",
     "envelope_follower": "f64 dependent-issue latency (one lane per stream segment)",
     "afftdn:fwd": "barriers of the shared-memory FFT + f64 tracking statistics",
 }

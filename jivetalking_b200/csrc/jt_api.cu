@@ -1385,7 +1385,9 @@ static void process_device(jt_ctx *c, const void *d_in, int64_t n_frames, int ra
     if (rc) JT_THROW(rc, "pass-4 spec");
     R.effective_target_i = eff; R.linear_possible = eff == tI;
     GraphRun g4;
-    jt_graph_enqueue(c, spec4, g2.out.d, g2.out.n, 44100, 1, JT_FMT_S16, 4096, true, true, g4);
+    c->meter_after_output = pcm_out != nullptr && !out_on_device && !getenv("JT_METER_FIRST");     // nothing waits for Pass 4's meter but the end of the call
+    try { jt_graph_enqueue(c, spec4, g2.out.d, g2.out.n, 44100, 1, JT_FMT_S16, 4096, true, true, g4); } catch (...) { c->meter_after_output = false; throw; }
+    c->meter_after_output = false;
     jt_trace(c, "pass4 enqueued");
     R.n_out = g4.out.n;
     if (pcm_out && g4.out.n > cap) JT_THROW(JT_ERR_BUFFER, "pcm_out holds %lld samples, chain produced %lld", (long long)cap, (long long)g4.out.n);

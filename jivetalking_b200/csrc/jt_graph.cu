@@ -402,6 +402,7 @@ void jt_graph_build(jt_ctx *c, const std::string &spec, const void *d_in, int64_
     Exec E; E.c = c; E.dry = dry;
     bool have_mono = false, r128_prelaunched = false;
     cudaEvent_t tail_fork = nullptr;      // see the ebur128 node
+    bool meter_deferred = false, meter_dual = false, meter_tp = false; Sig meter_sig;
     int64_t astats_prelaunched_upto = -1; const void *astats_prelaunched_sig = nullptr;
     const void *raw = d_in;
     if (channels == 1) { E.cur = dry ? dry_mono(n_frames, fmt, rate) : jt_downmix(c, raw, n_frames, 1, fmt, rate); have_mono = true; }
@@ -681,7 +682,13 @@ void jt_graph_build(jt_ctx *c, const std::string &spec, const void *d_in, int64_
                 for (size_t j = ni + 1; j < nodes.size(); j++) if (nodes[j].name == "astats" || nodes[j].name == "aspectralstats") later_analysis = true;
                 static const bool no_fork = getenv("JT_NO_TAIL_FORK") != nullptr;
                 if (!no_fork && !c->timing && !later_analysis && c->low_stream && (E.has_astats || E.has_spec) && E.cur.n >= (1 << 22)) tail_fork = jt_record_event(c);
-                jt_ebur128_launch(c, E.cur, dual, tp, g.r128p);
+                // the meter does not change the audio: when only the output stage follows and the caller asked for it, its kernels
+                // go behind that stage (graph tail), so `out_ready` -- and with it the download of the result -- comes first
+                bool only_output_follows = want_pcm && c->meter_after_output;
+                for (size_t j = ni + 1; j < nodes.size(); j++)
+                    if (!(nodes[j].name == "aformat" || nodes[j].name == "aresample" || nodes[j].name == "asetnsamples")) only_output_follows = false;
+                if (only_output_follows) { meter_deferred = true; meter_sig = E.cur; meter_dual = dual; meter_tp = tp; }
+                else jt_ebur128_launch(c, E.cur, dual, tp, g.r128p);
             }
             r128_prelaunched = false;
             g.r128_sig = E.cur; g.r128_dual = dual; g.r128_tp = tp;
@@ -708,6 +715,7 @@ void jt_graph_build(jt_ctx *c, const std::string &spec, const void *d_in, int64_
     // ---- analysis kernels whose input cadence depends on the final sink framing -------------
     const size_t nf = g.frames.size();
     cudaStream_t main_stream = c->stream;
+    if (meter_deferred) jt_ebur128_launch(c, meter_sig, meter_dual, meter_tp, g.r128p);
     if (tail_fork) {
         JT_CUDA(cudaStreamWaitEvent(c->low_stream, tail_fork, 0));
         c->stream = c->low_stream;

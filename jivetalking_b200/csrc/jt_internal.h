@@ -25,6 +25,8 @@ struct jt_ctx {
     // JT_TRACE=1: host timestamps (and an event on the main stream) at the driver's milestones, printed when the call returns
     struct TracePt { std::string label; double host; cudaEvent_t ev; };
     std::vector<TracePt> trace_pts; int trace = -1;
+    bool meter_after_output = false;      // set around Pass 4's enqueue: ebur128's kernels are queued behind the output stage, so the
+                                          // result's download starts ~7 ms earlier and hides under the meter and the analysis tail
     bool defer_astats = false;            // set by the adaptive driver around Pass 1's enqueue: a pre-launched astats goes to low_stream
     std::string last_error;
     std::atomic<int> cancel{0};

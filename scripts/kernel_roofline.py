@@ -20,7 +20,8 @@ M = N * 44100 // 48000              # samples at the output rate
 
 # kernel -> (bench.py timing group, algorithmic bytes of the whole-stream launch, what those bytes are)
 ALG = {
-    "k_anlmdn": ("anlmdn", 8 * N, "f32 in + f32 out"),
+    "k_anlmdn": ("anlmdn", 8 * N, "f32 in + f32 out (since the screen: only the listed hops)"),
+    "k_nlm_screen<3>": ("anlmdn:screen", 8 * N, "f32 in + f32 out (pass-through of every hop the screen clears)"),
     "k_dc_interp": ("adeclick:interp", 16 * M, "f64 in + f64 out at 44.1 kHz"),
     "k_dc_detect": ("adeclick:detect", 8 * M, "f64 in (flags out are tiny)"),
     "k_dc_autocorr": ("adeclick:autocorr", 8 * M, "f64 in (25 lags per window out)"),
