@@ -8,6 +8,7 @@
 #include <vector>
 #include <map>
 #include <cmath>
+#include <cstring>
 #include "../../include/jtdsp.h"
 
 #define JT_NSM_DEFAULT 148
@@ -83,6 +84,18 @@ template <class T> static inline T *jt_pinned(jt_ctx *c, size_t n) { return (T *
 // stream queued behind a file-sized upload (jt_prefetch_input) or the download of the result for up to 12 ms.  Either pointer may
 // be the pinned one (cudaHostAlloc memory is device-accessible under unified addressing).
 void jt_copy_small(jt_ctx *c, void *dst, const void *src, size_t bytes);
+// Device copy of a small PER-CALL parameter table (values that differ from file to file -- jt_dev_table would keep one device copy per
+// distinct content for the life of the context and waits for its upload): an arena block filled from pinned staging by the copy
+// kernel, in stream order, released with the pass's other buffers
+template <class T> static inline const T *jt_upload_params(jt_ctx *c, const std::vector<T> &v)
+{
+    T *d = jt_dalloc<T>(c, v.size());
+    if (v.empty()) return d;
+    T *h = jt_pinned<T>(c, v.size());
+    memcpy(h, v.data(), v.size() * sizeof(T));
+    jt_copy_small(c, d, h, v.size() * sizeof(T));
+    return d;
+}
 // an event (timing disabled) recorded on the context's stream now; owned by the context, recycled per API call
 cudaEvent_t jt_record_event(jt_ctx *c);
 void jt_release_since(jt_ctx *c, size_t mark, const void *keep);   // free allocations made after `mark`, except the one holding `keep`

@@ -458,7 +458,7 @@ Sig jt_afftdn(jt_ctx *c, const Sig &in, const AfftdnParams &P, const AfftdnCarry
     const int64_t n_hops = (in.n + K.A - 1) / K.A;
     const double *d_window = jt_dev_table(c, "afftdn_window", window);
     const float2 *d_tw = jt_dev_table(c, "afftdn_tw", tw);
-    const double *d_rel = jt_dev_table(c, "afftdn_relvar", rel_var);
+    const double *d_rel = jt_upload_params(c, rel_var);          // follows the file's band-noise profile: a per-call table
     const int *d_blo = jt_dev_table(c, "afftdn_bandlo", band_lo);
     const int *d_b2b = jt_dev_table(c, "afftdn_bin2band", bin2band);
     const double *d_alpha = jt_dev_table(c, "afftdn_alpha", alpha), *d_beta = jt_dev_table(c, "afftdn_beta", beta);
