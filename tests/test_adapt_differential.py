@@ -134,3 +134,31 @@ def test_detector_and_spec_agree_with_the_oracle(seed):
 @pytest.mark.parametrize("v", [12.0, -58.0, -52.37421875, -54.60033333333333, -79.99999999999999, -20.0, -61.3, 1e6, 123456.7, 1e-5, 0.000123])
 def test_go_g_agrees(v):
     assert A.go_format_g(v) == AO.go_g(v)
+
+
+@pytest.mark.parametrize("seed", range(0, 120, 7))
+def test_detector_before_astats_then_assign_equals_one_call(seed):
+    """The adaptive driver runs the detector while Pass 1's astats is still on the GPU (its whole-file values are the one product
+    of Pass 1 the host needs last) and fills the two values that read it afterwards (jt_vad_assign_astats): byte for byte the
+    VoiceActivity of a single jt_detect_voice_activity call on complete measurements (analyser.go:374-395, 515-531)."""
+    import ctypes as C
+    civ = to_c(random_stream(seed))
+    rnd = random.Random(2000 + seed)
+    full = dict(input_i=rnd.uniform(-45, -12), input_lra=rnd.uniform(2, 22), Dynamic_range=50.0, RMS_level=rnd.choice([0.0, rnd.uniform(-50, -15)]),
+                Peak_level=rnd.uniform(-20, 0), Noise_floor=rnd.choice([-70.0, math.nan, -55.5]))
+    m_full = A.new_measurements(**full)
+    va_full, runs_full, cands_full = A.detect_voice_activity(m_full, civ)
+    m_part = A.new_measurements(input_i=full["input_i"], input_lra=full["input_lra"])        # astats not collected yet
+    va, runs, cands = A.detect_voice_activity(m_part, civ)
+    for k in A.AS_NAMES:
+        if k in full:
+            m_part.astats[A.AS_NAMES.index(k)] = full[k]
+    L = A._L()
+    L.jt_vad_assign_astats.restype = None
+    L.jt_vad_assign_astats.argtypes = [C.c_void_p, C.c_void_p]
+    L.jt_vad_assign_astats(C.addressof(m_part), C.addressof(va))
+
+    def raw(s):                   # NaNs compare equal as bytes
+        return bytes(C.string_at(C.addressof(s), C.sizeof(s)))
+    assert raw(va) == raw(va_full)
+    assert [(r.start_ns, r.end_ns) for r in runs] == [(r.start_ns, r.end_ns) for r in runs_full] and len(cands) == len(cands_full)
