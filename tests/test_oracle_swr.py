@@ -116,3 +116,23 @@ def test_downsample_from_192k_matches_real_swr(rates):
     ref = G[f"dbl_noise_{rates[0]}_{rates[1]}_1"]
     y = O.swr_resample(G["in_noise"], rates[0], rates[1], flush=True)
     assert len(y) == len(ref) and np.max(np.abs(y - ref)) < 2e-15
+
+
+@pytest.mark.parametrize("rate", [22050, 48000, 44100])
+def test_ebur128_true_peak_is_the_real_resamplers_peak(rate):
+    """ebur128 peak=true feeds swr (-> 192 kHz, dbl) 100 ms at a time and keeps the running maximum of what comes out: the oracle's
+    per-tick cumulative true peak against the REAL libswresample driven the same way -- including a 22.05 kHz source, whose ratio
+    to 192 kHz takes swr's linear-interpolated path."""
+    import ref_swr
+    if not ref_swr.available():
+        pytest.skip("libswresample not in this image")
+    rng = np.random.default_rng(rate)
+    tick = rate // 10
+    x = (rng.standard_normal(tick * 23 + 517) * 0.2) * np.hanning(tick * 23 + 517)
+    r = O.ebur128(x, rate, true_peak=True)
+    counts = []
+    y = ref_swr.convert(x[:r["n_ticks"] * tick], "dbl", rate, "dbl", 192000, frame=tick, flush=False, per_call_counts=counts)
+    assert len(counts) == r["n_ticks"]
+    ends = np.cumsum(counts)
+    want = np.array([np.max(np.abs(y[:e])) if e else 0.0 for e in ends])
+    assert np.max(np.abs(r["true_peak_cum"] - want)) < 1e-14
