@@ -275,6 +275,14 @@ def main():
     d_out = torch.empty(out_cap, dtype=torch.int16, device="cuda")
     h_out = torch.empty(out_cap, dtype=torch.int16).pin_memory()
     ctx = gpudsp.Context(local)
+    if world > 1 and not os.environ.get("JT_HOST_THREADS"):
+        # the ranks of one node share its cores, and the barrier starts their steps together: each call's per-frame metadata
+        # workers get a share of the cores instead of eight threads per rank piling onto all of them
+        try:
+            cores = len(os.sched_getaffinity(0))
+        except AttributeError:
+            cores = os.cpu_count() or 1
+        gpudsp.lib().jt_set_host_threads(max(2, min(8, cores // world)))
     lib_stream = torch.cuda.ExternalStream(ctx.cuda_stream(), device=torch.device("cuda", local))   # the stream the kernels run on
 
     def barrier():
