@@ -366,7 +366,6 @@ void jt_graph_head(jt_ctx *c, const std::string &head_spec, const void *d_in, in
     out = GraphResume();
     out.head = head_spec;
     jt_graph_build(c, head_spec, d_in, n_frames, rate, channels, fmt, frame_size, true, false, JT_GRAPH_NORMAL, nullptr, g, nullptr, &out);
-    jt_trace(c, "     head built");
     if (predicted_spec && out.cur.d && out.cur.fmt == JT_FMT_FLT && out.link_fmt == JT_FMT_FLT) {
         const std::vector<FilterNode> nodes = jt_parse_spec(*predicted_spec);
         if ((size_t)out.n_nodes < nodes.size() && nodes[(size_t)out.n_nodes].name == "afftdn") {
@@ -701,7 +700,7 @@ void jt_graph_build(jt_ctx *c, const std::string &spec, const void *d_in, int64_
         }
     }
     if (!have_mono) JT_THROW(JT_ERR_UNSUPPORTED, "%d-channel graph without a mono downmix", channels);
-    if (capture) { jt_trace(c, "     capture"); capture->n_nodes = (int)nodes.size(); capture->cur = E.cur; capture->link_fmt = E.link_fmt; capture->frames = E.frames; capture->chain = E.chain; jt_trace(c, "     captured"); return; }
+    if (capture) { capture->n_nodes = (int)nodes.size(); capture->cur = E.cur; capture->link_fmt = E.link_fmt; capture->frames = E.frames; capture->chain = E.chain; return; }
     E.flush();
     if (E.cur.d && want_pcm) E.materialise();
     if (E.cur.d && want_pcm && mode == JT_GRAPH_NORMAL) g.out_ready = jt_record_event(c);     // the sink audio is complete; analysis kernels follow

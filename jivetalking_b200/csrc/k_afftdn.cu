@@ -378,22 +378,17 @@ void jt_afftdn_forward(jt_ctx *c, const Sig &in, const AfftdnParams &P, AfftdnFw
 {
     out = AfftdnFwd();
     if (in.fmt != JT_FMT_FLT || in.n <= 0) return;
-    jt_trace(c, "     afftdn fwd: entry");
     AfConst K; std::vector<double> window; std::vector<float2> tw;
     afftdn_geometry(in.rate, P, K, window, tw);
-    jt_trace(c, "     afftdn fwd: geometry");
     const int64_t n_hops = (in.n + K.A - 1) / K.A;
     const double *d_window = jt_dev_table(c, "afftdn_window", window);
     const float2 *d_tw = jt_dev_table(c, "afftdn_tw", tw);
-    jt_trace(c, "     afftdn fwd: tables");
     float2 *d_spec = jt_dalloc<float2>(c, (size_t)n_hops * K.bins);
     double *d_cand = jt_dalloc<double>(c, (size_t)n_hops * 2);
     size_t smem_fft; const int grid_fft = afftdn_fft_grid(c, K, n_hops, smem_fft);
     jt_smem_optin((const void *)k_afftdn_fwd, smem_fft);
-    jt_trace(c, "     afftdn fwd: allocated");
     { JtLaunch L(c, "afftdn:fwd");
       k_afftdn_fwd<<<grid_fft, AF_THREADS, smem_fft, c->stream>>>((const float *)in.d, in.n, n_hops, K, d_window, d_tw, d_spec, P.tn, d_cand); }
-    jt_trace(c, "     afftdn fwd: launched");
     out.d_spec = d_spec; out.d_cand = d_cand; out.src = in.d; out.n = in.n; out.n_hops = n_hops; out.rate = in.rate; out.tn = P.tn; out.fo = P.fo;
 }
 

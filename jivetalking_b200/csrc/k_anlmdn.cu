@@ -276,7 +276,6 @@ Sig jt_anlmdn(jt_ctx *c, const Sig &in, double strength, double patch_s, double 
     const int H = 2 * K + 1, N = H + 2 * (K + S);
     const int threads = std::max(32, (((S + NLM_V - 1) / NLM_V + 31) / 32) * 32);
     if (threads > 128) JT_THROW(JT_ERR_UNSUPPORTED, "anlmdn research radius %d samples (max 384)", S);
-    jt_trace(c, "     anlmdn: entry");
     Sig o = in; o.d = jt_dalloc<float>(c, in.n);
     if (in.n <= 0) return o;
     const float m = (float)smooth_m, a = (float)strength;
@@ -327,9 +326,7 @@ Sig jt_anlmdn(jt_ctx *c, const Sig &in, double strength, double patch_s, double 
         default: nlm_screen_launch<12>(c, (const float *)in.d, (float *)o.d, in.n, Q, n_hops, smem_screen, d_list, d_count); break;
         }
     }
-    jt_trace(c, "     anlmdn: screen queued");
     JtLaunch L(c, "anlmdn");
     k_anlmdn<<<grid, threads, smem, c->stream>>>((const float *)in.d, (float *)o.d, in.n, K, S, P, n_hops, d_list, d_count);
-    jt_trace(c, "     anlmdn: exact queued");
     return o;
 }
